@@ -1,0 +1,203 @@
+"""TEST INFRASTRUCTURE — ctypes bindings of the CPU oracle (oracle/oracle_api.h). Not the product.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+Two libraries export the same API under different prefixes:
+  ref  -> oracle/_ref/liborb_ref.so      (the reference's own TUs; built where /root/reference exists)
+  port -> oracle/_build/liborb_oracle.so (stand-alone restatement, orb_oracle.cc)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+CAND_DTYPE = np.dtype([('x', '<i4'), ('y', '<i4'), ('response', '<i4')])
+assert KP_DTYPE.itemsize == 28 and CAND_DTYPE.itemsize == 12
+
+
+class Camera(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ('fx', 'fy', 'cx', 'cy', 'bf', 'baseline')]
+
+
+def build(native=False):
+    """Compile the oracle libraries (port always; ref only where /root/reference is present)."""
+    targets = ['port'] + (['ref'] if os.path.isdir('/root/reference/src') else [])
+    if native:
+        targets = ['_build/liborb_oracle_native.so'] + (['_ref/liborb_ref_native.so'] if os.path.isdir('/root/reference/src') else [])
+        targets = [os.path.join(HERE, t) for t in targets]
+    subprocess.run(['make', '-s', '-C', HERE] + targets, check=True)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """kind: 'ref' | 'port'; native=True loads the -O3 -march=native timing build."""
+
+    def __init__(self, kind='port', native=False):
+        self.kind = kind
+        suffix = '_native' if native else ''
+        if kind == 'ref':
+            path, self.pre = os.path.join(HERE, '_ref', f'liborb_ref{suffix}.so'), 'ref_'
+        else:
+            path, self.pre = os.path.join(HERE, '_build', f'liborb_oracle{suffix}.so'), 'orc_'
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = C.CDLL(path)
+        f = self._f
+        f('extractor_create', C.c_void_p, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int])
+        f('extractor_destroy', None, [C.c_void_p])
+        f('extractor_extract', C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int])
+        f('extractor_level_size', C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)])
+        f('extractor_level_copy', C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t])
+        f('extractor_tables', None, [C.c_void_p] + [C.c_void_p] * 4)
+        f('feature_quotas', None, [C.c_int, C.c_float, C.c_int, C.c_void_p])
+        f('detect_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
+        f('quadtree', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int])
+        f('ic_angle', C.c_float, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int])
+        f('descriptor', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_void_p])
+        f('descriptor_distance', C.c_int, [C.c_void_p, C.c_void_p])
+        f('stereo_matches', C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Camera),
+                                      C.c_void_p, C.c_void_p])
+        f('knn2', None, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                         C.c_void_p, C.c_int])
+        f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
+        f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
+        f('cv_gaussian7', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t])
+        f('cv_fast_atan2', C.c_float, [C.c_float, C.c_float])
+        f('cv_round_f', C.c_int, [C.c_float])
+        f('cv_round_d', C.c_int, [C.c_double])
+
+    def _f(self, name, res, args):
+        fn = getattr(self.lib, self.pre + name)
+        fn.restype, fn.argtypes = res, args
+        setattr(self, '_' + name, fn)
+
+    # ---- primitives ----
+    def resize(self, src, dw, dh):
+        src = np.ascontiguousarray(src, np.uint8)
+        dst = np.empty((dh, dw), np.uint8)
+        self._cv_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+        return dst
+
+    def fast(self, img, th, nms=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.empty(img.size // 2 + 16, CAND_DTYPE)
+        n = self._cv_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], th, int(nms), _p(out), len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    def gaussian7(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        dst = np.empty_like(img)
+        self._cv_gaussian7(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dst), dst.strides[0])
+        return dst
+
+    def fast_atan2(self, y, x):
+        return np.float32(self._cv_fast_atan2(float(y), float(x)))
+
+    # ---- stages ----
+    def quotas(self, nfeatures, scale, nlevels):
+        out = np.zeros(nlevels, np.int32)
+        self._feature_quotas(nfeatures, scale, nlevels, _p(out))
+        return out
+
+    def detect_fast(self, img, ini=20, mn=7):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.empty(img.size // 4 + 16, CAND_DTYPE)
+        n = self._detect_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], ini, mn, _p(out), len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    def quadtree(self, cand, w, h, nfeatures):
+        cand = np.ascontiguousarray(cand, CAND_DTYPE)
+        out = np.empty(len(cand) + 16, CAND_DTYPE)
+        n = self._quadtree(_p(cand), len(cand), w, h, nfeatures, _p(out), len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    def ic_angle(self, img, x, y):
+        img = np.ascontiguousarray(img, np.uint8)
+        return np.float32(self._ic_angle(_p(img), img.shape[1], img.shape[0], img.strides[0], int(x), int(y)))
+
+    def descriptor(self, blurred, x, y, angle):
+        blurred = np.ascontiguousarray(blurred, np.uint8)
+        d = np.empty(32, np.uint8)
+        self._descriptor(_p(blurred), blurred.shape[1], blurred.shape[0], blurred.strides[0], int(x), int(y), float(angle), _p(d))
+        return d
+
+    def descriptor_distance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return int(self._descriptor_distance(_p(a), _p(b)))
+
+    # ---- extractor ----
+    def extractor(self, nfeatures=2000, scale=1.2, nlevels=8, ini=20, mn=7):
+        return _Extractor(self, nfeatures, scale, nlevels, ini, mn)
+
+    def stereo(self, kpL, descL, pyrL, kpR, descR, pyrR, scale, inv_scale, cam):
+        n = len(pyrL)
+        pyrL = [np.ascontiguousarray(p, np.uint8) for p in pyrL]
+        pyrR = [np.ascontiguousarray(p, np.uint8) for p in pyrR]
+        pl = (C.c_void_p * n)(*[p.ctypes.data for p in pyrL])
+        pr = (C.c_void_p * n)(*[p.ctypes.data for p in pyrR])
+        lw = np.array([p.shape[1] for p in pyrL], np.int32)
+        lh = np.array([p.shape[0] for p in pyrL], np.int32)
+        lp = np.array([p.strides[0] for p in pyrL], np.uint64)
+        kpL = np.ascontiguousarray(kpL, KP_DTYPE); kpR = np.ascontiguousarray(kpR, KP_DTYPE)
+        descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+        scale = np.ascontiguousarray(scale, np.float32); inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+        ur = np.empty(len(kpL), np.float32); dp = np.empty(len(kpL), np.float32)
+        c = Camera(*[float(v) for v in cam])
+        rc = self._stereo_matches(_p(kpL), len(kpL), _p(descL), pl, _p(kpR), len(kpR), _p(descR), pr, _p(lw), _p(lh), _p(lp), n,
+                                  _p(scale), _p(inv_scale), C.byref(c), _p(ur), _p(dp))
+        return rc, ur, dp
+
+    def knn2(self, query, train, th_low=50, nnratio=0.6, threads=1):
+        query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
+        nq = len(query)
+        idx = np.empty(nq, np.int32); best = np.empty(nq, np.uint16); second = np.empty(nq, np.uint16)
+        match = np.empty(nq, np.int32)
+        self._knn2(_p(query), nq, _p(train), len(train), th_low, nnratio, _p(idx), _p(best), _p(second), _p(match), threads)
+        return idx, best, second, match
+
+
+class _Extractor:
+    def __init__(self, o, nfeatures, scale, nlevels, ini, mn):
+        self.o, self.nlevels, self.nfeatures = o, nlevels, nfeatures
+        self.h = o._extractor_create(nfeatures, scale, nlevels, ini, mn)
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.o._extractor_destroy(self.h)
+            self.h = None
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64 * self.nlevels
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = self.o._extractor_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError(f'oracle extract failed: {n}')
+        return kps[:n].copy(), desc[:n].copy()
+
+    def pyramid(self):
+        out = []
+        for s in range(self.nlevels):
+            w, h = C.c_int(), C.c_int()
+            assert self.o._extractor_level_size(self.h, s, C.byref(w), C.byref(h)) == 0
+            a = np.empty((h.value, w.value), np.uint8)
+            self.o._extractor_level_copy(self.h, s, _p(a), a.strides[0])
+            out.append(a)
+        return out
+
+    def tables(self):
+        t = [np.empty(self.nlevels, np.float32) for _ in range(4)]
+        self.o._extractor_tables(self.h, *[_p(a) for a in t])
+        return t

@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE — CPU oracle, not the product.
+//
+// Minimal stand-in for the slice of OpenCV the reference hot path touches, so that
+// /root/reference/src/ORBextractor.cc (and the matcher line ranges) compile UNMODIFIED without an
+// OpenCV install. It also lets the drop-in host class
+// (orb_slam2_refactored_b200/csrc/host) build here; with a real OpenCV on the include path this
+// directory is simply not used.
+//
+// Only 8-bit single-channel matrices exist. The four arithmetic primitives forward to the pinned
+// restatements in oracle/cv_primitives.cc.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+typedef unsigned char uchar;
+
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_PI 3.1415926535897932384626433832795
+
+namespace cv {
+
+class Exception : public std::runtime_error
+{
+public:
+	explicit Exception(const std::string& m) : std::runtime_error(m) {}
+};
+
+}  // namespace cv
+
+#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception(std::string("CV_Assert failed: ") + #expr); } while (0)
+
+inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(float v) { return (int)lrintf(v); }
+inline int cvRound(int v) { return v; }
+
+namespace cv {
+
+template <class T> struct Point_
+{
+	T x, y;
+	Point_() : x(0), y(0) {}
+	Point_(T x_, T y_) : x(x_), y(y_) {}
+	Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }
+};
+typedef Point_<int> Point;
+typedef Point_<float> Point2f;
+
+struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
+struct Rect
+{
+	int x, y, width, height;
+	Rect() : x(0), y(0), width(0), height(0) {}
+	Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {}
+};
+struct Range { int start, end; Range(int s, int e) : start(s), end(e) {} };
+
+template <class T, int M, int N> struct Matx { T val[M * N]; };
+typedef Matx<float, 3, 1> Matx31f;
+
+struct KeyPoint
+{
+	Point2f pt;
+	float size;
+	float angle;
+	float response;
+	int octave;
+	int class_id;
+	KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+	KeyPoint(float x, float y, float size_, float angle_ = -1, float response_ = 0, int octave_ = 0, int class_id_ = -1)
+		: pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
+};
+static_assert(sizeof(KeyPoint) == 28, "KeyPoint must mirror cv::KeyPoint (7 x 4 bytes)");
+
+enum { BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4 };
+
+class Mat
+{
+public:
+	int rows, cols;
+	size_t step;
+	uchar* data;
+
+	Mat() : rows(0), cols(0), step(0), data(nullptr) {}
+	Mat(int r, int c, int type) : Mat() { create(r, c, type); }
+	// external (non-owning) buffer, like cv::Mat(rows, cols, type, void*, step)
+	Mat(int r, int c, int /*type*/, void* ext, size_t step_ = 0)
+		: rows(r), cols(c), step(step_ ? step_ : (size_t)c), data((uchar*)ext) {}
+
+	int type() const { return CV_8U; }
+	bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+	size_t step1() const { return step; }
+	bool isContinuous() const { return step == (size_t)cols; }
+
+	void create(int r, int c, int /*type*/)
+	{
+		if (r == rows && c == cols && data && owner_ && step == (size_t)c)
+			return;
+		owner_ = std::make_shared<std::vector<uchar>>((size_t)r * c);
+		rows = r; cols = c; step = (size_t)c; data = owner_->data();
+	}
+	void release() { owner_.reset(); rows = cols = 0; step = 0; data = nullptr; }
+	void setTo(int v)
+	{
+		for (int y = 0; y < rows; y++)
+			std::memset(data + (size_t)y * step, v, (size_t)cols);
+	}
+	void copyTo(Mat& dst) const
+	{
+		dst.create(rows, cols, CV_8U);
+		for (int y = 0; y < rows; y++)
+			std::memcpy(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols);
+	}
+	Mat clone() const { Mat m; copyTo(m); return m; }
+
+	Mat operator()(const Range& rr, const Range& cr) const
+	{
+		Mat m;
+		m.owner_ = owner_;
+		m.rows = rr.end - rr.start; m.cols = cr.end - cr.start; m.step = step;
+		m.data = data + (size_t)rr.start * step + cr.start;
+		return m;
+	}
+	Mat operator()(const Rect& r) const { return (*this)(Range(r.y, r.y + r.height), Range(r.x, r.x + r.width)); }
+	Mat row(int r) const { return (*this)(Range(r, r + 1), Range(0, cols)); }
+
+	uchar* ptr(int r = 0) { return data + (size_t)r * step; }
+	const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+	template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+	template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+	template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+	template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+
+private:
+	std::shared_ptr<std::vector<uchar>> owner_;
+};
+
+template <class T> class Mat_ : public Mat
+{
+public:
+	Mat_() {}
+	Mat_(const Mat& m) : Mat(m) {}
+	T& operator()(int y, int x) { return this->template at<T>(y, x); }
+	const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
+};
+typedef Mat_<uchar> Mat1b;
+
+// pinned restatements, defined in oracle/cvshim_impl.cc on top of oracle/cv_primitives.cc
+void resize(const Mat& src, Mat& dst, Size dsize);
+void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
+float fastAtan2(float y, float x);
+
+}  // namespace cv

@@ -1,0 +1,41 @@
+// TEST INFRASTRUCTURE — CPU oracle, not the product.
+// cv:: entry points of the shim, forwarding to the pinned restatements in cv_primitives.cc.
+#include <opencv2/core.hpp>
+
+#include "cv_primitives.h"
+
+namespace cv {
+
+void resize(const Mat& src, Mat& dst, Size dsize)
+{
+	CV_Assert(!src.empty() && dsize.width > 0 && dsize.height > 0);
+	Mat out;
+	out.create(dsize.height, dsize.width, CV_8U);
+	cvp::resize_linear_u8(src.data, src.cols, src.rows, src.step, out.data, out.cols, out.rows, out.step);
+	dst = out;
+}
+
+void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression)
+{
+	std::vector<cvp::FastPoint> pts;
+	cvp::fast9_16(image.data, image.cols, image.rows, image.step, threshold, nonmaxSuppression, pts);
+	keypoints.clear();
+	keypoints.reserve(pts.size());
+	for (const cvp::FastPoint& p : pts)
+		keypoints.push_back(KeyPoint((float)p.x, (float)p.y, 7.f, -1.f, (float)p.score));
+}
+
+void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY, int borderType)
+{
+	// the only configuration the reference uses (ORBextractor.cc:799)
+	CV_Assert(ksize.width == 7 && ksize.height == 7 && sigmaX == 2.0 && (sigmaY == 2.0 || sigmaY == 0.0));
+	CV_Assert(borderType == BORDER_REFLECT_101);
+	Mat out;
+	out.create(src.rows, src.cols, CV_8U);
+	cvp::gauss7x7_u8(src.data, src.cols, src.rows, src.step, out.data, out.step);
+	dst = out;
+}
+
+float fastAtan2(float y, float x) { return cvp::fast_atan2_deg(y, x); }
+
+}  // namespace cv

@@ -1,0 +1,97 @@
+// TEST INFRASTRUCTURE — CPU oracle, not the product.
+//
+// One C API, exported twice:
+//   * oracle/_ref/liborb_ref.so   (prefix ref_)  — the reference's own translation units, compiled
+//     where they lie under /root/reference against oracle/cvshim (see oracle/Makefile);
+//   * oracle/_build/liborb_oracle.so (prefix orc_) — the stand-alone restatement in orb_oracle.cc,
+//     which is what travels to machines without /root/reference.
+// tests/ cross-check the two wherever both exist, then check the CUDA path against the restatement.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load these libraries.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef ORACLE_PREFIX
+#error "define ORACLE_PREFIX (ref_ or orc_)"
+#endif
+#define ORACLE_CAT2(a, b) a##b
+#define ORACLE_CAT(a, b) ORACLE_CAT2(a, b)
+#define ORACLE_FN(name) ORACLE_CAT(ORACLE_PREFIX, name)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// mirrors cv::KeyPoint field for field (28 bytes)
+typedef struct oracle_keypoint
+{
+	float x, y, size, angle, response;
+	int32_t octave, class_id;
+} oracle_keypoint;
+
+// packed FAST candidate / selected keypoint in level coordinates
+typedef struct oracle_cand
+{
+	int32_t x, y, response;
+} oracle_cand;
+
+typedef struct oracle_camera
+{
+	float fx, fy, cx, cy, bf, baseline;
+} oracle_camera;
+
+// ---- extractor object (include/ORBextractor.h:34-80) ----
+void* ORACLE_FN(extractor_create)(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void ORACLE_FN(extractor_destroy)(void* ex);
+// Extract (src/ORBextractor.cc:743-820). Returns the keypoint count N (<= cap, else -needed),
+// or -1 when the input contract is violated (the reference throws cv::Exception / divides by zero).
+int ORACLE_FN(extractor_extract)(void* ex, const uint8_t* img, int w, int h, size_t pitch,
+                                  oracle_keypoint* kps, uint8_t* desc, int cap);
+int ORACLE_FN(extractor_level_size)(void* ex, int level, int* w, int* h);
+int ORACLE_FN(extractor_level_copy)(void* ex, int level, uint8_t* dst, size_t pitch);
+// scale tables, 4 x nlevels floats: scaleFactors, invScaleFactors, sigmaSq, invSigmaSq
+void ORACLE_FN(extractor_tables)(void* ex, float* scale, float* inv_scale, float* sigma_sq, float* inv_sigma_sq);
+// per-level quotas (ComputeNumFeaturesPerScale, src/ORBextractor.cc:472-487)
+void ORACLE_FN(feature_quotas)(int nfeatures, float scaleFactor, int nlevels, int* out);
+
+// ---- stages, stateless ----
+// DetectFAST (src/ORBextractor.cc:489-540) with the roi Extract uses (16 px border, :755,760).
+int ORACLE_FN(detect_fast)(const uint8_t* img, int w, int h, size_t pitch, int iniTh, int minTh,
+                            oracle_cand* out, int cap);
+// QuadTreeSuppression (src/ORBextractor.cc:542-693); roi as above from (w,h).
+int ORACLE_FN(quadtree)(const oracle_cand* in, int n, int w, int h, int nfeatures, oracle_cand* out, int cap);
+// IC_Angle (src/ORBextractor.cc:74-101)
+float ORACLE_FN(ic_angle)(const uint8_t* img, int w, int h, size_t pitch, int x, int y);
+// ComputeOrbDescriptor (src/ORBextractor.cc:103-140) on an already blurred level
+void ORACLE_FN(descriptor)(const uint8_t* blurred, int w, int h, size_t pitch, int x, int y, float angle_deg,
+                           uint8_t* desc32);
+
+// ---- matchers ----
+// ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1449-1457)
+int ORACLE_FN(descriptor_distance)(const uint8_t* a, const uint8_t* b);
+// ComputeStereoMatches (src/ORBmatcher.cc:72-247). Pyramid levels are given as parallel arrays.
+// Returns 0, or -1 when the reference would index an empty vector (no surviving match, :232-233);
+// uright/depth are then all -1.
+int ORACLE_FN(stereo_matches)(const oracle_keypoint* kpL, int nL, const uint8_t* descL,
+                               const uint8_t* const* pyrL, const oracle_keypoint* kpR, int nR, const uint8_t* descR,
+                               const uint8_t* const* pyrR, const int* level_w, const int* level_h,
+                               const size_t* level_pitch, int nlevels, const float* scale, const float* inv_scale,
+                               const oracle_camera* cam, float* uright, float* depth);
+// best/second scan of SearchByBoW (src/ORBmatcher.cc:477-507): restated in both builds (the
+// reference has no stand-alone entry point for it). match[q] = idx if accepted by
+// best <= th_low && (float)best < nnratio*(float)second, else -1. Uses `threads` host threads.
+void ORACLE_FN(knn2)(const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int th_low, float nnratio,
+                     int32_t* idx, uint16_t* best, uint16_t* second, int32_t* match, int threads);
+
+// ---- pinned third-party primitives (same code in both libraries; checked against cv2 4.13.0) ----
+void ORACLE_FN(cv_resize)(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
+int ORACLE_FN(cv_fast)(const uint8_t* img, int w, int h, size_t step, int th, int nms, oracle_cand* out, int cap);
+void ORACLE_FN(cv_gaussian7)(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+float ORACLE_FN(cv_fast_atan2)(float y, float x);
+int ORACLE_FN(cv_round_f)(float v);
+int ORACLE_FN(cv_round_d)(double v);
+
+#ifdef __cplusplus
+}
+#endif
