@@ -1,0 +1,170 @@
+/* orbx.h — C ABI of the B200-native ORB front-end (liborbx_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates: the reference's
+ * ORB feature extraction and Hamming matching. The reference has no FFI layer; its
+ * boundary is a handful of C++ symbols called from src/System.cc. Each entry point below names the
+ * reference interface it replaces. The C++ mirror of those symbols (same class/method names) lives
+ * in include/orbx/ORBextractor.h and include/orbx/ORBmatcher.h and forwards to this ABI; see
+ * INTEGRATION.md for the three-line change in src/System.cc.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an orbx_status; nothing throws
+ * across the boundary. All work runs on hand-written sm_100a CUDA kernels — there is no CPU
+ * fallback: on a machine without a usable GPU every call returns ORBX_ERR_CUDA.
+ * "host" pointers are ordinary (ideally pinned) host memory; "_device" variants take device
+ * pointers valid on the handle's device and enqueue on the handle's stream without copies.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum orbx_status
+{
+	ORBX_OK = 0,
+	ORBX_ERR_INVALID = 1,    /* argument outside the reference's own input contract (it would throw / divide by zero) */
+	ORBX_ERR_CUDA = 2,       /* CUDA runtime error or no sm_100 device; orbx_last_error() has the text */
+	ORBX_ERR_CAPACITY = 3,   /* caller's output buffer too small; required size is reported */
+	ORBX_ERR_STATE = 4       /* call order violated (e.g. stereo before extract) */
+} orbx_status;
+
+/* ORBextractor::Parameters — include/ORBextractor.h:38-47 (defaults 2000 / 1.2f / 8 / 20 / 7) */
+typedef struct orbx_params
+{
+	int32_t nfeatures;
+	float scale_factor;
+	int32_t nlevels;
+	int32_t ini_th_fast;
+	int32_t min_th_fast;
+} orbx_params;
+
+/* cv::KeyPoint, field for field (pt.x, pt.y, size, angle, response, octave, class_id) — 28 bytes.
+ * A std::vector<cv::KeyPoint> buffer can be handed in directly. */
+typedef struct orbx_keypoint
+{
+	float x, y, size, angle, response;
+	int32_t octave, class_id;
+} orbx_keypoint;
+
+/* CameraParams — include/CameraParameters.h:29-40 */
+typedef struct orbx_camera
+{
+	float fx, fy, cx, cy, bf, baseline;
+} orbx_camera;
+
+typedef struct orbx_extractor* orbx_handle;
+
+const char* orbx_last_error(void);
+/* number of CUDA devices with compute capability 10.x; 0 when none (or no driver) */
+int orbx_device_count(void);
+
+/* ---- ORBextractor (include/ORBextractor.h:34-80, src/ORBextractor.cc:695-835) ---- */
+
+/* ORBextractor::ORBextractor(const Parameters&) + Init() — src/ORBextractor.cc:695-741.
+ * `device` is the CUDA ordinal; one handle owns one stream and one scratch arena, so — like the
+ * reference instance (include/ORBextractor.h:74-76) — a handle is not re-entrant, while different
+ * handles may run concurrently (src/System.cc:449-452). */
+orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out);
+orbx_status orbx_destroy(orbx_handle h);
+
+/* GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares — include/ORBextractor.h:57-62. Each array holds nlevels floats; any may be NULL. */
+orbx_status orbx_get_params(orbx_handle h, orbx_params* out);
+orbx_status orbx_scale_tables(orbx_handle h, float* scale, float* inv_scale, float* sigma_sq, float* inv_sigma_sq);
+/* per-level keypoint quotas — ComputeNumFeaturesPerScale, src/ORBextractor.cc:472-487 */
+orbx_status orbx_feature_quotas(orbx_handle h, int32_t* quotas);
+
+/* ORBextractor::Extract(image, keypoints, descriptors) — src/ORBextractor.cc:743-820, one frame,
+ * host buffers. `kps` holds `cap` entries, `desc` cap*32 bytes (the N x 32 CV_8U matrix, row i = keypoint i).
+ * *n = keypoint count. When N == 0 the reference releases `descriptors` and leaves `keypoints` untouched
+ * (:778-782); here *n = 0 and the buffers are untouched. ORBX_ERR_CAPACITY sets *n to the needed count. */
+orbx_status orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, size_t pitch,
+                         orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* The same for a batch of `frames` equally sized images (frame f at images + f*frame_stride). Outputs are
+ * frame-major: kps + f*cap, desc + f*cap*32, n[f]. This is the throughput entry point: every kernel is
+ * launched once per pyramid level (or once) for the whole batch. */
+orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                               size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* Device-resident variant: inputs already in HBM, outputs stay in HBM (d_kps: frames*cap keypoints, d_desc:
+ * frames*cap*32 bytes, d_n: frames int32). Asynchronous on the handle's stream; call orbx_synchronize (or use
+ * orbx_stream) before reading. cap must be >= orbx_max_keypoints(h). */
+orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int frames, int width, int height,
+                                      size_t pitch, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
+                                      int cap, int32_t* d_n);
+/* upper bound of keypoints per frame: sum over levels of (quota + 3) (the quadtree overshoots by at most 3) */
+int orbx_max_keypoints(orbx_handle h);
+orbx_status orbx_synchronize(orbx_handle h);
+/* the handle's cudaStream_t, as void* */
+void* orbx_stream(orbx_handle h);
+
+/* ORBextractor::GetImagePyramid() — include/ORBextractor.h:63. The pyramid of the last extract call stays on
+ * the device; a level is downloaded only on request. Valid until the next extract on this handle. */
+orbx_status orbx_level_size(orbx_handle h, int level, int* width, int* height);
+orbx_status orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_pitch);
+/* device view of the same: base pointer of `level` of `frame`, and its pitch in bytes */
+orbx_status orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch);
+
+/* Stage probes for parity tests (same stage boundaries as the oracle): results of the last extract call.
+ * candidates: DetectFAST output order (src/ORBextractor.cc:489-540); selected: QuadTreeSuppression output order
+ * (:542-693); both as (x, y, response) int32 triples in level coordinates. blurred: cv::GaussianBlur result (:799). */
+orbx_status orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n);
+orbx_status orbx_debug_selected(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n);
+orbx_status orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_pitch);
+
+/* ---- Matching (include/ORBmatcher.h, src/ORBmatcher.cc) ---- */
+
+/* ORBmatcher::DescriptorDistance — src/ORBmatcher.cc:1449-1457, for n descriptor pairs (a[i], b[i]), 32 bytes
+ * each, host buffers. The single-pair call of the reference is n = 1. */
+orbx_status orbx_descriptor_distance(int device, const uint8_t* a, const uint8_t* b, int64_t n, int32_t* dist);
+
+/* ComputeStereoMatches — include/ORBmatcher.h:41-45, src/ORBmatcher.cc:72-247 — on the device-resident results
+ * of the last extract of `left` and `right` (same batch size, same image size, same device). uright/depth: host,
+ * frames*cap floats laid out like the keypoints of that extract (cap = its cap); entries past n[f] are not
+ * written. No keypoint/descriptor/pyramid traffic leaves the GPU. */
+orbx_status orbx_stereo_match(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* uright, float* depth);
+orbx_status orbx_stereo_match_device(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* d_uright,
+                                     float* d_depth);
+/* The same from host-side data, exactly the reference's argument list (one stereo pair): keypoints, descriptors
+ * and 8-bit pyramids of both images. Levels are passed as arrays of base pointers / widths / heights / pitches. */
+orbx_status orbx_stereo_match_host(int device, const orbx_keypoint* kps_l, int n_l, const uint8_t* desc_l,
+                                   const uint8_t* const* pyr_l, const orbx_keypoint* kps_r, int n_r,
+                                   const uint8_t* desc_r, const uint8_t* const* pyr_r, const int* level_w,
+                                   const int* level_h, const size_t* level_pitch, int nlevels, const float* scale,
+                                   const float* inv_scale, const orbx_camera* camera, float* uright, float* depth);
+
+/* Brute-force best / second-best scan with the reference's inner-loop semantics (SearchByBoW,
+ * src/ORBmatcher.cc:477-507): train rows are visited in ascending index order; idx = lowest index of the
+ * minimum distance (or -1 when no row is closer than 256), best = that distance, second = the smallest distance
+ * among the other rows (256 when none). match[q] = idx when best <= th_low && (float)best < nnratio*(float)second,
+ * else -1 (match may be NULL). Host buffers. */
+orbx_status orbx_knn2(int device, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int th_low,
+                      float nnratio, int32_t* idx, uint16_t* best, uint16_t* second, int32_t* match);
+/* Device-resident variant on `stream` (a cudaStream_t as void*, NULL = default stream); asynchronous. */
+orbx_status orbx_knn2_device(const uint8_t* d_query, int64_t nq, const uint8_t* d_train, int64_t nt, int th_low,
+                             float nnratio, int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match,
+                             void* stream);
+
+/* Train-sharded kNN (BASELINE.json config 5): each rank scans its contiguous slice of the train set and emits one
+ * packed 64-bit partial per query; the partials of all ranks are all-gathered (NCCL) rank-major into
+ * d_gathered[rank*nq + q] and merged. The merge equals one ascending scan over the whole train set.
+ * index_base = global index of the shard's first row. */
+orbx_status orbx_knn2_partial_device(const uint8_t* d_query, int64_t nq, const uint8_t* d_train_shard, int64_t nt_shard,
+                                     int64_t index_base, uint64_t* d_partial, void* stream);
+orbx_status orbx_knn2_merge_device(const uint64_t* d_gathered, int ranks, int64_t nq, int th_low, float nnratio,
+                                   int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match, void* stream);
+
+/* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
+ * `device` (all SMs, register operands). */
+orbx_status orbx_measure_popc_peak(int device, double* popc_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ORBX_H */

@@ -1,0 +1,352 @@
+"""Python host-side mirror of the reference's interface for the ORB front-end hot path, on top of the C ABI
+(include/orbx.h, liborbx_b200.so). Names and argument meaning follow the reference:
+
+    ORB_SLAM2::ORBextractor            include/ORBextractor.h:34-80     -> ORBextractor
+    ORB_SLAM2::ComputeStereoMatches    include/ORBmatcher.h:41-45       -> ComputeStereoMatches / StereoMatcher
+    ORBmatcher::DescriptorDistance     include/ORBmatcher.h:54          -> ORBmatcher.DescriptorDistance
+    best/second ratio-test inner loop  src/ORBmatcher.cc:477-507        -> ORBmatcher.knn2 / knn2_sharded
+
+Everything computes on the GPU through the shared library; there is no CPU path. If the library is missing or
+no sm_100 device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'),
+                     ('octave', '<i4'), ('class_id', '<i4')])
+assert KP_DTYPE.itemsize == 28
+
+ORBX_OK, ORBX_ERR_INVALID, ORBX_ERR_CUDA, ORBX_ERR_CAPACITY, ORBX_ERR_STATE = range(5)
+
+TH_HIGH = 100   # src/ORBmatcher.cc:41
+TH_LOW = 50     # src/ORBmatcher.cc:42
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f'orbx status {status}: {msg}')
+        self.status = status
+
+
+class _Params(C.Structure):
+    _fields_ = [('nfeatures', C.c_int32), ('scale_factor', C.c_float), ('nlevels', C.c_int32),
+                ('ini_th_fast', C.c_int32), ('min_th_fast', C.c_int32)]
+
+
+class _Camera(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ('fx', 'fy', 'cx', 'cy', 'bf', 'baseline')]
+
+
+_lib = None
+
+_SIGNATURES = {
+    'orbx_last_error': (C.c_char_p, []),
+    'orbx_device_count': (C.c_int, []),
+    'orbx_create': (C.c_int, [C.POINTER(_Params), C.c_int, C.POINTER(C.c_void_p)]),
+    'orbx_destroy': (C.c_int, [C.c_void_p]),
+    'orbx_get_params': (C.c_int, [C.c_void_p, C.POINTER(_Params)]),
+    'orbx_scale_tables': (C.c_int, [C.c_void_p] + [C.c_void_p] * 4),
+    'orbx_feature_quotas': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'orbx_extract': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_extract_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p]),
+    'orbx_extract_batch_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_void_p]),
+    'orbx_max_keypoints': (C.c_int, [C.c_void_p]),
+    'orbx_synchronize': (C.c_int, [C.c_void_p]),
+    'orbx_stream': (C.c_void_p, [C.c_void_p]),
+    'orbx_level_size': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'orbx_pyramid_level': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    'orbx_pyramid_level_device': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    'orbx_debug_candidates': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_debug_selected': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_debug_blurred_level': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    'orbx_descriptor_distance': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'orbx_stereo_match': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(_Camera), C.c_void_p, C.c_void_p]),
+    'orbx_stereo_match_device': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(_Camera), C.c_void_p, C.c_void_p]),
+    'orbx_stereo_match_host': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.POINTER(_Camera), C.c_void_p, C.c_void_p]),
+    'orbx_knn2': (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                            C.c_void_p, C.c_void_p]),
+    'orbx_knn2_device': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    'orbx_knn2_partial_device': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    'orbx_knn2_merge_device': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    'orbx_measure_popc_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+}
+
+
+def exported_symbols():
+    """Every entry point include/orbx.h declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def library_path():
+    return _build.LIB
+
+
+def lib():
+    """Loads liborbx_b200.so; raises if it has not been built (there is no fallback implementation)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError(f'{path} is missing: run `python -m orb_slam2_refactored_b200.build` (needs nvcc). '
+                              'The ORB front-end has no CPU fallback.')
+        l = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def _check(status):
+    if status != ORBX_OK:
+        raise OrbxError(status, lib().orbx_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().orbx_device_count()
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor (include/ORBextractor.h:34-80). Same parameters, getters and Extract semantics; plus
+    batch and device-resident entry points that the reference does not have."""
+
+    class Parameters:   # include/ORBextractor.h:38-47
+        def __init__(self, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+            self.nfeatures, self.scaleFactor, self.nlevels = nfeatures, scaleFactor, nlevels
+            self.iniThFAST, self.minThFAST = iniThFAST, minThFAST
+
+    def __init__(self, param=None, device=0, **kw):
+        if param is None:
+            param = ORBextractor.Parameters(**kw)
+        self.param_ = param
+        self.device = device
+        self._h = C.c_void_p()
+        p = _Params(param.nfeatures, param.scaleFactor, param.nlevels, param.iniThFAST, param.minThFAST)
+        _check(lib().orbx_create(C.byref(p), device, C.byref(self._h)))
+        n = param.nlevels
+        t = [np.empty(n, np.float32) for _ in range(4)]
+        _check(lib().orbx_scale_tables(self._h, *[_p(a) for a in t]))
+        self._scale, self._inv_scale, self._sigma_sq, self._inv_sigma_sq = t
+        self._last_frames = 0
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value and _lib is not None:
+            _lib.orbx_destroy(h)
+            self._h = C.c_void_p()
+
+    # ---- getters, include/ORBextractor.h:57-63
+    def GetLevels(self): return self.param_.nlevels
+    def GetScaleFactor(self): return np.float32(self.param_.scaleFactor)
+    def GetScaleFactors(self): return self._scale
+    def GetInverseScaleFactors(self): return self._inv_scale
+    def GetScaleSigmaSquares(self): return self._sigma_sq
+    def GetInverseScaleSigmaSquares(self): return self._inv_sigma_sq
+
+    def GetFeatureQuotas(self):
+        q = np.empty(self.param_.nlevels, np.int32)
+        _check(lib().orbx_feature_quotas(self._h, _p(q)))
+        return q
+
+    def max_keypoints(self):
+        return lib().orbx_max_keypoints(self._h)
+
+    def GetImagePyramid(self, frame=0):
+        """Levels of the last Extract, downloaded on request (they live on the device)."""
+        out = []
+        for s in range(self.param_.nlevels):
+            w, h = C.c_int(), C.c_int()
+            _check(lib().orbx_level_size(self._h, s, C.byref(w), C.byref(h)))
+            a = np.empty((h.value, w.value), np.uint8)
+            _check(lib().orbx_pyramid_level(self._h, frame, s, _p(a), a.strides[0]))
+            out.append(a)
+        return out
+
+    # ---- Extract, src/ORBextractor.cc:743-820
+    def Extract(self, image):
+        """image: (H, W) uint8. Returns (keypoints[KP_DTYPE], descriptors[N,32] uint8)."""
+        k, d = self.ExtractBatch(np.asarray(image)[None])
+        return k[0], d[0]
+
+    def ExtractBatch(self, images):
+        """images: (F, H, W) uint8 host array. Returns two lists of per-frame arrays."""
+        images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim != 3:
+            raise OrbxError(ORBX_ERR_INVALID, 'CV_Assert(image.type() == CV_8U): expected (F, H, W) uint8')   # :457
+        F, H, W = images.shape
+        cap = lib().orbx_max_keypoints(self._h)
+        kps = np.zeros((F, cap), KP_DTYPE)
+        desc = np.zeros((F, cap, 32), np.uint8)
+        n = np.zeros(F, np.int32)
+        _check(lib().orbx_extract_batch(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], _p(kps), _p(desc), cap, _p(n)))
+        self._last_frames = F
+        return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
+
+    def extract_batch_device(self, d_images, d_kps=None, d_desc=None, d_n=None):
+        """d_images: CUDA torch.uint8 tensor (F, H, W) (row stride free). Outputs are torch tensors on the same device:
+        kps (F, cap, 7) float32 viewable as KP_DTYPE, desc (F, cap, 32) uint8, n (F,) int32. Asynchronous on the
+        handle's stream; call synchronize() before reading."""
+        import torch
+        F, H, W = d_images.shape
+        assert d_images.dtype == torch.uint8 and d_images.is_cuda and d_images.stride(2) == 1
+        if d_kps is None:
+            # plan first so that cap is the exact per-size bound
+            cap = max(self.max_keypoints(), 1)
+            d_kps = torch.empty((F, cap, 7), dtype=torch.float32, device=d_images.device)
+            d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device=d_images.device)
+            d_n = torch.empty((F,), dtype=torch.int32, device=d_images.device)
+        cap = d_kps.shape[1]
+        _check(lib().orbx_extract_batch_device(self._h, C.c_void_p(d_images.data_ptr()), F, W, H, d_images.stride(1), d_images.stride(0),
+                                               C.c_void_p(d_kps.data_ptr()), C.c_void_p(d_desc.data_ptr()), cap, C.c_void_p(d_n.data_ptr())))
+        self._last_frames = F
+        return d_kps, d_desc, d_n
+
+    def synchronize(self):
+        _check(lib().orbx_synchronize(self._h))
+
+    def stream(self):
+        return lib().orbx_stream(self._h)
+
+    # ---- stage probes for parity tests
+    def debug_candidates(self, frame, level):
+        cap = 1 << 16
+        while True:
+            out = np.empty((cap, 3), np.int32); n = C.c_int()
+            st = lib().orbx_debug_candidates(self._h, frame, level, _p(out), cap, C.byref(n))
+            if st == ORBX_ERR_CAPACITY:
+                cap = n.value + 16
+                continue
+            _check(st)
+            return out[:n.value].copy()
+
+    def debug_selected(self, frame, level):
+        cap = self.max_keypoints() + 64
+        out = np.empty((cap, 3), np.int32); n = C.c_int()
+        _check(lib().orbx_debug_selected(self._h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_blurred(self, frame, level):
+        w, h = C.c_int(), C.c_int()
+        _check(lib().orbx_level_size(self._h, level, C.byref(w), C.byref(h)))
+        a = np.empty((h.value, w.value), np.uint8)
+        _check(lib().orbx_debug_blurred_level(self._h, frame, level, _p(a), a.strides[0]))
+        return a
+
+
+def ComputeStereoMatches(keypointsL, descriptorsL, pyramidL, keypointsR, descriptorsR, pyramidR, scaleFactors, invScaleFactors,
+                         camera, device=0):
+    """ORB_SLAM2::ComputeStereoMatches (include/ORBmatcher.h:41-45, src/ORBmatcher.cc:72-247), the reference's
+    argument list with host data. camera = (fx, fy, cx, cy, bf, baseline). Returns (uright, depth)."""
+    n = len(pyramidL)
+    pyramidL = [np.ascontiguousarray(p, np.uint8) for p in pyramidL]
+    pyramidR = [np.ascontiguousarray(p, np.uint8) for p in pyramidR]
+    pl = (C.c_void_p * n)(*[p.ctypes.data for p in pyramidL])
+    pr = (C.c_void_p * n)(*[p.ctypes.data for p in pyramidR])
+    lw = np.array([p.shape[1] for p in pyramidL], np.int32)
+    lh = np.array([p.shape[0] for p in pyramidL], np.int32)
+    lp = np.array([p.strides[0] for p in pyramidL], np.uint64)
+    kl = np.ascontiguousarray(keypointsL, KP_DTYPE); kr = np.ascontiguousarray(keypointsR, KP_DTYPE)
+    dl = np.ascontiguousarray(descriptorsL, np.uint8); dr = np.ascontiguousarray(descriptorsR, np.uint8)
+    sc = np.ascontiguousarray(scaleFactors, np.float32); isc = np.ascontiguousarray(invScaleFactors, np.float32)
+    ur = np.full(len(kl), -1, np.float32); dp = np.full(len(kl), -1, np.float32)
+    cam = _Camera(*[float(v) for v in camera])
+    _check(lib().orbx_stereo_match_host(device, _p(kl), len(kl), _p(dl), pl, _p(kr), len(kr), _p(dr), pr, _p(lw), _p(lh), _p(lp), n,
+                                        _p(sc), _p(isc), C.byref(cam), _p(ur), _p(dp)))
+    return ur, dp
+
+
+def ComputeStereoMatchesResident(extractorL, extractorR, camera):
+    """The same on the device-resident results of the last ExtractBatch of two extractors (what SystemImpl::TrackStereo
+    does at src/System.cc:449-461, without moving keypoints, descriptors or pyramids off the GPU).
+    Returns (uright, depth) as (F, cap) arrays; entries past a frame's keypoint count are undefined."""
+    F = extractorL._last_frames
+    cap = extractorL.max_keypoints()
+    ur = np.full((F, cap), -1, np.float32); dp = np.full((F, cap), -1, np.float32)
+    cam = _Camera(*[float(v) for v in camera])
+    _check(lib().orbx_stereo_match(extractorL._h, extractorR._h, C.byref(cam), _p(ur), _p(dp)))
+    return ur, dp
+
+
+class ORBmatcher:
+    """The Hamming pieces of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:47-103) that are on the hot path."""
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.fNNRatio_ = nnratio
+        self.checkOrientation_ = checkOri
+        self.device = device
+
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        """src/ORBmatcher.cc:1449-1457. a, b: 32-byte descriptors, or (n, 32) arrays for n pairs."""
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        single = a.ndim == 1
+        a2 = a.reshape(-1, 32); b2 = b.reshape(-1, 32)
+        out = np.empty(len(a2), np.int32)
+        _check(lib().orbx_descriptor_distance(device, _p(a2), _p(b2), len(a2), _p(out)))
+        return int(out[0]) if single else out
+
+    def knn2(self, query, train, th_low=TH_LOW):
+        """Best/second scan + ratio test (src/ORBmatcher.cc:477-507) of every query row against all train rows.
+        Returns (idx, best, second, match)."""
+        query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)
+        nq = len(query)
+        idx = np.empty(nq, np.int32); best = np.empty(nq, np.uint16); second = np.empty(nq, np.uint16); match = np.empty(nq, np.int32)
+        _check(lib().orbx_knn2(self.device, _p(query), nq, _p(train), len(train), th_low, self.fNNRatio_, _p(idx), _p(best), _p(second),
+                               _p(match)))
+        return idx, best, second, match
+
+    def knn2_device(self, d_query, d_train, th_low=TH_LOW, stream=None):
+        """torch CUDA uint8 tensors (nq, 32), (nt, 32) -> torch tensors (idx i32, best, second as int16 bit patterns, match i32)."""
+        import torch
+        nq = d_query.shape[0]
+        dev = d_query.device
+        idx = torch.empty(nq, dtype=torch.int32, device=dev); best = torch.empty(nq, dtype=torch.int16, device=dev)
+        second = torch.empty(nq, dtype=torch.int16, device=dev); match = torch.empty(nq, dtype=torch.int32, device=dev)
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib().orbx_knn2_device(C.c_void_p(d_query.data_ptr()), nq, C.c_void_p(d_train.data_ptr()), d_train.shape[0], th_low,
+                                      self.fNNRatio_, C.c_void_p(idx.data_ptr()), C.c_void_p(best.data_ptr()),
+                                      C.c_void_p(second.data_ptr()), C.c_void_p(match.data_ptr()), st))
+        return idx, best, second, match
+
+
+def knn2_partial_device(d_query, d_train_shard, index_base, d_partial=None, stream=None):
+    """One rank's share of the train-sharded scan: packed (best << 48 | second << 32 | global index) per query."""
+    import torch
+    nq = d_query.shape[0]
+    if d_partial is None:
+        d_partial = torch.empty(nq, dtype=torch.int64, device=d_query.device)
+    st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(d_query.device).cuda_stream)
+    _check(lib().orbx_knn2_partial_device(C.c_void_p(d_query.data_ptr()), nq, C.c_void_p(d_train_shard.data_ptr()),
+                                          d_train_shard.shape[0], index_base, C.c_void_p(d_partial.data_ptr()), st))
+    return d_partial
+
+
+def knn2_merge_device(d_gathered, ranks, nq, th_low=TH_LOW, nnratio=0.6, stream=None):
+    import torch
+    dev = d_gathered.device
+    idx = torch.empty(nq, dtype=torch.int32, device=dev); best = torch.empty(nq, dtype=torch.int16, device=dev)
+    second = torch.empty(nq, dtype=torch.int16, device=dev); match = torch.empty(nq, dtype=torch.int32, device=dev)
+    st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib().orbx_knn2_merge_device(C.c_void_p(d_gathered.data_ptr()), ranks, nq, th_low, nnratio, C.c_void_p(idx.data_ptr()),
+                                        C.c_void_p(best.data_ptr()), C.c_void_p(second.data_ptr()), C.c_void_p(match.data_ptr()), st))
+    return idx, best, second, match
+
+
+def measure_popc_peak(device=0):
+    v = C.c_double()
+    _check(lib().orbx_measure_popc_peak(device, C.byref(v)))
+    return v.value

@@ -1,0 +1,763 @@
+// Host side of the C ABI (include/orbx.h): plan construction (all float/double-derived tables are computed here
+// with the reference's exact operation order; kernels are integer-only on pixels), buffer management, launches.
+// No CPU compute path exists: without a usable sm_100 device every entry point fails with ORBX_ERR_CUDA.
+#include "orbx_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+int orbx_knn2_splits(int64_t nq, int64_t nt);
+
+namespace {
+
+thread_local std::string g_err;
+
+orbx_status fail(orbx_status s, const std::string& msg)
+{
+	g_err = msg;
+	return s;
+}
+
+#define CU(call)                                                                                         \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess)                                                                           \
+			return fail(ORBX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+	} while (0)
+
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_round(float v) { return (int)lrintf(v); }
+inline short sat_s16(int v) { return (short)std::min(32767, std::max(-32768, v)); }
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+template <class T> struct DevBuf
+{
+	T* p = nullptr;
+	size_t n = 0;
+	cudaError_t ensure(size_t count)
+	{
+		if (count <= n) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; n = 0;
+		cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+		if (e == cudaSuccess) n = count;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	~DevBuf() { release(); }
+	DevBuf() = default;
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+};
+
+bool device_ok(int device, std::string& why)
+{
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) { why = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); return false; }
+	if (device < 0 || device >= count) { why = "no such CUDA device"; return false; }
+	cudaDeviceProp p;
+	e = cudaGetDeviceProperties(&p, device);
+	if (e != cudaSuccess) { why = cudaGetErrorString(e); return false; }
+	if (p.major != 10) { why = "device is not compute capability 10.x (kernels are built for sm_100a only)"; return false; }
+	return true;
+}
+
+}  // namespace
+
+struct orbx_extractor
+{
+	orbx_params prm;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	std::vector<float> scale, inv_scale, sigma_sq, inv_sigma_sq;
+	std::vector<int> quota;
+
+	// plan (depends on image size)
+	int pw = 0, ph = 0, frames_cap = 0;
+	OrbxPlanDev P;
+	DevBuf<uint8_t> pyr, blur;
+	DevBuf<uint32_t> cand, qbuf0, qbuf1, sel;
+	DevBuf<int> cell_count, cand_count, sel_count;
+	DevBuf<int> root_x, xofs, yofs;
+	DevBuf<uint8_t> root_lut;
+	DevBuf<short2> xcoef, ycoef;
+	// outputs owned by the handle (host-buffer API) and the state of the last extract (for stereo / probes)
+	DevBuf<orbx_keypoint> out_kps;
+	DevBuf<uint8_t> out_desc;
+	DevBuf<int32_t> out_n;
+	DevBuf<float> st_uright, st_depth;
+	DevBuf<int> st_sad;
+	bool have_result = false;
+	int last_frames = 0, last_cap = 0;
+	const orbx_keypoint* last_kps = nullptr;
+	const uint8_t* last_desc = nullptr;
+	const int32_t* last_n = nullptr;
+};
+
+namespace {
+
+// ORBextractor::Init (src/ORBextractor.cc:720-740) and ComputeNumFeaturesPerScale (:472-487)
+void build_tables(orbx_extractor* h)
+{
+	const int nl = h->prm.nlevels;
+	h->scale.resize(nl); h->inv_scale.resize(nl); h->sigma_sq.resize(nl); h->inv_sigma_sq.resize(nl); h->quota.resize(nl);
+	float s = 1.f;
+	for (int i = 0; i < nl; i++)
+	{
+		h->scale[i] = s;
+		h->inv_scale[i] = 1.f / s;
+		h->sigma_sq[i] = s * s;
+		h->inv_sigma_sq[i] = 1.f / (s * s);
+		s *= h->prm.scale_factor;
+	}
+	const double factor = 1 / h->prm.scale_factor;
+	double nf = h->prm.nfeatures * (1 - factor) / (1 - std::pow(factor, nl));
+	int sum = 0;
+	for (int i = 0; i < nl - 1; i++)
+	{
+		h->quota[i] = cv_round(nf);
+		sum += h->quota[i];
+		nf *= factor;
+	}
+	h->quota[nl - 1] = std::max(h->prm.nfeatures - sum, 0);
+}
+
+// cv::resize coefficient tables
+void resize_tables(int dn, int sn, int* ofs, short2* coef)
+{
+	const double scale = 1.0 / ((double)dn / sn);
+	for (int d = 0; d < dn; d++)
+	{
+		float f = (float)((d + 0.5) * scale - 0.5);
+		int s = (int)std::floor(f);
+		f -= (float)s;
+		if (s < 0) { s = 0; f = 0.f; }
+		if (s + 1 >= sn) { s = sn - 1; f = 0.f; }
+		ofs[d] = s;
+		coef[d].x = sat_s16(cv_round((1.f - f) * 2048.f));
+		coef[d].y = sat_s16(cv_round(f * 2048.f));
+	}
+}
+
+orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
+{
+	const int nl = h->prm.nlevels;
+	if (w == h->pw && hgt == h->ph && frames <= h->frames_cap)
+	{
+		h->P.frames = frames;
+		return ORBX_OK;
+	}
+	if (w > 4096 || hgt > 4096)
+		return fail(ORBX_ERR_INVALID, "image larger than 4096 px per side (candidate packing limit)");
+
+	OrbxPlanDev& P = h->P;
+	std::memset(&P, 0, sizeof(P));
+	P.nlevels = nl; P.frames = frames;
+	P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
+
+	std::vector<int> root_x, xofs, yofs;
+	std::vector<uint8_t> root_lut;
+	std::vector<short2> xcoef, ycoef;
+	int64_t slab = 0;
+	int cells = 0, cands = 0, sels = 0, node_cap = 0;
+	for (int s = 0; s < nl; s++)
+	{
+		OrbxLevel& L = P.lv[s];
+		// ComputePyramid (:455-470): sizes always from the original dims
+		L.w = s == 0 ? w : cv_round(h->inv_scale[s] * (float)w);
+		L.h = s == 0 ? hgt : cv_round(h->inv_scale[s] * (float)hgt);
+		L.pitch = (int)align_up(L.w, 128);
+		L.offset = slab;
+		slab += (int64_t)L.pitch * L.h;
+		slab = align_up(slab, 256);
+		L.scale = h->scale[s];
+
+		// DetectFAST grid (:489-523)
+		const int rw = L.w - 2 * ORBX_BORDER, rh = L.h - 2 * ORBX_BORDER;
+		if (rw < ORBX_CELL || rh < ORBX_CELL)
+			return fail(ORBX_ERR_INVALID, "a pyramid level is smaller than 62 px: the reference divides by zero (src/ORBextractor.cc:508-511)");
+		L.minx = ORBX_BORDER; L.miny = ORBX_BORDER; L.maxx = L.minx + rw; L.maxy = L.miny + rh;
+		const int gridw = rw / ORBX_CELL, gridh = rh / ORBX_CELL;
+		L.cellw = (int)std::ceil(1. * rw / gridw);
+		L.cellh = (int)std::ceil(1. * rh / gridh);
+		L.ncx = 0;
+		for (int cx = 0, x0 = L.minx; cx < gridw && x0 + 6 < L.maxx; cx++, x0 += L.cellw) L.ncx++;
+		L.ncy = 0;
+		for (int cy = 0, y0 = L.miny; cy < gridh && y0 + 6 < L.maxy; cy++, y0 += L.cellh) L.ncy++;
+		L.cell_base = cells;
+		cells += L.ncx * L.ncy;
+		L.cell_cap = ((L.cellw + 1) / 2) * ((L.cellh + 1) / 2);
+		L.cand_base = cands;
+		L.cand_cap = L.ncx * L.ncy * L.cell_cap;
+		cands += L.cand_cap;
+
+		// QuadTreeSuppression roots (:547-581)
+		const int n0 = cv_round(1. * rw / rh);
+		if (n0 < 1 || n0 > ORBX_MAX_ROOTS)
+			return fail(ORBX_ERR_INVALID, "aspect ratio outside [1, 16]: the reference divides by zero for portrait images (src/ORBextractor.cc:547-548)");
+		const double hx = 1. * rw / n0;
+		L.n_roots = n0;
+		L.root_base = (int)root_x.size();
+		for (int i = 0; i <= n0; i++) root_x.push_back((int)(L.minx + hx * i));
+		L.rootlut_base = (int)root_lut.size();
+		for (int x = 0; x < L.w; x++)
+		{
+			int id = (int)(((float)x - L.minx) / hx);
+			root_lut.push_back((uint8_t)std::min(std::max(id, 0), n0 - 1));
+		}
+		L.quota = h->quota[s];
+		L.sel_cap = std::max(L.quota + 3, 4 * n0);
+		L.sel_base = sels;
+		sels += L.sel_cap;
+		node_cap = std::max(node_cap, L.sel_cap);
+
+		if (s > 0)
+		{
+			L.xtab_base = (int)xofs.size();
+			xofs.resize(xofs.size() + L.w); xcoef.resize(xcoef.size() + L.w);
+			resize_tables(L.w, P.lv[s - 1].w, xofs.data() + L.xtab_base, xcoef.data() + L.xtab_base);
+			L.ytab_base = (int)yofs.size();
+			yofs.resize(yofs.size() + L.h); ycoef.resize(ycoef.size() + L.h);
+			resize_tables(L.h, P.lv[s - 1].h, yofs.data() + L.ytab_base, ycoef.data() + L.ytab_base);
+		}
+	}
+	P.slab = slab;
+	P.cells_per_frame = cells; P.cand_per_frame = cands; P.sel_per_frame = sels;
+	P.node_cap = node_cap + 8;
+	P.out_cap = sels;
+	if (sels >= 65536)
+		return fail(ORBX_ERR_INVALID, "more than 65535 keypoints per frame");
+	if (orbx_quadtree_smem(P.node_cap) > 200 * 1024)
+		return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree kernel's shared memory");
+
+	CU(cudaSetDevice(h->device));
+	const size_t F = (size_t)frames;
+	CU(h->pyr.ensure(F * slab)); CU(h->blur.ensure(F * slab));
+	CU(h->cand.ensure(F * cands)); CU(h->qbuf0.ensure(F * cands)); CU(h->qbuf1.ensure(F * cands));
+	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
+	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl));
+	CU(h->sel.ensure(F * sels));
+	CU(h->root_x.ensure(root_x.size())); CU(h->root_lut.ensure(root_lut.size()));
+	CU(h->xofs.ensure(std::max<size_t>(xofs.size(), 1))); CU(h->xcoef.ensure(std::max<size_t>(xcoef.size(), 1)));
+	CU(h->yofs.ensure(std::max<size_t>(yofs.size(), 1))); CU(h->ycoef.ensure(std::max<size_t>(ycoef.size(), 1)));
+	CU(h->out_kps.ensure(F * sels)); CU(h->out_desc.ensure(F * sels * 32)); CU(h->out_n.ensure(F));
+	CU(cudaMemcpyAsync(h->root_x.p, root_x.data(), root_x.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(h->root_lut.p, root_lut.data(), root_lut.size(), cudaMemcpyHostToDevice, h->stream));
+	if (!xofs.empty())
+	{
+		CU(cudaMemcpyAsync(h->xofs.p, xofs.data(), xofs.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->xcoef.p, xcoef.data(), xcoef.size() * sizeof(short2), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->yofs.p, yofs.data(), yofs.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->ycoef.p, ycoef.data(), ycoef.size() * sizeof(short2), cudaMemcpyHostToDevice, h->stream));
+	}
+	CU(cudaStreamSynchronize(h->stream));    // the host vectors above die with this scope
+
+	P.pyr = h->pyr.p; P.blur = h->blur.p;
+	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
+	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
+	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p;
+	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
+	h->pw = w; h->ph = hgt; h->frames_cap = frames;
+	h->have_result = false;
+	return ORBX_OK;
+}
+
+// enqueue the whole extraction of P.frames frames; level 0 is at (l0, l0_pitch, l0_stride)
+orbx_status enqueue_extract(orbx_extractor* h, const uint8_t* l0, int64_t l0_pitch, int64_t l0_stride,
+                            orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap)
+{
+	OrbxPlanDev& P = h->P;
+	P.l0 = l0; P.l0_pitch = l0_pitch; P.l0_stride = l0_stride;
+	P.out_cap = cap;      // stride of the output arrays for this call (>= sel_per_frame)
+	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, h->stream);
+	orbx_launch_fast(P, h->stream);
+	orbx_launch_quadtree(P, h->stream);
+	orbx_launch_blur(P, h->stream);
+	orbx_launch_describe(P, d_kps, d_desc, d_n, h->stream);
+	CU(cudaGetLastError());
+	h->have_result = true;
+	h->last_frames = P.frames; h->last_cap = P.out_cap;
+	h->last_kps = d_kps; h->last_desc = d_desc; h->last_n = d_n;
+	return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orbx_last_error(void) { return g_err.c_str(); }
+
+int orbx_device_count(void)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+	int ok = 0;
+	for (int i = 0; i < count; i++)
+	{
+		cudaDeviceProp p;
+		if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+	}
+	return ok;
+}
+
+orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
+{
+	if (!params || !out) return fail(ORBX_ERR_INVALID, "null argument");
+	if (params->nlevels < 1 || params->nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "nlevels must be in [1, 12]");
+	if (params->nfeatures < 1) return fail(ORBX_ERR_INVALID, "nfeatures must be positive");
+	if (!(params->scale_factor > 1.f)) return fail(ORBX_ERR_INVALID, "scaleFactor must be > 1");
+	if (params->min_th_fast < 1 || params->ini_th_fast < params->min_th_fast || params->ini_th_fast > 254)
+		return fail(ORBX_ERR_INVALID, "need 1 <= minThFAST <= iniThFAST <= 254 (a zero response makes the reference dereference null, src/ORBextractor.cc:681-691)");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	CU(cudaSetDevice(device));
+	orbx_extractor* h = new orbx_extractor();
+	h->prm = *params;
+	h->device = device;
+	build_tables(h);
+	cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = orbx_upload_pattern();
+	if (e != cudaSuccess)
+	{
+		delete h;
+		return fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+	}
+	*out = h;
+	return ORBX_OK;
+}
+
+orbx_status orbx_destroy(orbx_handle h)
+{
+	if (!h) return ORBX_OK;
+	cudaSetDevice(h->device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
+	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
+	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
+	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
+	h->st_uright.release(); h->st_depth.release(); h->st_sad.release();
+	if (h->done) cudaEventDestroy(h->done);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return ORBX_OK;
+}
+
+orbx_status orbx_get_params(orbx_handle h, orbx_params* out)
+{
+	if (!h || !out) return fail(ORBX_ERR_INVALID, "null argument");
+	*out = h->prm;
+	return ORBX_OK;
+}
+
+orbx_status orbx_scale_tables(orbx_handle h, float* scale, float* inv_scale, float* sigma_sq, float* inv_sigma_sq)
+{
+	if (!h) return fail(ORBX_ERR_INVALID, "null handle");
+	const size_t b = sizeof(float) * h->prm.nlevels;
+	if (scale) std::memcpy(scale, h->scale.data(), b);
+	if (inv_scale) std::memcpy(inv_scale, h->inv_scale.data(), b);
+	if (sigma_sq) std::memcpy(sigma_sq, h->sigma_sq.data(), b);
+	if (inv_sigma_sq) std::memcpy(inv_sigma_sq, h->inv_sigma_sq.data(), b);
+	return ORBX_OK;
+}
+
+orbx_status orbx_feature_quotas(orbx_handle h, int32_t* quotas)
+{
+	if (!h || !quotas) return fail(ORBX_ERR_INVALID, "null argument");
+	std::memcpy(quotas, h->quota.data(), sizeof(int) * h->prm.nlevels);
+	return ORBX_OK;
+}
+
+int orbx_max_keypoints(orbx_handle h)
+{
+	if (!h) return 0;
+	// sum over levels of max(quota + 3, 4 * roots); roots <= 16 is only known with the image size, so assume the
+	// worst case before the first extract
+	if (h->pw) return h->P.sel_per_frame;
+	int s = 0;
+	for (int q : h->quota) s += std::max(q + 3, 4 * ORBX_MAX_ROOTS);
+	return s;
+}
+
+orbx_status orbx_synchronize(orbx_handle h)
+{
+	if (!h) return fail(ORBX_ERR_INVALID, "null handle");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	return ORBX_OK;
+}
+
+void* orbx_stream(orbx_handle h) { return h ? (void*)h->stream : nullptr; }
+
+orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int frames, int width, int height,
+                                      size_t pitch, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
+                                      int cap, int32_t* d_n)
+{
+	if (!h || !d_images || !d_kps || !d_desc || !d_n) return fail(ORBX_ERR_INVALID, "null argument");
+	if (frames < 1 || width < 1 || height < 1 || pitch < (size_t)width) return fail(ORBX_ERR_INVALID, "bad image geometry");
+	CU(cudaSetDevice(h->device));
+	orbx_status st = build_plan(h, width, height, frames);
+	if (st != ORBX_OK) return st;
+	if (cap < h->P.sel_per_frame || cap >= 65536)
+		return fail(ORBX_ERR_CAPACITY, "cap must be >= orbx_max_keypoints() (and < 65536)");
+	const uint8_t* l0 = d_images;
+	int64_t l0_pitch = (int64_t)pitch, l0_stride = (int64_t)frame_stride;
+	if (((uintptr_t)d_images & 15) || (pitch & 3) || (frame_stride & 3))
+	{
+		// kernels read level 0 with aligned 32-bit loads: repack a misaligned input into the slab
+		const OrbxLevel& L0 = h->P.lv[0];
+		for (int f = 0; f < frames; f++)
+			CU(cudaMemcpy2DAsync(h->pyr.p + (int64_t)f * h->P.slab + L0.offset, L0.pitch, d_images + (size_t)f * frame_stride, pitch,
+			                     width, height, cudaMemcpyDeviceToDevice, h->stream));
+		l0 = h->pyr.p + L0.offset; l0_pitch = L0.pitch; l0_stride = h->P.slab;
+	}
+	return enqueue_extract(h, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+}
+
+orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                               size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+	if (!h || !images || !n) return fail(ORBX_ERR_INVALID, "null argument");
+	if (frames < 1 || width < 1 || height < 1 || pitch < (size_t)width) return fail(ORBX_ERR_INVALID, "bad image geometry");
+	CU(cudaSetDevice(h->device));
+	orbx_status st = build_plan(h, width, height, frames);
+	if (st != ORBX_OK) return st;
+	const OrbxPlanDev& P = h->P;
+	const OrbxLevel& L0 = P.lv[0];
+	// level 0 is uploaded straight into the pyramid slab (ComputePyramid's copyTo, :462)
+	for (int f = 0; f < frames; f++)
+		CU(cudaMemcpy2DAsync(h->pyr.p + (int64_t)f * P.slab + L0.offset, L0.pitch, images + (size_t)f * frame_stride, pitch, width,
+		                     height, cudaMemcpyHostToDevice, h->stream));
+	st = enqueue_extract(h, h->pyr.p + L0.offset, L0.pitch, P.slab, h->out_kps.p, h->out_desc.p, h->out_n.p, P.sel_per_frame);
+	if (st != ORBX_OK) return st;
+	std::vector<int32_t> counts(frames);
+	CU(cudaMemcpyAsync(counts.data(), h->out_n.p, sizeof(int32_t) * frames, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	int need = 0;
+	for (int f = 0; f < frames; f++) { n[f] = counts[f]; need = std::max(need, counts[f]); }
+	if (need > cap || (need > 0 && (!kps || !desc)))
+	{
+		for (int f = 0; f < frames; f++) n[f] = counts[f];
+		return fail(ORBX_ERR_CAPACITY, "output buffers hold fewer keypoints than were found");
+	}
+	for (int f = 0; f < frames; f++)
+	{
+		if (counts[f] == 0) continue;    // :778-782 — outputs untouched
+		CU(cudaMemcpyAsync(kps + (size_t)f * cap, h->out_kps.p + (size_t)f * P.out_cap, sizeof(orbx_keypoint) * counts[f],
+		                   cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaMemcpyAsync(desc + (size_t)f * cap * 32, h->out_desc.p + (size_t)f * P.out_cap * 32, (size_t)32 * counts[f],
+		                   cudaMemcpyDeviceToHost, h->stream));
+	}
+	CU(cudaStreamSynchronize(h->stream));
+	return ORBX_OK;
+}
+
+orbx_status orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, size_t pitch,
+                         orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+	return orbx_extract_batch(h, image, 1, width, height, pitch, pitch * (size_t)height, kps, desc, cap, n);
+}
+
+orbx_status orbx_level_size(orbx_handle h, int level, int* width, int* height)
+{
+	if (!h || !h->pw) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (level < 0 || level >= h->prm.nlevels) return fail(ORBX_ERR_INVALID, "level out of range");
+	if (width) *width = h->P.lv[level].w;
+	if (height) *height = h->P.lv[level].h;
+	return ORBX_OK;
+}
+
+orbx_status orbx_pyramid_level_device(orbx_handle h, int frame, int level, const uint8_t** d_ptr, size_t* pitch)
+{
+	if (!h || !h->have_result) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+	const OrbxPlanDev& P = h->P;
+	if (level == 0) { *d_ptr = P.l0 + (int64_t)frame * P.l0_stride; *pitch = (size_t)P.l0_pitch; }
+	else { *d_ptr = P.pyr + (int64_t)frame * P.slab + P.lv[level].offset; *pitch = (size_t)P.lv[level].pitch; }
+	return ORBX_OK;
+}
+
+orbx_status orbx_pyramid_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_pitch)
+{
+	const uint8_t* p; size_t pitch;
+	orbx_status st = orbx_pyramid_level_device(h, frame, level, &p, &pitch);
+	if (st != ORBX_OK) return st;
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemcpy2DAsync(dst, dst_pitch, p, pitch, h->P.lv[level].w, h->P.lv[level].h, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return ORBX_OK;
+}
+
+orbx_status orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_pitch)
+{
+	if (!h || !h->have_result) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+	const OrbxPlanDev& P = h->P;
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemcpy2DAsync(dst, dst_pitch, P.blur + (int64_t)frame * P.slab + P.lv[level].offset, P.lv[level].pitch, P.lv[level].w,
+	                     P.lv[level].h, cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return ORBX_OK;
+}
+
+orbx_status orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n)
+{
+	if (!h || !h->have_result) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+	const OrbxPlanDev& P = h->P;
+	const OrbxLevel& L = P.lv[level];
+	CU(cudaSetDevice(h->device));
+	const int ncell = L.ncx * L.ncy;
+	std::vector<int> counts(ncell);
+	CU(cudaMemcpy(counts.data(), P.cell_count + (int64_t)frame * P.cells_per_frame + L.cell_base, sizeof(int) * ncell, cudaMemcpyDeviceToHost));
+	std::vector<uint32_t> slots((size_t)L.cand_cap);
+	CU(cudaMemcpy(slots.data(), P.cand + (int64_t)frame * P.cand_per_frame + L.cand_base, sizeof(uint32_t) * slots.size(), cudaMemcpyDeviceToHost));
+	int total = 0;
+	for (int c = 0; c < ncell; c++)
+		for (int k = 0; k < counts[c]; k++, total++)
+			if (total < cap)
+			{
+				const uint32_t v = slots[(size_t)c * L.cell_cap + k];
+				xyr[3 * total] = orbx_px(v); xyr[3 * total + 1] = orbx_py(v); xyr[3 * total + 2] = orbx_pr(v);
+			}
+	*n = total;
+	return total > cap ? fail(ORBX_ERR_CAPACITY, "candidate buffer too small") : ORBX_OK;
+}
+
+orbx_status orbx_debug_selected(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n)
+{
+	if (!h || !h->have_result) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (level < 0 || level >= h->prm.nlevels || frame < 0 || frame >= h->last_frames) return fail(ORBX_ERR_INVALID, "frame/level out of range");
+	const OrbxPlanDev& P = h->P;
+	const OrbxLevel& L = P.lv[level];
+	CU(cudaSetDevice(h->device));
+	int cnt = 0;
+	CU(cudaMemcpy(&cnt, P.sel_count + (int64_t)frame * P.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+	*n = cnt;
+	if (cnt > cap) return fail(ORBX_ERR_CAPACITY, "selected buffer too small");
+	std::vector<uint32_t> v(std::max(cnt, 1));
+	CU(cudaMemcpy(v.data(), P.sel + (int64_t)frame * P.sel_per_frame + L.sel_base, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < cnt; i++) { xyr[3 * i] = orbx_px(v[i]); xyr[3 * i + 1] = orbx_py(v[i]); xyr[3 * i + 2] = orbx_pr(v[i]); }
+	return ORBX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// matching
+// ---------------------------------------------------------------------------------------------------------------
+orbx_status orbx_descriptor_distance(int device, const uint8_t* a, const uint8_t* b, int64_t n, int32_t* dist)
+{
+	if (!a || !b || !dist || n < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (n == 0) return ORBX_OK;
+	CU(cudaSetDevice(device));
+	DevBuf<uint8_t> da, db; DevBuf<int32_t> dd;
+	CU(da.ensure(32 * n)); CU(db.ensure(32 * n)); CU(dd.ensure(n));
+	CU(cudaMemcpy(da.p, a, 32 * n, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(db.p, b, 32 * n, cudaMemcpyHostToDevice));
+	orbx_launch_hamming_pairs(da.p, db.p, n, dd.p, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(dist, dd.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+	da.release(); db.release(); dd.release();
+	return ORBX_OK;
+}
+
+orbx_status orbx_knn2_partial_device(const uint8_t* d_query, int64_t nq, const uint8_t* d_train_shard, int64_t nt_shard,
+                                     int64_t index_base, uint64_t* d_partial, void* stream)
+{
+	if (!d_query || !d_train_shard || !d_partial || nq < 1 || nt_shard < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (index_base + nt_shard > 0xfffffffell) return fail(ORBX_ERR_INVALID, "train index does not fit 32 bits");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int splits = orbx_knn2_splits(nq, nt_shard);
+	if (splits == 1)
+	{
+		orbx_launch_knn2_partial(d_query, nq, d_train_shard, nt_shard, index_base, d_partial, st);
+	}
+	else
+	{
+		// few queries: the shard is scanned in `splits` slices to fill the GPU, then folded to one partial per query
+		uint64_t* tmp = nullptr;
+		CU(cudaMallocAsync(&tmp, sizeof(uint64_t) * (size_t)splits * nq, st));
+		orbx_launch_knn2_partial(d_query, nq, d_train_shard, nt_shard, index_base, tmp, st);
+		orbx_launch_knn2_fold(tmp, splits, nq, d_partial, st);
+		CU(cudaFreeAsync(tmp, st));
+	}
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
+orbx_status orbx_knn2_merge_device(const uint64_t* d_gathered, int ranks, int64_t nq, int th_low, float nnratio,
+                                   int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match, void* stream)
+{
+	if (!d_gathered || ranks < 1 || nq < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	orbx_launch_knn2_merge(d_gathered, ranks, nq, th_low, nnratio, d_idx, d_best, d_second, d_match, (cudaStream_t)stream);
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
+orbx_status orbx_knn2_device(const uint8_t* d_query, int64_t nq, const uint8_t* d_train, int64_t nt, int th_low,
+                             float nnratio, int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match,
+                             void* stream)
+{
+	if (!d_query || !d_train || nq < 1 || nt < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (nt > 0xfffffffell) return fail(ORBX_ERR_INVALID, "train index does not fit 32 bits");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int splits = orbx_knn2_splits(nq, nt);
+	uint64_t* partial = nullptr;
+	CU(cudaMallocAsync(&partial, sizeof(uint64_t) * (size_t)splits * nq, st));
+	orbx_launch_knn2_partial(d_query, nq, d_train, nt, 0, partial, st);
+	orbx_launch_knn2_merge(partial, splits, nq, th_low, nnratio, d_idx, d_best, d_second, d_match, st);
+	CU(cudaGetLastError());
+	CU(cudaFreeAsync(partial, st));
+	return ORBX_OK;
+}
+
+orbx_status orbx_knn2(int device, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int th_low,
+                      float nnratio, int32_t* idx, uint16_t* best, uint16_t* second, int32_t* match)
+{
+	if (!query || !train || nq < 1 || nt < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	CU(cudaSetDevice(device));
+	DevBuf<uint8_t> dq, dt; DevBuf<int32_t> di, dm; DevBuf<uint16_t> db, ds;
+	CU(dq.ensure(32 * nq)); CU(dt.ensure(std::max<int64_t>(32 * nt, 32)));
+	CU(di.ensure(nq)); CU(dm.ensure(nq)); CU(db.ensure(nq)); CU(ds.ensure(nq));
+	CU(cudaMemcpy(dq.p, query, 32 * nq, cudaMemcpyHostToDevice));
+	if (nt) CU(cudaMemcpy(dt.p, train, 32 * nt, cudaMemcpyHostToDevice));
+	orbx_status st = orbx_knn2_device(dq.p, nq, dt.p, nt, th_low, nnratio, di.p, db.p, ds.p, dm.p, nullptr);
+	if (st == ORBX_OK)
+	{
+		CU(cudaDeviceSynchronize());
+		if (idx) CU(cudaMemcpy(idx, di.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+		if (best) CU(cudaMemcpy(best, db.p, sizeof(uint16_t) * nq, cudaMemcpyDeviceToHost));
+		if (second) CU(cudaMemcpy(second, ds.p, sizeof(uint16_t) * nq, cudaMemcpyDeviceToHost));
+		if (match) CU(cudaMemcpy(match, dm.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+	}
+	dq.release(); dt.release(); di.release(); dm.release(); db.release(); ds.release();
+	return st;
+}
+
+orbx_status orbx_stereo_match_device(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* d_uright, float* d_depth)
+{
+	if (!left || !right || !camera || !d_uright || !d_depth) return fail(ORBX_ERR_INVALID, "null argument");
+	if (!left->have_result || !right->have_result) return fail(ORBX_ERR_STATE, "both extractors must have run Extract first");
+	if (left->device != right->device) return fail(ORBX_ERR_INVALID, "left and right extractors live on different devices");
+	if (left->last_frames != right->last_frames || left->pw != right->pw || left->ph != right->ph ||
+	    left->prm.nlevels != right->prm.nlevels || left->last_cap != right->last_cap)
+		return fail(ORBX_ERR_INVALID, "left and right extractions differ in batch size, image size or parameters");
+	CU(cudaSetDevice(left->device));
+	const OrbxPlanDev& PL = left->P; const OrbxPlanDev& PR = right->P;
+	OrbxStereoArgs A;
+	std::memset(&A, 0, sizeof(A));
+	A.frames = left->last_frames; A.cap = left->last_cap; A.nlevels = PL.nlevels;
+	A.kl = left->last_kps; A.dl = left->last_desc; A.nl = left->last_n;
+	A.kr = right->last_kps; A.dr = right->last_desc; A.nr = right->last_n;
+	A.pl0 = PL.l0; A.pl0_pitch = PL.l0_pitch; A.pl0_stride = PL.l0_stride; A.pl = PL.pyr; A.pl_slab = PL.slab;
+	A.pr0 = PR.l0; A.pr0_pitch = PR.l0_pitch; A.pr0_stride = PR.l0_stride; A.pr = PR.pyr; A.pr_slab = PR.slab;
+	for (int s = 0; s < PL.nlevels; s++)
+	{
+		A.lw[s] = PL.lv[s].w; A.lh[s] = PL.lv[s].h; A.lpitch[s] = PL.lv[s].pitch; A.loff[s] = PL.lv[s].offset;
+		A.scale[s] = left->scale[s]; A.inv_scale[s] = left->inv_scale[s];
+	}
+	A.bf = camera->bf; A.baseline = camera->baseline;
+	A.uright = d_uright; A.depth = d_depth;
+	CU(left->st_sad.ensure((size_t)A.frames * A.cap));
+	A.sad = left->st_sad.p;
+	// the right extraction runs on its own stream: order it before the match
+	CU(cudaEventRecord(right->done, right->stream));
+	CU(cudaStreamWaitEvent(left->stream, right->done, 0));
+	orbx_launch_stereo(A, left->stream);
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
+orbx_status orbx_stereo_match(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* uright, float* depth)
+{
+	if (!left || !uright || !depth) return fail(ORBX_ERR_INVALID, "null argument");
+	if (!left->have_result) return fail(ORBX_ERR_STATE, "both extractors must have run Extract first");
+	CU(cudaSetDevice(left->device));
+	const size_t count = (size_t)left->last_frames * left->last_cap;
+	CU(left->st_uright.ensure(count)); CU(left->st_depth.ensure(count));
+	orbx_status st = orbx_stereo_match_device(left, right, camera, left->st_uright.p, left->st_depth.p);
+	if (st != ORBX_OK) return st;
+	CU(cudaMemcpyAsync(uright, left->st_uright.p, sizeof(float) * count, cudaMemcpyDeviceToHost, left->stream));
+	CU(cudaMemcpyAsync(depth, left->st_depth.p, sizeof(float) * count, cudaMemcpyDeviceToHost, left->stream));
+	CU(cudaStreamSynchronize(left->stream));
+	return ORBX_OK;
+}
+
+orbx_status orbx_stereo_match_host(int device, const orbx_keypoint* kps_l, int n_l, const uint8_t* desc_l,
+                                   const uint8_t* const* pyr_l, const orbx_keypoint* kps_r, int n_r,
+                                   const uint8_t* desc_r, const uint8_t* const* pyr_r, const int* level_w,
+                                   const int* level_h, const size_t* level_pitch, int nlevels, const float* scale,
+                                   const float* inv_scale, const orbx_camera* camera, float* uright, float* depth)
+{
+	if (!kps_l || !kps_r || !desc_l || !desc_r || !pyr_l || !pyr_r || !camera || !uright || !depth || n_l < 0 || n_r < 0)
+		return fail(ORBX_ERR_INVALID, "bad argument");
+	if (nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "nlevels must be in [1, 12]");
+	if (n_l >= 65536 || n_r >= 65536) return fail(ORBX_ERR_INVALID, "more than 65535 keypoints");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (n_l == 0) return ORBX_OK;
+	CU(cudaSetDevice(device));
+	const int cap = std::max(n_l, std::max(n_r, 1));
+	OrbxStereoArgs A;
+	std::memset(&A, 0, sizeof(A));
+	A.frames = 1; A.cap = cap; A.nlevels = nlevels;
+	int64_t slab = 0;
+	for (int s = 0; s < nlevels; s++)
+	{
+		A.lw[s] = level_w[s]; A.lh[s] = level_h[s];
+		A.lpitch[s] = (int)align_up(level_w[s], 16);
+		A.loff[s] = slab;
+		slab += (int64_t)A.lpitch[s] * level_h[s];
+		A.scale[s] = scale[s]; A.inv_scale[s] = inv_scale[s];
+	}
+	DevBuf<uint8_t> pl, pr, dl, dr; DevBuf<orbx_keypoint> kl, kr; DevBuf<int32_t> cnt; DevBuf<float> du, dd; DevBuf<int> sad;
+	CU(pl.ensure(slab)); CU(pr.ensure(slab)); CU(dl.ensure((size_t)cap * 32)); CU(dr.ensure((size_t)cap * 32));
+	CU(kl.ensure(cap)); CU(kr.ensure(cap)); CU(cnt.ensure(2)); CU(du.ensure(cap)); CU(dd.ensure(cap)); CU(sad.ensure(cap));
+	for (int s = 0; s < nlevels; s++)
+	{
+		CU(cudaMemcpy2D(pl.p + A.loff[s], A.lpitch[s], pyr_l[s], level_pitch[s], level_w[s], level_h[s], cudaMemcpyHostToDevice));
+		CU(cudaMemcpy2D(pr.p + A.loff[s], A.lpitch[s], pyr_r[s], level_pitch[s], level_w[s], level_h[s], cudaMemcpyHostToDevice));
+	}
+	CU(cudaMemcpy(kl.p, kps_l, sizeof(orbx_keypoint) * n_l, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(dl.p, desc_l, (size_t)32 * n_l, cudaMemcpyHostToDevice));
+	if (n_r)
+	{
+		CU(cudaMemcpy(kr.p, kps_r, sizeof(orbx_keypoint) * n_r, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(dr.p, desc_r, (size_t)32 * n_r, cudaMemcpyHostToDevice));
+	}
+	const int32_t counts[2] = { n_l, n_r };
+	CU(cudaMemcpy(cnt.p, counts, sizeof(counts), cudaMemcpyHostToDevice));
+	A.kl = kl.p; A.dl = dl.p; A.nl = cnt.p; A.kr = kr.p; A.dr = dr.p; A.nr = cnt.p + 1;
+	// level 0 is addressed through the l0 fields, the rest through the slab
+	A.pl0 = pl.p; A.pl0_pitch = A.lpitch[0]; A.pl0_stride = slab; A.pl = pl.p; A.pl_slab = slab;
+	A.pr0 = pr.p; A.pr0_pitch = A.lpitch[0]; A.pr0_stride = slab; A.pr = pr.p; A.pr_slab = slab;
+	A.bf = camera->bf; A.baseline = camera->baseline;
+	A.uright = du.p; A.depth = dd.p; A.sad = sad.p;
+	orbx_launch_stereo(A, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(uright, du.p, sizeof(float) * n_l, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(depth, dd.p, sizeof(float) * n_l, cudaMemcpyDeviceToHost));
+	pl.release(); pr.release(); dl.release(); dr.release(); kl.release(); kr.release(); cnt.release(); du.release(); dd.release(); sad.release();
+	return ORBX_OK;
+}
+
+orbx_status orbx_measure_popc_peak(int device, double* popc_per_second)
+{
+	if (!popc_per_second) return fail(ORBX_ERR_INVALID, "null argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	*popc_per_second = orbx_popc_probe(device);
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
+}  // extern "C"

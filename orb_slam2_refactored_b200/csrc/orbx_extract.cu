@@ -1,0 +1,977 @@
+// sm_100a kernels of the ORB extractor: pyramid, FAST cells, quadtree selection, blur, orientation + rBRIEF.
+// Reference behaviour reproduced (bit-exact): src/ORBextractor.cc:74-140, :402-693, :743-820 and the OpenCV
+// primitives it calls. Integer math only on pixels; every float op that the reference
+// performs is issued with an explicit round-to-nearest intrinsic so that nvcc cannot contract it into an FMA.
+#include "orbx_internal.cuh"
+
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+// =====================================================================================================
+// K1  pyramid_resize_u8 — cv::resize INTER_LINEAR 8UC1 in OpenCV's fixed point for
+//     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
+//     exact float/double operation order; the kernel is integer only. One thread = 4 output pixels.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, const int level)
+{
+	const OrbxLevel& D = P.lv[level];
+	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
+	const int f = blockIdx.z;
+	const int dx0 = (blockIdx.x * 64 + threadIdx.x) * 4;
+	const int dy = blockIdx.y * 4 + threadIdx.y;
+	if (dy >= D.h || dx0 >= D.w)
+		return;
+	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level - 1);
+	const int64_t sp = orbx_level_pitch(P, level - 1);
+	uint8_t* __restrict__ dst = P.pyr + (int64_t)f * P.slab + D.offset;
+
+	const int sy0 = __ldg(P.yofs + D.ytab_base + dy);
+	const short2 b = __ldg(P.ycoef + D.ytab_base + dy);
+	const int sy1 = min(sy0 + 1, sh - 1);
+	const uint8_t* __restrict__ r0 = src + (int64_t)sy0 * sp;
+	const uint8_t* __restrict__ r1 = src + (int64_t)sy1 * sp;
+
+	uint32_t out = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		const int dx = dx0 + j;
+		if (dx < D.w)
+		{
+			const int sx0 = __ldg(P.xofs + D.xtab_base + dx);
+			const short2 a = __ldg(P.xcoef + D.xtab_base + dx);
+			const int sx1 = min(sx0 + 1, sw - 1);
+			const int h0 = (int)__ldg(r0 + sx0) * a.x + (int)__ldg(r0 + sx1) * a.y;
+			const int h1 = (int)__ldg(r1 + sx0) * a.x + (int)__ldg(r1 + sx1) * a.y;
+			int v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+			v = min(max(v, 0), 255);
+			out |= (uint32_t)v << (8 * j);
+		}
+	}
+	*reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx0) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
+}
+
+// =====================================================================================================
+// K2  fast9_cell — DetectFAST (src/ORBextractor.cc:489-540) with cv::FAST(..., nms = true) semantics
+//     (SURVEY App. A.4). One CTA per ~30 px cell: the cell view (cell + 6 px) is staged in shared memory,
+//     the threshold-independent arc score S is computed for the pixels that pass a cheap 4-pair rejection
+//     at minThFAST, local maxima are found once, and the iniTh -> minTh retry is just a second count.
+//     Candidates are emitted row-major into the cell's private slot range, so DetectFAST's cell-major /
+//     row-major push_back order is reproduced without atomics on global memory.
+// =====================================================================================================
+#define FT_TS 80            // tile row stride in bytes (view <= 66 px + up to 3 px alignment slack)
+#define FT_TH 66
+#define FT_SS 64            // score row stride (region <= 60 px + 1 px zero border each side)
+#define FT_MAXR 60
+
+__constant__ int c_ring[16];    // ring offsets inside the shared tile, OpenCV order
+
+__device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c, const int* ring)
+{
+	// v[k] = (ring_k) | (255 - ring_k) << 16; max over an arc of 9 in both halves, then min over the 16 arcs:
+	// lo = min_arcs max_arc ring, hi = 255 - max_arcs min_arc ring. VIMNMX3.U16x2 does 3-input packed max/min.
+	uint32_t v[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++)
+		v[k] = (uint32_t)c[ring[k]] * 0xFFFF0001u + 0x00FF0000u;
+	uint32_t m3[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++)
+		m3[k] = __vimax3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+	uint32_t m9[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++)
+		m9[k] = __vimax3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+	uint32_t a = __vimin3_u16x2(m9[0], m9[1], m9[2]);
+	uint32_t b = __vimin3_u16x2(m9[3], m9[4], m9[5]);
+	uint32_t d = __vimin3_u16x2(m9[6], m9[7], m9[8]);
+	uint32_t e = __vimin3_u16x2(m9[9], m9[10], m9[11]);
+	uint32_t g = __vimin3_u16x2(m9[12], m9[13], m9[14]);
+	a = __vimin3_u16x2(a, b, d);
+	e = __vimin3_u16x2(e, g, m9[15]);
+	a = __vminu2(a, e);
+	const int centre = c[0];
+	const int dark = centre - (int)(a & 0xffffu);            // max_arcs min_arc (centre - ring)
+	const int bright = (255 - (int)(a >> 16)) - centre;      // max_arcs min_arc (ring - centre)
+	return max(dark, bright);
+}
+
+__global__ void __launch_bounds__(256) k_fast_cells(const OrbxPlanDev P)
+{
+	__shared__ __align__(16) uint8_t tile[FT_TH * FT_TS];
+	__shared__ uint8_t score[(FT_MAXR + 2) * FT_SS];
+	__shared__ uint8_t flag[FT_MAXR * FT_MAXR];
+	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
+	__shared__ int s_nlist, s_nhi;
+	__shared__ int s_wcnt[8];
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int cell = blockIdx.x, f = blockIdx.y;
+	int lvl = 0;
+	for (int l = 1; l < P.nlevels; l++)
+		if (cell >= P.lv[l].cell_base) lvl = l;
+	const OrbxLevel& L = P.lv[lvl];
+	const int c = cell - L.cell_base;
+	const int cy = c / L.ncx, cx = c - cy * L.ncx;
+	const int x0 = L.minx + cx * L.cellw, y0 = L.miny + cy * L.cellh;
+	const int x1 = min(x0 + L.cellw + 6, L.maxx), y1 = min(y0 + L.cellh + 6, L.maxy);
+	const int vw = x1 - x0, vh = y1 - y0;      // view
+	const int rw = vw - 6, rh = vh - 6;        // detection region, >= 1 by the reference's loop conditions (:519,521)
+	const int npx = rw * rh;
+
+	// ---- stage the view: aligned 32-bit loads; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
+	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl);
+	const int64_t pitch = orbx_level_pitch(P, lvl);
+	const int sh = x0 & 3;
+	const int nwords = (sh + vw + 3) >> 2;
+	for (int i = tid; i < vh * nwords; i += 256)
+	{
+		const int r = i / nwords, wd = i - r * nwords;
+		const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(img + (int64_t)(y0 + r) * pitch + (x0 - sh)) + wd);
+		*reinterpret_cast<uint32_t*>(tile + r * FT_TS + wd * 4) = v;
+	}
+	for (int i = tid; i < (rh + 2) * FT_SS; i += 256)
+		score[i] = 0;
+	if (tid == 0) { s_nlist = 0; s_nhi = 0; }
+	__syncthreads();
+
+	// ---- phase A: reject with 4 opposite pairs at minTh (every arc of 9 holds one pixel of each pair), then the
+	//      other 4 pairs; survivors are compacted so that phase B runs without divergence
+	const int tmin = P.min_th, tini = P.ini_th;
+	for (int i = tid; i < npx; i += 256)
+	{
+		const int ry = i / rw, rx = i - ry * rw;
+		const uint8_t* p = tile + (ry + 3) * FT_TS + sh + rx + 3;
+		const int cv = p[0], hi = cv + tmin, lo = cv - tmin;
+		bool bright = true, dark = true;
+#pragma unroll
+		for (int k = 0; k < 8; k += 2)
+		{
+			const int a = p[c_ring[k]], b = p[c_ring[k + 8]];
+			bright = bright && (a > hi || b > hi);
+			dark = dark && (a < lo || b < lo);
+		}
+		if (bright || dark)
+		{
+#pragma unroll
+			for (int k = 1; k < 8; k += 2)
+			{
+				const int a = p[c_ring[k]], b = p[c_ring[k + 8]];
+				bright = bright && (a > hi || b > hi);
+				dark = dark && (a < lo || b < lo);
+			}
+			if (bright || dark)
+				list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
+		}
+	}
+	__syncthreads();
+
+	// ---- phase B: exact arc score of the listed pixels
+	const int nlist = s_nlist;
+	for (int j = tid; j < nlist; j += 256)
+	{
+		const int i = list[j];
+		const int ry = i / rw, rx = i - ry * rw;
+		const int s = arc_score_packed(tile + (ry + 3) * FT_TS + sh + rx + 3, c_ring);
+		score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)min(max(s, 0), 255);
+	}
+	__syncthreads();
+
+	// ---- phase C: strict 8-neighbour local maxima (threshold independent), then the retry decision (:526-530):
+	//      survivors at t are {local max, S > t}; use iniTh if that set is non-empty, else minTh.
+	int nhi = 0;
+	for (int j = tid; j < nlist; j += 256)
+	{
+		const int i = list[j];
+		const int ry = i / rw, rx = i - ry * rw;
+		const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
+		const int s = sp[0];
+		uint8_t fl = 0;
+		if (s > tmin)
+		{
+			const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
+			                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
+			if (s > m)
+			{
+				fl = (s > tini) ? 3 : 1;
+				nhi += (s > tini);
+			}
+		}
+		flag[i] = fl;
+	}
+	// pixels never listed have no flag yet: clear them
+	// (cheaper than clearing everything first: flag[] of listed pixels is written exactly once above)
+	if (nhi) atomicAdd(&s_nhi, nhi);
+	__syncthreads();
+	const int want = s_nhi > 0 ? 2 : 1;
+
+	// ---- ordered emit: warp w owns the contiguous row-major pixel range [w*chunk, (w+1)*chunk)
+	// listed-ness is re-derived from score > 0 so flag[] needs no clearing pass
+	const int chunk = ((npx + 7) / 8 + 31) & ~31;
+	const int beg = warp * chunk, end = min(beg + chunk, npx);
+	int cnt = 0;
+	for (int i0 = beg; i0 < end; i0 += 32)
+	{
+		const int i = i0 + lane;
+		bool on = false;
+		if (i < end)
+		{
+			const int ry = i / rw, rx = i - ry * rw;
+			on = score[(ry + 1) * FT_SS + rx + 1] > tmin && (flag[i] & want);
+		}
+		cnt += __popc(__ballot_sync(0xffffffffu, on));
+	}
+	if (lane == 0) s_wcnt[warp] = cnt;
+	__syncthreads();
+	int base = 0, total = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++)
+	{
+		const int v = s_wcnt[w];
+		if (w < warp) base += v;
+		total += v;
+	}
+	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
+	for (int i0 = beg; i0 < end; i0 += 32)
+	{
+		const int i = i0 + lane;
+		bool on = false;
+		int ry = 0, rx = 0, s = 0;
+		if (i < end)
+		{
+			ry = i / rw; rx = i - ry * rw;
+			s = score[(ry + 1) * FT_SS + rx + 1];
+			on = s > tmin && (flag[i] & want);
+		}
+		const unsigned bal = __ballot_sync(0xffffffffu, on);
+		if (on)
+			out[base + __popc(bal & lanemask_lt())] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
+		base += __popc(bal);
+	}
+	if (tid == 0)
+		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
+}
+
+// =====================================================================================================
+// K3+K4  quadtree_select — QuadTreeSuppression + QTreeNode::divide (src/ORBextractor.cc:402-453, :542-693)
+//     in pass form (executable spec: oracle/orb_oracle.cc quadtree()). One CTA per
+//     (level, frame). A node owns a contiguous segment of packed candidates; dividing a node is a stable
+//     4-way partition of its segment into the other ping-pong buffer (one warp per node). The std::list is
+//     an array rebuilt every pass: [children of this pass in reverse push order] ++ [old list minus divided
+//     nodes]. Phase 2's std::sort (unstable, libstdc++ introsort) is replayed step for step by one thread,
+//     because its order among equal sizes decides which nodes are split before the quota break (:666-667).
+// =====================================================================================================
+#define QT_THREADS 256
+#define QT_WARPS 8
+
+struct QNode
+{
+	uint16_t x0, y0, x1, y1;
+	uint32_t beg;
+	uint32_t cnt;     // bit 31: which ping-pong buffer holds the segment
+};
+#define QN_CNT(n) ((n).cnt & 0x7fffffffu)
+#define QN_BUF(n) ((n).cnt >> 31)
+
+template <class Pred, class Emit>
+__device__ __forceinline__ int block_ordered(int n, int* s_w, Pred pred, Emit emit)
+{
+	// calls emit(i, rank) for every i in [0,n) with pred(i), rank = number of earlier true elements. Uniform result.
+	const int tid = threadIdx.x, warp = tid >> 5;
+	int base = 0;
+	for (int c0 = 0; c0 < n; c0 += QT_THREADS)
+	{
+		const int i = c0 + tid;
+		const bool p = (i < n) && pred(i);
+		const unsigned bal = __ballot_sync(0xffffffffu, p);
+		if ((tid & 31) == 0) s_w[warp] = __popc(bal);
+		__syncthreads();
+		int wbase = 0, tot = 0;
+#pragma unroll
+		for (int w = 0; w < QT_WARPS; w++)
+		{
+			const int v = s_w[w];
+			if (w < warp) wbase += v;
+			tot += v;
+		}
+		if (p) emit(i, base + wbase + __popc(bal & lanemask_lt()));
+		base += tot;
+		__syncthreads();
+	}
+	return base;
+}
+
+template <class Get, class Put>
+__device__ __forceinline__ int block_exscan(int n, int* s_w, Get get, Put put)
+{
+	// put(i, exclusive prefix of get) for i in [0,n); returns the total. Uniform result.
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	int base = 0;
+	for (int c0 = 0; c0 < n; c0 += QT_THREADS)
+	{
+		const int i = c0 + tid;
+		const int v = (i < n) ? get(i) : 0;
+		int inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const int t = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += t;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		int wbase = 0, tot = 0;
+#pragma unroll
+		for (int w = 0; w < QT_WARPS; w++)
+		{
+			const int t = s_w[w];
+			if (w < warp) wbase += t;
+			tot += t;
+		}
+		if (i < n) put(i, base + wbase + inc - v);
+		base += tot;
+		__syncthreads();
+	}
+	return base;
+}
+
+// ---- libstdc++ (GCC 13) std::sort with comp(a,b) = a.size > b.size, on 64-bit items (size << 32 | position)
+// /usr/include/c++/13/bits/stl_algo.h:85-104, 1792-1950; SURVEY App. E. Single thread, shared memory.
+__device__ __forceinline__ bool qs_before(uint64_t a, uint64_t b) { return (uint32_t)(a >> 32) > (uint32_t)(b >> 32); }
+__device__ __forceinline__ void qs_swap(uint64_t* a, int i, int j) { const uint64_t t = a[i]; a[i] = a[j]; a[j] = t; }
+
+__device__ void qs_sift(uint64_t* a, int first, int hole, int len, uint64_t v)
+{
+	const int top = hole;
+	int child = hole;
+	while (child < (len - 1) / 2)
+	{
+		child = 2 * (child + 1);
+		if (qs_before(a[first + child], a[first + child - 1])) child--;
+		a[first + hole] = a[first + child];
+		hole = child;
+	}
+	if ((len & 1) == 0 && child == (len - 2) / 2)
+	{
+		child = 2 * (child + 1);
+		a[first + hole] = a[first + child - 1];
+		hole = child - 1;
+	}
+	int parent = (hole - 1) / 2;
+	while (hole > top && qs_before(a[first + parent], v))
+	{
+		a[first + hole] = a[first + parent];
+		hole = parent;
+		parent = (hole - 1) / 2;
+	}
+	a[first + hole] = v;
+}
+
+__device__ void qs_heapsort(uint64_t* a, int first, int last)
+{
+	const int len = last - first;
+	if (len < 2) return;
+	for (int parent = (len - 2) / 2;; parent--)
+	{
+		qs_sift(a, first, parent, len, a[first + parent]);
+		if (parent == 0) break;
+	}
+	for (int end = last; end - first > 1;)
+	{
+		--end;
+		const uint64_t v = a[end];
+		a[end] = a[first];
+		qs_sift(a, first, 0, end - first, v);
+	}
+}
+
+__device__ __forceinline__ void qs_linear_insert(uint64_t* a, int last)
+{
+	const uint64_t v = a[last];
+	int next = last - 1;
+	while (qs_before(v, a[next])) { a[last] = a[next]; last = next; --next; }
+	a[last] = v;
+}
+
+__device__ void qs_insertion(uint64_t* a, int first, int last)
+{
+	if (first == last) return;
+	for (int i = first + 1; i != last; ++i)
+	{
+		if (qs_before(a[i], a[first]))
+		{
+			const uint64_t v = a[i];
+			for (int p = i; p != first; --p) a[p] = a[p - 1];
+			a[first] = v;
+		}
+		else qs_linear_insert(a, i);
+	}
+}
+
+__device__ void qs_sort(uint64_t* a, int n)
+{
+	if (n == 0) return;
+	int lg = 0;
+	for (int m = n; m > 1; m >>= 1) ++lg;
+	// introsort loop with an explicit stack (recursion on the right part, iteration on the left)
+	int st_first[48], st_last[48], st_depth[48];
+	int sp = 0;
+	st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
+	while (sp > 0)
+	{
+		--sp;
+		int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+		while (last - first > 16)
+		{
+			if (depth == 0) { qs_heapsort(a, first, last); break; }
+			--depth;
+			const int mid = first + (last - first) / 2;
+			{   // __move_median_to_first(first, first+1, mid, last-1)
+				const int r = first, x = first + 1, y = mid, z = last - 1;
+				if (qs_before(a[x], a[y]))
+				{
+					if (qs_before(a[y], a[z])) qs_swap(a, r, y);
+					else if (qs_before(a[x], a[z])) qs_swap(a, r, z);
+					else qs_swap(a, r, x);
+				}
+				else if (qs_before(a[x], a[z])) qs_swap(a, r, x);
+				else if (qs_before(a[y], a[z])) qs_swap(a, r, z);
+				else qs_swap(a, r, y);
+			}
+			int lo = first + 1, hi = last;
+			const uint64_t pivot_key = a[first];   // the pivot stays at a[first] during the partition
+			for (;;)
+			{
+				while (qs_before(a[lo], pivot_key)) ++lo;
+				--hi;
+				while (qs_before(pivot_key, a[hi])) --hi;
+				if (!(lo < hi)) break;
+				qs_swap(a, lo, hi);
+				++lo;
+			}
+			// right part [lo, last) is sorted "recursively" before the left part continues; the two ranges are
+			// disjoint, so deferring it on the stack yields the same result
+			st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp;
+			last = lo;
+		}
+	}
+	if (n > 16)
+	{
+		qs_insertion(a, 0, 16);
+		for (int i = 16; i != n; ++i) qs_linear_insert(a, i);
+	}
+	else qs_insertion(a, 0, n);
+}
+
+__device__ __forceinline__ int quadrant_of(uint32_t v, int xm, int ym)
+{
+	const int x = orbx_px(v), y = orbx_py(v);
+	return x < xm ? (y < ym ? 0 : 2) : (y < ym ? 1 : 3);
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off)
+{
+	extern __shared__ __align__(16) uint8_t qsm[];
+	const int M = P.node_cap;
+	QNode* listA = reinterpret_cast<QNode*>(qsm);
+	QNode* listB = listA + M;
+	uint64_t* items = reinterpret_cast<uint64_t*>(listB + M);          // phase-2 sort items
+	uint32_t* childcnt = reinterpret_cast<uint32_t*>(items + M);       // [M][4]
+	uint32_t* proc = childcnt + 4 * M;                                 // positions (old list) to divide, processing order
+	uint32_t* pbase = proc + M;                                        // exclusive scan of non-empty child counts
+	uint8_t* gone = reinterpret_cast<uint8_t*>(pbase + M);               // old-list positions removed by this pass
+	__shared__ int s_w[QT_WARPS];
+	__shared__ int s_K;
+	__shared__ int s_rootcnt[ORBX_MAX_ROOTS];
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lvl = blockIdx.x, f = blockIdx.y;
+	const OrbxLevel& L = P.lv[lvl];
+	const int ncell = L.ncx * L.ncy;
+	const int* __restrict__ ccount = P.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
+	int* __restrict__ coff = cell_off + (int64_t)f * P.cells_per_frame + L.cell_base;
+	const uint32_t* __restrict__ slots = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base;
+	uint32_t* buf0 = P.qbuf0 + (int64_t)f * P.cand_per_frame + L.cand_base;
+	uint32_t* buf1 = P.qbuf1 + (int64_t)f * P.cand_per_frame + L.cand_base;
+
+	// ---- K3: cell-major compaction of the candidate slots (DetectFAST's push_back order, :532-537)
+	const int n = block_exscan(ncell, s_w, [&](int i) { return ccount[i]; }, [&](int i, int off) { coff[i] = off; });
+	if (tid == 0) P.cand_count[(int64_t)f * P.nlevels + lvl] = n;
+	__syncthreads();
+	const int nroots = L.n_roots;
+	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
+	for (int cidx = warp; cidx < ncell; cidx += QT_WARPS)
+	{
+		const int cnt = ccount[cidx], off = coff[cidx];
+		const uint32_t* src = slots + (int64_t)cidx * L.cell_cap;
+		for (int k = lane; k < cnt; k += 32) gathered[off + k] = src[k];
+	}
+	__syncthreads();
+	if (n == 0)
+	{
+		if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = 0;    // early return of :544-545 (dst == src stays empty)
+		return;
+	}
+
+	// ---- roots (:547-581): vertical strips; candidate -> strip by the host-built table (double arithmetic there)
+	const int* __restrict__ rootx = P.root_x + L.root_base;
+	const uint8_t* __restrict__ rlut = P.root_lut + L.rootlut_base;
+	if (nroots == 1)
+	{
+		if (tid == 0) s_rootcnt[0] = n;
+	}
+	else
+	{
+		int at = 0;
+		for (int r = 0; r < nroots; r++)
+		{
+			const int c = block_ordered(n, s_w, [&](int i) { return rlut[orbx_px(buf1[i])] == r; },
+			                            [&](int i, int rank) { buf0[at + rank] = buf1[i]; });
+			if (tid == 0) s_rootcnt[r] = c;
+			at += c;
+		}
+	}
+	__syncthreads();
+	int listLen = 0;
+	{
+		int at = 0;
+		for (int r = 0; r < nroots; r++)
+		{
+			const int c = s_rootcnt[r];
+			if (c > 0)
+			{
+				if (tid == 0)
+				{
+					QNode nd;
+					nd.x0 = (uint16_t)rootx[r]; nd.y0 = (uint16_t)L.miny; nd.x1 = (uint16_t)rootx[r + 1]; nd.y1 = (uint16_t)L.maxy;
+					nd.beg = (uint32_t)at; nd.cnt = (uint32_t)c;     // buffer 0
+					listA[listLen] = nd;
+				}
+				listLen++;
+			}
+			at += c;
+		}
+	}
+	__syncthreads();
+
+	QNode* cur = listA;
+	QNode* nxt = listB;
+	const int quota = L.quota;
+	int phase = 1, lastP = 0;
+	for (;;)
+	{
+		// ---- which nodes does this pass divide, and in which order
+		int np;
+		if (phase == 1)
+		{
+			// every divisible node, list order (:588-631)
+			np = block_ordered(listLen, s_w, [&](int i) { return QN_CNT(cur[i]) > 1; }, [&](int i, int rank) { proc[rank] = i; });
+		}
+		else
+		{
+			// children of the previous pass with > 1 point, in push order (= back to front of the first lastP list
+			// entries), sorted by size descending with libstdc++'s tie order (:635-643)
+			np = block_ordered(lastP, s_w, [&](int g) { return QN_CNT(cur[lastP - 1 - g]) > 1; },
+			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
+			__syncthreads();
+			if (tid == 0) qs_sort(items, np);
+			__syncthreads();
+			for (int i = tid; i < np; i += QT_THREADS) proc[i] = (uint32_t)(items[i] & 0xffffffffu);
+		}
+		for (int i = tid; i < listLen; i += QT_THREADS) gone[i] = 0;
+		__syncthreads();
+
+		// ---- divide (speculatively all of them; Phase 2 may stop early, parents stay intact in their buffer)
+		for (int t = warp; t < np; t += QT_WARPS)
+		{
+			const QNode nd = cur[proc[t]];
+			const int cnt = (int)QN_CNT(nd);
+			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
+			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
+			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
+			int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+			for (int i0 = 0; i0 < cnt; i0 += 32)
+			{
+				const int i = i0 + lane;
+				const bool ok = i < cnt;
+				const int q = ok ? quadrant_of(src[i], xm, ym) : -1;
+				c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
+				c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+				c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
+				c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+			}
+			int a0 = 0, a1 = c0, a2 = c0 + c1, a3 = c0 + c1 + c2;
+			for (int i0 = 0; i0 < cnt; i0 += 32)
+			{
+				const int i = i0 + lane;
+				const bool ok = i < cnt;
+				const uint32_t v = ok ? src[i] : 0u;
+				const int q = ok ? quadrant_of(v, xm, ym) : -1;
+				const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+				const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+				const unsigned lt = lanemask_lt();
+				if (q == 0) dst[a0 + __popc(b0 & lt)] = v;
+				else if (q == 1) dst[a1 + __popc(b1 & lt)] = v;
+				else if (q == 2) dst[a2 + __popc(b2 & lt)] = v;
+				else if (q == 3) dst[a3 + __popc(b3 & lt)] = v;
+				a0 += __popc(b0); a1 += __popc(b1); a2 += __popc(b2); a3 += __popc(b3);
+			}
+			if (lane == 0)
+			{
+				childcnt[4 * t + 0] = c0; childcnt[4 * t + 1] = c1; childcnt[4 * t + 2] = c2; childcnt[4 * t + 3] = c3;
+			}
+		}
+		__syncthreads();
+
+		// ---- how many of them are really processed: Phase 2 breaks once the list reaches the quota (:666-667)
+		auto nkids = [&](int t) { return (int)(childcnt[4 * t] > 0) + (int)(childcnt[4 * t + 1] > 0) + (int)(childcnt[4 * t + 2] > 0) + (int)(childcnt[4 * t + 3] > 0); };
+		const int totalPush = block_exscan(np, s_w, nkids, [&](int t, int ex) { pbase[t] = ex; });
+		int K = np, Ppush = totalPush;
+		if (phase == 2)
+		{
+			if (tid == 0) s_K = np;
+			__syncthreads();
+			// list length after processing t+1 items = listLen + pbase[t] + nkids(t) - (t+1); non-decreasing in t
+			for (int t = tid; t < np; t += QT_THREADS)
+			{
+				const int after = listLen + (int)pbase[t] + nkids(t) - (t + 1);
+				const int before = listLen + (int)pbase[t] - t;
+				if (after >= quota && before < quota) s_K = t + 1;
+			}
+			__syncthreads();
+			K = s_K;
+			Ppush = (K < np) ? (int)pbase[K] : totalPush;
+			__syncthreads();
+		}
+
+		// ---- rebuild the list: children in reverse push order, then the surviving old nodes in old order
+		for (int t = tid; t < K; t += QT_THREADS)
+		{
+			const int pos = proc[t];
+			gone[pos] = 1;
+			const QNode nd = cur[pos];
+			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+			const uint32_t nb = (QN_BUF(nd) ^ 1u) << 31;
+			uint32_t at = nd.beg;
+			int g = (int)pbase[t];
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const uint32_t c = childcnt[4 * t + q];
+				if (c > 0)
+				{
+					QNode ch;
+					ch.x0 = (q & 1) ? (uint16_t)xm : nd.x0; ch.x1 = (q & 1) ? nd.x1 : (uint16_t)xm;
+					ch.y0 = (q & 2) ? (uint16_t)ym : nd.y0; ch.y1 = (q & 2) ? nd.y1 : (uint16_t)ym;
+					ch.beg = at; ch.cnt = c | nb;
+					nxt[Ppush - 1 - g] = ch;
+					g++;
+				}
+				at += c;
+			}
+		}
+		__syncthreads();
+		const int kept = block_ordered(listLen, s_w, [&](int i) { return gone[i] == 0; }, [&](int i, int rank) { nxt[Ppush + rank] = cur[i]; });
+		const int newLen = Ppush + kept;
+		{ QNode* t = cur; cur = nxt; nxt = t; }
+		const int prevLen = listLen;
+		listLen = newLen;
+		lastP = Ppush;
+		__syncthreads();
+		if (listLen >= quota || listLen == prevLen)
+			break;
+		if (phase == 1)
+		{
+			// toExpand = children of this pass with > 1 point (:617-622); switch to largest-first near the quota (:633-634)
+			const int ndiv = block_ordered(lastP, s_w, [&](int i) { return QN_CNT(cur[i]) > 1; }, [&](int, int) {});
+			if (listLen + 3 * ndiv > quota) phase = 2;
+		}
+	}
+
+	// ---- keep the best response of every node, first wins ties, list order (:677-692)
+	uint32_t* __restrict__ sel = P.sel + (int64_t)f * P.sel_per_frame + L.sel_base;
+	for (int i = warp; i < listLen; i += QT_WARPS)
+	{
+		const QNode nd = cur[i];
+		const int cnt = (int)QN_CNT(nd);
+		const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
+		int bestr = 0, besti = 0x7fffffff;
+		for (int k = lane; k < cnt; k += 32)
+		{
+			const int r = orbx_pr(src[k]);
+			if (r > bestr) { bestr = r; besti = k; }
+		}
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1)
+		{
+			const int orr = __shfl_xor_sync(0xffffffffu, bestr, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
+			if (orr > bestr || (orr == bestr && oi < besti)) { bestr = orr; besti = oi; }
+		}
+		if (lane == 0) sel[i] = src[besti];
+	}
+	if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = listLen;
+}
+
+// =====================================================================================================
+// K6  gauss7x7_u8 — cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's 8.8 fixed point
+//     (src/ORBextractor.cc:799). Tile 128 x 32 with a 3 px halo in shared memory.
+// =====================================================================================================
+#define GB_TW 128
+#define GB_TH 32
+#define GB_RW (GB_TW + 6)
+#define GB_RS 144
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+	if (i < 0) i = -i;
+	if (i >= n) i = 2 * n - 2 - i;
+	return i;
+}
+
+__global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int level)
+{
+	__shared__ uint8_t raw[(GB_TH + 6) * GB_RS];
+	__shared__ uint16_t hb[(GB_TH + 6) * GB_TW];
+	const OrbxLevel& L = P.lv[level];
+	const int f = blockIdx.z, tid = threadIdx.x;
+	const int x0 = blockIdx.x * GB_TW, y0 = blockIdx.y * GB_TH;
+	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level);
+	const int64_t sp = orbx_level_pitch(P, level);
+	uint8_t* __restrict__ dst = P.blur + (int64_t)f * P.slab + L.offset;
+
+	for (int i = tid; i < (GB_TH + 6) * GB_RW; i += 256)
+	{
+		const int r = i / GB_RW, c = i - r * GB_RW;
+		const int gy = reflect101(min(y0 + r - 3, L.h + 2), L.h), gx = reflect101(min(x0 + c - 3, L.w + 2), L.w);
+		raw[r * GB_RS + c] = __ldg(src + (int64_t)gy * sp + gx);
+	}
+	__syncthreads();
+	for (int i = tid; i < (GB_TH + 6) * GB_TW; i += 256)
+	{
+		const int r = i / GB_TW, c = i - r * GB_TW;
+		const uint8_t* p = raw + r * GB_RS + c;
+		hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+	}
+	__syncthreads();
+	const int c = tid & (GB_TW - 1), rbase = (tid >> 7) * (GB_TH / 2);
+	if (x0 + c < L.w)
+	{
+#pragma unroll 4
+		for (int rr = 0; rr < GB_TH / 2; rr++)
+		{
+			const int r = rbase + rr;
+			if (y0 + r >= L.h) break;
+			const uint16_t* p = hb + r * GB_TW + c;
+			const int v = 18 * ((int)p[0] + p[6 * GB_TW]) + 34 * ((int)p[GB_TW] + p[5 * GB_TW]) + 48 * ((int)p[2 * GB_TW] + p[4 * GB_TW]) + 56 * (int)p[3 * GB_TW];
+			dst[(int64_t)(y0 + r) * L.pitch + x0 + c] = (uint8_t)((v + 32768) >> 16);
+		}
+	}
+}
+
+// =====================================================================================================
+// K5+K7  orient_describe — IC_Angle (src/ORBextractor.cc:74-101) on the un-blurred level, then
+//     ComputeOrbDescriptor (:103-140) on the blurred level, then the keypoint record of Extract (:768-773,
+//     :811-815). One warp per output keypoint. Float path pinned per SURVEY H2 / App. A.6-A.7.
+// =====================================================================================================
+__constant__ int c_umax[ORBX_HALF_PATCH + 1];
+__constant__ signed char c_pattern[1024];
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+	const float R2D = (float)(180.0 / 3.14159265358979323846);
+	const float p1 = __fmul_rn(0.9997878412794807f, R2D), p3 = __fmul_rn(-0.3258083974640975f, R2D);
+	const float p5 = __fmul_rn(0.1555786518463281f, R2D), p7 = __fmul_rn(-0.04432655554792128f, R2D);
+	const float eps = (float)2.2204460492503131e-16;
+	const float ax = fabsf(x), ay = fabsf(y);
+	float a, c, c2;
+	if (ax >= ay)
+	{
+		c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+		c2 = __fmul_rn(c, c);
+		a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+	}
+	else
+	{
+		c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+		c2 = __fmul_rn(c, c);
+		a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+	}
+	if (x < 0.f) a = __fsub_rn(180.f, a);
+	if (y < 0.f) a = __fsub_rn(360.f, a);
+	return a;
+}
+
+__global__ void __launch_bounds__(256) k_orient_describe(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps,
+                                                         uint8_t* __restrict__ d_desc, int32_t* __restrict__ d_n)
+{
+	__shared__ uint32_t s_pat[256];      // pair p -> (x0,y0,x1,y1) int8x4, transposed so lane reads are conflict-free
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int f = blockIdx.y;
+	{
+		const int p = tid;   // 256 pairs
+		const uint32_t w = (uint32_t)(uint8_t)c_pattern[4 * p] | ((uint32_t)(uint8_t)c_pattern[4 * p + 1] << 8) |
+		                   ((uint32_t)(uint8_t)c_pattern[4 * p + 2] << 16) | ((uint32_t)(uint8_t)c_pattern[4 * p + 3] << 24);
+		s_pat[(p & 7) * 32 + (p >> 3)] = w;    // byte b = p>>3 handles pairs 8b..8b+7; stored at [bit][byte]
+	}
+	__syncthreads();
+
+	// which level does output slot `slot` belong to (levels are concatenated in order, :792-819)
+	const int slot = blockIdx.x * 8 + warp;
+	const int* __restrict__ cnt = P.sel_count + (int64_t)f * P.nlevels;
+	int lvl = -1, start = 0, total = 0;
+	for (int l = 0; l < P.nlevels; l++)
+	{
+		const int c = cnt[l];
+		if (lvl < 0 && slot < total + c) { lvl = l; start = total; }
+		total += c;
+	}
+	if (slot == 0 && lane == 0) d_n[f] = total;
+	if (lvl < 0 || slot >= P.out_cap)
+		return;
+	const OrbxLevel& L = P.lv[lvl];
+	const uint32_t kp = P.sel[(int64_t)f * P.sel_per_frame + L.sel_base + (slot - start)];
+	const int x = orbx_px(kp), y = orbx_py(kp), resp = orbx_pr(kp);
+
+	// ---- intensity centroid over the radius-15 disc: lane = column u in [-15,15]
+	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl) + (int64_t)y * orbx_level_pitch(P, lvl) + x;
+	const int64_t ip = orbx_level_pitch(P, lvl);
+	int m10 = 0, m01 = 0;
+	const int u = lane - ORBX_HALF_PATCH;
+	if (lane < 31)
+	{
+		const int au = abs(u);
+#pragma unroll 1
+		for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++)
+		{
+			if (au <= c_umax[abs(v)])
+			{
+				const int val = __ldg(img + (int64_t)v * ip + u);
+				m10 += u * val;
+				m01 += v * val;
+			}
+		}
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+		m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+	}
+	const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+	// ---- steered BRIEF: lane = descriptor byte, 8 pairs each
+	const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
+	const float arad = __fmul_rn(angle, factorPI);
+	const float ca = __double2float_rn(cos((double)arad)), sb = __double2float_rn(sin((double)arad));
+	const uint8_t* __restrict__ bl = P.blur + (int64_t)f * P.slab + L.offset + (int64_t)y * L.pitch + x;
+	const int bp = L.pitch;
+	uint32_t byte = 0;
+#pragma unroll
+	for (int bit = 0; bit < 8; bit++)
+	{
+		const uint32_t w = s_pat[bit * 32 + lane];
+		const float x0 = (float)(signed char)(w & 0xff), y0 = (float)(signed char)((w >> 8) & 0xff);
+		const float x1 = (float)(signed char)((w >> 16) & 0xff), y1 = (float)(signed char)(w >> 24);
+		const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
+		const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
+		const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
+		const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
+		const int t0 = __ldg(bl + r0 * bp + q0), t1 = __ldg(bl + r1 * bp + q1);
+		byte |= (uint32_t)(t0 < t1) << bit;
+	}
+	d_desc[((int64_t)f * P.out_cap + slot) * 32 + lane] = (uint8_t)byte;
+
+	if (lane == 0)
+	{
+		orbx_keypoint o;
+		o.x = (float)x; o.y = (float)y;
+		if (lvl > 0) { o.x = __fmul_rn(o.x, L.scale); o.y = __fmul_rn(o.y, L.scale); }   // :811-815
+		o.size = __fmul_rn(L.scale, (float)ORBX_PATCH);                                    // :771
+		o.angle = angle;
+		o.response = (float)resp;
+		o.octave = lvl;
+		o.class_id = -1;
+		d_kps[(int64_t)f * P.out_cap + slot] = o;
+	}
+}
+
+}  // namespace
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+cudaError_t orbx_upload_pattern()
+{
+	static const signed char pattern[1024] = {
+#include "orb_pattern.inc"
+	};
+	// umax_ of ORBextractor::Init (src/ORBextractor.cc:705-718)
+	int umax[ORBX_HALF_PATCH + 1];
+	const int vmax = (int)floor(ORBX_HALF_PATCH * sqrt(2.) / 2 + 1);
+	const int vmin = (int)ceil(ORBX_HALF_PATCH * sqrt(2.) / 2);
+	for (int v = 0; v <= vmax; ++v)
+		umax[v] = (int)lrint(sqrt((double)(ORBX_HALF_PATCH * ORBX_HALF_PATCH - v * v)));
+	for (int v = ORBX_HALF_PATCH, v0 = 0; v >= vmin; --v)
+	{
+		while (umax[v0] == umax[v0 + 1]) ++v0;
+		umax[v] = v0;
+		++v0;
+	}
+	static const int rdx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
+	static const int rdy[16] = { 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3 };
+	int ring[16];
+	for (int k = 0; k < 16; k++) ring[k] = rdy[k] * FT_TS + rdx[k];
+	cudaError_t e;
+	if ((e = cudaMemcpyToSymbol(c_pattern, pattern, sizeof(pattern))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(c_ring, ring, sizeof(ring))) != cudaSuccess) return e;
+	return cudaSuccess;
+}
+
+void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
+{
+	const OrbxLevel& D = P.lv[level];
+	dim3 block(64, 4), grid((D.w + 255) / 256, (D.h + 3) / 4, P.frames);
+	k_pyramid_resize<<<grid, block, 0, st>>>(P, level);
+}
+
+void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
+{
+	dim3 grid(P.cells_per_frame, P.frames);
+	k_fast_cells<<<grid, 256, 0, st>>>(P);
+}
+
+size_t orbx_quadtree_smem(int node_cap)
+{
+	// listA, listB (16 B), items (8 B), childcnt (16 B), proc, pbase (4 B each), gone (1 B)
+	return (size_t)node_cap * (16 + 16 + 8 + 16 + 4 + 4 + 1) + 64;
+}
+
+void orbx_launch_quadtree(const OrbxPlanDev& P, cudaStream_t st)
+{
+	const size_t smem = orbx_quadtree_smem(P.node_cap);
+	cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 grid(P.nlevels, P.frames);
+	// cell offsets live right behind the cell counts (the plan allocates 2x)
+	k_quadtree<<<grid, QT_THREADS, smem, st>>>(P, P.cell_count + (int64_t)P.frames * P.cells_per_frame);
+}
+
+void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
+{
+	for (int s = 0; s < P.nlevels; s++)
+	{
+		const OrbxLevel& L = P.lv[s];
+		dim3 grid((L.w + GB_TW - 1) / GB_TW, (L.h + GB_TH - 1) / GB_TH, P.frames);
+		k_gauss7<<<grid, 256, 0, st>>>(P, s);
+	}
+}
+
+void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st)
+{
+	dim3 grid((P.out_cap + 7) / 8, P.frames);
+	k_orient_describe<<<grid, 256, 0, st>>>(P, d_kps, d_desc, d_n);
+}

@@ -1,0 +1,107 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI host layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbx.h"
+
+#define ORBX_MAX_LEVELS 12
+#define ORBX_MAX_ROOTS 16
+#define ORBX_BORDER 16          // EDGE_THRESHOLD - 3, src/ORBextractor.cc:755
+#define ORBX_EDGE 19            // EDGE_THRESHOLD, :70
+#define ORBX_CELL 30            // CELL_SIZE, :491
+#define ORBX_HALF_PATCH 15      // HALF_PATCH_SIZE, :69
+#define ORBX_PATCH 31           // PATCH_SIZE, :68
+
+// Packed FAST candidate: x[0:12) | y[12:24) | response[24:32). Level coordinates; limits w,h <= 4096.
+__host__ __device__ inline uint32_t orbx_pack(int x, int y, int r) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24); }
+__host__ __device__ inline int orbx_px(uint32_t v) { return (int)(v & 0xfffu); }
+__host__ __device__ inline int orbx_py(uint32_t v) { return (int)((v >> 12) & 0xfffu); }
+__host__ __device__ inline int orbx_pr(uint32_t v) { return (int)(v >> 24); }
+
+// One pyramid level of the plan. All offsets are per frame.
+struct OrbxLevel
+{
+	int w, h, pitch;             // pixels, bytes
+	int64_t offset;              // byte offset of the level inside a frame slab
+	// FAST cell grid (src/ORBextractor.cc:489-540)
+	int minx, miny, maxx, maxy;  // roi
+	int ncx, ncy, cellw, cellh;  // cells actually visited, nominal cell size
+	int cell_base;               // first cell (of the frame's cell array) belonging to this level
+	int cell_cap;                // candidate slots per cell: ceil(cellw/2)*ceil(cellh/2), exact worst case of strict NMS
+	int cand_base, cand_cap;     // slot range of the level in the frame's candidate arrays
+	// quadtree (:542-693)
+	int quota, n_roots;
+	int root_base;               // offset of the n_roots+1 strip bounds in d_root_x
+	int rootlut_base;            // offset of the per-x root id table in d_root_lut
+	int sel_base, sel_cap;       // range of the level in the frame's selected-keypoint array
+	// resize tables of this level as destination (level >= 1)
+	int xtab_base, ytab_base;
+	float scale;                 // scaleFactors_[s]
+};
+
+struct OrbxPlanDev
+{
+	int nlevels, frames;
+	int ini_th, min_th;
+	int cells_per_frame, cand_per_frame, sel_per_frame;
+	int node_cap;                // max list length of the quadtree over all levels (+ margin)
+	int out_cap;                 // keypoint slots per frame in the output arrays
+	OrbxLevel lv[ORBX_MAX_LEVELS];
+	// level 0 may alias the caller's device buffer
+	const uint8_t* l0; int64_t l0_pitch, l0_stride;
+	uint8_t* pyr; uint8_t* blur; int64_t slab;         // frame slabs (levels >= 1 of pyr; all levels of blur)
+	uint32_t* cand;              // [frames][cand_per_frame] per-cell slots
+	int* cell_count;             // [frames][cells_per_frame]
+	uint32_t* qbuf0; uint32_t* qbuf1;   // [frames][cand_per_frame] quadtree ping-pong segments
+	int* cand_count;             // [frames][nlevels] DetectFAST totals (debug/probes)
+	uint32_t* sel;               // [frames][sel_per_frame] selected keypoints, list order
+	int* sel_count;              // [frames][nlevels]
+	const int* root_x; const uint8_t* root_lut;
+	const int* xofs; const short2* xcoef; const int* yofs; const short2* ycoef;   // resize tables
+};
+
+__device__ __forceinline__ const uint8_t* orbx_level_ptr(const OrbxPlanDev& P, int frame, int level)
+{
+	if (level == 0)
+		return P.l0 + (int64_t)frame * P.l0_stride;
+	return P.pyr + (int64_t)frame * P.slab + P.lv[level].offset;
+}
+__device__ __forceinline__ int64_t orbx_level_pitch(const OrbxPlanDev& P, int level)
+{
+	return level == 0 ? P.l0_pitch : (int64_t)P.lv[level].pitch;
+}
+
+// kernel launchers (orbx_extract.cu)
+void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_quadtree(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
+size_t orbx_quadtree_smem(int node_cap);
+cudaError_t orbx_upload_pattern();
+
+// matcher launchers (orbx_match.cu)
+void orbx_launch_hamming_pairs(const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, cudaStream_t st);
+void orbx_launch_knn2_partial(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int64_t base, uint64_t* partial,
+                              cudaStream_t st);
+void orbx_launch_knn2_fold(const uint64_t* parts, int nparts, int64_t nq, uint64_t* packed, cudaStream_t st);
+void orbx_launch_knn2_merge(const uint64_t* gathered, int ranks, int64_t nq, int th_low, float nnratio, int32_t* idx,
+                            uint16_t* best, uint16_t* second, int32_t* match, cudaStream_t st);
+
+struct OrbxStereoArgs
+{
+	int frames, cap, nlevels;
+	const orbx_keypoint* kl; const uint8_t* dl; const int32_t* nl;   // [frames][cap]
+	const orbx_keypoint* kr; const uint8_t* dr; const int32_t* nr;
+	// pyramids: level pointers per frame are base + frame*stride + offset[level]
+	const uint8_t* pl0; int64_t pl0_pitch, pl0_stride; const uint8_t* pl; int64_t pl_slab;
+	const uint8_t* pr0; int64_t pr0_pitch, pr0_stride; const uint8_t* pr; int64_t pr_slab;
+	int lw[ORBX_MAX_LEVELS], lh[ORBX_MAX_LEVELS], lpitch[ORBX_MAX_LEVELS]; int64_t loff[ORBX_MAX_LEVELS];
+	float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS];
+	float bf, baseline;
+	float* uright; float* depth;      // [frames][cap]
+	int* sad;                         // [frames][cap] scratch: SAD of kept matches, -1 otherwise
+};
+void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st);
+double orbx_popc_probe(int device);

@@ -1,0 +1,103 @@
+"""CPU tests: the stand-alone restatement against the reference's own translation units (oracle/_ref), live, on more
+inputs than the golden files hold. Skipped where neither /root/reference nor a prebuilt oracle/_ref exists."""
+import numpy as np
+import pytest
+
+from orb_slam2_refactored_b200 import synth
+
+
+@pytest.mark.parametrize('cfg,seeds', [('C1', (1, 2)), ('C2', (3,)), ('C3', (4,))])
+def test_extract_equal(oracle_port, oracle_ref, cfg, seeds):
+    c = synth.CONFIGS[cfg]
+    a, b = oracle_ref.extractor(c['nfeatures']), oracle_port.extractor(c['nfeatures'])
+    for seed in seeds:
+        img = synth.image(seed, c['w'], c['h'])
+        ka, da = a.extract(img); kb, db = b.extract(img)
+        assert ka.tobytes() == kb.tobytes() and np.array_equal(da, db)
+        for pa, pb in zip(a.pyramid(), b.pyramid()):
+            assert np.array_equal(pa, pb)
+
+
+def test_quadtree_tie_order_and_quotas(oracle_port, oracle_ref):
+    # many quotas on the same candidates: exercises Phase 1 / Phase 2 switches, the std::sort tie order and the break
+    img = synth.image(11, 640, 480)
+    cand = oracle_ref.detect_fast(img)
+    assert len(cand) > 1500
+    for quota in (0, 1, 2, 5, 17, 60, 100, 217, 333, 500, 1000, 1500, len(cand), len(cand) + 50):
+        a = oracle_ref.quadtree(cand, 640, 480, quota); b = oracle_port.quadtree(cand, 640, 480, quota)
+        assert a.tobytes() == b.tobytes(), quota
+    # a wide image has several root strips (cvRound(w/h) = 4)
+    img = synth.image(12, 1241, 376)
+    cand = oracle_ref.detect_fast(img)
+    for quota in (3, 50, 434, 2000):
+        a = oracle_ref.quadtree(cand, 1241, 376, quota); b = oracle_port.quadtree(cand, 1241, 376, quota)
+        assert a.tobytes() == b.tobytes(), quota
+
+
+def test_sort_restatement_including_heapsort_fallback():
+    # oracle/orb_oracle.cc restates libstdc++'s introsort; its heapsort fallback only triggers on adversarial input.
+    # Build such input through the quadtree is impractical, so the restatement is exercised through a tiny probe
+    # program compiled on the fly against std::sort itself.
+    import os, subprocess, tempfile, textwrap
+    src = textwrap.dedent(r'''
+        #include <algorithm>
+        #include <cstdio>
+        #include <random>
+        #include <vector>
+        #define ORACLE_SORT_PROBE
+        #include "orb_oracle.cc"
+        int main() {
+            std::mt19937 rng(5); long bad = 0, cases = 0;
+            for (int trial = 0; trial < 4000; trial++) {
+                int n = 1 + rng() % (trial % 40 == 0 ? 5000 : 300);
+                std::vector<SortItem> a(n);
+                int mode = trial % 4;
+                for (int i = 0; i < n; i++) {
+                    int key = mode == 0 ? 2 + (int)(rng() % 6) : mode == 1 ? i : mode == 2 ? n - i : (int)(rng() % 100000);
+                    a[i] = { key, i };
+                }
+                if (trial % 97 == 0) {   // median-of-3 killer: forces depth exhaustion -> heapsort
+                    for (int i = 0; i < n; i++) a[i].size = (i % 2 == 0) ? i / 2 : n / 2 + i / 2;
+                }
+                std::vector<SortItem> b = a;
+                std::sort(a.begin(), a.end(), [](const SortItem& x, const SortItem& y) { return x.size > y.size; });
+                libstdcxx_sort_desc(b);
+                bool same = true;
+                for (int i = 0; i < n; i++) same &= a[i].node == b[i].node;
+                bad += !same; cases++;
+            }
+            printf("%ld %ld\n", cases, bad);
+            return bad != 0;
+        }''')
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle')
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, 'probe.cc')
+        open(f, 'w').write(src.replace('namespace {', 'namespace {', 1))
+        exe = os.path.join(d, 'probe')
+        subprocess.run(['g++', '-std=c++14', '-O2', '-ffp-contract=off', '-I', here, '-I', os.path.join(here, 'cvshim'), f,
+                        os.path.join(here, 'cv_primitives.cc'), '-o', exe, '-lpthread'], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout
+        assert r.stdout.split()[1] == '0'
+
+
+def test_stereo_equal(oracle_port, oracle_ref):
+    c = synth.CONFIGS['C3']
+    for seed, noise in ((0, 3), (1, 0)):
+        L, R = synth.stereo_pair(seed, c['w'], c['h'], noise=noise)
+        eL, eR = oracle_ref.extractor(c['nfeatures']), oracle_ref.extractor(c['nfeatures'])
+        kl, dl = eL.extract(L); kr, dr = eR.extract(R)
+        sc, inv, _, _ = eL.tables()
+        a = oracle_ref.stereo(kl, dl, eL.pyramid(), kr, dr, eR.pyramid(), sc, inv, c['camera'])
+        b = oracle_port.stereo(kl, dl, eL.pyramid(), kr, dr, eR.pyramid(), sc, inv, c['camera'])
+        assert a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes()
+
+
+def test_knn2_and_distance_equal(oracle_port, oracle_ref):
+    q, t = synth.planted_descriptors(2, 200, 2500)
+    a = oracle_ref.knn2(q, t, 50, 0.6); b = oracle_port.knn2(q, t, 50, 0.6, threads=3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    for i in range(50):
+        assert oracle_ref.descriptor_distance(q[i], t[i]) == oracle_port.descriptor_distance(q[i], t[i]) == \
+            int(np.unpackbits(q[i] ^ t[i]).sum())
