@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: ORB extraction frames/s at 640x480 / 1000 keypoints
+(BASELINE.json configs[0], TUM1.yaml settings: scale 1.2, 8 levels, FAST 20/7), plus Hamming kNN Gpairs/s on the
+per-GPU share of configs[4] (1 M queries x 1.25 M train rows per GPU, train-sharded, NCCL all-gather merge at N > 1).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code on the host cores
+
+A step = one pass of the extractor over one batch of synthetic frames per GPU. One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from orb_slam2_refactored_b200 import synth  # noqa: E402
+
+W, H, NFEATURES = 640, 480, 1000
+METRIC = 'ORB extract frames/s @640x480 1000kp'
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def make_frames(n, seed0):
+    """n distinct synthetic frames from 24 generated base frames (vertical flips / row rolls keep the statistics)."""
+    base = [synth.image(seed0 + s, W, H) for s in range(min(n, 24))]
+    out = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        b = base[i % len(base)]
+        k = i // len(base)
+        out[i] = b if k == 0 else np.roll(b[::-1] if k & 1 else b, 37 * k, axis=0)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation on the host cores (oracle/_ref when it was built, else the restatement)
+# ---------------------------------------------------------------------------------------------------------------------
+def load_cpu_reference():
+    from oracle import bindings
+    try:
+        bindings.build()
+    except Exception as e:   # no compiler on the box: use what travelled
+        log('oracle build skipped:', e)
+    for kind, native in (('ref', True), ('ref', False), ('port', True), ('port', False)):
+        try:
+            return bindings.Oracle(kind, native=native), ('reference' if kind == 'ref' else 'port'), native
+        except (FileNotFoundError, OSError):
+            continue
+    raise RuntimeError('no CPU oracle library available')
+
+
+def cpu_extract_rate(o, frames, threads, per_thread):
+    """frames/s of Extract with one frame per thread at a time (the reference runs left/right on 2 threads,
+    src/System.cc:449-452); steady_clock around the calls as the example drivers do (mono_tum.cc:81-88)."""
+    exs = [o.extractor(NFEATURES) for _ in range(threads)]
+    for t in range(threads):
+        exs[t].extract(frames[t % len(frames)])      # warm-up
+    done = [0] * threads
+
+    def work(t):
+        for i in range(per_thread):
+            exs[t].extract(frames[(t * per_thread + i) % len(frames)])
+            done[t] += 1
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th: x.start()
+    for x in th: x.join()
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, dt
+
+
+def cpu_knn_rate(o, threads, nq=4096, nt=250000):
+    q = synth.descriptors(1, nq); t = synth.descriptors(2, nt)
+    o.knn2(q[:64], t[:1000], 50, 0.6, threads=1)
+    t0 = time.perf_counter()
+    o.knn2(q, t, 50, 0.6, threads=threads)
+    dt = time.perf_counter() - t0
+    return nq * nt / dt / 1e9, dt, f'{nq} queries x {nt} train rows, {threads} threads'
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    o, kind, native = load_cpu_reference()
+    threads = os.cpu_count() or 1
+    frames = make_frames(max(24, threads), 0)
+    per_thread = 2
+    for _ in range(args.warmup):
+        cpu_extract_rate(o, frames, threads, 1)
+    t_all, n_all = 0.0, 0
+    for _ in range(args.steps):
+        r, dt = cpu_extract_rate(o, frames, threads, per_thread)
+        t_all += dt; n_all += threads * per_thread
+    fps = n_all / t_all
+    gp, _, knn_sample = cpu_knn_rate(o, threads)
+    sample = f'{threads * per_thread} frames per step ({per_thread} per thread), {args.steps} steps'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': 'C1: ORBextractor::Extract on synthetic 640x480 gray frames, 1000 kp, scale 1.2, 8 levels, FAST 20/7',
+                   'library': os.path.relpath(o.path, ROOT), 'flags': '-O3 -march=x86-64-v3' if native else '-O2 -ffp-contract=off',
+                   'note': 'reference TUs compiled where they lie; OpenCV primitives are this repo\'s scalar restatements (no OpenCV on the box)'},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': kind, 'sample': sample},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'knn': {'value': gp, 'unit': 'Gpairs/s', 'sample': knn_sample, 'cores': threads},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# this repository's arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from orb_slam2_refactored_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    api.lib()     # fails loudly if the CUDA library is missing
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    B = args.batch
+    NB = 4                                     # rotating input batches: 4 x B x 300 KiB > 126 MB L2 for B >= 128
+    host = make_frames(B * 2, 1000 * rank)     # two distinct pinned host batches for the end-to-end leg
+    pinned = [torch.from_numpy(host[i * B:(i + 1) * B].copy()).pin_memory() for i in range(2)]
+    d_batches = []
+    for i in range(NB):
+        src = pinned[i % 2]
+        d = src.to(dev)
+        if i >= 2:
+            d = torch.roll(d, shifts=53 * i, dims=1).contiguous()
+        d_batches.append(d)
+
+    ex = api.ORBextractor(nfeatures=NFEATURES, device=local_rank)
+    cap = None
+    stream = torch.cuda.ExternalStream(ex.stream(), device=dev)
+    outs = None
+
+    def step(i):
+        nonlocal outs
+        if outs is None:
+            outs = ex.extract_batch_device(d_batches[i % NB])
+        else:
+            ex.extract_batch_device(d_batches[i % NB], *outs)
+
+    # ---- device-resident throughput
+    barrier()      # inputs were produced on torch's stream; the extractor runs on its own
+    for i in range(args.warmup):
+        step(i)
+    ex.synchronize()
+    ex.enable_stage_timing(True)
+    ex.stage_times()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    e1.synchronize()
+    t1 = time.time()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    stage_ms, calls = ex.stage_times()
+    ex.enable_stage_timing(False)
+    frames_total = world * B * args.steps
+    fps = frames_total / (ms * 1e-3)
+
+    # keypoint counts of the last step, for the algorithmic byte count
+    n_last = outs[2].cpu().numpy()
+    n_mean = float(n_last.mean())
+    sizes = ex.level_sizes()
+    S = sum(w * h for w, h in sizes); P0 = sizes[0][0] * sizes[0][1]; P7 = sizes[-1][0] * sizes[-1][1]
+    alg = {'pyramid': 2 * S - P0 - P7, 'fast': S, 'blur': 2 * S, 'describe': 1321 * n_mean, 'quadtree': 0.0}
+    b_alg = 5 * S - P0 - P7 + 1321 * n_mean
+    per_step = {k: v / max(calls, 1) for k, v in stage_ms.items()}
+    dominant = max(per_step, key=per_step.get)
+    launches_per_stage = {'pyramid': len(sizes) - 1, 'fast': 1, 'quadtree': 1, 'blur': len(sizes), 'describe': 1}
+    # roofline of the dominant stage, per launch: its algorithmic bytes for the whole batch / its device time
+    dom_bytes_per_step = alg[dominant] * B
+    dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': dom_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'launches_per_step': launches_per_stage[dominant],
+                'algorithmic_bytes_per_launch': dom_bytes_per_step / launches_per_stage[dominant],
+                'avg_launch_ms': per_step[dominant] / launches_per_stage[dominant],
+                'stages_ms_per_step': per_step,
+                'stages_gbs': {k: (alg[k] * B / (per_step[k] * 1e-3) / 1e9 if per_step[k] > 0 else None) for k in per_step},
+                'frame': {'algorithmic_bytes_per_frame': b_alg, 'achieved': b_alg * fps / world / 1e9, 'frac': b_alg * fps / world / 1e9 / hbm_peak}}
+
+    # ---- end to end through the public host-buffer API: pinned H2D of the frames, D2H of keypoints + descriptors
+    kcap = ex.max_keypoints()
+    kps_h = torch.empty((B, kcap, 28), dtype=torch.uint8).pin_memory().numpy()
+    desc_h = torch.empty((B, kcap, 32), dtype=torch.uint8).pin_memory().numpy()
+    n_h = np.zeros(B, np.int32)
+    import ctypes as C
+
+    def e2e_step(i):
+        a = pinned[i % 2].numpy()
+        api._check(api.lib().orbx_extract_batch(ex._h, C.c_void_p(a.ctypes.data), B, W, H, W, W * H, C.c_void_p(kps_h.ctypes.data),
+                                                C.c_void_p(desc_h.ctypes.data), kcap, C.c_void_p(n_h.ctypes.data)))
+    for i in range(max(1, min(args.warmup, 2))):
+        e2e_step(i)
+    e2e_steps = max(2, min(args.steps, 10))
+    barrier()
+    e0.record(stream)
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_fps = world * B * e2e_steps / (ms_e2e * 1e-3)
+    h2d = B * W * H
+    d2h = int(n_h.sum()) * 60 + 4 * B
+
+    # ---- kNN: per-GPU share of configs[4]
+    knn = None
+    launches_knn = 0
+    if not args.skip_knn:
+        nq, nt = args.knn_queries, args.knn_train_per_gpu
+        g = torch.Generator(device=dev); g.manual_seed(1234)
+        dq = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)     # queries replicated on every rank
+        g.manual_seed(99 + rank)
+        dt = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)     # this rank's train shard
+        m = api.ORBmatcher(0.6, device=local_rank)
+        gathered = torch.empty((world, nq), dtype=torch.int64, device=dev) if world > 1 else None
+        part = torch.empty(nq, dtype=torch.int64, device=dev)
+
+        def knn_step():
+            if world == 1:
+                return m.knn2_device(dq, dt)
+            api.knn2_partial_device(dq, dt, rank * nt, part)
+            dist.all_gather_into_tensor(gathered.view(-1), part)
+            return api.knn2_merge_device(gathered, world, nq, 50, 0.6)
+        knn_step()
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.knn_steps):
+            res = knn_step()
+        k1.record()
+        k1.synchronize()
+        barrier()
+        ms_knn = max_over_ranks(k0.elapsed_time(k1)) / args.knn_steps
+        gpairs = nq * (nt * world) / (ms_knn * 1e-3) / 1e9
+        popc_peak = api.measure_popc_peak(local_rank)
+        knn = {'value': gpairs, 'unit': 'Gpairs/s', 'ms_per_step': ms_knn, 'steps': args.knn_steps,
+               'workload': f'C5 share: {nq} queries x {nt} train rows per GPU ({nt * world} total), uniform random 256-bit descriptors',
+               'roofline': {'bound': 'popc', 'achieved': 8 * gpairs / world * 1e9, 'peak': popc_peak, 'unit': 'POPC.32/s',
+                            'frac': 8 * gpairs / world * 1e9 / popc_peak,
+                            'peak_source': 'orbx_measure_popc_peak (register-operand POPC loop on all SMs, same run)'},
+               'accepted_matches': int((res[3] >= 0).sum().item())}
+        launches_knn = args.knn_steps * (2 if world == 1 else 2)
+        # end to end on a bounded sample through the host-buffer API (uploads queries + train, downloads results)
+        if world == 1:
+            sq, st = 65536, min(nt, 1 << 20)
+            hq = dq[:sq].cpu().numpy(); ht = dt[:st].cpu().numpy()
+            m.knn2(hq[:1024], ht[:4096])
+            t0k = time.perf_counter()
+            m.knn2(hq, ht)
+            dtk = time.perf_counter() - t0k
+            knn['e2e'] = {'value': sq * st / dtk / 1e9, 'unit': 'Gpairs/s', 'h2d_bytes_per_step': 32 * (sq + st), 'd2h_bytes_per_step': 12 * sq,
+                          'sample': f'{sq} x {st} through orbx_knn2 (pageable host buffers, allocation included)'}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        try:
+            o, kind, native = load_cpu_reference()
+            threads = os.cpu_count() or 1
+            per_thread = 12
+            r, dt_cpu = cpu_extract_rate(o, host[:48], threads, per_thread)
+            cpu = {'value': r, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
+                   'sample': f'{threads * per_thread} frames of the same workload, one frame per thread at a time, {dt_cpu:.1f} s, '
+                             f'{os.path.relpath(o.path, ROOT)} ({"-O3 -march=x86-64-v3" if native else "-O2"}; OpenCV primitives restated scalar)'}
+            if knn is not None:
+                gp, dtk, smp = cpu_knn_rate(o, threads)
+                knn['cpu_baseline'] = {'value': gp, 'unit': 'Gpairs/s', 'cores': threads, 'kind': kind, 'sample': smp}
+        except Exception as e:   # the baseline is reported, never load-bearing
+            cpu = {'value': None, 'unit': 'frames/s', 'cores': 0, 'kind': 'port', 'sample': f'unavailable: {e}'}
+
+    if rank == 0:
+        launches = args.steps * sum(launches_per_stage.values()) + launches_knn
+        line = {
+            'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+            'data': 'synthetic',
+            'config': {'workload': 'C1: ORBextractor::Extract on synthetic 640x480 gray frames, 1000 kp, scale 1.2, 8 levels, FAST 20/7',
+                       'frames_per_step_per_gpu': B, 'keypoints_per_frame': n_mean, 'parallelism': f'frames sharded over {world} GPU(s), no data-path collective',
+                       'l2': f'inputs larger than L2: {NB} rotating device batches of {B} frames ({NB * B * W * H / 1e6:.0f} MB) + {B * 2.1:.0f} MB of pyramid/blur slabs per step'},
+            'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                    'api': 'orbx_extract_batch (pinned host frames in, keypoints + descriptors out)'},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+            'knn': knn,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
+    ap.add_argument('--knn-steps', type=int, default=2)
+    ap.add_argument('--knn-queries', type=int, default=1000000)
+    ap.add_argument('--knn-train-per-gpu', type=int, default=1250000)
+    ap.add_argument('--skip-knn', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

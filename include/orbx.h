@@ -103,6 +103,13 @@ orbx_status orbx_synchronize(orbx_handle h);
 /* the handle's cudaStream_t, as void* */
 void* orbx_stream(orbx_handle h);
 
+/* Per-stage device time, for roofline accounting (bench.py). While enabled, every extract call brackets its stages with
+ * CUDA events on the handle's stream; orbx_stage_times waits for the stream and returns the SUM over the calls since the
+ * last query, in milliseconds: [0] pyramid (levels 1..n-1), [1] FAST cells, [2] quadtree selection, [3] blur, [4] orientation +
+ * descriptor; *calls = number of extract calls summed. */
+orbx_status orbx_enable_stage_timing(orbx_handle h, int enable);
+orbx_status orbx_stage_times(orbx_handle h, float ms_sum[5], int* calls);
+
 /* ORBextractor::GetImagePyramid() — include/ORBextractor.h:63. The pyramid of the last extract call stays on
  * the device; a level is downloaded only on request. Valid until the next extract on this handle. */
 orbx_status orbx_level_size(orbx_handle h, int level, int* width, int* height);

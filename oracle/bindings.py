@@ -23,12 +23,16 @@ class Camera(C.Structure):
     _fields_ = [(n, C.c_float) for n in ('fx', 'fy', 'cx', 'cy', 'bf', 'baseline')]
 
 
-def build(native=False):
-    """Compile the oracle libraries (port always; ref only where /root/reference is present)."""
-    targets = ['port'] + (['ref'] if os.path.isdir('/root/reference/src') else [])
+def build(native=True):
+    """Compile the oracle libraries: the restatement always, the reference's own TUs only where /root/reference is
+    present (elsewhere the prebuilt oracle/_ref/*.so that travelled with the snapshot is used). native=True also
+    builds the -O3 timing variants used by bench.py's CPU baseline."""
+    have_ref = os.path.isdir('/root/reference/src')
+    targets = ['port'] + (['ref'] if have_ref else [])
     if native:
-        targets = ['_build/liborb_oracle_native.so'] + (['_ref/liborb_ref_native.so'] if os.path.isdir('/root/reference/src') else [])
-        targets = [os.path.join(HERE, t) for t in targets]
+        targets += [os.path.join(HERE, '_build', 'liborb_oracle_native.so')]
+        if have_ref:
+            targets += [os.path.join(HERE, '_ref', 'liborb_ref_native.so')]
     subprocess.run(['make', '-s', '-C', HERE] + targets, check=True)
 
 

@@ -59,6 +59,8 @@ _SIGNATURES = {
     'orbx_max_keypoints': (C.c_int, [C.c_void_p]),
     'orbx_synchronize': (C.c_int, [C.c_void_p]),
     'orbx_stream': (C.c_void_p, [C.c_void_p]),
+    'orbx_enable_stage_timing': (C.c_int, [C.c_void_p, C.c_int]),
+    'orbx_stage_times': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     'orbx_level_size': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'orbx_pyramid_level': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     'orbx_pyramid_level_device': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -214,6 +216,25 @@ class ORBextractor:
                                                C.c_void_p(d_kps.data_ptr()), C.c_void_p(d_desc.data_ptr()), cap, C.c_void_p(d_n.data_ptr())))
         self._last_frames = F
         return d_kps, d_desc, d_n
+
+    STAGES = ('pyramid', 'fast', 'quadtree', 'blur', 'describe')
+
+    def enable_stage_timing(self, on=True):
+        _check(lib().orbx_enable_stage_timing(self._h, int(on)))
+
+    def stage_times(self):
+        """(dict stage -> summed ms, number of extract calls) since the last query; waits for the stream."""
+        ms = np.zeros(5, np.float32); calls = C.c_int()
+        _check(lib().orbx_stage_times(self._h, _p(ms), C.byref(calls)))
+        return dict(zip(self.STAGES, [float(v) for v in ms])), calls.value
+
+    def level_sizes(self):
+        out = []
+        for s in range(self.param_.nlevels):
+            w, h = C.c_int(), C.c_int()
+            _check(lib().orbx_level_size(self._h, s, C.byref(w), C.byref(h)))
+            out.append((w.value, h.value))
+        return out
 
     def synchronize(self):
         _check(lib().orbx_synchronize(self._h))

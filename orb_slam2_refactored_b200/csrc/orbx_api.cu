@@ -93,6 +93,9 @@ struct orbx_extractor
 	DevBuf<int32_t> out_n;
 	DevBuf<float> st_uright, st_depth;
 	DevBuf<int> st_sad;
+	bool stage_timing = false;
+	std::vector<cudaEvent_t> ev_pool;   // 6 events per timed extract call
+	size_t ev_used = 0;
 	bool have_result = false;
 	int last_frames = 0, last_cap = 0;
 	const orbx_keypoint* last_kps = nullptr;
@@ -275,11 +278,29 @@ orbx_status enqueue_extract(orbx_extractor* h, const uint8_t* l0, int64_t l0_pit
 	OrbxPlanDev& P = h->P;
 	P.l0 = l0; P.l0_pitch = l0_pitch; P.l0_stride = l0_stride;
 	P.out_cap = cap;      // stride of the output arrays for this call (>= sel_per_frame)
+	cudaEvent_t* ev = nullptr;
+	if (h->stage_timing)
+	{
+		while (h->ev_pool.size() < h->ev_used + 6)
+		{
+			cudaEvent_t e;
+			CU(cudaEventCreate(&e));
+			h->ev_pool.push_back(e);
+		}
+		ev = h->ev_pool.data() + h->ev_used;
+		h->ev_used += 6;
+	}
+	if (ev) CU(cudaEventRecord(ev[0], h->stream));
 	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, h->stream);
+	if (ev) CU(cudaEventRecord(ev[1], h->stream));
 	orbx_launch_fast(P, h->stream);
+	if (ev) CU(cudaEventRecord(ev[2], h->stream));
 	orbx_launch_quadtree(P, h->stream);
+	if (ev) CU(cudaEventRecord(ev[3], h->stream));
 	orbx_launch_blur(P, h->stream);
+	if (ev) CU(cudaEventRecord(ev[4], h->stream));
 	orbx_launch_describe(P, d_kps, d_desc, d_n, h->stream);
+	if (ev) CU(cudaEventRecord(ev[5], h->stream));
 	CU(cudaGetLastError());
 	h->have_result = true;
 	h->last_frames = P.frames; h->last_cap = P.out_cap;
@@ -343,6 +364,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release();
+	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -394,6 +416,32 @@ orbx_status orbx_synchronize(orbx_handle h)
 }
 
 void* orbx_stream(orbx_handle h) { return h ? (void*)h->stream : nullptr; }
+
+orbx_status orbx_enable_stage_timing(orbx_handle h, int enable)
+{
+	if (!h) return fail(ORBX_ERR_INVALID, "null handle");
+	h->stage_timing = enable != 0;
+	return ORBX_OK;
+}
+
+orbx_status orbx_stage_times(orbx_handle h, float ms_sum[5], int* calls)
+{
+	if (!h || !ms_sum) return fail(ORBX_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	for (int i = 0; i < 5; i++) ms_sum[i] = 0.f;
+	const size_t n = h->ev_used / 6;
+	for (size_t c = 0; c < n; c++)
+		for (int i = 0; i < 5; i++)
+		{
+			float ms = 0.f;
+			CU(cudaEventElapsedTime(&ms, h->ev_pool[6 * c + i], h->ev_pool[6 * c + i + 1]));
+			ms_sum[i] += ms;
+		}
+	if (calls) *calls = (int)n;
+	h->ev_used = 0;
+	return ORBX_OK;
+}
 
 orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int frames, int width, int height,
                                       size_t pitch, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,

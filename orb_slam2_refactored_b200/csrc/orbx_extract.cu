@@ -8,7 +8,6 @@
 
 namespace {
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
 // =====================================================================================================
@@ -67,17 +66,19 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 #define FT_TH 66
 #define FT_SS 64            // score row stride (region <= 60 px + 1 px zero border each side)
 #define FT_MAXR 60
+#define FT_THREADS 128
 
-__constant__ int c_ring[16];    // ring offsets inside the shared tile, OpenCV order
-
-__device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c, const int* ring)
+__device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 {
-	// v[k] = (ring_k) | (255 - ring_k) << 16; max over an arc of 9 in both halves, then min over the 16 arcs:
-	// lo = min_arcs max_arc ring, hi = 255 - max_arcs min_arc ring. VIMNMX3.U16x2 does 3-input packed max/min.
+	// Ring offsets inside the shared tile, OpenCV order; compile-time so every load is [base + imm].
+	constexpr int R[16] = { 3 * FT_TS, 3 * FT_TS + 1, 2 * FT_TS + 2, FT_TS + 3, 3, -FT_TS + 3, -2 * FT_TS + 2, -3 * FT_TS + 1,
+	                        -3 * FT_TS, -3 * FT_TS - 1, -2 * FT_TS - 2, -FT_TS - 3, -3, FT_TS - 3, 2 * FT_TS - 2, 3 * FT_TS - 1 };
+	// v[k] = ring_k | (255 - ring_k) << 16 (one IMAD); max over an arc of 9 in both halves, then min over the 16 arcs:
+	// lo = min_arcs max_arc ring, hi = 255 - max_arcs min_arc ring. VIMNMX3.U16x2 is a 3-input packed max/min.
 	uint32_t v[16];
 #pragma unroll
 	for (int k = 0; k < 16; k++)
-		v[k] = (uint32_t)c[ring[k]] * 0xFFFF0001u + 0x00FF0000u;
+		v[k] = (uint32_t)c[R[k]] * 0xFFFF0001u + 0x00FF0000u;
 	uint32_t m3[16];
 #pragma unroll
 	for (int k = 0; k < 16; k++)
@@ -100,14 +101,15 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c, c
 	return max(dark, bright);
 }
 
-__global__ void __launch_bounds__(256) k_fast_cells(const OrbxPlanDev P)
+// One CTA (4 warps) per cell. Phases: stage view -> arc score S of every region pixel (dense: on textured frames a third
+// of the pixels pass any cheap rejection at minTh, so a branch-free network on all of them is cheaper than test + compaction)
+// -> strict 8-neighbour local maxima, which are threshold independent: survivors at t are {local max, S > t}; the retry of
+// :526-530 is therefore "use iniTh if that set is non-empty, else minTh" -> ordered emit.
+__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 {
 	__shared__ __align__(16) uint8_t tile[FT_TH * FT_TS];
-	__shared__ uint8_t score[(FT_MAXR + 2) * FT_SS];
-	__shared__ uint8_t flag[FT_MAXR * FT_MAXR];
-	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
-	__shared__ int s_nlist, s_nhi;
-	__shared__ int s_wcnt[8];
+	__shared__ __align__(4) uint8_t score[(FT_MAXR + 2) * FT_SS];
+	__shared__ int s_wsum[FT_THREADS / 32];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int cell = blockIdx.x, f = blockIdx.y;
@@ -122,135 +124,100 @@ __global__ void __launch_bounds__(256) k_fast_cells(const OrbxPlanDev P)
 	const int vw = x1 - x0, vh = y1 - y0;      // view
 	const int rw = vw - 6, rh = vh - 6;        // detection region, >= 1 by the reference's loop conditions (:519,521)
 	const int npx = rw * rh;
+	// floor(i / n) == (i * ((1 << 20) / n + 1)) >> 20 for n <= 64, i < 4096 (checked exhaustively): no integer division in loops
+	const uint32_t inv_rw = (1u << 20) / (uint32_t)rw + 1u;
 
 	// ---- stage the view: aligned 32-bit loads; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
 	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl);
 	const int64_t pitch = orbx_level_pitch(P, lvl);
 	const int sh = x0 & 3;
 	const int nwords = (sh + vw + 3) >> 2;
-	for (int i = tid; i < vh * nwords; i += 256)
+	const uint32_t inv_nw = (1u << 20) / (uint32_t)nwords + 1u;
+	const uint8_t* __restrict__ src0 = img + (int64_t)y0 * pitch + (x0 - sh);
+	for (int i = tid; i < vh * nwords; i += FT_THREADS)
 	{
-		const int r = i / nwords, wd = i - r * nwords;
-		const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(img + (int64_t)(y0 + r) * pitch + (x0 - sh)) + wd);
+		const int r = (int)(((uint32_t)i * inv_nw) >> 20), wd = i - r * nwords;
+		const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src0 + (int64_t)r * pitch) + wd);
 		*reinterpret_cast<uint32_t*>(tile + r * FT_TS + wd * 4) = v;
 	}
-	for (int i = tid; i < (rh + 2) * FT_SS; i += 256)
-		score[i] = 0;
-	if (tid == 0) { s_nlist = 0; s_nhi = 0; }
+	// zero frame around the scores (neighbours outside the detection region count as 0)
+	if (tid < FT_SS / 4)
+	{
+		reinterpret_cast<uint32_t*>(score)[tid] = 0;
+		reinterpret_cast<uint32_t*>(score + (rh + 1) * FT_SS)[tid] = 0;
+	}
+	for (int i = tid; i < rh; i += FT_THREADS)
+	{
+		score[(i + 1) * FT_SS] = 0;
+		score[(i + 1) * FT_SS + rw + 1] = 0;
+	}
 	__syncthreads();
 
-	// ---- phase A: reject with 4 opposite pairs at minTh (every arc of 9 holds one pixel of each pair), then the
-	//      other 4 pairs; survivors are compacted so that phase B runs without divergence
+	// ---- arc score of every region pixel
+	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
+	for (int i = tid; i < npx; i += FT_THREADS)
+	{
+		const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
+		const int s = arc_score_packed(t0 + ry * FT_TS + rx);
+		score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
+	}
+	__syncthreads();
+
+	// ---- local maxima of this thread's contiguous row-major run of pixels; results stay in two bit masks
 	const int tmin = P.min_th, tini = P.ini_th;
-	for (int i = tid; i < npx; i += 256)
+	const int chunk = (npx + FT_THREADS - 1) / FT_THREADS;        // <= 29
+	const int beg = tid * chunk, end = min(beg + chunk, npx);
+	uint32_t mlo = 0, mhi = 0;
 	{
-		const int ry = i / rw, rx = i - ry * rw;
-		const uint8_t* p = tile + (ry + 3) * FT_TS + sh + rx + 3;
-		const int cv = p[0], hi = cv + tmin, lo = cv - tmin;
-		bool bright = true, dark = true;
-#pragma unroll
-		for (int k = 0; k < 8; k += 2)
+		int ry = (int)(((uint32_t)beg * inv_rw) >> 20), rx = beg - ry * rw;
+		for (int j = 0; beg + j < end; j++)
 		{
-			const int a = p[c_ring[k]], b = p[c_ring[k + 8]];
-			bright = bright && (a > hi || b > hi);
-			dark = dark && (a < lo || b < lo);
-		}
-		if (bright || dark)
-		{
-#pragma unroll
-			for (int k = 1; k < 8; k += 2)
+			const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
+			const int s = sp[0];
+			if (s > tmin)
 			{
-				const int a = p[c_ring[k]], b = p[c_ring[k + 8]];
-				bright = bright && (a > hi || b > hi);
-				dark = dark && (a < lo || b < lo);
+				const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
+				                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
+				if (s > m)
+				{
+					mlo |= 1u << j;
+					if (s > tini) mhi |= 1u << j;
+				}
 			}
-			if (bright || dark)
-				list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
+			if (++rx == rw) { rx = 0; ++ry; }
 		}
 	}
-	__syncthreads();
+	const int any_hi = __syncthreads_or(mhi != 0);
+	uint32_t selm = any_hi ? mhi : mlo;
 
-	// ---- phase B: exact arc score of the listed pixels
-	const int nlist = s_nlist;
-	for (int j = tid; j < nlist; j += 256)
-	{
-		const int i = list[j];
-		const int ry = i / rw, rx = i - ry * rw;
-		const int s = arc_score_packed(tile + (ry + 3) * FT_TS + sh + rx + 3, c_ring);
-		score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)min(max(s, 0), 255);
-	}
-	__syncthreads();
-
-	// ---- phase C: strict 8-neighbour local maxima (threshold independent), then the retry decision (:526-530):
-	//      survivors at t are {local max, S > t}; use iniTh if that set is non-empty, else minTh.
-	int nhi = 0;
-	for (int j = tid; j < nlist; j += 256)
-	{
-		const int i = list[j];
-		const int ry = i / rw, rx = i - ry * rw;
-		const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
-		const int s = sp[0];
-		uint8_t fl = 0;
-		if (s > tmin)
-		{
-			const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
-			                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
-			if (s > m)
-			{
-				fl = (s > tini) ? 3 : 1;
-				nhi += (s > tini);
-			}
-		}
-		flag[i] = fl;
-	}
-	// pixels never listed have no flag yet: clear them
-	// (cheaper than clearing everything first: flag[] of listed pixels is written exactly once above)
-	if (nhi) atomicAdd(&s_nhi, nhi);
-	__syncthreads();
-	const int want = s_nhi > 0 ? 2 : 1;
-
-	// ---- ordered emit: warp w owns the contiguous row-major pixel range [w*chunk, (w+1)*chunk)
-	// listed-ness is re-derived from score > 0 so flag[] needs no clearing pass
-	const int chunk = ((npx + 7) / 8 + 31) & ~31;
-	const int beg = warp * chunk, end = min(beg + chunk, npx);
-	int cnt = 0;
-	for (int i0 = beg; i0 < end; i0 += 32)
-	{
-		const int i = i0 + lane;
-		bool on = false;
-		if (i < end)
-		{
-			const int ry = i / rw, rx = i - ry * rw;
-			on = score[(ry + 1) * FT_SS + rx + 1] > tmin && (flag[i] & want);
-		}
-		cnt += __popc(__ballot_sync(0xffffffffu, on));
-	}
-	if (lane == 0) s_wcnt[warp] = cnt;
-	__syncthreads();
-	int base = 0, total = 0;
+	// ---- ordered emit: exclusive scan of the per-thread counts, then each thread writes its run
+	const int cnt = __popc(selm);
+	int inc = cnt;
 #pragma unroll
-	for (int w = 0; w < 8; w++)
+	for (int d = 1; d < 32; d <<= 1)
 	{
-		const int v = s_wcnt[w];
+		const int t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += t;
+	}
+	if (lane == 31) s_wsum[warp] = inc;
+	__syncthreads();
+	int base = inc - cnt, total = 0;
+#pragma unroll
+	for (int w = 0; w < FT_THREADS / 32; w++)
+	{
+		const int v = s_wsum[w];
 		if (w < warp) base += v;
 		total += v;
 	}
 	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
-	for (int i0 = beg; i0 < end; i0 += 32)
+	while (selm)
 	{
-		const int i = i0 + lane;
-		bool on = false;
-		int ry = 0, rx = 0, s = 0;
-		if (i < end)
-		{
-			ry = i / rw; rx = i - ry * rw;
-			s = score[(ry + 1) * FT_SS + rx + 1];
-			on = s > tmin && (flag[i] & want);
-		}
-		const unsigned bal = __ballot_sync(0xffffffffu, on);
-		if (on)
-			out[base + __popc(bal & lanemask_lt())] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
-		base += __popc(bal);
+		const int j = __ffs(selm) - 1;
+		selm &= selm - 1;
+		const int i = beg + j;
+		const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
+		const int s = score[(ry + 1) * FT_SS + rx + 1];
+		out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
 	}
 	if (tid == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
@@ -720,10 +687,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 // K6  gauss7x7_u8 — cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's 8.8 fixed point
 //     (src/ORBextractor.cc:799). Tile 128 x 32 with a 3 px halo in shared memory.
 // =====================================================================================================
-#define GB_TW 128
+#define GB_TW 128                 // output tile
 #define GB_TH 32
-#define GB_RW (GB_TW + 6)
-#define GB_RS 144
+#define GB_RROWS (GB_TH + 8)      // raw rows y0-4 .. y0+35 (the row-pair grid needs an even start)
+#define GB_RWORDS (GB_TW / 4 + 2) // raw cols x0-4 .. x0+131 as 34 words
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
@@ -732,43 +699,85 @@ __device__ __forceinline__ int reflect101(int i, int n)
 	return i;
 }
 
+// Horizontal pass with IDP.4A on packed bytes (two 4-tap dot products per output), results stored as 16-bit row pairs
+// (h[2p][x] | h[2p+1][x] << 16); vertical pass with IDP.2A on those pairs (four 2-tap dot products per output).
+// h <= 255*256 fits 16 bits; v = sum K*h < 2^24; out = (v + 32768) >> 16.
 __global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int level)
 {
-	__shared__ uint8_t raw[(GB_TH + 6) * GB_RS];
-	__shared__ uint16_t hb[(GB_TH + 6) * GB_TW];
+	__shared__ __align__(16) uint32_t raw[GB_RROWS * GB_RWORDS];
+	__shared__ __align__(16) uint32_t hv[(GB_RROWS / 2) * GB_TW];
 	const OrbxLevel& L = P.lv[level];
 	const int f = blockIdx.z, tid = threadIdx.x;
 	const int x0 = blockIdx.x * GB_TW, y0 = blockIdx.y * GB_TH;
 	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level);
 	const int64_t sp = orbx_level_pitch(P, level);
 	uint8_t* __restrict__ dst = P.blur + (int64_t)f * P.slab + L.offset;
+	const int w = L.w, h = L.h;
 
-	for (int i = tid; i < (GB_TH + 6) * GB_RW; i += 256)
+	// ---- stage the raw tile; REFLECT_101 at the image border (-1 -> 1, n -> n-2)
+	for (int i = tid; i < GB_RROWS * GB_RWORDS; i += 256)
 	{
-		const int r = i / GB_RW, c = i - r * GB_RW;
-		const int gy = reflect101(min(y0 + r - 3, L.h + 2), L.h), gx = reflect101(min(x0 + c - 3, L.w + 2), L.w);
-		raw[r * GB_RS + c] = __ldg(src + (int64_t)gy * sp + gx);
-	}
-	__syncthreads();
-	for (int i = tid; i < (GB_TH + 6) * GB_TW; i += 256)
-	{
-		const int r = i / GB_TW, c = i - r * GB_TW;
-		const uint8_t* p = raw + r * GB_RS + c;
-		hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-	}
-	__syncthreads();
-	const int c = tid & (GB_TW - 1), rbase = (tid >> 7) * (GB_TH / 2);
-	if (x0 + c < L.w)
-	{
-#pragma unroll 4
-		for (int rr = 0; rr < GB_TH / 2; rr++)
+		const int r = i / GB_RWORDS, wd = i - r * GB_RWORDS;
+		const int gy = reflect101(min(y0 - 4 + r, h + 2), h);
+		const int gx = x0 - 4 + 4 * wd;
+		const uint8_t* __restrict__ row = src + (int64_t)gy * sp;
+		uint32_t v;
+		if (gx >= 0 && gx + 3 < w)
+			v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+		else
 		{
-			const int r = rbase + rr;
-			if (y0 + r >= L.h) break;
-			const uint16_t* p = hb + r * GB_TW + c;
-			const int v = 18 * ((int)p[0] + p[6 * GB_TW]) + 34 * ((int)p[GB_TW] + p[5 * GB_TW]) + 48 * ((int)p[2 * GB_TW] + p[4 * GB_TW]) + 56 * (int)p[3 * GB_TW];
-			dst[(int64_t)(y0 + r) * L.pitch + x0 + c] = (uint8_t)((v + 32768) >> 16);
+			v = 0;
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				v |= (uint32_t)__ldg(row + reflect101(min(gx + k, w + 2), w)) << (8 * k);
 		}
+		raw[i] = v;
+	}
+	__syncthreads();
+
+	// ---- horizontal pass: item = (row pair, column quad); output x = x0 + 4q + k taps raw cols 4q+1+k .. 4q+7+k
+	const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
+	for (int i = tid; i < (GB_RROWS / 2) * (GB_TW / 4); i += 256)
+	{
+		const int pr = i >> 5, q = i & 31;
+		const uint32_t* r0 = raw + (2 * pr) * GB_RWORDS + q;
+		const uint32_t* r1 = r0 + GB_RWORDS;
+		const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2];
+		uint4 o;
+		uint32_t he, ho;
+		he = __dp4a(__funnelshift_r(a0, a1, 8), KA, __dp4a(__funnelshift_r(a1, a2, 8), KB, 0u));
+		ho = __dp4a(__funnelshift_r(b0, b1, 8), KA, __dp4a(__funnelshift_r(b1, b2, 8), KB, 0u));
+		o.x = he | (ho << 16);
+		he = __dp4a(__funnelshift_r(a0, a1, 16), KA, __dp4a(__funnelshift_r(a1, a2, 16), KB, 0u));
+		ho = __dp4a(__funnelshift_r(b0, b1, 16), KA, __dp4a(__funnelshift_r(b1, b2, 16), KB, 0u));
+		o.y = he | (ho << 16);
+		he = __dp4a(__funnelshift_r(a0, a1, 24), KA, __dp4a(__funnelshift_r(a1, a2, 24), KB, 0u));
+		ho = __dp4a(__funnelshift_r(b0, b1, 24), KA, __dp4a(__funnelshift_r(b1, b2, 24), KB, 0u));
+		o.z = he | (ho << 16);
+		he = __dp4a(a1, KA, __dp4a(a2, KB, 0u));
+		ho = __dp4a(b1, KA, __dp4a(b2, KB, 0u));
+		o.w = he | (ho << 16);
+		reinterpret_cast<uint4*>(hv)[i] = o;      // hv[pr][4q .. 4q+3]
+	}
+	__syncthreads();
+
+	// ---- vertical pass: output row y0 + r taps grid rows r+1 .. r+7 (grid row g = image row y0-4+g, pair = g >> 1)
+	// r even: (0,K0)(K1,K2)(K3,K4)(K5,K6) on pairs r/2 .. r/2+3;  r odd: (K0,K1)(K2,K3)(K4,K5)(K6,0) on pairs (r+1)/2 ..
+	for (int i = tid; i < GB_TH * (GB_TW / 4); i += 256)
+	{
+		const int r = i >> 5, q = i & 31;
+		if (y0 + r >= h || x0 + 4 * q >= w) continue;
+		const bool odd = r & 1;
+		const uint32_t c01 = odd ? (18u | (34u << 8) | (48u << 16) | (56u << 24)) : ((18u << 8) | (34u << 16) | (48u << 24));
+		const uint32_t c23 = odd ? (48u | (34u << 8) | (18u << 16)) : (56u | (48u << 8) | (34u << 16) | (18u << 24));
+		const uint4* pp = reinterpret_cast<const uint4*>(hv) + ((r + 1) >> 1) * (GB_TW / 4) + q;
+		const uint4 p0 = pp[0], p1 = pp[GB_TW / 4], p2 = pp[2 * (GB_TW / 4)], p3 = pp[3 * (GB_TW / 4)];
+		uint32_t v0 = __dp2a_lo(p0.x, c01, 32768u), v1 = __dp2a_lo(p0.y, c01, 32768u), v2 = __dp2a_lo(p0.z, c01, 32768u), v3 = __dp2a_lo(p0.w, c01, 32768u);
+		v0 = __dp2a_hi(p1.x, c01, v0); v1 = __dp2a_hi(p1.y, c01, v1); v2 = __dp2a_hi(p1.z, c01, v2); v3 = __dp2a_hi(p1.w, c01, v3);
+		v0 = __dp2a_lo(p2.x, c23, v0); v1 = __dp2a_lo(p2.y, c23, v1); v2 = __dp2a_lo(p2.z, c23, v2); v3 = __dp2a_lo(p2.w, c23, v3);
+		v0 = __dp2a_hi(p3.x, c23, v0); v1 = __dp2a_hi(p3.y, c23, v1); v2 = __dp2a_hi(p3.z, c23, v2); v3 = __dp2a_hi(p3.w, c23, v3);
+		const uint32_t out = (v0 >> 16) | ((v1 >> 16) << 8) | ((v2 >> 16) << 16) | ((v3 >> 16) << 24);
+		*reinterpret_cast<uint32_t*>(dst + (int64_t)(y0 + r) * L.pitch + x0 + 4 * q) = out;
 	}
 }
 
@@ -844,7 +853,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(const OrbxPlanDev P, or
 	if (lane < 31)
 	{
 		const int au = abs(u);
-#pragma unroll 1
+#pragma unroll
 		for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++)
 		{
 			if (au <= c_umax[abs(v)])
@@ -921,14 +930,9 @@ cudaError_t orbx_upload_pattern()
 		umax[v] = v0;
 		++v0;
 	}
-	static const int rdx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
-	static const int rdy[16] = { 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3 };
-	int ring[16];
-	for (int k = 0; k < 16; k++) ring[k] = rdy[k] * FT_TS + rdx[k];
 	cudaError_t e;
 	if ((e = cudaMemcpyToSymbol(c_pattern, pattern, sizeof(pattern))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_ring, ring, sizeof(ring))) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
@@ -942,7 +946,7 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
 {
 	dim3 grid(P.cells_per_frame, P.frames);
-	k_fast_cells<<<grid, 256, 0, st>>>(P);
+	k_fast_cells<<<grid, FT_THREADS, 0, st>>>(P);
 }
 
 size_t orbx_quadtree_smem(int node_cap)
