@@ -80,14 +80,16 @@ orbx_status orbx_feature_quotas(orbx_handle h, int32_t* quotas);
 
 /* ORBextractor::Extract(image, keypoints, descriptors) — src/ORBextractor.cc:743-820, one frame,
  * host buffers. `kps` holds `cap` entries, `desc` cap*32 bytes (the N x 32 CV_8U matrix, row i = keypoint i).
- * *n = keypoint count. When N == 0 the reference releases `descriptors` and leaves `keypoints` untouched
- * (:778-782); here *n = 0 and the buffers are untouched. ORBX_ERR_CAPACITY sets *n to the needed count. */
+ * *n = keypoint count; entries of kps/desc at and beyond *n are unspecified. When N == 0 the reference releases
+ * `descriptors` and leaves `keypoints` untouched (:778-782); here *n = 0. ORBX_ERR_CAPACITY sets *n to the needed count. */
 orbx_status orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, size_t pitch,
                          orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
 
 /* The same for a batch of `frames` equally sized images (frame f at images + f*frame_stride). Outputs are
- * frame-major: kps + f*cap, desc + f*cap*32, n[f]. This is the throughput entry point: every kernel is
- * launched once per pyramid level (or once) for the whole batch. */
+ * frame-major: kps + f*cap, desc + f*cap*32, n[f]. This is the throughput entry point: the batch is cut into chunks
+ * that flow through two CUDA streams, so the upload of one chunk and the download of another overlap the kernels of a
+ * third; inside a chunk every kernel is launched once per pyramid level (or once) for all its frames. Use pinned host
+ * memory for the overlap to materialise. */
 orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
                                size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,6 +75,7 @@ struct orbx_extractor
 	orbx_params prm;
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr;     // second lane of the chunk pipeline of the host-buffer API
 	cudaEvent_t done = nullptr;
 	std::vector<float> scale, inv_scale, sigma_sq, inv_sigma_sq;
 	std::vector<int> quota;
@@ -81,16 +83,20 @@ struct orbx_extractor
 	// plan (depends on image size)
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
-	DevBuf<uint8_t> pyr, blur;
+	DevBuf<uint8_t> pyr, blur, l0buf;   // l0buf: level 0 of every frame, back to back (host-buffer API uploads land here)
+	int64_t l0_pitch = 0, l0_stride = 0;
 	DevBuf<uint32_t> cand, qbuf0, qbuf1, sel;
 	DevBuf<int> cell_count, cand_count, sel_count;
 	DevBuf<int> root_x, xofs, yofs;
 	DevBuf<uint8_t> root_lut;
 	DevBuf<short2> xcoef, ycoef;
+	DevBuf<int4> cell_tab;
 	// outputs owned by the handle (host-buffer API) and the state of the last extract (for stereo / probes)
 	DevBuf<orbx_keypoint> out_kps;
 	DevBuf<uint8_t> out_desc;
 	DevBuf<int32_t> out_n;
+	int32_t* h_counts = nullptr;        // pinned staging for the per-frame counts (a pageable target would serialise the pipeline)
+	size_t h_counts_n = 0;
 	DevBuf<float> st_uright, st_depth;
 	DevBuf<int> st_sad;
 	bool stage_timing = false;
@@ -167,6 +173,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	std::vector<int> root_x, xofs, yofs;
 	std::vector<uint8_t> root_lut;
 	std::vector<short2> xcoef, ycoef;
+	std::vector<int4> cell_tab;
 	int64_t slab = 0;
 	int cells = 0, cands = 0, sels = 0, node_cap = 0;
 	for (int s = 0; s < nl; s++)
@@ -195,6 +202,14 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		for (int cy = 0, y0 = L.miny; cy < gridh && y0 + 6 < L.maxy; cy++, y0 += L.cellh) L.ncy++;
 		L.cell_base = cells;
 		cells += L.ncx * L.ncy;
+		for (int cy = 0; cy < L.ncy; cy++)
+			for (int cx = 0; cx < L.ncx; cx++)
+			{
+				// cell view [x0, x1) x [y0, y1) (:521-524)
+				const int x0 = L.minx + cx * L.cellw, y0 = L.miny + cy * L.cellh;
+				const int x1 = std::min(x0 + L.cellw + 6, L.maxx), y1 = std::min(y0 + L.cellh + 6, L.maxy);
+				cell_tab.push_back(make_int4(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16), s, cy * L.ncx + cx));
+			}
 		L.cell_cap = ((L.cellw + 1) / 2) * ((L.cellh + 1) / 2);
 		L.cand_base = cands;
 		L.cand_cap = L.ncx * L.ncy * L.cell_cap;
@@ -228,6 +243,14 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			L.ytab_base = (int)yofs.size();
 			yofs.resize(yofs.size() + L.h); ycoef.resize(ycoef.size() + L.h);
 			resize_tables(L.h, P.lv[s - 1].h, yofs.data() + L.ytab_base, ycoef.data() + L.ytab_base);
+			// the resize kernel stages the source rows of a 32-row output tile in shared memory
+			const int th = orbx_pyramid_tile_rows();
+			for (int y0 = 0; y0 < L.h; y0 += th)
+			{
+				const int y1 = std::min(y0 + th, L.h) - 1;
+				if (yofs[L.ytab_base + y1] + 1 - yofs[L.ytab_base + y0] + 1 > orbx_pyramid_max_src_rows())
+					return fail(ORBX_ERR_INVALID, "scaleFactor too large for the resize kernel (max about 2.2)");
+			}
 		}
 	}
 	P.slab = slab;
@@ -242,6 +265,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(cudaSetDevice(h->device));
 	const size_t F = (size_t)frames;
 	CU(h->pyr.ensure(F * slab)); CU(h->blur.ensure(F * slab));
+	h->l0_pitch = P.lv[0].pitch; h->l0_stride = (int64_t)P.lv[0].pitch * P.lv[0].h;   // frames back to back: one strided copy uploads a whole chunk
+	CU(h->l0buf.ensure(F * h->l0_stride));
 	CU(h->cand.ensure(F * cands)); CU(h->qbuf0.ensure(F * cands)); CU(h->qbuf1.ensure(F * cands));
 	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
 	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl));
@@ -249,6 +274,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(h->root_x.ensure(root_x.size())); CU(h->root_lut.ensure(root_lut.size()));
 	CU(h->xofs.ensure(std::max<size_t>(xofs.size(), 1))); CU(h->xcoef.ensure(std::max<size_t>(xcoef.size(), 1)));
 	CU(h->yofs.ensure(std::max<size_t>(yofs.size(), 1))); CU(h->ycoef.ensure(std::max<size_t>(ycoef.size(), 1)));
+	CU(h->cell_tab.ensure(cell_tab.size()));
+	CU(cudaMemcpyAsync(h->cell_tab.p, cell_tab.data(), cell_tab.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
 	CU(h->out_kps.ensure(F * sels)); CU(h->out_desc.ensure(F * sels * 32)); CU(h->out_n.ensure(F));
 	CU(cudaMemcpyAsync(h->root_x.p, root_x.data(), root_x.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
 	CU(cudaMemcpyAsync(h->root_lut.p, root_lut.data(), root_lut.size(), cudaMemcpyHostToDevice, h->stream));
@@ -264,20 +291,32 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.pyr = h->pyr.p; P.blur = h->blur.p;
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
-	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p;
+	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
 	h->pw = w; h->ph = hgt; h->frames_cap = frames;
 	h->have_result = false;
 	return ORBX_OK;
 }
 
-// enqueue the whole extraction of P.frames frames; level 0 is at (l0, l0_pitch, l0_stride)
-orbx_status enqueue_extract(orbx_extractor* h, const uint8_t* l0, int64_t l0_pitch, int64_t l0_stride,
+// enqueue the extraction of frames [fb, fb + fc) of the planned batch on stream st; level 0 of frame f is at
+// l0 + f*l0_stride. All per-frame buffers are indexed by frame, so a chunk is the same launch with offset bases.
+orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, const uint8_t* l0, int64_t l0_pitch, int64_t l0_stride,
                             orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap)
 {
-	OrbxPlanDev& P = h->P;
-	P.l0 = l0; P.l0_pitch = l0_pitch; P.l0_stride = l0_stride;
-	P.out_cap = cap;      // stride of the output arrays for this call (>= sel_per_frame)
+	OrbxPlanDev& P0 = h->P;
+	P0.l0 = l0; P0.l0_pitch = l0_pitch; P0.l0_stride = l0_stride;
+	P0.out_cap = cap;      // stride of the output arrays for this call (>= sel_per_frame)
+	OrbxPlanDev P = P0;
+	int* cell_off = P0.cell_count + (int64_t)h->frames_cap * P0.cells_per_frame + (int64_t)fb * P0.cells_per_frame;
+	P.frames = fc;
+	P.l0 += (int64_t)fb * l0_stride;
+	P.pyr += (int64_t)fb * P.slab; P.blur += (int64_t)fb * P.slab;
+	P.cand += (int64_t)fb * P.cand_per_frame; P.qbuf0 += (int64_t)fb * P.cand_per_frame; P.qbuf1 += (int64_t)fb * P.cand_per_frame;
+	P.cell_count += (int64_t)fb * P.cells_per_frame;
+	P.cand_count += (int64_t)fb * P.nlevels; P.sel_count += (int64_t)fb * P.nlevels;
+	P.sel += (int64_t)fb * P.sel_per_frame;
+	d_kps += (int64_t)fb * cap; d_desc += (int64_t)fb * cap * 32; d_n += fb;
+
 	cudaEvent_t* ev = nullptr;
 	if (h->stage_timing)
 	{
@@ -290,22 +329,27 @@ orbx_status enqueue_extract(orbx_extractor* h, const uint8_t* l0, int64_t l0_pit
 		ev = h->ev_pool.data() + h->ev_used;
 		h->ev_used += 6;
 	}
-	if (ev) CU(cudaEventRecord(ev[0], h->stream));
-	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, h->stream);
-	if (ev) CU(cudaEventRecord(ev[1], h->stream));
-	orbx_launch_fast(P, h->stream);
-	if (ev) CU(cudaEventRecord(ev[2], h->stream));
-	orbx_launch_quadtree(P, h->stream);
-	if (ev) CU(cudaEventRecord(ev[3], h->stream));
-	orbx_launch_blur(P, h->stream);
-	if (ev) CU(cudaEventRecord(ev[4], h->stream));
-	orbx_launch_describe(P, d_kps, d_desc, d_n, h->stream);
-	if (ev) CU(cudaEventRecord(ev[5], h->stream));
+	if (ev) CU(cudaEventRecord(ev[0], st));
+	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, st);
+	if (ev) CU(cudaEventRecord(ev[1], st));
+	orbx_launch_fast(P, st);
+	if (ev) CU(cudaEventRecord(ev[2], st));
+	orbx_launch_quadtree(P, cell_off, st);
+	if (ev) CU(cudaEventRecord(ev[3], st));
+	orbx_launch_blur(P, st);
+	if (ev) CU(cudaEventRecord(ev[4], st));
+	orbx_launch_describe(P, d_kps, d_desc, d_n, st);
+	if (ev) CU(cudaEventRecord(ev[5], st));
 	CU(cudaGetLastError());
-	h->have_result = true;
-	h->last_frames = P.frames; h->last_cap = P.out_cap;
-	h->last_kps = d_kps; h->last_desc = d_desc; h->last_n = d_n;
 	return ORBX_OK;
+}
+
+void note_result(orbx_extractor* h, int frames, int cap, const orbx_keypoint* d_kps, const uint8_t* d_desc, const int32_t* d_n)
+{
+	h->have_result = true;
+	h->last_frames = frames; h->last_cap = cap;
+	h->last_kps = d_kps; h->last_desc = d_desc; h->last_n = d_n;
+	h->P.frames = frames;
 }
 
 }  // namespace
@@ -343,6 +387,7 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 	h->device = device;
 	build_tables(h);
 	cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = orbx_upload_pattern();
 	if (e != cudaSuccess)
@@ -359,14 +404,19 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (!h) return ORBX_OK;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->stream2) cudaStreamSynchronize(h->stream2);
+	h->l0buf.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
 	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
+	h->cell_tab.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release();
+	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
 	if (h->stream) cudaStreamDestroy(h->stream);
+	if (h->stream2) cudaStreamDestroy(h->stream2);
 	delete h;
 	return ORBX_OK;
 }
@@ -459,13 +509,14 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 	if (((uintptr_t)d_images & 15) || (pitch & 3) || (frame_stride & 3))
 	{
 		// kernels read level 0 with aligned 32-bit loads: repack a misaligned input into the slab
-		const OrbxLevel& L0 = h->P.lv[0];
 		for (int f = 0; f < frames; f++)
-			CU(cudaMemcpy2DAsync(h->pyr.p + (int64_t)f * h->P.slab + L0.offset, L0.pitch, d_images + (size_t)f * frame_stride, pitch,
+			CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)f * h->l0_stride, h->l0_pitch, d_images + (size_t)f * frame_stride, pitch,
 			                     width, height, cudaMemcpyDeviceToDevice, h->stream));
-		l0 = h->pyr.p + L0.offset; l0_pitch = L0.pitch; l0_stride = h->P.slab;
+		l0 = h->l0buf.p; l0_pitch = h->l0_pitch; l0_stride = h->l0_stride;
 	}
-	return enqueue_extract(h, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+	orbx_status st2 = enqueue_extract(h, 0, frames, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+	if (st2 == ORBX_OK) note_result(h, frames, cap, d_kps, d_desc, d_n);
+	return st2;
 }
 
 orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
@@ -477,32 +528,51 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 	orbx_status st = build_plan(h, width, height, frames);
 	if (st != ORBX_OK) return st;
 	const OrbxPlanDev& P = h->P;
-	const OrbxLevel& L0 = P.lv[0];
-	// level 0 is uploaded straight into the pyramid slab (ComputePyramid's copyTo, :462)
-	for (int f = 0; f < frames; f++)
-		CU(cudaMemcpy2DAsync(h->pyr.p + (int64_t)f * P.slab + L0.offset, L0.pitch, images + (size_t)f * frame_stride, pitch, width,
-		                     height, cudaMemcpyHostToDevice, h->stream));
-	st = enqueue_extract(h, h->pyr.p + L0.offset, L0.pitch, P.slab, h->out_kps.p, h->out_desc.p, h->out_n.p, P.sel_per_frame);
-	if (st != ORBX_OK) return st;
-	std::vector<int32_t> counts(frames);
-	CU(cudaMemcpyAsync(counts.data(), h->out_n.p, sizeof(int32_t) * frames, cudaMemcpyDeviceToHost, h->stream));
+	const int ocap = P.sel_per_frame;
+	// Chunk pipeline over two streams: upload of chunk c+1 and download of chunk c-1 overlap the kernels of chunk c.
+	// Level 0 is uploaded straight into the level-0 buffer (ComputePyramid's copyTo, :462).
+	int chunk = frames <= 32 ? frames : std::max(32, std::min(64, (frames + 3) / 4));
+	if (const char* e = getenv("ORBX_CHUNK")) chunk = std::max(1, atoi(e));   // tuning knob
+	const int ccap = std::min(cap, ocap);
+	if (h->h_counts_n < (size_t)frames)
+	{
+		if (h->h_counts) cudaFreeHost(h->h_counts);
+		h->h_counts = nullptr; h->h_counts_n = 0;
+		CU(cudaMallocHost(&h->h_counts, sizeof(int32_t) * (size_t)frames));
+		h->h_counts_n = (size_t)frames;
+	}
+	int32_t* counts = h->h_counts;
+	int ci = 0;
+	for (int fb = 0; fb < frames; fb += chunk, ci++)
+	{
+		const int fc = std::min(chunk, frames - fb);
+		cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
+		if (frame_stride == pitch * (size_t)height)
+			CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
+			                     (size_t)height * fc, cudaMemcpyHostToDevice, st));
+		else
+			for (int f = fb; f < fb + fc; f++)
+				CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
+				                     height, cudaMemcpyHostToDevice, st));
+		st = (ci & 1) ? h->stream2 : h->stream;
+		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0buf.p, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
+		if (e != ORBX_OK) return e;
+		CU(cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st));
+		if (kps && desc && ccap > 0)
+		{
+			CU(cudaMemcpy2DAsync(kps + (size_t)fb * cap, sizeof(orbx_keypoint) * (size_t)cap, h->out_kps.p + (size_t)fb * ocap,
+			                     sizeof(orbx_keypoint) * (size_t)ocap, sizeof(orbx_keypoint) * (size_t)ccap, fc, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpy2DAsync(desc + (size_t)fb * cap * 32, (size_t)32 * cap, h->out_desc.p + (size_t)fb * ocap * 32, (size_t)32 * ocap,
+			                     (size_t)32 * ccap, fc, cudaMemcpyDeviceToHost, st));
+		}
+	}
 	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaStreamSynchronize(h->stream2));
+	note_result(h, frames, ocap, h->out_kps.p, h->out_desc.p, h->out_n.p);
 	int need = 0;
 	for (int f = 0; f < frames; f++) { n[f] = counts[f]; need = std::max(need, counts[f]); }
 	if (need > cap || (need > 0 && (!kps || !desc)))
-	{
-		for (int f = 0; f < frames; f++) n[f] = counts[f];
 		return fail(ORBX_ERR_CAPACITY, "output buffers hold fewer keypoints than were found");
-	}
-	for (int f = 0; f < frames; f++)
-	{
-		if (counts[f] == 0) continue;    // :778-782 — outputs untouched
-		CU(cudaMemcpyAsync(kps + (size_t)f * cap, h->out_kps.p + (size_t)f * P.out_cap, sizeof(orbx_keypoint) * counts[f],
-		                   cudaMemcpyDeviceToHost, h->stream));
-		CU(cudaMemcpyAsync(desc + (size_t)f * cap * 32, h->out_desc.p + (size_t)f * P.out_cap * 32, (size_t)32 * counts[f],
-		                   cudaMemcpyDeviceToHost, h->stream));
-	}
-	CU(cudaStreamSynchronize(h->stream));
 	return ORBX_OK;
 }
 

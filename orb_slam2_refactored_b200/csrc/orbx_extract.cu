@@ -15,43 +15,69 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 //     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
 //     exact float/double operation order; the kernel is integer only. One thread = 4 output pixels.
 // =====================================================================================================
+#define PY_TW 128     // output tile
+#define PY_TH 32
+#define PY_SRC 72     // source rows a tile may touch: 31 * scaleFactor + 2; scale factors up to 2.2 (checked on the host)
 __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, const int level)
 {
+	// Two passes through shared memory. Horizontal: every source row the tile needs is filtered once, g = (s0*a0 + s1*a1) >> 4
+	// (the vertical pass only ever uses h >> 4, which fits 15 bits), two pixels per word; all loads of a thread are
+	// independent, so they overlap. Vertical: 4 output pixels per thread from two 8-byte shared loads.
+	__shared__ __align__(16) uint32_t g[PY_SRC * (PY_TW / 2)];
 	const OrbxLevel& D = P.lv[level];
 	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
-	const int f = blockIdx.z;
-	const int dx0 = (blockIdx.x * 64 + threadIdx.x) * 4;
-	const int dy = blockIdx.y * 4 + threadIdx.y;
-	if (dy >= D.h || dx0 >= D.w)
-		return;
+	const int f = blockIdx.z, tid = threadIdx.x;
+	const int dx0 = blockIdx.x * PY_TW, dy0 = blockIdx.y * PY_TH;
+	const int dy_last = min(dy0 + PY_TH, D.h) - 1;
 	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level - 1);
 	const int64_t sp = orbx_level_pitch(P, level - 1);
 	uint8_t* __restrict__ dst = P.pyr + (int64_t)f * P.slab + D.offset;
+	const int* __restrict__ yofs = P.yofs + D.ytab_base;
+	const short2* __restrict__ ycoef = P.ycoef + D.ytab_base;
 
-	const int sy0 = __ldg(P.yofs + D.ytab_base + dy);
-	const short2 b = __ldg(P.ycoef + D.ytab_base + dy);
-	const int sy1 = min(sy0 + 1, sh - 1);
-	const uint8_t* __restrict__ r0 = src + (int64_t)sy0 * sp;
-	const uint8_t* __restrict__ r1 = src + (int64_t)sy1 * sp;
+	const int s_lo = __ldg(yofs + dy0);
+	const int s_hi = min(__ldg(yofs + dy_last) + 1, sh - 1);
+	const int nsrc = min(s_hi - s_lo + 1, PY_SRC);
 
-	uint32_t out = 0;
-#pragma unroll
-	for (int j = 0; j < 4; j++)
 	{
-		const int dx = dx0 + j;
-		if (dx < D.w)
+		const int cp = tid & 63, rg = tid >> 6;
+		const int c0 = min(dx0 + 2 * cp, D.w - 1), c1 = min(dx0 + 2 * cp + 1, D.w - 1);   // columns past the edge repeat the last one
+		const int x00 = __ldg(P.xofs + D.xtab_base + c0), x10 = __ldg(P.xofs + D.xtab_base + c1);
+		const short2 ca = __ldg(P.xcoef + D.xtab_base + c0), cb = __ldg(P.xcoef + D.xtab_base + c1);
+		const int x01 = min(x00 + 1, sw - 1), x11 = min(x10 + 1, sw - 1);
+		const uint8_t* __restrict__ row = src + (int64_t)(s_lo + rg) * sp;
+#pragma unroll 4
+		for (int r = rg; r < nsrc; r += 4, row += 4 * sp)
 		{
-			const int sx0 = __ldg(P.xofs + D.xtab_base + dx);
-			const short2 a = __ldg(P.xcoef + D.xtab_base + dx);
-			const int sx1 = min(sx0 + 1, sw - 1);
-			const int h0 = (int)__ldg(r0 + sx0) * a.x + (int)__ldg(r0 + sx1) * a.y;
-			const int h1 = (int)__ldg(r1 + sx0) * a.x + (int)__ldg(r1 + sx1) * a.y;
-			int v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-			v = min(max(v, 0), 255);
-			out |= (uint32_t)v << (8 * j);
+			const int h0 = (int)__ldg(row + x00) * ca.x + (int)__ldg(row + x01) * ca.y;
+			const int h1 = (int)__ldg(row + x10) * cb.x + (int)__ldg(row + x11) * cb.y;
+			g[r * (PY_TW / 2) + cp] = (uint32_t)(h0 >> 4) | ((uint32_t)(h1 >> 4) << 16);
 		}
 	}
-	*reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx0) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
+	__syncthreads();
+
+	const int q = tid & 31, grp = tid >> 5;
+	if (dx0 + 4 * q >= D.w)
+		return;
+#pragma unroll
+	for (int k = 0; k < PY_TH / 8; k++)
+	{
+		const int dy = dy0 + grp + 8 * k;
+		if (dy >= D.h) break;
+		const int sy0 = __ldg(yofs + dy);
+		const short2 b = __ldg(ycoef + dy);
+		const int r0 = sy0 - s_lo, r1 = min(sy0 + 1, sh - 1) - s_lo;
+		const uint2 u0 = *reinterpret_cast<const uint2*>(g + r0 * (PY_TW / 2) + 2 * q);
+		const uint2 u1 = *reinterpret_cast<const uint2*>(g + r1 * (PY_TW / 2) + 2 * q);
+		const int b0 = b.x, b1 = b.y;
+		const int v0 = (((b0 * (int)(u0.x & 0xffffu)) >> 16) + ((b1 * (int)(u1.x & 0xffffu)) >> 16) + 2) >> 2;
+		const int v1 = (((b0 * (int)(u0.x >> 16)) >> 16) + ((b1 * (int)(u1.x >> 16)) >> 16) + 2) >> 2;
+		const int v2 = (((b0 * (int)(u0.y & 0xffffu)) >> 16) + ((b1 * (int)(u1.y & 0xffffu)) >> 16) + 2) >> 2;
+		const int v3 = (((b0 * (int)(u0.y >> 16)) >> 16) + ((b1 * (int)(u1.y >> 16)) >> 16) + 2) >> 2;
+		// coefficients sum to 2048, so v is already in [0, 255]
+		const uint32_t out = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+		*reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx0 + 4 * q) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
+	}
 }
 
 // =====================================================================================================
@@ -101,38 +127,35 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 	return max(dark, bright);
 }
 
+__constant__ uint32_t c_inv20[72];   // c_inv20[n] = (1 << 20) / n + 1: floor(i / n) == (i * c_inv20[n]) >> 20 for n <= 64, i < 4096 (exhaustively checked)
+
 // One CTA (4 warps) per cell. Phases: stage view -> arc score S of every region pixel (dense: on textured frames a third
-// of the pixels pass any cheap rejection at minTh, so a branch-free network on all of them is cheaper than test + compaction)
-// -> strict 8-neighbour local maxima, which are threshold independent: survivors at t are {local max, S > t}; the retry of
-// :526-530 is therefore "use iniTh if that set is non-empty, else minTh" -> ordered emit.
+// of the pixels pass any cheap rejection at minTh, so a branch-free network on all of them is cheaper than test + compaction);
+// pixels with S > minTh (about a fifth) are appended to a list -> strict 8-neighbour local-maximum test of the listed pixels
+// only. Local maxima are threshold independent: survivors at t are {local max, S > t}, so the retry of :526-530 is "use
+// iniTh if that set is non-empty, else minTh". Survivors set a bit in a row-major bitmap -> ordered emit from the bitmap.
 __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 {
 	__shared__ __align__(16) uint8_t tile[FT_TH * FT_TS];
 	__shared__ __align__(4) uint8_t score[(FT_MAXR + 2) * FT_SS];
+	__shared__ uint32_t bm_cand[FT_THREADS], bm_lo[FT_THREADS], bm_hi[FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
 	__shared__ int s_wsum[FT_THREADS / 32];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int cell = blockIdx.x, f = blockIdx.y;
-	int lvl = 0;
-	for (int l = 1; l < P.nlevels; l++)
-		if (cell >= P.lv[l].cell_base) lvl = l;
+	const int4 ct = __ldg(P.cell_tab + cell);        // host-built: x0 | y0 << 16, vw | vh << 16, level, cell index inside the level
+	const int x0 = ct.x & 0xffff, y0 = ct.x >> 16, vw = ct.y & 0xffff, vh = ct.y >> 16, lvl = ct.z, c = ct.w;
 	const OrbxLevel& L = P.lv[lvl];
-	const int c = cell - L.cell_base;
-	const int cy = c / L.ncx, cx = c - cy * L.ncx;
-	const int x0 = L.minx + cx * L.cellw, y0 = L.miny + cy * L.cellh;
-	const int x1 = min(x0 + L.cellw + 6, L.maxx), y1 = min(y0 + L.cellh + 6, L.maxy);
-	const int vw = x1 - x0, vh = y1 - y0;      // view
-	const int rw = vw - 6, rh = vh - 6;        // detection region, >= 1 by the reference's loop conditions (:519,521)
+	const int rw = vw - 6, rh = vh - 6;              // detection region, >= 1 by the reference's loop conditions (:519,521)
 	const int npx = rw * rh;
-	// floor(i / n) == (i * ((1 << 20) / n + 1)) >> 20 for n <= 64, i < 4096 (checked exhaustively): no integer division in loops
-	const uint32_t inv_rw = (1u << 20) / (uint32_t)rw + 1u;
+	const uint32_t inv_rw = c_inv20[rw];
 
 	// ---- stage the view: aligned 32-bit loads; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
 	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl);
 	const int64_t pitch = orbx_level_pitch(P, lvl);
 	const int sh = x0 & 3;
 	const int nwords = (sh + vw + 3) >> 2;
-	const uint32_t inv_nw = (1u << 20) / (uint32_t)nwords + 1u;
+	const uint32_t inv_nw = c_inv20[nwords];
 	const uint8_t* __restrict__ src0 = img + (int64_t)y0 * pitch + (x0 - sh);
 	for (int i = tid; i < vh * nwords; i += FT_THREADS)
 	{
@@ -151,46 +174,55 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 		score[(i + 1) * FT_SS] = 0;
 		score[(i + 1) * FT_SS + rw + 1] = 0;
 	}
+	bm_lo[tid] = 0; bm_hi[tid] = 0;
 	__syncthreads();
 
-	// ---- arc score of every region pixel
+	// ---- arc score of every region pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballot of
+	//      "S > minTh" IS the bitmap word of those pixels: no list, no atomics.
+	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
-	for (int i = tid; i < npx; i += FT_THREADS)
+	for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
 	{
-		const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-		const int s = arc_score_packed(t0 + ry * FT_TS + rx);
-		score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
+		const int i = i0 + tid;
+		bool is_cand = false;
+		if (i < npx)
+		{
+			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
+			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
+			score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
+			is_cand = s > tmin;
+		}
+		const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+		if (lane == 0) bm_cand[(i0 >> 5) + warp] = bal;
 	}
 	__syncthreads();
 
-	// ---- local maxima of this thread's contiguous row-major run of pixels; results stay in two bit masks
-	const int tmin = P.min_th, tini = P.ini_th;
-	const int chunk = (npx + FT_THREADS - 1) / FT_THREADS;        // <= 29
-	const int beg = tid * chunk, end = min(beg + chunk, npx);
-	uint32_t mlo = 0, mhi = 0;
+	// ---- strict local maxima among the candidates, same pixel-to-lane mapping; results are ballots again
+	bool hi_any = false;
+	for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
 	{
-		int ry = (int)(((uint32_t)beg * inv_rw) >> 20), rx = beg - ry * rw;
-		for (int j = 0; beg + j < end; j++)
+		const unsigned cw = bm_cand[(i0 >> 5) + warp];
+		if (cw == 0) continue;                       // warp-uniform
+		bool lm = false, lmh = false;
+		if ((cw >> lane) & 1u)
 		{
+			const int i = i0 + tid;
+			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
 			const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
 			const int s = sp[0];
-			if (s > tmin)
-			{
-				const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
-				                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
-				if (s > m)
-				{
-					mlo |= 1u << j;
-					if (s > tini) mhi |= 1u << j;
-				}
-			}
-			if (++rx == rw) { rx = 0; ++ry; }
+			const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
+			                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
+			lm = s > m;
+			lmh = lm && s > tini;
 		}
+		const unsigned blo = __ballot_sync(0xffffffffu, lm), bhi = __ballot_sync(0xffffffffu, lmh);
+		if (lane == 0) { bm_lo[(i0 >> 5) + warp] = blo; bm_hi[(i0 >> 5) + warp] = bhi; }
+		hi_any |= bhi != 0;
 	}
-	const int any_hi = __syncthreads_or(mhi != 0);
-	uint32_t selm = any_hi ? mhi : mlo;
+	const int any_hi = __syncthreads_or(hi_any);
+	uint32_t selm = any_hi ? bm_hi[tid] : bm_lo[tid];
 
-	// ---- ordered emit: exclusive scan of the per-thread counts, then each thread writes its run
+	// ---- ordered emit: thread t owns bitmap word t = pixels [32t, 32t + 32); exclusive scan of the popcounts
 	const int cnt = __popc(selm);
 	int inc = cnt;
 #pragma unroll
@@ -212,9 +244,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
 	while (selm)
 	{
-		const int j = __ffs(selm) - 1;
+		const int i = tid * 32 + __ffs(selm) - 1;
 		selm &= selm - 1;
-		const int i = beg + j;
 		const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
 		const int s = score[(ry + 1) * FT_SS + rx + 1];
 		out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
@@ -714,24 +745,38 @@ __global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int l
 	uint8_t* __restrict__ dst = P.blur + (int64_t)f * P.slab + L.offset;
 	const int w = L.w, h = L.h;
 
-	// ---- stage the raw tile; REFLECT_101 at the image border (-1 -> 1, n -> n-2)
+	// ---- stage the raw tile. Fast pass: every word with one aligned 32-bit load (address clamped into the row, so words
+	//      that touch the border hold junk); border pass: the <= 3 words per row that overlap [-3, 0) or [w, w + 3) are
+	//      rebuilt byte by byte with REFLECT_101 (-1 -> 1, n -> n-2). Words further out only feed outputs >= w.
+	const int gx_max = (w - 4) & ~3;
 	for (int i = tid; i < GB_RROWS * GB_RWORDS; i += 256)
 	{
 		const int r = i / GB_RWORDS, wd = i - r * GB_RWORDS;
 		const int gy = reflect101(min(y0 - 4 + r, h + 2), h);
-		const int gx = x0 - 4 + 4 * wd;
-		const uint8_t* __restrict__ row = src + (int64_t)gy * sp;
-		uint32_t v;
-		if (gx >= 0 && gx + 3 < w)
-			v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-		else
+		const int gx = min(max(x0 - 4 + 4 * wd, 0), gx_max);
+		raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)gy * sp + gx));
+	}
+	__syncthreads();
+	{
+		const int wl = (x0 == 0) ? 0 : -1;                    // word holding cols -4..-1
+		const int wr = (w - (x0 - 4)) >> 2;                   // first word not entirely inside [0, w)
+		const int r = tid / 3, which = tid - r * 3;
+		const int wd = which == 0 ? wl : wr + which - 1;
+		if (r < GB_RROWS && wd >= 0 && wd < GB_RWORDS && (which == 0 || (x0 - 4 + 4 * wd) < w + 3))
 		{
-			v = 0;
+			const int gy = reflect101(min(y0 - 4 + r, h + 2), h);
+			const uint8_t* __restrict__ row = src + (int64_t)gy * sp;
+			const int gx = x0 - 4 + 4 * wd;
+			uint32_t v = 0;
 #pragma unroll
 			for (int k = 0; k < 4; k++)
-				v |= (uint32_t)__ldg(row + reflect101(min(gx + k, w + 2), w)) << (8 * k);
+			{
+				const int a = abs(gx + k);
+				const int c = max(min(a, 2 * w - 2 - a), 0);      // reflect101 for -w < x < 2w - 1; further out is never used
+				v |= (uint32_t)__ldg(row + c) << (8 * k);
+			}
+			raw[r * GB_RWORDS + wd] = v;
 		}
-		raw[i] = v;
 	}
 	__syncthreads();
 
@@ -930,7 +975,11 @@ cudaError_t orbx_upload_pattern()
 		umax[v] = v0;
 		++v0;
 	}
+	uint32_t inv20[72];
+	inv20[0] = 0;
+	for (int n = 1; n < 72; n++) inv20[n] = (1u << 20) / (uint32_t)n + 1u;
 	cudaError_t e;
+	if ((e = cudaMemcpyToSymbol(c_inv20, inv20, sizeof(inv20))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_pattern, pattern, sizeof(pattern))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax))) != cudaSuccess) return e;
 	return cudaSuccess;
@@ -939,8 +988,8 @@ cudaError_t orbx_upload_pattern()
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
-	dim3 block(64, 4), grid((D.w + 255) / 256, (D.h + 3) / 4, P.frames);
-	k_pyramid_resize<<<grid, block, 0, st>>>(P, level);
+	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + PY_TH - 1) / PY_TH, P.frames);
+	k_pyramid_resize<<<grid, 256, 0, st>>>(P, level);
 }
 
 void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
@@ -949,19 +998,21 @@ void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
 	k_fast_cells<<<grid, FT_THREADS, 0, st>>>(P);
 }
 
+int orbx_pyramid_tile_rows() { return PY_TH; }
+int orbx_pyramid_max_src_rows() { return PY_SRC; }
+
 size_t orbx_quadtree_smem(int node_cap)
 {
 	// listA, listB (16 B), items (8 B), childcnt (16 B), proc, pbase (4 B each), gone (1 B)
 	return (size_t)node_cap * (16 + 16 + 8 + 16 + 4 + 4 + 1) + 64;
 }
 
-void orbx_launch_quadtree(const OrbxPlanDev& P, cudaStream_t st)
+void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 {
 	const size_t smem = orbx_quadtree_smem(P.node_cap);
 	cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 grid(P.nlevels, P.frames);
-	// cell offsets live right behind the cell counts (the plan allocates 2x)
-	k_quadtree<<<grid, QT_THREADS, smem, st>>>(P, P.cell_count + (int64_t)P.frames * P.cells_per_frame);
+	k_quadtree<<<grid, QT_THREADS, smem, st>>>(P, cell_off);
 }
 
 void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)

@@ -53,6 +53,7 @@ struct OrbxPlanDev
 	uint8_t* pyr; uint8_t* blur; int64_t slab;         // frame slabs (levels >= 1 of pyr; all levels of blur)
 	uint32_t* cand;              // [frames][cand_per_frame] per-cell slots
 	int* cell_count;             // [frames][cells_per_frame]
+	const int4* cell_tab;        // [cells_per_frame] x0 | y0 << 16, view w | h << 16, level, cell index inside the level
 	uint32_t* qbuf0; uint32_t* qbuf1;   // [frames][cand_per_frame] quadtree ping-pong segments
 	int* cand_count;             // [frames][nlevels] DetectFAST totals (debug/probes)
 	uint32_t* sel;               // [frames][sel_per_frame] selected keypoints, list order
@@ -75,10 +76,12 @@ __device__ __forceinline__ int64_t orbx_level_pitch(const OrbxPlanDev& P, int le
 // kernel launchers (orbx_extract.cu)
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
 void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st);
-void orbx_launch_quadtree(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap);
+int orbx_pyramid_tile_rows();
+int orbx_pyramid_max_src_rows();
 cudaError_t orbx_upload_pattern();
 
 // matcher launchers (orbx_match.cu)
