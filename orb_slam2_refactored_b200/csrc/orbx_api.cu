@@ -85,6 +85,7 @@ struct orbx_extractor
 	OrbxPlanDev P;
 	DevBuf<uint8_t> pyr, blur, l0buf;   // l0buf: level 0 of every frame, back to back (host-buffer API uploads land here)
 	int64_t l0_pitch = 0, l0_stride = 0;
+	uint8_t* l0base = nullptr;          // l0buf.p + 256: kernels may read up to 16 bytes in front of a row (aligned 16-byte tile copies)
 	DevBuf<uint32_t> cand, qbuf0, qbuf1, sel;
 	DevBuf<int> cell_count, cand_count, sel_count;
 	DevBuf<int> root_x, xofs, yofs;
@@ -243,14 +244,23 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			L.ytab_base = (int)yofs.size();
 			yofs.resize(yofs.size() + L.h); ycoef.resize(ycoef.size() + L.h);
 			resize_tables(L.h, P.lv[s - 1].h, yofs.data() + L.ytab_base, ycoef.data() + L.ytab_base);
-			// the resize kernel stages the source rows of a 32-row output tile in shared memory
-			const int th = orbx_pyramid_tile_rows();
+			// the resize kernel stages the source rows/columns of a 128 x 32 output tile in shared memory
+			const int th = orbx_pyramid_tile_rows(), tw = orbx_pyramid_tile_cols();
+			int max_rows = 0, max_bytes = 0;
 			for (int y0 = 0; y0 < L.h; y0 += th)
 			{
 				const int y1 = std::min(y0 + th, L.h) - 1;
-				if (yofs[L.ytab_base + y1] + 1 - yofs[L.ytab_base + y0] + 1 > orbx_pyramid_max_src_rows())
-					return fail(ORBX_ERR_INVALID, "scaleFactor too large for the resize kernel (max about 2.2)");
+				max_rows = std::max(max_rows, std::min(yofs[L.ytab_base + y1] + 1, P.lv[s - 1].h - 1) - yofs[L.ytab_base + y0] + 1);
 			}
+			for (int x0 = 0; x0 < L.w; x0 += tw)
+			{
+				const int x1 = std::min(x0 + tw, L.w) - 1;
+				const int xa = xofs[L.xtab_base + x0] & ~15, xb = std::min(xofs[L.xtab_base + x1] + 1, P.lv[s - 1].w - 1);
+				max_bytes = std::max(max_bytes, ((xb - xa + 16) >> 4) * 16);
+			}
+			if (max_rows > orbx_pyramid_max_src_rows() || max_bytes > orbx_pyramid_max_src_bytes())
+				return fail(ORBX_ERR_INVALID, "scaleFactor too large for the resize kernel (max about 2.2)");
+			L.py_smem = max_rows * max_bytes;
 		}
 	}
 	P.slab = slab;
@@ -264,9 +274,10 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 
 	CU(cudaSetDevice(h->device));
 	const size_t F = (size_t)frames;
-	CU(h->pyr.ensure(F * slab)); CU(h->blur.ensure(F * slab));
+	CU(h->pyr.ensure(F * slab + 512)); CU(h->blur.ensure(F * slab));
 	h->l0_pitch = P.lv[0].pitch; h->l0_stride = (int64_t)P.lv[0].pitch * P.lv[0].h;   // frames back to back: one strided copy uploads a whole chunk
-	CU(h->l0buf.ensure(F * h->l0_stride));
+	CU(h->l0buf.ensure(F * h->l0_stride + 512));
+	h->l0base = h->l0buf.p + 256;
 	CU(h->cand.ensure(F * cands)); CU(h->qbuf0.ensure(F * cands)); CU(h->qbuf1.ensure(F * cands));
 	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
 	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl));
@@ -288,7 +299,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	}
 	CU(cudaStreamSynchronize(h->stream));    // the host vectors above die with this scope
 
-	P.pyr = h->pyr.p; P.blur = h->blur.p;
+	P.pyr = h->pyr.p + 256; P.blur = h->blur.p;
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
@@ -504,16 +515,16 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 	if (st != ORBX_OK) return st;
 	if (cap < h->P.sel_per_frame || cap >= 65536)
 		return fail(ORBX_ERR_CAPACITY, "cap must be >= orbx_max_keypoints() (and < 65536)");
-	const uint8_t* l0 = d_images;
-	int64_t l0_pitch = (int64_t)pitch, l0_stride = (int64_t)frame_stride;
-	if (((uintptr_t)d_images & 15) || (pitch & 3) || (frame_stride & 3))
-	{
-		// kernels read level 0 with aligned 32-bit loads: repack a misaligned input into the slab
+	// Level 0 is always copied into the padded level-0 buffer (the kernels stage tiles with aligned 16-byte copies that may
+	// reach a few bytes outside a row); this is ComputePyramid's own copyTo (:462) and costs 2 x 300 KiB of HBM traffic per frame.
+	if (frame_stride == pitch * (size_t)height)
+		CU(cudaMemcpy2DAsync(h->l0base, h->l0_pitch, d_images, pitch, width, (size_t)height * frames, cudaMemcpyDeviceToDevice, h->stream));
+	else
 		for (int f = 0; f < frames; f++)
-			CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)f * h->l0_stride, h->l0_pitch, d_images + (size_t)f * frame_stride, pitch,
+			CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, d_images + (size_t)f * frame_stride, pitch,
 			                     width, height, cudaMemcpyDeviceToDevice, h->stream));
-		l0 = h->l0buf.p; l0_pitch = h->l0_pitch; l0_stride = h->l0_stride;
-	}
+	const uint8_t* l0 = h->l0base;
+	const int64_t l0_pitch = h->l0_pitch, l0_stride = h->l0_stride;
 	orbx_status st2 = enqueue_extract(h, 0, frames, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
 	if (st2 == ORBX_OK) note_result(h, frames, cap, d_kps, d_desc, d_n);
 	return st2;
@@ -548,14 +559,14 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 		const int fc = std::min(chunk, frames - fb);
 		cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
 		if (frame_stride == pitch * (size_t)height)
-			CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
+			CU(cudaMemcpy2DAsync(h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
 			                     (size_t)height * fc, cudaMemcpyHostToDevice, st));
 		else
 			for (int f = fb; f < fb + fc; f++)
-				CU(cudaMemcpy2DAsync(h->l0buf.p + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
+				CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
 				                     height, cudaMemcpyHostToDevice, st));
 		st = (ci & 1) ? h->stream2 : h->stream;
-		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0buf.p, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
+		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
 		if (e != ORBX_OK) return e;
 		CU(cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st));
 		if (kps && desc && ccap > 0)

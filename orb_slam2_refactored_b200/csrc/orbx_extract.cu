@@ -10,6 +10,21 @@ namespace {
 
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): a tile is staged with one or two instructions per thread and
+// all of them in flight at once, which is what hides DRAM latency for these small tiles. Both addresses 16-byte aligned.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+	asm volatile("cp.async.commit_group;\n" ::);
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+__constant__ uint32_t c_inv20[72];   // c_inv20[n] = (1 << 20) / n + 1: floor(i / n) == (i * c_inv20[n]) >> 20 for n <= 64, i < 4096 (exhaustively checked)
+
 // =====================================================================================================
 // K1  pyramid_resize_u8 — cv::resize INTER_LINEAR 8UC1 in OpenCV's fixed point for
 //     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
@@ -18,45 +33,60 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x &
 #define PY_TW 128     // output tile
 #define PY_TH 32
 #define PY_SRC 72     // source rows a tile may touch: 31 * scaleFactor + 2; scale factors up to 2.2 (checked on the host)
+#define PY_SW 304     // source bytes per staged row: 15 (alignment) + 128 * scaleFactor + 2, rounded up to 16
 __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, const int level)
 {
-	// Two passes through shared memory. Horizontal: every source row the tile needs is filtered once, g = (s0*a0 + s1*a1) >> 4
-	// (the vertical pass only ever uses h >> 4, which fits 15 bits), two pixels per word; all loads of a thread are
-	// independent, so they overlap. Vertical: 4 output pixels per thread from two 8-byte shared loads.
-	__shared__ __align__(16) uint32_t g[PY_SRC * (PY_TW / 2)];
+	// The source rows/columns an output tile needs are staged in shared memory with 16-byte async copies (level buffers
+	// are padded: pitch a multiple of 128, 256 spare bytes in front and behind); then one thread = 4 output columns x 4 rows.
+	extern __shared__ __align__(16) uint8_t stile[];
 	const OrbxLevel& D = P.lv[level];
 	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
 	const int f = blockIdx.z, tid = threadIdx.x;
 	const int dx0 = blockIdx.x * PY_TW, dy0 = blockIdx.y * PY_TH;
-	const int dy_last = min(dy0 + PY_TH, D.h) - 1;
+	const int dy_last = min(dy0 + PY_TH, D.h) - 1, dx_last = min(dx0 + PY_TW, D.w) - 1;
 	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level - 1);
 	const int64_t sp = orbx_level_pitch(P, level - 1);
 	uint8_t* __restrict__ dst = P.pyr + (int64_t)f * P.slab + D.offset;
 	const int* __restrict__ yofs = P.yofs + D.ytab_base;
 	const short2* __restrict__ ycoef = P.ycoef + D.ytab_base;
+	const int* __restrict__ xofs = P.xofs + D.xtab_base;
 
 	const int s_lo = __ldg(yofs + dy0);
 	const int s_hi = min(__ldg(yofs + dy_last) + 1, sh - 1);
-	const int nsrc = min(s_hi - s_lo + 1, PY_SRC);
-
+	const int nsrc = s_hi - s_lo + 1;                       // <= PY_SRC (host-checked)
+	const int xa = __ldg(xofs + dx0) & ~15;                 // first staged source column
+	const int xb = min(__ldg(xofs + dx_last) + 1, sw - 1);  // last needed source column
+	const int nchunk = (xb - xa + 16) >> 4;                 // 16-byte chunks per row, <= PY_SW / 16 (host-checked)
+	const int rs = nchunk * 16;                             // staged row stride
 	{
-		const int cp = tid & 63, rg = tid >> 6;
-		const int c0 = min(dx0 + 2 * cp, D.w - 1), c1 = min(dx0 + 2 * cp + 1, D.w - 1);   // columns past the edge repeat the last one
-		const int x00 = __ldg(P.xofs + D.xtab_base + c0), x10 = __ldg(P.xofs + D.xtab_base + c1);
-		const short2 ca = __ldg(P.xcoef + D.xtab_base + c0), cb = __ldg(P.xcoef + D.xtab_base + c1);
-		const int x01 = min(x00 + 1, sw - 1), x11 = min(x10 + 1, sw - 1);
-		const uint8_t* __restrict__ row = src + (int64_t)(s_lo + rg) * sp;
-#pragma unroll 4
-		for (int r = rg; r < nsrc; r += 4, row += 4 * sp)
+		const uint8_t* __restrict__ g0 = src + (int64_t)s_lo * sp + xa;
+		for (int i = tid; i < nsrc * nchunk; i += 256)
 		{
-			const int h0 = (int)__ldg(row + x00) * ca.x + (int)__ldg(row + x01) * ca.y;
-			const int h1 = (int)__ldg(row + x10) * cb.x + (int)__ldg(row + x11) * cb.y;
-			g[r * (PY_TW / 2) + cp] = (uint32_t)(h0 >> 4) | ((uint32_t)(h1 >> 4) << 16);
+			const int r = (int)(((uint32_t)i * c_inv20[nchunk]) >> 20), c = i - r * nchunk;
+			cp_async16(stile + r * rs + c * 16, g0 + (int64_t)r * sp + c * 16);
 		}
 	}
-	__syncthreads();
-
 	const int q = tid & 31, grp = tid >> 5;
+	int x0r[4], x1r[4], a0[4], a1[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		const int dx = min(dx0 + 4 * q + j, D.w - 1);   // columns past the edge repeat the last one; they land in row padding
+		const int sx = __ldg(xofs + dx);
+		const short2 a = __ldg(P.xcoef + D.xtab_base + dx);
+		x0r[j] = sx - xa; x1r[j] = min(sx + 1, sw - 1) - xa;
+		a0[j] = a.x; a1[j] = a.y;
+	}
+	int sy0[PY_TH / 8]; short2 bb[PY_TH / 8];
+#pragma unroll
+	for (int k = 0; k < PY_TH / 8; k++)
+	{
+		const int dy = min(dy0 + grp + 8 * k, D.h - 1);
+		sy0[k] = __ldg(yofs + dy);
+		bb[k] = __ldg(ycoef + dy);
+	}
+	cp_async_wait_all();
+	__syncthreads();
 	if (dx0 + 4 * q >= D.w)
 		return;
 #pragma unroll
@@ -64,18 +94,18 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 	{
 		const int dy = dy0 + grp + 8 * k;
 		if (dy >= D.h) break;
-		const int sy0 = __ldg(yofs + dy);
-		const short2 b = __ldg(ycoef + dy);
-		const int r0 = sy0 - s_lo, r1 = min(sy0 + 1, sh - 1) - s_lo;
-		const uint2 u0 = *reinterpret_cast<const uint2*>(g + r0 * (PY_TW / 2) + 2 * q);
-		const uint2 u1 = *reinterpret_cast<const uint2*>(g + r1 * (PY_TW / 2) + 2 * q);
-		const int b0 = b.x, b1 = b.y;
-		const int v0 = (((b0 * (int)(u0.x & 0xffffu)) >> 16) + ((b1 * (int)(u1.x & 0xffffu)) >> 16) + 2) >> 2;
-		const int v1 = (((b0 * (int)(u0.x >> 16)) >> 16) + ((b1 * (int)(u1.x >> 16)) >> 16) + 2) >> 2;
-		const int v2 = (((b0 * (int)(u0.y & 0xffffu)) >> 16) + ((b1 * (int)(u1.y & 0xffffu)) >> 16) + 2) >> 2;
-		const int v3 = (((b0 * (int)(u0.y >> 16)) >> 16) + ((b1 * (int)(u1.y >> 16)) >> 16) + 2) >> 2;
-		// coefficients sum to 2048, so v is already in [0, 255]
-		const uint32_t out = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+		const uint8_t* r0 = stile + (sy0[k] - s_lo) * rs;
+		const uint8_t* r1 = stile + (min(sy0[k] + 1, sh - 1) - s_lo) * rs;
+		const int b0 = bb[k].x, b1 = bb[k].y;
+		uint32_t out = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			const int h0 = (int)r0[x0r[j]] * a0[j] + (int)r0[x1r[j]] * a1[j];
+			const int h1 = (int)r1[x0r[j]] * a0[j] + (int)r1[x1r[j]] * a1[j];
+			const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;   // coefficients sum to 2048: v in [0, 255]
+			out |= (uint32_t)v << (8 * j);
+		}
 		*reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx0 + 4 * q) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
 	}
 }
@@ -88,7 +118,7 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 //     Candidates are emitted row-major into the cell's private slot range, so DetectFAST's cell-major /
 //     row-major push_back order is reproduced without atomics on global memory.
 // =====================================================================================================
-#define FT_TS 80            // tile row stride in bytes (view <= 66 px + up to 3 px alignment slack)
+#define FT_TS 96            // tile row stride in bytes (view <= 66 px + up to 15 px alignment slack, 16-byte chunks)
 #define FT_TH 66
 #define FT_SS 64            // score row stride (region <= 60 px + 1 px zero border each side)
 #define FT_MAXR 60
@@ -127,8 +157,6 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 	return max(dark, bright);
 }
 
-__constant__ uint32_t c_inv20[72];   // c_inv20[n] = (1 << 20) / n + 1: floor(i / n) == (i * c_inv20[n]) >> 20 for n <= 64, i < 4096 (exhaustively checked)
-
 // One CTA (4 warps) per cell. Phases: stage view -> arc score S of every region pixel (dense: on textured frames a third
 // of the pixels pass any cheap rejection at minTh, so a branch-free network on all of them is cheaper than test + compaction);
 // pixels with S > minTh (about a fifth) are appended to a list -> strict 8-neighbour local-maximum test of the listed pixels
@@ -150,18 +178,16 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 	const int npx = rw * rh;
 	const uint32_t inv_rw = c_inv20[rw];
 
-	// ---- stage the view: aligned 32-bit loads; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
+	// ---- stage the view with 16-byte async copies; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
 	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl);
 	const int64_t pitch = orbx_level_pitch(P, lvl);
-	const int sh = x0 & 3;
-	const int nwords = (sh + vw + 3) >> 2;
-	const uint32_t inv_nw = c_inv20[nwords];
+	const int sh = x0 & 15;
+	const int nchunk = (sh + vw + 15) >> 4;          // <= 6
 	const uint8_t* __restrict__ src0 = img + (int64_t)y0 * pitch + (x0 - sh);
-	for (int i = tid; i < vh * nwords; i += FT_THREADS)
+	for (int i = tid; i < vh * nchunk; i += FT_THREADS)
 	{
-		const int r = (int)(((uint32_t)i * inv_nw) >> 20), wd = i - r * nwords;
-		const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src0 + (int64_t)r * pitch) + wd);
-		*reinterpret_cast<uint32_t*>(tile + r * FT_TS + wd * 4) = v;
+		const int r = (int)(((uint32_t)i * c_inv20[nchunk]) >> 20), c = i - r * nchunk;
+		cp_async16(tile + r * FT_TS + c * 16, src0 + (int64_t)r * pitch + c * 16);
 	}
 	// zero frame around the scores (neighbours outside the detection region count as 0)
 	if (tid < FT_SS / 4)
@@ -175,6 +201,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 		score[(i + 1) * FT_SS + rw + 1] = 0;
 	}
 	bm_lo[tid] = 0; bm_hi[tid] = 0;
+	cp_async_wait_all();
 	__syncthreads();
 
 	// ---- arc score of every region pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballot of
@@ -721,7 +748,8 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 #define GB_TW 128                 // output tile
 #define GB_TH 32
 #define GB_RROWS (GB_TH + 8)      // raw rows y0-4 .. y0+35 (the row-pair grid needs an even start)
-#define GB_RWORDS (GB_TW / 4 + 2) // raw cols x0-4 .. x0+131 as 34 words
+#define GB_RWORDS 40              // raw cols x0-16 .. x0+143 as ten 16-byte chunks
+#define GB_LEFT 16                // raw byte of image column x0
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
@@ -745,47 +773,37 @@ __global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int l
 	uint8_t* __restrict__ dst = P.blur + (int64_t)f * P.slab + L.offset;
 	const int w = L.w, h = L.h;
 
-	// ---- stage the raw tile. Fast pass: every word with one aligned 32-bit load (address clamped into the row, so words
-	//      that touch the border hold junk); border pass: the <= 3 words per row that overlap [-3, 0) or [w, w + 3) are
-	//      rebuilt byte by byte with REFLECT_101 (-1 -> 1, n -> n-2). Words further out only feed outputs >= w.
-	const int gx_max = (w - 4) & ~3;
-	for (int i = tid; i < GB_RROWS * GB_RWORDS; i += 256)
+	// ---- stage the raw tile with 16-byte async copies (rows beyond the image come from the reflected row; the padded level
+	//      buffers make columns -16..-1 and w.. legal to read), then patch the 3 + 3 border columns in place with
+	//      REFLECT_101 (-1 -> 1, w -> w-2): the mirrored pixels are inside the same staged row.
+	uint8_t* rawb = reinterpret_cast<uint8_t*>(raw);
+	for (int i = tid; i < GB_RROWS * (GB_RWORDS / 4); i += 256)
 	{
-		const int r = i / GB_RWORDS, wd = i - r * GB_RWORDS;
+		const int r = i / (GB_RWORDS / 4), c = i - r * (GB_RWORDS / 4);
 		const int gy = reflect101(min(y0 - 4 + r, h + 2), h);
-		const int gx = min(max(x0 - 4 + 4 * wd, 0), gx_max);
-		raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)gy * sp + gx));
+		cp_async16(rawb + r * (GB_RWORDS * 4) + c * 16, src + (int64_t)gy * sp + (x0 - GB_LEFT) + c * 16);
 	}
+	cp_async_wait_all();
 	__syncthreads();
+	if (tid < GB_RROWS)
 	{
-		const int wl = (x0 == 0) ? 0 : -1;                    // word holding cols -4..-1
-		const int wr = (w - (x0 - 4)) >> 2;                   // first word not entirely inside [0, w)
-		const int r = tid / 3, which = tid - r * 3;
-		const int wd = which == 0 ? wl : wr + which - 1;
-		if (r < GB_RROWS && wd >= 0 && wd < GB_RWORDS && (which == 0 || (x0 - 4 + 4 * wd) < w + 3))
+		uint8_t* row = rawb + tid * (GB_RWORDS * 4) + GB_LEFT - x0;     // row[x] = image column x
+		if (x0 == 0) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
+		if (w < x0 + GB_TW + 3)                                         // columns w .. w+2 are inside this tile's window
 		{
-			const int gy = reflect101(min(y0 - 4 + r, h + 2), h);
-			const uint8_t* __restrict__ row = src + (int64_t)gy * sp;
-			const int gx = x0 - 4 + 4 * wd;
-			uint32_t v = 0;
 #pragma unroll
-			for (int k = 0; k < 4; k++)
-			{
-				const int a = abs(gx + k);
-				const int c = max(min(a, 2 * w - 2 - a), 0);      // reflect101 for -w < x < 2w - 1; further out is never used
-				v |= (uint32_t)__ldg(row + c) << (8 * k);
-			}
-			raw[r * GB_RWORDS + wd] = v;
+			for (int k = 0; k < 3; k++)
+				if (w + k < x0 + GB_TW + 3 && w - 2 - k >= x0 - GB_LEFT) row[w + k] = row[w - 2 - k];
 		}
 	}
 	__syncthreads();
 
-	// ---- horizontal pass: item = (row pair, column quad); output x = x0 + 4q + k taps raw cols 4q+1+k .. 4q+7+k
+	// ---- horizontal pass: item = (row pair, column quad); output x = x0 + 4q + k taps image columns x-3 .. x+3
 	const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24), KB = 48u | (34u << 8) | (18u << 16);
 	for (int i = tid; i < (GB_RROWS / 2) * (GB_TW / 4); i += 256)
 	{
 		const int pr = i >> 5, q = i & 31;
-		const uint32_t* r0 = raw + (2 * pr) * GB_RWORDS + q;
+		const uint32_t* r0 = raw + (2 * pr) * GB_RWORDS + q + 3;     // words holding image columns x0+4q-4 .. x0+4q+7
 		const uint32_t* r1 = r0 + GB_RWORDS;
 		const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2];
 		uint4 o;
@@ -989,7 +1007,8 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
 	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + PY_TH - 1) / PY_TH, P.frames);
-	k_pyramid_resize<<<grid, 256, 0, st>>>(P, level);
+	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem)
+	k_pyramid_resize<<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 }
 
 void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
@@ -1000,6 +1019,8 @@ void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
 
 int orbx_pyramid_tile_rows() { return PY_TH; }
 int orbx_pyramid_max_src_rows() { return PY_SRC; }
+int orbx_pyramid_tile_cols() { return PY_TW; }
+int orbx_pyramid_max_src_bytes() { return PY_SW; }
 
 size_t orbx_quadtree_smem(int node_cap)
 {

@@ -38,6 +38,7 @@ struct OrbxLevel
 	// resize tables of this level as destination (level >= 1)
 	int xtab_base, ytab_base;
 	float scale;                 // scaleFactors_[s]
+	int py_smem;                 // dynamic shared memory of the resize kernel producing this level
 };
 
 struct OrbxPlanDev
@@ -82,6 +83,8 @@ void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d
 size_t orbx_quadtree_smem(int node_cap);
 int orbx_pyramid_tile_rows();
 int orbx_pyramid_max_src_rows();
+int orbx_pyramid_tile_cols();
+int orbx_pyramid_max_src_bytes();
 cudaError_t orbx_upload_pattern();
 
 // matcher launchers (orbx_match.cu)
