@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20',
                                           '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -138,7 +138,7 @@ def cpu_knn_rate(o, threads, nq=4096, nt=250000):
     return nq * nt / dt / 1e9, dt, f'{nq} queries x {nt} train rows, {threads} threads'
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     o, kind, native = load_cpu_reference()
@@ -166,13 +166,13 @@ def run_reference(args, rank, world):
         'knn': {'value': gp, 'unit': 'Gpairs/s', 'sample': knn_sample, 'cores': threads},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # this repository's arm
 # ---------------------------------------------------------------------------------------------------------------------
-def run_b200(args, rank, world, local_rank):
+def run_b200(args, rank, world, local_rank, emit):
     import torch
     import torch.distributed as dist
     from orb_slam2_refactored_b200 import api
@@ -384,7 +384,7 @@ def run_b200(args, rank, world, local_rank):
             'cpu_baseline': cpu,
             'knn': knn,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
 
 
 def main():
@@ -403,8 +403,18 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     if world > 1:
         import torch
@@ -412,7 +422,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
-        run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank, emit)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -1,0 +1,41 @@
+"""The C++ drop-in classes (include/orbx/ORBextractor.h, ORBmatcher.h): compile against the OpenCV shim on any machine;
+run against the oracle on the GPU box."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, 'tests', 'cpp', '_build', 'dropin_test')
+
+
+def build_exe():
+    from orb_slam2_refactored_b200 import build
+    from oracle import bindings
+    lib = build.build()
+    bindings.build()
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    src = os.path.join(ROOT, 'tests', 'cpp', 'dropin_test.cc')
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(lib)):
+        return
+    cmd = ['g++', '-std=c++14', '-O1', '-Wall', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oracle', 'cvshim'),
+           '-I', os.path.join(ROOT, 'oracle'), src, '-o', EXE,
+           '-L', os.path.dirname(lib), '-lorbx_b200', '-L', os.path.join(ROOT, 'oracle', '_build'), '-lorb_oracle',
+           '-Wl,-rpath,' + os.path.dirname(lib), '-Wl,-rpath,' + os.path.join(ROOT, 'oracle', '_build')]
+    subprocess.run(cmd, check=True)
+
+
+def test_dropin_headers_compile_and_link():
+    build_exe()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_dropin_matches_oracle():
+    from orb_slam2_refactored_b200 import synth
+    build_exe()
+    L, R = synth.stereo_pair(7, 752, 480)
+    r = subprocess.run([EXE, '752', '480', '1200'], input=L.tobytes() + R.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert r.stdout.decode().startswith('OK')
