@@ -266,8 +266,15 @@ def run_b200(args, rank, world, local_rank, emit):
     # roofline of the dominant stage, per launch: its algorithmic bytes for the whole batch / its device time
     dom_bytes_per_step = alg[dominant] * B
     dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0
+    traffic = None
+    tj = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    kname = {'fast': 'k_fast_cells', 'describe': 'k_orient_describe', 'quadtree': 'k_quadtree'}.get(dominant)
+    if os.path.exists(tj) and kname:
+        t = json.load(open(tj)).get(kname)
+        if t:   # dram__bytes_read + write of one launch at 256 frames (ncu --set full, profiles/), scaled to this batch
+            traffic = t['dram_bytes_per_launch'] * B / 256.0
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': dom_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': dom_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'launches_per_step': launches_per_stage[dominant],
                 'algorithmic_bytes_per_launch': dom_bytes_per_step / launches_per_stage[dominant],
                 'avg_launch_ms': per_step[dominant] / launches_per_stage[dominant],
