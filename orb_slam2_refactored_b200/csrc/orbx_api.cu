@@ -77,6 +77,7 @@ struct orbx_extractor
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr;     // second lane of the chunk pipeline of the host-buffer API
 	cudaEvent_t done = nullptr;
+	cudaEvent_t fork = nullptr, join = nullptr;   // order the second lane inside the handle's stream for the device-resident API
 	std::vector<float> scale, inv_scale, sigma_sq, inv_sigma_sq;
 	std::vector<int> quota;
 
@@ -400,6 +401,8 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 	cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = orbx_upload_pattern();
 	if (e != cudaSuccess)
 	{
@@ -426,6 +429,8 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
+	if (h->fork) cudaEventDestroy(h->fork);
+	if (h->join) cudaEventDestroy(h->join);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	if (h->stream2) cudaStreamDestroy(h->stream2);
 	delete h;
@@ -525,7 +530,24 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 			                     width, height, cudaMemcpyDeviceToDevice, h->stream));
 	const uint8_t* l0 = h->l0base;
 	const int64_t l0_pitch = h->l0_pitch, l0_stride = h->l0_stride;
-	orbx_status st2 = enqueue_extract(h, 0, frames, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+	// The stages are bound by different things (FAST by instruction issue, pyramid/descriptor by memory latency), so the two
+	// halves of a large batch run on two streams and fill each other's stalls. The second lane is forked from and joined back
+	// into the handle's stream, so the call stays stream-ordered for the caller.
+	int lanes = (frames >= 64 && !h->stage_timing) ? 2 : 1;
+	if (const char* e = getenv("ORBX_LANES")) lanes = std::max(1, std::min(2, atoi(e)));
+	orbx_status st2 = ORBX_OK;
+	if (lanes == 1)
+		st2 = enqueue_extract(h, 0, frames, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+	else
+	{
+		const int half = (frames + 1) / 2;
+		CU(cudaEventRecord(h->fork, h->stream));
+		CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
+		st2 = enqueue_extract(h, 0, half, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+		if (st2 == ORBX_OK) st2 = enqueue_extract(h, half, frames - half, h->stream2, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+		CU(cudaEventRecord(h->join, h->stream2));
+		CU(cudaStreamWaitEvent(h->stream, h->join, 0));
+	}
 	if (st2 == ORBX_OK) note_result(h, frames, cap, d_kps, d_desc, d_n);
 	return st2;
 }

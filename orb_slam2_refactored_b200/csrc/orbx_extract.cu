@@ -157,16 +157,36 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 	return max(dark, bright);
 }
 
-// One CTA (4 warps) per cell. Phases: stage view -> arc score S of every region pixel (dense: on textured frames a third
-// of the pixels pass any cheap rejection at minTh, so a branch-free network on all of them is cheaper than test + compaction);
-// pixels with S > minTh (about a fifth) are appended to a list -> strict 8-neighbour local-maximum test of the listed pixels
-// only. Local maxima are threshold independent: survivors at t are {local max, S > t}, so the retry of :526-530 is "use
-// iniTh if that set is non-empty, else minTh". Survivors set a bit in a row-major bitmap -> ordered emit from the bitmap.
+// Upper bound of the arc score from the 4 opposite pairs at even ring positions: every arc of 9 contains one pixel of each
+// pair (k, k+8), so min_arc(ring) <= max(ring_k, ring_k+8) for every k, hence
+//   S_bright <= min_k max(ring_k, ring_k+8) - centre,   S_dark <= centre - max_k min(ring_k, ring_k+8).
+// Same packing as the exact network: both polarities in one VIMNMX.U16x2 chain.
+__device__ __forceinline__ int arc_score_bound(const uint8_t* __restrict__ c)
+{
+	constexpr int R[8] = { 3 * FT_TS, 2 * FT_TS + 2, 3, -2 * FT_TS + 2, -3 * FT_TS, -2 * FT_TS - 2, -3, 2 * FT_TS - 2 };   // ring 0,2,..,14
+	uint32_t v[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+		v[k] = (uint32_t)c[R[k]] * 0xFFFF0001u + 0x00FF0000u;
+	const uint32_t m = __vminu2(__vminu2(__vmaxu2(v[0], v[4]), __vmaxu2(v[1], v[5])), __vminu2(__vmaxu2(v[2], v[6]), __vmaxu2(v[3], v[7])));
+	const int centre = c[0];
+	return max((int)(m & 0xffffu) - centre, centre - 255 + (int)(m >> 16));
+}
+
+// One CTA (4 warps) per cell:
+//   A. every region pixel gets the cheap upper bound U >= S; warp ballots of (U > iniTh) and (minTh < U <= iniTh) are the
+//      row-major bitmaps of the pixels that can matter at either threshold;
+//   B. the exact arc score S is computed only for the pixels of the first bitmap (a few percent), compacted into a list so
+//      that every lane works; pixels never evaluated keep score 0, which is what M_t = (S > t ? S - 1 : 0) gives them anyway;
+//   C. strict 8-neighbour local maxima among them with S > iniTh. If the cell has none (the retry of :526-530), the second
+//      bitmap is evaluated too and the test repeats with minTh over both;
+//   D. ordered emit from the survivor bitmap: DetectFAST's cell-major / row-major push_back order without global atomics.
 __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 {
 	__shared__ __align__(16) uint8_t tile[FT_TH * FT_TS];
-	__shared__ __align__(4) uint8_t score[(FT_MAXR + 2) * FT_SS];
-	__shared__ uint32_t bm_cand[FT_THREADS], bm_lo[FT_THREADS], bm_hi[FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
+	__shared__ __align__(16) uint8_t score[(FT_MAXR + 2) * FT_SS];
+	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
+	__shared__ uint32_t bm_a[FT_THREADS], bm_b[FT_THREADS], bm_sel[FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
 	__shared__ int s_wsum[FT_THREADS / 32];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -186,88 +206,120 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 	const uint8_t* __restrict__ src0 = img + (int64_t)y0 * pitch + (x0 - sh);
 	for (int i = tid; i < vh * nchunk; i += FT_THREADS)
 	{
-		const int r = (int)(((uint32_t)i * c_inv20[nchunk]) >> 20), c = i - r * nchunk;
-		cp_async16(tile + r * FT_TS + c * 16, src0 + (int64_t)r * pitch + c * 16);
+		const int r = (int)(((uint32_t)i * c_inv20[nchunk]) >> 20), cc = i - r * nchunk;
+		cp_async16(tile + r * FT_TS + cc * 16, src0 + (int64_t)r * pitch + cc * 16);
 	}
-	// zero frame around the scores (neighbours outside the detection region count as 0)
-	if (tid < FT_SS / 4)
-	{
-		reinterpret_cast<uint32_t*>(score)[tid] = 0;
-		reinterpret_cast<uint32_t*>(score + (rh + 1) * FT_SS)[tid] = 0;
-	}
-	for (int i = tid; i < rh; i += FT_THREADS)
-	{
-		score[(i + 1) * FT_SS] = 0;
-		score[(i + 1) * FT_SS + rw + 1] = 0;
-	}
-	bm_lo[tid] = 0; bm_hi[tid] = 0;
+	for (int i = tid; i < (rh + 2) * (FT_SS / 4); i += FT_THREADS)
+		reinterpret_cast<uint32_t*>(score)[i] = 0;
+	bm_a[tid] = 0; bm_b[tid] = 0; bm_sel[tid] = 0;
 	cp_async_wait_all();
 	__syncthreads();
 
-	// ---- arc score of every region pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballot of
-	//      "S > minTh" IS the bitmap word of those pixels: no list, no atomics.
 	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
+
+	// ---- A: upper bound for every pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballots
+	//      are the bitmap words of those pixels.
 	for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
 	{
 		const int i = i0 + tid;
-		bool is_cand = false;
+		int u = 0;
 		if (i < npx)
 		{
 			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
-			score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
-			is_cand = s > tmin;
+			u = arc_score_bound(t0 + ry * FT_TS + rx);
 		}
-		const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-		if (lane == 0) bm_cand[(i0 >> 5) + warp] = bal;
+		const unsigned ba = __ballot_sync(0xffffffffu, u > tini), bb = __ballot_sync(0xffffffffu, u > tmin && u <= tini);
+		if (lane == 0) { bm_a[(i0 >> 5) + warp] = ba; bm_b[(i0 >> 5) + warp] = bb; }
 	}
 	__syncthreads();
 
-	// ---- strict local maxima among the candidates, same pixel-to-lane mapping; results are ballots again
-	bool hi_any = false;
-	for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
-	{
-		const unsigned cw = bm_cand[(i0 >> 5) + warp];
-		if (cw == 0) continue;                       // warp-uniform
-		bool lm = false, lmh = false;
-		if ((cw >> lane) & 1u)
+	// helpers -------------------------------------------------------------------------------------------------------
+	// exclusive block scan of one int per thread; returns this thread's offset, total in `total`
+	auto block_scan = [&](int v, int& total) {
+		int inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
 		{
-			const int i = i0 + tid;
+			const int t = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += t;
+		}
+		__syncthreads();                   // s_wsum may still be read from the previous scan
+		if (lane == 31) s_wsum[warp] = inc;
+		__syncthreads();
+		int base = inc - v;
+		total = 0;
+#pragma unroll
+		for (int w = 0; w < FT_THREADS / 32; w++)
+		{
+			const int t = s_wsum[w];
+			if (w < warp) base += t;
+			total += t;
+		}
+		return base;
+	};
+	// append the pixels of a bitmap to the list (row-major inside the bitmap); returns how many
+	auto expand = [&](const uint32_t* bm, int at) {
+		uint32_t w = bm[tid];
+		int total;
+		int pos = at + block_scan(__popc(w), total);
+		while (w)
+		{
+			list[pos++] = (uint16_t)(tid * 32 + __ffs(w) - 1);
+			w &= w - 1;
+		}
+		return total;
+	};
+	// exact score of list[from, to)
+	auto evaluate = [&](int from, int to) {
+		for (int j = from + tid; j < to; j += FT_THREADS)
+		{
+			const int i = list[j];
+			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
+			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
+			score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
+		}
+	};
+	// strict local maxima with S > t among list[0, to): set their bit; returns whether this thread found one
+	auto select = [&](int to, int t) {
+		bool found = false;
+		for (int j = tid; j < to; j += FT_THREADS)
+		{
+			const int i = list[j];
 			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
 			const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
 			const int s = sp[0];
-			const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
-			                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
-			lm = s > m;
-			lmh = lm && s > tini;
+			if (s > t)
+			{
+				const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
+				                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
+				if (s > m) { atomicOr(&bm_sel[i >> 5], 1u << (i & 31)); found = true; }
+			}
 		}
-		const unsigned blo = __ballot_sync(0xffffffffu, lm), bhi = __ballot_sync(0xffffffffu, lmh);
-		if (lane == 0) { bm_lo[(i0 >> 5) + warp] = blo; bm_hi[(i0 >> 5) + warp] = bhi; }
-		hi_any |= bhi != 0;
-	}
-	const int any_hi = __syncthreads_or(hi_any);
-	uint32_t selm = any_hi ? bm_hi[tid] : bm_lo[tid];
+		return found;
+	};
 
-	// ---- ordered emit: thread t owns bitmap word t = pixels [32t, 32t + 32); exclusive scan of the popcounts
-	const int cnt = __popc(selm);
-	int inc = cnt;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1)
-	{
-		const int t = __shfl_up_sync(0xffffffffu, inc, d);
-		if (lane >= d) inc += t;
-	}
-	if (lane == 31) s_wsum[warp] = inc;
+	// ---- B + C at iniTh
+	const int n1 = expand(bm_a, 0);
 	__syncthreads();
-	int base = inc - cnt, total = 0;
-#pragma unroll
-	for (int w = 0; w < FT_THREADS / 32; w++)
+	evaluate(0, n1);
+	__syncthreads();
+	const int any_hi = __syncthreads_or(select(n1, tini));
+	if (!any_hi)
 	{
-		const int v = s_wsum[w];
-		if (w < warp) base += v;
-		total += v;
+		// ---- retry at minTh (:529-530): the pixels with minTh < U <= iniTh become relevant too
+		const int n2 = expand(bm_b, n1);
+		__syncthreads();
+		evaluate(n1, n1 + n2);
+		__syncthreads();
+		select(n1 + n2, tmin);
+		__syncthreads();
 	}
+
+	// ---- D: ordered emit; thread t owns bitmap word t = pixels [32t, 32t + 32)
+	uint32_t selm = bm_sel[tid];
+	int total;
+	int base = block_scan(__popc(selm), total);
 	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
 	while (selm)
 	{
