@@ -275,7 +275,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 
 	CU(cudaSetDevice(h->device));
 	const size_t F = (size_t)frames;
-	CU(h->pyr.ensure(F * slab + 512)); CU(h->blur.ensure(F * slab));
+	CU(h->pyr.ensure(F * slab + 512)); CU(h->blur.ensure(F * slab + 512));
 	h->l0_pitch = P.lv[0].pitch; h->l0_stride = (int64_t)P.lv[0].pitch * P.lv[0].h;   // frames back to back: one strided copy uploads a whole chunk
 	CU(h->l0buf.ensure(F * h->l0_stride + 512));
 	h->l0base = h->l0buf.p + 256;

@@ -929,55 +929,119 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 	return a;
 }
 
-__global__ void __launch_bounds__(256) k_orient_describe(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps,
-                                                         uint8_t* __restrict__ d_desc, int32_t* __restrict__ d_n)
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
 {
-	__shared__ uint32_t s_pat[256];      // pair p -> (x0,y0,x1,y1) int8x4, transposed so lane reads are conflict-free
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
+#define OD_WARPS 8
+#define OD_PS 80                                     // patch row stride in shared memory (16-byte chunks; 20 words spreads rows over banks)
+#define OD_IMG_ROWS 31                               // un-blurred patch rows y-15 .. y+15, 48 bytes each from (x-16) & ~15
+#define OD_BLR_ROWS 37                               // blurred patch rows y-18 .. y+18, 64 bytes each from (x-18) & ~15
+#define OD_WARP_BYTES ((OD_IMG_ROWS + OD_BLR_ROWS) * OD_PS)
+#define OD_SMEM (OD_WARPS * OD_WARP_BYTES + 256 * 16 + 128 * 8)
+
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps,
+                                                                  uint8_t* __restrict__ d_desc, int32_t* __restrict__ d_n)
+{
+	// One warp per keypoint. Both patches the keypoint touches (31x31 of the level for IC_Angle, 37x37 of the blurred level for
+	// the 512 rBRIEF samples) are staged in shared memory with 16-byte async copies — 241 coalesced chunks instead of ~570
+	// scattered byte gathers — and everything after that reads shared memory.
+	extern __shared__ __align__(16) uint8_t od_smem[];
+	float4* s_pat = reinterpret_cast<float4*>(od_smem + OD_WARPS * OD_WARP_BYTES);   // pair p = 8*byte + bit -> (x0,y0,x1,y1), stored at [bit][byte]
+	uint2* s_mom = reinterpret_cast<uint2*>(s_pat + 256);                            // [k][|v|]: .x = ones mask, .y = column offsets u (s8) of window word k
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int f = blockIdx.y;
 	{
 		const int p = tid;   // 256 pairs
-		const uint32_t w = (uint32_t)(uint8_t)c_pattern[4 * p] | ((uint32_t)(uint8_t)c_pattern[4 * p + 1] << 8) |
-		                   ((uint32_t)(uint8_t)c_pattern[4 * p + 2] << 16) | ((uint32_t)(uint8_t)c_pattern[4 * p + 3] << 24);
-		s_pat[(p & 7) * 32 + (p >> 3)] = w;    // byte b = p>>3 handles pairs 8b..8b+7; stored at [bit][byte]
+		s_pat[(p & 7) * 32 + (p >> 3)] = make_float4((float)c_pattern[4 * p], (float)c_pattern[4 * p + 1], (float)c_pattern[4 * p + 2], (float)c_pattern[4 * p + 3]);
+		if (tid < 128)
+		{
+			// window word k holds columns u = 4k - 16 .. 4k - 13 of a disc row; inside the disc iff |u| <= umax[|v|]
+			const int k = tid >> 4, av = tid & 15, d = c_umax[av];
+			uint32_t ones = 0, us = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+			{
+				const int u = 4 * k + j - 16;
+				if (abs(u) <= d) { ones |= 1u << (8 * j); us |= (uint32_t)(uint8_t)(signed char)u << (8 * j); }
+			}
+			s_mom[k * 16 + av] = make_uint2(ones, us);
+		}
 	}
-	__syncthreads();
 
-	// which level does output slot `slot` belong to (levels are concatenated in order, :792-819)
-	const int slot = blockIdx.x * 8 + warp;
-	const int* __restrict__ cnt = P.sel_count + (int64_t)f * P.nlevels;
-	int lvl = -1, start = 0, total = 0;
-	for (int l = 0; l < P.nlevels; l++)
+	// which level does output slot `slot` belong to (levels are concatenated in order, :792-819): lane l holds level l's count
+	const int slot = blockIdx.x * OD_WARPS + warp;
+	const int cnt = (lane < P.nlevels) ? P.sel_count[(int64_t)f * P.nlevels + lane] : 0;
+	int incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 16; d <<= 1)
 	{
-		const int c = cnt[l];
-		if (lvl < 0 && slot < total + c) { lvl = l; start = total; }
-		total += c;
+		const int t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += t;
 	}
+	const int total = __shfl_sync(0xffffffffu, incl, ORBX_MAX_LEVELS - 1);
+	const unsigned inside = __ballot_sync(0xffffffffu, lane < P.nlevels && slot < incl);
 	if (slot == 0 && lane == 0) d_n[f] = total;
-	if (lvl < 0 || slot >= P.out_cap)
+	const bool live = inside != 0 && slot < P.out_cap;
+	int lvl = 0, x = 0, y = 0, resp = 0;
+	uint8_t* pimg = od_smem + warp * OD_WARP_BYTES;
+	uint8_t* pblr = pimg + OD_IMG_ROWS * OD_PS;
+	int xi = 0, xb = 0;
+	if (live)
+	{
+		lvl = __ffs(inside) - 1;
+		const int start = __shfl_sync(0xffffffffu, incl - cnt, lvl);
+		const OrbxLevel& L = P.lv[lvl];
+		const uint32_t kp = P.sel[(int64_t)f * P.sel_per_frame + L.sel_base + (slot - start)];
+		x = orbx_px(kp); y = orbx_py(kp); resp = orbx_pr(kp);
+		const int64_t ip = orbx_level_pitch(P, lvl);
+		xi = (x - 16) & ~15; xb = (x - 18) & ~15;
+		const uint8_t* __restrict__ gi = orbx_level_ptr(P, f, lvl) + (int64_t)(y - 15) * ip + xi;
+		const uint8_t* __restrict__ gb = P.blur + (int64_t)f * P.slab + L.offset + (int64_t)(y - 18) * L.pitch + xb;
+		for (int i = lane; i < OD_IMG_ROWS * 3; i += 32)
+		{
+			const int r = i / 3, c = i - r * 3;
+			cp_async16(pimg + r * OD_PS + c * 16, gi + (int64_t)r * ip + c * 16);
+		}
+		for (int i = lane; i < OD_BLR_ROWS * 4; i += 32)
+		{
+			const int r = i >> 2, c = i & 3;
+			cp_async16(pblr + r * OD_PS + c * 16, gb + (int64_t)r * L.pitch + c * 16);
+		}
+	}
+	cp_async_wait_all();
+	__syncthreads();            // patches of this warp and the block's tables are in shared memory
+	if (!live)
 		return;
 	const OrbxLevel& L = P.lv[lvl];
-	const uint32_t kp = P.sel[(int64_t)f * P.sel_per_frame + L.sel_base + (slot - start)];
-	const int x = orbx_px(kp), y = orbx_py(kp), resp = orbx_pr(kp);
 
-	// ---- intensity centroid over the radius-15 disc: lane = column u in [-15,15]
-	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl) + (int64_t)y * orbx_level_pitch(P, lvl) + x;
-	const int64_t ip = orbx_level_pitch(P, lvl);
+	// ---- intensity centroid over the radius-15 disc (IC_Angle, :74-101): lane = disc row v in [-15, 15]. The row's 32 bytes
+	//      [x-16, x+15] are 9 shared-memory words, re-aligned with funnel shifts and reduced with IDP.4A against the per-row
+	//      coefficient words: row sum (m01 = sum v * I) and sum of u * I (m10). Integer arithmetic, so any order is exact.
 	int m10 = 0, m01 = 0;
-	const int u = lane - ORBX_HALF_PATCH;
 	if (lane < 31)
 	{
-		const int au = abs(u);
+		const int v = lane - ORBX_HALF_PATCH;
+		const int o = x - 16 - xi;                                  // byte offset of column x-16 inside the staged row, 0..15
+		const uint32_t* wp = reinterpret_cast<const uint32_t*>(pimg + lane * OD_PS) + (o >> 2);
+		const int shb = (o & 3) * 8;
+		uint32_t w[9];
 #pragma unroll
-		for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++)
+		for (int k = 0; k < 9; k++) w[k] = wp[k];
+		const uint2* tab = s_mom + abs(v);
+		int rowsum = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++)
 		{
-			if (au <= c_umax[abs(v)])
-			{
-				const int val = __ldg(img + (int64_t)v * ip + u);
-				m10 += u * val;
-				m01 += v * val;
-			}
+			const uint32_t win = __funnelshift_r(w[k], w[k + 1], shb);
+			const uint2 cf = tab[k * 16];
+			rowsum = (int)__dp4a(win, cf.x, (uint32_t)rowsum);
+			m10 = dp4a_u8_s8(win, cf.y, m10);
 		}
+		m01 = v * rowsum;
 	}
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1)
@@ -987,24 +1051,21 @@ __global__ void __launch_bounds__(256) k_orient_describe(const OrbxPlanDev P, or
 	}
 	const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-	// ---- steered BRIEF: lane = descriptor byte, 8 pairs each
+	// ---- steered BRIEF (ComputeOrbDescriptor, :103-140): lane = descriptor byte, 8 pairs each, samples from the staged patch
 	const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
 	const float arad = __fmul_rn(angle, factorPI);
 	const float ca = __double2float_rn(cos((double)arad)), sb = __double2float_rn(sin((double)arad));
-	const uint8_t* __restrict__ bl = P.blur + (int64_t)f * P.slab + L.offset + (int64_t)y * L.pitch + x;
-	const int bp = L.pitch;
+	const uint8_t* bl = pblr + 18 * OD_PS + (x - xb);
 	uint32_t byte = 0;
 #pragma unroll
 	for (int bit = 0; bit < 8; bit++)
 	{
-		const uint32_t w = s_pat[bit * 32 + lane];
-		const float x0 = (float)(signed char)(w & 0xff), y0 = (float)(signed char)((w >> 8) & 0xff);
-		const float x1 = (float)(signed char)((w >> 16) & 0xff), y1 = (float)(signed char)(w >> 24);
-		const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
-		const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
-		const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
-		const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
-		const int t0 = __ldg(bl + r0 * bp + q0), t1 = __ldg(bl + r1 * bp + q1);
+		const float4 pt = s_pat[bit * 32 + lane];
+		const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, sb), __fmul_rn(pt.y, ca)));
+		const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, ca), __fmul_rn(pt.y, sb)));
+		const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, sb), __fmul_rn(pt.w, ca)));
+		const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, ca), __fmul_rn(pt.w, sb)));
+		const int t0 = bl[r0 * OD_PS + q0], t1 = bl[r1 * OD_PS + q1];
 		byte |= (uint32_t)(t0 < t1) << bit;
 	}
 	d_desc[((int64_t)f * P.out_cap + slot) * 32 + lane] = (uint8_t)byte;
@@ -1100,6 +1161,7 @@ void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
 
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st)
 {
-	dim3 grid((P.out_cap + 7) / 8, P.frames);
-	k_orient_describe<<<grid, 256, 0, st>>>(P, d_kps, d_desc, d_n);
+	dim3 grid((P.out_cap + OD_WARPS - 1) / OD_WARPS, P.frames);
+	cudaFuncSetAttribute(k_orient_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, OD_SMEM);
+	k_orient_describe<<<grid, OD_WARPS * 32, OD_SMEM, st>>>(P, d_kps, d_desc, d_n);
 }
