@@ -343,12 +343,14 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	}
 	if (ev) CU(cudaEventRecord(ev[0], st));
 	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, st);
+	// blur right after the pyramid (it only depends on it): its 1 MB/frame of dirty lines drain from L2 while FAST and the
+	// quadtree run, instead of competing with the descriptor stage's gathers
 	if (ev) CU(cudaEventRecord(ev[1], st));
-	orbx_launch_fast(P, st);
-	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_quadtree(P, cell_off, st);
-	if (ev) CU(cudaEventRecord(ev[3], st));
 	orbx_launch_blur(P, st);
+	if (ev) CU(cudaEventRecord(ev[2], st));
+	orbx_launch_fast(P, st);
+	if (ev) CU(cudaEventRecord(ev[3], st));
+	orbx_launch_quadtree(P, cell_off, st);
 	if (ev) CU(cudaEventRecord(ev[4], st));
 	orbx_launch_describe(P, d_kps, d_desc, d_n, st);
 	if (ev) CU(cudaEventRecord(ev[5], st));
@@ -502,7 +504,8 @@ orbx_status orbx_stage_times(orbx_handle h, float ms_sum[5], int* calls)
 		{
 			float ms = 0.f;
 			CU(cudaEventElapsedTime(&ms, h->ev_pool[6 * c + i], h->ev_pool[6 * c + i + 1]));
-			ms_sum[i] += ms;
+			static const int slot[5] = { 0, 3, 1, 2, 4 };   // launch order is pyramid, blur, FAST, quadtree, describe
+			ms_sum[slot[i]] += ms;
 		}
 	if (calls) *calls = (int)n;
 	h->ev_used = 0;
@@ -535,16 +538,30 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 	// into the handle's stream, so the call stays stream-ordered for the caller.
 	int lanes = (frames >= 64 && !h->stage_timing) ? 2 : 1;
 	if (const char* e = getenv("ORBX_LANES")) lanes = std::max(1, std::min(2, atoi(e)));
+	// Sub-batches keep a chunk's pyramid + blur slabs (2.1 MB per VGA frame) inside the 126 MB L2 between the stages.
+	int chunk = frames;
+	if (const char* e = getenv("ORBX_DEV_CHUNK")) chunk = std::max(1, atoi(e));
 	orbx_status st2 = ORBX_OK;
-	if (lanes == 1)
-		st2 = enqueue_extract(h, 0, frames, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
-	else
+	if (lanes == 2)
 	{
-		const int half = (frames + 1) / 2;
 		CU(cudaEventRecord(h->fork, h->stream));
 		CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
-		st2 = enqueue_extract(h, 0, half, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
-		if (st2 == ORBX_OK) st2 = enqueue_extract(h, half, frames - half, h->stream2, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+	}
+	int ci = 0;
+	for (int fb = 0; fb < frames && st2 == ORBX_OK; fb += chunk, ci++)
+	{
+		const int fc = std::min(chunk, frames - fb);
+		if (lanes == 1)
+			st2 = enqueue_extract(h, fb, fc, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+		else
+		{
+			const int half = (fc + 1) / 2;
+			st2 = enqueue_extract(h, fb, half, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+			if (st2 == ORBX_OK && fc > half) st2 = enqueue_extract(h, fb + half, fc - half, h->stream2, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+		}
+	}
+	if (lanes == 2)
+	{
 		CU(cudaEventRecord(h->join, h->stream2));
 		CU(cudaStreamWaitEvent(h->stream, h->join, 0));
 	}

@@ -7,12 +7,12 @@ import bench
 B = 256
 host = bench.make_frames(B, 0)
 d = [torch.from_numpy(host).cuda(), torch.roll(torch.from_numpy(host).cuda(), 77, 1).contiguous()]
-for lanes in (1, 2, 1, 2):
-    os.environ['ORBX_LANES'] = str(lanes)
+for lanes, chunk in ((1, 256), (2, 256), (1, 128), (1, 64), (2, 64), (1, 32), (2, 32), (1, 16)):
+    os.environ['ORBX_LANES'] = str(lanes); os.environ['ORBX_DEV_CHUNK'] = str(chunk)
     ex = api.ORBextractor(nfeatures=1000)
     outs = ex.extract_batch_device(d[0])
     for i in range(3): ex.extract_batch_device(d[i & 1], *outs)
     ex.synchronize(); t = time.perf_counter()
     for i in range(20): ex.extract_batch_device(d[i & 1], *outs)
     ex.synchronize(); dt = (time.perf_counter() - t) / 20
-    print('lanes', lanes, '%.3f ms/step %.0f fps' % (dt * 1e3, B / dt))
+    print('lanes', lanes, 'chunk', chunk, '%.3f ms/step %.0f fps' % (dt * 1e3, B / dt))
