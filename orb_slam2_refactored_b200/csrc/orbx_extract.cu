@@ -220,17 +220,20 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 
 	// ---- A: upper bound for every pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballots
 	//      are the bitmap words of those pixels.
-	for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
 	{
-		const int i = i0 + tid;
-		int u = 0;
-		if (i < npx)
+		// (ry, rx) of pixel tid, then stepped by 128 pixels per iteration without multiplications
+		const int step_y = (int)((128u * inv_rw) >> 20), step_x = 128 - step_y * rw;
+		int ry = (int)(((uint32_t)tid * inv_rw) >> 20), rx = tid - ry * rw;
+		const uint8_t* p = t0 + ry * FT_TS + rx;
+		const int step_p = step_y * FT_TS + step_x, wrap_p = FT_TS - rw;
+		for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
 		{
-			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-			u = arc_score_bound(t0 + ry * FT_TS + rx);
+			const int u = (i0 + tid < npx) ? arc_score_bound(p) : 0;
+			const unsigned ba = __ballot_sync(0xffffffffu, u > tini), bb = __ballot_sync(0xffffffffu, u > tmin && u <= tini);
+			if (lane == 0) { bm_a[(i0 >> 5) + warp] = ba; bm_b[(i0 >> 5) + warp] = bb; }
+			rx += step_x; p += step_p;
+			if (rx >= rw) { rx -= rw; p += wrap_p; }
 		}
-		const unsigned ba = __ballot_sync(0xffffffffu, u > tini), bb = __ballot_sync(0xffffffffu, u > tmin && u <= tini);
-		if (lane == 0) { bm_a[(i0 >> 5) + warp] = ba; bm_b[(i0 >> 5) + warp] = bb; }
 	}
 	__syncthreads();
 

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) k_hamming_pairs(const uint8_t* __restrict
 // ---------------------------------------------------------------------------------------------------
 // M2  hamming_knn2 — best / second-best scan (SearchByBoW inner loop, src/ORBmatcher.cc:477-507).
 //     Queries live in registers (KQ per thread), train rows stream through a double-buffered shared tile
-//     and are read as warp-wide broadcasts. Per pair: 8 LOP3(xor) + 8 POPC + 4 IADD3 + 1 key + 3 min/max.
+//     and are read as warp-wide broadcasts. Per pair: 8 LOP3(xor) + 6 LOP3(carry-save) + 5 POPC + ~4 add/shift + 1 key + 3 min/max.
 //     key = dist << 22 | row-in-chunk is unique inside a chunk (<= 4 Mi rows), so
 //         k2 = min(k2, max(k1, key)); k1 = min(k1, key)
 //     tracks the two smallest keys: k1 = (best, lowest index), k2 >> 22 = second-best distance. A row at
@@ -53,6 +53,22 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// 256-bit Hamming distance with 5 POPC instead of 8. Measured on this B200 (tools/pipe_probe.cu): POPC 15, LOP3 59
+// lane-ops/clk/SM, so the plain 8 x (XOR, POPC) form is POPC-bound at 0.53 clk/pair. Three carry-save adders (2 LOP3 each:
+// sum = a^b^c, carry = majority) fold seven of the eight XOR words into one "ones" word and three "twos" words:
+//   d = popc(ones) + popc(x7) + 2 * (popc(c1) + popc(c2) + popc(c3)).
+// That is 14 LOP3 + 5 POPC per pair, which balances the two pipes (a fourth adder would save one more POPC but makes the
+// LOP3 pipe the bottleneck: measured 711 vs 529 Gpairs/s for the plain form).
+__device__ __forceinline__ int hamming256_csa(const uint32_t* q, const uint4 lo, const uint4 hi)
+{
+	const uint32_t x0 = q[0] ^ lo.x, x1 = q[1] ^ lo.y, x2 = q[2] ^ lo.z, x3 = q[3] ^ lo.w;
+	const uint32_t x4 = q[4] ^ hi.x, x5 = q[5] ^ hi.y, x6 = q[6] ^ hi.z, x7 = q[7] ^ hi.w;
+	const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 ^ x1));
+	const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 ^ x4));
+	const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 ^ s2));
+	return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
 
 __device__ __forceinline__ uint64_t knn_pack(uint32_t best, uint32_t second, uint32_t idx)
 {
@@ -133,8 +149,7 @@ __global__ void __launch_bounds__(KN_THREADS) k_knn2_partial(const uint8_t* __re
 #pragma unroll
 					for (int k = 0; k < KN_KQ; k++)
 					{
-						const int d = __popc(q[k][0] ^ lo.x) + __popc(q[k][1] ^ lo.y) + __popc(q[k][2] ^ lo.z) + __popc(q[k][3] ^ lo.w) +
-						              __popc(q[k][4] ^ hi.x) + __popc(q[k][5] ^ hi.y) + __popc(q[k][6] ^ hi.z) + __popc(q[k][7] ^ hi.w);
+						const int d = hamming256_csa(q[k], lo, hi);
 						const uint32_t key = ((uint32_t)d << 22) + jj;
 						k2[k] = min(k2[k], max(k1[k], key));
 						k1[k] = min(k1[k], key);
@@ -150,8 +165,7 @@ __global__ void __launch_bounds__(KN_THREADS) k_knn2_partial(const uint8_t* __re
 #pragma unroll
 					for (int k = 0; k < KN_KQ; k++)
 					{
-						const int d = __popc(q[k][0] ^ lo.x) + __popc(q[k][1] ^ lo.y) + __popc(q[k][2] ^ lo.z) + __popc(q[k][3] ^ lo.w) +
-						              __popc(q[k][4] ^ hi.x) + __popc(q[k][5] ^ hi.y) + __popc(q[k][6] ^ hi.z) + __popc(q[k][7] ^ hi.w);
+						const int d = hamming256_csa(q[k], lo, hi);
 						const uint32_t key = ((uint32_t)d << 22) + jj;
 						k2[k] = min(k2[k], max(k1[k], key));
 						k1[k] = min(k1[k], key);
