@@ -168,6 +168,24 @@ orbx_status orbx_knn2_partial_device(const uint8_t* d_query, int64_t nq, const u
 orbx_status orbx_knn2_merge_device(const uint64_t* d_gathered, int ranks, int64_t nq, int th_low, float nnratio,
                                    int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match, void* stream);
 
+/* ---- rows "next" of the hot path: the steps either side of Extract and the N x N Hamming site ---- */
+
+/* ConvertToGray — src/System.cc:122-137 (cv::cvtColor {RGB,BGR,RGBA,BGRA}2GRAY, OpenCV 8-bit fixed point). Host buffers;
+ * channels = 3 or 4, rgb != 0 when the first channel is red (the reference's RGB_ flag). */
+orbx_status orbx_convert_to_gray(int device, const uint8_t* src, int width, int height, size_t pitch, int channels, int rgb,
+                                 uint8_t* dst, size_t dst_pitch);
+/* ConvertToGray fused into Extract (src/System.cc:445-450, 506-509, 560-567): interleaved colour frames in, the gray image is
+ * written straight into level 0 of the pyramid on the device. channels = 1 behaves like orbx_extract_batch. */
+orbx_status orbx_extract_batch_color(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                                     size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* ComputeStereoFromRGBD — src/System.cc:197-219: depth_map is width x height float32 (pitch in bytes). Host buffers. */
+orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
+                                  int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth);
+/* The distance matrix + least-median selection of MapPoint::ComputeDistinctiveDescriptors — src/MapPoint.cc:286-314, for a
+ * batch of descriptor sets: set s is rows [offsets[s], offsets[s+1]) of desc (32 bytes each). best[s] = index inside the set of
+ * the descriptor with the least median distance to the set (first wins ties), -1 for an empty set. Host buffers. */
+orbx_status orbx_distinctive_descriptors(int device, const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best);
+
 /* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
  * `device` (all SMs, register operands). */
 orbx_status orbx_measure_popc_peak(int device, double* popc_per_second);

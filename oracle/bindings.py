@@ -72,6 +72,9 @@ class Oracle:
                                       C.c_void_p, C.c_void_p])
         f('knn2', None, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_void_p, C.c_int])
+        f('convert_to_gray', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t])
+        f('stereo_from_rgbd', None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(Camera), C.c_void_p, C.c_void_p])
+        f('distinctive_index', C.c_int, [C.c_void_p, C.c_int])
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
         f('cv_gaussian7', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t])
@@ -140,6 +143,27 @@ class Oracle:
     def descriptor_distance(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return int(self._descriptor_distance(_p(a), _p(b)))
+
+    # ---- SURVEY §8(f) rows ----
+    def convert_to_gray(self, img, rgb=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        dst = np.empty((h, w), np.uint8)
+        self._convert_to_gray(_p(img), w, h, img.strides[0], ch, int(rgb), _p(dst), dst.strides[0])
+        return dst
+
+    def stereo_from_rgbd(self, kps, kps_un, depth_map, cam):
+        kps = np.ascontiguousarray(kps, KP_DTYPE); kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+        depth_map = np.ascontiguousarray(depth_map, np.float32)
+        ur = np.empty(len(kps), np.float32); dp = np.empty(len(kps), np.float32)
+        c = Camera(*[float(v) for v in cam])
+        self._stereo_from_rgbd(_p(kps), _p(kps_un), len(kps), _p(depth_map), depth_map.shape[1], depth_map.shape[0], depth_map.strides[0],
+                               C.byref(c), _p(ur), _p(dp))
+        return ur, dp
+
+    def distinctive_index(self, desc):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        return int(self._distinctive_index(_p(desc), len(desc)))
 
     # ---- extractor ----
     def extractor(self, nfeatures=2000, scale=1.2, nlevels=8, ini=20, mn=7):

@@ -263,4 +263,19 @@ float fast_atan2_deg(float y, float x)
 	return a;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cvtColor to gray, 8-bit fixed point with 15 fractional bits
+// ---------------------------------------------------------------------------------------------
+void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, bool rgb, uint8_t* dst, size_t dstep)
+{
+	const int ri = rgb ? 0 : 2, bi = rgb ? 2 : 0;
+	for (int y = 0; y < h; y++)
+	{
+		const uint8_t* s = src + (size_t)y * sstep;
+		uint8_t* d = dst + (size_t)y * dstep;
+		for (int x = 0; x < w; x++, s += channels)
+			d[x] = (uint8_t)((s[ri] * 9798 + s[1] * 19235 + s[bi] * 3735 + 16384) >> 15);
+	}
+}
+
 }  // namespace cvp

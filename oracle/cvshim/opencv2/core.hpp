@@ -6,7 +6,7 @@
 // (orb_slam2_refactored_b200/csrc/host) build here; with a real OpenCV on the include path this
 // directory is simply not used.
 //
-// Only 8-bit single-channel matrices exist. The four arithmetic primitives forward to the pinned
+// Matrices are byte buffers with an element size: 8-bit with 1/3/4 channels and 32-bit float exist. The four arithmetic primitives forward to the pinned
 // restatements in oracle/cv_primitives.cc.
 #pragma once
 #include <algorithm>
@@ -23,6 +23,10 @@ typedef unsigned char uchar;
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_8UC4 24
+#define CV_32F 5
+#define CV_32FC1 5
 #define CV_PI 3.1415926535897932384626433832795
 
 namespace cv {
@@ -87,36 +91,40 @@ public:
 	int rows, cols;
 	size_t step;
 	uchar* data;
+	int type_;
 
-	Mat() : rows(0), cols(0), step(0), data(nullptr) {}
+	Mat() : rows(0), cols(0), step(0), data(nullptr), type_(CV_8U) {}
 	Mat(int r, int c, int type) : Mat() { create(r, c, type); }
 	// external (non-owning) buffer, like cv::Mat(rows, cols, type, void*, step)
-	Mat(int r, int c, int /*type*/, void* ext, size_t step_ = 0)
-		: rows(r), cols(c), step(step_ ? step_ : (size_t)c), data((uchar*)ext) {}
+	Mat(int r, int c, int type, void* ext, size_t step_ = 0)
+		: rows(r), cols(c), step(step_ ? step_ : (size_t)c * esz(type)), data((uchar*)ext), type_(type) {}
 
-	int type() const { return CV_8U; }
+	static size_t esz(int type) { return ((type & 7) == 5 ? 4 : 1) * (size_t)((type >> 3) + 1); }
+	int type() const { return type_; }
+	int channels() const { return (type_ >> 3) + 1; }
+	size_t elemSize() const { return esz(type_); }
 	bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-	size_t step1() const { return step; }
-	bool isContinuous() const { return step == (size_t)cols; }
+	size_t step1() const { return step / ((type_ & 7) == 5 ? 4 : 1); }
+	bool isContinuous() const { return step == (size_t)cols * elemSize(); }
 
-	void create(int r, int c, int /*type*/)
+	void create(int r, int c, int type)
 	{
-		if (r == rows && c == cols && data && owner_ && step == (size_t)c)
+		if (r == rows && c == cols && type == type_ && data && owner_ && step == (size_t)c * esz(type))
 			return;
-		owner_ = std::make_shared<std::vector<uchar>>((size_t)r * c);
-		rows = r; cols = c; step = (size_t)c; data = owner_->data();
+		owner_ = std::make_shared<std::vector<uchar>>((size_t)r * c * esz(type));
+		rows = r; cols = c; type_ = type; step = (size_t)c * esz(type); data = owner_->data();
 	}
 	void release() { owner_.reset(); rows = cols = 0; step = 0; data = nullptr; }
 	void setTo(int v)
 	{
 		for (int y = 0; y < rows; y++)
-			std::memset(data + (size_t)y * step, v, (size_t)cols);
+			std::memset(data + (size_t)y * step, v, (size_t)cols * elemSize());
 	}
 	void copyTo(Mat& dst) const
 	{
-		dst.create(rows, cols, CV_8U);
+		dst.create(rows, cols, type_);
 		for (int y = 0; y < rows; y++)
-			std::memcpy(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols);
+			std::memcpy(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols * elemSize());
 	}
 	Mat clone() const { Mat m; copyTo(m); return m; }
 
@@ -124,8 +132,9 @@ public:
 	{
 		Mat m;
 		m.owner_ = owner_;
+		m.type_ = type_;
 		m.rows = rr.end - rr.start; m.cols = cr.end - cr.start; m.step = step;
-		m.data = data + (size_t)rr.start * step + cr.start;
+		m.data = data + (size_t)rr.start * step + (size_t)cr.start * elemSize();
 		return m;
 	}
 	Mat operator()(const Rect& r) const { return (*this)(Range(r.y, r.y + r.height), Range(r.x, r.x + r.width)); }
@@ -157,5 +166,8 @@ void resize(const Mat& src, Mat& dst, Size dsize);
 void FAST(const Mat& image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
 void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT);
 float fastAtan2(float y, float x);
+enum { COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7, COLOR_BGRA2GRAY = 10, COLOR_RGBA2GRAY = 11 };
+void cvtColor(const Mat& src, Mat& dst, int code);
+typedef Mat_<float> Mat1f;
 
 }  // namespace cv

@@ -38,4 +38,15 @@ void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double si
 
 float fastAtan2(float y, float x) { return cvp::fast_atan2_deg(y, x); }
 
+void cvtColor(const Mat& src, Mat& dst, int code)
+{
+	CV_Assert(code == COLOR_BGR2GRAY || code == COLOR_RGB2GRAY || code == COLOR_BGRA2GRAY || code == COLOR_RGBA2GRAY);
+	const int ch = (code == COLOR_BGR2GRAY || code == COLOR_RGB2GRAY) ? 3 : 4;
+	CV_Assert(src.channels() == ch);
+	Mat out;
+	out.create(src.rows, src.cols, CV_8U);
+	cvp::cvt_gray_u8(src.data, src.cols, src.rows, src.step, ch, code == COLOR_RGB2GRAY || code == COLOR_RGBA2GRAY, out.data, out.step);
+	dst = out;
+}
+
 }  // namespace cv

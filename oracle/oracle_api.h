@@ -84,6 +84,16 @@ int ORACLE_FN(stereo_matches)(const oracle_keypoint* kpL, int nL, const uint8_t*
 void ORACLE_FN(knn2)(const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int th_low, float nnratio,
                      int32_t* idx, uint16_t* best, uint16_t* second, int32_t* match, int threads);
 
+// ---- rows "next" of SURVEY §8(f) ----
+// ConvertToGray (src/System.cc:122-137): channels 3 or 4, rgb != 0 when the first channel is R
+void ORACLE_FN(convert_to_gray)(const uint8_t* src, int w, int h, size_t pitch, int channels, int rgb, uint8_t* dst, size_t dst_pitch);
+// ComputeStereoFromRGBD (src/System.cc:197-219): depth map is float32, pitch in bytes
+void ORACLE_FN(stereo_from_rgbd)(const oracle_keypoint* kps, const oracle_keypoint* kps_un, int n, const float* depth_map, int w, int h,
+                                 size_t pitch, const oracle_camera* cam, float* uright, float* depth);
+// the distance matrix + least-median selection of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314): index of the
+// descriptor with the least median distance to the others, first wins ties
+int ORACLE_FN(distinctive_index)(const uint8_t* desc, int n);
+
 // ---- pinned third-party primitives (same code in both libraries; checked against cv2 4.13.0) ----
 void ORACLE_FN(cv_resize)(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
 int ORACLE_FN(cv_fast)(const uint8_t* img, int w, int h, size_t step, int th, int nms, oracle_cand* out, int cap);

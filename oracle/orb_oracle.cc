@@ -743,6 +743,46 @@ void orc_knn2(const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt
 	for (auto& t : pool) t.join();
 }
 
+// ---- rows "next" of SURVEY §8(f) ----
+// ConvertToGray (src/System.cc:122-137) = cv::cvtColor with the code picked from (channels, RGB flag)
+void orc_convert_to_gray(const uint8_t* src, int w, int h, size_t pitch, int channels, int rgb, uint8_t* dst, size_t dst_pitch)
+{
+	cvp::cvt_gray_u8(src, w, h, pitch, channels, rgb != 0, dst, dst_pitch);
+}
+
+// ComputeStereoFromRGBD (src/System.cc:197-219)
+void orc_stereo_from_rgbd(const oracle_keypoint* kps, const oracle_keypoint* kps_un, int n, const float* depth_map, int /*w*/, int /*h*/,
+                          size_t pitch, const oracle_camera* cam, float* uright, float* depth)
+{
+	for (int i = 0; i < n; i++)
+	{
+		uright[i] = depth[i] = -1.f;
+		const int v = (int)kps[i].y, u = (int)kps[i].x;      // truncation, :210-211
+		const float d = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(depth_map) + (size_t)v * pitch + 4 * (size_t)u);
+		if (d > 0)
+		{
+			depth[i] = d;
+			uright[i] = kps_un[i].x - cam->bf / d;
+		}
+	}
+}
+
+// distance matrix + least median of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314)
+int orc_distinctive_index(const uint8_t* desc, int n)
+{
+	if (n <= 0) return -1;
+	int best_median = 0x7fffffff, best = 0;
+	std::vector<int> row(n);
+	for (int i = 0; i < n; i++)
+	{
+		for (int j = 0; j < n; j++) row[j] = i == j ? 0 : hamming256(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+		std::nth_element(row.begin(), row.begin() + (n - 1) / 2, row.end());     // value at sorted position (N-1)/2
+		const int median = row[(n - 1) / 2];
+		if (median < best_median) { best_median = median; best = i; }
+	}
+	return best;
+}
+
 void orc_cv_resize(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep)
 {
 	cvp::resize_linear_u8(src, sw, sh, sstep, dst, dw, dh, dstep);

@@ -36,6 +36,11 @@ void ComputeStereoMatches(
 	const std::vector<float>& scaleFactors, const std::vector<float>& invScaleFactors, const CameraParams& camera,
 	std::vector<float>& uright, std::vector<float>& depth);
 
+size_t DistinctiveIndex(const std::vector<cv::Mat>& descriptors);
+void ConvertToGrayRef(const cv::Mat& src, cv::Mat& dst, bool RGB);
+void ComputeStereoFromRGBDRef(const KeyPoints& keypoints, const KeyPoints& keypointsUn, const cv::Mat& depthImage,
+	const CameraParams& camera, std::vector<float>& uright, std::vector<float>& depth);
+
 // The reference indexes distIndices[0] even when nothing matched (src/ORBmatcher.cc:232-233). With
 // nL > 0 that is a harmless read of reserved storage; with nL == 0 it is a null dereference, so that
 // one case is refused here.

@@ -80,6 +80,12 @@ _SIGNATURES = {
     'orbx_knn2_partial_device': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     'orbx_knn2_merge_device': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    'orbx_convert_to_gray': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    'orbx_extract_batch_color': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'orbx_stereo_from_rgbd': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Camera),
+                                        C.c_void_p, C.c_void_p]),
+    'orbx_distinctive_descriptors': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_measure_popc_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
@@ -195,6 +201,17 @@ class ORBextractor:
         desc = np.zeros((F, cap, 32), np.uint8)
         n = np.zeros(F, np.int32)
         _check(lib().orbx_extract_batch(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], _p(kps), _p(desc), cap, _p(n)))
+        self._last_frames = F
+        return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
+
+    def ExtractBatchColor(self, images, RGB=True):
+        """images: (F, H, W, 3|4) uint8. ConvertToGray (src/System.cc:122-137) fused into the upload, then Extract."""
+        images = np.ascontiguousarray(images, np.uint8)
+        F, H, W, ch = images.shape
+        cap = lib().orbx_max_keypoints(self._h)
+        kps = np.zeros((F, cap), KP_DTYPE); desc = np.zeros((F, cap, 32), np.uint8); n = np.zeros(F, np.int32)
+        _check(lib().orbx_extract_batch_color(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], ch, int(RGB), _p(kps),
+                                              _p(desc), cap, _p(n)))
         self._last_frames = F
         return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
 
@@ -365,6 +382,40 @@ def knn2_merge_device(d_gathered, ranks, nq, th_low=TH_LOW, nnratio=0.6, stream=
     _check(lib().orbx_knn2_merge_device(C.c_void_p(d_gathered.data_ptr()), ranks, nq, th_low, nnratio, C.c_void_p(idx.data_ptr()),
                                         C.c_void_p(best.data_ptr()), C.c_void_p(second.data_ptr()), C.c_void_p(match.data_ptr()), st))
     return idx, best, second, match
+
+
+def ConvertToGray(src, RGB=True, device=0):
+    """static ConvertToGray of src/System.cc:122-137 for a (H, W, 3|4) uint8 image; 1-channel input is returned as is (:129-133)."""
+    src = np.asarray(src)
+    if src.ndim == 2:
+        return src
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, ch = src.shape
+    dst = np.empty((h, w), np.uint8)
+    _check(lib().orbx_convert_to_gray(device, _p(src), w, h, src.strides[0], ch, int(RGB), _p(dst), dst.strides[0]))
+    return dst
+
+
+def ComputeStereoFromRGBD(keypoints, keypointsUn, depthImage, camera, device=0):
+    """src/System.cc:197-219. depthImage: (H, W) float32. Returns (uright, depth)."""
+    k = np.ascontiguousarray(keypoints, KP_DTYPE); ku = np.ascontiguousarray(keypointsUn, KP_DTYPE)
+    dm = np.ascontiguousarray(depthImage, np.float32)
+    ur = np.full(len(k), -1, np.float32); dp = np.full(len(k), -1, np.float32)
+    cam = _Camera(*[float(v) for v in camera])
+    _check(lib().orbx_stereo_from_rgbd(device, _p(k), _p(ku), len(k), _p(dm), dm.shape[1], dm.shape[0], dm.strides[0], C.byref(cam), _p(ur), _p(dp)))
+    return ur, dp
+
+
+def ComputeDistinctiveDescriptors(descriptor_sets, device=0):
+    """The distance matrix + least-median selection of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314) for a list
+    of (N_i, 32) descriptor arrays; returns the index of the most distinctive descriptor of every set (-1 for an empty set)."""
+    sets = [np.ascontiguousarray(d, np.uint8).reshape(-1, 32) for d in descriptor_sets]
+    off = np.zeros(len(sets) + 1, np.int64)
+    off[1:] = np.cumsum([len(d) for d in sets])
+    allrows = np.concatenate(sets) if off[-1] else np.zeros((1, 32), np.uint8)
+    best = np.empty(len(sets), np.int32)
+    _check(lib().orbx_distinctive_descriptors(device, _p(allrows), _p(off), len(sets), _p(best)))
+    return best
 
 
 def measure_popc_peak(device=0):

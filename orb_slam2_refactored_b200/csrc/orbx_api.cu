@@ -84,6 +84,7 @@ struct orbx_extractor
 	// plan (depends on image size)
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
+	DevBuf<uint8_t> color;              // interleaved colour frames of the current batch (orbx_extract_batch_color)
 	DevBuf<uint8_t> pyr, blur, l0buf;   // l0buf: level 0 of every frame, back to back (host-buffer API uploads land here)
 	int64_t l0_pitch = 0, l0_stride = 0;
 	uint8_t* l0base = nullptr;          // l0buf.p + 256: kernels may read up to 16 bytes in front of a row (aligned 16-byte tile copies)
@@ -421,7 +422,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->stream2) cudaStreamSynchronize(h->stream2);
-	h->l0buf.release();
+	h->l0buf.release(); h->color.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
 	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
 	h->cell_tab.release();
@@ -569,16 +570,19 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 	return st2;
 }
 
-orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
-                               size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                                      size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
 {
 	if (!h || !images || !n) return fail(ORBX_ERR_INVALID, "null argument");
-	if (frames < 1 || width < 1 || height < 1 || pitch < (size_t)width) return fail(ORBX_ERR_INVALID, "bad image geometry");
+	if (channels != 1 && channels != 3 && channels != 4)
+		return fail(ORBX_ERR_INVALID, "CV_Assert(ch == 1 || ch == 3 || ch == 4) (src/System.cc:127)");
+	if (frames < 1 || width < 1 || height < 1 || pitch < (size_t)width * channels) return fail(ORBX_ERR_INVALID, "bad image geometry");
 	CU(cudaSetDevice(h->device));
 	orbx_status st = build_plan(h, width, height, frames);
 	if (st != ORBX_OK) return st;
 	const OrbxPlanDev& P = h->P;
 	const int ocap = P.sel_per_frame;
+	if (channels != 1) CU(h->color.ensure((size_t)frames * width * channels * height));
 	// Chunk pipeline over two streams: upload of chunk c+1 and download of chunk c-1 overlap the kernels of chunk c.
 	// Level 0 is uploaded straight into the level-0 buffer (ComputePyramid's copyTo, :462).
 	int chunk = frames <= 32 ? frames : std::max(32, std::min(64, (frames + 3) / 4));
@@ -597,13 +601,27 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 	{
 		const int fc = std::min(chunk, frames - fb);
 		cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
-		if (frame_stride == pitch * (size_t)height)
-			CU(cudaMemcpy2DAsync(h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
-			                     (size_t)height * fc, cudaMemcpyHostToDevice, st));
+		if (channels == 1)
+		{
+			if (frame_stride == pitch * (size_t)height)
+				CU(cudaMemcpy2DAsync(h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
+				                     (size_t)height * fc, cudaMemcpyHostToDevice, st));
+			else
+				for (int f = fb; f < fb + fc; f++)
+					CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
+					                     height, cudaMemcpyHostToDevice, st));
+		}
 		else
+		{
+			// ConvertToGray (src/System.cc:122-137) fused into the upload: colour frames land in a staging buffer and the
+			// conversion kernel writes level 0 of the pyramid directly
+			const size_t cpitch = (size_t)width * channels, cstride = cpitch * height;
 			for (int f = fb; f < fb + fc; f++)
-				CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
-				                     height, cudaMemcpyHostToDevice, st));
+				CU(cudaMemcpy2DAsync(h->color.p + (size_t)f * cstride, cpitch, images + (size_t)f * frame_stride, pitch, cpitch, height,
+				                     cudaMemcpyHostToDevice, st));
+			orbx_launch_gray(h->color.p + (size_t)fb * cstride, (int64_t)cpitch, (int64_t)cstride, channels, rgb, h->l0base + (int64_t)fb * h->l0_stride,
+			                 h->l0_pitch, h->l0_stride, width, height, fc, st);
+		}
 		st = (ci & 1) ? h->stream2 : h->stream;
 		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
 		if (e != ORBX_OK) return e;
@@ -624,6 +642,18 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 	if (need > cap || (need > 0 && (!kps || !desc)))
 		return fail(ORBX_ERR_CAPACITY, "output buffers hold fewer keypoints than were found");
 	return ORBX_OK;
+}
+
+orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                               size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+	return extract_batch_impl(h, images, frames, width, height, pitch, frame_stride, 1, 0, kps, desc, cap, n);
+}
+
+orbx_status orbx_extract_batch_color(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
+                                     size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+	return extract_batch_impl(h, images, frames, width, height, pitch, frame_stride, channels, rgb, kps, desc, cap, n);
 }
 
 orbx_status orbx_extract(orbx_handle h, const uint8_t* image, int width, int height, size_t pitch,
@@ -915,6 +945,66 @@ orbx_status orbx_stereo_match_host(int device, const orbx_keypoint* kps_l, int n
 	CU(cudaMemcpy(uright, du.p, sizeof(float) * n_l, cudaMemcpyDeviceToHost));
 	CU(cudaMemcpy(depth, dd.p, sizeof(float) * n_l, cudaMemcpyDeviceToHost));
 	pl.release(); pr.release(); dl.release(); dr.release(); kl.release(); kr.release(); cnt.release(); du.release(); dd.release(); sad.release();
+	return ORBX_OK;
+}
+
+orbx_status orbx_convert_to_gray(int device, const uint8_t* src, int width, int height, size_t pitch, int channels, int rgb,
+                                 uint8_t* dst, size_t dst_pitch)
+{
+	if (!src || !dst || width < 1 || height < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (channels != 3 && channels != 4) return fail(ORBX_ERR_INVALID, "channels must be 3 or 4");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	CU(cudaSetDevice(device));
+	const size_t cpitch = (size_t)width * channels;
+	const int64_t dpitch = align_up(width, 128);
+	DevBuf<uint8_t> ds, dd;
+	CU(ds.ensure(cpitch * height)); CU(dd.ensure((size_t)dpitch * height));
+	CU(cudaMemcpy2D(ds.p, cpitch, src, pitch, cpitch, height, cudaMemcpyHostToDevice));
+	orbx_launch_gray(ds.p, (int64_t)cpitch, 0, channels, rgb, dd.p, dpitch, 0, width, height, 1, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy2D(dst, dst_pitch, dd.p, dpitch, width, height, cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
+                                  int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth)
+{
+	if (!kps || !kps_un || !depth_map || !camera || !uright || !depth || n < 0 || width < 1 || height < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (n == 0) return ORBX_OK;
+	CU(cudaSetDevice(device));
+	DevBuf<orbx_keypoint> dk, du; DevBuf<uint8_t> dm; DevBuf<float> dr, dz;
+	const size_t dpitch = (size_t)width * 4;
+	CU(dk.ensure(n)); CU(du.ensure(n)); CU(dm.ensure(dpitch * height)); CU(dr.ensure(n)); CU(dz.ensure(n));
+	CU(cudaMemcpy(dk.p, kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(du.p, kps_un, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy2D(dm.p, dpitch, depth_map, pitch, dpitch, height, cudaMemcpyHostToDevice));
+	orbx_launch_stereo_from_rgbd(dk.p, du.p, n, dm.p, (int64_t)dpitch, camera->bf, dr.p, dz.p, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(uright, dr.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(depth, dz.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_distinctive_descriptors(int device, const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best)
+{
+	if (!desc || !offsets || !best || nsets < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (nsets == 0) return ORBX_OK;
+	for (int s = 0; s < nsets; s++)
+		if (offsets[s + 1] < offsets[s]) return fail(ORBX_ERR_INVALID, "offsets must be non-decreasing");
+	CU(cudaSetDevice(device));
+	const int64_t rows = offsets[nsets];
+	DevBuf<uint8_t> dd; DevBuf<int64_t> dof; DevBuf<int32_t> db;
+	CU(dd.ensure(std::max<int64_t>(32 * rows, 32))); CU(dof.ensure(nsets + 1)); CU(db.ensure(nsets));
+	if (rows) CU(cudaMemcpy(dd.p, desc, 32 * rows, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(dof.p, offsets, sizeof(int64_t) * (nsets + 1), cudaMemcpyHostToDevice));
+	orbx_launch_distinctive(dd.p, dof.p, nsets, db.p, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(best, db.p, sizeof(int32_t) * nsets, cudaMemcpyDeviceToHost));
 	return ORBX_OK;
 }
 

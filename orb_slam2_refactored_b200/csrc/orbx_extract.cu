@@ -26,6 +26,28 @@ __device__ __forceinline__ void cp_async_wait_all()
 __constant__ uint32_t c_inv20[72];   // c_inv20[n] = (1 << 20) / n + 1: floor(i / n) == (i * c_inv20[n]) >> 20 for n <= 64, i < 4096 (exhaustively checked)
 
 // =====================================================================================================
+// K0  gray_u8 — ConvertToGray (src/System.cc:122-137) = cv::cvtColor {RGB,BGR,RGBA,BGRA}2GRAY, 8-bit fixed point of
+//     OpenCV 4.13.0: (R*9798 + G*19235 + B*3735 + 16384) >> 15. Writes level 0 of the pyramid directly (4 pixels per thread).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_gray_to_l0(const uint8_t* __restrict__ src, int64_t spitch, int64_t sstride, int channels, int r_index,
+                                                   uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride, int w, int h)
+{
+	const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
+	if (x0 >= w || y >= h) return;
+	const uint8_t* __restrict__ s = src + (int64_t)f * sstride + (int64_t)y * spitch + (int64_t)x0 * channels;
+	uint32_t out = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		if (x0 + j < w)
+		{
+			const uint8_t* p = s + j * channels;
+			const int v = ((int)__ldg(p + r_index) * 9798 + (int)__ldg(p + 1) * 19235 + (int)__ldg(p + 2 - r_index) * 3735 + 16384) >> 15;
+			out |= (uint32_t)v << (8 * j);
+		}
+	*reinterpret_cast<uint32_t*>(dst + (int64_t)f * dstride + (int64_t)y * dpitch + x0) = out;   // dpitch is a multiple of 128
+}
+
+// =====================================================================================================
 // K1  pyramid_resize_u8 — cv::resize INTER_LINEAR 8UC1 in OpenCV's fixed point for
 //     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
 //     exact float/double operation order; the kernel is integer only. One thread = 4 output pixels.
@@ -1117,6 +1139,13 @@ cudaError_t orbx_upload_pattern()
 	if ((e = cudaMemcpyToSymbol(c_pattern, pattern, sizeof(pattern))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax))) != cudaSuccess) return e;
 	return cudaSuccess;
+}
+
+void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,
+                      int w, int h, int frames, cudaStream_t st)
+{
+	dim3 grid((w + 255) / 256, (h + 3) / 4, frames);
+	k_gray_to_l0<<<grid, 256, 0, st>>>(src, spitch, sstride, channels, rgb ? 0 : 2, dst, dpitch, dstride, w, h);
 }
 
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)

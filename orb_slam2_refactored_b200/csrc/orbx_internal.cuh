@@ -75,6 +75,8 @@ __device__ __forceinline__ int64_t orbx_level_pitch(const OrbxPlanDev& P, int le
 }
 
 // kernel launchers (orbx_extract.cu)
+void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,
+                      int w, int h, int frames, cudaStream_t st);
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
 void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
@@ -110,4 +112,7 @@ struct OrbxStereoArgs
 	int* sad;                         // [frames][cap] scratch: SAD of kept matches, -1 otherwise
 };
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st);
+void orbx_launch_stereo_from_rgbd(const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const uint8_t* depth_map, int64_t pitch, float bf,
+                                  float* uright, float* depth, cudaStream_t st);
+void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best, cudaStream_t st);
 double orbx_popc_probe(int device);

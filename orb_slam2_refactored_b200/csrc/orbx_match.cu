@@ -406,6 +406,85 @@ __global__ void __launch_bounds__(256) k_stereo_median_cut(const OrbxStereoArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ComputeStereoFromRGBD (src/System.cc:197-219): one thread per keypoint
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stereo_from_rgbd(const orbx_keypoint* __restrict__ kps, const orbx_keypoint* __restrict__ kps_un, int n,
+                                                          const uint8_t* __restrict__ depth_map, int64_t pitch, float bf,
+                                                          float* __restrict__ uright, float* __restrict__ depth)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const int v = (int)kps[i].y, u = (int)kps[i].x;       // truncation, :210-211
+	const float d = __ldg(reinterpret_cast<const float*>(depth_map + (int64_t)v * pitch) + u);
+	float ur = -1.f, dp = -1.f;
+	if (d > 0.f)
+	{
+		dp = d;
+		ur = __fsub_rn(kps_un[i].x, __fdiv_rn(bf, d));
+	}
+	uright[i] = ur;
+	depth[i] = dp;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The N x N Hamming site of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314): for every descriptor the
+// median (sorted position (N-1)/2, the zero self-distance included) of its distances to the set; the result is the first
+// descriptor with the least median. One CTA per set, one warp per row: 257-bin histogram in shared memory + prefix scan.
+// ---------------------------------------------------------------------------------------------------
+#define DD_WARPS 4
+__global__ void __launch_bounds__(DD_WARPS * 32) k_distinctive(const uint8_t* __restrict__ desc, const int64_t* __restrict__ offsets,
+                                                              int32_t* __restrict__ best)
+{
+	__shared__ int hist[DD_WARPS][288];
+	__shared__ unsigned long long s_best;       // median << 32 | row: the minimum is the first row with the least median
+	const int set = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t b = offsets[set];
+	const int n = (int)(offsets[set + 1] - b);
+	if (threadIdx.x == 0) s_best = ~0ull;
+	__syncthreads();
+	const uint4* __restrict__ d = reinterpret_cast<const uint4*>(desc + 32 * b);
+	const int k = (n - 1) / 2;
+	for (int i = warp; i < n; i += DD_WARPS)
+	{
+		for (int t = lane; t < 288; t += 32) hist[warp][t] = 0;
+		__syncwarp();
+		const uint4 lo = __ldg(d + 2 * i), hi = __ldg(d + 2 * i + 1);
+		for (int j = lane; j < n; j += 32)
+		{
+			const uint4 a = __ldg(d + 2 * j), c = __ldg(d + 2 * j + 1);
+			const int dist = __popc(lo.x ^ a.x) + __popc(lo.y ^ a.y) + __popc(lo.z ^ a.z) + __popc(lo.w ^ a.w) +
+			                 __popc(hi.x ^ c.x) + __popc(hi.y ^ c.y) + __popc(hi.z ^ c.z) + __popc(hi.w ^ c.w);
+			atomicAdd(&hist[warp][dist], 1);
+		}
+		__syncwarp();
+		// smallest value v with count(dist <= v) >= k + 1: lane l owns bins 9l .. 9l+8
+		int c[9], sum = 0;
+#pragma unroll
+		for (int t = 0; t < 9; t++) { c[t] = hist[warp][9 * lane + t]; sum += c[t]; }
+		int incl = sum;
+#pragma unroll
+		for (int dd = 1; dd < 32; dd <<= 1)
+		{
+			const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+			if (lane >= dd) incl += t;
+		}
+		int run = incl - sum, median = 0x7fffffff;
+#pragma unroll
+		for (int t = 0; t < 9; t++)
+		{
+			run += c[t];
+			if (median == 0x7fffffff && run >= k + 1) median = 9 * lane + t;
+		}
+#pragma unroll
+		for (int dd = 16; dd > 0; dd >>= 1) median = min(median, __shfl_xor_sync(0xffffffffu, median, dd));
+		if (lane == 0) atomicMin(&s_best, ((unsigned long long)(unsigned)median << 32) | (unsigned)i);
+		__syncwarp();
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) best[set] = n > 0 ? (int32_t)(s_best & 0xffffffffu) : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // POPC-pipe probe: dependent-free popcounts on registers, all SMs; the matcher's roofline denominator.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_popc_probe(uint32_t* out, int iters)
@@ -468,6 +547,19 @@ void orbx_launch_knn2_fold(const uint64_t* parts, int nparts, int64_t nq, uint64
 {
 	if (nq <= 0) return;
 	k_knn2_merge<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(parts, nparts, nq, 0, 0.f, nullptr, nullptr, nullptr, nullptr, packed);
+}
+
+void orbx_launch_stereo_from_rgbd(const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const uint8_t* depth_map, int64_t pitch, float bf,
+                                  float* uright, float* depth, cudaStream_t st)
+{
+	if (n <= 0) return;
+	k_stereo_from_rgbd<<<(n + 255) / 256, 256, 0, st>>>(kps, kps_un, n, depth_map, pitch, bf, uright, depth);
+}
+
+void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best, cudaStream_t st)
+{
+	if (nsets <= 0) return;
+	k_distinctive<<<nsets, DD_WARPS * 32, 0, st>>>(desc, offsets, best);
 }
 
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st)

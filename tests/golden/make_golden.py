@@ -51,6 +51,12 @@ def primitives():
     for name, src in (('img', img), ('noise', noise), ('blocks', blocks)):
         for th in (20, 7):
             out[f'fast_{name}_{th}'] = fast_cv(src, th)
+    rc = np.random.RandomState(11)
+    for ch in (3, 4):
+        col = rc.randint(0, 256, (61, 83, ch)).astype(np.uint8)
+        out[f'color{ch}_crc'] = crc(col)
+        out[f'gray{ch}_rgb'] = cv2.cvtColor(col, cv2.COLOR_RGB2GRAY if ch == 3 else cv2.COLOR_RGBA2GRAY)
+        out[f'gray{ch}_bgr'] = cv2.cvtColor(col, cv2.COLOR_BGR2GRAY if ch == 3 else cv2.COLOR_BGRA2GRAY)
     r = np.random.RandomState(3)
     y = r.randint(-60000, 60000, 4000).astype(np.float32); x = r.randint(-60000, 60000, 4000).astype(np.float32)
     y[:50] = 0; x[50:100] = 0; y[100] = 0; x[100] = 0

@@ -1,0 +1,64 @@
+"""GPU parity of the SURVEY §8(f) rows built so far: ConvertToGray (#3, standalone and fused into Extract),
+ComputeStereoFromRGBD (#3) and the N x N Hamming site of MapPoint::ComputeDistinctiveDescriptors (#4). Bit-exact bar."""
+import numpy as np
+import pytest
+
+from orb_slam2_refactored_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _color(seed, w, h, ch):
+    g = synth.image(seed, w, h).astype(np.int16)
+    r = np.random.RandomState(seed)
+    img = np.stack([np.clip(g + r.randint(-40, 41, g.shape), 0, 255) for _ in range(ch)], -1).astype(np.uint8)
+    return img
+
+
+@pytest.mark.parametrize('ch,rgb', [(3, True), (3, False), (4, True), (4, False)])
+def test_convert_to_gray(orbx, oracle_port, ch, rgb):
+    img = _color(ch * 2 + rgb, 643, 481, ch)     # width not a multiple of 4
+    assert np.array_equal(orbx.ConvertToGray(img, rgb), oracle_port.convert_to_gray(img, rgb))
+    mono = img[..., 0]
+    assert orbx.ConvertToGray(mono, rgb) is mono                                    # ch == 1: dst = src (src/System.cc:129-133)
+
+
+def test_extract_color_fused(orbx, oracle_port):
+    imgs = np.stack([_color(s, 640, 480, 3) for s in range(3)])
+    ex = orbx.ORBextractor(nfeatures=1000)
+    k, d = ex.ExtractBatchColor(imgs, RGB=False)
+    e = oracle_port.extractor(1000)
+    for f in range(len(imgs)):
+        ok, od = e.extract(oracle_port.convert_to_gray(imgs[f], False))
+        assert k[f].tobytes() == ok.tobytes() and np.array_equal(d[f], od)
+    assert np.array_equal(ex.GetImagePyramid(1)[0], oracle_port.convert_to_gray(imgs[1], False))
+
+
+def test_stereo_from_rgbd(orbx, oracle_port):
+    img = synth.image(9, 640, 480)
+    ex = orbx.ORBextractor(nfeatures=1000)
+    kps, _ = ex.Extract(img)
+    un = kps.copy(); un['x'] += np.float32(0.37)
+    r = np.random.RandomState(4)
+    dm = r.uniform(-0.5, 6.0, (480, 640)).astype(np.float32)
+    dm[r.rand(480, 640) < 0.2] = 0
+    ur, dp = orbx.ComputeStereoFromRGBD(kps, un, dm, synth.KITTI_CAMERA)
+    wu, wd = oracle_port.stereo_from_rgbd(kps, un, dm, synth.KITTI_CAMERA)
+    assert ur.tobytes() == wu.tobytes() and dp.tobytes() == wd.tobytes()
+    assert 0 < (wd > 0).sum() < len(kps)
+
+
+def test_distinctive_descriptors(orbx, oracle_port):
+    r = np.random.RandomState(5)
+    sets = []
+    for n in (1, 2, 3, 4, 7, 16, 33, 64, 150, 0, 5):
+        base = synth.descriptors(n + 1, 1)[0]
+        d = np.repeat(base[None], n, 0)
+        for i in range(n):          # observations of one map point: noisy copies of one descriptor (+ exact duplicates -> ties)
+            bits = np.unpackbits(d[i]); flip = r.choice(256, r.randint(0, 40), replace=False); bits[flip] ^= 1; d[i] = np.packbits(bits)
+        if n > 4:
+            d[n - 1] = d[1]
+        sets.append(d)
+    got = orbx.ComputeDistinctiveDescriptors(sets)
+    want = np.array([oracle_port.distinctive_index(d) if len(d) else -1 for d in sets], np.int32)
+    assert np.array_equal(got, want)

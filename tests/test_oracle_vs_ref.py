@@ -101,3 +101,23 @@ def test_knn2_and_distance_equal(oracle_port, oracle_ref):
     for i in range(50):
         assert oracle_ref.descriptor_distance(q[i], t[i]) == oracle_port.descriptor_distance(q[i], t[i]) == \
             int(np.unpackbits(q[i] ^ t[i]).sum())
+
+
+def test_next_rows_equal(oracle_port, oracle_ref):
+    """SURVEY §8(f) #3/#4: ConvertToGray, ComputeStereoFromRGBD and the distinctive-descriptor selection, reference text vs restatement."""
+    from oracle.bindings import KP_DTYPE
+    r = np.random.RandomState(3)
+    for ch in (3, 4):
+        img = r.randint(0, 256, (50, 71, ch)).astype(np.uint8)
+        for rgb in (True, False):
+            assert np.array_equal(oracle_ref.convert_to_gray(img, rgb), oracle_port.convert_to_gray(img, rgb))
+    kps = np.zeros(200, KP_DTYPE)
+    kps['x'] = r.uniform(0, 99, 200).astype(np.float32); kps['y'] = r.uniform(0, 79, 200).astype(np.float32)
+    un = kps.copy(); un['x'] += np.float32(0.25)
+    dm = r.uniform(-1, 5, (80, 100)).astype(np.float32)
+    a = oracle_ref.stereo_from_rgbd(kps, un, dm, synth.KITTI_CAMERA); b = oracle_port.stereo_from_rgbd(kps, un, dm, synth.KITTI_CAMERA)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+    for n in (1, 2, 3, 4, 9, 40, 101):
+        d = synth.descriptors(n, n)
+        d[n // 2] = d[0]
+        assert oracle_ref.distinctive_index(d) == oracle_port.distinctive_index(d)
