@@ -84,6 +84,7 @@ struct orbx_extractor
 	// plan (depends on image size)
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
+	OrbxTmaMaps maps;
 	DevBuf<uint8_t> color;              // interleaved colour frames of the current batch (orbx_extract_batch_color)
 	DevBuf<uint8_t> pyr, blur, l0buf;   // l0buf: level 0 of every frame, back to back (host-buffer API uploads land here)
 	int64_t l0_pitch = 0, l0_stride = 0;
@@ -306,6 +307,33 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
+	// TMA descriptors for the FAST kernel's tile loads: level s of every frame as a (pitch, h, frames) u8 tensor
+	{
+		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+		                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+		std::memset(&h->maps, 0, sizeof(h->maps));
+		for (int s = 0; s < nl; s++)
+		{
+			const OrbxLevel& L = P.lv[s];
+			int box_h = 0;
+			for (int cy = 0, y0 = L.miny; cy < L.ncy; cy++, y0 += L.cellh) box_h = std::max(box_h, std::min(y0 + L.cellh + 6, L.maxy) - y0);
+			if (box_h > orbx_fast_tile_rows()) return fail(ORBX_ERR_INVALID, "cell taller than the FAST tile");
+			h->maps.box_h[s] = box_h;
+			void* base = s == 0 ? (void*)h->l0base : (void*)(P.pyr + L.offset);
+			const cuuint64_t dims[3] = { (cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)frames };
+			const cuuint64_t strides[2] = { (cuuint64_t)L.pitch, (cuuint64_t)(s == 0 ? h->l0_stride : P.slab) };
+			const cuuint32_t box[3] = { (cuuint32_t)orbx_fast_tile_stride(), (cuuint32_t)box_h, 1 };
+			const cuuint32_t estr[3] = { 1, 1, 1 };
+			const CUresult r = ((EncodeFn)fn)(&h->maps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			if (r != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+		}
+	}
 	h->pw = w; h->ph = hgt; h->frames_cap = frames;
 	h->have_result = false;
 	return ORBX_OK;
@@ -322,6 +350,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	OrbxPlanDev P = P0;
 	int* cell_off = P0.cell_count + (int64_t)h->frames_cap * P0.cells_per_frame + (int64_t)fb * P0.cells_per_frame;
 	P.frames = fc;
+	P.frame0 = fb;
 	P.l0 += (int64_t)fb * l0_stride;
 	P.pyr += (int64_t)fb * P.slab; P.blur += (int64_t)fb * P.slab;
 	P.cand += (int64_t)fb * P.cand_per_frame; P.qbuf0 += (int64_t)fb * P.cand_per_frame; P.qbuf1 += (int64_t)fb * P.cand_per_frame;
@@ -349,7 +378,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	if (ev) CU(cudaEventRecord(ev[1], st));
 	orbx_launch_blur(P, st);
 	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_fast(P, st);
+	orbx_launch_fast(P, h->maps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
 	orbx_launch_quadtree(P, cell_off, st);
 	if (ev) CU(cudaEventRecord(ev[4], st));

@@ -23,6 +23,32 @@ __device__ __forceinline__ void cp_async_wait_all()
 	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: one thread issues a whole 2-D tile load, the copy engine writes shared memory and
+// completes the transaction count on the barrier; the CTA's threads only wait. SASS: UTMALDG / SYNCS.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+	asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+	             ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+	const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+	unsigned done = 0;
+	for (int spin = 0; spin < (1 << 24) && !done; spin++)
+		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+	if (!done) __trap();      // a lost transaction must not hang the device
+}
+
 __constant__ uint32_t c_inv20[72];   // c_inv20[n] = (1 << 20) / n + 1: floor(i / n) == (i * c_inv20[n]) >> 20 for n <= 64, i < 4096 (exhaustively checked)
 
 // =====================================================================================================
@@ -203,9 +229,10 @@ __device__ __forceinline__ int arc_score_bound(const uint8_t* __restrict__ c)
 //   C. strict 8-neighbour local maxima among them with S > iniTh. If the cell has none (the retry of :526-530), the second
 //      bitmap is evaluated too and the test repeats with minTh over both;
 //   D. ordered emit from the survivor bitmap: DetectFAST's cell-major / row-major push_back order without global atomics.
-__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
+__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps)
 {
-	__shared__ __align__(16) uint8_t tile[FT_TH * FT_TS];
+	__shared__ __align__(128) uint8_t tile[FT_TH * FT_TS];
+	__shared__ __align__(8) uint64_t tma_bar;
 	__shared__ __align__(16) uint8_t score[(FT_MAXR + 2) * FT_SS];
 	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
 	__shared__ uint32_t bm_a[FT_THREADS], bm_b[FT_THREADS], bm_sel[FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
@@ -220,22 +247,22 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P)
 	const int npx = rw * rh;
 	const uint32_t inv_rw = c_inv20[rw];
 
-	// ---- stage the view with 16-byte async copies; pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]
-	const uint8_t* __restrict__ img = orbx_level_ptr(P, f, lvl);
-	const int64_t pitch = orbx_level_pitch(P, lvl);
+	// ---- stage the view with one TMA tile load: box FT_TS x box_h of level `lvl`, frame `frame0 + f`. The innermost start
+	//      coordinate of a u8 tile must be a multiple of 16 bytes (measured: tools/tma_probe.cu faults otherwise), so the box
+	//      starts at x0 - sh and pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]. Columns/rows past the view are other
+	//      pixels of the level (or zero fill past its edge) and are never read.
 	const int sh = x0 & 15;
-	const int nchunk = (sh + vw + 15) >> 4;          // <= 6
-	const uint8_t* __restrict__ src0 = img + (int64_t)y0 * pitch + (x0 - sh);
-	for (int i = tid; i < vh * nchunk; i += FT_THREADS)
+	if (tid == 0)
 	{
-		const int r = (int)(((uint32_t)i * c_inv20[nchunk]) >> 20), cc = i - r * nchunk;
-		cp_async16(tile + r * FT_TS + cc * 16, src0 + (int64_t)r * pitch + cc * 16);
+		mbar_init(&tma_bar, 1);
+		mbar_expect_tx(&tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
+		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, &tma_bar);
 	}
 	for (int i = tid; i < (rh + 2) * (FT_SS / 4); i += FT_THREADS)
 		reinterpret_cast<uint32_t*>(score)[i] = 0;
 	bm_a[tid] = 0; bm_b[tid] = 0; bm_sel[tid] = 0;
-	cp_async_wait_all();
-	__syncthreads();
+	__syncthreads();            // the barrier init by thread 0 is visible to every waiter
+	mbar_wait(&tma_bar, 0);
 
 	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
@@ -1156,10 +1183,13 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 	k_pyramid_resize<<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 }
 
-void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st)
+int orbx_fast_tile_stride() { return FT_TS; }
+int orbx_fast_tile_rows() { return FT_TH; }
+
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st)
 {
 	dim3 grid(P.cells_per_frame, P.frames);
-	k_fast_cells<<<grid, FT_THREADS, 0, st>>>(P);
+	k_fast_cells<<<grid, FT_THREADS, 0, st>>>(P, maps);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the sm_100a kernels and the C-ABI host layer (not installed).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,6 +45,7 @@ struct OrbxLevel
 struct OrbxPlanDev
 {
 	int nlevels, frames;
+	int frame0;                  // index of this launch's first frame inside the planned batch (tensor maps address the whole batch)
 	int ini_th, min_th;
 	int cells_per_frame, cand_per_frame, sel_per_frame;
 	int node_cap;                // max list length of the quadtree over all levels (+ margin)
@@ -74,11 +76,20 @@ __device__ __forceinline__ int64_t orbx_level_pitch(const OrbxPlanDev& P, int le
 	return level == 0 ? P.l0_pitch : (int64_t)P.lv[level].pitch;
 }
 
+// TMA descriptors of the pyramid levels as seen by the FAST kernel: 3-D u8 tensors (x, y, frame), box FT_TS x box_h x 1
+struct OrbxTmaMaps
+{
+	CUtensorMap level[ORBX_MAX_LEVELS];
+	int box_h[ORBX_MAX_LEVELS];
+};
+int orbx_fast_tile_stride();
+int orbx_fast_tile_rows();
+
 // kernel launchers (orbx_extract.cu)
 void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,
                       int w, int h, int frames, cudaStream_t st);
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
-void orbx_launch_fast(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
