@@ -142,3 +142,40 @@ def test_getters_match_reference_tables(orbx, oracle_port):
     assert ex.GetLevels() == 8 and ex.GetScaleFactor() == np.float32(1.2)
     assert list(ex.GetFeatureQuotas()) == [217, 181, 151, 126, 105, 87, 73, 60]
     assert list(orbx.ORBextractor(nfeatures=8000).GetFeatureQuotas()) == [1737, 1448, 1207, 1005, 838, 698, 582, 485]
+
+
+def test_plan_rebuild_and_odd_batches(orbx, oracle_port):
+    # one handle, changing image sizes and batch sizes (plan rebuild, chunk pipeline with a ragged last chunk)
+    ex = orbx.ORBextractor(nfeatures=700)
+    e = oracle_port.extractor(700)
+    for (w, h, frames) in ((640, 480, 3), (752, 480, 1), (640, 480, 70), (400, 300, 5), (640, 480, 2)):
+        imgs = np.stack([synth.image(1000 + w + s, w, h) for s in range(min(frames, 6))])
+        if frames > len(imgs):
+            imgs = np.concatenate([imgs] * (frames // len(imgs) + 1))[:frames]
+        k, d = ex.ExtractBatch(imgs)
+        assert len(k) == frames
+        ref = {}
+        for f in range(frames):
+            key = f % 6
+            if key not in ref:
+                ref[key] = e.extract(imgs[f])
+            assert k[f].tobytes() == ref[key][0].tobytes() and np.array_equal(d[f], ref[key][1]), (w, h, frames, f)
+
+
+def test_two_extractors_on_two_threads(orbx, oracle_port):
+    # src/System.cc:449-452 runs the left and right extractor on two std::threads
+    import threading
+    c = synth.CONFIGS['C3']
+    L, R = synth.stereo_pair(31, c['w'], c['h'])
+    exs = [orbx.ORBextractor(nfeatures=c['nfeatures']) for _ in range(2)]
+    out = [None, None]
+
+    def work(i, img):
+        for _ in range(5):
+            out[i] = exs[i].Extract(img)
+    th = [threading.Thread(target=work, args=(0, L)), threading.Thread(target=work, args=(1, R))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for i, img in enumerate((L, R)):
+        ok, od = oracle_port.extractor(c['nfeatures']).extract(img)
+        assert out[i][0].tobytes() == ok.tobytes() and np.array_equal(out[i][1], od)
