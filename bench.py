@@ -268,7 +268,7 @@ def run_b200(args, rank, world, local_rank, emit):
     dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0
     traffic = None
     tj = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    kname = {'fast': 'k_fast_cells', 'describe': 'k_orient_describe', 'quadtree': 'k_quadtree'}.get(dominant)
+    kname = {'fast': 'k_fast_cells', 'describe': 'k_orient_describe', 'quadtree': 'k_quadtree'}.get(dominant)   # single-launch stages
     if os.path.exists(tj) and kname:
         t = json.load(open(tj)).get(kname)
         if t:   # dram__bytes_read + write of one launch at 256 frames (ncu --set full, profiles/), scaled to this batch

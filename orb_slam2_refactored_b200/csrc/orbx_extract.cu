@@ -953,8 +953,12 @@ __global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int l
 //     ComputeOrbDescriptor (:103-140) on the blurred level, then the keypoint record of Extract (:768-773,
 //     :811-815). One warp per output keypoint. Float path pinned per SURVEY H2 / App. A.6-A.7.
 // =====================================================================================================
-__constant__ int c_umax[ORBX_HALF_PATCH + 1];
-__constant__ signed char c_pattern[1024];
+__device__ int g_umax[ORBX_HALF_PATCH + 1];     // umax_ of ORBextractor::Init; global for the same reason as g_pattern
+// rBRIEF test pairs (src/ORBextractor.cc:142-400) in global memory: every thread of a block reads a different pair when the
+// shared-memory copy is built, which would serialise on the constant cache but is one coalesced 128-byte request here
+__device__ const signed char g_pattern[1024] = {
+#include "orb_pattern.inc"
+};
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 {
@@ -1008,11 +1012,12 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 	const int f = blockIdx.y;
 	{
 		const int p = tid;   // 256 pairs
-		s_pat[(p & 7) * 32 + (p >> 3)] = make_float4((float)c_pattern[4 * p], (float)c_pattern[4 * p + 1], (float)c_pattern[4 * p + 2], (float)c_pattern[4 * p + 3]);
+		const char4 pp = __ldg(reinterpret_cast<const char4*>(g_pattern) + p);
+		s_pat[(p & 7) * 32 + (p >> 3)] = make_float4((float)pp.x, (float)pp.y, (float)pp.z, (float)pp.w);
 		if (tid < 128)
 		{
 			// window word k holds columns u = 4k - 16 .. 4k - 13 of a disc row; inside the disc iff |u| <= umax[|v|]
-			const int k = tid >> 4, av = tid & 15, d = c_umax[av];
+			const int k = tid >> 4, av = tid & 15, d = g_umax[av];
 			uint32_t ones = 0, us = 0;
 #pragma unroll
 			for (int j = 0; j < 4; j++)
@@ -1064,10 +1069,11 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 			cp_async16(pblr + r * OD_PS + c * 16, gb + (int64_t)r * L.pitch + c * 16);
 		}
 	}
-	cp_async_wait_all();
-	__syncthreads();            // patches of this warp and the block's tables are in shared memory
+	__syncthreads();            // the block's tables are in shared memory (does not wait for the async copies)
 	if (!live)
 		return;
+	cp_async_wait_all();
+	__syncwarp();               // this warp's two patches have landed; warps do not wait for each other's DRAM latency
 	const OrbxLevel& L = P.lv[lvl];
 
 	// ---- intensity centroid over the radius-15 disc (IC_Angle, :74-101): lane = disc row v in [-15, 15]. The row's 32 bytes
@@ -1143,9 +1149,6 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 // =====================================================================================================
 cudaError_t orbx_upload_pattern()
 {
-	static const signed char pattern[1024] = {
-#include "orb_pattern.inc"
-	};
 	// umax_ of ORBextractor::Init (src/ORBextractor.cc:705-718)
 	int umax[ORBX_HALF_PATCH + 1];
 	const int vmax = (int)floor(ORBX_HALF_PATCH * sqrt(2.) / 2 + 1);
@@ -1163,8 +1166,7 @@ cudaError_t orbx_upload_pattern()
 	for (int n = 1; n < 72; n++) inv20[n] = (1u << 20) / (uint32_t)n + 1u;
 	cudaError_t e;
 	if ((e = cudaMemcpyToSymbol(c_inv20, inv20, sizeof(inv20))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_pattern, pattern, sizeof(pattern))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_umax, umax, sizeof(umax))) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
