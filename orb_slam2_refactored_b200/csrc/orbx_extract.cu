@@ -953,13 +953,10 @@ __global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int l
 //     ComputeOrbDescriptor (:103-140) on the blurred level, then the keypoint record of Extract (:768-773,
 //     :811-815). One warp per output keypoint. Float path pinned per SURVEY H2 / App. A.6-A.7.
 // =====================================================================================================
-__device__ int g_umax[ORBX_HALF_PATCH + 1];     // umax_ of ORBextractor::Init; global for the same reason as g_pattern
-// rBRIEF test pairs (src/ORBextractor.cc:142-400) in global memory: every thread of a block reads a different pair when the
-// shared-memory copy is built, which would serialise on the constant cache but is one coalesced 128-byte request here
-__device__ const signed char g_pattern[1024] = {
-#include "orb_pattern.inc"
-};
-
+// Lookup tables of the orientation/descriptor kernel live in global memory (L1-resident): lanes read different entries, which
+// would serialise on the constant cache (measured: 28 % of the kernel) but is one coalesced request here.
+__device__ float4 g_patf[256];                  // pair 8*byte + bit -> (x0,y0,x1,y1) as floats, stored at [bit][byte]: a warp reads 512 contiguous bytes
+__device__ uint2 g_mom[8 * 16];                 // [k][|v|]: .x = ones mask, .y = column offsets u (s8) of window word k of disc row v
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 {
 	const float R2D = (float)(180.0 / 3.14159265358979323846);
@@ -997,7 +994,7 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
 #define OD_IMG_ROWS 31                               // un-blurred patch rows y-15 .. y+15, 48 bytes each from (x-16) & ~15
 #define OD_BLR_ROWS 37                               // blurred patch rows y-18 .. y+18, 64 bytes each from (x-18) & ~15
 #define OD_WARP_BYTES ((OD_IMG_ROWS + OD_BLR_ROWS) * OD_PS)
-#define OD_SMEM (OD_WARPS * OD_WARP_BYTES + 256 * 16 + 128 * 8)
+#define OD_SMEM (OD_WARPS * OD_WARP_BYTES)
 
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps,
                                                                   uint8_t* __restrict__ d_desc, int32_t* __restrict__ d_n)
@@ -1006,28 +1003,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 	// the 512 rBRIEF samples) are staged in shared memory with 16-byte async copies — 241 coalesced chunks instead of ~570
 	// scattered byte gathers — and everything after that reads shared memory.
 	extern __shared__ __align__(16) uint8_t od_smem[];
-	float4* s_pat = reinterpret_cast<float4*>(od_smem + OD_WARPS * OD_WARP_BYTES);   // pair p = 8*byte + bit -> (x0,y0,x1,y1), stored at [bit][byte]
-	uint2* s_mom = reinterpret_cast<uint2*>(s_pat + 256);                            // [k][|v|]: .x = ones mask, .y = column offsets u (s8) of window word k
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int f = blockIdx.y;
-	{
-		const int p = tid;   // 256 pairs
-		const char4 pp = __ldg(reinterpret_cast<const char4*>(g_pattern) + p);
-		s_pat[(p & 7) * 32 + (p >> 3)] = make_float4((float)pp.x, (float)pp.y, (float)pp.z, (float)pp.w);
-		if (tid < 128)
-		{
-			// window word k holds columns u = 4k - 16 .. 4k - 13 of a disc row; inside the disc iff |u| <= umax[|v|]
-			const int k = tid >> 4, av = tid & 15, d = g_umax[av];
-			uint32_t ones = 0, us = 0;
-#pragma unroll
-			for (int j = 0; j < 4; j++)
-			{
-				const int u = 4 * k + j - 16;
-				if (abs(u) <= d) { ones |= 1u << (8 * j); us |= (uint32_t)(uint8_t)(signed char)u << (8 * j); }
-			}
-			s_mom[k * 16 + av] = make_uint2(ones, us);
-		}
-	}
 
 	// which level does output slot `slot` belong to (levels are concatenated in order, :792-819): lane l holds level l's count
 	const int slot = blockIdx.x * OD_WARPS + warp;
@@ -1069,11 +1046,10 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 			cp_async16(pblr + r * OD_PS + c * 16, gb + (int64_t)r * L.pitch + c * 16);
 		}
 	}
-	__syncthreads();            // the block's tables are in shared memory (does not wait for the async copies)
 	if (!live)
 		return;
 	cp_async_wait_all();
-	__syncwarp();               // this warp's two patches have landed; warps do not wait for each other's DRAM latency
+	__syncwarp();               // this warp's two patches have landed; warps never wait for each other (no block barrier in this kernel)
 	const OrbxLevel& L = P.lv[lvl];
 
 	// ---- intensity centroid over the radius-15 disc (IC_Angle, :74-101): lane = disc row v in [-15, 15]. The row's 32 bytes
@@ -1089,13 +1065,13 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 		uint32_t w[9];
 #pragma unroll
 		for (int k = 0; k < 9; k++) w[k] = wp[k];
-		const uint2* tab = s_mom + abs(v);
+		const uint2* __restrict__ tab = g_mom + abs(v);
 		int rowsum = 0;
 #pragma unroll
 		for (int k = 0; k < 8; k++)
 		{
 			const uint32_t win = __funnelshift_r(w[k], w[k + 1], shb);
-			const uint2 cf = tab[k * 16];
+			const uint2 cf = __ldg(tab + k * 16);
 			rowsum = (int)__dp4a(win, cf.x, (uint32_t)rowsum);
 			m10 = dp4a_u8_s8(win, cf.y, m10);
 		}
@@ -1118,7 +1094,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 #pragma unroll
 	for (int bit = 0; bit < 8; bit++)
 	{
-		const float4 pt = s_pat[bit * 32 + lane];
+		const float4 pt = __ldg(g_patf + bit * 32 + lane);
 		const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, sb), __fmul_rn(pt.y, ca)));
 		const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, ca), __fmul_rn(pt.y, sb)));
 		const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, sb), __fmul_rn(pt.w, ca)));
@@ -1161,12 +1137,32 @@ cudaError_t orbx_upload_pattern()
 		umax[v] = v0;
 		++v0;
 	}
+	static const signed char pattern[1024] = {
+#include "orb_pattern.inc"
+	};
+	float4 patf[256];
+	for (int p = 0; p < 256; p++)
+		patf[(p & 7) * 32 + (p >> 3)] = make_float4((float)pattern[4 * p], (float)pattern[4 * p + 1], (float)pattern[4 * p + 2], (float)pattern[4 * p + 3]);
+	uint2 mom[8 * 16];
+	for (int k = 0; k < 8; k++)
+		for (int av = 0; av < 16; av++)
+		{
+			// window word k holds columns u = 4k - 16 .. 4k - 13 of a disc row; inside the disc iff |u| <= umax[|v|]
+			uint32_t ones = 0, us = 0;
+			for (int j = 0; j < 4; j++)
+			{
+				const int u = 4 * k + j - 16;
+				if (abs(u) <= umax[av]) { ones |= 1u << (8 * j); us |= (uint32_t)(uint8_t)(signed char)u << (8 * j); }
+			}
+			mom[k * 16 + av] = make_uint2(ones, us);
+		}
 	uint32_t inv20[72];
 	inv20[0] = 0;
 	for (int n = 1; n < 72; n++) inv20[n] = (1u << 20) / (uint32_t)n + 1u;
 	cudaError_t e;
 	if ((e = cudaMemcpyToSymbol(c_inv20, inv20, sizeof(inv20))) != cudaSuccess) return e;
-	if ((e = cudaMemcpyToSymbol(g_umax, umax, sizeof(umax))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_patf, patf, sizeof(patf))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(g_mom, mom, sizeof(mom))) != cudaSuccess) return e;
 	return cudaSuccess;
 }
 
