@@ -129,7 +129,7 @@ def cpu_extract_rate(o, frames, threads, per_thread):
     return sum(done) / dt, dt
 
 
-def cpu_knn_rate(o, threads, nq=4096, nt=250000):
+def cpu_knn_rate(o, threads, nq=8192, nt=1000000):
     q = synth.descriptors(1, nq); t = synth.descriptors(2, nt)
     o.knn2(q[:64], t[:1000], 50, 0.6, threads=1)
     t0 = time.perf_counter()
@@ -144,9 +144,9 @@ def run_reference(args, rank, world, emit):
     o, kind, native = load_cpu_reference()
     threads = os.cpu_count() or 1
     frames = make_frames(max(24, threads), 0)
-    per_thread = 2
-    for _ in range(args.warmup):
-        cpu_extract_rate(o, frames, threads, 1)
+    for _ in range(max(args.warmup, 1)):
+        r0, _ = cpu_extract_rate(o, frames, threads, 1)
+    per_thread = max(2, int(1.5 * r0 / threads))                                   # each step is about 1.5 s of CPU work
     t_all, n_all = 0.0, 0
     for _ in range(args.steps):
         r, dt = cpu_extract_rate(o, frames, threads, per_thread)
@@ -363,7 +363,8 @@ def run_b200(args, rank, world, local_rank, emit):
         try:
             o, kind, native = load_cpu_reference()
             threads = os.cpu_count() or 1
-            per_thread = 12
+            r0, _ = cpu_extract_rate(o, host[:48], threads, 2)                    # calibration
+            per_thread = max(4, int(12.0 * r0 / threads))                          # about 12 s of CPU work
             r, dt_cpu = cpu_extract_rate(o, host[:48], threads, per_thread)
             cpu = {'value': r, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
                    'sample': f'{threads * per_thread} frames of the same workload, one frame per thread at a time, {dt_cpu:.1f} s, '
