@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	__shared__ int s_rootcnt[ORBX_MAX_ROOTS];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int lvl = blockIdx.x, f = blockIdx.y;
+	const int lvl = blockIdx.y, f = blockIdx.x;      // x = frame: all level-0 CTAs (the longest) are scheduled first
 	const OrbxLevel& L = P.lv[lvl];
 	const int ncell = L.ncx * L.ncy;
 	const int* __restrict__ ccount = P.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
@@ -1205,7 +1205,7 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 {
 	const size_t smem = orbx_quadtree_smem(P.node_cap);
 	cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	dim3 grid(P.nlevels, P.frames);
+	dim3 grid(P.frames, P.nlevels);
 	k_quadtree<<<grid, QT_THREADS, smem, st>>>(P, cell_off);
 }
 
