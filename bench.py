@@ -412,7 +412,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
+    ap.add_argument('--batch', type=int, default=512, help='frames per step per GPU')
     ap.add_argument('--e2e-handles', type=int, default=2, help='extractor instances (host threads) of the end-to-end leg')
     ap.add_argument('--knn-steps', type=int, default=2)
     ap.add_argument('--knn-queries', type=int, default=1000000)
