@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 #define FT_SS 64            // score row stride (region <= 60 px + 1 px zero border each side)
 #define FT_MAXR 60
 #define FT_THREADS 128
+#define FT_WORDS ((FT_MAXR * FT_MAXR + 31) / 32)                      // bitmap words for the largest region
+#define FT_WPT ((FT_WORDS + FT_THREADS - 1) / FT_THREADS)           // bitmap words owned by one thread
 
 __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 {
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 	__shared__ __align__(8) uint64_t tma_bar;
 	__shared__ __align__(16) uint8_t score[(FT_MAXR + 2) * FT_SS];
 	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
-	__shared__ uint32_t bm_a[FT_THREADS], bm_b[FT_THREADS], bm_sel[FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
+	__shared__ uint32_t bm_a[FT_WPT * FT_THREADS], bm_b[FT_WPT * FT_THREADS], bm_sel[FT_WPT * FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
 	__shared__ int s_wsum[FT_THREADS / 32];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,7 +262,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 	}
 	for (int i = tid; i < (rh + 2) * (FT_SS / 4); i += FT_THREADS)
 		reinterpret_cast<uint32_t*>(score)[i] = 0;
-	bm_a[tid] = 0; bm_b[tid] = 0; bm_sel[tid] = 0;
+#pragma unroll
+	for (int k = 0; k < FT_WPT; k++) { bm_a[tid * FT_WPT + k] = 0; bm_b[tid * FT_WPT + k] = 0; bm_sel[tid * FT_WPT + k] = 0; }
 	__syncthreads();            // the barrier init by thread 0 is visible to every waiter
 	mbar_wait(&tma_bar, 0);
 
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 	//      are the bitmap words of those pixels.
 	{
 		// (ry, rx) of pixel tid, then stepped by 128 pixels per iteration without multiplications
-		const int step_y = (int)((128u * inv_rw) >> 20), step_x = 128 - step_y * rw;
+		const int step_y = (int)(((uint32_t)FT_THREADS * inv_rw) >> 20), step_x = FT_THREADS - step_y * rw;
 		int ry = (int)(((uint32_t)tid * inv_rw) >> 20), rx = tid - ry * rw;
 		const uint8_t* p = t0 + ry * FT_TS + rx;
 		const int step_p = step_y * FT_TS + step_x, wrap_p = FT_TS - rw;
@@ -312,14 +315,19 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 	};
 	// append the pixels of a bitmap to the list (row-major inside the bitmap); returns how many
 	auto expand = [&](const uint32_t* bm, int at) {
-		uint32_t w = bm[tid];
+		uint32_t w[FT_WPT];
+		int cnt = 0;
+#pragma unroll
+		for (int k = 0; k < FT_WPT; k++) { w[k] = bm[tid * FT_WPT + k]; cnt += __popc(w[k]); }
 		int total;
-		int pos = at + block_scan(__popc(w), total);
-		while (w)
-		{
-			list[pos++] = (uint16_t)(tid * 32 + __ffs(w) - 1);
-			w &= w - 1;
-		}
+		int pos = at + block_scan(cnt, total);
+#pragma unroll
+		for (int k = 0; k < FT_WPT; k++)
+			while (w[k])
+			{
+				list[pos++] = (uint16_t)((tid * FT_WPT + k) * 32 + __ffs(w[k]) - 1);
+				w[k] &= w[k] - 1;
+			}
 		return total;
 	};
 	// exact score of list[from, to)
@@ -368,19 +376,24 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 		__syncthreads();
 	}
 
-	// ---- D: ordered emit; thread t owns bitmap word t = pixels [32t, 32t + 32)
-	uint32_t selm = bm_sel[tid];
+	// ---- D: ordered emit; thread t owns bitmap words [t*FT_WPT, (t+1)*FT_WPT)
+	uint32_t selw[FT_WPT];
+	int nsel = 0;
+#pragma unroll
+	for (int k = 0; k < FT_WPT; k++) { selw[k] = bm_sel[tid * FT_WPT + k]; nsel += __popc(selw[k]); }
 	int total;
-	int base = block_scan(__popc(selm), total);
+	int base = block_scan(nsel, total);
 	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
-	while (selm)
-	{
-		const int i = tid * 32 + __ffs(selm) - 1;
-		selm &= selm - 1;
-		const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-		const int s = score[(ry + 1) * FT_SS + rx + 1];
-		out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
-	}
+#pragma unroll
+	for (int k = 0; k < FT_WPT; k++)
+		while (selw[k])
+		{
+			const int i = (tid * FT_WPT + k) * 32 + __ffs(selw[k]) - 1;
+			selw[k] &= selw[k] - 1;
+			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
+			const int s = score[(ry + 1) * FT_SS + rx + 1];
+			out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
+		}
 	if (tid == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
 }
