@@ -367,6 +367,44 @@ def run_b200(args, rank, world, local_rank, emit):
             knn['e2e'] = {'value': sq * st / dtk / 1e9, 'unit': 'Gpairs/s', 'h2d_bytes_per_step': 32 * (sq + st), 'd2h_bytes_per_step': 12 * sq,
                           'sample': f'{sq} x {st} through orbx_knn2 (pageable host buffers, allocation included)'}
 
+    # ---- stereo: BASELINE.json configs[1] (KITTI shape 1241x376, 2000 kp, left + right Extract + ComputeStereoMatches), resident
+    stereo = None
+    if not args.skip_stereo:
+        c2 = synth.CONFIGS['C2']
+        SB = args.stereo_pairs
+        base = [synth.stereo_pair(500 + 100 * rank + s, c2['w'], c2['h']) for s in range(8)]
+        Ls = np.stack([base[i % 8][0] if (i // 8) % 2 == 0 else base[i % 8][0][::-1] for i in range(SB)])
+        Rs = np.stack([base[i % 8][1] if (i // 8) % 2 == 0 else base[i % 8][1][::-1] for i in range(SB)])
+        dL = torch.from_numpy(np.ascontiguousarray(Ls)).to(dev); dR = torch.from_numpy(np.ascontiguousarray(Rs)).to(dev)
+        eL = api.ORBextractor(nfeatures=c2['nfeatures'], device=local_rank); eR = api.ORBextractor(nfeatures=c2['nfeatures'], device=local_rank)
+        oL = eL.extract_batch_device(dL); oR = eR.extract_batch_device(dR)
+        capS = oL[0].shape[1]
+        d_ur = torch.empty((SB, capS), dtype=torch.float32, device=dev); d_dp = torch.empty((SB, capS), dtype=torch.float32, device=dev)
+        cam = api._Camera(*[float(v) for v in c2['camera']])
+
+        def stereo_step():
+            eL.extract_batch_device(dL, *oL); eR.extract_batch_device(dR, *oR)
+            api._check(api.lib().orbx_stereo_match_device(eL._h, eR._h, C.byref(cam), C.c_void_p(d_ur.data_ptr()), C.c_void_p(d_dp.data_ptr())))
+        for _ in range(3):
+            stereo_step()
+        eL.synchronize(); eR.synchronize()
+        barrier()
+        sL = torch.cuda.ExternalStream(eL.stream(), device=dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ssteps = max(2, min(args.steps, 10))
+        torch.cuda.synchronize(dev)
+        s0.record(sL)
+        for _ in range(ssteps):
+            stereo_step()
+        s1.record(sL)           # the match runs on the left extractor's stream after waiting for the right one
+        s1.synchronize(); eR.synchronize()
+        barrier()
+        ms_st = max_over_ranks(s0.elapsed_time(s1)) / ssteps
+        matched = int((d_dp[:, :] > 0).sum().item())
+        stereo = {'value': world * SB / (ms_st * 1e-3), 'unit': 'stereo pairs/s', 'ms_per_step': ms_st, 'pairs_per_step_per_gpu': SB,
+                  'workload': 'C2: 1241x376 stereo, 2000 kp per image, Extract left + right and ComputeStereoMatches, device-resident',
+                  'matched_per_pair': matched / SB}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -402,6 +440,7 @@ def run_b200(args, rank, world, local_rank, emit):
             'roofline': roofline,
             'cpu_baseline': cpu,
             'knn': knn,
+            'stereo': stereo,
         }
         emit(json.dumps(line))
 
@@ -418,6 +457,8 @@ def main():
     ap.add_argument('--knn-queries', type=int, default=1000000)
     ap.add_argument('--knn-train-per-gpu', type=int, default=1250000)
     ap.add_argument('--skip-knn', action='store_true')
+    ap.add_argument('--skip-stereo', action='store_true')
+    ap.add_argument('--stereo-pairs', type=int, default=64)
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

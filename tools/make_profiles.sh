@@ -4,7 +4,7 @@
 set -u
 R=${1:-r01}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --skip-cpu --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144"
+CMD="python bench.py --steps 3 --warmup 3 --batch 256 --skip-cpu --skip-stereo --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144"
 $CMD > gpurun_out/${R}_plain.json 2> gpurun_out/${R}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${R}_plain.err; exit 1; }
 # device-resident steps: 6 x 18 launches (+1 D2D copy each), then e2e chunks; capture a window that covers one whole step
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 140 --csv --log-file gpurun_out/${R}_launches.csv $CMD > gpurun_out/${R}_ncu_launches.log 2>&1
