@@ -554,12 +554,44 @@ __device__ void qs_insertion(uint64_t* a, int first, int last)
 	}
 }
 
-__device__ void qs_sort(uint64_t* a, int n)
+// One partition step of __introsort_loop on [first, last) (last - first > 16): median of three to the front, unguarded
+// partition around it. Returns the cut. Executed by a single thread.
+__device__ int qs_partition(uint64_t* a, int first, int last)
+{
+	const int mid = first + (last - first) / 2;
+	{   // __move_median_to_first(first, first+1, mid, last-1)
+		const int r = first, x = first + 1, y = mid, z = last - 1;
+		if (qs_before(a[x], a[y]))
+		{
+			if (qs_before(a[y], a[z])) qs_swap(a, r, y);
+			else if (qs_before(a[x], a[z])) qs_swap(a, r, z);
+			else qs_swap(a, r, x);
+		}
+		else if (qs_before(a[x], a[z])) qs_swap(a, r, x);
+		else if (qs_before(a[y], a[z])) qs_swap(a, r, z);
+		else qs_swap(a, r, y);
+	}
+	int lo = first + 1, hi = last;
+	const uint64_t pivot_key = a[first];   // the pivot stays at a[first] during the partition
+	for (;;)
+	{
+		while (qs_before(a[lo], pivot_key)) ++lo;
+		--hi;
+		while (qs_before(pivot_key, a[hi])) --hi;
+		if (!(lo < hi)) break;
+		qs_swap(a, lo, hi);
+		++lo;
+	}
+	return lo;
+}
+
+// std::sort by one thread: __introsort_loop with an explicit stack, then __final_insertion_sort. Used for small inputs,
+// where the rounds of the block-parallel version below cost more barriers than they save.
+__device__ __noinline__ void qs_sort_serial(uint64_t* a, int n)
 {
 	if (n == 0) return;
 	int lg = 0;
 	for (int m = n; m > 1; m >>= 1) ++lg;
-	// introsort loop with an explicit stack (recursion on the right part, iteration on the left)
 	int st_first[48], st_last[48], st_depth[48];
 	int sp = 0;
 	st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
@@ -571,34 +603,11 @@ __device__ void qs_sort(uint64_t* a, int n)
 		{
 			if (depth == 0) { qs_heapsort(a, first, last); break; }
 			--depth;
-			const int mid = first + (last - first) / 2;
-			{   // __move_median_to_first(first, first+1, mid, last-1)
-				const int r = first, x = first + 1, y = mid, z = last - 1;
-				if (qs_before(a[x], a[y]))
-				{
-					if (qs_before(a[y], a[z])) qs_swap(a, r, y);
-					else if (qs_before(a[x], a[z])) qs_swap(a, r, z);
-					else qs_swap(a, r, x);
-				}
-				else if (qs_before(a[x], a[z])) qs_swap(a, r, x);
-				else if (qs_before(a[y], a[z])) qs_swap(a, r, z);
-				else qs_swap(a, r, y);
-			}
-			int lo = first + 1, hi = last;
-			const uint64_t pivot_key = a[first];   // the pivot stays at a[first] during the partition
-			for (;;)
-			{
-				while (qs_before(a[lo], pivot_key)) ++lo;
-				--hi;
-				while (qs_before(pivot_key, a[hi])) --hi;
-				if (!(lo < hi)) break;
-				qs_swap(a, lo, hi);
-				++lo;
-			}
-			// right part [lo, last) is sorted "recursively" before the left part continues; the two ranges are
-			// disjoint, so deferring it on the stack yields the same result
-			st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp;
-			last = lo;
+			const int cut = qs_partition(a, first, last);
+			// the right part is sorted "recursively" before the left part continues; the ranges are disjoint, so deferring it
+			// on the stack yields the same result
+			st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp;
+			last = cut;
 		}
 	}
 	if (n > 16)
@@ -609,12 +618,134 @@ __device__ void qs_sort(uint64_t* a, int n)
 	else qs_insertion(a, 0, n);
 }
 
+// std::sort replayed by the whole CTA with the SAME result as the serial algorithm. Two facts make that possible:
+//  * after a partition step the two sub-ranges are never touched together again, so __introsort_loop's "recurse right,
+//    iterate left" can run both sides at the same time: every round, each pending range (> 16 elements) is partitioned by
+//    one thread; a range keeps the depth budget it would have had (both sides inherit depth - 1; budget 0 = heapsort);
+//  * the partition leaves every element of a left range "not after" every element of the range to its right (sizes >= pivot
+//    on the left, <= pivot on the right), so __final_insertion_sort never moves an element across a range boundary: it is
+//    a stable insertion sort of every final range (<= 16 elements) on its own.
+// Time is ~2n serial steps (n + n/2 + n/4 ...) instead of ~1.4 n log2 n.
+struct QSeg { int first, last, depth; };
+
+__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, int2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0)
+	{
+		int lg = 0;
+		for (int m = n; m > 1; m >>= 1) ++lg;
+		s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
+		if (n > 16) { segq[0] = { 0, n, 2 * lg }; s_cnt[0] = 1; }
+		else if (n > 1) { leaf[0] = make_int2(0, n); s_cnt[2] = 1; }
+	}
+	__syncthreads();
+	int cur = 0;
+	for (;;)
+	{
+		const int ns = s_cnt[cur];
+		if (ns == 0) break;
+		__syncthreads();
+		if (tid == 0) s_cnt[cur ^ 1] = 0;
+		__syncthreads();
+		QSeg* in = segq + cur * segcap;
+		QSeg* out = segq + (cur ^ 1) * segcap;
+		for (int si = tid; si < ns; si += QT_THREADS)
+		{
+			const QSeg sg = in[si];
+			if (sg.depth == 0) { qs_heapsort(a, sg.first, sg.last); continue; }     // fully sorted, no insertion pass needed
+			const int cut = qs_partition(a, sg.first, sg.last);
+#pragma unroll
+			for (int side = 0; side < 2; side++)
+			{
+				const int f0 = side ? cut : sg.first, l0 = side ? sg.last : cut;
+				if (l0 - f0 > 16) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = { f0, l0, sg.depth - 1 };
+				else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_int2(f0, l0);
+			}
+		}
+		__syncthreads();
+		cur ^= 1;
+	}
+	const int nleaf = s_cnt[2];
+	for (int li = tid; li < nleaf; li += QT_THREADS) qs_insertion(a, leaf[li].x, leaf[li].y);
+	__syncthreads();
+}
+
 __device__ __forceinline__ int quadrant_of(uint32_t v, int xm, int ym)
 {
 	const int x = orbx_px(v), y = orbx_py(v);
 	return x < xm ? (y < ym ? 0 : 2) : (y < ym ? 1 : 3);
 }
 
+#define QT_BIG 2048
+// Stable 4-way partition of one big node by the whole CTA (see the call site).
+__device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint32_t* buf1, uint32_t* cc, int (*s_bigc)[4], int (*s_bigw)[QT_WARPS][4])
+{
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int cnt = (int)QN_CNT(nd);
+	const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
+	uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
+	const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+	for (int i = tid; i < cnt; i += QT_THREADS)
+	{
+		const int q = quadrant_of(src[i], xm, ym);
+		c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1)
+	{
+		c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+		c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
+	}
+	if (lane == 0) { s_bigc[warp][0] = c0; s_bigc[warp][1] = c1; s_bigc[warp][2] = c2; s_bigc[warp][3] = c3; }
+	__syncthreads();
+	int tot[4], run[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++)
+	{
+		tot[q] = 0;
+#pragma unroll
+		for (int w = 0; w < QT_WARPS; w++) tot[q] += s_bigc[w][q];
+	}
+	run[0] = 0; run[1] = tot[0]; run[2] = tot[0] + tot[1]; run[3] = tot[0] + tot[1] + tot[2];
+	int par = 0;
+	for (int i0 = 0; i0 < cnt; i0 += QT_THREADS, par ^= 1)
+	{
+		const int i = i0 + tid;
+		const bool ok = i < cnt;
+		const uint32_t v = ok ? src[i] : 0u;
+		const int q = ok ? quadrant_of(v, xm, ym) : -1;
+		unsigned bq[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) bq[k] = __ballot_sync(0xffffffffu, q == k);
+		if (lane < 4) s_bigw[par][warp][lane] = __popc(lane == 0 ? bq[0] : lane == 1 ? bq[1] : lane == 2 ? bq[2] : bq[3]);
+		__syncthreads();                     // one barrier per chunk: the count buffers alternate
+		int before = 0, mine = 0, chunk_tot[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			chunk_tot[k] = 0;
+#pragma unroll
+			for (int w = 0; w < QT_WARPS; w++)
+			{
+				const int x = s_bigw[par][w][k];
+				chunk_tot[k] += x;
+				if (w < warp && k == q) before += x;
+			}
+			if (k == q) mine = run[k] + __popc(bq[k] & lanemask_lt());
+		}
+		if (ok) dst[mine + before] = v;
+#pragma unroll
+		for (int k = 0; k < 4; k++) run[k] += chunk_tot[k];
+	}
+	if (tid == 0) { cc[0] = tot[0]; cc[1] = tot[1]; cc[2] = tot[2]; cc[3] = tot[3]; }
+	__syncthreads();
+}
+
+// BIG selects the variant with the CTA-parallel sort and big-node partition (4K-class levels); the plain variant keeps the
+// register count at 40 for VGA-class levels, where occupancy matters more than the serial tails.
+template <bool BIG>
 __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off)
 {
 	extern __shared__ __align__(16) uint8_t qsm[];
@@ -625,10 +756,15 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	uint32_t* childcnt = reinterpret_cast<uint32_t*>(items + M);       // [M][4]
 	uint32_t* proc = childcnt + 4 * M;                                 // positions (old list) to divide, processing order
 	uint32_t* pbase = proc + M;                                        // exclusive scan of non-empty child counts
-	uint8_t* gone = reinterpret_cast<uint8_t*>(pbase + M);               // old-list positions removed by this pass
+	int2* leaf = reinterpret_cast<int2*>(pbase + M);                   // ranges (<= 16 items) left for the insertion pass of the sort
+	const int segcap = M / 16 + 4;
+	QSeg* segq = reinterpret_cast<QSeg*>(leaf + M);                    // [2][segcap] ranges still to be partitioned
+	uint8_t* gone = reinterpret_cast<uint8_t*>(segq + 2 * segcap);     // old-list positions removed by this pass
 	__shared__ int s_w[QT_WARPS];
 	__shared__ int s_K;
+	__shared__ int s_sort[3];
 	__shared__ int s_rootcnt[ORBX_MAX_ROOTS];
+	__shared__ int s_bigc[QT_WARPS][4], s_bigw[2][QT_WARPS][4];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lvl = blockIdx.y, f = blockIdx.x;      // x = frame: all level-0 CTAs (the longest) are scheduled first
@@ -720,18 +856,35 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			np = block_ordered(lastP, s_w, [&](int g) { return QN_CNT(cur[lastP - 1 - g]) > 1; },
 			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
 			__syncthreads();
-			if (tid == 0) qs_sort(items, np);
-			__syncthreads();
+			if (BIG && np > 512)
+				qs_sort_block(items, np, segq, segcap, leaf, s_sort);      // large levels (4K): ~2n serial steps instead of ~1.4 n log2 n
+			else
+			{
+				if (tid == 0) qs_sort_serial(items, np);
+				__syncthreads();
+			}
 			for (int i = tid; i < np; i += QT_THREADS) proc[i] = (uint32_t)(items[i] & 0xffffffffu);
 		}
 		for (int i = tid; i < listLen; i += QT_THREADS) gone[i] = 0;
 		__syncthreads();
+
+		// ---- big nodes (the first passes of a large level: one node can hold tens of thousands of candidates) are divided by
+		//      the whole CTA: chunks of QT_THREADS elements in order, position = quadrant base + earlier chunks + earlier warps of the
+		//      chunk + earlier lanes of the warp, i.e. the same stable 4-way partition as the warp version below.
+		if (BIG && np <= 64)
+			for (int t = 0; t < np; t++)
+			{
+				const QNode nd = cur[proc[t]];
+				if ((int)QN_CNT(nd) >= QT_BIG)                  // uniform: every thread sees the same node
+					qt_divide_big(nd, buf0, buf1, childcnt + 4 * t, s_bigc, s_bigw);
+			}
 
 		// ---- divide (speculatively all of them; Phase 2 may stop early, parents stay intact in their buffer)
 		for (int t = warp; t < np; t += QT_WARPS)
 		{
 			const QNode nd = cur[proc[t]];
 			const int cnt = (int)QN_CNT(nd);
+			if (BIG && np <= 64 && cnt >= QT_BIG) continue;        // done by the whole CTA above
 			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
 			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
@@ -1210,16 +1363,24 @@ int orbx_pyramid_max_src_bytes() { return PY_SW; }
 
 size_t orbx_quadtree_smem(int node_cap)
 {
-	// listA, listB (16 B), items (8 B), childcnt (16 B), proc, pbase (4 B each), gone (1 B)
-	return (size_t)node_cap * (16 + 16 + 8 + 16 + 4 + 4 + 1) + 64;
+	// listA, listB (16 B), items (8 B), childcnt (16 B), proc, pbase (4 B each), leaf (8 B), gone (1 B), 2 segment queues (12 B x cap/16)
+	return (size_t)node_cap * (16 + 16 + 8 + 16 + 4 + 4 + 8 + 1) + 2 * 12 * ((size_t)node_cap / 16 + 4) + 64;
 }
 
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 {
 	const size_t smem = orbx_quadtree_smem(P.node_cap);
-	cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 grid(P.frames, P.nlevels);
-	k_quadtree<<<grid, QT_THREADS, smem, st>>>(P, cell_off);
+	if (P.node_cap > 1024)      // some level keeps more than ~1000 keypoints: its sort and first divides are worth a whole CTA
+	{
+		cudaFuncSetAttribute(k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_quadtree<true><<<grid, QT_THREADS, smem, st>>>(P, cell_off);
+	}
+	else
+	{
+		cudaFuncSetAttribute(k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_quadtree<false><<<grid, QT_THREADS, smem, st>>>(P, cell_off);
+	}
 }
 
 void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
