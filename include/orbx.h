@@ -186,6 +186,64 @@ orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const or
  * the descriptor with the least median distance to the set (first wins ties), -1 for an empty set. Host buffers. */
 orbx_status orbx_distinctive_descriptors(int device, const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best);
 
+/* ---- guided matchers: FeaturesGrid + the window searches of Tracking ---- */
+
+typedef struct orbx_bounds { float minx, maxx, miny, maxy; } orbx_bounds;   /* ImageBounds, include/Frame.h:40-48 */
+typedef struct orbx_pose { float R[9]; float t[3]; } orbx_pose;             /* CameraPose (include/CameraPose.h:32-90), R row-major */
+
+/* A Frame as the matchers see it (include/Frame.h:83-168): keypointsUn, descriptors (n x 32), uright (NULL = every entry -1),
+ * imageBounds, pyramid.nlevels (<= 16) and pyramid.scaleFactors. Host pointers. */
+typedef struct orbx_frame_view
+{
+	int32_t n;
+	const orbx_keypoint* kps_un;
+	const uint8_t* desc;
+	const float* uright;
+	orbx_bounds bounds;
+	int32_t nlevels;
+	const float* scale_factors;
+} orbx_frame_view;
+
+/* One candidate map point of SearchByProjection(Frame&, mappoints, th): the track* members set by Tracking::SearchLocalPoints
+ * (include/MapPoint.h:92-97). flags bit 0 = trackInView && !isBad(), bit 1 = Observations() > 0. */
+typedef struct orbx_track_point { float proj_x, proj_y, proj_xr, view_cos; int32_t scale_level; int32_t flags; } orbx_track_point;
+/* One keypoint of the last frame for SearchByProjection(currFrame, lastFrame, th, monocular): world position of its map point,
+ * lastFrame.keypoints[i].octave, lastFrame.keypointsUn[i].angle. flags bit 0 = has a map point && !outlier, bit 1 = Observations() > 0. */
+typedef struct orbx_last_point { float xw[3]; int32_t octave; float angle; int32_t flags; } orbx_last_point;
+
+/* A frame resident on one GPU: keypoints, descriptors, right coordinates and its FeaturesGrid (FeaturesGrid::AssignFeatures,
+ * src/Frame.cc:70-100, built on the device). Not re-entrant, like a Frame that is being matched. */
+typedef struct orbx_frame_s* orbx_frame;
+orbx_status orbx_frame_create(const orbx_frame_view* view, int device, orbx_frame* out);
+orbx_status orbx_frame_destroy(orbx_frame f);
+/* The grid as CSR: cell_start has 64*48+1 entries, cell = cx*48 + cy (grid_[cx][cy], include/Frame.h:72-79); items holds the keypoint
+ * indices of every cell in push_back order. *n_items = number of keypoints inside the grid. */
+orbx_status orbx_frame_grid(orbx_frame f, int32_t* cell_start, int32_t* items, int cap, int* n_items);
+/* FeaturesGrid::GetFeaturesInArea (src/Frame.cc:102-145) for nq windows: xyr = (x, y, r) triples, levels = (minLevel, maxLevel) pairs.
+ * offsets gets nq+1 entries; the indices of window q are indices[offsets[q] .. offsets[q+1]) in the reference's output order.
+ * ORBX_ERR_CAPACITY when cap < offsets[nq] (offsets are valid then). */
+orbx_status orbx_frame_features_in_area(orbx_frame f, const float* xyr, const int32_t* levels, int nq, int32_t* offsets, int32_t* indices,
+                                        int cap);
+
+/* frame_mp (f->n entries, in/out) stands for frame.mappoints: -1 = null, >= 0 = index into `pts` of the map point stored there,
+ * -2 = some other map point with Observations() > 0, -3 = some other map point without observations. */
+
+/* ORBmatcher::SearchByProjection(Frame&, const std::vector<MapPoint*>&, float th) — src/ORBmatcher.cc:315-382 (local-map tracking).
+ * pt_desc = mappoint->GetDescriptor() of every point, 32 bytes each. nnratio = the matcher's fNNRatio_. */
+orbx_status orbx_search_by_projection_local_map(orbx_frame f, int32_t* frame_mp, const orbx_track_point* pts, const uint8_t* pt_desc,
+                                                int npts, float th, float nnratio, int* nmatches);
+/* ORBmatcher::SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular) — src/ORBmatcher.cc:1279-1362
+ * (motion-model tracking) with CheckOrientation (:249-309) when check_orientation != 0. camera/cur_pose belong to currFrame. */
+orbx_status orbx_search_by_projection_last_frame(orbx_frame cur, const orbx_camera* camera, const orbx_pose* cur_pose,
+                                                 const orbx_pose* last_pose, int32_t* frame_mp, const orbx_last_point* pts,
+                                                 const uint8_t* pt_desc, int npts, float th, int monocular, int check_orientation,
+                                                 int* nmatches);
+/* ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:614-694. prev_matched: f1->n (x, y) pairs, in/out; matches12: f1->n, out. */
+orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size,
+                                           float nnratio, int check_orientation, int* nmatches);
+/* rounds the last search on `f` needed to reach the sequential result (diagnostic; >= 1) */
+orbx_status orbx_frame_last_rounds(orbx_frame f, int* rounds);
+
 /* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
  * `device` (all SMs, register operands). */
 orbx_status orbx_measure_popc_peak(int device, double* popc_per_second);

@@ -19,6 +19,25 @@ CAND_DTYPE = np.dtype([('x', '<i4'), ('y', '<i4'), ('response', '<i4')])
 assert KP_DTYPE.itemsize == 28 and CAND_DTYPE.itemsize == 12
 
 
+TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
+                              ('flags', '<i4')])
+LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
+assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24
+
+
+class Bounds(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ('minx', 'maxx', 'miny', 'maxy')]
+
+
+class FrameView(C.Structure):
+    _fields_ = [('n', C.c_int32), ('kps_un', C.c_void_p), ('desc', C.c_void_p), ('uright', C.c_void_p), ('bounds', Bounds),
+                ('nlevels', C.c_int32), ('scale_factors', C.c_void_p)]
+
+
+class Pose(C.Structure):
+    _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3)]
+
+
 class Camera(C.Structure):
     _fields_ = [(n, C.c_float) for n in ('fx', 'fy', 'cx', 'cy', 'bf', 'baseline')]
 
@@ -75,6 +94,13 @@ class Oracle:
         f('convert_to_gray', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t])
         f('stereo_from_rgbd', None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(Camera), C.c_void_p, C.c_void_p])
         f('distinctive_index', C.c_int, [C.c_void_p, C.c_int])
+        f('grid_create', C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(Bounds), C.c_int])
+        f('grid_destroy', None, [C.c_void_p])
+        f('grid_query', C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int])
+        f('search_local_map', C.c_int, [C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float])
+        f('search_last_frame', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.POINTER(Pose), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int])
+        f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
         f('cv_gaussian7', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t])
@@ -166,6 +192,63 @@ class Oracle:
         return int(self._distinctive_index(_p(desc), len(desc)))
 
     # ---- extractor ----
+    # ---- guided matchers. `frame` is a dict: kps_un, desc, uright (or None), bounds (4 floats), nlevels, scale_factors
+    @staticmethod
+    def _frame_view(frame):
+        keep = {
+            'kps': np.ascontiguousarray(frame['kps_un']).view(KP_DTYPE),
+            'desc': np.ascontiguousarray(frame['desc'], np.uint8),
+            'ur': None if frame.get('uright') is None else np.ascontiguousarray(frame['uright'], np.float32),
+            'sf': np.ascontiguousarray(frame['scale_factors'], np.float32),
+        }
+        v = FrameView(len(keep['kps']), keep['kps'].ctypes.data, keep['desc'].ctypes.data,
+                      None if keep['ur'] is None else keep['ur'].ctypes.data, Bounds(*[float(b) for b in frame['bounds']]),
+                      int(frame['nlevels']), keep['sf'].ctypes.data)
+        return v, keep
+
+    def grid_queries(self, frame, queries):
+        """queries: iterable of (x, y, r, min_level, max_level) -> list of index arrays in the reference's output order."""
+        kps = np.ascontiguousarray(frame['kps_un']).view(KP_DTYPE)
+        g = self._grid_create(_p(kps), len(kps), C.byref(Bounds(*[float(b) for b in frame['bounds']])), int(frame['nlevels']))
+        out, buf = [], np.empty(len(kps) + 1, np.int32)
+        for (x, y, r, lo, hi) in queries:
+            n = self._grid_query(g, float(x), float(y), float(r), int(lo), int(hi), _p(buf), len(buf))
+            out.append(buf[:n].copy())
+        self._grid_destroy(g)
+        return out
+
+    def search_local_map(self, frame, frame_mp, pts, pt_desc, th=3.0, nnratio=0.8):
+        v, keep = self._frame_view(frame)
+        mp = np.array(frame_mp, np.int32)
+        pts = np.ascontiguousarray(pts).view(TRACK_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        n = self._search_local_map(C.byref(v), _p(mp), _p(pts), _p(pt_desc), len(pts), th, nnratio)
+        return n, mp
+
+    def search_last_frame(self, frame, cam, cur_pose, last_pose, frame_mp, pts, pt_desc, th=15.0, monocular=False, nnratio=0.9,
+                          check_orientation=True):
+        v, keep = self._frame_view(frame)
+        mp = np.array(frame_mp, np.int32)
+        pts = np.ascontiguousarray(pts).view(LAST_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        poses = []
+        for R, t in (cur_pose, last_pose):
+            P = Pose()
+            P.R[:] = [float(x) for x in np.asarray(R, np.float32).reshape(9)]
+            P.t[:] = [float(x) for x in np.asarray(t, np.float32).reshape(3)]
+            poses.append(P)
+        n = self._search_last_frame(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(poses[0]), C.byref(poses[1]), _p(mp),
+                                    _p(pts), _p(pt_desc), len(pts), th, int(monocular), nnratio, int(check_orientation))
+        return n, mp
+
+    def search_for_initialization(self, f1, f2, prev_matched, window=100, nnratio=0.9, check_orientation=True):
+        v1, k1 = self._frame_view(f1)
+        v2, k2 = self._frame_view(f2)
+        prev = np.array(prev_matched, np.float32).reshape(-1, 2)
+        m12 = np.empty(v1.n, np.int32)
+        n = self._search_for_initialization(C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(window), nnratio, int(check_orientation))
+        return n, m12, prev
+
     def extractor(self, nfeatures=2000, scale=1.2, nlevels=8, ini=20, mn=7):
         return _Extractor(self, nfeatures, scale, nlevels, ini, mn)
 

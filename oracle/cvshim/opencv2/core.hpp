@@ -66,8 +66,60 @@ struct Rect
 };
 struct Range { int start, end; Range(int s, int e) : start(s), end(e) {} };
 
-template <class T, int M, int N> struct Matx { T val[M * N]; };
+// cv::Matx as far as the camera-pose headers use it (include/CameraPose.h, include/CameraProjection.h). The arithmetic follows
+// modules/core/include/opencv2/core/matx.hpp of the pinned OpenCV: a product accumulates s = 0; s += a(i,k)*b(k,j) for k ascending
+// in the element type, a sum is element-wise, unary minus scales by -1.
+template <class T, int M, int N> struct Matx
+{
+	T val[M * N];
+	Matx() { for (int i = 0; i < M * N; i++) val[i] = T(0); }
+	Matx(T v0, T v1, T v2) { static_assert(M * N == 3, "3 values"); val[0] = v0; val[1] = v1; val[2] = v2; }
+	Matx(T v0, T v1, T v2, T v3, T v4, T v5, T v6, T v7, T v8)
+	{
+		static_assert(M * N == 9, "9 values");
+		val[0] = v0; val[1] = v1; val[2] = v2; val[3] = v3; val[4] = v4; val[5] = v5; val[6] = v6; val[7] = v7; val[8] = v8;
+	}
+	static Matx zeros() { return Matx(); }
+	static Matx eye() { Matx m; for (int i = 0; i < (M < N ? M : N); i++) m.val[i * N + i] = T(1); return m; }
+	T& operator()(int i, int j) { return val[i * N + j]; }
+	const T& operator()(int i, int j) const { return val[i * N + j]; }
+	T& operator()(int i) { static_assert(M == 1 || N == 1, "vector"); return val[i]; }
+	const T& operator()(int i) const { static_assert(M == 1 || N == 1, "vector"); return val[i]; }
+	Matx<T, N, M> t() const { Matx<T, N, M> r; for (int i = 0; i < M; i++) for (int j = 0; j < N; j++) r.val[j * M + i] = val[i * N + j]; return r; }
+	T dot(const Matx& o) const { T s = 0; for (int i = 0; i < M * N; i++) s += val[i] * o.val[i]; return s; }
+};
+template <class T, int M, int L, int N> inline Matx<T, M, N> operator*(const Matx<T, M, L>& a, const Matx<T, L, N>& b)
+{
+	Matx<T, M, N> r;
+	for (int i = 0; i < M; i++)
+		for (int j = 0; j < N; j++)
+		{
+			T s = 0;
+			for (int k = 0; k < L; k++) s += a(i, k) * b(k, j);
+			r.val[i * N + j] = s;
+		}
+	return r;
+}
+template <class T, int M, int N> inline Matx<T, M, N> operator+(const Matx<T, M, N>& a, const Matx<T, M, N>& b)
+{
+	Matx<T, M, N> r;
+	for (int i = 0; i < M * N; i++) r.val[i] = a.val[i] + b.val[i];
+	return r;
+}
+template <class T, int M, int N> inline Matx<T, M, N> operator-(const Matx<T, M, N>& a, const Matx<T, M, N>& b)
+{
+	Matx<T, M, N> r;
+	for (int i = 0; i < M * N; i++) r.val[i] = a.val[i] - b.val[i];
+	return r;
+}
+template <class T, int M, int N> inline Matx<T, M, N> operator-(const Matx<T, M, N>& a)
+{
+	Matx<T, M, N> r;
+	for (int i = 0; i < M * N; i++) r.val[i] = a.val[i] * -1;
+	return r;
+}
 typedef Matx<float, 3, 1> Matx31f;
+typedef Matx<float, 3, 3> Matx33f;
 
 struct KeyPoint
 {
@@ -156,6 +208,14 @@ template <class T> class Mat_ : public Mat
 public:
 	Mat_() {}
 	Mat_(const Mat& m) : Mat(m) {}
+	Mat_(int r, int c) : Mat(r, c, sizeof(T) == 4 ? CV_32F : CV_8U) {}
+	static Mat_ eye(int r, int c)
+	{
+		Mat_ m(r, c);
+		m.setTo(0);
+		for (int i = 0; i < (r < c ? r : c); i++) m(i, i) = T(1);
+		return m;
+	}
 	T& operator()(int y, int x) { return this->template at<T>(y, x); }
 	const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
 };

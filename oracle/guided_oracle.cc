@@ -1,0 +1,374 @@
+// TEST INFRASTRUCTURE — CPU oracle, not the product.
+//
+// Stand-alone restatement of the guided matchers in the array / pass form the CUDA path uses, so that it is at the
+// same time the executable specification of orbx_guided.cu. Checked against the reference text itself (oracle/_ref, rule guided_gen.cc)
+// by tests/test_oracle_vs_ref.py; travels to machines without /root/reference.
+//
+//   FeaturesGrid::AssignFeatures / GetFeaturesInArea          src/Frame.cc:70-145
+//   CheckOrientation                                          src/ORBmatcher.cc:249-309
+//   ORBmatcher::SearchByProjection(Frame&, mappoints, th)     src/ORBmatcher.cc:315-382
+//   ORBmatcher::SearchForInitialization                       src/ORBmatcher.cc:614-694
+//   ORBmatcher::SearchByProjection(currFrame, lastFrame, ..)  src/ORBmatcher.cc:1279-1362
+//
+// The two SearchByProjection loops are sequential in the reference: a keypoint taken by an earlier map point with observations is
+// skipped by every later one. Here they are restated as a FIXPOINT: choice[i] = best candidate of point i among the keypoints not
+// taken by any point j < i; iterate from "nothing taken" until no choice changes. By induction on i the unique fixpoint is the
+// sequential result (choice[0] never depends on anyone; choice[i] only on choices of j < i), and the GPU runs exactly these rounds.
+#define ORACLE_PREFIX orc_
+#include "oracle_api.h"
+
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "stdsort_replay.h"
+
+namespace {
+
+int g_stat[2];   // [0] rounds of the last run_rounds, [1] matches revoked by the last search_for_initialization (test coverage only)
+
+const int COLS = 64, ROWS = 48;        // include/Frame.h:72-73
+const int TH_HIGH = 100, TH_LOW = 50;  // src/ORBmatcher.cc:41-42
+const int HISTO_LENGTH = 30;           // :43
+
+inline int hamming256(const uint8_t* a, const uint8_t* b)   // DescriptorDistance, :1449-1457
+{
+	int d = 0;
+	for (int i = 0; i < 8; i++)
+	{
+		uint32_t x, y;
+		memcpy(&x, a + 4 * i, 4);
+		memcpy(&y, b + 4 * i, 4);
+		d += __builtin_popcount(x ^ y);
+	}
+	return d;
+}
+
+// grid_[cx][cy] as one CSR array: cell = cx * ROWS + cy, items ascending (the push_back order of :87-99)
+struct Grid
+{
+	std::vector<oracle_keypoint> kps;
+	oracle_bounds b;
+	int nlevels;
+	float invW, invH;
+	std::vector<int> start, items;
+
+	void assign(const oracle_keypoint* k, int n, const oracle_bounds& bounds, int nl)
+	{
+		kps.assign(k, k + n);
+		b = bounds;
+		nlevels = nl;
+		invW = COLS / (b.maxx - b.minx);   // :73-74, int / float
+		invH = ROWS / (b.maxy - b.miny);
+		std::vector<int> cell((size_t)n);
+		start.assign(COLS * ROWS + 1, 0);
+		for (int i = 0; i < n; i++)
+		{
+			const int cx = (int)std::round(invW * (k[i].x - b.minx));   // :91-92, half away from zero
+			const int cy = (int)std::round(invH * (k[i].y - b.miny));
+			cell[i] = (cx < 0 || cx >= COLS || cy < 0 || cy >= ROWS) ? -1 : cx * ROWS + cy;
+			if (cell[i] >= 0) start[cell[i] + 1]++;
+		}
+		for (int c = 0; c < COLS * ROWS; c++) start[c + 1] += start[c];
+		items.assign((size_t)start[COLS * ROWS], 0);
+		std::vector<int> fill(start.begin(), start.end() - 1);
+		for (int i = 0; i < n; i++)
+			if (cell[i] >= 0) items[fill[cell[i]]++] = i;
+	}
+
+	// GetFeaturesInArea (:102-145): calls f(idx) in the reference's output order
+	template <class F> void query(float x, float y, float r, int minLevel, int maxLevel, F f) const
+	{
+		const int mincx = std::max((int)std::floor(invW * (x - r - b.minx)), 0);
+		const int maxcx = std::min((int)std::ceil(invW * (x + r - b.minx)), COLS - 1);
+		const int mincy = std::max((int)std::floor(invH * (y - r - b.miny)), 0);
+		const int maxcy = std::min((int)std::ceil(invH * (y + r - b.miny)), ROWS - 1);
+		if (mincx >= COLS || maxcx < 0 || mincy >= ROWS || maxcy < 0) return;
+		const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+		if (maxLevel < 0) maxLevel = nlevels;
+		for (int cx = mincx; cx <= maxcx; cx++)
+			for (int cy = mincy; cy <= maxcy; cy++)
+				for (int p = start[cx * ROWS + cy]; p < start[cx * ROWS + cy + 1]; p++)
+				{
+					const int idx = items[p];
+					const oracle_keypoint& kp = kps[idx];
+					if (checkLevels && (kp.octave < minLevel || kp.octave > maxLevel)) continue;
+					if (std::fabs(kp.x - x) < r && std::fabs(kp.y - y) < r) f(idx);
+				}
+	}
+};
+
+Grid make_grid(const oracle_frame_view* v)
+{
+	Grid g;
+	g.assign(v->kps_un, v->n, v->bounds, v->nlevels);
+	return g;
+}
+
+// CheckOrientation (:249-309). matches are (index into angle1, index into angle2 == index into status), in push order.
+// erased[k] is set for every match whose status entry the reference invalidates; returns matches - reduction.
+int check_orientation(const std::vector<std::pair<int, int>>& matches, const float* angle1, size_t stride1, const float* angle2, size_t stride2,
+                      std::vector<int>& erased_i2)
+{
+	const float factor = 1.f / HISTO_LENGTH;
+	std::vector<int> hist[HISTO_LENGTH];
+	for (const auto& m : matches)
+	{
+		float diff = *(const float*)((const char*)angle1 + stride1 * m.first) - *(const float*)((const char*)angle2 + stride2 * m.second);
+		if (diff < 0) diff += 360;
+		int bin = (int)lrintf(factor * diff);   // cvRound(float)
+		if (bin == HISTO_LENGTH) bin = 0;
+		hist[bin].push_back(m.second);
+	}
+	// std::sort of the 30 bins by size, descending: unstable, so replayed (stdsort_replay.h)
+	std::vector<stdsort::SortItem> order(HISTO_LENGTH);
+	for (int i = 0; i < HISTO_LENGTH; i++) order[i] = { (int)hist[i].size(), i };
+	stdsort::libstdcxx_sort_desc(order);
+	const size_t max1 = (size_t)order[0].size, max2 = (size_t)order[1].size, max3 = (size_t)order[2].size;
+	int eraseBin = 3;
+	if (max2 < 0.1 * max1) eraseBin = 1;
+	else if (max3 < 0.1 * max1) eraseBin = 2;
+	int reduction = 0;
+	erased_i2.clear();
+	for (int b = eraseBin; b < HISTO_LENGTH; b++)
+		for (int i2 : hist[order[b].node])
+		{
+			erased_i2.push_back(i2);
+			reduction++;
+		}
+	return (int)matches.size() - reduction;
+}
+
+// what one point asks of the frame: a window, a level range, the right-image coordinate, its descriptor
+struct Probe
+{
+	bool active;
+	float u, v, ur, radius;
+	int minLevel, maxLevel;
+	bool obs;              // Observations() > 0: the keypoint it takes is closed to later points
+};
+
+struct Pick { int idx, best, second, bestLevel, secondLevel; };
+
+// best / second scan of :337-367 (and, ignoring the second-best fields, of :1327-1347) over the window of one probe.
+// `taken(idx)` is the only state-dependent test.
+template <class Taken> Pick scan_window(const Grid& g, const oracle_frame_view* f, const Probe& p, const uint8_t* desc, Taken taken)
+{
+	Pick k = { -1, 256, 256, -1, -1 };
+	g.query(p.u, p.v, p.radius, p.minLevel, p.maxLevel, [&](int idx) {
+		if (taken(idx)) return;
+		const float ur2 = f->uright ? f->uright[idx] : -1.f;
+		if (ur2 > 0 && std::fabs(p.ur - ur2) > p.radius) return;
+		const int d = hamming256(desc, f->desc + (size_t)idx * 32);
+		if (d < k.best)
+		{
+			k.second = k.best; k.best = d;
+			k.secondLevel = k.bestLevel; k.bestLevel = g.kps[idx].octave;
+			k.idx = idx;
+		}
+		else if (d < k.second)
+		{
+			k.secondLevel = g.kps[idx].octave;
+			k.second = d;
+		}
+	});
+	return k;
+}
+
+// The fixpoint described in the header. accept(pick) says whether point i takes pick.idx. On return choice[i] is the keypoint taken
+// by point i (or -1) and frame_mp is updated to the reference's final frame.mappoints.
+template <class Accept>
+int run_rounds(const Grid& g, const oracle_frame_view* f, const std::vector<Probe>& probes, const uint8_t* pt_desc, int32_t* frame_mp,
+               std::vector<int>& choice, Accept accept)
+{
+	const int np = (int)probes.size(), n = f->n;
+	choice.assign((size_t)np, -1);
+	// keypoints closed from the start: frame.mappoints[idx] && frame.mappoints[idx]->Observations() > 0 on entry
+	std::vector<char> closed((size_t)n);
+	for (int c = 0; c < n; c++) closed[c] = frame_mp[c] == -2 || (frame_mp[c] >= 0 && probes[(size_t)frame_mp[c]].obs);
+	std::vector<int> owner((size_t)n);   // lowest point index with observations that takes the keypoint; INT_MAX = nobody
+	for (int round = 0;; round++)
+	{
+		for (int c = 0; c < n; c++) owner[c] = INT_MAX;
+		for (int i = 0; i < np; i++)
+			if (choice[i] >= 0 && probes[i].obs && i < owner[choice[i]]) owner[choice[i]] = i;
+		bool changed = false;
+		for (int i = 0; i < np; i++)
+		{
+			if (!probes[i].active) continue;
+			const Pick k = scan_window(g, f, probes[i], pt_desc + (size_t)i * 32,
+			                           [&](int idx) { return closed[idx] || owner[idx] < i; });
+			const int c = accept(k) ? k.idx : -1;
+			if (c != choice[i]) { choice[i] = c; changed = true; }
+		}
+		g_stat[0] = round + 1;
+		if (!changed) break;
+	}
+	int nmatches = 0;
+	for (int i = 0; i < np; i++)
+		if (choice[i] >= 0) { frame_mp[choice[i]] = i; nmatches++; }   // ascending i: the last writer wins, as in the reference loop
+	return nmatches;
+}
+
+}  // namespace
+
+extern "C" {
+
+// port only: coverage counters of the last call (see g_stat)
+int orc_guided_stat(int which) { return g_stat[which & 1]; }
+
+void* orc_grid_create(const oracle_keypoint* kps, int n, const oracle_bounds* b, int nlevels)
+{
+	Grid* g = new Grid;
+	g->assign(kps, n, *b, nlevels);
+	return g;
+}
+
+void orc_grid_destroy(void* g) { delete static_cast<Grid*>(g); }
+
+int orc_grid_query(void* g, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap)
+{
+	int n = 0;
+	static_cast<Grid*>(g)->query(x, y, r, min_level, max_level, [&](int idx) { if (n < cap) out[n] = idx; n++; });
+	return n;
+}
+
+int orc_search_local_map(const oracle_frame_view* f, int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc, int npts, float th,
+                         float nnratio)
+{
+	const Grid g = make_grid(f);
+	std::vector<Probe> probes((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		Probe& p = probes[i];
+		p.active = (pts[i].flags & 1) != 0;
+		p.obs = (pts[i].flags & 2) != 0;
+		if (!p.active) continue;
+		const int ps = pts[i].scale_level;
+		const float r = pts[i].view_cos > 0.998 ? 2.5f : 4.f;   // RadiusByViewingCos (:53): float against a double literal
+		p.radius = th * r * f->scale_factors[ps];             // :326-327
+		p.u = pts[i].proj_x; p.v = pts[i].proj_y; p.ur = pts[i].proj_xr;
+		p.minLevel = ps - 1; p.maxLevel = ps;                   // :332
+	}
+	std::vector<int> choice;
+	return run_rounds(g, f, probes, pt_desc, frame_mp, choice, [&](const Pick& k) {
+		if (!(k.best <= TH_HIGH)) return false;                                               // :370
+		if (k.bestLevel == k.secondLevel && k.best > nnratio * k.second) return false;        // :372-373
+		return true;
+	});
+}
+
+int orc_search_last_frame(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* cp, const oracle_pose* lp, int32_t* frame_mp,
+                          const oracle_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular, float nnratio,
+                          int check_ori)
+{
+	(void)nnratio;
+	const Grid g = make_grid(f);
+	// tlc = Rlw * (-Rcw^T * tcw) + tlw (:1286); every product accumulates from 0 in k order like cv::Matx
+	float twc[3], tlc[3];
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0;
+		for (int k = 0; k < 3; k++) s += (cp->R[k * 3 + i] * -1) * cp->t[k];
+		twc[i] = s;
+	}
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0;
+		for (int k = 0; k < 3; k++) s += lp->R[i * 3 + k] * twc[k];
+		tlc[i] = s + lp->t[i];
+	}
+	const bool forward = tlc[2] > cam->baseline && !monocular;    // :1287-1288
+	const bool backward = -tlc[2] > cam->baseline && !monocular;
+
+	std::vector<Probe> probes((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		Probe& p = probes[i];
+		p.active = false;
+		p.obs = (pts[i].flags & 2) != 0;
+		if (!(pts[i].flags & 1)) continue;                         // :1296-1297
+		float xc[3];
+		for (int r = 0; r < 3; r++)
+		{
+			float s = 0;
+			for (int k = 0; k < 3; k++) s += cp->R[r * 3 + k] * pts[i].xw[k];
+			xc[r] = s + cp->t[r];
+		}
+		if (xc[2] < 0.f) continue;                                 // :1302-1303
+		const float invZ = 1.f / xc[2];                            // CameraProjection::CameraToImage
+		p.u = invZ * cam->fx * xc[0] + cam->cx;
+		p.v = invZ * cam->fy * xc[1] + cam->cy;
+		p.ur = p.u - cam->bf / xc[2];                              // :1308
+		if (!(p.u >= f->bounds.minx && p.u < f->bounds.maxx && p.v >= f->bounds.miny && p.v < f->bounds.maxy)) continue;   // :1310
+		const int oct = pts[i].octave;
+		p.radius = th * f->scale_factors[oct];                     // :1316
+		p.minLevel = forward ? oct : (backward ? 0 : oct - 1);     // :1318-1319
+		p.maxLevel = forward ? -1 : (backward ? oct : oct + 1);
+		p.active = true;
+	}
+	std::vector<int> choice;
+	const int nmatches = run_rounds(g, f, probes, pt_desc, frame_mp, choice, [&](const Pick& k) { return k.best <= TH_HIGH; });
+	if (!check_ori) return nmatches;
+	std::vector<std::pair<int, int>> matches;
+	for (int i = 0; i < npts; i++)
+		if (choice[i] >= 0) matches.push_back({ i, choice[i] });
+	std::vector<int> erased;
+	const int kept = check_orientation(matches, &pts[0].angle, sizeof(oracle_last_point), &f->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+	for (int i2 : erased) frame_mp[i2] = -1;
+	return kept;
+}
+
+int orc_search_for_initialization(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev, int32_t* matches12, int window,
+                                  float nnratio, int check_ori)
+{
+	const Grid g2 = make_grid(f2);
+	int nmatches = 0;
+	g_stat[1] = 0;
+	for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+	std::vector<int> matchedDistance((size_t)f2->n, INT_MAX), matches21((size_t)f2->n, -1);
+	std::vector<std::pair<int, int>> matchIds;
+	const float radius = (float)window;
+	for (int i1 = 0; i1 < f1->n; i1++)
+	{
+		if (f1->kps_un[i1].octave > 0) continue;                    // :629-631
+		int best = INT_MAX, second = INT_MAX, bestIdx = -1;
+		g2.query(prev[2 * i1], prev[2 * i1 + 1], radius, 0, 0, [&](int i2) {
+			const int d = hamming256(f1->desc + (size_t)i1 * 32, f2->desc + (size_t)i2 * 32);
+			if (matchedDistance[i2] <= d) return;                    // :651-652
+			if (d < best) { second = best; best = d; bestIdx = i2; }
+			else if (d < second) second = d;
+		});
+		if (bestIdx < 0) continue;
+		if (best <= TH_LOW && best < second * nnratio)              // :666
+		{
+			if (matches21[bestIdx] >= 0)
+			{
+				matches12[matches21[bestIdx]] = -1;
+				nmatches--;
+				g_stat[1]++;
+			}
+			matches12[i1] = bestIdx;
+			matches21[bestIdx] = i1;
+			matchedDistance[bestIdx] = best;
+			nmatches++;
+			if (check_ori) matchIds.push_back({ bestIdx, i1 });
+		}
+	}
+	if (check_ori)
+	{
+		std::vector<int> erased;
+		nmatches = check_orientation(matchIds, &f2->kps_un[0].angle, sizeof(oracle_keypoint), &f1->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+		for (int i1 : erased) matches12[i1] = -1;
+	}
+	for (int i1 = 0; i1 < f1->n; i1++)
+		if (matches12[i1] >= 0)
+		{
+			prev[2 * i1] = f2->kps_un[matches12[i1]].x;
+			prev[2 * i1 + 1] = f2->kps_un[matches12[i1]].y;
+		}
+	return nmatches;
+}
+
+}  // extern "C"

@@ -94,6 +94,44 @@ void ORACLE_FN(stereo_from_rgbd)(const oracle_keypoint* kps, const oracle_keypoi
 // descriptor with the least median distance to the others, first wins ties
 int ORACLE_FN(distinctive_index)(const uint8_t* desc, int n);
 
+// ---- guided matchers, SURVEY §8(f) #1 ----
+typedef struct oracle_bounds { float minx, maxx, miny, maxy; } oracle_bounds;
+// a Frame as the guided matchers see it (include/Frame.h:83-168): undistorted keypoints, descriptors, right coordinates (NULL = all -1),
+// image bounds, pyramid scale factors
+typedef struct oracle_frame_view
+{
+	int32_t n;
+	const oracle_keypoint* kps_un;
+	const uint8_t* desc;
+	const float* uright;
+	oracle_bounds bounds;
+	int32_t nlevels;
+	const float* scale_factors;
+} oracle_frame_view;
+typedef struct oracle_pose { float R[9]; float t[3]; } oracle_pose;   // CameraPose (include/CameraPose.h), R row-major
+// one candidate map point of SearchByProjection(Frame&, mappoints, th): the track* scratch (include/MapPoint.h:92-97);
+// flags bit0 = trackInView && !isBad(), bit1 = Observations() > 0
+typedef struct oracle_track_point { float proj_x, proj_y, proj_xr, view_cos; int32_t scale_level; int32_t flags; } oracle_track_point;
+// one keypoint of the last frame for SearchByProjection(currFrame, lastFrame, ...): world position of its map point, octave of
+// lastFrame.keypoints[i], angle of lastFrame.keypointsUn[i]; flags bit0 = has a map point && !outlier, bit1 = Observations() > 0
+typedef struct oracle_last_point { float xw[3]; int32_t octave; float angle; int32_t flags; } oracle_last_point;
+
+// FeaturesGrid (src/Frame.cc:65-145)
+void* ORACLE_FN(grid_create)(const oracle_keypoint* kps, int n, const oracle_bounds* bounds, int nlevels);
+void ORACLE_FN(grid_destroy)(void* grid);
+// GetFeaturesInArea; returns the count (indices beyond cap are dropped)
+int ORACLE_FN(grid_query)(void* grid, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+// The three matchers. frame_mp (n entries, in/out) is frame.mappoints: -1 = null, >= 0 = index of a point of `pts`, -2 = some other
+// map point with Observations() > 0, -3 = some other map point without observations. All return nmatches.
+int ORACLE_FN(search_local_map)(const oracle_frame_view* frame, int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc,
+                                int npts, float th, float nnratio);
+int ORACLE_FN(search_last_frame)(const oracle_frame_view* cur, const oracle_camera* cam, const oracle_pose* cur_pose,
+                                 const oracle_pose* last_pose, int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc,
+                                 int npts, float th, int monocular, float nnratio, int check_orientation);
+// prev_matched: n1 x 2 floats in/out; matches12: n1 out
+int ORACLE_FN(search_for_initialization)(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev_matched, int32_t* matches12,
+                                         int window, float nnratio, int check_orientation);
+
 // ---- pinned third-party primitives (same code in both libraries; checked against cv2 4.13.0) ----
 void ORACLE_FN(cv_resize)(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
 int ORACLE_FN(cv_fast)(const uint8_t* img, int w, int h, size_t step, int th, int nms, oracle_cand* out, int cap);

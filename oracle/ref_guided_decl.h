@@ -1,0 +1,77 @@
+// TEST INFRASTRUCTURE — CPU oracle, not the product.
+//
+// Stand-ins for the object graph the guided matchers walk, so that the reference text of
+//   src/Frame.cc:32-34, 39-59, 63-145          (Round*, ImageBounds, FeaturesGrid)
+//   include/Frame.h:40-81                      (ImageBounds, ScalePyramidInfo, FeaturesGrid declarations)
+//   src/ORBmatcher.cc:37-58, 249-309           (constants, CheckOrientation)
+//   src/ORBmatcher.cc:315-382                  SearchByProjection(Frame&, mappoints, th)       — local-map tracking
+//   src/ORBmatcher.cc:614-694                  SearchForInitialization                          — monocular initialisation
+//   src/ORBmatcher.cc:1279-1362                SearchByProjection(currFrame, lastFrame, th, m)  — motion-model tracking
+// compiles by line range (oracle/Makefile, rule guided_gen.cc) with the reference's own include/Point.h,
+// include/CameraParameters.h, include/CameraPose.h and include/CameraProjection.h. The real Frame/MapPoint/KeyFrame drag
+// in DBoW2, the vocabulary and the map; only the members those three functions touch exist here, under the same names
+// (include/Frame.h:83-168, include/MapPoint.h:49-97).
+//
+// This header is included INSIDE namespace ORB_SLAM2 of the generated TU, after the Frame.h declarations.
+#pragma once
+
+struct MapPoint
+{
+	// tracking scratch (include/MapPoint.h:92-97)
+	float trackProjX = 0.f, trackProjY = 0.f, trackProjXR = 0.f;
+	bool trackInView = false;
+	int trackScaleLevel = 0;
+	float trackViewCos = 0.f;
+
+	// what the accessors return (include/MapPoint.h:49,55,64,75)
+	Point3D worldPos;
+	int nobs = 0;
+	bool bad = false;
+	cv::Mat descriptor;     // 1 x 32 CV_8U row header
+
+	Point3D GetWorldPos() const { return worldPos; }
+	int Observations() const { return nobs; }
+	bool isBad() const { return bad; }
+	cv::Mat GetDescriptor() const { return descriptor; }
+};
+
+class KeyFrame;
+class Sim3;
+
+struct Frame
+{
+	CameraParams camera;
+	int N = 0;
+	KeyPoints keypoints;
+	KeyPoints keypointsUn;
+	std::vector<float> uright;
+	cv::Mat descriptors;
+	std::vector<MapPoint*> mappoints;
+	std::vector<bool> outlier;
+	FeaturesGrid grid;
+	CameraPose pose;
+	ScalePyramidInfo pyramid;
+	ImageBounds imageBounds;
+
+	// src/Frame.cc:216-219
+	std::vector<size_t> GetFeaturesInArea(float x, float y, float r, int minLevel = -1, int maxLevel = -1) const
+	{
+		return grid.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+	}
+};
+
+// include/ORBmatcher.h:47-104, the members compiled here
+class ORBmatcher
+{
+public:
+	ORBmatcher(float nnratio = 0.6, bool checkOri = true) : fNNRatio_(nnratio), checkOrientation_(checkOri) {}
+	static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+	int SearchByProjection(Frame& frame, const std::vector<MapPoint*>& mappoints, float th = 3);
+	int SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular);
+	int SearchForInitialization(Frame& frame1, Frame& frame2, std::vector<cv::Point2f>& prevMatched, std::vector<int>& matches12,
+		int windowSize = 10);
+
+private:
+	float fNNRatio_;
+	bool checkOrientation_;
+};

@@ -41,6 +41,25 @@ class _Camera(C.Structure):
     _fields_ = [(n, C.c_float) for n in ('fx', 'fy', 'cx', 'cy', 'bf', 'baseline')]
 
 
+class _Bounds(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ('minx', 'maxx', 'miny', 'maxy')]
+
+
+class _FrameView(C.Structure):
+    _fields_ = [('n', C.c_int32), ('kps_un', C.c_void_p), ('desc', C.c_void_p), ('uright', C.c_void_p), ('bounds', _Bounds),
+                ('nlevels', C.c_int32), ('scale_factors', C.c_void_p)]
+
+
+class _Pose(C.Structure):
+    _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3)]
+
+
+TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
+                              ('flags', '<i4')])
+LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
+assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24
+GRID_COLS, GRID_ROWS = 64, 48   # include/Frame.h:72-73
+
 _lib = None
 
 _SIGNATURES = {
@@ -87,6 +106,17 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p]),
     'orbx_distinctive_descriptors': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_measure_popc_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    'orbx_frame_create': (C.c_int, [C.POINTER(_FrameView), C.c_int, C.POINTER(C.c_void_p)]),
+    'orbx_frame_destroy': (C.c_int, [C.c_void_p]),
+    'orbx_frame_grid': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_frame_features_in_area': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    'orbx_search_by_projection_local_map': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                                      C.POINTER(C.c_int)]),
+    'orbx_search_by_projection_last_frame': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose), C.POINTER(_Pose), C.c_void_p,
+                                                       C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_search_for_initialization': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                                 C.POINTER(C.c_int)]),
+    'orbx_frame_last_rounds': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
 }
 
 
@@ -319,13 +349,114 @@ def ComputeStereoMatchesResident(extractorL, extractorR, camera):
     return ur, dp
 
 
+class Frame:
+    """What the guided matchers need of ORB_SLAM2::Frame (include/Frame.h:83-168), resident on one GPU: keypointsUn, descriptors,
+    uright, imageBounds, the pyramid's scale factors and the FeaturesGrid (built on the device at construction, src/Frame.cc:70-100).
+    `mappoints` mirrors frame.mappoints as codes: -1 null, >= 0 index into the point list of the last search, -2 / -3 some other map
+    point with / without observations."""
+
+    def __init__(self, keypointsUn, descriptors, scaleFactors, imageBounds, uright=None, device=0):
+        self.keypointsUn = np.ascontiguousarray(keypointsUn).view(KP_DTYPE)
+        self.descriptors = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        self.scaleFactors = np.ascontiguousarray(scaleFactors, np.float32)
+        self.imageBounds = tuple(float(np.float32(b)) for b in imageBounds)     # (minx, maxx, miny, maxy)
+        self.N = len(self.keypointsUn)
+        self.mappoints = np.full(self.N, -1, np.int32)
+        view = _FrameView(self.N, self.keypointsUn.ctypes.data, self.descriptors.ctypes.data,
+                          None if self.uright is None else self.uright.ctypes.data, _Bounds(*self.imageBounds), len(self.scaleFactors),
+                          self.scaleFactors.ctypes.data)
+        h = C.c_void_p()
+        _check(lib().orbx_frame_create(C.byref(view), device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and _lib is not None:
+            _lib.orbx_frame_destroy(h)
+            self._h = None
+
+    def grid(self):
+        """(cell_start[64*48+1], items): grid_[cx][cy] is items[cell_start[cx*48+cy] : cell_start[cx*48+cy+1]]."""
+        start = np.empty(GRID_COLS * GRID_ROWS + 1, np.int32)
+        items = np.empty(max(self.N, 1), np.int32)
+        n = C.c_int()
+        _check(lib().orbx_frame_grid(self._h, _p(start), _p(items), len(items), C.byref(n)))
+        return start, items[:n.value].copy()
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        return self.GetFeaturesInAreaBatch([(x, y, r, minLevel, maxLevel)])[0]
+
+    def GetFeaturesInAreaBatch(self, queries):
+        """queries: (x, y, r, minLevel, maxLevel) rows -> list of index arrays in the reference's output order (src/Frame.cc:102-145)."""
+        q = np.asarray(queries, np.float64).reshape(-1, 5)
+        xyr = np.ascontiguousarray(q[:, :3], np.float32)
+        lv = np.ascontiguousarray(q[:, 3:], np.int32)
+        off = np.empty(len(q) + 1, np.int32)
+        idx = np.empty(max(self.N * 4, 1024), np.int32)
+        st = lib().orbx_frame_features_in_area(self._h, _p(xyr), _p(lv), len(q), _p(off), _p(idx), len(idx))
+        if st == ORBX_ERR_CAPACITY:
+            idx = np.empty(int(off[-1]), np.int32)
+            st = lib().orbx_frame_features_in_area(self._h, _p(xyr), _p(lv), len(q), _p(off), _p(idx), len(idx))
+        _check(st)
+        return [idx[off[i]:off[i + 1]].copy() for i in range(len(q))]
+
+    def last_rounds(self):
+        n = C.c_int()
+        _check(lib().orbx_frame_last_rounds(self._h, C.byref(n)))
+        return n.value
+
+
+def _pose(p):
+    R, t = p
+    P = _Pose()
+    P.R[:] = [float(x) for x in np.asarray(R, np.float32).reshape(9)]
+    P.t[:] = [float(x) for x in np.asarray(t, np.float32).reshape(3)]
+    return P
+
+
 class ORBmatcher:
-    """The Hamming pieces of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:47-103) that are on the hot path."""
+    """The pieces of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:47-103) that are on the hot path: the Hamming kernels and the guided
+    window searches of Tracking."""
 
     def __init__(self, nnratio=0.6, checkOri=True, device=0):
         self.fNNRatio_ = nnratio
         self.checkOrientation_ = checkOri
         self.device = device
+
+    def SearchByProjection(self, frame, mappoints, descriptors, th=3.0):
+        """SearchByProjection(Frame&, const std::vector<MapPoint*>&, float th) — src/ORBmatcher.cc:315-382. mappoints: TRACK_POINT_DTYPE
+        records (the track* members of each MapPoint), descriptors: their GetDescriptor() rows. Updates frame.mappoints; returns nmatches."""
+        pts = np.ascontiguousarray(mappoints).view(TRACK_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        n = C.c_int()
+        _check(lib().orbx_search_by_projection_local_map(frame._h, _p(frame.mappoints), _p(pts), _p(desc), len(pts), th, self.fNNRatio_,
+                                                         C.byref(n)))
+        return n.value
+
+    def SearchByProjectionLastFrame(self, currFrame, camera, currPose, lastPose, lastPoints, descriptors, th, monocular):
+        """SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular) — src/ORBmatcher.cc:1279-1362.
+        lastPoints: LAST_POINT_DTYPE records, one per keypoint of the last frame; poses are (R 3x3, t 3) of CameraPose."""
+        pts = np.ascontiguousarray(lastPoints).view(LAST_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        n = C.c_int()
+        cam = _Camera(*[float(c) for c in camera])
+        cp, lp = _pose(currPose), _pose(lastPose)
+        _check(lib().orbx_search_by_projection_last_frame(currFrame._h, C.byref(cam), C.byref(cp), C.byref(lp), _p(currFrame.mappoints),
+                                                          _p(pts), _p(desc), len(pts), th, int(bool(monocular)),
+                                                          int(bool(self.checkOrientation_)), C.byref(n)))
+        return n.value
+
+    def SearchForInitialization(self, frame1, frame2, prevMatched, windowSize=10):
+        """src/ORBmatcher.cc:614-694. prevMatched: (N1, 2) float32, updated in place; returns (nmatches, matches12)."""
+        prev = np.ascontiguousarray(prevMatched, np.float32).reshape(-1, 2)
+        m12 = np.empty(max(frame1.N, 1), np.int32)
+        n = C.c_int()
+        _check(lib().orbx_search_for_initialization(frame1._h, frame2._h, _p(prev), _p(m12), int(windowSize), self.fNNRatio_,
+                                                    int(bool(self.checkOrientation_)), C.byref(n)))
+        if prev is not prevMatched:
+            np.copyto(np.asarray(prevMatched).reshape(-1, 2), prev, casting='unsafe')
+        return n.value, m12[:frame1.N]
 
     @staticmethod
     def DescriptorDistance(a, b, device=0):

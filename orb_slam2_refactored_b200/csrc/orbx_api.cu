@@ -70,6 +70,15 @@ bool device_ok(int device, std::string& why)
 
 }  // namespace
 
+orbx_status orbx_fail(orbx_status s, const char* msg) { return fail(s, msg); }
+bool orbx_device_usable(int device, const char** why)
+{
+	static thread_local std::string text;
+	const bool ok = device_ok(device, text);
+	*why = text.c_str();
+	return ok;
+}
+
 struct orbx_extractor
 {
 	orbx_params prm;

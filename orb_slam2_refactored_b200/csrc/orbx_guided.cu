@@ -1,0 +1,866 @@
+// Guided matchers on sm_100a: FeaturesGrid and the window searches of Tracking, bit-exact against the reference's
+// sequential loops.
+//
+//   FeaturesGrid::AssignFeatures / GetFeaturesInArea            src/Frame.cc:70-145            k_grid_build, k_features_in_area
+//   ORBmatcher::SearchByProjection(Frame&, mappoints, th)       src/ORBmatcher.cc:315-382      k_guided_search, mode LOCAL_MAP
+//   ORBmatcher::SearchByProjection(currFrame, lastFrame, ...)   src/ORBmatcher.cc:1279-1362    k_guided_search, mode LAST_FRAME
+//   ORBmatcher::SearchForInitialization                         src/ORBmatcher.cc:614-694      k_guided_search, mode INITIALIZATION
+//   CheckOrientation                                            src/ORBmatcher.cc:249-309      inside k_guided_search
+//
+// The reference loops are sequential: a map point skips keypoints that an EARLIER map point (with observations) has taken, and
+// SearchForInitialization skips a keypoint that an earlier one matched at a smaller-or-equal distance. Both are restated as a
+// fixpoint over rounds (oracle/guided_oracle.cc carries the argument): every point recomputes its choice against the claims of the
+// lower-numbered points of the previous round until nothing changes; the unique fixpoint is the sequential result. Everything that
+// does not depend on that state — window enumeration in the reference's output order, the uright gate, all Hamming distances — is done
+// once, in parallel, into a per-point candidate list; a round only re-scans those short lists.
+//
+// One CTA per search (a frame holds 1-8 k keypoints: the work is latency-, not bandwidth-bound); phases are separated by block barriers.
+#include "orbx_internal.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "orbx_sort.cuh"
+
+namespace {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;   // include/Frame.h:72-73
+constexpr int G_THREADS = 1024;
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;                        // src/ORBmatcher.cc:41-43
+constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2;
+
+// candidate entry: keypoint index [0:19) | octave [19:23) | distance [23:32) (511 = removed by the uright gate)
+constexpr int E_IDX_BITS = 19, E_LVL_BITS = 4;
+constexpr uint32_t E_IDX_MASK = (1u << E_IDX_BITS) - 1, E_SKIP = 511;
+
+struct GridDev
+{
+	int n, nlevels;
+	orbx_bounds b;
+	float invW, invH;
+	const int* cell_start;   // [GRID_CELLS + 1]
+	const int4* rec;         // per grid item, cell-major: x bits, y bits, keypoint index, octave
+};
+
+struct GuidedArgs
+{
+	GridDev G;
+	const orbx_keypoint* kps2;   // keypointsUn of the searched frame
+	const uint8_t* desc2;
+	const float* uright2;
+	float sf[16];
+	int mode, npts;
+	const orbx_track_point* tp;
+	const orbx_last_point* lp;
+	const orbx_keypoint* kps1;   // INIT: frame 1
+	float* prev;                 // INIT: prevMatched, in/out
+	const uint8_t* pt_desc;
+	float th, nnratio, radius;
+	float fx, fy, cx, cy, bf;
+	float R[9], t[3];
+	int forward, backward, check_ori;
+	// scratch, per point
+	float* pu; float* pv; float* pur; float* prad;
+	int* plevels;                // minLevel | maxLevel << 16 (as int16), -32768 in the low half = inactive
+	int* off;                    // [npts + 1]
+	int* choice;                 // keypoint taken by the point
+	int* aux0; int* aux1;        // INIT: best distance of the accepted match, ping-pong; LAST_FRAME: histogram bin of the match
+	int* next;                   // INIT: claim lists
+	// scratch, per keypoint of the searched frame
+	int* owner;
+	// candidate lists
+	uint32_t* list; int* entry_pt; int cap;
+	int32_t* frame_mp;           // in/out (LOCAL_MAP, LAST_FRAME); INIT: matches12 out [npts]
+	int* result;                 // [0] nmatches, [1] entries, [2] rounds, [3] overflow
+};
+
+__device__ __forceinline__ int hamming256(const uint8_t* a, const uint8_t* b)
+{
+	const uint4 a0 = *reinterpret_cast<const uint4*>(a), a1 = *reinterpret_cast<const uint4*>(a + 16);
+	const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *reinterpret_cast<const uint4*>(b + 16);
+	return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+	       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// GetFeaturesInArea (src/Frame.cc:102-145): f(index, octave) for every hit, in the reference's output order. A column of cells
+// (fixed cx, cy ascending) is one contiguous run of the cell-major record array.
+template <class F>
+__device__ __forceinline__ void for_window(const GridDev& G, float x, float y, float r, int minLevel, int maxLevel, F f)
+{
+	const int mincx = max(__float2int_rd(G.invW * (x - r - G.b.minx)), 0);
+	const int maxcx = min(__float2int_ru(G.invW * (x + r - G.b.minx)), GRID_COLS - 1);
+	const int mincy = max(__float2int_rd(G.invH * (y - r - G.b.miny)), 0);
+	const int maxcy = min(__float2int_ru(G.invH * (y + r - G.b.miny)), GRID_ROWS - 1);
+	if (mincx >= GRID_COLS || maxcx < 0 || mincy >= GRID_ROWS || maxcy < 0) return;
+	const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+	if (maxLevel < 0) maxLevel = G.nlevels;
+	for (int cx = mincx; cx <= maxcx; cx++)
+	{
+		const int a = G.cell_start[cx * GRID_ROWS + mincy], b = G.cell_start[cx * GRID_ROWS + maxcy + 1];
+		for (int p = a; p < b; p++)
+		{
+			const int4 rec = G.rec[p];
+			if (checkLevels && (rec.w < minLevel || rec.w > maxLevel)) continue;
+			if (fabsf(__int_as_float(rec.x) - x) < r && fabsf(__int_as_float(rec.y) - y) < r) f(rec.z, rec.w);
+		}
+	}
+}
+
+// exclusive scan of a[0..m) in place by the whole CTA; returns the total. s_w: G_THREADS/32 + 1 ints of shared memory.
+__device__ int block_exscan_inplace(int* a, int m, int* s_w)
+{
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	int base = 0;
+	for (int i0 = 0; i0 < m; i0 += G_THREADS)
+	{
+		const int i = i0 + tid;
+		const int v = i < m ? a[i] : 0;
+		int inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const int o = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += o;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		int wbase = 0, tot = 0;
+		for (int w = 0; w < G_THREADS / 32; w++)
+		{
+			const int t = s_w[w];
+			if (w < warp) wbase += t;
+			tot += t;
+		}
+		if (i < m) a[i] = base + wbase + inc - v;
+		base += tot;
+		__syncthreads();
+	}
+	return base;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// FeaturesGrid::AssignFeatures (src/Frame.cc:70-100): counting sort of the keypoints into grid_[cx][cy], push_back order kept
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(G_THREADS) k_grid_build(const orbx_keypoint* __restrict__ kps, int n, orbx_bounds b, float invW, float invH,
+                                                          int* __restrict__ cell_start, int4* __restrict__ rec, int* __restrict__ cell_of)
+{
+	__shared__ int s_cnt[GRID_CELLS];
+	__shared__ int s_beg[GRID_CELLS];
+	__shared__ int s_w[G_THREADS / 32 + 1];
+	const int tid = threadIdx.x;
+	for (int c = tid; c < GRID_CELLS; c += G_THREADS) s_cnt[c] = 0;
+	__syncthreads();
+	for (int i = tid; i < n; i += G_THREADS)
+	{
+		const int cx = (int)roundf(invW * (kps[i].x - b.minx));   // Round() = std::round, :32, :91-92
+		const int cy = (int)roundf(invH * (kps[i].y - b.miny));
+		const int cell = (cx < 0 || cx >= GRID_COLS || cy < 0 || cy >= GRID_ROWS) ? -1 : cx * GRID_ROWS + cy;   // :95-96
+		cell_of[i] = cell;
+		if (cell >= 0) atomicAdd(&s_cnt[cell], 1);
+	}
+	__syncthreads();
+	for (int c = tid; c < GRID_CELLS; c += G_THREADS) s_beg[c] = s_cnt[c];
+	__syncthreads();
+	const int total = block_exscan_inplace(s_beg, GRID_CELLS, s_w);
+	for (int c = tid; c < GRID_CELLS; c += G_THREADS) { cell_start[c] = s_beg[c]; s_cnt[c] = s_beg[c]; }
+	if (tid == 0) cell_start[GRID_CELLS] = total;
+	__syncthreads();
+	for (int i = tid; i < n; i += G_THREADS)
+	{
+		const int cell = cell_of[i];
+		if (cell < 0) continue;
+		const int p = atomicAdd(&s_cnt[cell], 1);
+		rec[p] = make_int4(__float_as_int(kps[i].x), __float_as_int(kps[i].y), i, kps[i].octave);
+	}
+	__syncthreads();
+	// the atomics filled each cell in arbitrary order; a cell holds a handful of keypoints: sort it by index (= push_back order)
+	for (int c = tid; c < GRID_CELLS; c += G_THREADS)
+	{
+		const int a = s_beg[c], e = s_cnt[c];
+		for (int i = a + 1; i < e; i++)
+		{
+			const int4 v = rec[i];
+			int j = i - 1;
+			while (j >= a && rec[j].z > v.z) { rec[j + 1] = rec[j]; --j; }
+			rec[j + 1] = v;
+		}
+	}
+}
+
+// GetFeaturesInArea for a batch of windows: count, scan, fill
+__global__ void __launch_bounds__(G_THREADS) k_features_in_area(GridDev G, const float* __restrict__ xyr, const int* __restrict__ levels, int nq,
+                                                               int* __restrict__ offsets, int* __restrict__ indices, int cap)
+{
+	__shared__ int s_w[G_THREADS / 32 + 1];
+	const int tid = threadIdx.x;
+	for (int q = tid; q < nq; q += G_THREADS)
+	{
+		int c = 0;
+		for_window(G, xyr[3 * q], xyr[3 * q + 1], xyr[3 * q + 2], levels[2 * q], levels[2 * q + 1], [&](int, int) { c++; });
+		offsets[q] = c;
+	}
+	__syncthreads();
+	const int total = block_exscan_inplace(offsets, nq, s_w);
+	if (tid == 0) offsets[nq] = total;
+	if (total > cap) return;
+	for (int q = tid; q < nq; q += G_THREADS)
+	{
+		int p = offsets[q];
+		for_window(G, xyr[3 * q], xyr[3 * q + 1], xyr[3 * q + 2], levels[2 * q], levels[2 * q + 1], [&](int idx, int) { indices[p++] = idx; });
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The three window searches
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pack_levels(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
+__device__ __forceinline__ int level_lo(int v) { return (int)(short)(v & 0xffff); }
+__device__ __forceinline__ int level_hi(int v) { return v >> 16; }
+constexpr int INACTIVE = -32768;
+
+// CheckOrientation (:249-309) over the matches (i, choice[i]); bins were stored by the caller. Invalidates through `erase(i)`,
+// returns matches - reduction. s_hist: HISTO_LENGTH ints, zeroed by the caller before the bins were counted; s_misc: 2 ints.
+template <class Erase>
+__device__ int check_orientation(const GuidedArgs& A, const int* bin_of, int* s_hist, uint64_t* s_items, int* s_misc, Erase erase)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0)
+	{
+		int total = 0;
+		for (int b = 0; b < HISTO_LENGTH; b++)
+		{
+			s_items[b] = ((uint64_t)(uint32_t)s_hist[b] << 32) | (uint32_t)b;
+			total += s_hist[b];
+		}
+		qs_sort_serial(s_items, HISTO_LENGTH);   // std::sort by size, descending: unstable, so replayed (orbx_sort.cuh)
+		const double max1 = (double)(uint32_t)(s_items[0] >> 32), max2 = (double)(uint32_t)(s_items[1] >> 32),
+		             max3 = (double)(uint32_t)(s_items[2] >> 32);
+		int eraseBin = 3;
+		if (max2 < 0.1 * max1) eraseBin = 1;
+		else if (max3 < 0.1 * max1) eraseBin = 2;
+		uint32_t mask = 0;
+		int reduction = 0;
+		for (int b = eraseBin; b < HISTO_LENGTH; b++)
+		{
+			mask |= 1u << (uint32_t)(s_items[b] & 31u);
+			reduction += (int)(s_items[b] >> 32);
+		}
+		s_misc[0] = (int)mask;
+		s_misc[1] = total - reduction;
+	}
+	__syncthreads();
+	const uint32_t mask = (uint32_t)s_misc[0];
+	for (int i = tid; i < A.npts; i += G_THREADS)
+		if (A.choice[i] >= 0 && ((mask >> bin_of[i]) & 1u)) erase(i);
+	return s_misc[1];
+}
+
+__device__ __forceinline__ int orientation_bin(float a1, float a2)
+{
+	float diff = a1 - a2;
+	if (diff < 0) diff += 360;
+	int bin = __float2int_rn((1.f / HISTO_LENGTH) * diff);   // cvRound
+	if (bin == HISTO_LENGTH) bin = 0;
+	// the reference asserts 0 <= bin < 30 (:279) and would throw on angles outside [0, 360); keep the shared histogram in bounds
+	return min(max(bin, 0), HISTO_LENGTH - 1);
+}
+
+__global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
+{
+	__shared__ int s_w[G_THREADS / 32 + 1];
+	__shared__ int s_hist[HISTO_LENGTH];
+	__shared__ uint64_t s_items[HISTO_LENGTH];
+	__shared__ int s_misc[2];
+	__shared__ int s_count;
+	const int tid = threadIdx.x;
+	const GridDev& G = A.G;
+	const int npts = A.npts, n2 = G.n;
+
+	// ---- the window of every point
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f;
+		int lv = pack_levels(INACTIVE, 0);
+		if (A.mode == MODE_LOCAL_MAP)
+		{
+			const orbx_track_point p = A.tp[i];
+			if (p.flags & 1)                                                   // :321-322
+			{
+				const int ps = p.scale_level;
+				const float r = p.view_cos > 0.998 ? 2.5f : 4.f;                  // RadiusByViewingCos, :53 (float against a double literal)
+				radius = A.th * r * A.sf[ps];                                     // :327
+				u = p.proj_x; v = p.proj_y; ur = p.proj_xr;
+				lv = pack_levels(ps - 1, ps);                                     // :332
+			}
+		}
+		else if (A.mode == MODE_LAST_FRAME)
+		{
+			const orbx_last_point p = A.lp[i];
+			if (p.flags & 1)                                                   // :1295-1297
+			{
+				// CameraProjection::WorldToCamera: cv::Matx product (s = 0; s += R(r,k) * Xw(k), k ascending), then + tcw
+				float xc[3];
+#pragma unroll
+				for (int r = 0; r < 3; r++)
+				{
+					float s = 0.f;
+#pragma unroll
+					for (int k = 0; k < 3; k++) s = __fadd_rn(s, __fmul_rn(A.R[r * 3 + k], p.xw[k]));
+					xc[r] = __fadd_rn(s, A.t[r]);
+				}
+				if (!(xc[2] < 0.f))                                            // :1302-1303
+				{
+					const float invZ = __fdiv_rn(1.f, xc[2]);                  // CameraToImage
+					u = __fadd_rn(__fmul_rn(__fmul_rn(invZ, A.fx), xc[0]), A.cx);
+					v = __fadd_rn(__fmul_rn(__fmul_rn(invZ, A.fy), xc[1]), A.cy);
+					ur = __fsub_rn(u, __fdiv_rn(A.bf, xc[2]));                 // :1308
+					if (u >= G.b.minx && u < G.b.maxx && v >= G.b.miny && v < G.b.maxy)   // ImageBounds::Contains, :1310
+					{
+						const int oct = p.octave;
+						radius = A.th * A.sf[oct];                               // :1316
+						lv = pack_levels(A.forward ? oct : (A.backward ? 0 : oct - 1), A.forward ? -1 : (A.backward ? oct : oct + 1));   // :1318-1319
+					}
+				}
+			}
+		}
+		else
+		{
+			if (!(A.kps1[i].octave > 0))                                       // :629-631
+			{
+				u = A.prev[2 * i]; v = A.prev[2 * i + 1];
+				radius = A.radius;
+				lv = pack_levels(0, 0);                                           // :637
+			}
+		}
+		A.pu[i] = u; A.pv[i] = v; A.pur[i] = ur; A.prad[i] = radius; A.plevels[i] = lv;
+		A.choice[i] = -1;
+		if (A.mode == MODE_INIT) { A.aux0[i] = INT_MAX; A.aux1[i] = INT_MAX; }
+	}
+	__syncthreads();
+
+	// ---- candidate lists: count, scan, fill in GetFeaturesInArea order
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		int c = 0;
+		const int lv = A.plevels[i];
+		if (level_lo(lv) != INACTIVE) for_window(G, A.pu[i], A.pv[i], A.prad[i], level_lo(lv), level_hi(lv), [&](int, int) { c++; });
+		A.off[i] = c;
+	}
+	__syncthreads();
+	const int total = block_exscan_inplace(A.off, npts, s_w);
+	if (tid == 0) { A.off[npts] = total; A.result[1] = total; A.result[3] = total > A.cap; }
+	if (total > A.cap) return;
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		int p = A.off[i];
+		const int lv = A.plevels[i];
+		if (level_lo(lv) != INACTIVE)
+			for_window(G, A.pu[i], A.pv[i], A.prad[i], level_lo(lv), level_hi(lv), [&](int idx, int oct) {
+				A.list[p] = (uint32_t)idx | ((uint32_t)oct << E_IDX_BITS);
+				A.entry_pt[p] = i;
+				p++;
+			});
+	}
+	__syncthreads();
+
+	// ---- every distance, one thread per candidate (DescriptorDistance, :1449-1457), and the stereo gate (:342-343, :1333-1334)
+	for (int e = tid; e < total; e += G_THREADS)
+	{
+		const uint32_t ent = A.list[e];
+		const int idx = (int)(ent & E_IDX_MASK), i = A.entry_pt[e];
+		uint32_t d;
+		const float ur2 = A.uright2[idx];
+		if (A.mode != MODE_INIT && ur2 > 0 && fabsf(A.pur[i] - ur2) > A.prad[i]) d = E_SKIP;
+		else d = (uint32_t)hamming256(A.pt_desc + (size_t)i * 32, A.desc2 + (size_t)idx * 32);
+		A.list[e] = ent | (d << (E_IDX_BITS + E_LVL_BITS));
+	}
+	__syncthreads();
+
+	int rounds = 0;
+	if (A.mode != MODE_INIT)
+	{
+		// ---- rounds: owner[c] = lowest point index with observations that takes keypoint c (-1: closed on entry)
+		for (;;)
+		{
+			for (int c = tid; c < n2; c += G_THREADS)
+			{
+				const int m = A.frame_mp[c];
+				const bool closed = m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
+				A.owner[c] = closed ? -1 : INT_MAX;
+			}
+			__syncthreads();
+			for (int i = tid; i < npts; i += G_THREADS)
+			{
+				const int c = A.choice[i];
+				if (c >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2)) atomicMin(&A.owner[c], i);
+			}
+			__syncthreads();
+			int changed = 0;
+			for (int i = tid; i < npts; i += G_THREADS)
+			{
+				int best = 256, second = 256, bestLevel = -1, secondLevel = -1, bestIdx = -1;
+				for (int e = A.off[i]; e < A.off[i + 1]; e++)
+				{
+					const uint32_t ent = A.list[e];
+					const int d = (int)(ent >> (E_IDX_BITS + E_LVL_BITS));
+					if (d == (int)E_SKIP) continue;
+					const int idx = (int)(ent & E_IDX_MASK);
+					if (A.owner[idx] < i) continue;                            // :339-340, :1330-1331
+					const int lvl = (int)((ent >> E_IDX_BITS) & ((1u << E_LVL_BITS) - 1));
+					if (d < best) { second = best; best = d; secondLevel = bestLevel; bestLevel = lvl; bestIdx = idx; }
+					else if (d < second) { secondLevel = lvl; second = d; }
+				}
+				bool ok = best <= TH_HIGH;                                        // :370, :1349
+				if (ok && A.mode == MODE_LOCAL_MAP && bestLevel == secondLevel && (float)best > A.nnratio * (float)second) ok = false;   // :372-373
+				const int c = ok ? bestIdx : -1;
+				if (c != A.choice[i]) { A.choice[i] = c; changed = 1; }
+			}
+			rounds++;
+			if (!__syncthreads_or(changed)) break;
+		}
+
+		// ---- frame.mappoints: the last point (in loop order) that took a keypoint stays there
+		if (tid == 0) s_count = 0;
+		for (int b = tid; b < HISTO_LENGTH; b += G_THREADS) s_hist[b] = 0;
+		for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;
+		__syncthreads();
+		int mine = 0;
+		for (int i = tid; i < npts; i += G_THREADS)
+		{
+			const int c = A.choice[i];
+			if (c < 0) continue;
+			mine++;
+			atomicMax(&A.owner[c], i);
+			if (A.mode == MODE_LAST_FRAME && A.check_ori)
+			{
+				const int bin = orientation_bin(A.lp[i].angle, A.kps2[c].angle);   // keypoints1 = lastFrame.keypointsUn, :1358
+				A.aux0[i] = bin;
+				atomicAdd(&s_hist[bin], 1);
+			}
+		}
+		if (mine) atomicAdd(&s_count, mine);
+		__syncthreads();
+		for (int c = tid; c < n2; c += G_THREADS)
+			if (A.owner[c] >= 0) A.frame_mp[c] = A.owner[c];
+		__syncthreads();
+		int nmatches = s_count;
+		if (A.mode == MODE_LAST_FRAME && A.check_ori)
+			nmatches = check_orientation(A, A.aux0, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[A.choice[i]] = -1; });   // :298-304
+		if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
+		return;
+	}
+
+	// ---- SearchForInitialization: matchedDistance[c] as seen by point i = the smallest accepted distance among points j < i on c
+	int* bd_old = A.aux0;
+	int* bd_new = A.aux1;
+	for (;;)
+	{
+		for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;         // heads of the claim lists
+		__syncthreads();
+		for (int i = tid; i < npts; i += G_THREADS)
+			if (A.choice[i] >= 0) A.next[i] = atomicExch(&A.owner[A.choice[i]], i);
+		__syncthreads();
+		int changed = 0;
+		for (int i = tid; i < npts; i += G_THREADS)
+		{
+			int best = INT_MAX, second = INT_MAX, bestIdx = -1;
+			for (int e = A.off[i]; e < A.off[i + 1]; e++)
+			{
+				const uint32_t ent = A.list[e];
+				const int d = (int)(ent >> (E_IDX_BITS + E_LVL_BITS));
+				const int idx = (int)(ent & E_IDX_MASK);
+				int md = INT_MAX;
+				for (int j = A.owner[idx]; j >= 0; j = A.next[j])
+					if (j < i) md = min(md, bd_old[j]);
+				if (md <= d) continue;                                         // :651-652
+				if (d < best) { second = best; best = d; bestIdx = idx; }
+				else if (d < second) second = d;
+			}
+			const bool ok = bestIdx >= 0 && best <= TH_LOW && (float)best < (float)second * A.nnratio;   // :666
+			const int c = ok ? bestIdx : -1;
+			const int bd = ok ? best : INT_MAX;
+			if (c != A.choice[i] || bd != bd_old[i]) changed = 1;
+			A.choice[i] = c;
+			bd_new[i] = bd;
+		}
+		rounds++;
+		int* t = bd_old; bd_old = bd_new; bd_new = t;
+		if (!__syncthreads_or(changed)) break;
+	}
+	// matches21[c] = the last accepted point on c; earlier ones were revoked (:668-672)
+	if (tid == 0) s_count = 0;
+	for (int b = tid; b < HISTO_LENGTH; b += G_THREADS) s_hist[b] = 0;
+	for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;
+	__syncthreads();
+	int accepted = 0;
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		const int c = A.choice[i];
+		if (c < 0) continue;
+		accepted++;
+		atomicMax(&A.owner[c], i);
+		if (A.check_ori)
+		{
+			const int bin = orientation_bin(A.kps2[c].angle, A.kps1[i].angle);     // keypoints1 = frame2.keypointsUn, :686
+			bd_new[i] = bin;
+			atomicAdd(&s_hist[bin], 1);
+		}
+	}
+	__syncthreads();
+	int distinct = 0;
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		const int c = A.choice[i];
+		const bool keep = c >= 0 && A.owner[c] == i;
+		A.frame_mp[i] = keep ? c : -1;
+		distinct += keep;
+	}
+	atomicAdd(&s_count, A.check_ori ? accepted : distinct);   // with CheckOrientation the count restarts from matchIds.size() (:686)
+	__syncthreads();
+	int nmatches = s_count;
+	if (A.check_ori) nmatches = check_orientation(A, bd_new, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[i] = -1; });
+	__syncthreads();
+	for (int i = tid; i < npts; i += G_THREADS)
+	{
+		const int c = A.frame_mp[i];
+		if (c >= 0) { A.prev[2 * i] = A.kps2[c].x; A.prev[2 * i + 1] = A.kps2[c].y; }   // :689-691
+	}
+	if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
+}
+
+template <class T> struct GBuf
+{
+	T* p = nullptr;
+	size_t n = 0;
+	cudaError_t ensure(size_t count)
+	{
+		if (count <= n) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; n = 0;
+		const size_t want = count + count / 2 + 64;
+		cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+		if (e == cudaSuccess) n = want;
+		return e;
+	}
+	~GBuf() { if (p) cudaFree(p); }
+	GBuf() = default;
+	GBuf(const GBuf&) = delete;
+	GBuf& operator=(const GBuf&) = delete;
+};
+
+#define GCU(call)                                                                                             \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                              \
+		if (e_ != cudaSuccess)                                                                                \
+			return orbx_fail(ORBX_ERR_CUDA, (std::string(#call) + ": " + cudaGetErrorString(e_)).c_str());     \
+	} while (0)
+
+}  // namespace
+
+struct orbx_frame_s
+{
+	int device = 0;
+	int n = 0, nlevels = 0;
+	orbx_bounds b{};
+	float invW = 0.f, invH = 0.f;
+	float sf[16] = {};
+	cudaStream_t st = nullptr;
+	int* h_res = nullptr;        // pinned: nmatches, entries, rounds, overflow
+	int last_rounds = 0;
+	GBuf<orbx_keypoint> kps;
+	GBuf<uint8_t> desc;
+	GBuf<float> uright;
+	GBuf<int> cell_start, cell_of;
+	GBuf<int4> rec;
+	// per-search scratch
+	GBuf<uint8_t> pts, pt_desc;
+	GBuf<float> pf;
+	GBuf<int> pi, owner, entry_pt, res, mp;
+	GBuf<uint32_t> list;
+	GBuf<float> prev, qf;
+	GBuf<int> qi, qoff, qidx;
+
+	GridDev grid() const
+	{
+		GridDev G;
+		G.n = n; G.nlevels = nlevels; G.b = b; G.invW = invW; G.invH = invH;
+		G.cell_start = cell_start.p; G.rec = rec.p;
+		return G;
+	}
+	~orbx_frame_s()
+	{
+		if (h_res) cudaFreeHost(h_res);
+		if (st) cudaStreamDestroy(st);
+	}
+};
+
+namespace {
+
+// fills the frame part and the scratch pointers of the kernel arguments; npts-sized scratch is carved from f->pf / f->pi
+orbx_status prepare(orbx_frame_s* f, int npts, GuidedArgs& A)
+{
+	GCU(cudaSetDevice(f->device));
+	GCU(f->pf.ensure((size_t)npts * 4 + 4));
+	GCU(f->pi.ensure((size_t)npts * 6 + 8));
+	GCU(f->owner.ensure((size_t)f->n + 1));
+	GCU(f->res.ensure(4));
+	GCU(f->mp.ensure((size_t)std::max(f->n, npts) + 1));
+	const size_t want = (size_t)npts * 48 + 4096;
+	if (f->list.n < want)
+	{
+		GCU(f->list.ensure(want));
+		GCU(f->entry_pt.ensure(want));
+	}
+	A.G = f->grid();
+	A.kps2 = f->kps.p; A.desc2 = f->desc.p; A.uright2 = f->uright.p;
+	for (int i = 0; i < 16; i++) A.sf[i] = f->sf[i];
+	A.npts = npts;
+	A.pu = f->pf.p; A.pv = A.pu + npts; A.pur = A.pv + npts; A.prad = A.pur + npts;
+	A.plevels = f->pi.p; A.off = A.plevels + npts; A.choice = A.off + npts + 1; A.aux0 = A.choice + npts; A.aux1 = A.aux0 + npts;
+	A.next = A.aux1 + npts;
+	A.owner = f->owner.p;
+	A.list = f->list.p; A.entry_pt = f->entry_pt.p; A.cap = (int)std::min(f->list.n, f->entry_pt.n);
+	A.frame_mp = f->mp.p;
+	A.result = f->res.p;
+	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr;
+	A.th = 0.f; A.nnratio = 0.f; A.radius = 0.f; A.fx = A.fy = A.cx = A.cy = A.bf = 0.f;
+	for (int i = 0; i < 9; i++) A.R[i] = 0.f;
+	for (int i = 0; i < 3; i++) A.t[i] = 0.f;
+	A.forward = A.backward = A.check_ori = 0;
+	return ORBX_OK;
+}
+
+// launches the search; grows the candidate arrays and repeats when they were too small. The inputs must already be on the device.
+orbx_status run_search(orbx_frame_s* f, GuidedArgs& A, int* nmatches)
+{
+	for (int attempt = 0; attempt < 2; attempt++)
+	{
+		k_guided_search<<<1, G_THREADS, 0, f->st>>>(A);
+		GCU(cudaGetLastError());
+		GCU(cudaMemcpyAsync(f->h_res, f->res.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
+		GCU(cudaStreamSynchronize(f->st));
+		if (!f->h_res[3]) break;
+		if (attempt == 1) return orbx_fail(ORBX_ERR_CUDA, "candidate list overflow after regrowth");
+		// INIT mode is restartable because prev/choice are only written after the overflow check
+		GCU(f->list.ensure((size_t)f->h_res[1] + 1024));
+		GCU(f->entry_pt.ensure((size_t)f->h_res[1] + 1024));
+		A.list = f->list.p; A.entry_pt = f->entry_pt.p; A.cap = (int)std::min(f->list.n, f->entry_pt.n);
+	}
+	f->last_rounds = f->h_res[2];
+	if (nmatches) *nmatches = f->h_res[0];
+	return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+orbx_status orbx_frame_create(const orbx_frame_view* v, int device, orbx_frame* out)
+{
+	if (!v || !out) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	if (v->n < 0 || (v->n > 0 && (!v->kps_un || !v->desc))) return orbx_fail(ORBX_ERR_INVALID, "frame without keypoints/descriptors");
+	if (v->n >= (1 << E_IDX_BITS)) return orbx_fail(ORBX_ERR_INVALID, "more than 524287 keypoints in a frame");
+	if (v->nlevels < 1 || v->nlevels > 16 || !v->scale_factors) return orbx_fail(ORBX_ERR_INVALID, "nlevels must be in [1, 16]");
+	if (!(v->bounds.maxx > v->bounds.minx) || !(v->bounds.maxy > v->bounds.miny))
+		return orbx_fail(ORBX_ERR_INVALID, "empty image bounds (the reference divides by zero, src/Frame.cc:73-74)");
+	for (int i = 0; i < v->n; i++)
+		if (v->kps_un[i].octave < 0 || v->kps_un[i].octave >= 16) return orbx_fail(ORBX_ERR_INVALID, "keypoint octave outside [0, 16)");
+	const char* why = nullptr;
+	if (!orbx_device_usable(device, &why)) return orbx_fail(ORBX_ERR_CUDA, why);
+	GCU(cudaSetDevice(device));
+	orbx_frame_s* f = new orbx_frame_s;
+	f->device = device;
+	f->n = v->n; f->nlevels = v->nlevels; f->b = v->bounds;
+	f->invW = GRID_COLS / (v->bounds.maxx - v->bounds.minx);   // src/Frame.cc:73-74
+	f->invH = GRID_ROWS / (v->bounds.maxy - v->bounds.miny);
+	for (int i = 0; i < 16; i++) f->sf[i] = i < v->nlevels ? v->scale_factors[i] : 0.f;
+	auto bail = [&](cudaError_t e, const char* what) {
+		delete f;
+		return orbx_fail(ORBX_ERR_CUDA, (std::string(what) + ": " + cudaGetErrorString(e)).c_str());
+	};
+	cudaError_t e;
+	if ((e = cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+	if ((e = cudaMallocHost(&f->h_res, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMallocHost");
+	const size_t n = (size_t)std::max(v->n, 1);
+	if ((e = f->kps.ensure(n)) != cudaSuccess || (e = f->desc.ensure(n * 32)) != cudaSuccess || (e = f->uright.ensure(n)) != cudaSuccess ||
+	    (e = f->cell_start.ensure(GRID_CELLS + 1)) != cudaSuccess || (e = f->cell_of.ensure(n)) != cudaSuccess || (e = f->rec.ensure(n)) != cudaSuccess)
+		return bail(e, "cudaMalloc");
+	if (v->n > 0)
+	{
+		if ((e = cudaMemcpyAsync(f->kps.p, v->kps_un, (size_t)v->n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, f->st)) != cudaSuccess ||
+		    (e = cudaMemcpyAsync(f->desc.p, v->desc, (size_t)v->n * 32, cudaMemcpyHostToDevice, f->st)) != cudaSuccess)
+			return bail(e, "cudaMemcpyAsync");
+		if (v->uright)
+			e = cudaMemcpyAsync(f->uright.p, v->uright, (size_t)v->n * sizeof(float), cudaMemcpyHostToDevice, f->st);
+		else
+		{
+			std::vector<float> neg((size_t)v->n, -1.f);   // a monocular Frame: uright = -1 everywhere (src/Frame.cc, monocular constructor)
+			e = cudaMemcpyAsync(f->uright.p, neg.data(), (size_t)v->n * sizeof(float), cudaMemcpyHostToDevice, f->st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(f->st);
+		}
+		if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+	}
+	k_grid_build<<<1, G_THREADS, 0, f->st>>>(f->kps.p, f->n, f->b, f->invW, f->invH, f->cell_start.p, f->rec.p, f->cell_of.p);
+	if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(f->st)) != cudaSuccess) return bail(e, "k_grid_build");
+	*out = f;
+	return ORBX_OK;
+}
+
+orbx_status orbx_frame_destroy(orbx_frame f)
+{
+	if (!f) return ORBX_OK;
+	cudaSetDevice(f->device);
+	delete f;
+	return ORBX_OK;
+}
+
+orbx_status orbx_frame_grid(orbx_frame f, int32_t* cell_start, int32_t* items, int cap, int* n_items)
+{
+	if (!f || !cell_start || !n_items) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	GCU(cudaSetDevice(f->device));
+	GCU(cudaMemcpy(cell_start, f->cell_start.p, (GRID_CELLS + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+	*n_items = cell_start[GRID_CELLS];
+	if (*n_items > cap || (!items && *n_items > 0)) return orbx_fail(ORBX_ERR_CAPACITY, "items buffer too small");
+	std::vector<int4> rec((size_t)*n_items);
+	if (*n_items) GCU(cudaMemcpy(rec.data(), f->rec.p, rec.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < *n_items; i++) items[i] = rec[i].z;
+	return ORBX_OK;
+}
+
+orbx_status orbx_frame_features_in_area(orbx_frame f, const float* xyr, const int32_t* levels, int nq, int32_t* offsets, int32_t* indices, int cap)
+{
+	if (!f || !xyr || !levels || !offsets || nq < 0 || cap < 0 || (cap > 0 && !indices)) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	GCU(cudaSetDevice(f->device));
+	GCU(f->qf.ensure((size_t)nq * 3 + 1));
+	GCU(f->qi.ensure((size_t)nq * 2 + 1));
+	GCU(f->qoff.ensure((size_t)nq + 1));
+	GCU(f->qidx.ensure((size_t)cap + 1));
+	if (nq)
+	{
+		GCU(cudaMemcpyAsync(f->qf.p, xyr, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->qi.p, levels, (size_t)nq * 2 * sizeof(int), cudaMemcpyHostToDevice, f->st));
+	}
+	k_features_in_area<<<1, G_THREADS, 0, f->st>>>(f->grid(), f->qf.p, f->qi.p, nq, f->qoff.p, f->qidx.p, cap);
+	GCU(cudaGetLastError());
+	GCU(cudaMemcpyAsync(offsets, f->qoff.p, (size_t)(nq + 1) * sizeof(int), cudaMemcpyDeviceToHost, f->st));
+	GCU(cudaStreamSynchronize(f->st));
+	if (offsets[nq] > cap) return orbx_fail(ORBX_ERR_CAPACITY, "indices buffer too small; offsets[nq] holds the needed size");
+	if (offsets[nq]) GCU(cudaMemcpy(indices, f->qidx.p, (size_t)offsets[nq] * sizeof(int), cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_search_by_projection_local_map(orbx_frame f, int32_t* frame_mp, const orbx_track_point* pts, const uint8_t* pt_desc, int npts,
+                                                float th, float nnratio, int* nmatches)
+{
+	if (!f || !frame_mp || npts < 0 || (npts > 0 && (!pts || !pt_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	for (int i = 0; i < npts; i++)
+		if ((pts[i].flags & 1) && (pts[i].scale_level < 0 || pts[i].scale_level >= f->nlevels))
+			return orbx_fail(ORBX_ERR_INVALID, "trackScaleLevel outside the pyramid (the reference indexes scaleFactors out of range)");
+	for (int c = 0; c < f->n; c++)
+		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
+	GuidedArgs A;
+	if (orbx_status s = prepare(f, npts, A)) return s;
+	GCU(f->pts.ensure((size_t)npts * sizeof(orbx_track_point) + 16));
+	GCU(f->pt_desc.ensure((size_t)npts * 32 + 32));
+	if (npts)
+	{
+		GCU(cudaMemcpyAsync(f->pts.p, pts, (size_t)npts * sizeof(orbx_track_point), cudaMemcpyHostToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->pt_desc.p, pt_desc, (size_t)npts * 32, cudaMemcpyHostToDevice, f->st));
+	}
+	if (f->n) GCU(cudaMemcpyAsync(f->mp.p, frame_mp, (size_t)f->n * sizeof(int), cudaMemcpyHostToDevice, f->st));
+	A.mode = MODE_LOCAL_MAP;
+	A.tp = reinterpret_cast<const orbx_track_point*>(f->pts.p);
+	A.pt_desc = f->pt_desc.p;
+	A.th = th; A.nnratio = nnratio;
+	if (orbx_status s = run_search(f, A, nmatches)) return s;
+	if (f->n) GCU(cudaMemcpy(frame_mp, f->mp.p, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_search_by_projection_last_frame(orbx_frame f, const orbx_camera* cam, const orbx_pose* cp, const orbx_pose* lp, int32_t* frame_mp,
+                                                 const orbx_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular,
+                                                 int check_orientation, int* nmatches)
+{
+	if (!f || !cam || !cp || !lp || !frame_mp || npts < 0 || (npts > 0 && (!pts || !pt_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	for (int i = 0; i < npts; i++)
+		if ((pts[i].flags & 1) && (pts[i].octave < 0 || pts[i].octave >= f->nlevels))
+			return orbx_fail(ORBX_ERR_INVALID, "octave outside the pyramid (the reference indexes scaleFactors out of range)");
+	for (int c = 0; c < f->n; c++)
+		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
+	GuidedArgs A;
+	if (orbx_status s = prepare(f, npts, A)) return s;
+	GCU(f->pts.ensure((size_t)npts * sizeof(orbx_last_point) + 16));
+	GCU(f->pt_desc.ensure((size_t)npts * 32 + 32));
+	if (npts)
+	{
+		GCU(cudaMemcpyAsync(f->pts.p, pts, (size_t)npts * sizeof(orbx_last_point), cudaMemcpyHostToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->pt_desc.p, pt_desc, (size_t)npts * 32, cudaMemcpyHostToDevice, f->st));
+	}
+	if (f->n) GCU(cudaMemcpyAsync(f->mp.p, frame_mp, (size_t)f->n * sizeof(int), cudaMemcpyHostToDevice, f->st));
+	A.mode = MODE_LAST_FRAME;
+	A.lp = reinterpret_cast<const orbx_last_point*>(f->pts.p);
+	A.pt_desc = f->pt_desc.p;
+	A.th = th;
+	A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+	for (int i = 0; i < 9; i++) A.R[i] = cp->R[i];
+	for (int i = 0; i < 3; i++) A.t[i] = cp->t[i];
+	// tlc = Rlw * (-Rcw^T * tcw) + tlw (src/ORBmatcher.cc:1286); cv::Matx products accumulate from 0 in k order. Host float math,
+	// compiled without contraction (build.py passes -ffp-contract=off).
+	float twc[3], tlc2 = 0.f;
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0.f;
+		for (int k = 0; k < 3; k++) s += (cp->R[k * 3 + i] * -1) * cp->t[k];
+		twc[i] = s;
+	}
+	{
+		float s = 0.f;
+		for (int k = 0; k < 3; k++) s += lp->R[2 * 3 + k] * twc[k];
+		tlc2 = s + lp->t[2];
+	}
+	A.forward = tlc2 > cam->baseline && !monocular;      // :1287-1288
+	A.backward = -tlc2 > cam->baseline && !monocular;
+	A.check_ori = check_orientation != 0;
+	if (orbx_status s = run_search(f, A, nmatches)) return s;
+	if (f->n) GCU(cudaMemcpy(frame_mp, f->mp.p, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size, float nnratio,
+                                           int check_orientation, int* nmatches)
+{
+	if (!f1 || !f2 || !prev_matched || !matches12) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	if (f1->device != f2->device) return orbx_fail(ORBX_ERR_INVALID, "frames live on different devices");
+	const int npts = f1->n;
+	GuidedArgs A;
+	if (orbx_status s = prepare(f2, npts, A)) return s;
+	GCU(f2->prev.ensure((size_t)npts * 2 + 2));
+	if (npts) GCU(cudaMemcpyAsync(f2->prev.p, prev_matched, (size_t)npts * 2 * sizeof(float), cudaMemcpyHostToDevice, f2->st));
+	A.mode = MODE_INIT;
+	A.kps1 = f1->kps.p;
+	A.pt_desc = f1->desc.p;
+	A.prev = f2->prev.p;
+	A.radius = (float)window_size;                          // :626
+	A.nnratio = nnratio;
+	A.check_ori = check_orientation != 0;
+	if (orbx_status s = run_search(f2, A, nmatches)) return s;
+	if (npts)
+	{
+		GCU(cudaMemcpy(matches12, f2->mp.p, (size_t)npts * sizeof(int), cudaMemcpyDeviceToHost));
+		GCU(cudaMemcpy(prev_matched, f2->prev.p, (size_t)npts * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+	}
+	return ORBX_OK;
+}
+
+orbx_status orbx_frame_last_rounds(orbx_frame f, int* rounds)
+{
+	if (!f || !rounds) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	*rounds = f->last_rounds;
+	return ORBX_OK;
+}
+
+}  // extern "C"

@@ -127,3 +127,7 @@ void orbx_launch_stereo_from_rgbd(const orbx_keypoint* kps, const orbx_keypoint*
                                   float* uright, float* depth, cudaStream_t st);
 void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best, cudaStream_t st);
 double orbx_popc_probe(int device);
+
+// shared by the host layers (orbx_api.cu owns the thread-local error text)
+orbx_status orbx_fail(orbx_status s, const char* msg);
+bool orbx_device_usable(int device, const char** why);

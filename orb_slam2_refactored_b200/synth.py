@@ -79,3 +79,150 @@ CONFIGS = {
     'C3': dict(w=752, h=480, nfeatures=1200, camera=EUROC_CAMERA),
     'C4': dict(w=3840, h=2160, nfeatures=8000),
 }
+
+
+# ---- guided-matcher scenes: a frame as Tracking sees it plus the map points projected into it ----
+KP_DTYPE = np.dtype([('x', '<f4'), ('y', '<f4'), ('size', '<f4'), ('angle', '<f4'), ('response', '<f4'), ('octave', '<i4'),
+                     ('class_id', '<i4')])
+TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
+                              ('flags', '<i4')])
+LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
+
+
+def scale_factors(nlevels=8, factor=1.2):
+    """float32 cumulative products, as ORBextractor::Init builds them (src/ORBextractor.cc:728-737)."""
+    sf = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        sf[i] = np.float32(sf[i - 1] * np.float32(factor))
+    return sf
+
+
+def _flip_bits(r, d, k):
+    bits = np.unpackbits(d)
+    bits[r.choice(256, k, replace=False)] ^= 1
+    return np.packbits(bits)
+
+
+def frame(seed, n=1500, w=640, h=480, nlevels=8, stereo=True, level0_share=None, bounds_margin=0.0):
+    """A synthetic Frame: keypoints on level-integer positions times the level scale (as Extract emits them), octaves drawn like the
+    per-level quotas, uniform angles, random descriptors, uright for ~70 % of the keypoints when stereo."""
+    r = np.random.RandomState(seed)
+    sf = scale_factors(nlevels)
+    p = (1.0 / 1.2) ** np.arange(nlevels)
+    if level0_share is not None:
+        p[0] = level0_share * p[1:].sum() / (1.0 - level0_share)
+    octv = r.choice(nlevels, n, p=p / p.sum()).astype(np.int32)
+    kps = np.zeros(n, KP_DTYPE)
+    lw = np.maximum((w / sf[octv]).astype(np.int32) - 32, 1)
+    lh = np.maximum((h / sf[octv]).astype(np.int32) - 32, 1)
+    kps['x'] = ((16 + (r.rand(n) * lw).astype(np.int32)).astype(np.float32) * sf[octv]).astype(np.float32)
+    kps['y'] = ((16 + (r.rand(n) * lh).astype(np.int32)).astype(np.float32) * sf[octv]).astype(np.float32)
+    kps['size'] = np.float32(31.0) * sf[octv]
+    kps['angle'] = (r.rand(n) * 360.0).astype(np.float32)
+    kps['response'] = r.randint(8, 120, n).astype(np.float32)
+    kps['octave'] = octv
+    kps['class_id'] = -1
+    ur = None
+    if stereo:
+        ur = np.where(r.rand(n) < 0.7, kps['x'] - (1.0 + 60.0 * r.rand(n)).astype(np.float32), np.float32(-1.0)).astype(np.float32)
+    m = np.float32(bounds_margin)
+    return dict(kps_un=kps, desc=r.randint(0, 256, (n, 32)).astype(np.uint8), uright=ur,
+                bounds=(np.float32(-m), np.float32(w + m), np.float32(-m * 0.5), np.float32(h + m * 0.5)), nlevels=nlevels, scale_factors=sf)
+
+
+def initial_frame_mappoints(seed, n, p_seen=0.05, p_unseen=0.03):
+    """frame.mappoints on entry: -1 null, -2 a map point with observations, -3 one without (see include/orbx.h)."""
+    r = np.random.RandomState(seed + 77)
+    u = r.rand(n)
+    return np.where(u < p_seen, -2, np.where(u < p_seen + p_unseen, -3, -1)).astype(np.int32)
+
+
+def local_map_points(seed, fr, npts=1200, dup=0.2, max_flips=70):
+    """Map points in view of `fr` for SearchByProjection(Frame&, mappoints, th): each aims at a keypoint (20 % at one that another point
+    already aims at, so the greedy 'already matched' state matters), with a jittered projection and a descriptor a few bits away."""
+    r = np.random.RandomState(seed + 1)
+    kps, n = fr['kps_un'], len(fr['kps_un'])
+    sf = fr['scale_factors']
+    tgt = r.randint(0, n, npts)
+    d = r.rand(npts) < dup
+    tgt[d] = tgt[r.randint(0, npts, d.sum())]
+    pts = np.zeros(npts, TRACK_POINT_DTYPE)
+    octv = kps['octave'][tgt]
+    pts['scale_level'] = np.clip(octv + r.choice([0, 0, 1, 1, 2, -1], npts), 0, fr['nlevels'] - 1)
+    jit = (r.randn(npts, 2) * 2.0).astype(np.float32) * sf[pts['scale_level']][:, None]
+    pts['proj_x'] = kps['x'][tgt] + jit[:, 0]
+    pts['proj_y'] = kps['y'][tgt] + jit[:, 1]
+    ur = fr['uright'][tgt] if fr['uright'] is not None else np.full(npts, -1.0, np.float32)
+    pts['proj_xr'] = np.where(r.rand(npts) < 0.85, ur + jit[:, 0], ur + (r.randn(npts) * 40).astype(np.float32)).astype(np.float32)
+    pts['view_cos'] = (0.99 + 0.01 * r.rand(npts)).astype(np.float32)
+    pts['flags'] = (r.rand(npts) < 0.92).astype(np.int32) | ((r.rand(npts) < 0.8).astype(np.int32) << 1)
+    desc = np.stack([_flip_bits(r, fr['desc'][t], r.randint(0, max_flips + 1)) for t in tgt])
+    return pts, desc
+
+
+def last_frame_points(seed, fr, cam, npts=1200, dz=0.0, dup=0.2, max_flips=70):
+    """The last frame's tracked keypoints for SearchByProjection(currFrame, lastFrame, th, monocular): world points that project near
+    keypoints of `fr` under cur_pose. dz moves the last camera along z so that the forward / backward branches trigger
+    (src/ORBmatcher.cc:1286-1288). Returns (cur_pose, last_pose, pts, desc); poses are (R 3x3, t 3) float32."""
+    r = np.random.RandomState(seed + 2)
+    kps, n = fr['kps_un'], len(fr['kps_un'])
+    fx, fy, cx, cy = cam[:4]
+    a = 0.02 * r.randn(3)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    U, _, Vt = np.linalg.svd(np.eye(3) + K)
+    R = (U @ Vt).astype(np.float32)
+    t = (0.1 * r.randn(3)).astype(np.float32)
+    last_R = np.eye(3, dtype=np.float32)
+    last_t = np.array([0.01, -0.02, dz], np.float32)
+    tgt = r.randint(0, n, npts)
+    d = r.rand(npts) < dup
+    tgt[d] = tgt[r.randint(0, npts, d.sum())]
+    z = 2.0 + 28.0 * r.rand(npts)
+    z[r.rand(npts) < 0.03] *= -1.0
+    octv = np.clip(kps['octave'][tgt] + r.choice([0, 0, 0, 1, -1], npts), 0, fr['nlevels'] - 1).astype(np.int32)
+    jit = r.randn(npts, 2) * 3.0 * fr['scale_factors'][octv][:, None]
+    u = kps['x'][tgt] + jit[:, 0]
+    v = kps['y'][tgt] + jit[:, 1]
+    far = r.rand(npts) < 0.03
+    u[far] += 2000.0
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    Xw = (Xc - t.astype(np.float64)) @ R.astype(np.float64)      # R^T (Xc - t)
+    pts = np.zeros(npts, LAST_POINT_DTYPE)
+    pts['xw'] = Xw.astype(np.float32)
+    pts['octave'] = octv
+    rot = 25.0
+    ang = kps['angle'][tgt] + rot + 4.0 * r.randn(npts)
+    wild = r.rand(npts) < 0.15
+    ang[wild] = 360.0 * r.rand(wild.sum())
+    pts['angle'] = np.mod(ang, 360.0).astype(np.float32)
+    pts['flags'] = (r.rand(npts) < 0.9).astype(np.int32) | ((r.rand(npts) < 0.8).astype(np.int32) << 1)
+    desc = np.stack([_flip_bits(r, fr['desc'][t], r.randint(0, max_flips + 1)) for t in tgt])
+    return (R, t), (last_R, last_t), pts, desc
+
+
+def initialization_pair(seed, n=1500, w=640, h=480, max_flips=60):
+    """Two monocular frames for SearchForInitialization: frame 2 holds frame 1's keypoints moved by a few pixels (descriptors a few bits
+    away, angles turned by a common rotation) in shuffled order plus unrelated ones; level 0 carries most keypoints."""
+    r = np.random.RandomState(seed + 3)
+    f1 = frame(seed, n, w, h, stereo=False, level0_share=0.6)
+    f2 = frame(seed + 500, n, w, h, stereo=False, level0_share=0.6)
+    m = int(0.7 * n)
+    src = r.permutation(n)[:m]
+    dst = r.permutation(n)[:m]
+    k1, k2 = f1['kps_un'], f2['kps_un']
+    k2['x'][dst] = k1['x'][src] + (r.randn(m) * 6.0).astype(np.float32)
+    k2['y'][dst] = k1['y'][src] + (r.randn(m) * 6.0).astype(np.float32)
+    k2['octave'][dst] = k1['octave'][src]
+    ang = k1['angle'][src] + 40.0 + 5.0 * r.randn(m)
+    wild = r.rand(m) < 0.15
+    ang[wild] = 360.0 * r.rand(wild.sum())
+    k2['angle'][dst] = np.mod(ang, 360.0).astype(np.float32)
+    for s, d in zip(src, dst):
+        f2['desc'][d] = _flip_bits(r, f1['desc'][s], r.randint(0, max_flips + 1))
+    # near-duplicates in frame 2 so that two frame-1 keypoints compete for one frame-2 keypoint and matches get revoked (:668-672)
+    for s in src[: m // 6]:
+        j = r.randint(0, n)
+        k1['x'][j], k1['y'][j], k1['octave'][j] = k1['x'][s] + np.float32(1.5), k1['y'][s] - np.float32(1.0), k1['octave'][s]
+        f1['desc'][j] = _flip_bits(r, f1['desc'][s], r.randint(0, 12))
+    prev = np.stack([k1['x'], k1['y']], 1).astype(np.float32)
+    return f1, f2, prev

@@ -7,6 +7,7 @@ primitives.npz   outputs of cv2 4.13.0 (IPP off) for the four un-vendored primit
 pipeline.npz     outputs of the REFERENCE's own translation units (oracle/_ref, built from
                  /root/reference/src/ORBextractor.cc and ORBmatcher.cc line ranges) for Extract, the stages,
                  ComputeStereoMatches and the best/second scan on small synthetic inputs.
+guided.npz       outputs of the reference's guided matchers (src/Frame.cc, src/ORBmatcher.cc line ranges) on seeded scenes.
 Inputs are regenerated from orb_slam2_refactored_b200/synth.py (numpy RandomState); a CRC of every input is stored so
 that a silent change of the generator is caught.
 """
@@ -111,8 +112,26 @@ def pipeline():
     print('pipeline.npz: c1', len(kps), 'kps; stereo matched', int((dp > 0).sum()), '; knn accepted', int((match >= 0).sum()))
 
 
+def guided():
+    """guided.npz: outputs of the reference text of FeaturesGrid / SearchByProjection x2 / SearchForInitialization (oracle/_ref, rule
+    guided_gen.cc) on the small cases of tests/guided_cases.py."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import guided_cases as gc
+    ref = bindings.Oracle('ref')
+    out = {}
+    for name, kind, c in gc.cases(small=True):
+        res = gc.run_oracle(ref, kind, c)
+        for k, v in res.items():
+            out[f'{name}.{k}'] = v
+        fr = c.get('frame', c.get('f2'))
+        out[f'{name}.crc'] = np.array([crc(fr['kps_un']), crc(fr['desc'])])
+    np.savez_compressed(os.path.join(HERE, 'guided.npz'), **out)
+    print('guided.npz:', len(out), 'arrays')
+
+
 if __name__ == '__main__':
     primitives()
     pipeline()
-    for f in ('primitives.npz', 'pipeline.npz'):
+    guided()
+    for f in ('primitives.npz', 'pipeline.npz', 'guided.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')

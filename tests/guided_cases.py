@@ -1,0 +1,120 @@
+"""Seeded cases for the guided matchers, shared by the golden generator, the oracle tests and the GPU parity tests.
+Every case is (name, kind, inputs); run_oracle / run_product evaluate it and return a dict of arrays that must agree bit for bit."""
+import numpy as np
+
+from orb_slam2_refactored_b200 import synth
+
+TUM_CAMERA = (517.306408, 516.469215, 318.643040, 255.313989, 40.0, 40.0 / 517.306408)   # Examples/Monocular/TUM1.yaml + RGB-D bf
+
+
+def grid_queries(seed, n=400):
+    r = np.random.RandomState(seed + 9)
+    q = []
+    for lo, hi in [(-1, -1), (0, 0), (2, 3), (1, -1), (0, 7), (-1, 2), (5, 4)]:
+        for _ in range(n // 7):
+            q.append((r.rand() * 760 - 60, r.rand() * 600 - 60, r.rand() * 60 + 0.5, lo, hi))
+    q += [(-500.0, 10.0, 5.0, -1, -1), (10.0, 5000.0, 5.0, -1, -1), (320.0, 240.0, 2000.0, -1, -1), (0.0, 0.0, 0.0, -1, -1)]
+    return np.array(q, np.float64)
+
+
+def cases(small=False):
+    """small=True: the subset stored as golden vectors."""
+    out = []
+    seeds = (0, 1) if small else range(6)
+    for seed in seeds:
+        fr = synth.frame(seed, n=900 if small else 1500, bounds_margin=3.7 if seed % 2 else 0.0, stereo=seed % 3 != 2)
+        out.append((f'grid{seed}', 'grid', dict(frame=fr, queries=grid_queries(seed, 140 if small else 400))))
+        mp0 = synth.initial_frame_mappoints(seed, len(fr['kps_un']))
+        pts, desc = synth.local_map_points(seed, fr, npts=700 if small else 1200)
+        out.append((f'local{seed}', 'local', dict(frame=fr, mp=mp0, pts=pts, desc=desc, th=3.0 if seed % 3 else 5.0, nnratio=0.8)))
+        cam = synth.KITTI_CAMERA if seed % 2 else TUM_CAMERA
+        for dz in ((0.0, 1.0, -1.0) if not small else (0.0, 1.0)):
+            cp, lp, lpts, ldesc = synth.last_frame_points(seed, fr, cam, npts=700 if small else 1200, dz=dz)
+            for mono in (False, True):
+                if small and mono and dz:
+                    continue
+                out.append((f'last{seed}_dz{dz:+.0f}_m{int(mono)}', 'last',
+                            dict(frame=fr, cam=cam, cur_pose=cp, last_pose=lp, mp=mp0, pts=lpts, desc=ldesc, th=15.0 if mono else 7.0,
+                                 monocular=mono, check=seed != 3)))
+        f1, f2, prev = synth.initialization_pair(seed, n=800 if small else 1500)
+        for win in ((100,) if small else (100, 20)):
+            out.append((f'init{seed}_w{win}', 'init', dict(f1=f1, f2=f2, prev=prev, window=win, nnratio=0.9, check=seed != 4)))
+    if not small:
+        # crowded: most points aim at a keypoint some other point wants too, and the alternatives are close: long dependency chains
+        fr = synth.frame(40, n=600, w=320, h=240)
+        pts, desc = synth.local_map_points(40, fr, npts=3000, dup=0.8, max_flips=40)
+        pts['flags'] |= 2
+        out.append(('local_crowded', 'local', dict(frame=fr, mp=np.full(600, -1, np.int32), pts=pts, desc=desc, th=6.0, nnratio=0.9)))
+        cp, lp, lpts, ldesc = synth.last_frame_points(41, fr, TUM_CAMERA, npts=3000, dup=0.8, max_flips=40)
+        out.append(('last_crowded', 'last', dict(frame=fr, cam=TUM_CAMERA, cur_pose=cp, last_pose=lp, mp=np.full(600, -1, np.int32), pts=lpts,
+                                                 desc=ldesc, th=15.0, monocular=True, check=True)))
+        # ladder: K keypoints on one spot at distances 0, 1, 2, ... from one descriptor, K + 3 identical points: point i must end on
+        # keypoint i, which takes one round per rung (the worst case of the fixpoint)
+        K = 12
+        fr = synth.frame(60, n=400)
+        base = fr['desc'][0].copy()
+        for j in range(K):
+            fr['kps_un']['x'][j], fr['kps_un']['y'][j], fr['kps_un']['octave'][j] = 200.0 + 0.1 * j, 150.0, 0
+            bits = np.unpackbits(base)
+            bits[:j] ^= 1
+            fr['desc'][j] = np.packbits(bits)
+        if fr['uright'] is not None:
+            fr['uright'][:K] = -1.0
+        pts = np.zeros(K + 3, synth.TRACK_POINT_DTYPE)
+        pts['proj_x'], pts['proj_y'], pts['proj_xr'], pts['view_cos'], pts['scale_level'], pts['flags'] = 200.5, 150.0, -1.0, 0.9, 0, 3
+        out.append(('local_ladder', 'local', dict(frame=fr, mp=np.full(400, -1, np.int32), pts=pts, desc=np.tile(base, (K + 3, 1)), th=3.0,
+                                                  nnratio=1.0)))
+        # degenerate inputs
+        fr = synth.frame(50, n=300)
+        pts, desc = synth.local_map_points(50, fr, npts=50)
+        pts['flags'] &= ~1
+        out.append(('local_all_inactive', 'local', dict(frame=fr, mp=np.full(300, -1, np.int32), pts=pts, desc=desc, th=3.0, nnratio=0.8)))
+        out.append(('local_no_points', 'local', dict(frame=fr, mp=synth.initial_frame_mappoints(50, 300), pts=pts[:0], desc=desc[:0], th=3.0,
+                                                     nnratio=0.8)))
+        one = synth.frame(51, n=1)
+        p1, d1 = synth.local_map_points(51, one, npts=5, max_flips=10)
+        p1['flags'] = 3
+        out.append(('local_one_keypoint', 'local', dict(frame=one, mp=np.full(1, -1, np.int32), pts=p1, desc=d1, th=5.0, nnratio=0.8)))
+    return out
+
+
+def run_oracle(o, kind, c):
+    if kind == 'grid':
+        res = o.grid_queries(c['frame'], c['queries'])
+        return dict(counts=np.array([len(r) for r in res], np.int32), indices=np.concatenate(res + [np.empty(0, np.int32)]).astype(np.int32))
+    if kind == 'local':
+        n, mp = o.search_local_map(c['frame'], c['mp'], c['pts'], c['desc'], c['th'], c['nnratio'])
+        return dict(n=np.int32(n), mp=mp)
+    if kind == 'last':
+        n, mp = o.search_last_frame(c['frame'], c['cam'], c['cur_pose'], c['last_pose'], c['mp'], c['pts'], c['desc'], c['th'], c['monocular'],
+                                    0.9, c['check'])
+        return dict(n=np.int32(n), mp=mp)
+    n, m12, prev = o.search_for_initialization(c['f1'], c['f2'], c['prev'], c['window'], c['nnratio'], c['check'])
+    return dict(n=np.int32(n), m12=m12, prev=prev)
+
+
+def make_frame(api, fr, device=0):
+    return api.Frame(fr['kps_un'], fr['desc'], fr['scale_factors'], fr['bounds'], fr['uright'], device=device)
+
+
+def run_product(api, kind, c, device=0):
+    """The same through the C ABI (orb_slam2_refactored_b200.api). Also returns the number of rounds under key '_rounds'."""
+    if kind == 'grid':
+        f = make_frame(api, c['frame'], device)
+        res = f.GetFeaturesInAreaBatch(c['queries'])
+        return dict(counts=np.array([len(r) for r in res], np.int32), indices=np.concatenate(res + [np.empty(0, np.int32)]).astype(np.int32))
+    if kind == 'local':
+        f = make_frame(api, c['frame'], device)
+        f.mappoints[:] = c['mp']
+        n = api.ORBmatcher(c['nnratio'], True, device).SearchByProjection(f, c['pts'], c['desc'], c['th'])
+        return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
+    if kind == 'last':
+        f = make_frame(api, c['frame'], device)
+        f.mappoints[:] = c['mp']
+        n = api.ORBmatcher(0.9, c['check'], device).SearchByProjectionLastFrame(f, c['cam'], c['cur_pose'], c['last_pose'], c['pts'], c['desc'],
+                                                                                c['th'], c['monocular'])
+        return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
+    f1, f2 = make_frame(api, c['f1'], device), make_frame(api, c['f2'], device)
+    prev = c['prev'].copy()
+    n, m12 = api.ORBmatcher(c['nnratio'], c['check'], device).SearchForInitialization(f1, f2, prev, c['window'])
+    return dict(n=np.int32(n), m12=m12.copy(), prev=prev, _rounds=f2.last_rounds())

@@ -1,0 +1,111 @@
+"""GPU parity of the guided matchers through the C ABI: FeaturesGrid (src/Frame.cc:63-145), SearchByProjection for
+local-map and motion-model tracking (src/ORBmatcher.cc:315-382, 1279-1362), SearchForInitialization (:614-694) and CheckOrientation
+(:249-309). Bit-exact against the CPU oracle and against the committed outputs of the reference text."""
+import os
+
+import numpy as np
+import pytest
+
+import guided_cases as gc
+from orb_slam2_refactored_b200 import synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_grid_layout(orbx, oracle_port):
+    """AssignFeatures: cell = round-half-away(invW * (x - minx)), out-of-grid keypoints dropped, push_back order kept."""
+    for seed, margin in ((0, 0.0), (1, 3.7), (2, 40.0)):
+        fr = synth.frame(seed, n=2500, bounds_margin=margin)
+        if seed == 2:   # undistorted keypoints may leave the image (src/Frame.cc:94-96)
+            fr['kps_un']['x'][::17] -= 120.0
+            fr['kps_un']['y'][::13] += 90.0
+        f = gc.make_frame(orbx, fr)
+        start, items = f.grid()
+        b = fr['bounds']
+        invW = np.float32(64) / np.float32(b[1] - b[0]); invH = np.float32(48) / np.float32(b[3] - b[2])
+        vx = (invW * (fr['kps_un']['x'] - b[0])).astype(np.float32); vy = (invH * (fr['kps_un']['y'] - b[2])).astype(np.float32)
+        cx = (np.sign(vx) * np.floor(np.abs(vx) + np.float32(0.5))).astype(np.int64)
+        cy = (np.sign(vy) * np.floor(np.abs(vy) + np.float32(0.5))).astype(np.int64)
+        inside = (cx >= 0) & (cx < 64) & (cy >= 0) & (cy < 48)
+        cell = cx * 48 + cy
+        want = [np.flatnonzero(inside & (cell == c)) for c in range(64 * 48)]
+        assert start[-1] == inside.sum() == len(items)
+        for c in range(64 * 48):
+            assert np.array_equal(items[start[c]:start[c + 1]], want[c]), (seed, c)
+        if seed == 2:
+            assert inside.sum() < len(inside)
+
+
+def test_all_cases_against_oracle(orbx, oracle_port):
+    kinds, max_rounds = {}, 0
+    for name, kind, c in gc.cases():
+        want = gc.run_oracle(oracle_port, kind, c)
+        got = gc.run_product(orbx, kind, c)
+        for k, v in want.items():
+            assert np.array_equal(got[k], v), (name, k)
+        kinds[kind] = kinds.get(kind, 0) + 1
+        max_rounds = max(max_rounds, got.get('_rounds', 0))
+        if name == 'local_ladder':
+            assert got['_rounds'] >= 12 and list(got['mp'][:12]) == list(range(12))
+    assert set(kinds) == {'grid', 'local', 'last', 'init'} and max_rounds >= 12
+
+
+def test_reference_golden(orbx):
+    g = np.load(os.path.join(G, 'guided.npz'))
+    n = 0
+    for name, kind, c in gc.cases(small=True):
+        got = gc.run_product(orbx, kind, c)
+        for k in got:
+            if not k.startswith('_'):
+                assert np.array_equal(g[f'{name}.{k}'], got[k]), (name, k)
+                n += 1
+    assert n >= 25
+
+
+def test_frame_reuse_and_state_codes(orbx, oracle_port):
+    """One device frame serves several searches (TrackWithMotionModel then SearchLocalPoints); the second search starts from the
+    map points the first one stored."""
+    fr = synth.frame(7, n=2000)
+    f = gc.make_frame(orbx, fr)
+    cp, lp, lpts, ldesc = synth.last_frame_points(7, fr, synth.KITTI_CAMERA)
+    m = orbx.ORBmatcher(0.9, True)
+    n1 = m.SearchByProjectionLastFrame(f, synth.KITTI_CAMERA, cp, lp, lpts, ldesc, 7.0, False)
+    w1, mp1 = oracle_port.search_last_frame(fr, synth.KITTI_CAMERA, cp, lp, np.full(2000, -1, np.int32), lpts, ldesc, 7.0, False, 0.9, True)
+    assert n1 == w1 and np.array_equal(f.mappoints, mp1)
+    # the local-map search sees those as "some other map point": with observations when the last-frame point had them
+    state = np.where(mp1 >= 0, np.where((lpts['flags'][np.maximum(mp1, 0)] & 2) != 0, -2, -3), -1).astype(np.int32)
+    f.mappoints[:] = state
+    pts, desc = synth.local_map_points(8, fr, npts=2500)
+    n2 = orbx.ORBmatcher(0.8, True).SearchByProjection(f, pts, desc, 3.0)
+    w2, mp2 = oracle_port.search_local_map(fr, state, pts, desc, 3.0, 0.8)
+    assert n2 == w2 and np.array_equal(f.mappoints, mp2)
+
+
+def test_large_frame_and_list_regrowth(orbx, oracle_port):
+    """8000 keypoints (C4) and wide windows: the candidate arrays outgrow their first allocation and the search is repeated."""
+    fr = synth.frame(9, n=8000, w=3840, h=2160)
+    pts, desc = synth.local_map_points(9, fr, npts=6000)
+    f = gc.make_frame(orbx, fr)
+    f.mappoints[:] = -1
+    n = orbx.ORBmatcher(0.8, True).SearchByProjection(f, pts, desc, 3.0)
+    w, mp = oracle_port.search_local_map(fr, np.full(8000, -1, np.int32), pts, desc, 3.0, 0.8)
+    assert n == w and np.array_equal(f.mappoints, mp)
+    small = synth.frame(10, n=3000, w=320, h=240)
+    pts, desc = synth.local_map_points(10, small, npts=500)
+    f = gc.make_frame(orbx, small)
+    n = orbx.ORBmatcher(0.8, True).SearchByProjection(f, pts, desc, 40.0)     # ~500 candidates per point
+    w, mp = oracle_port.search_local_map(small, np.full(3000, -1, np.int32), pts, desc, 40.0, 0.8)
+    assert n == w and np.array_equal(f.mappoints, mp)
+
+
+def test_contract_errors(orbx):
+    fr = synth.frame(3, n=100)
+    with pytest.raises(orbx.OrbxError):
+        orbx.Frame(fr['kps_un'], fr['desc'], fr['scale_factors'], (0.0, 0.0, 0.0, 480.0))      # empty bounds: division by zero upstream
+    f = gc.make_frame(orbx, fr)
+    pts, desc = synth.local_map_points(3, fr, npts=10)
+    pts['scale_level'][0] = 9
+    pts['flags'][0] = 1
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBmatcher(0.8).SearchByProjection(f, pts, desc, 3.0)

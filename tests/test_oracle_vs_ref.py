@@ -121,3 +121,25 @@ def test_next_rows_equal(oracle_port, oracle_ref):
         d = synth.descriptors(n, n)
         d[n // 2] = d[0]
         assert oracle_ref.distinctive_index(d) == oracle_port.distinctive_index(d)
+
+
+def test_guided_matchers_equal(oracle_port, oracle_ref):
+    """FeaturesGrid, the two SearchByProjection loops, SearchForInitialization and CheckOrientation: the reference text
+    (src/Frame.cc:63-145, src/ORBmatcher.cc:249-382, 614-694, 1279-1362, compiled by line range) against the pass-form restatement
+    whose rounds the GPU executes. Also checks that the cases really exercise the sequential state (rounds > 2, revoked matches)."""
+    import ctypes
+    import guided_cases as gc
+    stat = oracle_port.lib.orc_guided_stat
+    stat.restype, stat.argtypes = ctypes.c_int, [ctypes.c_int]
+    max_rounds, revoked, kinds = 0, 0, set()
+    for name, kind, c in gc.cases():
+        a, b = gc.run_oracle(oracle_ref, kind, c), gc.run_oracle(oracle_port, kind, c)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (name, k)
+        kinds.add(kind)
+        if kind in ('local', 'last'):
+            max_rounds = max(max_rounds, stat(0))
+        if kind == 'init':
+            revoked += stat(1)
+    assert kinds == {'grid', 'local', 'last', 'init'}
+    assert max_rounds >= 12 and revoked > 50, (max_rounds, revoked)
