@@ -405,6 +405,48 @@ def run_b200(args, rank, world, local_rank, emit):
                   'workload': 'C2: 1241x376 stereo, 2000 kp per image, Extract left + right and ComputeStereoMatches, device-resident',
                   'matched_per_pair': matched / SB}
 
+    # ---- guided matchers: one tracking search per call through the C ABI, host buffers in and out. Latency-bound
+    #      (one CTA per search), so it is reported as microseconds per call next to the reference text on one host core.
+    guided = None
+    if rank == 0 and not args.skip_guided:
+        fr = synth.frame(1, n=1000)
+        gf = api.Frame(fr['kps_un'], fr['desc'], fr['scale_factors'], fr['bounds'], fr['uright'], device=local_rank)
+        gpts, gdesc = synth.local_map_points(1, fr, npts=1000)
+        gcp, glp, glpts, gldesc = synth.last_frame_points(1, fr, synth.KITTI_CAMERA, npts=1000)
+        gm = api.ORBmatcher(0.8, True, device=local_rank)
+
+        def g_local():
+            gf.mappoints[:] = -1
+            return gm.SearchByProjection(gf, gpts, gdesc, 3.0)
+
+        def g_last():
+            gf.mappoints[:] = -1
+            return gm.SearchByProjectionLastFrame(gf, synth.KITTI_CAMERA, gcp, glp, glpts, gldesc, 7.0, False)
+
+        def per_call(fn, reps=200):
+            for _ in range(10):
+                fn()
+            t0g = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0g) / reps * 1e6
+        guided = {'workload': '1000 keypoints (640x480), 1000 map points; SearchByProjection for local-map and motion-model tracking',
+                  'unit': 'us per call', 'local_map': per_call(g_local), 'local_map_kernel': gf.last_stats()[1] * 1e3,
+                  'last_frame': per_call(g_last), 'last_frame_kernel': gf.last_stats()[1] * 1e3, 'rounds': gf.last_rounds(),
+                  'frame_assign': per_call(lambda: gf.assign(fr['kps_un'], fr['desc'], fr['scale_factors'], fr['bounds'], fr['uright'])),
+                  'h2d_bytes_per_call': int(gpts.nbytes + gdesc.nbytes + 4 * len(fr['kps_un'])), 'd2h_bytes_per_call': int(4 * len(fr['kps_un']) + 16)}
+        if world == 1 and not args.skip_cpu:
+            try:
+                o, kind, native = load_cpu_reference()
+                mp0 = np.full(len(fr['kps_un']), -1, np.int32)
+                guided['cpu_baseline'] = {
+                    'local_map': o.time_search_local_map(fr, mp0, gpts, gdesc, 3.0, 0.8, 100) * 1e6,
+                    'last_frame': o.time_search_last_frame(fr, synth.KITTI_CAMERA, gcp, glp, mp0, glpts, gldesc, 7.0, False, 0.9, True, 100) * 1e6,
+                    'unit': 'us per call', 'cores': 1, 'kind': kind,
+                    'sample': '100 calls each; Frame, grid and map points built outside the timed region'}
+            except Exception as e:
+                guided['cpu_baseline'] = {'unavailable': str(e)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -441,6 +483,7 @@ def run_b200(args, rank, world, local_rank, emit):
             'cpu_baseline': cpu,
             'knn': knn,
             'stereo': stereo,
+            'guided': guided,
         }
         emit(json.dumps(line))
 
@@ -460,6 +503,7 @@ def main():
     ap.add_argument('--skip-stereo', action='store_true')
     ap.add_argument('--stereo-pairs', type=int, default=64)
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-guided', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 

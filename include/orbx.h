@@ -215,6 +215,8 @@ typedef struct orbx_last_point { float xw[3]; int32_t octave; float angle; int32
  * src/Frame.cc:70-100, built on the device). Not re-entrant, like a Frame that is being matched. */
 typedef struct orbx_frame_s* orbx_frame;
 orbx_status orbx_frame_create(const orbx_frame_view* view, int device, orbx_frame* out);
+/* Re-uses the device buffers of `f` for another frame (Tracking builds one Frame per image): uploads the view, rebuilds the grid. */
+orbx_status orbx_frame_assign(orbx_frame f, const orbx_frame_view* view);
 orbx_status orbx_frame_destroy(orbx_frame f);
 /* The grid as CSR: cell_start has 64*48+1 entries, cell = cx*48 + cy (grid_[cx][cy], include/Frame.h:72-79); items holds the keypoint
  * indices of every cell in push_back order. *n_items = number of keypoints inside the grid. */
@@ -241,8 +243,9 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame cur, const orbx_came
 /* ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:614-694. prev_matched: f1->n (x, y) pairs, in/out; matches12: f1->n, out. */
 orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size,
                                            float nnratio, int check_orientation, int* nmatches);
-/* rounds the last search on `f` needed to reach the sequential result (diagnostic; >= 1) */
-orbx_status orbx_frame_last_rounds(orbx_frame f, int* rounds);
+/* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1) and the kernel's duration (CUDA events).
+ * Either pointer may be NULL. */
+orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms);
 
 /* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
  * `device` (all SMs, register operands). */

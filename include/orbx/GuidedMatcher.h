@@ -1,0 +1,207 @@
+// Drop-in host side for the guided matchers of the reference, forwarding to the C ABI (include/orbx.h):
+//
+//   FeaturesGrid::AssignFeatures / GetFeaturesInArea                       include/Frame.h:61-81,    src/Frame.cc:63-145
+//   int ORBmatcher::SearchByProjection(Frame&, const std::vector<MapPoint*>&, float th)
+//                                                                          include/ORBmatcher.h:58,  src/ORBmatcher.cc:315-382
+//   int ORBmatcher::SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular)
+//                                                                          include/ORBmatcher.h:62,  src/ORBmatcher.cc:1279-1362
+//   int ORBmatcher::SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int windowSize)
+//                                                                          include/ORBmatcher.h:80,  src/ORBmatcher.cc:614-694
+//
+// The methods are templates over the reference's own Frame and MapPoint types: they read exactly the members the reference code
+// reads (frame.keypointsUn, .descriptors, .uright, .mappoints, .outlier, .keypoints, .imageBounds, .pyramid.scaleFactors, .camera,
+// .pose; mappoint->trackInView, trackScaleLevel, trackViewCos, trackProjX/Y/XR, isBad(), Observations(), GetDescriptor(),
+// GetWorldPos()) and write exactly what it writes (frame.mappoints, prevMatched, matches12). The sequential "already matched" state
+// of the loops is reproduced on the GPU, so the results are identical, not approximately equal. No CPU fallback.
+#ifndef ORBX_GUIDEDMATCHER_H
+#define ORBX_GUIDEDMATCHER_H
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include <opencv2/core.hpp>
+
+#include "../orbx.h"
+#include "ORBmatcher.h"
+
+namespace ORB_SLAM2
+{
+namespace b200
+{
+
+// A Frame's matcher-visible data on the GPU, with its FeaturesGrid. Construct it once per Frame (or Assign() a long-lived one to each
+// new Frame: the device buffers are reused) and pass it next to the Frame.
+class DeviceFrame
+{
+public:
+	template <class FrameT> explicit DeviceFrame(const FrameT& frame, int device = 0) : h_(nullptr)
+	{
+		Storage s;
+		const orbx_frame_view v = View(frame, s);
+		Check(orbx_frame_create(&v, device, &h_), "DeviceFrame");
+	}
+	template <class FrameT> void Assign(const FrameT& frame)
+	{
+		Storage s;
+		const orbx_frame_view v = View(frame, s);
+		Check(orbx_frame_assign(h_, &v), "DeviceFrame::Assign");
+	}
+	~DeviceFrame() { orbx_frame_destroy(h_); }
+	DeviceFrame(const DeviceFrame&) = delete;
+	DeviceFrame& operator=(const DeviceFrame&) = delete;
+
+	// FeaturesGrid::GetFeaturesInArea (src/Frame.cc:102-145), same output order. One window per call is a kernel launch; the
+	// matchers below never call it — they enumerate all their windows on the device.
+	std::vector<size_t> GetFeaturesInArea(float x, float y, float r, int minLevel = -1, int maxLevel = -1) const
+	{
+		const float xyr[3] = { x, y, r };
+		const int32_t lv[2] = { minLevel, maxLevel };
+		int32_t off[2] = { 0, 0 };
+		std::vector<int32_t> idx(256);
+		orbx_status st = orbx_frame_features_in_area(h_, xyr, lv, 1, off, idx.data(), (int)idx.size());
+		if (st == ORBX_ERR_CAPACITY)
+		{
+			idx.resize((size_t)off[1]);
+			st = orbx_frame_features_in_area(h_, xyr, lv, 1, off, idx.data(), (int)idx.size());
+		}
+		Check(st, "GetFeaturesInArea");
+		return std::vector<size_t>(idx.begin(), idx.begin() + off[1]);
+	}
+
+	orbx_frame Handle() const { return h_; }
+
+private:
+	struct Storage { cv::Mat desc; };
+	template <class FrameT> static orbx_frame_view View(const FrameT& frame, Storage& s)
+	{
+		static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint layout");
+		orbx_frame_view v;
+		v.n = static_cast<int32_t>(frame.keypointsUn.size());
+		v.kps_un = reinterpret_cast<const orbx_keypoint*>(frame.keypointsUn.data());
+		s.desc = frame.descriptors;
+		if (v.n > 0 && s.desc.step != 32) { cv::Mat c; s.desc.copyTo(c); s.desc = c; }
+		v.desc = s.desc.data;
+		v.uright = frame.uright.size() == frame.keypointsUn.size() && v.n > 0 ? frame.uright.data() : nullptr;
+		v.bounds.minx = frame.imageBounds.minx; v.bounds.maxx = frame.imageBounds.maxx;
+		v.bounds.miny = frame.imageBounds.miny; v.bounds.maxy = frame.imageBounds.maxy;
+		v.nlevels = static_cast<int32_t>(frame.pyramid.scaleFactors.size());
+		v.scale_factors = frame.pyramid.scaleFactors.data();
+		return v;
+	}
+	orbx_frame h_;
+};
+
+class GuidedMatcher
+{
+public:
+	GuidedMatcher(float nnratio = 0.6f, bool checkOri = true) : fNNRatio_(nnratio), checkOrientation_(checkOri) {}
+
+	// src/ORBmatcher.cc:315-382
+	template <class FrameT, class MapPointT>
+	int SearchByProjection(FrameT& frame, DeviceFrame& dev, const std::vector<MapPointT*>& mappoints, float th = 3.f) const
+	{
+		const int npts = static_cast<int>(mappoints.size());
+		std::vector<orbx_track_point> pts((size_t)npts);
+		std::vector<uint8_t> desc((size_t)npts * 32);
+		for (int i = 0; i < npts; i++)
+		{
+			const MapPointT* m = mappoints[i];
+			orbx_track_point& p = pts[i];
+			const bool active = m->trackInView && !m->isBad();                       // :321-322
+			p.proj_x = m->trackProjX; p.proj_y = m->trackProjY; p.proj_xr = m->trackProjXR;
+			p.view_cos = m->trackViewCos; p.scale_level = m->trackScaleLevel;
+			p.flags = (active ? 1 : 0) | (m->Observations() > 0 ? 2 : 0);
+			if (active) std::memcpy(&desc[(size_t)i * 32], m->GetDescriptor().data, 32);
+		}
+		std::vector<int32_t> state = Encode(frame);
+		int nmatches = 0;
+		Check(orbx_search_by_projection_local_map(dev.Handle(), state.data(), pts.data(), desc.data(), npts, th, fNNRatio_, &nmatches),
+			"SearchByProjection");
+		for (size_t c = 0; c < state.size(); c++)
+			if (state[c] >= 0) frame.mappoints[c] = mappoints[(size_t)state[c]];           // :375
+		return nmatches;
+	}
+
+	// src/ORBmatcher.cc:1279-1362
+	template <class FrameT>
+	int SearchByProjection(FrameT& currFrame, DeviceFrame& devCurr, const FrameT& lastFrame, float th, bool monocular) const
+	{
+		const int npts = lastFrame.N;
+		std::vector<orbx_last_point> pts((size_t)npts);
+		std::vector<uint8_t> desc((size_t)npts * 32);
+		for (int i = 0; i < npts; i++)
+		{
+			orbx_last_point& p = pts[i];
+			const auto* m = lastFrame.mappoints[i];
+			p.flags = 0;
+			p.xw[0] = p.xw[1] = p.xw[2] = 0.f;
+			p.octave = lastFrame.keypoints[i].octave;                                 // :1313
+			p.angle = lastFrame.keypointsUn[i].angle;                                 // CheckOrientation, :273
+			if (m && !lastFrame.outlier[i])                                           // :1295-1297
+			{
+				const auto Xw = m->GetWorldPos();
+				p.xw[0] = Xw(0); p.xw[1] = Xw(1); p.xw[2] = Xw(2);
+				p.flags = 1 | (m->Observations() > 0 ? 2 : 0);
+				std::memcpy(&desc[(size_t)i * 32], m->GetDescriptor().data, 32);
+			}
+		}
+		const auto& cam = currFrame.camera;
+		const orbx_camera ocam = { cam.fx, cam.fy, cam.cx, cam.cy, cam.bf, cam.baseline };
+		const orbx_pose cp = Pose(currFrame.pose), lp = Pose(lastFrame.pose);
+		std::vector<int32_t> state = Encode(currFrame);
+		int nmatches = 0;
+		Check(orbx_search_by_projection_last_frame(devCurr.Handle(), &ocam, &cp, &lp, state.data(), pts.data(), desc.data(), npts, th,
+			monocular ? 1 : 0, checkOrientation_ ? 1 : 0, &nmatches), "SearchByProjection");
+		for (size_t c = 0; c < state.size(); c++)
+		{
+			if (state[c] >= 0) currFrame.mappoints[c] = lastFrame.mappoints[(size_t)state[c]];   // :1351
+			else if (state[c] == -1) currFrame.mappoints[c] = nullptr;                           // CheckOrientation, :301
+		}
+		return nmatches;
+	}
+
+	// src/ORBmatcher.cc:614-694
+	template <class FrameT>
+	int SearchForInitialization(FrameT& frame1, DeviceFrame& dev1, FrameT& frame2, DeviceFrame& dev2, std::vector<cv::Point2f>& prevMatched,
+		std::vector<int>& matches12, int windowSize = 10) const
+	{
+		(void)frame2;
+		const size_t n1 = frame1.keypointsUn.size();
+		static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f layout");
+		matches12.assign(n1, -1);
+		if (n1 == 0) return 0;
+		int nmatches = 0;
+		Check(orbx_search_for_initialization(dev1.Handle(), dev2.Handle(), reinterpret_cast<float*>(prevMatched.data()), matches12.data(), windowSize,
+			fNNRatio_, checkOrientation_ ? 1 : 0, &nmatches), "SearchForInitialization");
+		return nmatches;
+	}
+
+private:
+	// frame.mappoints as the C ABI's codes: -1 null, -2 / -3 a map point with / without observations
+	template <class FrameT> static std::vector<int32_t> Encode(const FrameT& frame)
+	{
+		std::vector<int32_t> code(frame.mappoints.size());
+		for (size_t c = 0; c < code.size(); c++)
+			code[c] = !frame.mappoints[c] ? -1 : (frame.mappoints[c]->Observations() > 0 ? -2 : -3);
+		return code;
+	}
+	template <class PoseT> static orbx_pose Pose(const PoseT& pose)
+	{
+		orbx_pose p;
+		for (int i = 0; i < 3; i++)
+		{
+			for (int j = 0; j < 3; j++) p.R[i * 3 + j] = pose.R()(i, j);
+			p.t[i] = pose.t()(i);
+		}
+		return p;
+	}
+
+	float fNNRatio_;
+	bool checkOrientation_;
+};
+
+} // namespace b200
+} // namespace ORB_SLAM2
+
+#endif

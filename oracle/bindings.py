@@ -100,6 +100,9 @@ class Oracle:
         f('search_local_map', C.c_int, [C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float])
         f('search_last_frame', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.POINTER(Pose), C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int])
+        f('time_search_local_map', C.c_double, [C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int])
+        f('time_search_last_frame', C.c_double, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.POINTER(Pose), C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
@@ -240,6 +243,34 @@ class Oracle:
         n = self._search_last_frame(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(poses[0]), C.byref(poses[1]), _p(mp),
                                     _p(pts), _p(pt_desc), len(pts), th, int(monocular), nnratio, int(check_orientation))
         return n, mp
+
+    @staticmethod
+    def _poses(cur_pose, last_pose):
+        poses = []
+        for R, t in (cur_pose, last_pose):
+            P = Pose()
+            P.R[:] = [float(x) for x in np.asarray(R, np.float32).reshape(9)]
+            P.t[:] = [float(x) for x in np.asarray(t, np.float32).reshape(3)]
+            poses.append(P)
+        return poses
+
+    def time_search_local_map(self, frame, frame_mp, pts, pt_desc, th=3.0, nnratio=0.8, reps=20):
+        """Mean seconds per SearchByProjection(Frame&, mappoints, th) call on one host core, Frame and grid built outside the timed region."""
+        v, keep = self._frame_view(frame)
+        mp = np.ascontiguousarray(frame_mp, np.int32)
+        pts = np.ascontiguousarray(pts).view(TRACK_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        return self._time_search_local_map(C.byref(v), _p(mp), _p(pts), _p(pt_desc), len(pts), th, nnratio, reps)
+
+    def time_search_last_frame(self, frame, cam, cur_pose, last_pose, frame_mp, pts, pt_desc, th=15.0, monocular=False, nnratio=0.9,
+                               check_orientation=True, reps=20):
+        v, keep = self._frame_view(frame)
+        mp = np.ascontiguousarray(frame_mp, np.int32)
+        pts = np.ascontiguousarray(pts).view(LAST_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        poses = self._poses(cur_pose, last_pose)
+        return self._time_search_last_frame(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(poses[0]), C.byref(poses[1]),
+                                            _p(mp), _p(pts), _p(pt_desc), len(pts), th, int(monocular), nnratio, int(check_orientation), reps)
 
     def search_for_initialization(self, f1, f2, prev_matched, window=100, nnratio=0.9, check_orientation=True):
         v1, k1 = self._frame_view(f1)

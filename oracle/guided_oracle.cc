@@ -17,6 +17,8 @@
 #define ORACLE_PREFIX orc_
 #include "oracle_api.h"
 
+#include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -234,10 +236,9 @@ int orc_grid_query(void* g, float x, float y, float r, int min_level, int max_le
 	return n;
 }
 
-int orc_search_local_map(const oracle_frame_view* f, int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc, int npts, float th,
-                         float nnratio)
+static int search_local_map(const Grid& g, const oracle_frame_view* f, int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc,
+                            int npts, float th, float nnratio)
 {
-	const Grid g = make_grid(f);
 	std::vector<Probe> probes((size_t)npts);
 	for (int i = 0; i < npts; i++)
 	{
@@ -259,12 +260,10 @@ int orc_search_local_map(const oracle_frame_view* f, int32_t* frame_mp, const or
 	});
 }
 
-int orc_search_last_frame(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* cp, const oracle_pose* lp, int32_t* frame_mp,
-                          const oracle_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular, float nnratio,
-                          int check_ori)
+static int search_last_frame(const Grid& g, const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* cp, const oracle_pose* lp,
+                             int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular,
+                             int check_ori)
 {
-	(void)nnratio;
-	const Grid g = make_grid(f);
 	// tlc = Rlw * (-Rcw^T * tcw) + tlw (:1286); every product accumulates from 0 in k order like cv::Matx
 	float twc[3], tlc[3];
 	for (int i = 0; i < 3; i++)
@@ -318,6 +317,55 @@ int orc_search_last_frame(const oracle_frame_view* f, const oracle_camera* cam, 
 	const int kept = check_orientation(matches, &pts[0].angle, sizeof(oracle_last_point), &f->kps_un[0].angle, sizeof(oracle_keypoint), erased);
 	for (int i2 : erased) frame_mp[i2] = -1;
 	return kept;
+}
+
+int orc_search_local_map(const oracle_frame_view* f, int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc, int npts, float th,
+                         float nnratio)
+{
+	return search_local_map(make_grid(f), f, frame_mp, pts, pt_desc, npts, th, nnratio);
+}
+
+int orc_search_last_frame(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* cp, const oracle_pose* lp, int32_t* frame_mp,
+                          const oracle_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular, float nnratio,
+                          int check_ori)
+{
+	(void)nnratio;
+	return search_last_frame(make_grid(f), f, cam, cp, lp, frame_mp, pts, pt_desc, npts, th, monocular, check_ori);
+}
+
+// timing of the restatement (the grid is built once, outside the timed region); see oracle_api.h
+double orc_time_search_local_map(const oracle_frame_view* f, const int32_t* frame_mp, const oracle_track_point* pts, const uint8_t* pt_desc,
+                                 int npts, float th, float nnratio, int reps)
+{
+	const Grid g = make_grid(f);
+	std::vector<int32_t> mp((size_t)f->n);
+	double total = 0;
+	for (int r = 0; r < reps; r++)
+	{
+		std::copy(frame_mp, frame_mp + f->n, mp.begin());
+		const auto t0 = std::chrono::steady_clock::now();
+		search_local_map(g, f, mp.data(), pts, pt_desc, npts, th, nnratio);
+		total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	return total / (reps > 0 ? reps : 1);
+}
+
+double orc_time_search_last_frame(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* cp, const oracle_pose* lp,
+                                  const int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc, int npts, float th, int monocular,
+                                  float nnratio, int check_ori, int reps)
+{
+	(void)nnratio;
+	const Grid g = make_grid(f);
+	std::vector<int32_t> mp((size_t)f->n);
+	double total = 0;
+	for (int r = 0; r < reps; r++)
+	{
+		std::copy(frame_mp, frame_mp + f->n, mp.begin());
+		const auto t0 = std::chrono::steady_clock::now();
+		search_last_frame(g, f, cam, cp, lp, mp.data(), pts, pt_desc, npts, th, monocular, check_ori);
+		total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	return total / (reps > 0 ? reps : 1);
 }
 
 int orc_search_for_initialization(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev, int32_t* matches12, int window,

@@ -128,6 +128,14 @@ int ORACLE_FN(search_local_map)(const oracle_frame_view* frame, int32_t* frame_m
 int ORACLE_FN(search_last_frame)(const oracle_frame_view* cur, const oracle_camera* cam, const oracle_pose* cur_pose,
                                  const oracle_pose* last_pose, int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc,
                                  int npts, float th, int monocular, float nnratio, int check_orientation);
+// CPU-baseline timing of the two tracking searches: the Frame (grid included) and the map points are built once, outside the timed
+// region; each repetition restores frame.mappoints and times the matcher call alone. Returns mean seconds per call.
+double ORACLE_FN(time_search_local_map)(const oracle_frame_view* frame, const int32_t* frame_mp, const oracle_track_point* pts,
+                                        const uint8_t* pt_desc, int npts, float th, float nnratio, int reps);
+double ORACLE_FN(time_search_last_frame)(const oracle_frame_view* cur, const oracle_camera* cam, const oracle_pose* cur_pose,
+                                         const oracle_pose* last_pose, const int32_t* frame_mp, const oracle_last_point* pts,
+                                         const uint8_t* pt_desc, int npts, float th, int monocular, float nnratio, int check_orientation,
+                                         int reps);
 // prev_matched: n1 x 2 floats in/out; matches12: n1 out
 int ORACLE_FN(search_for_initialization)(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev_matched, int32_t* matches12,
                                          int window, float nnratio, int check_orientation);

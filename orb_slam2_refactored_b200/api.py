@@ -116,7 +116,8 @@ _SIGNATURES = {
                                                        C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_for_initialization': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
                                                  C.POINTER(C.c_int)]),
-    'orbx_frame_last_rounds': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
 }
 
 
@@ -356,6 +357,13 @@ class Frame:
     point with / without observations."""
 
     def __init__(self, keypointsUn, descriptors, scaleFactors, imageBounds, uright=None, device=0):
+        self._h = None
+        view = self._view(keypointsUn, descriptors, scaleFactors, imageBounds, uright)
+        h = C.c_void_p()
+        _check(lib().orbx_frame_create(C.byref(view), device, C.byref(h)))
+        self._h = h
+
+    def _view(self, keypointsUn, descriptors, scaleFactors, imageBounds, uright):
         self.keypointsUn = np.ascontiguousarray(keypointsUn).view(KP_DTYPE)
         self.descriptors = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
         self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
@@ -363,12 +371,14 @@ class Frame:
         self.imageBounds = tuple(float(np.float32(b)) for b in imageBounds)     # (minx, maxx, miny, maxy)
         self.N = len(self.keypointsUn)
         self.mappoints = np.full(self.N, -1, np.int32)
-        view = _FrameView(self.N, self.keypointsUn.ctypes.data, self.descriptors.ctypes.data,
+        return _FrameView(self.N, self.keypointsUn.ctypes.data, self.descriptors.ctypes.data,
                           None if self.uright is None else self.uright.ctypes.data, _Bounds(*self.imageBounds), len(self.scaleFactors),
                           self.scaleFactors.ctypes.data)
-        h = C.c_void_p()
-        _check(lib().orbx_frame_create(C.byref(view), device, C.byref(h)))
-        self._h = h
+
+    def assign(self, keypointsUn, descriptors, scaleFactors, imageBounds, uright=None):
+        """The next image's Frame in the same device buffers (Tracking constructs one Frame per image)."""
+        view = self._view(keypointsUn, descriptors, scaleFactors, imageBounds, uright)
+        _check(lib().orbx_frame_assign(self._h, C.byref(view)))
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -402,9 +412,13 @@ class Frame:
         return [idx[off[i]:off[i + 1]].copy() for i in range(len(q))]
 
     def last_rounds(self):
-        n = C.c_int()
-        _check(lib().orbx_frame_last_rounds(self._h, C.byref(n)))
-        return n.value
+        return self.last_stats()[0]
+
+    def last_stats(self):
+        """(rounds, kernel milliseconds) of the last search on this frame."""
+        n, ms = C.c_int(), C.c_float()
+        _check(lib().orbx_frame_last_stats(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
 
 def _pose(p):

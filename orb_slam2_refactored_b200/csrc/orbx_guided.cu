@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -57,7 +58,7 @@ struct GuidedArgs
 	const orbx_track_point* tp;
 	const orbx_last_point* lp;
 	const orbx_keypoint* kps1;   // INIT: frame 1
-	float* prev;                 // INIT: prevMatched, in/out
+	float* prev;                 // INIT: prevMatched, out
 	const uint8_t* pt_desc;
 	float th, nnratio, radius;
 	float fx, fy, cx, cy, bf;
@@ -74,7 +75,9 @@ struct GuidedArgs
 	int* owner;
 	// candidate lists
 	uint32_t* list; int* entry_pt; int cap;
-	int32_t* frame_mp;           // in/out (LOCAL_MAP, LAST_FRAME); INIT: matches12 out [npts]
+	const int32_t* mp_in;        // frame.mappoints on entry (LOCAL_MAP, LAST_FRAME)
+	const float* prev_in;        // INIT: prevMatched on entry
+	int32_t* frame_mp;           // out: frame.mappoints (LOCAL_MAP, LAST_FRAME); INIT: matches12 [npts]
 	int* result;                 // [0] nmatches, [1] entries, [2] rounds, [3] overflow
 };
 
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		{
 			if (!(A.kps1[i].octave > 0))                                       // :629-631
 			{
-				u = A.prev[2 * i]; v = A.prev[2 * i + 1];
+				u = A.prev_in[2 * i]; v = A.prev_in[2 * i + 1];
 				radius = A.radius;
 				lv = pack_levels(0, 0);                                           // :637
 			}
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		{
 			for (int c = tid; c < n2; c += G_THREADS)
 			{
-				const int m = A.frame_mp[c];
+				const int m = A.mp_in[c];
 				const bool closed = m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
 				A.owner[c] = closed ? -1 : INT_MAX;
 			}
@@ -444,8 +447,7 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		}
 		if (mine) atomicAdd(&s_count, mine);
 		__syncthreads();
-		for (int c = tid; c < n2; c += G_THREADS)
-			if (A.owner[c] >= 0) A.frame_mp[c] = A.owner[c];
+		for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = A.owner[c] >= 0 ? A.owner[c] : A.mp_in[c];
 		__syncthreads();
 		int nmatches = s_count;
 		if (A.mode == MODE_LAST_FRAME && A.check_ori)
@@ -527,7 +529,8 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 	for (int i = tid; i < npts; i += G_THREADS)
 	{
 		const int c = A.frame_mp[i];
-		if (c >= 0) { A.prev[2 * i] = A.kps2[c].x; A.prev[2 * i + 1] = A.kps2[c].y; }   // :689-691
+		A.prev[2 * i] = c >= 0 ? A.kps2[c].x : A.prev_in[2 * i];                          // :689-691
+		A.prev[2 * i + 1] = c >= 0 ? A.kps2[c].y : A.prev_in[2 * i + 1];
 	}
 	if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
 }
@@ -569,20 +572,45 @@ struct orbx_frame_s
 	float invW = 0.f, invH = 0.f;
 	float sf[16] = {};
 	cudaStream_t st = nullptr;
-	int* h_res = nullptr;        // pinned: nmatches, entries, rounds, overflow
 	int last_rounds = 0;
+	float last_kernel_ms = 0.f;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// one pinned staging buffer each way: a search is one H2D copy, one kernel, one D2H copy
+	uint8_t* h_in = nullptr; size_t h_in_cap = 0;
+	uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+	GBuf<uint8_t> d_in, d_out;
 	GBuf<orbx_keypoint> kps;
 	GBuf<uint8_t> desc;
 	GBuf<float> uright;
 	GBuf<int> cell_start, cell_of;
 	GBuf<int4> rec;
 	// per-search scratch
-	GBuf<uint8_t> pts, pt_desc;
 	GBuf<float> pf;
-	GBuf<int> pi, owner, entry_pt, res, mp;
+	GBuf<int> pi, owner, entry_pt;
 	GBuf<uint32_t> list;
-	GBuf<float> prev, qf;
+	GBuf<float> qf;
 	GBuf<int> qi, qoff, qidx;
+
+	cudaError_t ensure_staging(size_t in_bytes, size_t out_bytes)
+	{
+		cudaError_t e;
+		if (in_bytes > h_in_cap)
+		{
+			if (h_in) cudaFreeHost(h_in);
+			h_in = nullptr; h_in_cap = 0;
+			if ((e = cudaMallocHost(&h_in, in_bytes * 2)) != cudaSuccess) return e;
+			h_in_cap = in_bytes * 2;
+		}
+		if (out_bytes > h_out_cap)
+		{
+			if (h_out) cudaFreeHost(h_out);
+			h_out = nullptr; h_out_cap = 0;
+			if ((e = cudaMallocHost(&h_out, out_bytes * 2)) != cudaSuccess) return e;
+			h_out_cap = out_bytes * 2;
+		}
+		if ((e = d_in.ensure(in_bytes)) != cudaSuccess) return e;
+		return d_out.ensure(out_bytes);
+	}
 
 	GridDev grid() const
 	{
@@ -593,28 +621,43 @@ struct orbx_frame_s
 	}
 	~orbx_frame_s()
 	{
-		if (h_res) cudaFreeHost(h_res);
+		if (h_in) cudaFreeHost(h_in);
+		if (h_out) cudaFreeHost(h_out);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
 		if (st) cudaStreamDestroy(st);
 	}
 };
 
 namespace {
 
+inline size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Layout of one search in the staging buffers. Input: [points | point descriptors | frame_mp or prevMatched]; output:
+// [result (4 ints) | frame_mp / matches12 | prevMatched]. One copy each way.
+struct Staging
+{
+	size_t in_pts = 0, in_desc = 0, in_state = 0, in_bytes = 0;
+	size_t out_res = 0, out_mp = 0, out_prev = 0, out_bytes = 0;
+};
+
 // fills the frame part and the scratch pointers of the kernel arguments; npts-sized scratch is carved from f->pf / f->pi
-orbx_status prepare(orbx_frame_s* f, int npts, GuidedArgs& A)
+orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_bytes, size_t state_bytes, size_t mp_entries, size_t prev_bytes,
+                    GuidedArgs& A, Staging& S)
 {
 	GCU(cudaSetDevice(f->device));
 	GCU(f->pf.ensure((size_t)npts * 4 + 4));
 	GCU(f->pi.ensure((size_t)npts * 6 + 8));
 	GCU(f->owner.ensure((size_t)f->n + 1));
-	GCU(f->res.ensure(4));
-	GCU(f->mp.ensure((size_t)std::max(f->n, npts) + 1));
 	const size_t want = (size_t)npts * 48 + 4096;
 	if (f->list.n < want)
 	{
 		GCU(f->list.ensure(want));
 		GCU(f->entry_pt.ensure(want));
 	}
+	S.in_pts = 0; S.in_desc = up16(pts_bytes); S.in_state = S.in_desc + up16(desc_bytes); S.in_bytes = S.in_state + up16(state_bytes) + 16;
+	S.out_res = 0; S.out_mp = 16; S.out_prev = S.out_mp + up16(mp_entries * sizeof(int)); S.out_bytes = S.out_prev + up16(prev_bytes) + 16;
+	GCU(f->ensure_staging(S.in_bytes, S.out_bytes));
 	A.G = f->grid();
 	A.kps2 = f->kps.p; A.desc2 = f->desc.p; A.uright2 = f->uright.p;
 	for (int i = 0; i < 16; i++) A.sf[i] = f->sf[i];
@@ -624,9 +667,9 @@ orbx_status prepare(orbx_frame_s* f, int npts, GuidedArgs& A)
 	A.next = A.aux1 + npts;
 	A.owner = f->owner.p;
 	A.list = f->list.p; A.entry_pt = f->entry_pt.p; A.cap = (int)std::min(f->list.n, f->entry_pt.n);
-	A.frame_mp = f->mp.p;
-	A.result = f->res.p;
-	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr;
+	A.result = reinterpret_cast<int*>(f->d_out.p + S.out_res);
+	A.frame_mp = reinterpret_cast<int32_t*>(f->d_out.p + S.out_mp);
+	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr; A.mp_in = nullptr; A.prev_in = nullptr;
 	A.th = 0.f; A.nnratio = 0.f; A.radius = 0.f; A.fx = A.fy = A.cx = A.cy = A.bf = 0.f;
 	for (int i = 0; i < 9; i++) A.R[i] = 0.f;
 	for (int i = 0; i < 3; i++) A.t[i] = 0.f;
@@ -634,24 +677,80 @@ orbx_status prepare(orbx_frame_s* f, int npts, GuidedArgs& A)
 	return ORBX_OK;
 }
 
-// launches the search; grows the candidate arrays and repeats when they were too small. The inputs must already be on the device.
-orbx_status run_search(orbx_frame_s* f, GuidedArgs& A, int* nmatches)
+// One H2D copy of the staged inputs, the search, one D2H copy of the staged outputs. Grows the candidate arrays and repeats when they
+// were too small (the kernel has not touched its outputs then).
+orbx_status run_search(orbx_frame_s* f, GuidedArgs& A, const Staging& S, int* nmatches)
 {
 	for (int attempt = 0; attempt < 2; attempt++)
 	{
+		if (attempt == 0) GCU(cudaMemcpyAsync(f->d_in.p, f->h_in, S.in_bytes, cudaMemcpyHostToDevice, f->st));
+		GCU(cudaEventRecord(f->ev0, f->st));
 		k_guided_search<<<1, G_THREADS, 0, f->st>>>(A);
 		GCU(cudaGetLastError());
-		GCU(cudaMemcpyAsync(f->h_res, f->res.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
+		GCU(cudaEventRecord(f->ev1, f->st));
+		GCU(cudaMemcpyAsync(f->h_out, f->d_out.p, S.out_bytes, cudaMemcpyDeviceToHost, f->st));
 		GCU(cudaStreamSynchronize(f->st));
-		if (!f->h_res[3]) break;
+		const int* res = reinterpret_cast<const int*>(f->h_out + S.out_res);
+		if (!res[3]) break;
 		if (attempt == 1) return orbx_fail(ORBX_ERR_CUDA, "candidate list overflow after regrowth");
-		// INIT mode is restartable because prev/choice are only written after the overflow check
-		GCU(f->list.ensure((size_t)f->h_res[1] + 1024));
-		GCU(f->entry_pt.ensure((size_t)f->h_res[1] + 1024));
+		GCU(f->list.ensure((size_t)res[1] + 1024));
+		GCU(f->entry_pt.ensure((size_t)res[1] + 1024));
 		A.list = f->list.p; A.entry_pt = f->entry_pt.p; A.cap = (int)std::min(f->list.n, f->entry_pt.n);
 	}
-	f->last_rounds = f->h_res[2];
-	if (nmatches) *nmatches = f->h_res[0];
+	const int* res = reinterpret_cast<const int*>(f->h_out + S.out_res);
+	f->last_rounds = res[2];
+	cudaEventElapsedTime(&f->last_kernel_ms, f->ev0, f->ev1);
+	if (nmatches) *nmatches = res[0];
+	return ORBX_OK;
+}
+
+// uploads a frame view into `f` (buffers grow as needed) and rebuilds the grid
+orbx_status assign_frame(orbx_frame_s* f, const orbx_frame_view* v)
+{
+	GCU(cudaSetDevice(f->device));
+	f->n = v->n; f->nlevels = v->nlevels; f->b = v->bounds;
+	f->invW = GRID_COLS / (v->bounds.maxx - v->bounds.minx);   // src/Frame.cc:73-74
+	f->invH = GRID_ROWS / (v->bounds.maxy - v->bounds.miny);
+	for (int i = 0; i < 16; i++) f->sf[i] = i < v->nlevels ? v->scale_factors[i] : 0.f;
+	const size_t n = (size_t)std::max(v->n, 1);
+	GCU(f->kps.ensure(n));
+	GCU(f->desc.ensure(n * 32));
+	GCU(f->uright.ensure(n));
+	GCU(f->cell_start.ensure(GRID_CELLS + 1));
+	GCU(f->cell_of.ensure(n));
+	GCU(f->rec.ensure(n));
+	// one staged copy: [keypoints | descriptors | uright]
+	const size_t o_desc = up16((size_t)v->n * sizeof(orbx_keypoint)), o_ur = o_desc + up16((size_t)v->n * 32);
+	const size_t bytes = o_ur + up16((size_t)v->n * sizeof(float)) + 16;
+	GCU(f->ensure_staging(bytes, 64));
+	if (v->n > 0)
+	{
+		memcpy(f->h_in, v->kps_un, (size_t)v->n * sizeof(orbx_keypoint));
+		memcpy(f->h_in + o_desc, v->desc, (size_t)v->n * 32);
+		float* ur = reinterpret_cast<float*>(f->h_in + o_ur);
+		if (v->uright) memcpy(ur, v->uright, (size_t)v->n * sizeof(float));
+		else for (int i = 0; i < v->n; i++) ur[i] = -1.f;   // a monocular Frame: uright = -1 everywhere (src/Frame.cc, monocular constructor)
+		GCU(cudaMemcpyAsync(f->d_in.p, f->h_in, bytes, cudaMemcpyHostToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->kps.p, f->d_in.p, (size_t)v->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->desc.p, f->d_in.p + o_desc, (size_t)v->n * 32, cudaMemcpyDeviceToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->uright.p, f->d_in.p + o_ur, (size_t)v->n * sizeof(float), cudaMemcpyDeviceToDevice, f->st));
+	}
+	k_grid_build<<<1, G_THREADS, 0, f->st>>>(f->kps.p, f->n, f->b, f->invW, f->invH, f->cell_start.p, f->rec.p, f->cell_of.p);
+	GCU(cudaGetLastError());
+	GCU(cudaStreamSynchronize(f->st));
+	return ORBX_OK;
+}
+
+orbx_status check_view(const orbx_frame_view* v)
+{
+	if (!v) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	if (v->n < 0 || (v->n > 0 && (!v->kps_un || !v->desc))) return orbx_fail(ORBX_ERR_INVALID, "frame without keypoints/descriptors");
+	if (v->n >= (1 << E_IDX_BITS)) return orbx_fail(ORBX_ERR_INVALID, "more than 524287 keypoints in a frame");
+	if (v->nlevels < 1 || v->nlevels > 16 || !v->scale_factors) return orbx_fail(ORBX_ERR_INVALID, "nlevels must be in [1, 16]");
+	if (!(v->bounds.maxx > v->bounds.minx) || !(v->bounds.maxy > v->bounds.miny))
+		return orbx_fail(ORBX_ERR_INVALID, "empty image bounds (the reference divides by zero, src/Frame.cc:73-74)");
+	for (int i = 0; i < v->n; i++)
+		if (v->kps_un[i].octave < 0 || v->kps_un[i].octave >= 16) return orbx_fail(ORBX_ERR_INVALID, "keypoint octave outside [0, 16)");
 	return ORBX_OK;
 }
 
@@ -661,53 +760,34 @@ extern "C" {
 
 orbx_status orbx_frame_create(const orbx_frame_view* v, int device, orbx_frame* out)
 {
-	if (!v || !out) return orbx_fail(ORBX_ERR_INVALID, "null argument");
-	if (v->n < 0 || (v->n > 0 && (!v->kps_un || !v->desc))) return orbx_fail(ORBX_ERR_INVALID, "frame without keypoints/descriptors");
-	if (v->n >= (1 << E_IDX_BITS)) return orbx_fail(ORBX_ERR_INVALID, "more than 524287 keypoints in a frame");
-	if (v->nlevels < 1 || v->nlevels > 16 || !v->scale_factors) return orbx_fail(ORBX_ERR_INVALID, "nlevels must be in [1, 16]");
-	if (!(v->bounds.maxx > v->bounds.minx) || !(v->bounds.maxy > v->bounds.miny))
-		return orbx_fail(ORBX_ERR_INVALID, "empty image bounds (the reference divides by zero, src/Frame.cc:73-74)");
-	for (int i = 0; i < v->n; i++)
-		if (v->kps_un[i].octave < 0 || v->kps_un[i].octave >= 16) return orbx_fail(ORBX_ERR_INVALID, "keypoint octave outside [0, 16)");
+	if (!out) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	if (orbx_status s = check_view(v)) return s;
 	const char* why = nullptr;
 	if (!orbx_device_usable(device, &why)) return orbx_fail(ORBX_ERR_CUDA, why);
 	GCU(cudaSetDevice(device));
 	orbx_frame_s* f = new orbx_frame_s;
 	f->device = device;
-	f->n = v->n; f->nlevels = v->nlevels; f->b = v->bounds;
-	f->invW = GRID_COLS / (v->bounds.maxx - v->bounds.minx);   // src/Frame.cc:73-74
-	f->invH = GRID_ROWS / (v->bounds.maxy - v->bounds.miny);
-	for (int i = 0; i < 16; i++) f->sf[i] = i < v->nlevels ? v->scale_factors[i] : 0.f;
-	auto bail = [&](cudaError_t e, const char* what) {
-		delete f;
-		return orbx_fail(ORBX_ERR_CUDA, (std::string(what) + ": " + cudaGetErrorString(e)).c_str());
-	};
 	cudaError_t e;
-	if ((e = cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-	if ((e = cudaMallocHost(&f->h_res, 4 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMallocHost");
-	const size_t n = (size_t)std::max(v->n, 1);
-	if ((e = f->kps.ensure(n)) != cudaSuccess || (e = f->desc.ensure(n * 32)) != cudaSuccess || (e = f->uright.ensure(n)) != cudaSuccess ||
-	    (e = f->cell_start.ensure(GRID_CELLS + 1)) != cudaSuccess || (e = f->cell_of.ensure(n)) != cudaSuccess || (e = f->rec.ensure(n)) != cudaSuccess)
-		return bail(e, "cudaMalloc");
-	if (v->n > 0)
+	if ((e = cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&f->ev0)) != cudaSuccess ||
+	    (e = cudaEventCreate(&f->ev1)) != cudaSuccess)
 	{
-		if ((e = cudaMemcpyAsync(f->kps.p, v->kps_un, (size_t)v->n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, f->st)) != cudaSuccess ||
-		    (e = cudaMemcpyAsync(f->desc.p, v->desc, (size_t)v->n * 32, cudaMemcpyHostToDevice, f->st)) != cudaSuccess)
-			return bail(e, "cudaMemcpyAsync");
-		if (v->uright)
-			e = cudaMemcpyAsync(f->uright.p, v->uright, (size_t)v->n * sizeof(float), cudaMemcpyHostToDevice, f->st);
-		else
-		{
-			std::vector<float> neg((size_t)v->n, -1.f);   // a monocular Frame: uright = -1 everywhere (src/Frame.cc, monocular constructor)
-			e = cudaMemcpyAsync(f->uright.p, neg.data(), (size_t)v->n * sizeof(float), cudaMemcpyHostToDevice, f->st);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(f->st);
-		}
-		if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+		delete f;
+		return orbx_fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
 	}
-	k_grid_build<<<1, G_THREADS, 0, f->st>>>(f->kps.p, f->n, f->b, f->invW, f->invH, f->cell_start.p, f->rec.p, f->cell_of.p);
-	if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(f->st)) != cudaSuccess) return bail(e, "k_grid_build");
+	if (orbx_status s = assign_frame(f, v))
+	{
+		delete f;
+		return s;
+	}
 	*out = f;
 	return ORBX_OK;
+}
+
+orbx_status orbx_frame_assign(orbx_frame f, const orbx_frame_view* v)
+{
+	if (!f) return orbx_fail(ORBX_ERR_INVALID, "null handle");
+	if (orbx_status s = check_view(v)) return s;
+	return assign_frame(f, v);
 }
 
 orbx_status orbx_frame_destroy(orbx_frame f)
@@ -763,21 +843,22 @@ orbx_status orbx_search_by_projection_local_map(orbx_frame f, int32_t* frame_mp,
 	for (int c = 0; c < f->n; c++)
 		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
 	GuidedArgs A;
-	if (orbx_status s = prepare(f, npts, A)) return s;
-	GCU(f->pts.ensure((size_t)npts * sizeof(orbx_track_point) + 16));
-	GCU(f->pt_desc.ensure((size_t)npts * 32 + 32));
+	Staging S;
+	const size_t pts_bytes = (size_t)npts * sizeof(orbx_track_point), mp_bytes = (size_t)f->n * sizeof(int);
+	if (orbx_status s = prepare(f, npts, pts_bytes, (size_t)npts * 32, mp_bytes, (size_t)f->n, 0, A, S)) return s;
 	if (npts)
 	{
-		GCU(cudaMemcpyAsync(f->pts.p, pts, (size_t)npts * sizeof(orbx_track_point), cudaMemcpyHostToDevice, f->st));
-		GCU(cudaMemcpyAsync(f->pt_desc.p, pt_desc, (size_t)npts * 32, cudaMemcpyHostToDevice, f->st));
+		memcpy(f->h_in + S.in_pts, pts, pts_bytes);
+		memcpy(f->h_in + S.in_desc, pt_desc, (size_t)npts * 32);
 	}
-	if (f->n) GCU(cudaMemcpyAsync(f->mp.p, frame_mp, (size_t)f->n * sizeof(int), cudaMemcpyHostToDevice, f->st));
+	if (f->n) memcpy(f->h_in + S.in_state, frame_mp, mp_bytes);
 	A.mode = MODE_LOCAL_MAP;
-	A.tp = reinterpret_cast<const orbx_track_point*>(f->pts.p);
-	A.pt_desc = f->pt_desc.p;
+	A.tp = reinterpret_cast<const orbx_track_point*>(f->d_in.p + S.in_pts);
+	A.pt_desc = f->d_in.p + S.in_desc;
+	A.mp_in = reinterpret_cast<const int32_t*>(f->d_in.p + S.in_state);
 	A.th = th; A.nnratio = nnratio;
-	if (orbx_status s = run_search(f, A, nmatches)) return s;
-	if (f->n) GCU(cudaMemcpy(frame_mp, f->mp.p, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost));
+	if (orbx_status s = run_search(f, A, S, nmatches)) return s;
+	if (f->n) memcpy(frame_mp, f->h_out + S.out_mp, mp_bytes);
 	return ORBX_OK;
 }
 
@@ -792,18 +873,19 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame f, const orbx_camera
 	for (int c = 0; c < f->n; c++)
 		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
 	GuidedArgs A;
-	if (orbx_status s = prepare(f, npts, A)) return s;
-	GCU(f->pts.ensure((size_t)npts * sizeof(orbx_last_point) + 16));
-	GCU(f->pt_desc.ensure((size_t)npts * 32 + 32));
+	Staging S;
+	const size_t pts_bytes = (size_t)npts * sizeof(orbx_last_point), mp_bytes = (size_t)f->n * sizeof(int);
+	if (orbx_status s = prepare(f, npts, pts_bytes, (size_t)npts * 32, mp_bytes, (size_t)f->n, 0, A, S)) return s;
 	if (npts)
 	{
-		GCU(cudaMemcpyAsync(f->pts.p, pts, (size_t)npts * sizeof(orbx_last_point), cudaMemcpyHostToDevice, f->st));
-		GCU(cudaMemcpyAsync(f->pt_desc.p, pt_desc, (size_t)npts * 32, cudaMemcpyHostToDevice, f->st));
+		memcpy(f->h_in + S.in_pts, pts, pts_bytes);
+		memcpy(f->h_in + S.in_desc, pt_desc, (size_t)npts * 32);
 	}
-	if (f->n) GCU(cudaMemcpyAsync(f->mp.p, frame_mp, (size_t)f->n * sizeof(int), cudaMemcpyHostToDevice, f->st));
+	if (f->n) memcpy(f->h_in + S.in_state, frame_mp, mp_bytes);
 	A.mode = MODE_LAST_FRAME;
-	A.lp = reinterpret_cast<const orbx_last_point*>(f->pts.p);
-	A.pt_desc = f->pt_desc.p;
+	A.lp = reinterpret_cast<const orbx_last_point*>(f->d_in.p + S.in_pts);
+	A.pt_desc = f->d_in.p + S.in_desc;
+	A.mp_in = reinterpret_cast<const int32_t*>(f->d_in.p + S.in_state);
 	A.th = th;
 	A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
 	for (int i = 0; i < 9; i++) A.R[i] = cp->R[i];
@@ -825,8 +907,8 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame f, const orbx_camera
 	A.forward = tlc2 > cam->baseline && !monocular;      // :1287-1288
 	A.backward = -tlc2 > cam->baseline && !monocular;
 	A.check_ori = check_orientation != 0;
-	if (orbx_status s = run_search(f, A, nmatches)) return s;
-	if (f->n) GCU(cudaMemcpy(frame_mp, f->mp.p, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost));
+	if (orbx_status s = run_search(f, A, S, nmatches)) return s;
+	if (f->n) memcpy(frame_mp, f->h_out + S.out_mp, mp_bytes);
 	return ORBX_OK;
 }
 
@@ -837,29 +919,32 @@ orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* 
 	if (f1->device != f2->device) return orbx_fail(ORBX_ERR_INVALID, "frames live on different devices");
 	const int npts = f1->n;
 	GuidedArgs A;
-	if (orbx_status s = prepare(f2, npts, A)) return s;
-	GCU(f2->prev.ensure((size_t)npts * 2 + 2));
-	if (npts) GCU(cudaMemcpyAsync(f2->prev.p, prev_matched, (size_t)npts * 2 * sizeof(float), cudaMemcpyHostToDevice, f2->st));
+	Staging S;
+	const size_t prev_bytes = (size_t)npts * 2 * sizeof(float);
+	if (orbx_status s = prepare(f2, npts, 0, 0, prev_bytes, (size_t)npts, prev_bytes, A, S)) return s;
+	if (npts) memcpy(f2->h_in + S.in_state, prev_matched, prev_bytes);
 	A.mode = MODE_INIT;
 	A.kps1 = f1->kps.p;
 	A.pt_desc = f1->desc.p;
-	A.prev = f2->prev.p;
+	A.prev_in = reinterpret_cast<const float*>(f2->d_in.p + S.in_state);
+	A.prev = reinterpret_cast<float*>(f2->d_out.p + S.out_prev);
 	A.radius = (float)window_size;                          // :626
 	A.nnratio = nnratio;
 	A.check_ori = check_orientation != 0;
-	if (orbx_status s = run_search(f2, A, nmatches)) return s;
+	if (orbx_status s = run_search(f2, A, S, nmatches)) return s;
 	if (npts)
 	{
-		GCU(cudaMemcpy(matches12, f2->mp.p, (size_t)npts * sizeof(int), cudaMemcpyDeviceToHost));
-		GCU(cudaMemcpy(prev_matched, f2->prev.p, (size_t)npts * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+		memcpy(matches12, f2->h_out + S.out_mp, (size_t)npts * sizeof(int));
+		memcpy(prev_matched, f2->h_out + S.out_prev, prev_bytes);
 	}
 	return ORBX_OK;
 }
 
-orbx_status orbx_frame_last_rounds(orbx_frame f, int* rounds)
+orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms)
 {
-	if (!f || !rounds) return orbx_fail(ORBX_ERR_INVALID, "null argument");
-	*rounds = f->last_rounds;
+	if (!f) return orbx_fail(ORBX_ERR_INVALID, "null handle");
+	if (rounds) *rounds = f->last_rounds;
+	if (kernel_ms) *kernel_ms = f->last_kernel_ms;
 	return ORBX_OK;
 }
 

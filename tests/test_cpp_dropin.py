@@ -8,6 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, 'tests', 'cpp', '_build', 'dropin_test')
+EXE_GUIDED = os.path.join(ROOT, 'tests', 'cpp', '_build', 'guided_dropin_test')
 
 
 def build_exe():
@@ -16,19 +17,21 @@ def build_exe():
     lib = build.build()
     bindings.build()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    src = os.path.join(ROOT, 'tests', 'cpp', 'dropin_test.cc')
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(lib)):
-        return
-    cmd = ['g++', '-std=c++14', '-O1', '-Wall', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oracle', 'cvshim'),
-           '-I', os.path.join(ROOT, 'oracle'), src, '-o', EXE,
-           '-L', os.path.dirname(lib), '-lorbx_b200', '-L', os.path.join(ROOT, 'oracle', '_build'), '-lorb_oracle',
-           '-Wl,-rpath,' + os.path.dirname(lib), '-Wl,-rpath,' + os.path.join(ROOT, 'oracle', '_build')]
-    subprocess.run(cmd, check=True)
+    hdrs = [os.path.join(ROOT, 'include', 'orbx', h) for h in ('ORBextractor.h', 'ORBmatcher.h', 'GuidedMatcher.h')]
+    for name, exe in (('dropin_test.cc', EXE), ('guided_dropin_test.cc', EXE_GUIDED)):
+        src = os.path.join(ROOT, 'tests', 'cpp', name)
+        if os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(src), os.path.getmtime(lib)] + [os.path.getmtime(h) for h in hdrs]):
+            continue
+        cmd = ['g++', '-std=c++14', '-O1', '-Wall', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oracle', 'cvshim'),
+               '-I', os.path.join(ROOT, 'oracle'), src, '-o', exe,
+               '-L', os.path.dirname(lib), '-lorbx_b200', '-L', os.path.join(ROOT, 'oracle', '_build'), '-lorb_oracle',
+               '-Wl,-rpath,' + os.path.dirname(lib), '-Wl,-rpath,' + os.path.join(ROOT, 'oracle', '_build')]
+        subprocess.run(cmd, check=True)
 
 
 def test_dropin_headers_compile_and_link():
     build_exe()
-    assert os.path.exists(EXE)
+    assert os.path.exists(EXE) and os.path.exists(EXE_GUIDED)
 
 
 @pytest.mark.gpu
@@ -37,5 +40,14 @@ def test_dropin_matches_oracle():
     build_exe()
     L, R = synth.stereo_pair(7, 752, 480)
     r = subprocess.run([EXE, '752', '480', '1200'], input=L.tobytes() + R.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert r.stdout.decode().startswith('OK')
+
+
+@pytest.mark.gpu
+def test_guided_dropin_matches_oracle():
+    """include/orbx/GuidedMatcher.h driven with Frame / MapPoint types that carry the reference's member names."""
+    build_exe()
+    r = subprocess.run([EXE_GUIDED], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     assert r.stdout.decode().startswith('OK')
