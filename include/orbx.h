@@ -243,9 +243,10 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame cur, const orbx_came
 /* ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:614-694. prev_matched: f1->n (x, y) pairs, in/out; matches12: f1->n, out. */
 orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size,
                                            float nnratio, int check_orientation, int* nmatches);
-/* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1) and the kernel's duration (CUDA events).
- * Either pointer may be NULL. */
-orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms);
+/* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1), the kernel's duration (CUDA events) and
+ * the microseconds its phases took (enumeration, -, -, distances, rounds, finalisation, and the part of `rounds` spent staging state into
+ * shared memory; %globaltimer). Any pointer may be NULL; phase_us needs room for 7 floats. */
+orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms, float* phase_us);
 
 /* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
  * `device` (all SMs, register operands). */

@@ -116,7 +116,7 @@ _SIGNATURES = {
                                                        C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_for_initialization': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
                                                  C.POINTER(C.c_int)]),
-    'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
 }
 
@@ -417,8 +417,14 @@ class Frame:
     def last_stats(self):
         """(rounds, kernel milliseconds) of the last search on this frame."""
         n, ms = C.c_int(), C.c_float()
-        _check(lib().orbx_frame_last_stats(self._h, C.byref(n), C.byref(ms)))
+        _check(lib().orbx_frame_last_stats(self._h, C.byref(n), C.byref(ms), None))
         return n.value, ms.value
+
+    def last_phase_us(self):
+        """Microseconds of the last search's phases: windows, count + scan, fill, distances, rounds, finalisation."""
+        ph = np.zeros(7, np.float32)
+        _check(lib().orbx_frame_last_stats(self._h, None, None, _p(ph)))
+        return ph
 
 
 def _pose(p):

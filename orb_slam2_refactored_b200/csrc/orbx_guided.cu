@@ -17,6 +17,7 @@
 // One CTA per search (a frame holds 1-8 k keypoints: the work is latency-, not bandwidth-bound); phases are separated by block barriers.
 #include "orbx_internal.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include <algorithm>
@@ -31,6 +32,8 @@ namespace {
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;   // include/Frame.h:72-73
 constexpr int G_THREADS = 1024;
+constexpr int G_SMEM_INTS = 200 * 1024 / 4;   // dynamic shared memory of the search kernel, in ints
+constexpr int G_CLUSTER = 8;          // CTAs (= SMs) of one search: a thread-block cluster, the portable maximum
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;                        // src/ORBmatcher.cc:41-43
 constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2;
 
@@ -67,7 +70,10 @@ struct GuidedArgs
 	// scratch, per point
 	float* pu; float* pv; float* pur; float* prad;
 	int* plevels;                // minLevel | maxLevel << 16 (as int16), -32768 in the low half = inactive
-	int* off;                    // [npts + 1]
+	int* off;                    // start of the point's candidate list
+	int* len;                    // its length
+	int* cursor;                 // [2] list allocation cursors, used alternately (the idle one is zeroed for the next launch)
+	int parity, lanes;           // cursor in use; threads per point in the enumeration (power of two <= 32)
 	int* choice;                 // keypoint taken by the point
 	int* aux0; int* aux1;        // INIT: best distance of the accepted match, ping-pong; LAST_FRAME: histogram bin of the match
 	int* next;                   // INIT: claim lists
@@ -79,6 +85,9 @@ struct GuidedArgs
 	const float* prev_in;        // INIT: prevMatched on entry
 	int32_t* frame_mp;           // out: frame.mappoints (LOCAL_MAP, LAST_FRAME); INIT: matches12 [npts]
 	int* result;                 // [0] nmatches, [1] entries, [2] rounds, [3] overflow
+	unsigned long long* stamps;  // [8] %globaltimer at the phase boundaries (diagnostics)
+	int use_smem;                // cell offsets, owner, its initial value and choice in dynamic shared memory
+	int smem_ints;               // dynamic shared memory of this launch, in ints
 };
 
 __device__ __forceinline__ int hamming256(const uint8_t* a, const uint8_t* b)
@@ -102,6 +111,25 @@ __device__ __forceinline__ void for_window(const GridDev& G, float x, float y, f
 	const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
 	if (maxLevel < 0) maxLevel = G.nlevels;
 	for (int cx = mincx; cx <= maxcx; cx++)
+	{
+		const int a = G.cell_start[cx * GRID_ROWS + mincy], b = G.cell_start[cx * GRID_ROWS + maxcy + 1];
+		for (int p = a; p < b; p++)
+		{
+			const int4 rec = G.rec[p];
+			if (checkLevels && (rec.w < minLevel || rec.w > maxLevel)) continue;
+			if (fabsf(__int_as_float(rec.x) - x) < r && fabsf(__int_as_float(rec.y) - y) < r) f(rec.z, rec.w);
+		}
+	}
+}
+
+// The same walk restricted to the cell columns [c0, c1) of an already clipped window (mincy..maxcy); used when several lanes share a window.
+template <class F>
+__device__ __forceinline__ void for_columns(const GridDev& G, float x, float y, float r, int minLevel, int maxLevel, int c0, int c1, int mincy,
+                                            int maxcy, F f)
+{
+	const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+	if (maxLevel < 0) maxLevel = G.nlevels;
+	for (int cx = c0; cx < c1; cx++)
 	{
 		const int a = G.cell_start[cx * GRID_ROWS + mincy], b = G.cell_start[cx * GRID_ROWS + maxcy + 1];
 		for (int p = a; p < b; p++)
@@ -228,7 +256,7 @@ constexpr int INACTIVE = -32768;
 // CheckOrientation (:249-309) over the matches (i, choice[i]); bins were stored by the caller. Invalidates through `erase(i)`,
 // returns matches - reduction. s_hist: HISTO_LENGTH ints, zeroed by the caller before the bins were counted; s_misc: 2 ints.
 template <class Erase>
-__device__ int check_orientation(const GuidedArgs& A, const int* bin_of, int* s_hist, uint64_t* s_items, int* s_misc, Erase erase)
+__device__ int check_orientation(const GuidedArgs& A, const int* choice, const int* bin_of, int* s_hist, uint64_t* s_items, int* s_misc, Erase erase)
 {
 	const int tid = threadIdx.x;
 	if (tid == 0)
@@ -258,7 +286,7 @@ __device__ int check_orientation(const GuidedArgs& A, const int* bin_of, int* s_
 	__syncthreads();
 	const uint32_t mask = (uint32_t)s_misc[0];
 	for (int i = tid; i < A.npts; i += G_THREADS)
-		if (A.choice[i] >= 0 && ((mask >> bin_of[i]) & 1u)) erase(i);
+		if (choice[i] >= 0 && ((mask >> bin_of[i]) & 1u)) erase(i);
 	return s_misc[1];
 }
 
@@ -272,19 +300,64 @@ __device__ __forceinline__ int orientation_bin(float a1, float a2)
 	return min(max(bin, 0), HISTO_LENGTH - 1);
 }
 
-__global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
+__device__ __forceinline__ void stamp(const GuidedArgs& A, int k)
 {
+	if (threadIdx.x == 0)
+	{
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		A.stamps[k] = t;
+	}
+}
+
+// One search = one cluster of G_CLUSTER CTAs. The state-free phases (windows, enumeration, distances) run on all of them, separated by
+// cluster barriers (release/acquire at cluster scope, so the global arrays written before are visible after); the rounds and the
+// finalisation run in CTA 0, whose shared memory holds the state.
+__global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1) k_guided_search(const GuidedArgs A)
+{
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = (int)cluster.block_rank();
+	const int gid = rank * G_THREADS + (int)threadIdx.x, gstride = G_CLUSTER * G_THREADS;
 	__shared__ int s_w[G_THREADS / 32 + 1];
 	__shared__ int s_hist[HISTO_LENGTH];
 	__shared__ uint64_t s_items[HISTO_LENGTH];
 	__shared__ int s_misc[2];
 	__shared__ int s_count;
+	extern __shared__ int s_dyn[];
 	const int tid = threadIdx.x;
-	const GridDev& G = A.G;
+	GridDev G = A.G;
 	const int npts = A.npts, n2 = G.n;
+	// the arrays every phase chases pointers through live in shared memory when they fit (the host decides): the grid's cell
+	// offsets, the per-keypoint owner / claim heads, the per-point list offsets and picks
+	int* owner = A.owner;
+	int* off = A.off;                  // written by every CTA: global
+	int* choice = A.choice;
+	{
+		int* cs = s_dyn;               // every CTA keeps its own copy of the cell offsets
+		for (int c = tid; c <= GRID_CELLS; c += G_THREADS) cs[c] = A.G.cell_start[c];
+		G.cell_start = cs;
+		if (A.use_smem)
+		{
+			owner = cs + GRID_CELLS + 1;
+			choice = owner + 2 * n2;     // owner's initial value sits between them (see the rounds)
+		}
+		__syncthreads();
+	}
 
-	// ---- the window of every point
-	for (int i = tid; i < npts; i += G_THREADS)
+	if (rank == 0) stamp(A, 0);
+	if (rank == 0)
+	{
+		for (int i = tid; i < npts; i += G_THREADS) choice[i] = -1;
+		if (tid == 0) A.cursor[A.parity ^ 1] = 0;
+	}
+	// ---- the window of every point and its candidate list in GetFeaturesInArea order. `lanes` consecutive threads share a point:
+	//      each takes a contiguous block of the window's cell columns, counts its hits, the group's leader reserves the list with one
+	//      atomicAdd, and a second walk (now out of L1) writes the entries at the lane's offset.
+	const int L = A.lanes, lig = tid & (L - 1);
+	const unsigned gmask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << ((tid & 31) & ~(L - 1)));
+	int* const cursor = A.cursor + A.parity;
+	for (int i = gid / L; i < npts; i += gstride / L)
 	{
 		float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f;
 		int lv = pack_levels(INACTIVE, 0);
@@ -339,39 +412,59 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 				lv = pack_levels(0, 0);                                           // :637
 			}
 		}
-		A.pu[i] = u; A.pv[i] = v; A.pur[i] = ur; A.prad[i] = radius; A.plevels[i] = lv;
-		A.choice[i] = -1;
-		if (A.mode == MODE_INIT) { A.aux0[i] = INT_MAX; A.aux1[i] = INT_MAX; }
-	}
-	__syncthreads();
-
-	// ---- candidate lists: count, scan, fill in GetFeaturesInArea order
-	for (int i = tid; i < npts; i += G_THREADS)
-	{
+		if (lig == 0)
+		{
+			A.pu[i] = u; A.pv[i] = v; A.pur[i] = ur; A.prad[i] = radius; A.plevels[i] = lv;
+			if (A.mode == MODE_INIT) { A.aux0[i] = INT_MAX; A.aux1[i] = INT_MAX; }
+		}
+		// the window's cells (src/Frame.cc:112-118)
+		const int mincx = max(__float2int_rd(G.invW * (u - radius - G.b.minx)), 0);
+		const int maxcx = min(__float2int_ru(G.invW * (u + radius - G.b.minx)), GRID_COLS - 1);
+		const int mincy = max(__float2int_rd(G.invH * (v - radius - G.b.miny)), 0);
+		const int maxcy = min(__float2int_ru(G.invH * (v + radius - G.b.miny)), GRID_ROWS - 1);
+		const bool live = level_lo(lv) != INACTIVE && !(mincx >= GRID_COLS || maxcx < 0 || mincy >= GRID_ROWS || maxcy < 0);
+		const int ncols = live ? max(maxcx - mincx + 1, 0) : 0;
+		const int q = (ncols + L - 1) / L;
+		const int c0 = mincx + lig * q, c1 = min(c0 + q, mincx + ncols);
 		int c = 0;
-		const int lv = A.plevels[i];
-		if (level_lo(lv) != INACTIVE) for_window(G, A.pu[i], A.pv[i], A.prad[i], level_lo(lv), level_hi(lv), [&](int, int) { c++; });
-		A.off[i] = c;
-	}
-	__syncthreads();
-	const int total = block_exscan_inplace(A.off, npts, s_w);
-	if (tid == 0) { A.off[npts] = total; A.result[1] = total; A.result[3] = total > A.cap; }
-	if (total > A.cap) return;
-	for (int i = tid; i < npts; i += G_THREADS)
-	{
-		int p = A.off[i];
-		const int lv = A.plevels[i];
-		if (level_lo(lv) != INACTIVE)
-			for_window(G, A.pu[i], A.pv[i], A.prad[i], level_lo(lv), level_hi(lv), [&](int idx, int oct) {
+		for_columns(G, u, v, radius, level_lo(lv), level_hi(lv), c0, c1, mincy, maxcy, [&](int, int) { c++; });
+		int inc = c;
+		for (int d = 1; d < L; d <<= 1)
+		{
+			const int o = __shfl_up_sync(gmask, inc, d, L);
+			if (lig >= d) inc += o;
+		}
+		const int tot = __shfl_sync(gmask, inc, L - 1, L);
+		int base = 0;
+		if (lig == 0)
+		{
+			if (tot > 0) base = atomicAdd(cursor, tot);
+			off[i] = base;
+			A.len[i] = tot;
+		}
+		base = __shfl_sync(gmask, base, 0, L);
+		int p = base + inc - c;
+		if (base + tot <= A.cap)       // otherwise the launch is repeated with larger arrays
+			for_columns(G, u, v, radius, level_lo(lv), level_hi(lv), c0, c1, mincy, maxcy, [&](int idx, int oct) {
 				A.list[p] = (uint32_t)idx | ((uint32_t)oct << E_IDX_BITS);
 				A.entry_pt[p] = i;
 				p++;
 			});
 	}
-	__syncthreads();
+	cluster.sync();
+	const int total = *cursor;
+	if (total > A.cap)
+	{
+		if (gid == 0) { A.result[1] = total; A.result[3] = 1; }
+		return;
+	}
+	if (gid == 0) { A.result[1] = total; A.result[3] = 0; }
+	if (rank == 0) { stamp(A, 1); stamp(A, 2); }
+	cluster.sync();
+	if (rank == 0) stamp(A, 3);
 
 	// ---- every distance, one thread per candidate (DescriptorDistance, :1449-1457), and the stereo gate (:342-343, :1333-1334)
-	for (int e = tid; e < total; e += G_THREADS)
+	for (int e = gid; e < total; e += gstride)
 	{
 		const uint32_t ent = A.list[e];
 		const int idx = (int)(ent & E_IDX_MASK), i = A.entry_pt[e];
@@ -381,38 +474,64 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		else d = (uint32_t)hamming256(A.pt_desc + (size_t)i * 32, A.desc2 + (size_t)idx * 32);
 		A.list[e] = ent | (d << (E_IDX_BITS + E_LVL_BITS));
 	}
-	__syncthreads();
+	cluster.sync();
+	if (rank != 0) return;
+	stamp(A, 4);
+
+	// the rounds re-scan every candidate list: keep the lists (and their bounds) in shared memory when they fit beside the state
+	const uint32_t* lst = A.list;
+	const int* lstart = off;
+	const int* llen = A.len;
+	if (A.use_smem && GRID_CELLS + 1 + 2 * n2 + 4 * npts + total <= A.smem_ints)
+	{
+		int* st = choice + 2 * npts;
+		int* ln = st + npts;
+		uint32_t* ls = reinterpret_cast<uint32_t*>(ln + npts);
+		for (int i = tid; i < npts; i += G_THREADS) { st[i] = off[i]; ln[i] = A.len[i]; }
+		for (int e = tid; e < total; e += G_THREADS) ls[e] = A.list[e];
+		lst = ls; lstart = st; llen = ln;
+		__syncthreads();
+	}
 
 	int rounds = 0;
 	if (A.mode != MODE_INIT)
 	{
 		// ---- rounds: owner[c] = lowest point index with observations that takes keypoint c (-1: closed on entry)
+		// Everything a round reads is staged once: owner's value before any claim (own0) and Observations() > 0 per point (obs),
+		// in shared memory when the state fits there.
+		const bool have_own0 = A.use_smem != 0;
+		int* own0 = owner + n2;
+		int* obs = have_own0 ? choice + npts : A.aux0;
+		auto closed_on_entry = [&](int c) {
+			const int m = A.mp_in[c];
+			return m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
+		};
+		if (have_own0)
+			for (int c = tid; c < n2; c += G_THREADS) own0[c] = closed_on_entry(c) ? -1 : INT_MAX;
+		for (int i = tid; i < npts; i += G_THREADS) obs[i] = ((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2) ? 1 : 0;
+		__syncthreads();
+		stamp(A, 7);
 		for (;;)
 		{
-			for (int c = tid; c < n2; c += G_THREADS)
-			{
-				const int m = A.mp_in[c];
-				const bool closed = m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
-				A.owner[c] = closed ? -1 : INT_MAX;
-			}
+			for (int c = tid; c < n2; c += G_THREADS) owner[c] = have_own0 ? own0[c] : (closed_on_entry(c) ? -1 : INT_MAX);
 			__syncthreads();
 			for (int i = tid; i < npts; i += G_THREADS)
 			{
-				const int c = A.choice[i];
-				if (c >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2)) atomicMin(&A.owner[c], i);
+				const int c = choice[i];
+				if (c >= 0 && obs[i]) atomicMin(&owner[c], i);
 			}
 			__syncthreads();
 			int changed = 0;
 			for (int i = tid; i < npts; i += G_THREADS)
 			{
 				int best = 256, second = 256, bestLevel = -1, secondLevel = -1, bestIdx = -1;
-				for (int e = A.off[i]; e < A.off[i + 1]; e++)
+				for (int e = lstart[i], e1 = lstart[i] + llen[i]; e < e1; e++)
 				{
-					const uint32_t ent = A.list[e];
+					const uint32_t ent = lst[e];
 					const int d = (int)(ent >> (E_IDX_BITS + E_LVL_BITS));
 					if (d == (int)E_SKIP) continue;
 					const int idx = (int)(ent & E_IDX_MASK);
-					if (A.owner[idx] < i) continue;                            // :339-340, :1330-1331
+					if (owner[idx] < i) continue;                            // :339-340, :1330-1331
 					const int lvl = (int)((ent >> E_IDX_BITS) & ((1u << E_LVL_BITS) - 1));
 					if (d < best) { second = best; best = d; secondLevel = bestLevel; bestLevel = lvl; bestIdx = idx; }
 					else if (d < second) { secondLevel = lvl; second = d; }
@@ -420,24 +539,25 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 				bool ok = best <= TH_HIGH;                                        // :370, :1349
 				if (ok && A.mode == MODE_LOCAL_MAP && bestLevel == secondLevel && (float)best > A.nnratio * (float)second) ok = false;   // :372-373
 				const int c = ok ? bestIdx : -1;
-				if (c != A.choice[i]) { A.choice[i] = c; changed = 1; }
+				if (c != choice[i]) { choice[i] = c; changed = 1; }
 			}
 			rounds++;
 			if (!__syncthreads_or(changed)) break;
 		}
 
+		stamp(A, 5);
 		// ---- frame.mappoints: the last point (in loop order) that took a keypoint stays there
 		if (tid == 0) s_count = 0;
 		for (int b = tid; b < HISTO_LENGTH; b += G_THREADS) s_hist[b] = 0;
-		for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;
+		for (int c = tid; c < n2; c += G_THREADS) owner[c] = -1;
 		__syncthreads();
 		int mine = 0;
 		for (int i = tid; i < npts; i += G_THREADS)
 		{
-			const int c = A.choice[i];
+			const int c = choice[i];
 			if (c < 0) continue;
 			mine++;
-			atomicMax(&A.owner[c], i);
+			atomicMax(&owner[c], i);
 			if (A.mode == MODE_LAST_FRAME && A.check_ori)
 			{
 				const int bin = orientation_bin(A.lp[i].angle, A.kps2[c].angle);   // keypoints1 = lastFrame.keypointsUn, :1358
@@ -447,12 +567,13 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		}
 		if (mine) atomicAdd(&s_count, mine);
 		__syncthreads();
-		for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = A.owner[c] >= 0 ? A.owner[c] : A.mp_in[c];
+		for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = owner[c] >= 0 ? owner[c] : A.mp_in[c];
 		__syncthreads();
 		int nmatches = s_count;
 		if (A.mode == MODE_LAST_FRAME && A.check_ori)
-			nmatches = check_orientation(A, A.aux0, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[A.choice[i]] = -1; });   // :298-304
+			nmatches = check_orientation(A, choice, A.aux0, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[choice[i]] = -1; });   // :298-304
 		if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
+		stamp(A, 6);
 		return;
 	}
 
@@ -461,22 +582,22 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 	int* bd_new = A.aux1;
 	for (;;)
 	{
-		for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;         // heads of the claim lists
+		for (int c = tid; c < n2; c += G_THREADS) owner[c] = -1;         // heads of the claim lists
 		__syncthreads();
 		for (int i = tid; i < npts; i += G_THREADS)
-			if (A.choice[i] >= 0) A.next[i] = atomicExch(&A.owner[A.choice[i]], i);
+			if (choice[i] >= 0) A.next[i] = atomicExch(&owner[choice[i]], i);
 		__syncthreads();
 		int changed = 0;
 		for (int i = tid; i < npts; i += G_THREADS)
 		{
 			int best = INT_MAX, second = INT_MAX, bestIdx = -1;
-			for (int e = A.off[i]; e < A.off[i + 1]; e++)
+			for (int e = lstart[i], e1 = lstart[i] + llen[i]; e < e1; e++)
 			{
-				const uint32_t ent = A.list[e];
+				const uint32_t ent = lst[e];
 				const int d = (int)(ent >> (E_IDX_BITS + E_LVL_BITS));
 				const int idx = (int)(ent & E_IDX_MASK);
 				int md = INT_MAX;
-				for (int j = A.owner[idx]; j >= 0; j = A.next[j])
+				for (int j = owner[idx]; j >= 0; j = A.next[j])
 					if (j < i) md = min(md, bd_old[j]);
 				if (md <= d) continue;                                         // :651-652
 				if (d < best) { second = best; best = d; bestIdx = idx; }
@@ -485,26 +606,27 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 			const bool ok = bestIdx >= 0 && best <= TH_LOW && (float)best < (float)second * A.nnratio;   // :666
 			const int c = ok ? bestIdx : -1;
 			const int bd = ok ? best : INT_MAX;
-			if (c != A.choice[i] || bd != bd_old[i]) changed = 1;
-			A.choice[i] = c;
+			if (c != choice[i] || bd != bd_old[i]) changed = 1;
+			choice[i] = c;
 			bd_new[i] = bd;
 		}
 		rounds++;
 		int* t = bd_old; bd_old = bd_new; bd_new = t;
 		if (!__syncthreads_or(changed)) break;
 	}
+	stamp(A, 5);
 	// matches21[c] = the last accepted point on c; earlier ones were revoked (:668-672)
 	if (tid == 0) s_count = 0;
 	for (int b = tid; b < HISTO_LENGTH; b += G_THREADS) s_hist[b] = 0;
-	for (int c = tid; c < n2; c += G_THREADS) A.owner[c] = -1;
+	for (int c = tid; c < n2; c += G_THREADS) owner[c] = -1;
 	__syncthreads();
 	int accepted = 0;
 	for (int i = tid; i < npts; i += G_THREADS)
 	{
-		const int c = A.choice[i];
+		const int c = choice[i];
 		if (c < 0) continue;
 		accepted++;
-		atomicMax(&A.owner[c], i);
+		atomicMax(&owner[c], i);
 		if (A.check_ori)
 		{
 			const int bin = orientation_bin(A.kps2[c].angle, A.kps1[i].angle);     // keypoints1 = frame2.keypointsUn, :686
@@ -516,15 +638,15 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 	int distinct = 0;
 	for (int i = tid; i < npts; i += G_THREADS)
 	{
-		const int c = A.choice[i];
-		const bool keep = c >= 0 && A.owner[c] == i;
+		const int c = choice[i];
+		const bool keep = c >= 0 && owner[c] == i;
 		A.frame_mp[i] = keep ? c : -1;
 		distinct += keep;
 	}
 	atomicAdd(&s_count, A.check_ori ? accepted : distinct);   // with CheckOrientation the count restarts from matchIds.size() (:686)
 	__syncthreads();
 	int nmatches = s_count;
-	if (A.check_ori) nmatches = check_orientation(A, bd_new, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[i] = -1; });
+	if (A.check_ori) nmatches = check_orientation(A, choice, bd_new, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[i] = -1; });
 	__syncthreads();
 	for (int i = tid; i < npts; i += G_THREADS)
 	{
@@ -533,6 +655,7 @@ __global__ void __launch_bounds__(G_THREADS) k_guided_search(const GuidedArgs A)
 		A.prev[2 * i + 1] = c >= 0 ? A.kps2[c].y : A.prev_in[2 * i + 1];
 	}
 	if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
+	stamp(A, 6);
 }
 
 template <class T> struct GBuf
@@ -574,6 +697,7 @@ struct orbx_frame_s
 	cudaStream_t st = nullptr;
 	int last_rounds = 0;
 	float last_kernel_ms = 0.f;
+	unsigned long long last_stamps[8] = {};
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// one pinned staging buffer each way: a search is one H2D copy, one kernel, one D2H copy
 	uint8_t* h_in = nullptr; size_t h_in_cap = 0;
@@ -586,7 +710,8 @@ struct orbx_frame_s
 	GBuf<int4> rec;
 	// per-search scratch
 	GBuf<float> pf;
-	GBuf<int> pi, owner, entry_pt;
+	GBuf<int> pi, owner, entry_pt, cursor;
+	int launches = 0, last_entries = 0;
 	GBuf<uint32_t> list;
 	GBuf<float> qf;
 	GBuf<int> qi, qoff, qidx;
@@ -647,7 +772,7 @@ orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_byt
 {
 	GCU(cudaSetDevice(f->device));
 	GCU(f->pf.ensure((size_t)npts * 4 + 4));
-	GCU(f->pi.ensure((size_t)npts * 6 + 8));
+	GCU(f->pi.ensure((size_t)npts * 7 + 8));
 	GCU(f->owner.ensure((size_t)f->n + 1));
 	const size_t want = (size_t)npts * 48 + 4096;
 	if (f->list.n < want)
@@ -656,7 +781,7 @@ orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_byt
 		GCU(f->entry_pt.ensure(want));
 	}
 	S.in_pts = 0; S.in_desc = up16(pts_bytes); S.in_state = S.in_desc + up16(desc_bytes); S.in_bytes = S.in_state + up16(state_bytes) + 16;
-	S.out_res = 0; S.out_mp = 16; S.out_prev = S.out_mp + up16(mp_entries * sizeof(int)); S.out_bytes = S.out_prev + up16(prev_bytes) + 16;
+	S.out_res = 0; S.out_mp = 16 + 8 * sizeof(unsigned long long); S.out_prev = S.out_mp + up16(mp_entries * sizeof(int)); S.out_bytes = S.out_prev + up16(prev_bytes) + 16;
 	GCU(f->ensure_staging(S.in_bytes, S.out_bytes));
 	A.G = f->grid();
 	A.kps2 = f->kps.p; A.desc2 = f->desc.p; A.uright2 = f->uright.p;
@@ -664,10 +789,17 @@ orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_byt
 	A.npts = npts;
 	A.pu = f->pf.p; A.pv = A.pu + npts; A.pur = A.pv + npts; A.prad = A.pur + npts;
 	A.plevels = f->pi.p; A.off = A.plevels + npts; A.choice = A.off + npts + 1; A.aux0 = A.choice + npts; A.aux1 = A.aux0 + npts;
-	A.next = A.aux1 + npts;
+	A.next = A.aux1 + npts; A.len = A.next + npts;
+	A.cursor = f->cursor.p;
+	{
+		int lanes = 1;
+		while (lanes < 16 && (size_t)npts * lanes * 2 <= (size_t)G_CLUSTER * G_THREADS) lanes *= 2;
+		A.lanes = lanes;
+	}
 	A.owner = f->owner.p;
 	A.list = f->list.p; A.entry_pt = f->entry_pt.p; A.cap = (int)std::min(f->list.n, f->entry_pt.n);
 	A.result = reinterpret_cast<int*>(f->d_out.p + S.out_res);
+	A.stamps = reinterpret_cast<unsigned long long*>(f->d_out.p + S.out_res + 16);
 	A.frame_mp = reinterpret_cast<int32_t*>(f->d_out.p + S.out_mp);
 	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr; A.mp_in = nullptr; A.prev_in = nullptr;
 	A.th = 0.f; A.nnratio = 0.f; A.radius = 0.f; A.fx = A.fy = A.cx = A.cy = A.bf = 0.f;
@@ -685,7 +817,15 @@ orbx_status run_search(orbx_frame_s* f, GuidedArgs& A, const Staging& S, int* nm
 	{
 		if (attempt == 0) GCU(cudaMemcpyAsync(f->d_in.p, f->h_in, S.in_bytes, cudaMemcpyHostToDevice, f->st));
 		GCU(cudaEventRecord(f->ev0, f->st));
-		k_guided_search<<<1, G_THREADS, 0, f->st>>>(A);
+		A.parity = f->launches++ & 1;
+		const size_t state = (size_t)GRID_CELLS + 1 + 2 * (size_t)A.G.n + 2 * (size_t)A.npts;
+		A.use_smem = state <= (size_t)G_SMEM_INTS;
+		// room for the candidate lists too when they are likely to fit (sized from the last search on this frame); asking for all of
+		// the SM's shared memory regardless would shrink L1 under the enumeration
+		size_t want = A.use_smem ? state + 2 * (size_t)A.npts + std::max<size_t>((size_t)f->last_entries * 5 / 4, (size_t)A.npts * 8) : (size_t)GRID_CELLS + 1;
+		if (want > (size_t)G_SMEM_INTS) want = A.use_smem ? state : (size_t)GRID_CELLS + 1;
+		A.smem_ints = (int)want;
+		k_guided_search<<<G_CLUSTER, G_THREADS, sizeof(int) * want, f->st>>>(A);
 		GCU(cudaGetLastError());
 		GCU(cudaEventRecord(f->ev1, f->st));
 		GCU(cudaMemcpyAsync(f->h_out, f->d_out.p, S.out_bytes, cudaMemcpyDeviceToHost, f->st));
@@ -699,6 +839,8 @@ orbx_status run_search(orbx_frame_s* f, GuidedArgs& A, const Staging& S, int* nm
 	}
 	const int* res = reinterpret_cast<const int*>(f->h_out + S.out_res);
 	f->last_rounds = res[2];
+	f->last_entries = res[1];
+	memcpy(f->last_stamps, f->h_out + S.out_res + 16, sizeof(f->last_stamps));
 	cudaEventElapsedTime(&f->last_kernel_ms, f->ev0, f->ev1);
 	if (nmatches) *nmatches = res[0];
 	return ORBX_OK;
@@ -770,6 +912,17 @@ orbx_status orbx_frame_create(const orbx_frame_view* v, int device, orbx_frame* 
 	cudaError_t e;
 	if ((e = cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreate(&f->ev0)) != cudaSuccess ||
 	    (e = cudaEventCreate(&f->ev1)) != cudaSuccess)
+	{
+		delete f;
+		return orbx_fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+	}
+	// function attributes are per device: set on every create (cheap), after cudaSetDevice above
+	if ((e = cudaFuncSetAttribute(k_guided_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(int) * G_SMEM_INTS)) != cudaSuccess)
+	{
+		delete f;
+		return orbx_fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
+	}
+	if ((e = f->cursor.ensure(2)) != cudaSuccess || (e = cudaMemset(f->cursor.p, 0, 2 * sizeof(int))) != cudaSuccess)
 	{
 		delete f;
 		return orbx_fail(ORBX_ERR_CUDA, cudaGetErrorString(e));
@@ -940,11 +1093,16 @@ orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* 
 	return ORBX_OK;
 }
 
-orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms)
+orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms, float* phase_us)
 {
 	if (!f) return orbx_fail(ORBX_ERR_INVALID, "null handle");
 	if (rounds) *rounds = f->last_rounds;
 	if (kernel_ms) *kernel_ms = f->last_kernel_ms;
+	if (phase_us)
+	{
+		for (int k = 0; k < 6; k++) phase_us[k] = (float)(f->last_stamps[k + 1] - f->last_stamps[k]) * 1e-3f;
+		phase_us[6] = f->last_stamps[7] > f->last_stamps[4] ? (float)(f->last_stamps[7] - f->last_stamps[4]) * 1e-3f : 0.f;   // staging before the rounds
+	}
 	return ORBX_OK;
 }
 

@@ -50,6 +50,7 @@ def main():
                  rounds_local=f.last_rounds(), gpu_last=bench(g_last, 50), kernel_last=f.last_stats()[1] * 1e3, rounds_last=f.last_rounds(),
                  cpu_local=bench(lambda: ref.search_local_map(fr, mp0, pts, desc, 3.0, 0.8), 10),
                  cpu_last=bench(lambda: ref.search_last_frame(fr, synth.KITTI_CAMERA, cp, lp, mp0, lpts, ldesc, 7.0, False, 0.9, True), 10))
+        g_local(); print(tag, 'local phases us', np.round(f.last_phase_us(), 1)); g_last(); print(tag, 'last phases us', np.round(f.last_phase_us(), 1))
         print(tag, {k: round(v, 1) for k, v in r.items()}, 'us (cpu = %s incl. building its Frame/grid and the ctypes marshalling)' % ref.kind)
 
 
