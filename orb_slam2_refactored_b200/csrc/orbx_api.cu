@@ -111,7 +111,8 @@ struct orbx_extractor
 	int32_t* h_counts = nullptr;        // pinned staging for the per-frame counts (a pageable target would serialise the pipeline)
 	size_t h_counts_n = 0;
 	DevBuf<float> st_uright, st_depth;
-	DevBuf<int> st_sad;
+	DevBuf<int> st_sad, st_rows;
+	DevBuf<uint2> st_items;
 	bool stage_timing = false;
 	std::vector<cudaEvent_t> ev_pool;   // 6 events per timed extract call
 	size_t ev_used = 0;
@@ -466,7 +467,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->cell_tab.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
-	h->st_uright.release(); h->st_depth.release(); h->st_sad.release();
+	h->st_uright.release(); h->st_depth.release(); h->st_sad.release(); h->st_rows.release(); h->st_items.release();
 	if (h->h_counts) cudaFreeHost(h->h_counts);
 	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
@@ -905,6 +906,11 @@ orbx_status orbx_stereo_match_device(orbx_handle left, orbx_handle right, const 
 	A.uright = d_uright; A.depth = d_depth;
 	CU(left->st_sad.ensure((size_t)A.frames * A.cap));
 	A.sad = left->st_sad.p;
+	A.rows = PL.lv[0].h;
+	A.items_cap = A.cap * orbx_stereo_items_per_keypoint(left->scale[PL.nlevels - 1]);
+	CU(left->st_rows.ensure((size_t)A.frames * (A.rows + 1)));
+	CU(left->st_items.ensure((size_t)A.frames * A.items_cap));
+	A.row_start = left->st_rows.p; A.row_items = left->st_items.p;
 	// the right extraction runs on its own stream: order it before the match
 	CU(cudaEventRecord(right->done, right->stream));
 	CU(cudaStreamWaitEvent(left->stream, right->done, 0));
@@ -938,6 +944,7 @@ orbx_status orbx_stereo_match_host(int device, const orbx_keypoint* kps_l, int n
 		return fail(ORBX_ERR_INVALID, "bad argument");
 	if (nlevels < 1 || nlevels > ORBX_MAX_LEVELS) return fail(ORBX_ERR_INVALID, "nlevels must be in [1, 12]");
 	if (n_l >= 65536 || n_r >= 65536) return fail(ORBX_ERR_INVALID, "more than 65535 keypoints");
+	if (level_h[0] > 4096) return fail(ORBX_ERR_INVALID, "image taller than 4096 rows");
 	std::string why;
 	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
 	if (n_l == 0) return ORBX_OK;
@@ -955,7 +962,14 @@ orbx_status orbx_stereo_match_host(int device, const orbx_keypoint* kps_l, int n
 		slab += (int64_t)A.lpitch[s] * level_h[s];
 		A.scale[s] = scale[s]; A.inv_scale[s] = inv_scale[s];
 	}
-	DevBuf<uint8_t> pl, pr, dl, dr; DevBuf<orbx_keypoint> kl, kr; DevBuf<int32_t> cnt; DevBuf<float> du, dd; DevBuf<int> sad;
+	DevBuf<uint8_t> pl, pr, dl, dr; DevBuf<orbx_keypoint> kl, kr; DevBuf<int32_t> cnt; DevBuf<float> du, dd; DevBuf<int> sad, rowbuf;
+	DevBuf<uint2> itembuf;
+	float max_scale = 1.f;
+	for (int s = 0; s < nlevels; s++) max_scale = std::max(max_scale, scale[s]);
+	A.rows = level_h[0];
+	A.items_cap = cap * orbx_stereo_items_per_keypoint(max_scale);
+	CU(rowbuf.ensure((size_t)A.rows + 1)); CU(itembuf.ensure((size_t)A.items_cap));
+	A.row_start = rowbuf.p; A.row_items = itembuf.p;
 	CU(pl.ensure(slab)); CU(pr.ensure(slab)); CU(dl.ensure((size_t)cap * 32)); CU(dr.ensure((size_t)cap * 32));
 	CU(kl.ensure(cap)); CU(kr.ensure(cap)); CU(cnt.ensure(2)); CU(du.ensure(cap)); CU(dd.ensure(cap)); CU(sad.ensure(cap));
 	for (int s = 0; s < nlevels; s++)

@@ -121,7 +121,11 @@ struct OrbxStereoArgs
 	float bf, baseline;
 	float* uright; float* depth;      // [frames][cap]
 	int* sad;                         // [frames][cap] scratch: SAD of kept matches, -1 otherwise
+	// rowIndices of src/ORBmatcher.cc:84-100 as CSR per frame: row_start[frames][rows + 1], row_items[frames][items_cap] = (x bits, iR | octave << 16)
+	int rows, items_cap;
+	int* row_start; uint2* row_items;
 };
+int orbx_stereo_items_per_keypoint(float max_scale);   // upper bound of the rows one right keypoint is listed in
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st);
 void orbx_launch_stereo_from_rgbd(const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const uint8_t* depth_map, int64_t pitch, float bf,
                                   float* uright, float* depth, cudaStream_t st);

@@ -238,6 +238,71 @@ __device__ __forceinline__ const uint8_t* lvl_ptr(const uint8_t* l0, int64_t l0_
 	return o == 0 ? l0 + (int64_t)f * l0_stride : slab + (int64_t)f * slab_stride + off[o];
 }
 
+// rowIndices (src/ORBmatcher.cc:84-100): every right keypoint is listed in the rows [floor(y - r), ceil(y + r)], r = 2 * scale[octave].
+// One CTA per frame builds the lists as CSR with shared-memory counters. The order inside a row is arbitrary here; the match below
+// reduces with min over (distance, iR), which is what the reference's ascending scan with a strict '<' computes.
+constexpr int ST_MAX_ROWS = 4096;
+__global__ void __launch_bounds__(1024) k_stereo_rows(const OrbxStereoArgs A)
+{
+	__shared__ int s_cnt[ST_MAX_ROWS];
+	__shared__ int s_beg[ST_MAX_ROWS];
+	__shared__ int s_w[33];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int f = blockIdx.x, nR = A.nr[f], rows = A.rows;
+	const orbx_keypoint* __restrict__ kr = A.kr + (int64_t)f * A.cap;
+	int* __restrict__ rs = A.row_start + (int64_t)f * (rows + 1);
+	uint2* __restrict__ items = A.row_items + (int64_t)f * A.items_cap;
+	for (int y = tid; y < rows; y += 1024) s_cnt[y] = 0;
+	__syncthreads();
+	for (int iR = tid; iR < nR; iR += 1024)
+	{
+		const orbx_keypoint k = kr[iR];
+		const float r = __fmul_rn(2.f, A.scale[k.octave]);
+		const int miny = max((int)floorf(__fsub_rn(k.y, r)), 0), maxy = min((int)ceilf(__fadd_rn(k.y, r)), rows - 1);
+		for (int y = miny; y <= maxy; y++) atomicAdd(&s_cnt[y], 1);
+	}
+	__syncthreads();
+	// exclusive scan of the row counts
+	int base = 0;
+	for (int y0 = 0; y0 < rows; y0 += 1024)
+	{
+		const int y = y0 + tid;
+		const int v = y < rows ? s_cnt[y] : 0;
+		int inc = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const int o = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += o;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		int wbase = 0, tot = 0;
+		for (int w = 0; w < 32; w++)
+		{
+			const int t = s_w[w];
+			if (w < warp) wbase += t;
+			tot += t;
+		}
+		if (y < rows) { s_beg[y] = base + wbase + inc - v; rs[y] = s_beg[y]; }
+		base += tot;
+		__syncthreads();
+	}
+	if (tid == 0) rs[rows] = min(base, A.items_cap);
+	for (int iR = tid; iR < nR; iR += 1024)
+	{
+		const orbx_keypoint k = kr[iR];
+		const float r = __fmul_rn(2.f, A.scale[k.octave]);
+		const int miny = max((int)floorf(__fsub_rn(k.y, r)), 0), maxy = min((int)ceilf(__fadd_rn(k.y, r)), rows - 1);
+		const uint2 it = make_uint2(__float_as_uint(k.x), (uint32_t)iR | ((uint32_t)k.octave << 16));
+		for (int y = miny; y <= maxy; y++)
+		{
+			const int p = atomicAdd(&s_beg[y], 1);
+			if (p < A.items_cap) items[p] = it;
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) k_stereo_match(const OrbxStereoArgs A)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -267,25 +332,25 @@ __global__ void __launch_bounds__(256) k_stereo_match(const OrbxStereoArgs A)
 	// key = dist << 16 | iR; strict "<" against TH_HIGH with lowest index winning
 	uint32_t bestKey = ((uint32_t)TH_HIGH << 16);
 	bool any = false;
-	for (int i0 = 0; i0 < nR; i0 += 32)
+	// candidates = rowIndices[(int)vL] (:122): one CSR range; lanes stride over it
+	if (row >= 0 && row < A.rows)
 	{
-		const int iR = i0 + lane;
-		if (iR < nR)
+		const int* __restrict__ rs = A.row_start + (int64_t)f * (A.rows + 1);
+		const uint2* __restrict__ items = A.row_items + (int64_t)f * A.items_cap;
+		const int a = rs[row], b = min(rs[row + 1], A.items_cap);
+		any = b > a;
+		for (int p = a + lane; p < b; p += 32)
 		{
-			const orbx_keypoint k = kr[iR];
-			const float r = __fmul_rn(2.f, A.scale[k.octave]);
-			const int miny = (int)floorf(__fsub_rn(k.y, r)), maxy = (int)ceilf(__fadd_rn(k.y, r));
-			if (row >= miny && row <= maxy)
+			const uint2 it = items[p];
+			const int octR = (int)(it.y >> 16), iR = (int)(it.y & 0xffffu);
+			const float uR = __uint_as_float(it.x);
+			if (!(octR < kl.octave - 1 || octR > kl.octave + 1) && uR >= minu && uR <= maxu)
 			{
-				any = true;
-				if (!(k.octave < kl.octave - 1 || k.octave > kl.octave + 1) && k.x >= minu && k.x <= maxu)
-				{
-					const uint4* p = reinterpret_cast<const uint4*>(dr + (int64_t)iR * 32);
-					const uint4 lo = __ldg(p), hi = __ldg(p + 1);
-					const int d = __popc(dq[0] ^ lo.x) + __popc(dq[1] ^ lo.y) + __popc(dq[2] ^ lo.z) + __popc(dq[3] ^ lo.w) +
-					              __popc(dq[4] ^ hi.x) + __popc(dq[5] ^ hi.y) + __popc(dq[6] ^ hi.z) + __popc(dq[7] ^ hi.w);
-					if (d < TH_HIGH) bestKey = min(bestKey, ((uint32_t)d << 16) | (uint32_t)iR);
-				}
+				const uint4* p4 = reinterpret_cast<const uint4*>(dr + (int64_t)iR * 32);
+				const uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
+				const int d = __popc(dq[0] ^ lo.x) + __popc(dq[1] ^ lo.y) + __popc(dq[2] ^ lo.z) + __popc(dq[3] ^ lo.w) +
+				              __popc(dq[4] ^ hi.x) + __popc(dq[5] ^ hi.y) + __popc(dq[6] ^ hi.z) + __popc(dq[7] ^ hi.w);
+				if (d < TH_HIGH) bestKey = min(bestKey, ((uint32_t)d << 16) | (uint32_t)iR);
 			}
 		}
 	}
@@ -562,9 +627,12 @@ void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int ns
 	k_distinctive<<<nsets, DD_WARPS * 32, 0, st>>>(desc, offsets, best);
 }
 
+int orbx_stereo_items_per_keypoint(float max_scale) { return 2 * (int)ceilf(2.f * max_scale) + 3; }
+
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st)
 {
 	dim3 grid((A.cap + 7) / 8, A.frames);
+	k_stereo_rows<<<A.frames, 1024, 0, st>>>(A);
 	k_stereo_match<<<grid, 256, 0, st>>>(A);
 	k_stereo_median_cut<<<A.frames, 256, 0, st>>>(A);
 }
