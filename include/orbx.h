@@ -178,6 +178,18 @@ orbx_status orbx_convert_to_gray(int device, const uint8_t* src, int width, int 
  * written straight into level 0 of the pyramid on the device. channels = 1 behaves like orbx_extract_batch. */
 orbx_status orbx_extract_batch_color(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
                                      size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* The rectification step in front of TrackStereo — Examples/Stereo/stereo_euroc.cc:100-101: cv::remap(im, imRect, M1, M2, INTER_LINEAR)
+ * with the CV_32F maps of cv::initUndistortRectifyMap (:88-89); OpenCV's 1/32-pixel fixed point, constant border 0. Host buffers;
+ * map_pitch in bytes; dst is width x height, the maps' size. */
+orbx_status orbx_remap(int device, const uint8_t* src, int src_width, int src_height, size_t src_pitch, const float* map1, const float* map2,
+                       size_t map_pitch, uint8_t* dst, int width, int height, size_t dst_pitch);
+/* The same fused into Extract: the maps are converted and uploaded once per extractor (one per camera, as the reference keeps M1l/M2l
+ * and M1r/M2r), then raw frames go in and the rectified image is written straight into level 0 of the pyramid on the device.
+ * GetImagePyramid()[0] of such an extract is the rectified image. */
+orbx_status orbx_set_rectification(orbx_handle h, const float* map1, const float* map2, size_t map_pitch, int width, int height, int src_width,
+                                   int src_height);
+orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, int frames, int src_width, int src_height, size_t pitch,
+                                         size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
 /* ComputeStereoFromRGBD — src/System.cc:197-219: depth_map is width x height float32 (pitch in bytes). Host buffers. */
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
                                   int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth);

@@ -107,6 +107,7 @@ class Oracle:
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
         f('cv_gaussian7', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t])
+        f('cv_remap', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast_atan2', C.c_float, [C.c_float, C.c_float])
         f('cv_round_f', C.c_int, [C.c_float])
         f('cv_round_d', C.c_int, [C.c_double])
@@ -134,6 +135,15 @@ class Oracle:
         img = np.ascontiguousarray(img, np.uint8)
         dst = np.empty_like(img)
         self._cv_gaussian7(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dst), dst.strides[0])
+        return dst
+
+    def remap(self, img, mapx, mapy):
+        """cv::remap(img, mapx, mapy, INTER_LINEAR) for an 8-bit image and two float32 maps of the output size."""
+        img = np.ascontiguousarray(img, np.uint8)
+        mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+        dst = np.empty(mapx.shape, np.uint8)
+        self._cv_remap(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(mapx), _p(mapy), mapx.strides[0], _p(dst), dst.shape[1], dst.shape[0],
+                       dst.strides[0])
         return dst
 
     def fast_atan2(self, y, x):

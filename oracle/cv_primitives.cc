@@ -278,4 +278,31 @@ void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, b
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv::remap, INTER_LINEAR, BORDER_CONSTANT(0), CV_8UC1 source, two CV_32FC1 maps (modules/imgproc/src/imgwarp.cpp): the maps are
+// converted to 1/32-pixel fixed point with cvRound (INTER_BITS = 5), the four weights come from a table of products scaled to 2^15
+// (exact for bilinear: multiples of 32), taps outside the source read the border value 0, and the sum is rounded by (v + 2^14) >> 15.
+// Pinned by tests/golden/primitives.npz (cv2 4.13.0).
+// ---------------------------------------------------------------------------------------------
+void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, size_t mstep_bytes,
+                     uint8_t* dst, int dw, int dh, size_t dstep)
+{
+	for (int y = 0; y < dh; y++)
+	{
+		const float* mx = reinterpret_cast<const float*>(reinterpret_cast<const char*>(mapx) + (size_t)y * mstep_bytes);
+		const float* my = reinterpret_cast<const float*>(reinterpret_cast<const char*>(mapy) + (size_t)y * mstep_bytes);
+		uint8_t* d = dst + (size_t)y * dstep;
+		for (int x = 0; x < dw; x++)
+		{
+			const int sx = round_rne(mx[x] * 32), sy = round_rne(my[x] * 32);
+			const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+			auto tap = [&](int yy, int xx) -> int {
+				return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sstep + xx] : 0;
+			};
+			const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+			d[x] = (uint8_t)((tap(iy, ix) * w00 + tap(iy, ix + 1) * w01 + tap(iy + 1, ix) * w10 + tap(iy + 1, ix + 1) * w11 + (1 << 14)) >> 15);
+		}
+	}
+}
+
 }  // namespace cvp

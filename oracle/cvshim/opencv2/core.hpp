@@ -229,5 +229,8 @@ float fastAtan2(float y, float x);
 enum { COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7, COLOR_BGRA2GRAY = 10, COLOR_RGBA2GRAY = 11 };
 void cvtColor(const Mat& src, Mat& dst, int code);
 typedef Mat_<float> Mat1f;
+enum { INTER_LINEAR = 1 };
+// cv::remap as Examples/Stereo/stereo_euroc.cc:100-101 calls it: 8-bit single channel, two CV_32F maps, INTER_LINEAR, default border
+void remap(const Mat& src, Mat& dst, const Mat& map1, const Mat& map2, int interpolation);
 
 }  // namespace cv

@@ -49,4 +49,14 @@ void cvtColor(const Mat& src, Mat& dst, int code)
 	dst = out;
 }
 
+void remap(const Mat& src, Mat& dst, const Mat& map1, const Mat& map2, int interpolation)
+{
+	CV_Assert(interpolation == INTER_LINEAR && src.type() == CV_8U && map1.type() == CV_32F && map2.type() == CV_32F);
+	CV_Assert(map1.rows == map2.rows && map1.cols == map2.cols && map1.step == map2.step);
+	Mat out;
+	out.create(map1.rows, map1.cols, CV_8U);
+	cvp::remap_linear_u8(src.data, src.cols, src.rows, src.step, map1.ptr<float>(), map2.ptr<float>(), map1.step, out.data, out.cols, out.rows, out.step);
+	dst = out;
+}
+
 }  // namespace cv

@@ -144,6 +144,9 @@ int ORACLE_FN(search_for_initialization)(const oracle_frame_view* f1, const orac
 void ORACLE_FN(cv_resize)(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
 int ORACLE_FN(cv_fast)(const uint8_t* img, int w, int h, size_t step, int th, int nms, oracle_cand* out, int cap);
 void ORACLE_FN(cv_gaussian7)(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+// cv::remap(INTER_LINEAR) of an 8-bit image through two float maps (Examples/Stereo/stereo_euroc.cc:100-101); map pitch in bytes
+void ORACLE_FN(cv_remap)(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, size_t mstep, uint8_t* dst,
+                         int dw, int dh, size_t dstep);
 float ORACLE_FN(cv_fast_atan2)(float y, float x);
 int ORACLE_FN(cv_round_f)(float v);
 int ORACLE_FN(cv_round_d)(double v);

@@ -668,6 +668,11 @@ void orc_cv_gaussian7(const uint8_t* src, int w, int h, size_t sstep, uint8_t* d
 {
 	cvp::gauss7x7_u8(src, w, h, sstep, dst, dstep);
 }
+void orc_cv_remap(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, size_t mstep, uint8_t* dst, int dw, int dh,
+                  size_t dstep)
+{
+	cvp::remap_linear_u8(src, sw, sh, sstep, mapx, mapy, mstep, dst, dw, dh, dstep);
+}
 float orc_cv_fast_atan2(float y, float x) { return cvp::fast_atan2_deg(y, x); }
 int orc_cv_round_f(float v) { return cvp::round_rne(v); }
 int orc_cv_round_d(double v) { return cvp::round_rne(v); }

@@ -106,6 +106,11 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p]),
     'orbx_distinctive_descriptors': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_measure_popc_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    'orbx_remap': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
+                             C.c_size_t]),
+    'orbx_set_rectification': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'orbx_extract_batch_rectified': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p]),
     'orbx_frame_create': (C.c_int, [C.POINTER(_FrameView), C.c_int, C.POINTER(C.c_void_p)]),
     'orbx_frame_destroy': (C.c_int, [C.c_void_p]),
     'orbx_frame_grid': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -243,6 +248,25 @@ class ORBextractor:
         kps = np.zeros((F, cap), KP_DTYPE); desc = np.zeros((F, cap, 32), np.uint8); n = np.zeros(F, np.int32)
         _check(lib().orbx_extract_batch_color(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], ch, int(RGB), _p(kps),
                                               _p(desc), cap, _p(n)))
+        self._last_frames = F
+        return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
+
+    def SetRectification(self, map1, map2, src_shape):
+        """Keeps the maps of cv::initUndistortRectifyMap (Examples/Stereo/stereo_euroc.cc:88-89) on the device; src_shape = (h, w) of the raw
+        frames. ExtractBatchRectified then remaps and extracts in one pass."""
+        map1 = np.ascontiguousarray(map1, np.float32); map2 = np.ascontiguousarray(map2, np.float32)
+        _check(lib().orbx_set_rectification(self._h, _p(map1), _p(map2), map1.strides[0], map1.shape[1], map1.shape[0], int(src_shape[1]),
+                                            int(src_shape[0])))
+
+    def ExtractBatchRectified(self, images):
+        """images: (F, h, w) raw (unrectified) uint8 frames. cv::remap (Examples/Stereo/stereo_euroc.cc:100-101) fused into the upload,
+        then Extract on the rectified image. Returns two lists of per-frame arrays like ExtractBatch."""
+        images = np.ascontiguousarray(images, np.uint8)
+        F, H, W = images.shape
+        cap = lib().orbx_max_keypoints(self._h)
+        kps = np.zeros((F, cap), KP_DTYPE); desc = np.zeros((F, cap, 32), np.uint8); n = np.zeros(F, np.int32)
+        _check(lib().orbx_extract_batch_rectified(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], _p(kps), _p(desc), cap,
+                                                  _p(n)))
         self._last_frames = F
         return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
 
@@ -544,6 +568,16 @@ def ConvertToGray(src, RGB=True, device=0):
     h, w, ch = src.shape
     dst = np.empty((h, w), np.uint8)
     _check(lib().orbx_convert_to_gray(device, _p(src), w, h, src.strides[0], ch, int(RGB), _p(dst), dst.strides[0]))
+    return dst
+
+
+def Remap(src, map1, map2, device=0):
+    """cv::remap(src, dst, map1, map2, cv::INTER_LINEAR) as Examples/Stereo/stereo_euroc.cc:100-101 calls it (8-bit image, float32 maps)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    map1 = np.ascontiguousarray(map1, np.float32); map2 = np.ascontiguousarray(map2, np.float32)
+    dst = np.empty(map1.shape, np.uint8)
+    _check(lib().orbx_remap(device, _p(src), src.shape[1], src.shape[0], src.strides[0], _p(map1), _p(map2), map1.strides[0], _p(dst),
+                            dst.shape[1], dst.shape[0], dst.strides[0]))
     return dst
 
 

@@ -35,6 +35,24 @@ inline int cv_round(float v) { return (int)lrintf(v); }
 inline short sat_s16(int v) { return (short)std::min(32767, std::max(-32768, v)); }
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// cv::remap's own conversion of float maps to fixed point (modules/imgproc/src/imgwarp.cpp, INTER_BITS = 5): sx = cvRound(mapx * 32),
+// integer part saturate_cast<short>(sx >> 5), fraction sx & 31
+void pack_remap_table(const float* map1, const float* map2, size_t map_pitch, int w, int h, std::vector<int2>& tab)
+{
+	tab.resize((size_t)w * h);
+	for (int y = 0; y < h; y++)
+	{
+		const float* mx = reinterpret_cast<const float*>(reinterpret_cast<const char*>(map1) + (size_t)y * map_pitch);
+		const float* my = reinterpret_cast<const float*>(reinterpret_cast<const char*>(map2) + (size_t)y * map_pitch);
+		for (int x = 0; x < w; x++)
+		{
+			const int sx = cv_round(mx[x] * 32), sy = cv_round(my[x] * 32);
+			const int ix = sat_s16(sx >> 5), iy = sat_s16(sy >> 5);
+			tab[(size_t)y * w + x] = make_int2((ix & 0xffff) | (int)((unsigned)iy << 16), (sx & 31) | ((sy & 31) << 5));
+		}
+	}
+}
+
 template <class T> struct DevBuf
 {
 	T* p = nullptr;
@@ -94,7 +112,9 @@ struct orbx_extractor
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
 	OrbxTmaMaps maps;
-	DevBuf<uint8_t> color;              // interleaved colour frames of the current batch (orbx_extract_batch_color)
+	DevBuf<uint8_t> color;              // interleaved colour frames / unrectified frames of the current batch (orbx_extract_batch_color / _rectified)
+	DevBuf<int2> rect_tab;              // rectification table (orbx_set_rectification): per output pixel (ix | iy << 16, fx | fy << 5)
+	int rect_w = 0, rect_h = 0, rect_sw = 0, rect_sh = 0;
 	DevBuf<uint8_t> pyr, blur, l0buf;   // l0buf: level 0 of every frame, back to back (host-buffer API uploads land here)
 	int64_t l0_pitch = 0, l0_stride = 0;
 	uint8_t* l0base = nullptr;          // l0buf.p + 256: kernels may read up to 16 bytes in front of a row (aligned 16-byte tile copies)
@@ -610,18 +630,29 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 }
 
 static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int frames, int width, int height, size_t pitch,
-                                      size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+                                      size_t frame_stride, int channels, int rgb, orbx_keypoint* kps, uint8_t* desc, int cap, int* n,
+                                      bool rectify = false)
 {
 	if (!h || !images || !n) return fail(ORBX_ERR_INVALID, "null argument");
+	// rectify: width x height is the RAW frame; Extract runs on the rectified image, whose size is the table's
+	const int raw_w = width, raw_h = height;
+	if (rectify)
+	{
+		if (!h->rect_tab.p) return fail(ORBX_ERR_STATE, "orbx_set_rectification has not been called on this handle");
+		if (width != h->rect_sw || height != h->rect_sh) return fail(ORBX_ERR_INVALID, "frame size differs from the one the rectification maps were set for");
+		if (channels != 1) return fail(ORBX_ERR_INVALID, "rectification takes single-channel frames");
+	}
 	if (channels != 1 && channels != 3 && channels != 4)
 		return fail(ORBX_ERR_INVALID, "CV_Assert(ch == 1 || ch == 3 || ch == 4) (src/System.cc:127)");
 	if (frames < 1 || width < 1 || height < 1 || pitch < (size_t)width * channels) return fail(ORBX_ERR_INVALID, "bad image geometry");
 	CU(cudaSetDevice(h->device));
+	if (rectify) { width = h->rect_w; height = h->rect_h; }
 	orbx_status st = build_plan(h, width, height, frames);
 	if (st != ORBX_OK) return st;
 	const OrbxPlanDev& P = h->P;
 	const int ocap = P.sel_per_frame;
 	if (channels != 1) CU(h->color.ensure((size_t)frames * width * channels * height));
+	if (rectify) CU(h->color.ensure((size_t)frames * raw_w * raw_h));
 	// Chunk pipeline over two streams: upload of chunk c+1 and download of chunk c-1 overlap the kernels of chunk c.
 	// Level 0 is uploaded straight into the level-0 buffer (ComputePyramid's copyTo, :462).
 	int chunk = frames <= 32 ? frames : std::max(32, std::min(64, (frames + 3) / 4));
@@ -640,7 +671,18 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 	{
 		const int fc = std::min(chunk, frames - fb);
 		cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
-		if (channels == 1)
+		if (rectify)
+		{
+			// the rectification remap (Examples/Stereo/stereo_euroc.cc:100-101) fused into the upload: raw frames land in a staging
+			// buffer, the remap kernel writes level 0 of the pyramid
+			const size_t rstride = (size_t)raw_w * raw_h;
+			for (int f = fb; f < fb + fc; f++)
+				CU(cudaMemcpy2DAsync(h->color.p + (size_t)f * rstride, raw_w, images + (size_t)f * frame_stride, pitch, raw_w, raw_h,
+				                     cudaMemcpyHostToDevice, st));
+			orbx_launch_remap(h->color.p + (size_t)fb * rstride, raw_w, (int64_t)rstride, raw_w, raw_h, h->rect_tab.p,
+			                  h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, h->l0_stride, width, height, fc, st);
+		}
+		else if (channels == 1)
 		{
 			if (frame_stride == pitch * (size_t)height)
 				CU(cudaMemcpy2DAsync(h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, images + (size_t)fb * frame_stride, pitch, width,
@@ -1017,6 +1059,46 @@ orbx_status orbx_convert_to_gray(int device, const uint8_t* src, int width, int 
 	CU(cudaGetLastError());
 	CU(cudaMemcpy2D(dst, dst_pitch, dd.p, dpitch, width, height, cudaMemcpyDeviceToHost));
 	return ORBX_OK;
+}
+
+orbx_status orbx_remap(int device, const uint8_t* src, int src_width, int src_height, size_t src_pitch, const float* map1, const float* map2,
+                       size_t map_pitch, uint8_t* dst, int width, int height, size_t dst_pitch)
+{
+	if (!src || !map1 || !map2 || !dst || src_width < 1 || src_height < 1 || width < 1 || height < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	CU(cudaSetDevice(device));
+	std::vector<int2> tab;
+	pack_remap_table(map1, map2, map_pitch, width, height, tab);
+	const int64_t dpitch = align_up(width, 128);
+	DevBuf<uint8_t> ds, dd; DevBuf<int2> dt;
+	CU(ds.ensure((size_t)src_width * src_height)); CU(dd.ensure((size_t)dpitch * height)); CU(dt.ensure(tab.size()));
+	CU(cudaMemcpy2D(ds.p, src_width, src, src_pitch, src_width, src_height, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(dt.p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+	orbx_launch_remap(ds.p, src_width, 0, src_width, src_height, dt.p, dd.p, dpitch, 0, width, height, 1, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy2D(dst, dst_pitch, dd.p, dpitch, width, height, cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_set_rectification(orbx_handle h, const float* map1, const float* map2, size_t map_pitch, int width, int height, int src_width,
+                                   int src_height)
+{
+	if (!h || !map1 || !map2 || width < 1 || height < 1 || src_width < 1 || src_height < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	CU(cudaSetDevice(h->device));
+	std::vector<int2> tab;
+	pack_remap_table(map1, map2, map_pitch, width, height, tab);
+	CU(cudaStreamSynchronize(h->stream)); CU(cudaStreamSynchronize(h->stream2));
+	CU(h->rect_tab.ensure(tab.size()));
+	CU(cudaMemcpy(h->rect_tab.p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+	h->rect_w = width; h->rect_h = height; h->rect_sw = src_width; h->rect_sh = src_height;
+	return ORBX_OK;
+}
+
+orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, int frames, int src_width, int src_height, size_t pitch,
+                                         size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
+{
+	return extract_batch_impl(h, images, frames, src_width, src_height, pitch, frame_stride, 1, 0, kps, desc, cap, n, true);
 }
 
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,

@@ -76,6 +76,50 @@ __global__ void __launch_bounds__(256) k_gray_to_l0(const uint8_t* __restrict__ 
 }
 
 // =====================================================================================================
+// K0b remap_u8 — cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) of the rectification step in front of Extract
+//     (Examples/Stereo/stereo_euroc.cc:100-101). The float maps are converted once on the host, exactly as OpenCV converts them per
+//     call (cvRound(map * 32): integer position as two shorts, 5 + 5 fraction bits); the kernel is integer only: four taps, weights
+//     (32-fx)(32-fy)*32 ... summing to 2^15, (v + 2^14) >> 15. Writes level 0 of the pyramid directly, 4 pixels per thread.
+//     Traffic per output pixel: 8 B of table, ~1 B of source (the gathers of a warp hit neighbouring lines), 1 B written.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_remap_to_l0(const uint8_t* __restrict__ src, int64_t spitch, int64_t sstride, int sw, int sh,
+                                                    const int2* __restrict__ tab, uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride,
+                                                    int w, int h)
+{
+	const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
+	if (x0 >= w || y >= h) return;
+	const uint8_t* __restrict__ s = src + (int64_t)f * sstride;
+	const int2* __restrict__ t = tab + (int64_t)y * w + x0;
+	uint32_t out = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		if (x0 + j < w)
+		{
+			const int2 e = __ldg(t + j);
+			const int ix = (int)(short)(e.x & 0xffff), iy = e.x >> 16, fx = e.y & 31, fy = e.y >> 5;
+			int v00 = 0, v01 = 0, v10 = 0, v11 = 0;
+			if ((unsigned)ix < (unsigned)(sw - 1) && (unsigned)iy < (unsigned)(sh - 1))
+			{
+				const uint8_t* p = s + (int64_t)iy * spitch + ix;
+				v00 = __ldg(p); v01 = __ldg(p + 1); v10 = __ldg(p + spitch); v11 = __ldg(p + spitch + 1);
+			}
+			else
+			{
+				const bool x0in = (unsigned)ix < (unsigned)sw, x1in = (unsigned)(ix + 1) < (unsigned)sw;
+				const bool y0in = (unsigned)iy < (unsigned)sh, y1in = (unsigned)(iy + 1) < (unsigned)sh;
+				if (y0in && x0in) v00 = __ldg(s + (int64_t)iy * spitch + ix);
+				if (y0in && x1in) v01 = __ldg(s + (int64_t)iy * spitch + ix + 1);
+				if (y1in && x0in) v10 = __ldg(s + (int64_t)(iy + 1) * spitch + ix);
+				if (y1in && x1in) v11 = __ldg(s + (int64_t)(iy + 1) * spitch + ix + 1);
+			}
+			const int v = (v00 * ((32 - fx) * (32 - fy) * 32) + v01 * (fx * (32 - fy) * 32) + v10 * ((32 - fx) * fy * 32) + v11 * (fx * fy * 32) +
+			               (1 << 14)) >> 15;
+			out |= (uint32_t)v << (8 * j);
+		}
+	*reinterpret_cast<uint32_t*>(dst + (int64_t)f * dstride + (int64_t)y * dpitch + x0) = out;   // dpitch is a multiple of 4
+}
+
+// =====================================================================================================
 // K1  pyramid_resize_u8 — cv::resize INTER_LINEAR 8UC1 in OpenCV's fixed point for
 //     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
 //     exact float/double operation order; the kernel is integer only. One thread = 4 output pixels.
@@ -1202,6 +1246,13 @@ void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int c
 {
 	dim3 grid((w + 255) / 256, (h + 3) / 4, frames);
 	k_gray_to_l0<<<grid, 256, 0, st>>>(src, spitch, sstride, channels, rgb ? 0 : 2, dst, dpitch, dstride, w, h);
+}
+
+void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
+                       int64_t dstride, int w, int h, int frames, cudaStream_t st)
+{
+	dim3 grid((w + 255) / 256, (h + 3) / 4, frames);
+	k_remap_to_l0<<<grid, 256, 0, st>>>(src, spitch, sstride, sw, sh, tab, dst, dpitch, dstride, w, h);
 }
 
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)

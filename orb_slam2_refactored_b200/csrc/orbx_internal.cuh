@@ -88,6 +88,8 @@ int orbx_fast_tile_rows();
 // kernel launchers (orbx_extract.cu)
 void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,
                       int w, int h, int frames, cudaStream_t st);
+void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
+                       int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
 void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]

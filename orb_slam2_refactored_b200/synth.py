@@ -226,3 +226,25 @@ def initialization_pair(seed, n=1500, w=640, h=480, max_flips=60):
         f1['desc'][j] = _flip_bits(r, f1['desc'][s], r.randint(0, 12))
     prev = np.stack([k1['x'], k1['y']], 1).astype(np.float32)
     return f1, f2, prev
+
+
+def rectification_maps(seed, w, h, strength=1.0):
+    """Float32 (map_x, map_y) of an undistort + rectify warp like the ones cv::initUndistortRectifyMap hands to cv::remap in
+    Examples/Stereo/stereo_euroc.cc:88-101: pinhole + radial/tangential distortion + a small rotation. Near the borders the maps leave
+    the source image, which exercises the constant border."""
+    r = np.random.RandomState(seed + 31)
+    fx = fy = 0.61 * w
+    cx, cy = 0.49 * w + r.randn(), 0.52 * h + r.randn()
+    k1, k2, p1, p2 = -0.28 * strength, 0.07 * strength, 2e-4 * strength, 2e-5 * strength
+    a = 0.01 * strength * r.randn(3)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    U, _, Vt = np.linalg.svd(np.eye(3) + K)
+    R = U @ Vt
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    X = np.stack([(u - 0.5 * w) / fx, (v - 0.5 * h) / fy, np.ones_like(u)], -1) @ R      # rays of the rectified camera in the old one
+    x, y = X[..., 0] / X[..., 2], X[..., 1] / X[..., 2]
+    r2 = x * x + y * y
+    d = 1 + k1 * r2 + k2 * r2 * r2
+    xd = x * d + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * d + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return (fx * xd + cx).astype(np.float32), (fy * yd + cy).astype(np.float32)

@@ -38,6 +38,17 @@ def fast_cv(img, th):
     return np.array([(int(p.pt[0]), int(p.pt[1]), int(p.response)) for p in k], np.int32).reshape(-1, 3)
 
 
+def adversarial_maps(seed, w, h):
+    """Maps of a different size than the source with coordinates up to 10 px outside it and many exact x.5/32 ties."""
+    r = np.random.RandomState(seed)
+    dh, dw = h - 17, w - 11
+    mx = (r.rand(dh, dw) * (w + 20) - 10).astype(np.float32)
+    my = (r.rand(dh, dw) * (h + 20) - 10).astype(np.float32)
+    mx[::3, ::5] = (np.floor(mx[::3, ::5] * 32) + 0.5) / 32      # sx * 32 lands on .5: cvRound goes to even
+    my[1::4, ::7] = (np.floor(my[1::4, ::7] * 32) + 0.5) / 32
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
 def primitives():
     out = {}
     img = synth.image(42, 160, 120)
@@ -58,6 +69,14 @@ def primitives():
         out[f'color{ch}_crc'] = crc(col)
         out[f'gray{ch}_rgb'] = cv2.cvtColor(col, cv2.COLOR_RGB2GRAY if ch == 3 else cv2.COLOR_RGBA2GRAY)
         out[f'gray{ch}_bgr'] = cv2.cvtColor(col, cv2.COLOR_BGR2GRAY if ch == 3 else cv2.COLOR_BGRA2GRAY)
+    # cv::remap(INTER_LINEAR), float maps: a rectification warp and an adversarial map (out of range, 1/64-pixel rounding ties)
+    for name, src in (('img', img), ('noise', noise)):
+        hh, ww = src.shape
+        mx, my = synth.rectification_maps(5, ww, hh)
+        out[f'remap_rect_{name}'] = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+        ax, ay = adversarial_maps(6, ww, hh)
+        out[f'remap_adv_{name}'] = cv2.remap(src, ax, ay, cv2.INTER_LINEAR)
+        out[f'remap_{name}_crc'] = np.array([crc(mx), crc(my), crc(ax), crc(ay)])
     r = np.random.RandomState(3)
     y = r.randint(-60000, 60000, 4000).astype(np.float32); x = r.randint(-60000, 60000, 4000).astype(np.float32)
     y[:50] = 0; x[50:100] = 0; y[100] = 0; x[100] = 0

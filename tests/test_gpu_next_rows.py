@@ -62,3 +62,46 @@ def test_distinctive_descriptors(orbx, oracle_port):
     got = orbx.ComputeDistinctiveDescriptors(sets)
     want = np.array([oracle_port.distinctive_index(d) if len(d) else -1 for d in sets], np.int32)
     assert np.array_equal(got, want)
+
+
+def test_remap_standalone(orbx, oracle_port):
+    """cv::remap(INTER_LINEAR) of the rectification step (Examples/Stereo/stereo_euroc.cc:100-101): a rectification warp at the EuRoC
+    frame size, and an adversarial map (other output size, taps outside the source, 1/64-pixel rounding ties). Also against cv2's
+    own output stored in tests/golden/primitives.npz."""
+    import os
+    from test_oracle_golden import adversarial_maps, _inputs, G
+    img = synth.image(3, 752, 480)
+    mx, my = synth.rectification_maps(3, 752, 480)
+    assert np.array_equal(orbx.Remap(img, mx, my), oracle_port.remap(img, mx, my))
+    ax, ay = adversarial_maps(4, 752, 480)
+    assert np.array_equal(orbx.Remap(img, ax, ay), oracle_port.remap(img, ax, ay))
+    prim = np.load(os.path.join(G, 'primitives.npz'))
+    i = _inputs()
+    for name in ('img', 'noise'):
+        hh, ww = i[name].shape
+        rx, ry = synth.rectification_maps(5, ww, hh)
+        assert np.array_equal(orbx.Remap(i[name], rx, ry), prim[f'remap_rect_{name}'])
+        bx, by = adversarial_maps(6, ww, hh)
+        assert np.array_equal(orbx.Remap(i[name], bx, by), prim[f'remap_adv_{name}'])
+
+
+def test_extract_rectified_fused(orbx, oracle_port):
+    """Raw EuRoC-size frames in, remap fused into the upload, Extract on the rectified image: equals remap-then-Extract of the oracle;
+    level 0 of the pyramid is the rectified image. The maps crop the output to 736x464 to exercise a size change."""
+    raw = np.stack([synth.image(20 + s, 752, 480) for s in range(3)])
+    mx, my = synth.rectification_maps(8, 752, 480)
+    mx, my = np.ascontiguousarray(mx[8:472, 8:744]), np.ascontiguousarray(my[8:472, 8:744])
+    ex = orbx.ORBextractor(nfeatures=1200)
+    ex.SetRectification(mx, my, raw.shape[1:])
+    k, d = ex.ExtractBatchRectified(raw)
+    e = oracle_port.extractor(1200)
+    for f in range(len(raw)):
+        rect = oracle_port.remap(raw[f], mx, my)
+        ok, od = e.extract(rect)
+        assert len(ok) > 800
+        assert k[f].tobytes() == ok.tobytes() and np.array_equal(d[f], od)
+    assert np.array_equal(ex.GetImagePyramid(2)[0], oracle_port.remap(raw[2], mx, my))
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBextractor(nfeatures=500).ExtractBatchRectified(raw)        # no maps set
+    with pytest.raises(orbx.OrbxError):
+        ex.ExtractBatchRectified(raw[:, :400])                              # not the frame size the maps were set for
