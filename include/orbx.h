@@ -188,6 +188,11 @@ orbx_status orbx_remap(int device, const uint8_t* src, int src_width, int src_he
  * GetImagePyramid()[0] of such an extract is the rectified image. */
 orbx_status orbx_set_rectification(orbx_handle h, const float* map1, const float* map2, size_t map_pitch, int width, int height, int src_width,
                                    int src_height);
+/* Device-resident remap of a batch with the handle's maps, asynchronous on the handle's stream: d_raw holds `frames` raw frames of the
+ * size given to orbx_set_rectification; d_dst receives the rectified frames (dst_pitch a multiple of 4, >= width; the kernel writes
+ * whole 4-byte words, so a row may be written up to 3 bytes past `width`). */
+orbx_status orbx_rectify_batch_device(orbx_handle h, const uint8_t* d_raw, int frames, size_t pitch, size_t frame_stride, uint8_t* d_dst,
+                                      size_t dst_pitch, size_t dst_stride);
 orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, int frames, int src_width, int src_height, size_t pitch,
                                          size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
 /* ComputeStereoFromRGBD — src/System.cc:197-219: depth_map is width x height float32 (pitch in bytes). Host buffers. */

@@ -109,6 +109,7 @@ _SIGNATURES = {
     'orbx_remap': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
                              C.c_size_t]),
     'orbx_set_rectification': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'orbx_rectify_batch_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
     'orbx_extract_batch_rectified': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                                C.c_int, C.c_void_p]),
     'orbx_frame_create': (C.c_int, [C.POINTER(_FrameView), C.c_int, C.POINTER(C.c_void_p)]),

@@ -1095,6 +1095,19 @@ orbx_status orbx_set_rectification(orbx_handle h, const float* map1, const float
 	return ORBX_OK;
 }
 
+orbx_status orbx_rectify_batch_device(orbx_handle h, const uint8_t* d_raw, int frames, size_t pitch, size_t frame_stride, uint8_t* d_dst,
+                                      size_t dst_pitch, size_t dst_stride)
+{
+	if (!h || !d_raw || !d_dst || frames < 1) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (!h->rect_tab.p) return fail(ORBX_ERR_STATE, "orbx_set_rectification has not been called on this handle");
+	if (dst_pitch % 4 != 0 || dst_pitch < (size_t)h->rect_w) return fail(ORBX_ERR_INVALID, "dst_pitch must be a multiple of 4 and >= the rectified width");
+	CU(cudaSetDevice(h->device));
+	orbx_launch_remap(d_raw, (int64_t)pitch, (int64_t)frame_stride, h->rect_sw, h->rect_sh, h->rect_tab.p, d_dst, (int64_t)dst_pitch,
+	                  (int64_t)dst_stride, h->rect_w, h->rect_h, frames, h->stream);
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
 orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, int frames, int src_width, int src_height, size_t pitch,
                                          size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n)
 {
