@@ -28,7 +28,10 @@ def main():
         ref = bindings.Oracle('ref', native=True)
     except FileNotFoundError:
         ref = bindings.Oracle('port', native=True)
-    for tag, (n, w, h, npts) in {'C1': (1000, 640, 480, 1000), 'C2': (2000, 1241, 376, 2000), 'C4': (8000, 3840, 2160, 6000)}.items():
+    sizes = {'C1': (1000, 640, 480, 1000), 'C2': (2000, 1241, 376, 2000), 'C4': (8000, 3840, 2160, 6000)}
+    if '--quick' in sys.argv:      # profiling runs: the small case only
+        sizes = {'C1': sizes['C1']}
+    for tag, (n, w, h, npts) in sizes.items():
         fr = synth.frame(1, n=n, w=w, h=h)
         f = gc.make_frame(api, fr)
         mp0 = np.full(n, -1, np.int32)

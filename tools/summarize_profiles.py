@@ -38,7 +38,7 @@ def launches():
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(P, f'{R}_launches.txt'), 'w') as o:
         o.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES), window of {len(rows) - 1} launches\n')
-        o.write('# command: python bench.py --steps 3 --warmup 3 --skip-cpu --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144\n')
+        o.write('# command: python bench.py --steps 3 --warmup 3 --batch 256 --skip-cpu --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144 (tools/profile_one.sh)\n')
         o.write(f'{"kernel":28s} {"n":>4s} {"sum_us":>10s} {"avg_us":>9s} {"share":>7s}\n')
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             o.write(f'{k[:28]:28s} {len(v):4d} {sum(v) / 1e3:10.1f} {sum(v) / len(v) / 1e3:9.1f} {sum(v) / tot:7.3f}\n')
@@ -71,14 +71,19 @@ def to_bytes(val, unit):
 
 
 launches()
-traffic = {}
-for k in ('k_fast_cells', 'k_gauss7', 'k_pyramid_resize', 'k_orient_describe', 'k_quadtree', 'k_knn2_partial'):
+tj = os.path.join(P, f'{R}_traffic.json')
+traffic = json.load(open(tj)) if os.path.exists(tj) else {}      # captures arrive one gpurun call at a time: keep what is already there
+NOTES = {'k_guided_search': 'one search, 1000 keypoints x 1000 map points (tools/guided_probe.py), a cluster of 8 CTAs',
+         'k_remap_to_l0': 'one launch of 256 frames 752x480 (bench.py remap block)',
+         'k_stereo_match': 'one launch of 64 C2 stereo pairs (bench.py stereo block)'}
+for k in ('k_fast_cells', 'k_gauss7', 'k_pyramid_resize', 'k_orient_describe', 'k_quadtree', 'k_knn2_partial', 'k_guided_search', 'k_remap_to_l0',
+          'k_stereo_match'):
     d = full(k)
     if d and 'dram__bytes_read.sum' in d:
         traffic[k] = {'dram_bytes_per_launch': to_bytes(*d['dram__bytes_read.sum']) + to_bytes(*d['dram__bytes_write.sum']),
                       'launch_us': float(d['gpu__time_duration.sum'][0].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}[d['gpu__time_duration.sum'][1]],
                       'grid': d['launch__grid_size'][0],
-                      'note': 'one launch of the bench default batch (256 frames); k_gauss7 / k_pyramid_resize: one level of it'}
+                      'note': NOTES.get(k, 'one launch of the bench default batch (256 frames); k_gauss7 / k_pyramid_resize: one level of it')}
 if traffic:
     json.dump(traffic, open(os.path.join(P, f'{R}_traffic.json'), 'w'), indent=1)
     print(traffic)
