@@ -277,7 +277,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			L.ytab_base = (int)yofs.size();
 			yofs.resize(yofs.size() + L.h); ycoef.resize(ycoef.size() + L.h);
 			resize_tables(L.h, P.lv[s - 1].h, yofs.data() + L.ytab_base, ycoef.data() + L.ytab_base);
-			// the resize kernel stages the source rows/columns of a 128 x 32 output tile in shared memory
+			// the resize kernel stages the source rows/columns of one output tile (128 x 128) in shared memory
 			const int th = orbx_pyramid_tile_rows(), tw = orbx_pyramid_tile_cols();
 			int max_rows = 0, max_bytes = 0;
 			for (int y0 = 0; y0 < L.h; y0 += th)

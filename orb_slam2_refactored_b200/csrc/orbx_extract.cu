@@ -124,14 +124,18 @@ __global__ void __launch_bounds__(256) k_remap_to_l0(const uint8_t* __restrict__
 //     ComputePyramid (src/ORBextractor.cc:455-470). Coefficient tables are built on the host with the
 //     exact float/double operation order; the kernel is integer only. One thread = 4 output pixels.
 // =====================================================================================================
-#define PY_TW 128     // output tile
-#define PY_TH 32
-#define PY_SRC 72     // source rows a tile may touch: 31 * scaleFactor + 2; scale factors up to 2.2 (checked on the host)
+#define PY_TW 128     // output tile: 128 columns x 128 rows per CTA; warp w owns rows [16w, 16w + 16), lane l owns columns [4l, 4l + 4)
+#define PY_TH 128
+#define PY_RW 16      // output rows per warp
+#define PY_SRC 288    // source rows a tile may touch: 127 * scaleFactor + 2; scale factors up to 2.2 (checked on the host)
 #define PY_SW 304     // source bytes per staged row: 15 (alignment) + 128 * scaleFactor + 2, rounded up to 16
 __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, const int level)
 {
-	// The source rows/columns an output tile needs are staged in shared memory with 16-byte async copies (level buffers
-	// are padded: pitch a multiple of 128, 256 spare bytes in front and behind); then one thread = 4 output columns x 4 rows.
+	// The source rows/columns an output tile needs are staged in shared memory with 16-byte async copies (level buffers are padded:
+	// pitch a multiple of 128, 256 spare bytes in front and behind). A thread then walks DOWN its 4 columns: the horizontal pass of a
+	// source row (2 taps x 4 columns) is computed once and kept in registers while the 1-2 output rows that need it are produced, so
+	// the column offsets and coefficients are loaded once per thread and a source row is interpolated ~1.25 instead of 2 times per
+	// output row.
 	extern __shared__ __align__(16) uint8_t stile[];
 	const OrbxLevel& D = P.lv[level];
 	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
@@ -160,47 +164,63 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 			cp_async16(stile + r * rs + c * 16, g0 + (int64_t)r * sp + c * 16);
 		}
 	}
-	const int q = tid & 31, grp = tid >> 5;
+	const int lane = tid & 31, warp = tid >> 5;
 	int x0r[4], x1r[4], a0[4], a1[4];
 #pragma unroll
 	for (int j = 0; j < 4; j++)
 	{
-		const int dx = min(dx0 + 4 * q + j, D.w - 1);   // columns past the edge repeat the last one; they land in row padding
+		const int dx = min(dx0 + 4 * lane + j, D.w - 1);   // columns past the edge repeat the last one; they land in row padding
 		const int sx = __ldg(xofs + dx);
 		const short2 a = __ldg(P.xcoef + D.xtab_base + dx);
 		x0r[j] = sx - xa; x1r[j] = min(sx + 1, sw - 1) - xa;
 		a0[j] = a.x; a1[j] = a.y;
 	}
-	int sy0[PY_TH / 8]; short2 bb[PY_TH / 8];
-#pragma unroll
-	for (int k = 0; k < PY_TH / 8; k++)
+	// the warp's rows: lane k holds source row and coefficients of row k, broadcast by shuffle in the loop
+	const int wy0 = dy0 + warp * PY_RW;
+	int my_sy = 0, my_b = 0;
+	if (lane < PY_RW)
 	{
-		const int dy = min(dy0 + grp + 8 * k, D.h - 1);
-		sy0[k] = __ldg(yofs + dy);
-		bb[k] = __ldg(ycoef + dy);
+		const int dy = min(wy0 + lane, D.h - 1);
+		my_sy = __ldg(yofs + dy);
+		const short2 b = __ldg(ycoef + dy);
+		my_b = (int)(uint16_t)b.x | ((int)b.y << 16);
 	}
 	cp_async_wait_all();
 	__syncthreads();
-	if (dx0 + 4 * q >= D.w)
-		return;
+	if (wy0 >= D.h) return;
+	const bool store = dx0 + 4 * lane < D.w;
+
+	// horizontal pass of staged row r for this thread's 4 columns: (s[x0] * a0 + s[x1] * a1) >> 4
+	auto hrow = [&](int r, int (&h)[4]) {
+		const uint8_t* __restrict__ row = stile + (r - s_lo) * rs;
 #pragma unroll
-	for (int k = 0; k < PY_TH / 8; k++)
+		for (int j = 0; j < 4; j++) h[j] = ((int)row[x0r[j]] * a0[j] + (int)row[x1r[j]] * a1[j]) >> 4;
+	};
+	int rc = -2, h0[4], h1[4];          // h0 = row rc, h1 = row min(rc + 1, sh - 1)
+	const int nrows = min(PY_RW, D.h - wy0);
+	for (int k = 0; k < nrows; k++)
 	{
-		const int dy = dy0 + grp + 8 * k;
-		if (dy >= D.h) break;
-		const uint8_t* r0 = stile + (sy0[k] - s_lo) * rs;
-		const uint8_t* r1 = stile + (min(sy0[k] + 1, sh - 1) - s_lo) * rs;
-		const int b0 = bb[k].x, b1 = bb[k].y;
+		const int r = __shfl_sync(0xffffffffu, my_sy, k), bw = __shfl_sync(0xffffffffu, my_b, k);
+		if (r != rc)
+		{
+			if (r == rc + 1)
+			{
+#pragma unroll
+				for (int j = 0; j < 4; j++) h0[j] = h1[j];
+			}
+			else hrow(r, h0);
+			hrow(min(r + 1, sh - 1), h1);      // at the last source row both taps are that row, as in the reference table
+			rc = r;
+		}
+		const int b0 = (int)(short)(bw & 0xffff), b1 = bw >> 16;
 		uint32_t out = 0;
 #pragma unroll
 		for (int j = 0; j < 4; j++)
 		{
-			const int h0 = (int)r0[x0r[j]] * a0[j] + (int)r0[x1r[j]] * a1[j];
-			const int h1 = (int)r1[x0r[j]] * a0[j] + (int)r1[x1r[j]] * a1[j];
-			const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;   // coefficients sum to 2048: v in [0, 255]
+			const int v = (((b0 * h0[j]) >> 16) + ((b1 * h1[j]) >> 16) + 2) >> 2;   // coefficients sum to 2048: v in [0, 255]
 			out |= (uint32_t)v << (8 * j);
 		}
-		*reinterpret_cast<uint32_t*>(dst + (int64_t)dy * D.pitch + dx0 + 4 * q) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
+		if (store) *reinterpret_cast<uint32_t*>(dst + (int64_t)(wy0 + k) * D.pitch + dx0 + 4 * lane) = out;   // pitch is a multiple of 128: in-row padding absorbs the tail
 	}
 }
 
@@ -1259,7 +1279,15 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
 	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + PY_TH - 1) / PY_TH, P.frames);
-	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem)
+	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem), up to PY_SRC * PY_SW = 86 KB
+	static bool attr_set[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 64 && !attr_set[dev])
+	{
+		cudaFuncSetAttribute(k_pyramid_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
+		attr_set[dev] = true;
+	}
 	k_pyramid_resize<<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 }
 
