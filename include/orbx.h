@@ -260,6 +260,16 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame cur, const orbx_came
 /* ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:614-694. prev_matched: f1->n (x, y) pairs, in/out; matches12: f1->n, out. */
 orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size,
                                            float nnratio, int check_orientation, int* nmatches);
+/* DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h: std::map<NodeId, std::vector<unsigned>>) flattened: node ids ascending,
+ * the features of node k are indices[start[k] .. start[k+1]). */
+typedef struct orbx_feature_vector { int32_t nnodes; const uint32_t* node_ids; const int32_t* start; const uint32_t* indices; } orbx_feature_vector;
+/* ORBmatcher::SearchByBoW — src/ORBmatcher.cc:452-516 (KeyFrame vs Frame: valid2 == NULL) and :696-766 (KeyFrame vs KeyFrame), with
+ * FeatureVectorIterator (:406-450) and CheckOrientation. f1 is the (first) key frame, f2 the frame / second key frame, both resident.
+ * valid1 / valid2: per keypoint, map point present && !isBad(). match2 (f2->n entries, out) = the keypoint of f1 matched to keypoint
+ * idx2 of f2, or -1: `matches[idx2] = mappoints1[match2[idx2]]` for the first variant, `matches12[match2[idx2]] = mappoints2[idx2]`
+ * for the second. The vocabulary transform that produces the feature vectors is not part of this library. */
+orbx_status orbx_search_by_bow(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* valid1, orbx_frame f2, const orbx_feature_vector* fv2,
+                               const uint8_t* valid2, float nnratio, int check_orientation, int32_t* match2, int* nmatches);
 /* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1), the kernel's duration (CUDA events) and
  * the microseconds its phases took (enumeration, -, -, distances, rounds, finalisation, and the part of `rounds` spent staging state into
  * shared memory; %globaltimer). Any pointer may be NULL; phase_us needs room for 7 floats. */

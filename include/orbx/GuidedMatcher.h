@@ -5,6 +5,8 @@
 //                                                                          include/ORBmatcher.h:58,  src/ORBmatcher.cc:315-382
 //   int ORBmatcher::SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular)
 //                                                                          include/ORBmatcher.h:62,  src/ORBmatcher.cc:1279-1362
+//   int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, std::vector<MapPoint*>&) / (KeyFrame*, KeyFrame*, std::vector<MapPoint*>&)
+//                                                                          include/ORBmatcher.h:72-73, src/ORBmatcher.cc:406-516, 696-766
 //   int ORBmatcher::SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int windowSize)
 //                                                                          include/ORBmatcher.h:80,  src/ORBmatcher.cc:614-694
 //
@@ -177,7 +179,70 @@ public:
 		return nmatches;
 	}
 
+	// src/ORBmatcher.cc:452-516 — KeyFrameT needs featureVector (DBoW2::FeatureVector, i.e. std::map<NodeId, std::vector<unsigned>>),
+	// GetMapPointMatches(); FrameT needs featureVector. dev1 / dev2 hold keyframe's and frame's keypointsUn + descriptors.
+	template <class KeyFrameT, class FrameT, class MapPointT>
+	int SearchByBoW(KeyFrameT* keyframe, DeviceFrame& dev1, FrameT& frame, DeviceFrame& dev2, std::vector<MapPointT*>& matches) const
+	{
+		const std::vector<MapPointT*> mappoints1 = keyframe->GetMapPointMatches();
+		const size_t n2 = frame.keypointsUn.size();
+		matches.assign(n2, nullptr);                                                          // :456
+		std::vector<uint8_t> valid1(mappoints1.size());
+		for (size_t i = 0; i < valid1.size(); i++) valid1[i] = mappoints1[i] && !mappoints1[i]->isBad();
+		std::vector<int32_t> match2(n2 ? n2 : 1);
+		const int nmatches = Bow(keyframe->featureVector, valid1, dev1, frame.featureVector, nullptr, dev2, match2);
+		for (size_t c = 0; c < n2; c++)
+			if (match2[c] >= 0) matches[c] = mappoints1[(size_t)match2[c]];                     // :503
+		return nmatches;
+	}
+
+	// src/ORBmatcher.cc:696-766
+	template <class KeyFrameT, class MapPointT>
+	int SearchByBoW(KeyFrameT* keyframe1, DeviceFrame& dev1, KeyFrameT* keyframe2, DeviceFrame& dev2, std::vector<MapPointT*>& matches12) const
+	{
+		const std::vector<MapPointT*> mappoints1 = keyframe1->GetMapPointMatches(), mappoints2 = keyframe2->GetMapPointMatches();
+		matches12.assign(mappoints1.size(), nullptr);                                         // :707
+		std::vector<uint8_t> valid1(mappoints1.size()), valid2(mappoints2.size());
+		for (size_t i = 0; i < valid1.size(); i++) valid1[i] = mappoints1[i] && !mappoints1[i]->isBad();
+		for (size_t i = 0; i < valid2.size(); i++) valid2[i] = mappoints2[i] && !mappoints2[i]->isBad();
+		std::vector<int32_t> match2(valid2.size() ? valid2.size() : 1);
+		const int nmatches = Bow(keyframe1->featureVector, valid1, dev1, keyframe2->featureVector, &valid2, dev2, match2);
+		for (size_t c = 0; c < valid2.size(); c++)
+			if (match2[c] >= 0) matches12[(size_t)match2[c]] = mappoints2[c];                   // :752
+		return nmatches;
+	}
+
 private:
+	struct FlatFeatureVector
+	{
+		std::vector<uint32_t> ids, indices;
+		std::vector<int32_t> start;
+		orbx_feature_vector view() const { return orbx_feature_vector{ (int32_t)ids.size(), ids.data(), start.data(), indices.data() }; }
+	};
+	template <class FeatureVectorT> static FlatFeatureVector Flatten(const FeatureVectorT& fv)
+	{
+		FlatFeatureVector f;
+		f.start.push_back(0);
+		for (const auto& node : fv)      // std::map: ascending node id
+		{
+			f.ids.push_back((uint32_t)node.first);
+			for (auto i : node.second) f.indices.push_back((uint32_t)i);
+			f.start.push_back((int32_t)f.indices.size());
+		}
+		return f;
+	}
+	template <class FeatureVectorT>
+	int Bow(const FeatureVectorT& fv1, const std::vector<uint8_t>& valid1, DeviceFrame& dev1, const FeatureVectorT& fv2,
+		const std::vector<uint8_t>* valid2, DeviceFrame& dev2, std::vector<int32_t>& match2) const
+	{
+		const FlatFeatureVector a = Flatten(fv1), b = Flatten(fv2);
+		const orbx_feature_vector va = a.view(), vb = b.view();
+		int nmatches = 0;
+		Check(orbx_search_by_bow(dev1.Handle(), &va, valid1.data(), dev2.Handle(), &vb, valid2 ? valid2->data() : nullptr, fNNRatio_,
+			checkOrientation_ ? 1 : 0, match2.data(), &nmatches), "SearchByBoW");
+		return nmatches;
+	}
+
 	// frame.mappoints as the C ABI's codes: -1 null, -2 / -3 a map point with / without observations
 	template <class FrameT> static std::vector<int32_t> Encode(const FrameT& frame)
 	{

@@ -34,6 +34,10 @@ class FrameView(C.Structure):
                 ('nlevels', C.c_int32), ('scale_factors', C.c_void_p)]
 
 
+class FeatureVector(C.Structure):
+    _fields_ = [('nnodes', C.c_int32), ('node_ids', C.c_void_p), ('start', C.c_void_p), ('indices', C.c_void_p)]
+
+
 class Pose(C.Structure):
     _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3)]
 
@@ -103,6 +107,8 @@ class Oracle:
         f('time_search_local_map', C.c_double, [C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int])
         f('time_search_last_frame', C.c_double, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.POINTER(Pose), C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int])
+        f('search_by_bow', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
+                                     C.c_void_p, C.c_float, C.c_int, C.c_void_p])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
@@ -281,6 +287,25 @@ class Oracle:
         poses = self._poses(cur_pose, last_pose)
         return self._time_search_last_frame(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(poses[0]), C.byref(poses[1]),
                                             _p(mp), _p(pts), _p(pt_desc), len(pts), th, int(monocular), nnratio, int(check_orientation), reps)
+
+    @staticmethod
+    def _fv(fv):
+        """fv: (node_ids uint32 ascending, start int32 [nnodes + 1], indices uint32)."""
+        ids = np.ascontiguousarray(fv[0], np.uint32); start = np.ascontiguousarray(fv[1], np.int32); idx = np.ascontiguousarray(fv[2], np.uint32)
+        return FeatureVector(len(ids), ids.ctypes.data, start.ctypes.data, idx.ctypes.data), (ids, start, idx)
+
+    def search_by_bow(self, f1, fv1, valid1, f2, fv2, valid2=None, nnratio=0.7, check_orientation=True):
+        """SearchByBoW; valid2 None = KeyFrame vs Frame, else KeyFrame vs KeyFrame. Returns (nmatches, match2)."""
+        v1, k1 = self._frame_view(f1)
+        v2, k2 = self._frame_view(f2)
+        c1, keep1 = self._fv(fv1)
+        c2, keep2 = self._fv(fv2)
+        va1 = np.ascontiguousarray(valid1, np.uint8)
+        va2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m2 = np.empty(v2.n, np.int32)
+        n = self._search_by_bow(C.byref(v1), C.byref(c1), _p(va1), C.byref(v2), C.byref(c2), None if va2 is None else _p(va2), nnratio,
+                                int(check_orientation), _p(m2))
+        return n, m2
 
     def search_for_initialization(self, f1, f2, prev_matched, window=100, nnratio=0.9, check_orientation=True):
         v1, k1 = self._frame_view(f1)

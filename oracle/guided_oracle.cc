@@ -368,6 +368,63 @@ double orc_time_search_last_frame(const oracle_frame_view* f, const oracle_camer
 	return total / (reps > 0 ? reps : 1);
 }
 
+// SearchByBoW (:452-516 KeyFrame vs Frame when valid2 == NULL, :696-766 KeyFrame vs KeyFrame otherwise). FeatureVectorIterator
+// (:406-450) walks the nodes both feature vectors share, in ascending node id: a merge join of the two sorted id arrays.
+int orc_search_by_bow(const oracle_frame_view* f1, const oracle_feature_vector* fv1, const uint8_t* valid1, const oracle_frame_view* f2,
+                      const oracle_feature_vector* fv2, const uint8_t* valid2, float nnratio, int check_ori, int32_t* match2)
+{
+	for (int i = 0; i < f2->n; i++) match2[i] = -1;
+	std::vector<std::pair<int, int>> matchIds;      // (idx1, idx2) in acceptance order
+	int nmatches = 0;
+	int a = 0, b = 0;
+	while (a < fv1->nnodes && b < fv2->nnodes)
+	{
+		if (fv1->node_ids[a] < fv2->node_ids[b]) { a++; continue; }
+		if (fv2->node_ids[b] < fv1->node_ids[a]) { b++; continue; }
+		for (int p1 = fv1->start[a]; p1 < fv1->start[a + 1]; p1++)
+		{
+			const int idx1 = (int)fv1->indices[p1];
+			if (!valid1[idx1]) continue;                                            // :471-472, :719-720
+			int best = 256, second = 256, bestIdx2 = -1;
+			for (int p2 = fv2->start[b]; p2 < fv2->start[b + 1]; p2++)
+			{
+				const int idx2 = (int)fv2->indices[p2];
+				if (match2[idx2] >= 0) continue;                                    // matches[idx2] / matched2[idx2]
+				if (valid2 && !valid2[idx2]) continue;                             // :731-732
+				const int d = hamming256(f1->desc + (size_t)idx1 * 32, f2->desc + (size_t)idx2 * 32);
+				if (d < best) { second = best; best = d; bestIdx2 = idx2; }
+				else if (d < second) second = d;
+			}
+			const bool low = valid2 ? best < TH_LOW : best <= TH_LOW;               // :750 vs :501
+			if (low && best < nnratio * second)
+			{
+				match2[bestIdx2] = idx1;
+				nmatches++;
+				matchIds.push_back({ idx1, bestIdx2 });
+			}
+		}
+		a++; b++;
+	}
+	if (!check_ori) return nmatches;
+	std::vector<int> erased;
+	if (!valid2)
+	{
+		// CheckOrientation(keyframe->keypointsUn, frame.keypointsUn, (idx1, bestIdx2), matches) (:512): status indexed by idx2
+		nmatches = check_orientation(matchIds, &f1->kps_un[0].angle, sizeof(oracle_keypoint), &f2->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+		for (int i2 : erased) match2[i2] = -1;
+	}
+	else
+	{
+		// CheckOrientation(keypoints2, keypoints1, (bestIdx2, idx1), matches12) (:763): status indexed by idx1
+		std::vector<std::pair<int, int>> swapped;
+		std::vector<int> of1((size_t)f1->n, -1);
+		for (const auto& m : matchIds) { swapped.push_back({ m.second, m.first }); of1[m.first] = m.second; }
+		nmatches = check_orientation(swapped, &f2->kps_un[0].angle, sizeof(oracle_keypoint), &f1->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+		for (int i1 : erased) match2[of1[i1]] = -1;
+	}
+	return nmatches;
+}
+
 int orc_search_for_initialization(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev, int32_t* matches12, int window,
                                   float nnratio, int check_ori)
 {

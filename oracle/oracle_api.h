@@ -128,6 +128,14 @@ int ORACLE_FN(search_local_map)(const oracle_frame_view* frame, int32_t* frame_m
 int ORACLE_FN(search_last_frame)(const oracle_frame_view* cur, const oracle_camera* cam, const oracle_pose* cur_pose,
                                  const oracle_pose* last_pose, int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc,
                                  int npts, float th, int monocular, float nnratio, int check_orientation);
+// DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h) as CSR: node ids ascending, the feature indices of node k are
+// indices[start[k] .. start[k+1])
+typedef struct oracle_feature_vector { int32_t nnodes; const uint32_t* node_ids; const int32_t* start; const uint32_t* indices; } oracle_feature_vector;
+// SearchByBoW: KeyFrame vs Frame (src/ORBmatcher.cc:452-516) when valid2 == NULL, KeyFrame vs KeyFrame (:696-766) otherwise.
+// valid1 / valid2: per keypoint, map point present && !isBad(). match2 (f2->n entries, out): the keypoint of frame 1 matched to
+// keypoint idx2 of frame 2, or -1. Returns nmatches.
+int ORACLE_FN(search_by_bow)(const oracle_frame_view* f1, const oracle_feature_vector* fv1, const uint8_t* valid1, const oracle_frame_view* f2,
+                             const oracle_feature_vector* fv2, const uint8_t* valid2, float nnratio, int check_orientation, int32_t* match2);
 // CPU-baseline timing of the two tracking searches: the Frame (grid included) and the map points are built once, outside the timed
 // region; each repetition restores frame.mappoints and times the matcher call alone. Returns mean seconds per call.
 double ORACLE_FN(time_search_local_map)(const oracle_frame_view* frame, const int32_t* frame_mp, const oracle_track_point* pts,

@@ -5,6 +5,7 @@
 //   include/Frame.h:40-81                      (ImageBounds, ScalePyramidInfo, FeaturesGrid declarations)
 //   src/ORBmatcher.cc:37-58, 249-309           (constants, CheckOrientation)
 //   src/ORBmatcher.cc:315-382                  SearchByProjection(Frame&, mappoints, th)       — local-map tracking
+//   src/ORBmatcher.cc:406-516, 696-766         FeatureVectorIterator, SearchByBoW x2            — reference keyframe / relocalisation / loop
 //   src/ORBmatcher.cc:614-694                  SearchForInitialization                          — monocular initialisation
 //   src/ORBmatcher.cc:1279-1362                SearchByProjection(currFrame, lastFrame, th, m)  — motion-model tracking
 // compiles by line range (oracle/Makefile, rule guided_gen.cc) with the reference's own include/Point.h,
@@ -35,7 +36,6 @@ struct MapPoint
 	cv::Mat GetDescriptor() const { return descriptor; }
 };
 
-class KeyFrame;
 class Sim3;
 
 struct Frame
@@ -52,12 +52,24 @@ struct Frame
 	CameraPose pose;
 	ScalePyramidInfo pyramid;
 	ImageBounds imageBounds;
+	DBoW2::FeatureVector featureVector;
 
 	// src/Frame.cc:216-219
 	std::vector<size_t> GetFeaturesInArea(float x, float y, float r, int minLevel = -1, int maxLevel = -1) const
 	{
 		return grid.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
 	}
+};
+
+// include/KeyFrame.h:78, 110, 141-148: what SearchByBoW reads of a KeyFrame
+struct KeyFrame
+{
+	int N = 0;
+	KeyPoints keypointsUn;
+	cv::Mat descriptorsL;
+	DBoW2::FeatureVector featureVector;
+	std::vector<MapPoint*> mappoints;
+	std::vector<MapPoint*> GetMapPointMatches() const { return mappoints; }
 };
 
 // include/ORBmatcher.h:47-104, the members compiled here
@@ -68,6 +80,8 @@ public:
 	static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
 	int SearchByProjection(Frame& frame, const std::vector<MapPoint*>& mappoints, float th = 3);
 	int SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular);
+	int SearchByBoW(KeyFrame* keyframe, Frame& frame, std::vector<MapPoint*>& matches);
+	int SearchByBoW(KeyFrame* keyframe1, KeyFrame* keyframe2, std::vector<MapPoint*>& matches12);
 	int SearchForInitialization(Frame& frame1, Frame& frame2, std::vector<cv::Point2f>& prevMatched, std::vector<int>& matches12,
 		int windowSize = 10);
 

@@ -50,6 +50,10 @@ class _FrameView(C.Structure):
                 ('nlevels', C.c_int32), ('scale_factors', C.c_void_p)]
 
 
+class _FeatureVector(C.Structure):
+    _fields_ = [('nnodes', C.c_int32), ('node_ids', C.c_void_p), ('start', C.c_void_p), ('indices', C.c_void_p)]
+
+
 class _Pose(C.Structure):
     _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3)]
 
@@ -123,6 +127,8 @@ _SIGNATURES = {
     'orbx_search_for_initialization': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
                                                  C.POINTER(C.c_int)]),
     'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p]),
+    'orbx_search_by_bow': (C.c_int, [C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_float,
+                                     C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
 }
 
@@ -491,6 +497,23 @@ class ORBmatcher:
                                                           _p(pts), _p(desc), len(pts), th, int(bool(monocular)),
                                                           int(bool(self.checkOrientation_)), C.byref(n)))
         return n.value
+
+    def SearchByBoW(self, keyframe, featureVector1, valid1, frame, featureVector2, valid2=None):
+        """SearchByBoW(KeyFrame*, Frame&, matches) — src/ORBmatcher.cc:452-516 — when valid2 is None, SearchByBoW(KeyFrame*, KeyFrame*,
+        matches12) — :696-766 — otherwise. Feature vectors are (node_ids, start, indices) CSR triples of DBoW2::FeatureVector; valid*:
+        per keypoint, map point present and not bad. Returns (nmatches, match2) with match2[idx2] = matched keypoint of `keyframe` or -1."""
+        def fv(t):
+            ids = np.ascontiguousarray(t[0], np.uint32); start = np.ascontiguousarray(t[1], np.int32); idx = np.ascontiguousarray(t[2], np.uint32)
+            return _FeatureVector(len(ids), ids.ctypes.data, start.ctypes.data, idx.ctypes.data), (ids, start, idx)
+        c1, k1 = fv(featureVector1)
+        c2, k2 = fv(featureVector2)
+        v1 = np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m2 = np.empty(max(frame.N, 1), np.int32)
+        n = C.c_int()
+        _check(lib().orbx_search_by_bow(keyframe._h, C.byref(c1), _p(v1), frame._h, C.byref(c2), None if v2 is None else _p(v2), self.fNNRatio_,
+                                        int(bool(self.checkOrientation_)), _p(m2), C.byref(n)))
+        return n.value, m2[:frame.N]
 
     def SearchForInitialization(self, frame1, frame2, prevMatched, windowSize=10):
         """src/ORBmatcher.cc:614-694. prevMatched: (N1, 2) float32, updated in place; returns (nmatches, matches12)."""

@@ -35,7 +35,7 @@ constexpr int G_THREADS = 1024;
 constexpr int G_SMEM_INTS = 200 * 1024 / 4;   // dynamic shared memory of the search kernel, in ints
 constexpr int G_CLUSTER = 8;          // CTAs (= SMs) of one search: a thread-block cluster, the portable maximum
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;                        // src/ORBmatcher.cc:41-43
-constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2;
+constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2, MODE_BOW = 3;
 
 // candidate entry: keypoint index [0:19) | octave [19:23) | distance [23:32) (511 = removed by the uright gate)
 constexpr int E_IDX_BITS = 19, E_LVL_BITS = 4;
@@ -85,6 +85,9 @@ struct GuidedArgs
 	const float* prev_in;        // INIT: prevMatched on entry
 	int32_t* frame_mp;           // out: frame.mappoints (LOCAL_MAP, LAST_FRAME); INIT: matches12 [npts]
 	int* result;                 // [0] nmatches, [1] entries, [2] rounds, [3] overflow
+	// BOW: point i = (keypoint of frame 1, first position and count of its vocabulary node's features in bow_idx2)
+	const int* bow_pt; const uint32_t* bow_idx2; const uint8_t* bow_valid2;
+	int bow_strict, ori_swap;    // best < TH_LOW instead of <= (:750 vs :501); CheckOrientation's argument order (:763 vs :512)
 	unsigned long long* stamps;  // [8] %globaltimer at the phase boundaries (diagnostics)
 	int use_smem;                // cell offsets, owner, its initial value and choice in dynamic shared memory
 	int smem_ints;               // dynamic shared memory of this launch, in ints
@@ -357,6 +360,44 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 	const int L = A.lanes, lig = tid & (L - 1);
 	const unsigned gmask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << ((tid & 31) & ~(L - 1)));
 	int* const cursor = A.cursor + A.parity;
+	if (A.mode == MODE_BOW)
+	{
+		// SearchByBoW: the candidates of a point are the features of frame 2 in the same vocabulary node, in the node's order (:477)
+		for (int i = gid / L; i < npts; i += gstride / L)
+		{
+			const int s0 = A.bow_pt[3 * i + 1], len = A.bow_pt[3 * i + 2];
+			const int q = (len + L - 1) / L;
+			const int c0 = s0 + min(lig * q, len), c1 = s0 + min(lig * q + q, len);
+			int c = 0;
+			for (int p2 = c0; p2 < c1; p2++) c += !A.bow_valid2 || A.bow_valid2[A.bow_idx2[p2]];     // :731-732
+			int inc = c;
+			for (int d = 1; d < L; d <<= 1)
+			{
+				const int o = __shfl_up_sync(gmask, inc, d, L);
+				if (lig >= d) inc += o;
+			}
+			const int tot = __shfl_sync(gmask, inc, L - 1, L);
+			int base = 0;
+			if (lig == 0)
+			{
+				if (tot > 0) base = atomicAdd(cursor, tot);
+				off[i] = base;
+				A.len[i] = tot;
+			}
+			base = __shfl_sync(gmask, base, 0, L);
+			int p = base + inc - c;
+			if (base + tot <= A.cap)
+				for (int p2 = c0; p2 < c1; p2++)
+				{
+					const uint32_t idx2 = A.bow_idx2[p2];
+					if (A.bow_valid2 && !A.bow_valid2[idx2]) continue;
+					A.list[p] = idx2;
+					A.entry_pt[p] = i;
+					p++;
+				}
+		}
+	}
+	else
 	for (int i = gid / L; i < npts; i += gstride / L)
 	{
 		float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f;
@@ -470,7 +511,8 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 		const int idx = (int)(ent & E_IDX_MASK), i = A.entry_pt[e];
 		uint32_t d;
 		const float ur2 = A.uright2[idx];
-		if (A.mode != MODE_INIT && ur2 > 0 && fabsf(A.pur[i] - ur2) > A.prad[i]) d = E_SKIP;
+		if (A.mode == MODE_BOW) d = (uint32_t)hamming256(A.pt_desc + (size_t)A.bow_pt[3 * i] * 32, A.desc2 + (size_t)idx * 32);
+		else if (A.mode != MODE_INIT && ur2 > 0 && fabsf(A.pur[i] - ur2) > A.prad[i]) d = E_SKIP;
 		else d = (uint32_t)hamming256(A.pt_desc + (size_t)i * 32, A.desc2 + (size_t)idx * 32);
 		A.list[e] = ent | (d << (E_IDX_BITS + E_LVL_BITS));
 	}
@@ -503,12 +545,14 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 		int* own0 = owner + n2;
 		int* obs = have_own0 ? choice + npts : A.aux0;
 		auto closed_on_entry = [&](int c) {
+			if (A.mode == MODE_BOW) return false;                               // matches starts all null (:456, :709)
 			const int m = A.mp_in[c];
 			return m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
 		};
 		if (have_own0)
 			for (int c = tid; c < n2; c += G_THREADS) own0[c] = closed_on_entry(c) ? -1 : INT_MAX;
-		for (int i = tid; i < npts; i += G_THREADS) obs[i] = ((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2) ? 1 : 0;
+		for (int i = tid; i < npts; i += G_THREADS)
+			obs[i] = A.mode == MODE_BOW ? 1 : (((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2) ? 1 : 0);   // BoW: any match closes the keypoint (:477-478)
 		__syncthreads();
 		stamp(A, 7);
 		for (;;)
@@ -538,6 +582,8 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 				}
 				bool ok = best <= TH_HIGH;                                        // :370, :1349
 				if (ok && A.mode == MODE_LOCAL_MAP && bestLevel == secondLevel && (float)best > A.nnratio * (float)second) ok = false;   // :372-373
+				if (A.mode == MODE_BOW)
+					ok = (A.bow_strict ? best < TH_LOW : best <= TH_LOW) && (float)best < A.nnratio * (float)second;                  // :501, :750
 				const int c = ok ? bestIdx : -1;
 				if (c != choice[i]) { choice[i] = c; changed = 1; }
 			}
@@ -558,6 +604,13 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 			if (c < 0) continue;
 			mine++;
 			atomicMax(&owner[c], i);
+			if (A.mode == MODE_BOW && A.check_ori)
+			{
+				const float a1 = A.kps1[A.bow_pt[3 * i]].angle, a2 = A.kps2[c].angle;
+				const int bin = A.ori_swap ? orientation_bin(a2, a1) : orientation_bin(a1, a2);      // :763 / :512
+				A.aux0[i] = bin;
+				atomicAdd(&s_hist[bin], 1);
+			}
 			if (A.mode == MODE_LAST_FRAME && A.check_ori)
 			{
 				const int bin = orientation_bin(A.lp[i].angle, A.kps2[c].angle);   // keypoints1 = lastFrame.keypointsUn, :1358
@@ -567,10 +620,13 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 		}
 		if (mine) atomicAdd(&s_count, mine);
 		__syncthreads();
-		for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = owner[c] >= 0 ? owner[c] : A.mp_in[c];
+		if (A.mode == MODE_BOW)
+			for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = owner[c] >= 0 ? A.bow_pt[3 * owner[c]] : -1;   // the keypoint of frame 1
+		else
+			for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = owner[c] >= 0 ? owner[c] : A.mp_in[c];
 		__syncthreads();
 		int nmatches = s_count;
-		if (A.mode == MODE_LAST_FRAME && A.check_ori)
+		if ((A.mode == MODE_LAST_FRAME || A.mode == MODE_BOW) && A.check_ori)
 			nmatches = check_orientation(A, choice, A.aux0, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[choice[i]] = -1; });   // :298-304
 		if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
 		stamp(A, 6);
@@ -802,6 +858,7 @@ orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_byt
 	A.stamps = reinterpret_cast<unsigned long long*>(f->d_out.p + S.out_res + 16);
 	A.frame_mp = reinterpret_cast<int32_t*>(f->d_out.p + S.out_mp);
 	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr; A.mp_in = nullptr; A.prev_in = nullptr;
+	A.bow_pt = nullptr; A.bow_idx2 = nullptr; A.bow_valid2 = nullptr; A.bow_strict = 0; A.ori_swap = 0;
 	A.th = 0.f; A.nnratio = 0.f; A.radius = 0.f; A.fx = A.fy = A.cx = A.cy = A.bf = 0.f;
 	for (int i = 0; i < 9; i++) A.R[i] = 0.f;
 	for (int i = 0; i < 3; i++) A.t[i] = 0.f;
@@ -1090,6 +1147,56 @@ orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* 
 		memcpy(matches12, f2->h_out + S.out_mp, (size_t)npts * sizeof(int));
 		memcpy(prev_matched, f2->h_out + S.out_prev, prev_bytes);
 	}
+	return ORBX_OK;
+}
+
+orbx_status orbx_search_by_bow(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* valid1, orbx_frame f2, const orbx_feature_vector* fv2,
+                               const uint8_t* valid2, float nnratio, int check_orientation, int32_t* match2, int* nmatches)
+{
+	if (!f1 || !f2 || !fv1 || !fv2 || !valid1 || !match2) return orbx_fail(ORBX_ERR_INVALID, "null argument");
+	if (f1->device != f2->device) return orbx_fail(ORBX_ERR_INVALID, "frames live on different devices");
+	if (fv1->nnodes < 0 || fv2->nnodes < 0 || (fv1->nnodes && (!fv1->node_ids || !fv1->start || !fv1->indices)) ||
+	    (fv2->nnodes && (!fv2->node_ids || !fv2->start || !fv2->indices)))
+		return orbx_fail(ORBX_ERR_INVALID, "malformed feature vector");
+	const int n_idx2 = fv2->nnodes ? fv2->start[fv2->nnodes] : 0;
+	for (int p = 0; p < n_idx2; p++)
+		if (fv2->indices[p] >= (uint32_t)f2->n) return orbx_fail(ORBX_ERR_INVALID, "feature index outside frame 2");
+	// FeatureVectorIterator (src/ORBmatcher.cc:406-450): the nodes both vectors hold, ascending; the points are frame 1's valid
+	// features of those nodes in the nodes' order
+	std::vector<int> pts;
+	for (int a = 0, b = 0; a < fv1->nnodes && b < fv2->nnodes;)
+	{
+		if (fv1->node_ids[a] < fv2->node_ids[b]) { a++; continue; }
+		if (fv2->node_ids[b] < fv1->node_ids[a]) { b++; continue; }
+		for (int p1 = fv1->start[a]; p1 < fv1->start[a + 1]; p1++)
+		{
+			const uint32_t idx1 = fv1->indices[p1];
+			if (idx1 >= (uint32_t)f1->n) return orbx_fail(ORBX_ERR_INVALID, "feature index outside frame 1");
+			if (!valid1[idx1]) continue;                                               // :471-472, :719-720
+			pts.push_back((int)idx1); pts.push_back(fv2->start[b]); pts.push_back(fv2->start[b + 1] - fv2->start[b]);
+		}
+		a++; b++;
+	}
+	const int npts = (int)pts.size() / 3;
+	GuidedArgs A;
+	Staging S;
+	const size_t pts_bytes = pts.size() * sizeof(int), idx_bytes = (size_t)n_idx2 * sizeof(uint32_t), val_bytes = valid2 ? (size_t)f2->n : 0;
+	if (orbx_status s = prepare(f2, npts, pts_bytes, idx_bytes, val_bytes, (size_t)f2->n, 0, A, S)) return s;
+	if (npts) memcpy(f2->h_in + S.in_pts, pts.data(), pts_bytes);
+	if (n_idx2) memcpy(f2->h_in + S.in_desc, fv2->indices, idx_bytes);
+	if (valid2 && f2->n) memcpy(f2->h_in + S.in_state, valid2, val_bytes);
+	A.mode = MODE_BOW;
+	A.bow_pt = reinterpret_cast<const int*>(f2->d_in.p + S.in_pts);
+	A.bow_idx2 = reinterpret_cast<const uint32_t*>(f2->d_in.p + S.in_desc);
+	A.bow_valid2 = valid2 ? f2->d_in.p + S.in_state : nullptr;
+	A.bow_strict = valid2 != nullptr;                      // the KeyFrame-KeyFrame variant tests best < TH_LOW (:750)
+	A.ori_swap = valid2 != nullptr;                        // and hands CheckOrientation (keypoints2, keypoints1) (:763)
+	A.kps1 = f1->kps.p;
+	A.pt_desc = f1->desc.p;
+	A.nnratio = nnratio;
+	A.check_ori = check_orientation != 0;
+	if (orbx_status s = run_search(f2, A, S, nmatches)) return s;
+	if (f2->n) memcpy(match2, f2->h_out + S.out_mp, (size_t)f2->n * sizeof(int));
 	return ORBX_OK;
 }
 

@@ -248,3 +248,45 @@ def rectification_maps(seed, w, h, strength=1.0):
     xd = x * d + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
     yd = y * d + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
     return (fx * xd + cx).astype(np.float32), (fy * yd + cy).astype(np.float32)
+
+
+def feature_vector(node_of):
+    """DBoW2::FeatureVector of a frame as CSR (node_ids ascending, start, indices): node_of[i] = vocabulary node of keypoint i;
+    indices inside a node ascend, as FeatureVector::addFeature fills them when transform() walks the descriptors in order."""
+    node_of = np.asarray(node_of, np.uint32)
+    ids = np.unique(node_of)
+    order = np.argsort(node_of, kind='stable')
+    counts = np.searchsorted(node_of[order], ids, side='right')
+    start = np.concatenate([[0], counts]).astype(np.int32)
+    return ids.astype(np.uint32), start, order.astype(np.uint32)
+
+
+def bow_pair(seed, n=1500, w=640, h=480, nodes=90, max_flips=60):
+    """Two frames with feature vectors for SearchByBoW: 70 % of frame 2's keypoints are moved copies of frame 1's (descriptor a few
+    bits away, same vocabulary node with probability 0.9, angle turned by a common rotation); near-duplicates inside a node make
+    several keypoints of frame 1 compete for one keypoint of frame 2. Returns f1, fv1, valid1, f2, fv2, valid2."""
+    r = np.random.RandomState(seed + 4)
+    f1 = frame(seed, n, w, h, stereo=False)
+    f2 = frame(seed + 700, n, w, h, stereo=False)
+    node_ids = np.sort(r.choice(100000, nodes, replace=False)).astype(np.uint32)
+    n1 = node_ids[r.randint(0, nodes, n)]
+    n2 = node_ids[r.randint(0, nodes, n)]
+    m = int(0.7 * n)
+    src = r.permutation(n)[:m]
+    dst = r.permutation(n)[:m]
+    k1, k2 = f1['kps_un'], f2['kps_un']
+    ang = k1['angle'][src] + 30.0 + 5.0 * r.randn(m)
+    wild = r.rand(m) < 0.15
+    ang[wild] = 360.0 * r.rand(wild.sum())
+    k2['angle'][dst] = np.mod(ang, 360.0).astype(np.float32)
+    for s, d in zip(src, dst):
+        f2['desc'][d] = _flip_bits(r, f1['desc'][s], r.randint(0, max_flips + 1))
+    same = r.rand(m) < 0.9
+    n2[dst[same]] = n1[src[same]]
+    for s in src[: m // 5]:      # a second keypoint of frame 1, in the same node, that looks like s
+        j = r.randint(0, n)
+        f1['desc'][j] = _flip_bits(r, f1['desc'][s], r.randint(0, 10))
+        n1[j] = n1[s]
+    valid1 = (r.rand(n) < 0.85).astype(np.uint8)
+    valid2 = (r.rand(n) < 0.85).astype(np.uint8)
+    return f1, feature_vector(n1), valid1, f2, feature_vector(n2), valid2

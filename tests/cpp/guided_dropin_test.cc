@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <random>
 #include <vector>
 
@@ -38,8 +39,11 @@ struct MapPoint
 	cv::Matx31f GetWorldPos() const { return worldPos; }
 };
 
+using FeatureVector = std::map<unsigned, std::vector<unsigned>>;   // DBoW2::FeatureVector's base class
+
 struct Frame
 {
+	FeatureVector featureVector;
 	CameraParams camera;
 	int N = 0;
 	std::vector<cv::KeyPoint> keypoints, keypointsUn;
@@ -85,6 +89,29 @@ void noisy_copy(unsigned char* dst, const unsigned char* src, int flips)
 	memcpy(dst, src, 32);
 	for (int k = 0; k < flips; k++) { const int b = irand(256); dst[b >> 3] ^= (unsigned char)(1 << (b & 7)); }
 }
+
+struct KeyFrame
+{
+	std::vector<cv::KeyPoint> keypointsUn;
+	cv::Mat descriptors;
+	ImageBounds imageBounds;
+	ScalePyramidInfo pyramid;
+	std::vector<float> uright;
+	FeatureVector featureVector;
+	std::vector<MapPoint*> mappoints;
+	std::vector<MapPoint*> GetMapPointMatches() const { return mappoints; }
+};
+
+struct FlatFv
+{
+	std::vector<uint32_t> ids, idx; std::vector<int32_t> start;
+	explicit FlatFv(const FeatureVector& fv)
+	{
+		start.push_back(0);
+		for (const auto& n : fv) { ids.push_back(n.first); for (unsigned i : n.second) idx.push_back(i); start.push_back((int32_t)idx.size()); }
+	}
+	oracle_feature_vector view() const { return oracle_feature_vector{ (int32_t)ids.size(), ids.data(), start.data(), idx.data() }; }
+};
 
 oracle_frame_view view_of(const Frame& f)
 {
@@ -226,7 +253,47 @@ int main()
 		if (w3 != g3 || m12 != m12_want) { printf("initialization %d vs %d\n", g3, w3); return 1; }
 		if (memcmp(prev.data(), prev_want.data(), sizeof(cv::Point2f) * n) != 0) { printf("prevMatched differs\n"); return 1; }
 
-		printf("OK local %d, last %d, init %d\n", got_n, total, g3);
+		// ---- SearchByBoW, both variants: frame -> key frame 1, f2 -> frame / key frame 2
+		KeyFrame kf1, kf2;
+		kf1.keypointsUn = frame.keypointsUn; kf1.descriptors = frame.descriptors; kf1.imageBounds = frame.imageBounds; kf1.pyramid = frame.pyramid;
+		kf2.keypointsUn = f2.keypointsUn; kf2.descriptors = f2.descriptors; kf2.imageBounds = f2.imageBounds; kf2.pyramid = f2.pyramid;
+		std::vector<MapPoint> mp1(n), mp2(n);
+		std::vector<uint8_t> va1(n), va2(n);
+		kf1.mappoints.assign(n, nullptr); kf2.mappoints.assign(n, nullptr);
+		for (int i = 0; i < n; i++)
+		{
+			va1[i] = irand(10) < 8; va2[i] = irand(10) < 8;
+			if (va1[i]) kf1.mappoints[i] = &mp1[i];
+			if (va2[i]) kf2.mappoints[i] = &mp2[i];
+			kf1.featureVector[1000 + 7 * (unsigned)irand(60)].push_back((unsigned)i);
+		}
+		for (int i = 0; i < n; i++) kf2.featureVector[1000 + 7 * (unsigned)irand(60)].push_back((unsigned)i);
+		f2.featureVector = kf2.featureVector;
+		const FlatFv a1(kf1.featureVector), a2(kf2.featureVector);
+		const oracle_feature_vector o1 = a1.view(), o2 = a2.view();
+		std::vector<int32_t> want_m2(n);
+		ORB_SLAM2::b200::GuidedMatcher bow(0.9f, true);
+		{
+			const int w4 = orc_search_by_bow(&fv, &o1, va1.data(), &fv2, &o2, nullptr, 0.9f, 1, want_m2.data());
+			std::vector<MapPoint*> matches;
+			const int g4 = bow.SearchByBoW(&kf1, dev, f2, dev2, matches);
+			if (w4 != g4) { printf("bow kf-frame nmatches %d vs %d\n", g4, w4); return 1; }
+			for (int c = 0; c < n; c++)
+				if (matches[c] != (want_m2[c] >= 0 ? &mp1[want_m2[c]] : nullptr)) { printf("bow kf-frame matches[%d]\n", c); return 1; }
+			total += g4;
+		}
+		{
+			const int w5 = orc_search_by_bow(&fv, &o1, va1.data(), &fv2, &o2, va2.data(), 0.9f, 1, want_m2.data());
+			std::vector<MapPoint*> matches12;
+			const int g5 = bow.SearchByBoW(&kf1, dev, &kf2, dev2, matches12);
+			if (w5 != g5) { printf("bow kf-kf nmatches %d vs %d\n", g5, w5); return 1; }
+			std::vector<MapPoint*> want12(n, nullptr);
+			for (int c = 0; c < n; c++) if (want_m2[c] >= 0) want12[want_m2[c]] = &mp2[c];
+			if (matches12 != want12) { printf("bow kf-kf matches12\n"); return 1; }
+			total += g5;
+		}
+
+		printf("OK local %d, last+bow %d, init %d\n", got_n, total, g3);
 		return 0;
 	}
 	catch (const cv::Exception& e)

@@ -39,6 +39,10 @@ def cases(small=False):
         f1, f2, prev = synth.initialization_pair(seed, n=800 if small else 1500)
         for win in ((100,) if small else (100, 20)):
             out.append((f'init{seed}_w{win}', 'init', dict(f1=f1, f2=f2, prev=prev, window=win, nnratio=0.9, check=seed != 4)))
+        f1, fv1, va1, f2, fv2, va2 = synth.bow_pair(seed, n=800 if small else 1500)
+        out.append((f'bow{seed}_kf_frame', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=None, nnratio=0.7, check=seed != 5)))
+        out.append((f'bow{seed}_kf_kf', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=va2, nnratio=0.8 if seed % 2 else 0.75,
+                                                    check=seed != 2)))
     if not small:
         # crowded: most points aim at a keypoint some other point wants too, and the alternatives are close: long dependency chains
         fr = synth.frame(40, n=600, w=320, h=240)
@@ -89,6 +93,9 @@ def run_oracle(o, kind, c):
         n, mp = o.search_last_frame(c['frame'], c['cam'], c['cur_pose'], c['last_pose'], c['mp'], c['pts'], c['desc'], c['th'], c['monocular'],
                                     0.9, c['check'])
         return dict(n=np.int32(n), mp=mp)
+    if kind == 'bow':
+        n, m2 = o.search_by_bow(c['f1'], c['fv1'], c['valid1'], c['f2'], c['fv2'], c['valid2'], c['nnratio'], c['check'])
+        return dict(n=np.int32(n), m2=m2)
     n, m12, prev = o.search_for_initialization(c['f1'], c['f2'], c['prev'], c['window'], c['nnratio'], c['check'])
     return dict(n=np.int32(n), m12=m12, prev=prev)
 
@@ -115,6 +122,9 @@ def run_product(api, kind, c, device=0):
                                                                                 c['th'], c['monocular'])
         return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
     f1, f2 = make_frame(api, c['f1'], device), make_frame(api, c['f2'], device)
+    if kind == 'bow':
+        n, m2 = api.ORBmatcher(c['nnratio'], c['check'], device).SearchByBoW(f1, c['fv1'], c['valid1'], f2, c['fv2'], c['valid2'])
+        return dict(n=np.int32(n), m2=m2.copy(), _rounds=f2.last_rounds())
     prev = c['prev'].copy()
     n, m12 = api.ORBmatcher(c['nnratio'], c['check'], device).SearchForInitialization(f1, f2, prev, c['window'])
     return dict(n=np.int32(n), m12=m12.copy(), prev=prev, _rounds=f2.last_rounds())

@@ -1,5 +1,5 @@
 """GPU parity of the guided matchers through the C ABI: FeaturesGrid (src/Frame.cc:63-145), SearchByProjection for
-local-map and motion-model tracking (src/ORBmatcher.cc:315-382, 1279-1362), SearchForInitialization (:614-694) and CheckOrientation
+local-map and motion-model tracking (src/ORBmatcher.cc:315-382, 1279-1362), SearchForInitialization (:614-694), SearchByBoW x2 (:406-516, 696-766) and CheckOrientation
 (:249-309). Bit-exact against the CPU oracle and against the committed outputs of the reference text."""
 import os
 
@@ -48,7 +48,7 @@ def test_all_cases_against_oracle(orbx, oracle_port):
         max_rounds = max(max_rounds, got.get('_rounds', 0))
         if name == 'local_ladder':
             assert got['_rounds'] >= 12 and list(got['mp'][:12]) == list(range(12))
-    assert set(kinds) == {'grid', 'local', 'last', 'init'} and max_rounds >= 12
+    assert set(kinds) == {'grid', 'local', 'last', 'init', 'bow'} and max_rounds >= 12
 
 
 def test_reference_golden(orbx):
