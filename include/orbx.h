@@ -260,6 +260,25 @@ orbx_status orbx_search_by_projection_last_frame(orbx_frame cur, const orbx_came
 /* ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:614-694. prev_matched: f1->n (x, y) pairs, in/out; matches12: f1->n, out. */
 orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* prev_matched, int32_t* matches12, int window_size,
                                            float nnratio, int check_orientation, int* nmatches);
+/* One map point of a key frame for the relocalisation search: world position, the members minDistance_ / maxDistance_ behind
+ * Get{Min,Max}DistanceInvariance and PredictScale (src/MapPoint.cc:382-414), the angle of the key frame's keypoint (CheckOrientation).
+ * flags bit 0 = map point present && !isBad() && not in alreadyFound. */
+typedef struct orbx_keyframe_point { float xw[3]; float min_distance, max_distance; float angle; int32_t flags; } orbx_keyframe_point;
+/* ORBmatcher::SearchByProjection(Frame& frame, KeyFrame* keyframe, const std::set<MapPoint*>& alreadyFound, float th, int ORBdist) —
+ * src/ORBmatcher.cc:1364-1447 (relocalisation). camera / pose belong to `frame`; log_scale_factor = frame.pyramid.logScaleFactor
+ * (src/System.cc:143). Any non-null frame.mappoints entry closes its keypoint (:1412-1413). The per-point geometry (projection,
+ * cv::norm, PredictScale's log) is evaluated on the host in the reference's operation order; the window search runs on the device. */
+orbx_status orbx_search_by_projection_keyframe(orbx_frame f, const orbx_camera* camera, const orbx_pose* pose, float log_scale_factor,
+                                              int32_t* frame_mp, const orbx_keyframe_point* pts, const uint8_t* pt_desc, int npts, float th,
+                                              int orb_dist, int check_orientation, int* nmatches);
+/* The window search underneath it, for callers that evaluate the geometry themselves (the C++ mirror does, with the reference's own
+ * MapPoint::PredictScale and camera classes): window i is centred on (u, v) with half-size radius and admits the octaves
+ * [min_level, max_level] with GetFeaturesInArea's level semantics; flags bit 0 = search this point; angle = the orientation compared
+ * with the keypoint's by CheckOrientation. Loop semantics of src/ORBmatcher.cc:1410-1432: any non-null frame.mappoints entry closes
+ * its keypoint, best distance wins (first on ties), accepted when best <= max_dist; every match closes its keypoint for later points. */
+typedef struct orbx_window { float u, v, radius, angle; int32_t min_level, max_level; int32_t flags; } orbx_window;
+orbx_status orbx_search_windows(orbx_frame f, int32_t* frame_mp, const orbx_window* windows, const uint8_t* pt_desc, int npts, int max_dist,
+                                int check_orientation, int* nmatches);
 /* DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h: std::map<NodeId, std::vector<unsigned>>) flattened: node ids ascending,
  * the features of node k are indices[start[k] .. start[k+1]). */
 typedef struct orbx_feature_vector { int32_t nnodes; const uint32_t* node_ids; const int32_t* start; const uint32_t* indices; } orbx_feature_vector;

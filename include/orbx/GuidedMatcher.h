@@ -5,6 +5,8 @@
 //                                                                          include/ORBmatcher.h:58,  src/ORBmatcher.cc:315-382
 //   int ORBmatcher::SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular)
 //                                                                          include/ORBmatcher.h:62,  src/ORBmatcher.cc:1279-1362
+//   int ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const std::set<MapPoint*>& alreadyFound, float th, int ORBdist)
+//                                                                          include/ORBmatcher.h:66,  src/ORBmatcher.cc:1364-1447
 //   int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, std::vector<MapPoint*>&) / (KeyFrame*, KeyFrame*, std::vector<MapPoint*>&)
 //                                                                          include/ORBmatcher.h:72-73, src/ORBmatcher.cc:406-516, 696-766
 //   int ORBmatcher::SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int windowSize)
@@ -159,6 +161,54 @@ public:
 		{
 			if (state[c] >= 0) currFrame.mappoints[c] = lastFrame.mappoints[(size_t)state[c]];   // :1351
 			else if (state[c] == -1) currFrame.mappoints[c] = nullptr;                           // CheckOrientation, :301
+		}
+		return nmatches;
+	}
+
+	// src/ORBmatcher.cc:1364-1447 (relocalisation). The geometry is evaluated here with the reference's own classes — cv::Matx
+	// arithmetic, cv::norm, mappoint->Get{Min,Max}DistanceInvariance(), mappoint->PredictScale(dist, &frame) — so it is the
+	// reference's arithmetic by construction; the window search, its "already matched" state and CheckOrientation run on the GPU.
+	template <class FrameT, class KeyFrameT, class SetT>
+	int SearchByProjection(FrameT& frame, DeviceFrame& dev, KeyFrameT* keyframe, const SetT& alreadyFound, float th, int ORBdist) const
+	{
+		const auto mappoints = keyframe->GetMapPointMatches();
+		const int npts = static_cast<int>(mappoints.size());
+		std::vector<orbx_window> win((size_t)npts);
+		std::vector<uint8_t> desc((size_t)npts * 32);
+		const cv::Matx33f Rcw = frame.pose.R();
+		const cv::Matx31f tcw = frame.pose.t();
+		const cv::Matx31f Ow = frame.GetCameraCenter();
+		for (int i = 0; i < npts; i++)
+		{
+			orbx_window& w = win[i];
+			w.u = w.v = w.radius = 0.f; w.min_level = w.max_level = 0; w.flags = 0;
+			w.angle = keyframe->keypointsUn[i].angle;
+			auto* mappoint = mappoints[i];
+			if (!mappoint || mappoint->isBad() || alreadyFound.count(mappoint)) continue;       // :1379-1381
+			const cv::Matx31f Xw = mappoint->GetWorldPos();
+			const cv::Matx31f Xc = Rcw * Xw + tcw;                                              // CameraProjection::WorldToImage
+			const float invZ = 1.f / Xc(2);
+			const float u = invZ * frame.camera.fx * Xc(0) + frame.camera.cx, v = invZ * frame.camera.fy * Xc(1) + frame.camera.cy;
+			if (!(u >= frame.imageBounds.minx && u < frame.imageBounds.maxx && v >= frame.imageBounds.miny && v < frame.imageBounds.maxy)) continue;
+			const cv::Matx31f PO = Xw - Ow;
+			const float dist3D = static_cast<float>(cv::norm(PO));
+			if (dist3D < mappoint->GetMinDistanceInvariance() || dist3D > mappoint->GetMaxDistanceInvariance()) continue;   // :1400-1401
+			const int predictedScale = mappoint->PredictScale(dist3D, &frame);
+			w.u = u; w.v = v;
+			w.radius = th * frame.pyramid.scaleFactors[predictedScale];                          // :1406
+			w.min_level = predictedScale - 1; w.max_level = predictedScale + 1;                  // :1408
+			w.flags = 1;
+			std::memcpy(&desc[(size_t)i * 32], mappoint->GetDescriptor().data, 32);
+		}
+		std::vector<int32_t> state(frame.mappoints.size());
+		for (size_t c = 0; c < state.size(); c++) state[c] = frame.mappoints[c] ? -2 : -1;       // :1412-1413: any map point closes
+		int nmatches = 0;
+		Check(orbx_search_windows(dev.Handle(), state.data(), win.data(), desc.data(), npts, ORBdist, checkOrientation_ ? 1 : 0, &nmatches),
+			"SearchByProjection");
+		for (size_t c = 0; c < state.size(); c++)
+		{
+			if (state[c] >= 0) frame.mappoints[c] = mappoints[(size_t)state[c]];                 // :1426
+			else if (state[c] == -1) frame.mappoints[c] = nullptr;                               // CheckOrientation, :301
 		}
 		return nmatches;
 	}

@@ -22,7 +22,8 @@ assert KP_DTYPE.itemsize == 28 and CAND_DTYPE.itemsize == 12
 TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
                               ('flags', '<i4')])
 LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
-assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24
+KF_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('angle', '<f4'), ('flags', '<i4')])
+assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24 and KF_POINT_DTYPE.itemsize == 28
 
 
 class Bounds(C.Structure):
@@ -107,6 +108,8 @@ class Oracle:
         f('time_search_local_map', C.c_double, [C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int])
         f('time_search_last_frame', C.c_double, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.POINTER(Pose), C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int])
+        f('search_keyframe_projection', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int])
         f('search_by_bow', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
                                      C.c_void_p, C.c_float, C.c_int, C.c_void_p])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
@@ -306,6 +309,18 @@ class Oracle:
         n = self._search_by_bow(C.byref(v1), C.byref(c1), _p(va1), C.byref(v2), C.byref(c2), None if va2 is None else _p(va2), nnratio,
                                 int(check_orientation), _p(m2))
         return n, m2
+
+    def search_keyframe_projection(self, frame, cam, pose, log_scale_factor, frame_mp, pts, pt_desc, th=10.0, orb_dist=100,
+                                   check_orientation=True):
+        """SearchByProjection(Frame&, KeyFrame*, alreadyFound, th, ORBdist) (relocalisation). Returns (nmatches, frame_mp)."""
+        v, keep = self._frame_view(frame)
+        mp = np.array(frame_mp, np.int32)
+        pts = np.ascontiguousarray(pts).view(KF_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        P = self._poses(pose, pose)[0]
+        n = self._search_keyframe_projection(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(P), float(np.float32(log_scale_factor)),
+                                             _p(mp), _p(pts), _p(pt_desc), len(pts), th, int(orb_dist), int(check_orientation))
+        return n, mp
 
     def search_for_initialization(self, f1, f2, prev_matched, window=100, nnratio=0.9, check_orientation=True):
         v1, k1 = self._frame_view(f1)

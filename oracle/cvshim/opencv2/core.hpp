@@ -120,6 +120,13 @@ template <class T, int M, int N> inline Matx<T, M, N> operator-(const Matx<T, M,
 }
 typedef Matx<float, 3, 1> Matx31f;
 typedef Matx<float, 3, 3> Matx33f;
+// cv::norm(Matx) = std::sqrt(normL2Sqr<_Tp, double>(val, m*n)): squares accumulated in double (matx.hpp, base.hpp)
+template <class T, int M, int N> inline double norm(const Matx<T, M, N>& a)
+{
+	double s = 0;
+	for (int i = 0; i < M * N; i++) s += (double)a.val[i] * (double)a.val[i];
+	return std::sqrt(s);
+}
 
 struct KeyPoint
 {

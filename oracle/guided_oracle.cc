@@ -182,13 +182,14 @@ template <class Taken> Pick scan_window(const Grid& g, const oracle_frame_view* 
 // by point i (or -1) and frame_mp is updated to the reference's final frame.mappoints.
 template <class Accept>
 int run_rounds(const Grid& g, const oracle_frame_view* f, const std::vector<Probe>& probes, const uint8_t* pt_desc, int32_t* frame_mp,
-               std::vector<int>& choice, Accept accept)
+               std::vector<int>& choice, Accept accept, bool any_map_point_closes = false)
 {
 	const int np = (int)probes.size(), n = f->n;
 	choice.assign((size_t)np, -1);
 	// keypoints closed from the start: frame.mappoints[idx] && frame.mappoints[idx]->Observations() > 0 on entry
 	std::vector<char> closed((size_t)n);
-	for (int c = 0; c < n; c++) closed[c] = frame_mp[c] == -2 || (frame_mp[c] >= 0 && probes[(size_t)frame_mp[c]].obs);
+	for (int c = 0; c < n; c++)
+		closed[c] = any_map_point_closes ? frame_mp[c] != -1 : (frame_mp[c] == -2 || (frame_mp[c] >= 0 && probes[(size_t)frame_mp[c]].obs));
 	std::vector<int> owner((size_t)n);   // lowest point index with observations that takes the keypoint; INT_MAX = nobody
 	for (int round = 0;; round++)
 	{
@@ -366,6 +367,63 @@ double orc_time_search_last_frame(const oracle_frame_view* f, const oracle_camer
 		total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	}
 	return total / (reps > 0 ? reps : 1);
+}
+
+// SearchByProjection(Frame&, KeyFrame*, alreadyFound, th, ORBdist) (:1364-1447, relocalisation). The geometry per map point is host
+// arithmetic in the reference's operation order; the window search runs through the same rounds as the other two.
+int orc_search_keyframe_projection(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* pose, float log_scale_factor,
+                                   int32_t* frame_mp, const oracle_kf_point* pts, const uint8_t* pt_desc, int npts, float th, int orb_dist,
+                                   int check_ori)
+{
+	const Grid g = make_grid(f);
+	float Ow[3];                                   // frame.GetCameraCenter() = pose.Invt() = -R^T * t (src/Frame.cc:203-206)
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0;
+		for (int k = 0; k < 3; k++) s += (pose->R[k * 3 + i] * -1) * pose->t[k];
+		Ow[i] = s;
+	}
+	std::vector<Probe> probes((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		Probe& p = probes[i];
+		p.active = false;
+		p.obs = true;                              // any stored map point closes its keypoint (:1412-1413)
+		if (!(pts[i].flags & 1)) continue;         // :1379-1381
+		float xc[3];
+		for (int r = 0; r < 3; r++)
+		{
+			float s = 0;
+			for (int k = 0; k < 3; k++) s += pose->R[r * 3 + k] * pts[i].xw[k];
+			xc[r] = s + pose->t[r];
+		}
+		const float invZ = 1.f / xc[2];            // WorldToImage: no depth test in this variant (:1385)
+		p.u = invZ * cam->fx * xc[0] + cam->cx;
+		p.v = invZ * cam->fy * xc[1] + cam->cy;
+		p.ur = NAN;                                // no stereo gate
+		if (!(p.u >= f->bounds.minx && p.u < f->bounds.maxx && p.v >= f->bounds.miny && p.v < f->bounds.maxy)) continue;   // :1389
+		double ss = 0;                             // cv::norm(PO): squares accumulated in double
+		for (int k = 0; k < 3; k++) { const float d = pts[i].xw[k] - Ow[k]; ss += (double)d * (double)d; }
+		const float dist3D = (float)std::sqrt(ss);
+		const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;   // src/MapPoint.cc:382-392
+		if (dist3D < minDistance || dist3D > maxDistance) continue;                                       // :1400-1401
+		const float ratio = pts[i].max_distance / dist3D;                                                 // PredictScale, src/MapPoint.cc:405-414
+		const int scale = (int)std::ceil(std::log((double)ratio) / log_scale_factor);
+		const int ps = std::max(0, std::min(scale, f->nlevels - 1));
+		p.radius = th * f->scale_factors[ps];      // :1406
+		p.minLevel = ps - 1; p.maxLevel = ps + 1;  // :1408
+		p.active = true;
+	}
+	std::vector<int> choice;
+	const int nmatches = run_rounds(g, f, probes, pt_desc, frame_mp, choice, [&](const Pick& k) { return k.idx >= 0 && k.best <= orb_dist; }, true);
+	if (!check_ori) return nmatches;
+	std::vector<std::pair<int, int>> matches;
+	for (int i = 0; i < npts; i++)
+		if (choice[i] >= 0) matches.push_back({ i, choice[i] });
+	std::vector<int> erased;
+	const int kept = check_orientation(matches, &pts[0].angle, sizeof(oracle_kf_point), &f->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+	for (int i2 : erased) frame_mp[i2] = -1;
+	return kept;
 }
 
 // SearchByBoW (:452-516 KeyFrame vs Frame when valid2 == NULL, :696-766 KeyFrame vs KeyFrame otherwise). FeatureVectorIterator

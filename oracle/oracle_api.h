@@ -128,6 +128,14 @@ int ORACLE_FN(search_local_map)(const oracle_frame_view* frame, int32_t* frame_m
 int ORACLE_FN(search_last_frame)(const oracle_frame_view* cur, const oracle_camera* cam, const oracle_pose* cur_pose,
                                  const oracle_pose* last_pose, int32_t* frame_mp, const oracle_last_point* pts, const uint8_t* pt_desc,
                                  int npts, float th, int monocular, float nnratio, int check_orientation);
+// one map point of a key frame for SearchByProjection(Frame&, KeyFrame*, alreadyFound, th, ORBdist) (src/ORBmatcher.cc:1364-1447): world
+// position, the members minDistance_ / maxDistance_ behind Get{Min,Max}DistanceInvariance and PredictScale, the angle of the key frame's
+// keypoint (CheckOrientation); flags bit0 = map point present && !isBad() && not in alreadyFound
+typedef struct oracle_kf_point { float xw[3]; float min_distance, max_distance; float angle; int32_t flags; } oracle_kf_point;
+// frame_mp as for the other searches (any non-null entry closes its keypoint here, :1412-1413); log_scale_factor = pyramid.logScaleFactor
+int ORACLE_FN(search_keyframe_projection)(const oracle_frame_view* frame, const oracle_camera* cam, const oracle_pose* pose, float log_scale_factor,
+                                          int32_t* frame_mp, const oracle_kf_point* pts, const uint8_t* pt_desc, int npts, float th, int orb_dist,
+                                          int check_orientation);
 // DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h) as CSR: node ids ascending, the feature indices of node k are
 // indices[start[k] .. start[k+1])
 typedef struct oracle_feature_vector { int32_t nnodes; const uint32_t* node_ids; const int32_t* start; const uint32_t* indices; } oracle_feature_vector;

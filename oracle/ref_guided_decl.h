@@ -8,6 +8,8 @@
 //   src/ORBmatcher.cc:406-516, 696-766         FeatureVectorIterator, SearchByBoW x2            — reference keyframe / relocalisation / loop
 //   src/ORBmatcher.cc:614-694                  SearchForInitialization                          — monocular initialisation
 //   src/ORBmatcher.cc:1279-1362                SearchByProjection(currFrame, lastFrame, th, m)  — motion-model tracking
+//   src/ORBmatcher.cc:1364-1447                SearchByProjection(frame, keyframe, found, th, d) — relocalisation
+//   src/MapPoint.cc:382-392, 405-414; src/Frame.cc:203-206   distance invariance, PredictScale, GetCameraCenter
 // compiles by line range (oracle/Makefile, rule guided_gen.cc) with the reference's own include/Point.h,
 // include/CameraParameters.h, include/CameraPose.h and include/CameraProjection.h. The real Frame/MapPoint/KeyFrame drag
 // in DBoW2, the vocabulary and the map; only the members those three functions touch exist here, under the same names
@@ -15,6 +17,12 @@
 //
 // This header is included INSIDE namespace ORB_SLAM2 of the generated TU, after the Frame.h declarations.
 #pragma once
+
+// src/MapPoint.cc:29 takes a std::mutex here; the stand-in map points are touched by one thread
+#define LOCK_MUTEX_POSITION()
+
+struct Frame;
+struct KeyFrame;
 
 struct MapPoint
 {
@@ -29,6 +37,12 @@ struct MapPoint
 	int nobs = 0;
 	bool bad = false;
 	cv::Mat descriptor;     // 1 x 32 CV_8U row header
+
+	// scale-invariance distances (include/MapPoint.h; bodies from src/MapPoint.cc:382-392, 405-414 by line range)
+	float minDistance_ = 0.f, maxDistance_ = 0.f;
+	float GetMinDistanceInvariance() const;
+	float GetMaxDistanceInvariance() const;
+	int PredictScale(float dist, const Frame* frame) const;
 
 	Point3D GetWorldPos() const { return worldPos; }
 	int Observations() const { return nobs; }
@@ -53,6 +67,8 @@ struct Frame
 	ScalePyramidInfo pyramid;
 	ImageBounds imageBounds;
 	DBoW2::FeatureVector featureVector;
+
+	Point3D GetCameraCenter() const;   // src/Frame.cc:203-206 by line range
 
 	// src/Frame.cc:216-219
 	std::vector<size_t> GetFeaturesInArea(float x, float y, float r, int minLevel = -1, int maxLevel = -1) const
@@ -80,6 +96,7 @@ public:
 	static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
 	int SearchByProjection(Frame& frame, const std::vector<MapPoint*>& mappoints, float th = 3);
 	int SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular);
+	int SearchByProjection(Frame& frame, KeyFrame* keyframe, const std::set<MapPoint*>& alreadyFound, float th, int ORBdist);
 	int SearchByBoW(KeyFrame* keyframe, Frame& frame, std::vector<MapPoint*>& matches);
 	int SearchByBoW(KeyFrame* keyframe1, KeyFrame* keyframe2, std::vector<MapPoint*>& matches12);
 	int SearchForInitialization(Frame& frame1, Frame& frame2, std::vector<cv::Point2f>& prevMatched, std::vector<int>& matches12,

@@ -61,7 +61,8 @@ class _Pose(C.Structure):
 TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
                               ('flags', '<i4')])
 LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
-assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24
+KF_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('angle', '<f4'), ('flags', '<i4')])
+assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24 and KF_POINT_DTYPE.itemsize == 28
 GRID_COLS, GRID_ROWS = 64, 48   # include/Frame.h:72-73
 
 _lib = None
@@ -127,6 +128,9 @@ _SIGNATURES = {
     'orbx_search_for_initialization': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
                                                  C.POINTER(C.c_int)]),
     'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p]),
+    'orbx_search_by_projection_keyframe': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_search_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_by_bow': (C.c_int, [C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_float,
                                      C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
@@ -496,6 +500,19 @@ class ORBmatcher:
         _check(lib().orbx_search_by_projection_last_frame(currFrame._h, C.byref(cam), C.byref(cp), C.byref(lp), _p(currFrame.mappoints),
                                                           _p(pts), _p(desc), len(pts), th, int(bool(monocular)),
                                                           int(bool(self.checkOrientation_)), C.byref(n)))
+        return n.value
+
+    def SearchByProjectionKeyFrame(self, frame, camera, pose, logScaleFactor, keyframePoints, descriptors, th, ORBdist):
+        """SearchByProjection(Frame&, KeyFrame*, alreadyFound, th, ORBdist) — src/ORBmatcher.cc:1364-1447 (relocalisation).
+        keyframePoints: KF_POINT_DTYPE records, one per keypoint of the key frame. Updates frame.mappoints; returns nmatches."""
+        pts = np.ascontiguousarray(keyframePoints).view(KF_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        n = C.c_int()
+        cam = _Camera(*[float(c) for c in camera])
+        P = _pose(pose)
+        _check(lib().orbx_search_by_projection_keyframe(frame._h, C.byref(cam), C.byref(P), float(np.float32(logScaleFactor)), _p(frame.mappoints),
+                                                        _p(pts), _p(desc), len(pts), th, int(ORBdist), int(bool(self.checkOrientation_)),
+                                                        C.byref(n)))
         return n.value
 
     def SearchByBoW(self, keyframe, featureVector1, valid1, frame, featureVector2, valid2=None):

@@ -35,7 +35,11 @@ constexpr int G_THREADS = 1024;
 constexpr int G_SMEM_INTS = 200 * 1024 / 4;   // dynamic shared memory of the search kernel, in ints
 constexpr int G_CLUSTER = 8;          // CTAs (= SMs) of one search: a thread-block cluster, the portable maximum
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;                        // src/ORBmatcher.cc:41-43
-constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2, MODE_BOW = 3;
+constexpr int MODE_LOCAL_MAP = 0, MODE_LAST_FRAME = 1, MODE_INIT = 2, MODE_BOW = 3, MODE_WINDOWS = 4;
+
+// a search window computed on the host (MODE_WINDOWS): the geometry of the variants whose projection involves log / sqrt stays in
+// host arithmetic, identical to the reference's; the device does the search
+struct GuidedWindow { float u, v, radius, angle; int levels; int flags; };   // levels = minLevel | maxLevel << 16; flags bit0 = active
 
 // candidate entry: keypoint index [0:19) | octave [19:23) | distance [23:32) (511 = removed by the uright gate)
 constexpr int E_IDX_BITS = 19, E_LVL_BITS = 4;
@@ -85,6 +89,8 @@ struct GuidedArgs
 	const float* prev_in;        // INIT: prevMatched on entry
 	int32_t* frame_mp;           // out: frame.mappoints (LOCAL_MAP, LAST_FRAME); INIT: matches12 [npts]
 	int* result;                 // [0] nmatches, [1] entries, [2] rounds, [3] overflow
+	const GuidedWindow* win;     // WINDOWS
+	int max_dist;                // WINDOWS: accept best <= max_dist (ORBdist, :1424)
 	// BOW: point i = (keypoint of frame 1, first position and count of its vocabulary node's features in bow_idx2)
 	const int* bow_pt; const uint32_t* bow_idx2; const uint8_t* bow_valid2;
 	int bow_strict, ori_swap;    // best < TH_LOW instead of <= (:750 vs :501); CheckOrientation's argument order (:763 vs :512)
@@ -444,6 +450,16 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 				}
 			}
 		}
+		else if (A.mode == MODE_WINDOWS)
+		{
+			const GuidedWindow wd = A.win[i];
+			if (wd.flags & 1)
+			{
+				u = wd.u; v = wd.v; radius = wd.radius;
+				ur = __int_as_float(0x7fc00000);                                   // NaN: no stereo gate in this variant
+				lv = wd.levels;
+			}
+		}
 		else
 		{
 			if (!(A.kps1[i].octave > 0))                                       // :629-631
@@ -547,12 +563,13 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 		auto closed_on_entry = [&](int c) {
 			if (A.mode == MODE_BOW) return false;                               // matches starts all null (:456, :709)
 			const int m = A.mp_in[c];
+			if (A.mode == MODE_WINDOWS) return m != -1;                         // any stored map point closes the keypoint (:1412-1413)
 			return m == -2 || (m >= 0 && ((A.mode == MODE_LOCAL_MAP ? A.tp[m].flags : A.lp[m].flags) & 2));
 		};
 		if (have_own0)
 			for (int c = tid; c < n2; c += G_THREADS) own0[c] = closed_on_entry(c) ? -1 : INT_MAX;
 		for (int i = tid; i < npts; i += G_THREADS)
-			obs[i] = A.mode == MODE_BOW ? 1 : (((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2) ? 1 : 0);   // BoW: any match closes the keypoint (:477-478)
+			obs[i] = (A.mode == MODE_BOW || A.mode == MODE_WINDOWS) ? 1 : (((A.mode == MODE_LOCAL_MAP ? A.tp[i].flags : A.lp[i].flags) & 2) ? 1 : 0);   // BoW: any match closes the keypoint (:477-478)
 		__syncthreads();
 		stamp(A, 7);
 		for (;;)
@@ -582,6 +599,7 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 				}
 				bool ok = best <= TH_HIGH;                                        // :370, :1349
 				if (ok && A.mode == MODE_LOCAL_MAP && bestLevel == secondLevel && (float)best > A.nnratio * (float)second) ok = false;   // :372-373
+				if (A.mode == MODE_WINDOWS) ok = bestIdx >= 0 && best <= A.max_dist;                                                  // :1424
 				if (A.mode == MODE_BOW)
 					ok = (A.bow_strict ? best < TH_LOW : best <= TH_LOW) && (float)best < A.nnratio * (float)second;                  // :501, :750
 				const int c = ok ? bestIdx : -1;
@@ -611,6 +629,12 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 				A.aux0[i] = bin;
 				atomicAdd(&s_hist[bin], 1);
 			}
+			if (A.mode == MODE_WINDOWS && A.check_ori)
+			{
+				const int bin = orientation_bin(A.win[i].angle, A.kps2[c].angle);  // keypoints1 = keyframe->keypointsUn, :1444
+				A.aux0[i] = bin;
+				atomicAdd(&s_hist[bin], 1);
+			}
 			if (A.mode == MODE_LAST_FRAME && A.check_ori)
 			{
 				const int bin = orientation_bin(A.lp[i].angle, A.kps2[c].angle);   // keypoints1 = lastFrame.keypointsUn, :1358
@@ -626,7 +650,7 @@ __global__ void __cluster_dims__(G_CLUSTER, 1, 1) __launch_bounds__(G_THREADS, 1
 			for (int c = tid; c < n2; c += G_THREADS) A.frame_mp[c] = owner[c] >= 0 ? owner[c] : A.mp_in[c];
 		__syncthreads();
 		int nmatches = s_count;
-		if ((A.mode == MODE_LAST_FRAME || A.mode == MODE_BOW) && A.check_ori)
+		if ((A.mode == MODE_LAST_FRAME || A.mode == MODE_BOW || A.mode == MODE_WINDOWS) && A.check_ori)
 			nmatches = check_orientation(A, choice, A.aux0, s_hist, s_items, s_misc, [&](int i) { A.frame_mp[choice[i]] = -1; });   // :298-304
 		if (tid == 0) { A.result[0] = nmatches; A.result[2] = rounds; }
 		stamp(A, 6);
@@ -858,6 +882,7 @@ orbx_status prepare(orbx_frame_s* f, int npts, size_t pts_bytes, size_t desc_byt
 	A.stamps = reinterpret_cast<unsigned long long*>(f->d_out.p + S.out_res + 16);
 	A.frame_mp = reinterpret_cast<int32_t*>(f->d_out.p + S.out_mp);
 	A.tp = nullptr; A.lp = nullptr; A.kps1 = nullptr; A.prev = nullptr; A.pt_desc = nullptr; A.mp_in = nullptr; A.prev_in = nullptr;
+	A.win = nullptr; A.max_dist = 0;
 	A.bow_pt = nullptr; A.bow_idx2 = nullptr; A.bow_valid2 = nullptr; A.bow_strict = 0; A.ori_swap = 0;
 	A.th = 0.f; A.nnratio = 0.f; A.radius = 0.f; A.fx = A.fy = A.cx = A.cy = A.bf = 0.f;
 	for (int i = 0; i < 9; i++) A.R[i] = 0.f;
@@ -1148,6 +1173,100 @@ orbx_status orbx_search_for_initialization(orbx_frame f1, orbx_frame f2, float* 
 		memcpy(prev_matched, f2->h_out + S.out_prev, prev_bytes);
 	}
 	return ORBX_OK;
+}
+
+namespace {
+// the windows are already in the staging buffer: stage descriptors and frame.mappoints, search, copy frame.mappoints back
+orbx_status finish_windows(orbx_frame_s* f, GuidedArgs& A, const Staging& S, int32_t* frame_mp, const uint8_t* pt_desc, int npts, int max_dist,
+                           int check_orientation, int* nmatches)
+{
+	const size_t mp_bytes = (size_t)f->n * sizeof(int);
+	if (npts) memcpy(f->h_in + S.in_desc, pt_desc, (size_t)npts * 32);
+	if (f->n) memcpy(f->h_in + S.in_state, frame_mp, mp_bytes);
+	A.mode = MODE_WINDOWS;
+	A.win = reinterpret_cast<const GuidedWindow*>(f->d_in.p + S.in_pts);
+	A.pt_desc = f->d_in.p + S.in_desc;
+	A.mp_in = reinterpret_cast<const int32_t*>(f->d_in.p + S.in_state);
+	A.max_dist = max_dist;
+	A.check_ori = check_orientation != 0;
+	if (orbx_status s = run_search(f, A, S, nmatches)) return s;
+	if (f->n) memcpy(frame_mp, f->h_out + S.out_mp, mp_bytes);
+	return ORBX_OK;
+}
+}  // namespace
+
+orbx_status orbx_search_by_projection_keyframe(orbx_frame f, const orbx_camera* cam, const orbx_pose* pose, float log_scale_factor,
+                                              int32_t* frame_mp, const orbx_keyframe_point* pts, const uint8_t* pt_desc, int npts, float th,
+                                              int orb_dist, int check_orientation, int* nmatches)
+{
+	if (!f || !cam || !pose || !frame_mp || npts < 0 || (npts > 0 && (!pts || !pt_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (!(log_scale_factor > 0.f)) return orbx_fail(ORBX_ERR_INVALID, "logScaleFactor must be positive");
+	for (int c = 0; c < f->n; c++)
+		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
+	GuidedArgs A;
+	Staging S;
+	const size_t win_bytes = (size_t)npts * sizeof(GuidedWindow), mp_bytes = (size_t)f->n * sizeof(int);
+	if (orbx_status s = prepare(f, npts, win_bytes, (size_t)npts * 32, mp_bytes, (size_t)f->n, 0, A, S)) return s;
+	// The geometry of src/ORBmatcher.cc:1376-1406 per map point, in the reference's operation order (cv::Matx products accumulate from
+	// 0 in k order; cv::norm squares in double; MapPoint::PredictScale takes log in double). Host arithmetic, no contraction.
+	GuidedWindow* win = reinterpret_cast<GuidedWindow*>(f->h_in + S.in_pts);
+	float Ow[3];                                   // frame.GetCameraCenter() = -R^T * t (src/Frame.cc:203-206)
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0.f;
+		for (int k = 0; k < 3; k++) s += (pose->R[k * 3 + i] * -1) * pose->t[k];
+		Ow[i] = s;
+	}
+	for (int i = 0; i < npts; i++)
+	{
+		GuidedWindow& w = win[i];
+		w.u = w.v = w.radius = 0.f; w.angle = pts[i].angle; w.levels = 0; w.flags = 0;
+		if (!(pts[i].flags & 1)) continue;         // :1379-1381
+		float xc[3];
+		for (int r = 0; r < 3; r++)
+		{
+			float s = 0.f;
+			for (int k = 0; k < 3; k++) s += pose->R[r * 3 + k] * pts[i].xw[k];
+			xc[r] = s + pose->t[r];
+		}
+		const float invZ = 1.f / xc[2];            // WorldToImage: this variant has no depth test (:1385)
+		const float u = invZ * cam->fx * xc[0] + cam->cx, v = invZ * cam->fy * xc[1] + cam->cy;
+		if (!(u >= f->b.minx && u < f->b.maxx && v >= f->b.miny && v < f->b.maxy)) continue;   // :1389
+		double ss = 0;
+		for (int k = 0; k < 3; k++) { const float d = pts[i].xw[k] - Ow[k]; ss += (double)d * (double)d; }
+		const float dist3D = (float)std::sqrt(ss);                                             // cv::norm(PO), :1394
+		const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;   // src/MapPoint.cc:382-392
+		if (dist3D < minDistance || dist3D > maxDistance) continue;                            // :1400-1401
+		const float ratio = pts[i].max_distance / dist3D;                                      // PredictScale, src/MapPoint.cc:405-414
+		const int scale = (int)std::ceil(std::log((double)ratio) / log_scale_factor);
+		const int ps = std::max(0, std::min(scale, f->nlevels - 1));
+		w.u = u; w.v = v;
+		w.radius = th * f->sf[ps];                 // :1406
+		w.levels = ((ps - 1) & 0xffff) | ((ps + 1) << 16);   // :1408
+		w.flags = 1;
+	}
+	return finish_windows(f, A, S, frame_mp, pt_desc, npts, orb_dist, check_orientation, nmatches);
+}
+
+orbx_status orbx_search_windows(orbx_frame f, int32_t* frame_mp, const orbx_window* windows, const uint8_t* pt_desc, int npts, int max_dist,
+                                int check_orientation, int* nmatches)
+{
+	if (!f || !frame_mp || npts < 0 || (npts > 0 && (!windows || !pt_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	for (int c = 0; c < f->n; c++)
+		if (frame_mp[c] < -3 || frame_mp[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "frame_mp entry is not -3..-1 or a point index");
+	GuidedArgs A;
+	Staging S;
+	if (orbx_status s = prepare(f, npts, (size_t)npts * sizeof(GuidedWindow), (size_t)npts * 32, (size_t)f->n * sizeof(int), (size_t)f->n, 0, A, S)) return s;
+	GuidedWindow* win = reinterpret_cast<GuidedWindow*>(f->h_in + S.in_pts);
+	for (int i = 0; i < npts; i++)
+	{
+		const orbx_window& w = windows[i];
+		if (w.min_level < -32767 || w.min_level > 32767 || w.max_level < -32767 || w.max_level > 32767) return orbx_fail(ORBX_ERR_INVALID, "level out of range");
+		win[i].u = w.u; win[i].v = w.v; win[i].radius = w.radius; win[i].angle = w.angle;
+		win[i].levels = (w.min_level & 0xffff) | (w.max_level << 16);
+		win[i].flags = w.flags & 1;
+	}
+	return finish_windows(f, A, S, frame_mp, pt_desc, npts, max_dist, check_orientation, nmatches);
 }
 
 orbx_status orbx_search_by_bow(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* valid1, orbx_frame f2, const orbx_feature_vector* fv2,

@@ -290,3 +290,32 @@ def bow_pair(seed, n=1500, w=640, h=480, nodes=90, max_flips=60):
     valid1 = (r.rand(n) < 0.85).astype(np.uint8)
     valid2 = (r.rand(n) < 0.85).astype(np.uint8)
     return f1, feature_vector(n1), valid1, f2, feature_vector(n2), valid2
+
+
+KF_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('angle', '<f4'), ('flags', '<i4')])
+
+
+def log_scale_factor(factor=1.2):
+    """pyramid.logScaleFactor as src/System.cc:143 computes it: log (double) of the float scale factor, stored in a float."""
+    return np.float32(np.log(np.float64(np.float32(factor))))
+
+
+def keyframe_points(seed, fr, cam, npts=1200, dup=0.2, max_flips=70):
+    """Map points of a key frame for the relocalisation search SearchByProjection(Frame&, KeyFrame*, alreadyFound, th, ORBdist): world
+    points that project near keypoints of `fr` under the returned pose, with the distance-invariance range of a point first seen at
+    the keypoint's octave (some out of range, some behind the camera, some already found). Returns (pose, pts, desc)."""
+    r = np.random.RandomState(seed + 5)
+    (R, t), _, lp, desc = last_frame_points(seed + 50, fr, cam, npts=npts, dup=dup, max_flips=max_flips)
+    pts = np.zeros(npts, KF_POINT_DTYPE)
+    pts['xw'] = lp['xw']
+    Ow = -(R.astype(np.float64).T @ t.astype(np.float64))
+    dist = np.linalg.norm(lp['xw'].astype(np.float64) - Ow, axis=1)
+    lvl = np.clip(lp['octave'] + r.choice([0, 0, 1, -1], npts), 0, fr['nlevels'] - 1)
+    sf = fr['scale_factors'].astype(np.float64)
+    pts['max_distance'] = (dist * sf[lvl] * (1.0 + 0.05 * r.randn(npts))).astype(np.float32)        # dist * levelScaleFactor (MapPoint::UpdateNormalAndDepth)
+    pts['min_distance'] = (pts['max_distance'] / sf[fr['nlevels'] - 1]).astype(np.float32)
+    far = r.rand(npts) < 0.05
+    pts['max_distance'][far] *= np.float32(0.3)
+    pts['angle'] = lp['angle']
+    pts['flags'] = (r.rand(npts) < 0.85).astype(np.int32)
+    return (R, t), pts, desc

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <random>
+#include <set>
 #include <vector>
 
 #include "orbx/GuidedMatcher.h"
@@ -16,7 +17,7 @@
 namespace {
 
 struct ImageBounds { float minx, maxx, miny, maxy; };
-struct ScalePyramidInfo { std::vector<float> scaleFactors; };
+struct ScalePyramidInfo { std::vector<float> scaleFactors; float logScaleFactor = 0.f; int nlevels = 8; };
 struct CameraParams { float fx, fy, cx, cy, bf, baseline; };
 struct CameraPose
 {
@@ -25,8 +26,13 @@ struct CameraPose
 	const cv::Matx31f& t() const { return t_; }
 };
 
+struct Frame;
 struct MapPoint
 {
+	float minDistance_ = 0, maxDistance_ = 0;                          // include/MapPoint.h; accessors as src/MapPoint.cc:382-414
+	float GetMinDistanceInvariance() const { return 0.8f * minDistance_; }
+	float GetMaxDistanceInvariance() const { return 1.2f * maxDistance_; }
+	inline int PredictScale(float dist, const Frame* frame) const;
 	float trackProjX = 0, trackProjY = 0, trackProjXR = 0, trackViewCos = 0;
 	bool trackInView = false;
 	int trackScaleLevel = 0;
@@ -54,7 +60,15 @@ struct Frame
 	CameraPose pose;
 	ScalePyramidInfo pyramid;
 	ImageBounds imageBounds;
+	cv::Matx31f GetCameraCenter() const { return -pose.R_.t() * pose.t_; }   // src/Frame.cc:203-206, include/CameraPose.h:47
 };
+
+inline int MapPoint::PredictScale(float dist, const Frame* frame) const
+{
+	const float ratio = maxDistance_ / dist;
+	const int scale = static_cast<int>(ceil(log(ratio) / frame->pyramid.logScaleFactor));
+	return std::max(0, std::min(scale, frame->pyramid.nlevels - 1));
+}
 
 std::mt19937 rng(12345);
 float uni(float a, float b) { return std::uniform_real_distribution<float>(a, b)(rng); }
@@ -64,6 +78,7 @@ void make_frame(Frame& f, int n, std::vector<unsigned char>& desc)
 {
 	f.N = n;
 	f.pyramid.scaleFactors.resize(8);
+	f.pyramid.logScaleFactor = (float)log((double)1.2f);
 	f.pyramid.scaleFactors[0] = 1.f;
 	for (int i = 1; i < 8; i++) f.pyramid.scaleFactors[i] = f.pyramid.scaleFactors[i - 1] * 1.2f;
 	f.imageBounds = { 0.f, 640.f, 0.f, 480.f };
@@ -252,6 +267,45 @@ int main()
 		const int g3 = ORB_SLAM2::b200::GuidedMatcher(0.9f, true).SearchForInitialization(frame, dev, f2, dev2, prev, m12, 100);
 		if (w3 != g3 || m12 != m12_want) { printf("initialization %d vs %d\n", g3, w3); return 1; }
 		if (memcmp(prev.data(), prev_want.data(), sizeof(cv::Point2f) * n) != 0) { printf("prevMatched differs\n"); return 1; }
+
+		// ---- SearchByProjection(frame, keyframe, alreadyFound, th, ORBdist): reuse `last`'s world points as the key frame's map points
+		{
+			KeyFrame kf;
+			kf.keypointsUn = last.keypointsUn;
+			kf.mappoints.assign(npts, nullptr);
+			std::set<MapPoint*> found;
+			std::vector<oracle_kf_point> kpts(npts);
+			const cv::Matx31f Ow = frame.GetCameraCenter();
+			for (int i = 0; i < npts; i++)
+			{
+				MapPoint& m = store[i];
+				const cv::Matx31f d = m.worldPos - Ow;
+				const float dist = (float)cv::norm(d);
+				m.maxDistance_ = dist * frame.pyramid.scaleFactors[last.keypoints[i].octave] * uni(0.9f, 1.1f);
+				m.minDistance_ = m.maxDistance_ / frame.pyramid.scaleFactors[7];
+				const bool has = irand(10) < 9;
+				if (has) kf.mappoints[i] = &m;
+				if (has && irand(10) == 0) found.insert(&m);
+				kpts[i] = { { m.worldPos(0), m.worldPos(1), m.worldPos(2) }, m.minDistance_, m.maxDistance_, kf.keypointsUn[i].angle,
+				            (has && !found.count(&m)) ? 1 : 0 };
+			}
+			MapPoint other;
+			for (int c = 0; c < n; c++)
+			{
+				const bool occ = irand(20) == 0;
+				frame.mappoints[c] = occ ? &other : nullptr; code[c] = occ ? -3 : -1;
+			}
+			const int w6 = orc_search_keyframe_projection(&fv, &ocam, &cp, frame.pyramid.logScaleFactor, code.data(), kpts.data(), odesc.data(), npts, 10.f,
+			                                              100, 1);
+			const int g6 = ORB_SLAM2::b200::GuidedMatcher(0.9f, true).SearchByProjection(frame, dev, &kf, found, 10.f, 100);
+			if (w6 != g6) { printf("relocalisation nmatches %d vs %d\n", g6, w6); return 1; }
+			for (int c = 0; c < n; c++)
+			{
+				const MapPoint* w = code[c] >= 0 ? &store[code[c]] : code[c] == -3 ? &other : nullptr;
+				if (frame.mappoints[c] != w) { printf("relocalisation frame.mappoints[%d]\n", c); return 1; }
+			}
+			total += g6;
+		}
 
 		// ---- SearchByBoW, both variants: frame -> key frame 1, f2 -> frame / key frame 2
 		KeyFrame kf1, kf2;

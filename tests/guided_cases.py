@@ -39,6 +39,9 @@ def cases(small=False):
         f1, f2, prev = synth.initialization_pair(seed, n=800 if small else 1500)
         for win in ((100,) if small else (100, 20)):
             out.append((f'init{seed}_w{win}', 'init', dict(f1=f1, f2=f2, prev=prev, window=win, nnratio=0.9, check=seed != 4)))
+        kpose, kpts, kdesc = synth.keyframe_points(seed, fr, cam, npts=700 if small else 1200)
+        out.append((f'reloc{seed}', 'reloc', dict(frame=fr, cam=cam, pose=kpose, mp=mp0, pts=kpts, desc=kdesc, th=10.0 if seed % 2 else 3.0,
+                                                  orb_dist=100 if seed % 2 else 64, check=seed != 1)))
         f1, fv1, va1, f2, fv2, va2 = synth.bow_pair(seed, n=800 if small else 1500)
         out.append((f'bow{seed}_kf_frame', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=None, nnratio=0.7, check=seed != 5)))
         out.append((f'bow{seed}_kf_kf', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=va2, nnratio=0.8 if seed % 2 else 0.75,
@@ -93,6 +96,10 @@ def run_oracle(o, kind, c):
         n, mp = o.search_last_frame(c['frame'], c['cam'], c['cur_pose'], c['last_pose'], c['mp'], c['pts'], c['desc'], c['th'], c['monocular'],
                                     0.9, c['check'])
         return dict(n=np.int32(n), mp=mp)
+    if kind == 'reloc':
+        n, mp = o.search_keyframe_projection(c['frame'], c['cam'], c['pose'], synth.log_scale_factor(), c['mp'], c['pts'], c['desc'], c['th'],
+                                             c['orb_dist'], c['check'])
+        return dict(n=np.int32(n), mp=mp)
     if kind == 'bow':
         n, m2 = o.search_by_bow(c['f1'], c['fv1'], c['valid1'], c['f2'], c['fv2'], c['valid2'], c['nnratio'], c['check'])
         return dict(n=np.int32(n), m2=m2)
@@ -120,6 +127,12 @@ def run_product(api, kind, c, device=0):
         f.mappoints[:] = c['mp']
         n = api.ORBmatcher(0.9, c['check'], device).SearchByProjectionLastFrame(f, c['cam'], c['cur_pose'], c['last_pose'], c['pts'], c['desc'],
                                                                                 c['th'], c['monocular'])
+        return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
+    if kind == 'reloc':
+        f = make_frame(api, c['frame'], device)
+        f.mappoints[:] = c['mp']
+        n = api.ORBmatcher(0.9, c['check'], device).SearchByProjectionKeyFrame(f, c['cam'], c['pose'], synth.log_scale_factor(), c['pts'], c['desc'],
+                                                                               c['th'], c['orb_dist'])
         return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
     f1, f2 = make_frame(api, c['f1'], device), make_frame(api, c['f2'], device)
     if kind == 'bow':
