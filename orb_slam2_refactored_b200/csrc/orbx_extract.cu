@@ -5,6 +5,8 @@
 #include "orbx_internal.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 #include "orbx_sort.cuh"
 
@@ -606,7 +608,6 @@ __device__ __forceinline__ int quadrant_of(uint32_t v, int xm, int ym)
 	return x < xm ? (y < ym ? 0 : 2) : (y < ym ? 1 : 3);
 }
 
-#define QT_BIG 2048
 // Stable 4-way partition of one big node by the whole CTA (see the call site).
 __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint32_t* buf1, uint32_t* cc, int (*s_bigc)[4], int (*s_bigw)[QT_WARPS][4])
 {
@@ -675,8 +676,11 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 // BIG selects the variant with the CTA-parallel sort and big-node partition (4K-class levels); the plain variant keeps the
 // register count at 40 for VGA-class levels, where occupancy matters more than the serial tails.
 template <bool BIG>
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off)
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off, const int big_node_min, const int par_sort_min, unsigned long long* dbg)
 {
+	int dbgk = 0;
+#define QT_STAMP() do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && dbgk < 63) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[1 + dbgk++] = t_; dbg[0] = dbgk; } } while (0)
+	QT_STAMP();
 	extern __shared__ __align__(16) uint8_t qsm[];
 	const int M = P.node_cap;
 	QNode* listA = reinterpret_cast<QNode*>(qsm);
@@ -711,13 +715,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	__syncthreads();
 	const int nroots = L.n_roots;
 	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
-	for (int cidx = warp; cidx < ncell; cidx += QT_WARPS)
+	// 8 lanes per cell (a cell holds ~15 candidates): four cells per warp in flight, so the chain of dependent loads
+	// (count, offset, slots) is walked ncell / 32 times per warp instead of ncell / 8 times
+	for (int cidx = tid >> 3; cidx < ncell; cidx += QT_THREADS / 8)
 	{
 		const int cnt = ccount[cidx], off = coff[cidx];
 		const uint32_t* src = slots + (int64_t)cidx * L.cell_cap;
-		for (int k = lane; k < cnt; k += 32) gathered[off + k] = src[k];
+		for (int k = tid & 7; k < cnt; k += 8) gathered[off + k] = src[k];
 	}
 	__syncthreads();
+	QT_STAMP();
 	if (n == 0)
 	{
 		if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = 0;    // early return of :544-545 (dst == src stays empty)
@@ -765,6 +772,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	}
 	__syncthreads();
 
+	QT_STAMP();
 	QNode* cur = listA;
 	QNode* nxt = listB;
 	const int quota = L.quota;
@@ -785,7 +793,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			np = block_ordered(lastP, s_w, [&](int g) { return QN_CNT(cur[lastP - 1 - g]) > 1; },
 			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
 			__syncthreads();
-			if (BIG && np > 512)
+			if (BIG && np > par_sort_min)
 				qs_sort_block(items, np, segq, segcap, leaf, s_sort);      // large levels (4K): ~2n serial steps instead of ~1.4 n log2 n
 			else
 			{
@@ -796,6 +804,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 		}
 		for (int i = tid; i < listLen; i += QT_THREADS) gone[i] = 0;
 		__syncthreads();
+		QT_STAMP();
 
 		// ---- big nodes (the first passes of a large level: one node can hold tens of thousands of candidates) are divided by
 		//      the whole CTA: chunks of QT_THREADS elements in order, position = quadrant base + earlier chunks + earlier warps of the
@@ -804,7 +813,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			for (int t = 0; t < np; t++)
 			{
 				const QNode nd = cur[proc[t]];
-				if ((int)QN_CNT(nd) >= QT_BIG)                  // uniform: every thread sees the same node
+				if ((int)QN_CNT(nd) >= big_node_min)            // uniform: every thread sees the same node
 					qt_divide_big(nd, buf0, buf1, childcnt + 4 * t, s_bigc, s_bigw);
 			}
 
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 		{
 			const QNode nd = cur[proc[t]];
 			const int cnt = (int)QN_CNT(nd);
-			if (BIG && np <= 64 && cnt >= QT_BIG) continue;        // done by the whole CTA above
+			if (BIG && np <= 64 && cnt >= big_node_min) continue;  // done by the whole CTA above
 			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
 			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
@@ -851,6 +860,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 		}
 		__syncthreads();
 
+		QT_STAMP();
 		// ---- how many of them are really processed: Phase 2 breaks once the list reaches the quota (:666-667)
 		auto nkids = [&](int t) { return (int)(childcnt[4 * t] > 0) + (int)(childcnt[4 * t + 1] > 0) + (int)(childcnt[4 * t + 2] > 0) + (int)(childcnt[4 * t + 3] > 0); };
 		const int totalPush = block_exscan(np, s_w, nkids, [&](int t, int ex) { pbase[t] = ex; });
@@ -872,6 +882,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			__syncthreads();
 		}
 
+		QT_STAMP();
 		// ---- rebuild the list: children in reverse push order, then the surviving old nodes in old order
 		for (int t = tid; t < K; t += QT_THREADS)
 		{
@@ -916,28 +927,35 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 		}
 	}
 
+	QT_STAMP();
 	// ---- keep the best response of every node, first wins ties, list order (:677-692)
 	uint32_t* __restrict__ sel = P.sel + (int64_t)f * P.sel_per_frame + L.sel_base;
-	for (int i = warp; i < listLen; i += QT_WARPS)
+	// 8 lanes per node (final nodes hold ~10 candidates): four nodes per warp in flight. The loop bound is rounded up so that every
+	// lane of a warp takes part in the shuffles.
+	for (int i0 = 0; i0 < listLen; i0 += QT_THREADS / 8)
 	{
-		const QNode nd = cur[i];
-		const int cnt = (int)QN_CNT(nd);
+		const int i = i0 + (tid >> 3);
+		const bool live = i < listLen;
+		const QNode nd = cur[live ? i : 0];
+		const int cnt = live ? (int)QN_CNT(nd) : 0;
 		const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 		int bestr = 0, besti = 0x7fffffff;
-		for (int k = lane; k < cnt; k += 32)
+		for (int k = tid & 7; k < cnt; k += 8)
 		{
 			const int r = orbx_pr(src[k]);
 			if (r > bestr) { bestr = r; besti = k; }
 		}
 #pragma unroll
-		for (int d = 16; d > 0; d >>= 1)
+		for (int d = 4; d > 0; d >>= 1)
 		{
 			const int orr = __shfl_xor_sync(0xffffffffu, bestr, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
 			if (orr > bestr || (orr == bestr && oi < besti)) { bestr = orr; besti = oi; }
 		}
-		if (lane == 0) sel[i] = src[besti];
+		if (live && (tid & 7) == 0) sel[i] = src[besti];
 	}
 	if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = listLen;
+	QT_STAMP();
+#undef QT_STAMP
 }
 
 // =====================================================================================================
@@ -1315,15 +1333,33 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 {
 	const size_t smem = orbx_quadtree_smem(P.node_cap);
 	dim3 grid(P.frames, P.nlevels);
-	if (P.node_cap > 1024)      // some level keeps more than ~1000 keypoints: its sort and first divides are worth a whole CTA
+	// Two variants: BIG replays std::sort with the whole CTA and partitions large nodes block-wide. It costs registers (61 vs 40),
+	// so it pays where one CTA's latency is what the launch waits for: levels that keep more than ~1000 keypoints (4K plans), and
+	// small batches (a frame at a time, as Tracking calls Extract), where the GPU is far from full anyway.
+	static const int force_big = getenv("ORBX_QT_BIG") ? atoi(getenv("ORBX_QT_BIG")) : -1;   // tuning knob
+	const bool large_plan = P.node_cap > 1024, small_batch = P.frames <= 16;
+	static unsigned long long* dbg = nullptr;
+	static const bool want_dbg = getenv("ORBX_QT_STAMPS") != nullptr;
+	if (want_dbg && !dbg) { cudaMalloc(&dbg, 64 * 8); }
+	if (want_dbg) cudaMemsetAsync(dbg, 0, 64 * 8, st);
+	if (force_big >= 0 ? force_big != 0 : (large_plan || small_batch))
 	{
 		cudaFuncSetAttribute(k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_quadtree<true><<<grid, QT_THREADS, smem, st>>>(P, cell_off);
+		k_quadtree<true><<<grid, QT_THREADS, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
 	}
 	else
 	{
 		cudaFuncSetAttribute(k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_quadtree<false><<<grid, QT_THREADS, smem, st>>>(P, cell_off);
+		k_quadtree<false><<<grid, QT_THREADS, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+	}
+	if (want_dbg)
+	{
+		unsigned long long h[64];
+		cudaStreamSynchronize(st);
+		cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[quadtree stamps, level 0 frame 0, us]");
+		for (unsigned long long k = 2; k <= h[0] && k < 64; k++) fprintf(stderr, " %.1f", (double)(h[k] - h[k - 1]) * 1e-3);
+		fprintf(stderr, "\n");
 	}
 }
 
