@@ -282,7 +282,7 @@ def run_b200(args, rank, world, local_rank, emit):
     b_alg = 5 * S - P0 - P7 + 1321 * n_mean
     per_step = {k: v / max(calls, 1) for k, v in stage_ms.items()}
     dominant = max(per_step, key=per_step.get)
-    launches_per_stage = {'pyramid': len(sizes) - 1, 'fast': 1, 'quadtree': 1, 'blur': len(sizes), 'describe': 1}
+    launches_per_stage = {'pyramid': len(sizes) - 1, 'fast': 1, 'quadtree': 1, 'blur': 1, 'describe': 1}
     # roofline of the dominant stage, per launch: its algorithmic bytes for the whole batch / its device time
     dom_bytes_per_step = alg[dominant] * B
     dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0

@@ -978,13 +978,29 @@ __device__ __forceinline__ int reflect101(int i, int n)
 // Horizontal pass with IDP.4A on packed bytes (two 4-tap dot products per output), results stored as 16-bit row pairs
 // (h[2p][x] | h[2p+1][x] << 16); vertical pass with IDP.2A on those pairs (four 2-tap dot products per output).
 // h <= 255*256 fits 16 bits; v = sum K*h < 2^24; out = (v + 32768) >> 16.
-__global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const int level)
+// One launch blurs every level: blockIdx.x runs over the tiles of all levels (the levels do not depend on each other).
+struct BlurTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; };
+// ALL = false: one level per launch (grid = tiles_x, tiles_y, frames), the level is a kernel parameter.
+template <bool ALL>
+__global__ void __launch_bounds__(256) k_gauss7(const OrbxPlanDev P, const BlurTiles T, const int one_level)
 {
 	__shared__ __align__(16) uint32_t raw[GB_RROWS * GB_RWORDS];
 	__shared__ __align__(16) uint32_t hv[(GB_RROWS / 2) * GB_TW];
+	int level = one_level, tile_x = blockIdx.x, tile_y = blockIdx.y;
+	if (ALL)
+	{
+		// unrolled so that every index into T is a compile-time constant (a dynamic index would copy the struct to local memory)
+		int base = 0, tx = T.tx[0];
+		level = 0;
+#pragma unroll
+		for (int s = 1; s < ORBX_MAX_LEVELS; s++)
+			if ((int)blockIdx.x >= T.base[s] && T.base[s + 1] > T.base[s]) { level = s; base = T.base[s]; tx = T.tx[s]; }
+		const int tile = (int)blockIdx.x - base;
+		tile_y = tile / tx; tile_x = tile - tile_y * tx;
+	}
 	const OrbxLevel& L = P.lv[level];
 	const int f = blockIdx.z, tid = threadIdx.x;
-	const int x0 = blockIdx.x * GB_TW, y0 = blockIdx.y * GB_TH;
+	const int x0 = tile_x * GB_TW, y0 = tile_y * GB_TH;
 	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level);
 	const int64_t sp = orbx_level_pitch(P, level);
 	uint8_t* __restrict__ dst = P.blur + (int64_t)f * P.slab + L.offset;
@@ -1365,11 +1381,29 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 
 void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
 {
+	// Small batches (a frame at a time): one launch over the tiles of all levels, 8 launches fewer on the critical path (single-frame
+	// blur 36 -> 9 us). Large batches: one launch per level, which measures ~6 % faster there.
+	const bool one_launch = P.frames <= 16;
+	BlurTiles T = {};
+	if (one_launch)
+	{
+		T.base[0] = 0;
+		for (int s = 0; s < P.nlevels; s++)
+		{
+			const OrbxLevel& L = P.lv[s];
+			T.tx[s] = (L.w + GB_TW - 1) / GB_TW;
+			T.base[s + 1] = T.base[s] + T.tx[s] * ((L.h + GB_TH - 1) / GB_TH);
+		}
+		for (int s = P.nlevels; s < ORBX_MAX_LEVELS; s++) { T.tx[s] = 1; T.base[s + 1] = T.base[s]; }
+		dim3 grid(T.base[P.nlevels], 1, P.frames);
+		k_gauss7<true><<<grid, 256, 0, st>>>(P, T, 0);
+		return;
+	}
 	for (int s = 0; s < P.nlevels; s++)
 	{
 		const OrbxLevel& L = P.lv[s];
 		dim3 grid((L.w + GB_TW - 1) / GB_TW, (L.h + GB_TH - 1) / GB_TH, P.frames);
-		k_gauss7<<<grid, 256, 0, st>>>(P, s);
+		k_gauss7<false><<<grid, 256, 0, st>>>(P, T, s);
 	}
 }
 
