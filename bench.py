@@ -503,6 +503,19 @@ def run_b200(args, rank, world, local_rank, emit):
                               'note': 'the 2.9 MB table is shared by all frames of a launch and stays in L2, so DRAM traffic is ~2 B/px'}}
         del d_rect, d_raw
 
+    # ---- single-frame latency: what SystemImpl::Track* sees per image (one Extract call, host frame in, keypoints + descriptors out)
+    latency = None
+    if rank == 0 and not args.skip_guided:
+        lex = api.ORBextractor(nfeatures=1000, device=local_rank)
+        one = torch.from_numpy(host[:1].copy()).pin_memory().numpy()
+        for _ in range(10):
+            lex.ExtractBatch(one)
+        t0l = time.perf_counter()
+        for _ in range(100):
+            lex.ExtractBatch(one)
+        latency = {'workload': 'C1, one frame per call through ORBextractor.ExtractBatch (pinned host frame in, host keypoints + descriptors out)',
+                   'ms_per_call': (time.perf_counter() - t0l) / 100 * 1e3}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -541,6 +554,7 @@ def run_b200(args, rank, world, local_rank, emit):
             'stereo': stereo,
             'guided': guided,
             'remap': remap,
+            'latency': latency,
         }
         emit(json.dumps(line))
 
