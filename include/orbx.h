@@ -195,6 +195,11 @@ orbx_status orbx_rectify_batch_device(orbx_handle h, const uint8_t* d_raw, int f
                                       size_t dst_pitch, size_t dst_stride);
 orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, int frames, int src_width, int src_height, size_t pitch,
                                          size_t frame_stride, orbx_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* UndistortKeyPoints — src/System.cc:153-174: cv::undistortPoints(pts, pts, K, distCoeffs, noArray(), K) on every keypoint position
+ * (OpenCV's 5-round double-precision iteration); `dist` holds ndist (0..14) OpenCV distortion coefficients k1 k2 p1 p2 [k3 [k4 k5 k6
+ * [s1..s4]]]. kps_un = kps when dist[0] == 0, as the reference does. Host buffers. */
+orbx_status orbx_undistort_keypoints(int device, const orbx_keypoint* kps, int n, const orbx_camera* camera, const float* dist, int ndist,
+                                     orbx_keypoint* kps_un);
 /* ComputeStereoFromRGBD — src/System.cc:197-219: depth_map is width x height float32 (pitch in bytes). Host buffers. */
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
                                   int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth);

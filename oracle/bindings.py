@@ -99,6 +99,7 @@ class Oracle:
         f('convert_to_gray', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t])
         f('stereo_from_rgbd', None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(Camera), C.c_void_p, C.c_void_p])
         f('distinctive_index', C.c_int, [C.c_void_p, C.c_int])
+        f('undistort_keypoints', None, [C.c_void_p, C.c_int, C.POINTER(Camera), C.c_void_p, C.c_int, C.c_void_p])
         f('grid_create', C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(Bounds), C.c_int])
         f('grid_destroy', None, [C.c_void_p])
         f('grid_query', C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int])
@@ -208,6 +209,14 @@ class Oracle:
         self._stereo_from_rgbd(_p(kps), _p(kps_un), len(kps), _p(depth_map), depth_map.shape[1], depth_map.shape[0], depth_map.strides[0],
                                C.byref(c), _p(ur), _p(dp))
         return ur, dp
+
+    def undistort_keypoints(self, kps, cam, dist):
+        """UndistortKeyPoints (src/System.cc:153-174): cam = (fx, fy, cx, cy, bf, baseline), dist = OpenCV distortion coefficients."""
+        kps = np.ascontiguousarray(kps).view(KP_DTYPE)
+        d = np.ascontiguousarray(dist, np.float32)
+        out = np.empty_like(kps)
+        self._undistort_keypoints(_p(kps), len(kps), C.byref(Camera(*[float(c) for c in cam])), _p(d), len(d), _p(out))
+        return out
 
     def distinctive_index(self, desc):
         desc = np.ascontiguousarray(desc, np.uint8)

@@ -305,4 +305,36 @@ void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const flo
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) (modules/calib3d/src/undistort.dispatch.cpp, cvUndistortPointsInternal):
+// everything in double, 5 fixed iterations (TermCriteria(MAX_ITER, 5, 0.01): no epsilon test), coefficients k1 k2 p1 p2 k3 k4 k5 k6
+// s1..s4, no tilt; then the new camera matrix P = K is applied and the result is rounded to float. Pinned by tests/golden/primitives.npz.
+// ---------------------------------------------------------------------------------------------
+void undistort_points(const float* xy, int n, float fx_, float fy_, float cx_, float cy_, const float* dist, int ndist, float* out)
+{
+	double k[14] = { 0 };
+	for (int i = 0; i < ndist && i < 14; i++) k[i] = dist[i];
+	const double fx = fx_, fy = fy_, cx = cx_, cy = cy_, ifx = 1. / fx, ify = 1. / fy;
+	for (int i = 0; i < n; i++)
+	{
+		const double u = xy[2 * i], v = xy[2 * i + 1];
+		double x = (u - cx) * ifx, y = (v - cy) * ify;
+		const double x0 = x, y0 = y;
+		for (int j = 0; j < 5; j++)
+		{
+			const double r2 = x * x + y * y;
+			const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+			if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+			const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+			const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+			x = (x0 - deltaX) * icdist;
+			y = (y0 - deltaY) * icdist;
+		}
+		// RR = P * I with P = K: rows (fx 0 cx), (0 fy cy), (0 0 1)
+		const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+		out[2 * i] = (float)(xx * ww);
+		out[2 * i + 1] = (float)(yy * ww);
+	}
+}
+
 }  // namespace cvp

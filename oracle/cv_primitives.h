@@ -49,6 +49,7 @@ void gauss7x7_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, s
 // cv::cvtColor(src, dst, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY), 8-bit: (R*9798 + G*19235 + B*3735 + 16384) >> 15
 // (OpenCV 4.13.0, verified on 5 M random pixels, IPP on and off). channels = 3 or 4; rgb = first channel is R.
 void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, bool rgb, uint8_t* dst, size_t dstep);
+void undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist, float* out);
 void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, size_t mstep_bytes,
                      uint8_t* dst, int dw, int dh, size_t dstep);
 

@@ -223,6 +223,8 @@ public:
 		for (int i = 0; i < (r < c ? r : c); i++) m(i, i) = T(1);
 		return m;
 	}
+	T& operator()(int i) { return reinterpret_cast<T*>(this->data)[i]; }                 // vector-like access, continuous matrices
+	const T& operator()(int i) const { return reinterpret_cast<const T*>(this->data)[i]; }
 	T& operator()(int y, int x) { return this->template at<T>(y, x); }
 	const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
 };
@@ -236,6 +238,8 @@ float fastAtan2(float y, float x);
 enum { COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7, COLOR_BGRA2GRAY = 10, COLOR_RGBA2GRAY = 11 };
 void cvtColor(const Mat& src, Mat& dst, int code);
 typedef Mat_<float> Mat1f;
+// cv::undistortPoints as src/System.cc:165 calls it: points in place, K 3x3 CV_32F, distortion coefficients CV_32F, no R, P = K
+void undistortPoints(const std::vector<Point2f>& src, std::vector<Point2f>& dst, const Mat& K, const Mat& distCoeffs, const Mat& R, const Mat& P);
 enum { INTER_LINEAR = 1 };
 // cv::remap as Examples/Stereo/stereo_euroc.cc:100-101 calls it: 8-bit single channel, two CV_32F maps, INTER_LINEAR, default border
 void remap(const Mat& src, Mat& dst, const Mat& map1, const Mat& map2, int interpolation);

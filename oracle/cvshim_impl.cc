@@ -49,6 +49,17 @@ void cvtColor(const Mat& src, Mat& dst, int code)
 	dst = out;
 }
 
+void undistortPoints(const std::vector<Point2f>& src, std::vector<Point2f>& dst, const Mat& K, const Mat& distCoeffs, const Mat& R, const Mat& P)
+{
+	CV_Assert(K.type() == CV_32F && K.rows == 3 && K.cols == 3 && distCoeffs.type() == CV_32F && R.empty());
+	CV_Assert(P.data == K.data || (P.rows == 3 && P.cols == 3));
+	const int nd = distCoeffs.rows * distCoeffs.cols;
+	std::vector<Point2f> out(src.size());
+	cvp::undistort_points(reinterpret_cast<const float*>(src.data()), (int)src.size(), K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2),
+	                      K.at<float>(1, 2), distCoeffs.ptr<float>(), nd, reinterpret_cast<float*>(out.data()));
+	dst = out;
+}
+
 void remap(const Mat& src, Mat& dst, const Mat& map1, const Mat& map2, int interpolation)
 {
 	CV_Assert(interpolation == INTER_LINEAR && src.type() == CV_8U && map1.type() == CV_32F && map2.type() == CV_32F);

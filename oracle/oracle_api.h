@@ -90,6 +90,9 @@ void ORACLE_FN(convert_to_gray)(const uint8_t* src, int w, int h, size_t pitch, 
 // ComputeStereoFromRGBD (src/System.cc:197-219): depth map is float32, pitch in bytes
 void ORACLE_FN(stereo_from_rgbd)(const oracle_keypoint* kps, const oracle_keypoint* kps_un, int n, const float* depth_map, int w, int h,
                                  size_t pitch, const oracle_camera* cam, float* uright, float* depth);
+// UndistortKeyPoints (src/System.cc:153-174): cv::undistortPoints with P = K; dist has ndist (4, 5, 8, 12) coefficients; kps_un = kps when
+// dist[0] == 0
+void ORACLE_FN(undistort_keypoints)(const oracle_keypoint* kps, int n, const oracle_camera* cam, const float* dist, int ndist, oracle_keypoint* kps_un);
 // the distance matrix + least-median selection of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314): index of the
 // descriptor with the least median distance to the others, first wins ties
 int ORACLE_FN(distinctive_index)(const uint8_t* desc, int n);

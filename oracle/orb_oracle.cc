@@ -668,6 +668,16 @@ void orc_cv_gaussian7(const uint8_t* src, int w, int h, size_t sstep, uint8_t* d
 {
 	cvp::gauss7x7_u8(src, w, h, sstep, dst, dstep);
 }
+void orc_undistort_keypoints(const oracle_keypoint* kps, int n, const oracle_camera* cam, const float* dist, int ndist, oracle_keypoint* kps_un)
+{
+	// UndistortKeyPoints (src/System.cc:153-174): untouched when distCoeffs(0) == 0, else every pt through cv::undistortPoints(.., K, dist, noArray(), K)
+	for (int i = 0; i < n; i++) kps_un[i] = kps[i];
+	if (ndist < 1 || dist[0] == 0.f) return;
+	std::vector<float> in((size_t)n * 2), out((size_t)n * 2);
+	for (int i = 0; i < n; i++) { in[2 * i] = kps[i].x; in[2 * i + 1] = kps[i].y; }
+	cvp::undistort_points(in.data(), n, cam->fx, cam->fy, cam->cx, cam->cy, dist, ndist, out.data());
+	for (int i = 0; i < n; i++) { kps_un[i].x = out[2 * i]; kps_un[i].y = out[2 * i + 1]; }
+}
 void orc_cv_remap(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, size_t mstep, uint8_t* dst, int dw, int dh,
                   size_t dstep)
 {

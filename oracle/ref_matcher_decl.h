@@ -38,6 +38,7 @@ void ComputeStereoMatches(
 
 size_t DistinctiveIndex(const std::vector<cv::Mat>& descriptors);
 void ConvertToGrayRef(const cv::Mat& src, cv::Mat& dst, bool RGB);
+void UndistortKeyPointsRef(const KeyPoints& src, KeyPoints& dst, const cv::Mat& K, const cv::Mat1f& distCoeffs);
 void ComputeStereoFromRGBDRef(const KeyPoints& keypoints, const KeyPoints& keypointsUn, const cv::Mat& depthImage,
 	const CameraParams& camera, std::vector<float>& uright, std::vector<float>& depth);
 

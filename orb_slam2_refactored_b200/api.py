@@ -111,6 +111,7 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p]),
     'orbx_distinctive_descriptors': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_measure_popc_peak': (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    'orbx_undistort_keypoints': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(_Camera), C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_remap': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
                              C.c_size_t]),
     'orbx_set_rectification': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -610,6 +611,16 @@ def ConvertToGray(src, RGB=True, device=0):
     dst = np.empty((h, w), np.uint8)
     _check(lib().orbx_convert_to_gray(device, _p(src), w, h, src.strides[0], ch, int(RGB), _p(dst), dst.strides[0]))
     return dst
+
+
+def UndistortKeyPoints(keypoints, camera, distCoeffs, device=0):
+    """src/System.cc:153-174: keypoints with their positions run through cv::undistortPoints(.., K, distCoeffs, noArray(), K)."""
+    kps = np.ascontiguousarray(keypoints).view(KP_DTYPE)
+    d = np.ascontiguousarray(distCoeffs, np.float32).reshape(-1)
+    out = np.empty_like(kps)
+    cam = _Camera(*[float(c) for c in camera])
+    _check(lib().orbx_undistort_keypoints(device, _p(kps), len(kps), C.byref(cam), _p(d), len(d), _p(out)))
+    return out
 
 
 def Remap(src, map1, map2, device=0):

@@ -1114,6 +1114,29 @@ orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, i
 	return extract_batch_impl(h, images, frames, src_width, src_height, pitch, frame_stride, 1, 0, kps, desc, cap, n, true);
 }
 
+orbx_status orbx_undistort_keypoints(int device, const orbx_keypoint* kps, int n, const orbx_camera* camera, const float* dist, int ndist,
+                                     orbx_keypoint* kps_un)
+{
+	if (!kps || !kps_un || !camera || n < 0 || ndist < 0 || ndist > 14 || (ndist > 0 && !dist)) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (ndist == 0 || dist[0] == 0.f)            // src/System.cc:155-159: dst = src
+	{
+		if (kps_un != kps) std::memcpy(kps_un, kps, sizeof(orbx_keypoint) * (size_t)n);
+		return ORBX_OK;
+	}
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (n == 0) return ORBX_OK;
+	CU(cudaSetDevice(device));
+	DevBuf<orbx_keypoint> ds, dd;
+	CU(ds.ensure(n)); CU(dd.ensure(n));
+	CU(cudaMemcpy(ds.p, kps, sizeof(orbx_keypoint) * n, cudaMemcpyHostToDevice));
+	const float cam4[4] = { camera->fx, camera->fy, camera->cx, camera->cy };
+	orbx_launch_undistort(ds.p, dd.p, n, cam4, dist, ndist, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(kps_un, dd.p, sizeof(orbx_keypoint) * n, cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
                                   int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth)
 {

@@ -131,6 +131,7 @@ int orbx_stereo_items_per_keypoint(float max_scale);   // upper bound of the row
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st);
 void orbx_launch_stereo_from_rgbd(const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const uint8_t* depth_map, int64_t pitch, float bf,
                                   float* uright, float* depth, cudaStream_t st);
+void orbx_launch_undistort(const orbx_keypoint* src, orbx_keypoint* dst, int n, const float* cam4, const float* dist, int ndist, cudaStream_t st);
 void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int nsets, int32_t* best, cudaStream_t st);
 double orbx_popc_probe(int device);
 

@@ -627,6 +627,54 @@ void orbx_launch_distinctive(const uint8_t* desc, const int64_t* offsets, int ns
 	k_distinctive<<<nsets, DD_WARPS * 32, 0, st>>>(desc, offsets, best);
 }
 
+// UndistortKeyPoints (src/System.cc:153-174) = cv::undistortPoints(pts, pts, K, distCoeffs, noArray(), K): OpenCV's double-precision
+// fixed-point iteration (5 rounds, no epsilon test), then the camera matrix again, rounded to float. FP64 on the device, no contraction.
+struct UndistortArgs { double fx, fy, cx, cy, k[14]; };
+__global__ void __launch_bounds__(256) k_undistort_keypoints(const orbx_keypoint* __restrict__ src, orbx_keypoint* __restrict__ dst, int n, const UndistortArgs A)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	orbx_keypoint kp = src[i];
+	const double ifx = __ddiv_rn(1.0, A.fx), ify = __ddiv_rn(1.0, A.fy);
+	const double u = (double)kp.x, v = (double)kp.y;
+	double x = __dmul_rn(__dsub_rn(u, A.cx), ifx), y = __dmul_rn(__dsub_rn(v, A.cy), ify);
+	const double x0 = x, y0 = y;
+	const double* k = A.k;
+	for (int j = 0; j < 5; j++)
+	{
+		const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+		const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+		const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+		const double icdist = __ddiv_rn(num, den);
+		if (icdist < 0) { x = __dmul_rn(__dsub_rn(u, A.cx), ifx); y = __dmul_rn(__dsub_rn(v, A.cy), ify); break; }
+		// deltaX = 2*k[2]*x*y + k[3]*(r2 + 2*x*x) + k[8]*r2 + k[9]*r2*r2, left to right
+		const double dX = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y),
+		                                                __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))),
+		                                      __dmul_rn(k[8], r2)), __dmul_rn(__dmul_rn(k[9], r2), r2));
+		// deltaY = k[2]*(r2 + 2*y*y) + 2*k[3]*x*y + k[10]*r2 + k[11]*r2*r2
+		const double dY = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+		                                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y)),
+		                                      __dmul_rn(k[10], r2)), __dmul_rn(__dmul_rn(k[11], r2), r2));
+		x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+		y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+	}
+	// RR = K * I: xx = fx*x + 0*y + cx, yy = 0*x + fy*y + cy, ww = 1 / (0*x + 0*y + 1)
+	const double xx = __dadd_rn(__dadd_rn(__dmul_rn(A.fx, x), __dmul_rn(0.0, y)), A.cx);
+	const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(A.fy, y)), A.cy);
+	const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(0.0, y)), 1.0));
+	kp.x = __double2float_rn(__dmul_rn(xx, ww));
+	kp.y = __double2float_rn(__dmul_rn(yy, ww));
+	dst[i] = kp;
+}
+
+void orbx_launch_undistort(const orbx_keypoint* src, orbx_keypoint* dst, int n, const float* cam4, const float* dist, int ndist, cudaStream_t st)
+{
+	UndistortArgs A;
+	A.fx = cam4[0]; A.fy = cam4[1]; A.cx = cam4[2]; A.cy = cam4[3];
+	for (int i = 0; i < 14; i++) A.k[i] = i < ndist ? (double)dist[i] : 0.0;
+	k_undistort_keypoints<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, A);
+}
+
 int orbx_stereo_items_per_keypoint(float max_scale) { return 2 * (int)ceilf(2.f * max_scale) + 3; }
 
 void orbx_launch_stereo(const OrbxStereoArgs& A, cudaStream_t st)

@@ -38,6 +38,13 @@ def fast_cv(img, th):
     return np.array([(int(p.pt[0]), int(p.pt[1]), int(p.response)) for p in k], np.int32).reshape(-1, 3)
 
 
+UNDISTORT_CASES = {
+    'tum1': ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+    'k4': ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),          # EuRoC cam0, 4 coefficients
+    'strong': ((300.0, 310.0, 320.0, 240.0), (-0.9, 2.5, 0.01, -0.02, -4.0, 0.3, -0.2, 0.1)),                     # 8 coefficients, hits icdist < 0
+}
+
+
 def adversarial_maps(seed, w, h):
     """Maps of a different size than the source with coordinates up to 10 px outside it and many exact x.5/32 ties."""
     r = np.random.RandomState(seed)
@@ -77,6 +84,13 @@ def primitives():
         ax, ay = adversarial_maps(6, ww, hh)
         out[f'remap_adv_{name}'] = cv2.remap(src, ax, ay, cv2.INTER_LINEAR)
         out[f'remap_{name}_crc'] = np.array([crc(mx), crc(my), crc(ax), crc(ay)])
+    # cv::undistortPoints(pts, K, dist, None, K) with the TUM1 and a strong synthetic distortion (Examples/Monocular/TUM1.yaml:9-18)
+    ru = np.random.RandomState(12)
+    upts = np.stack([ru.rand(4000) * 660 - 10, ru.rand(4000) * 500 - 10], 1).astype(np.float32)
+    out['undist_pts_crc'] = crc(upts)
+    for tag, (cam, dist) in UNDISTORT_CASES.items():
+        K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+        out[f'undist_{tag}'] = cv2.undistortPoints(upts.reshape(-1, 1, 2), K, np.array(dist, np.float32), None, K).reshape(-1, 2)
     r = np.random.RandomState(3)
     y = r.randint(-60000, 60000, 4000).astype(np.float32); x = r.randint(-60000, 60000, 4000).astype(np.float32)
     y[:50] = 0; x[50:100] = 0; y[100] = 0; x[100] = 0

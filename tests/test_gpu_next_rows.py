@@ -105,3 +105,24 @@ def test_extract_rectified_fused(orbx, oracle_port):
         orbx.ORBextractor(nfeatures=500).ExtractBatchRectified(raw)        # no maps set
     with pytest.raises(orbx.OrbxError):
         ex.ExtractBatchRectified(raw[:, :400])                              # not the frame size the maps were set for
+
+
+def test_undistort_keypoints(orbx, oracle_port):
+    """UndistortKeyPoints (src/System.cc:153-174) on the keypoints of a real extraction with the TUM1 distortion, and on scattered points
+    with 4-, 5- and 8-coefficient models against cv2's own output (tests/golden/primitives.npz). Bit-exact: FP64 on the device."""
+    import os
+    from test_oracle_golden import UNDISTORT_CASES, undistort_input, G
+    prim = np.load(os.path.join(G, 'primitives.npz'))
+    cam, dist = UNDISTORT_CASES['tum1']
+    cam6 = cam + (40.0, 40.0 / cam[0])
+    kps, _ = orbx.ORBextractor(nfeatures=1000).Extract(synth.image(4, 640, 480))
+    got = orbx.UndistortKeyPoints(kps, cam6, dist)
+    assert got.tobytes() == oracle_port.undistort_keypoints(kps, cam6, dist).tobytes()
+    assert np.abs(got['x'] - kps['x']).max() > 1.0 and np.array_equal(got['angle'], kps['angle'])
+    assert orbx.UndistortKeyPoints(kps, cam6, [0, 0, 0, 0, 0]).tobytes() == kps.tobytes()       # distCoeffs(0) == 0: dst = src
+    pts = undistort_input()
+    scattered = np.zeros(len(pts), kps.dtype)
+    scattered['x'], scattered['y'] = pts[:, 0], pts[:, 1]
+    for tag, (c, d) in UNDISTORT_CASES.items():
+        out = orbx.UndistortKeyPoints(scattered, c + (40.0, 0.1), d)
+        assert np.array_equal(np.stack([out['x'], out['y']], 1), prim[f'undist_{tag}']), tag
