@@ -179,3 +179,29 @@ def test_two_extractors_on_two_threads(orbx, oracle_port):
     for i, img in enumerate((L, R)):
         ok, od = oracle_port.extractor(c['nfeatures']).extract(img)
         assert out[i][0].tobytes() == ok.tobytes() and np.array_equal(out[i][1], od)
+
+
+@pytest.mark.parametrize('w,h,nf,scale,nlevels,ini,mn', [
+    (640, 480, 1000, 1.1, 8, 20, 7),        # slow pyramid: every source row feeds two output rows
+    (640, 480, 1000, 1.5, 4, 20, 7),
+    (1241, 376, 1500, 2.0, 3, 20, 7),       # the steepest pyramid the resize tiles take
+    (800, 600, 300, 1.2, 12, 20, 7),        # 12 levels (ORBX_MAX_LEVELS), small quota: the quadtree stops early everywhere
+    (752, 480, 5000, 1.2, 8, 12, 5),        # more keypoints than corners on the upper levels, low thresholds
+    (640, 480, 1000, 1.2, 8, 40, 30),       # high thresholds: many empty cells
+    (640, 480, 1000, 1.2, 1, 20, 7),        # a single level
+    (333, 251, 500, 1.3, 5, 20, 7),         # odd sizes, widths that are no multiple of 4
+])
+def test_parameter_sweep(orbx, oracle_port, w, h, nf, scale, nlevels, ini, mn):
+    """Extract with non-default ORBextractor::Parameters (include/ORBextractor.h:38-50): keypoints and descriptors bit-equal, and the
+    pyramid levels too (the resize tables depend on the scale factor)."""
+    ex = orbx.ORBextractor(nfeatures=nf, scaleFactor=scale, nlevels=nlevels, iniThFAST=ini, minThFAST=mn)
+    e = oracle_port.extractor(nf, scale, nlevels, ini, mn)
+    for seed in (31, 32):
+        img = synth.image(seed, w, h)
+        k, d = ex.Extract(img)
+        ok, od = e.extract(img)
+        assert len(ok) > 50
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od), (w, h, nf, scale, nlevels, seed)
+    for a, b in zip(ex.GetImagePyramid(), e.pyramid()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(ex.GetFeatureQuotas(), oracle_port.quotas(nf, scale, nlevels))
