@@ -131,8 +131,12 @@ __global__ void __launch_bounds__(256) k_remap_to_l0(const uint8_t* __restrict__
 #define PY_RW 16      // output rows per warp
 #define PY_SRC 288    // source rows a tile may touch: 127 * scaleFactor + 2; scale factors up to 2.2 (checked on the host)
 #define PY_SW 304     // source bytes per staged row: 15 (alignment) + 128 * scaleFactor + 2, rounded up to 16
+// RW = output rows per warp (tile height 8 * RW): 16 for throughput, 4 for small batches, where a level has too few 128-row tiles to
+// fill the GPU and the per-warp row walk is the launch's latency.
+template <int RW>
 __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, const int level)
 {
+	constexpr int TH = 8 * RW;
 	// The source rows/columns an output tile needs are staged in shared memory with 16-byte async copies (level buffers are padded:
 	// pitch a multiple of 128, 256 spare bytes in front and behind). A thread then walks DOWN its 4 columns: the horizontal pass of a
 	// source row (2 taps x 4 columns) is computed once and kept in registers while the 1-2 output rows that need it are produced, so
@@ -142,8 +146,8 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 	const OrbxLevel& D = P.lv[level];
 	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
 	const int f = blockIdx.z, tid = threadIdx.x;
-	const int dx0 = blockIdx.x * PY_TW, dy0 = blockIdx.y * PY_TH;
-	const int dy_last = min(dy0 + PY_TH, D.h) - 1, dx_last = min(dx0 + PY_TW, D.w) - 1;
+	const int dx0 = blockIdx.x * PY_TW, dy0 = blockIdx.y * TH;
+	const int dy_last = min(dy0 + TH, D.h) - 1, dx_last = min(dx0 + PY_TW, D.w) - 1;
 	const uint8_t* __restrict__ src = orbx_level_ptr(P, f, level - 1);
 	const int64_t sp = orbx_level_pitch(P, level - 1);
 	uint8_t* __restrict__ dst = P.pyr + (int64_t)f * P.slab + D.offset;
@@ -178,9 +182,9 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 		a0[j] = a.x; a1[j] = a.y;
 	}
 	// the warp's rows: lane k holds source row and coefficients of row k, broadcast by shuffle in the loop
-	const int wy0 = dy0 + warp * PY_RW;
+	const int wy0 = dy0 + warp * RW;
 	int my_sy = 0, my_b = 0;
-	if (lane < PY_RW)
+	if (lane < RW)
 	{
 		const int dy = min(wy0 + lane, D.h - 1);
 		my_sy = __ldg(yofs + dy);
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 		for (int j = 0; j < 4; j++) h[j] = ((int)row[x0r[j]] * a0[j] + (int)row[x1r[j]] * a1[j]) >> 4;
 	};
 	int rc = -2, h0[4], h1[4];          // h0 = row rc, h1 = row min(rc + 1, sh - 1)
-	const int nrows = min(PY_RW, D.h - wy0);
+	const int nrows = min(RW, D.h - wy0);
 	for (int k = 0; k < nrows; k++)
 	{
 		const int r = __shfl_sync(0xffffffffu, my_sy, k), bw = __shfl_sync(0xffffffffu, my_b, k);
@@ -1312,17 +1316,22 @@ void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int 
 void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
-	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + PY_TH - 1) / PY_TH, P.frames);
+	const bool small_batch = P.frames <= 16;
+	const int th = small_batch ? 32 : PY_TH;
+	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + th - 1) / th, P.frames);
 	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem), up to PY_SRC * PY_SW = 86 KB
 	static bool attr_set[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev >= 0 && dev < 64 && !attr_set[dev])
 	{
-		cudaFuncSetAttribute(k_pyramid_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
+		cudaFuncSetAttribute(k_pyramid_resize<PY_RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
+		cudaFuncSetAttribute(k_pyramid_resize<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
 		attr_set[dev] = true;
 	}
-	k_pyramid_resize<<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
+	// py_smem is sized for the 128-row tile: an upper bound for the 32-row one
+	if (small_batch) k_pyramid_resize<4><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
+	else k_pyramid_resize<PY_RW><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 }
 
 int orbx_fast_tile_stride() { return FT_TS; }
