@@ -200,6 +200,9 @@ orbx_status orbx_extract_batch_rectified(orbx_handle h, const uint8_t* images, i
  * [s1..s4]]]. kps_un = kps when dist[0] == 0, as the reference does. Host buffers. */
 orbx_status orbx_undistort_keypoints(int device, const orbx_keypoint* kps, int n, const orbx_camera* camera, const float* dist, int ndist,
                                      orbx_keypoint* kps_un);
+/* Device-resident variant, asynchronous on `stream` (a cudaStream_t as void*, NULL = default stream); in place when d_kps_un == d_kps. */
+orbx_status orbx_undistort_keypoints_device(const orbx_keypoint* d_kps, int n, const orbx_camera* camera, const float* dist, int ndist,
+                                            orbx_keypoint* d_kps_un, void* stream);
 /* ComputeStereoFromRGBD — src/System.cc:197-219: depth_map is width x height float32 (pitch in bytes). Host buffers. */
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
                                   int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth);
@@ -239,6 +242,12 @@ typedef struct orbx_frame_s* orbx_frame;
 orbx_status orbx_frame_create(const orbx_frame_view* view, int device, orbx_frame* out);
 /* Re-uses the device buffers of `f` for another frame (Tracking builds one Frame per image): uploads the view, rebuilds the grid. */
 orbx_status orbx_frame_assign(orbx_frame f, const orbx_frame_view* view);
+/* The same from device-resident data — e.g. straight from orbx_extract_batch_device's outputs (through orbx_undistort_keypoints_device
+ * where the camera has distortion) and orbx_stereo_match_device's uright: Extract -> Frame -> SearchByProjection without the keypoints
+ * and descriptors ever leaving the GPU. The frame copies what it is given (device to device); d_uright may be NULL (monocular). The
+ * caller must have ordered the producing work before this call (it runs on the frame's own stream). Octaves must be < 16. */
+orbx_status orbx_frame_assign_device(orbx_frame f, const orbx_keypoint* d_kps_un, const uint8_t* d_desc, const float* d_uright, int n,
+                                     const orbx_bounds* bounds, int nlevels, const float* scale_factors);
 orbx_status orbx_frame_destroy(orbx_frame f);
 /* The grid as CSR: cell_start has 64*48+1 entries, cell = cx*48 + cy (grid_[cx][cy], include/Frame.h:72-79); items holds the keypoint
  * indices of every cell in push_back order. *n_items = number of keypoints inside the grid. */

@@ -134,6 +134,8 @@ _SIGNATURES = {
     'orbx_search_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_by_bow': (C.c_int, [C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_float,
                                      C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    'orbx_frame_assign_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Bounds), C.c_int, C.c_void_p]),
+    'orbx_undistort_keypoints_device': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_Camera), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
 }
 
@@ -421,6 +423,19 @@ class Frame:
         if h is not None and _lib is not None:
             _lib.orbx_frame_destroy(h)
             self._h = None
+
+    def assign_device(self, d_kps_un, d_desc, n, scaleFactors, imageBounds, d_uright=None):
+        """The next Frame from device-resident keypoints / descriptors (torch tensors or anything with data_ptr()), e.g. the outputs of
+        ORBextractor.extract_batch_device. `mappoints` is reset to all -1; keypointsUn / descriptors are not mirrored on the host."""
+        sf = np.ascontiguousarray(scaleFactors, np.float32)
+        b = _Bounds(*[float(np.float32(v)) for v in imageBounds])
+        _check(lib().orbx_frame_assign_device(self._h, C.c_void_p(d_kps_un.data_ptr()), C.c_void_p(d_desc.data_ptr()),
+                                              None if d_uright is None else C.c_void_p(d_uright.data_ptr()), int(n), C.byref(b), len(sf), _p(sf)))
+        self.N = int(n)
+        self.scaleFactors = sf
+        self.imageBounds = tuple(float(np.float32(v)) for v in imageBounds)
+        self.mappoints = np.full(self.N, -1, np.int32)
+        self.keypointsUn = None; self.descriptors = None; self.uright = None
 
     def grid(self):
         """(cell_start[64*48+1], items): grid_[cx][cy] is items[cell_start[cx*48+cy] : cell_start[cx*48+cy+1]]."""

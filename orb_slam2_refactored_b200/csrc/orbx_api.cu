@@ -1137,6 +1137,23 @@ orbx_status orbx_undistort_keypoints(int device, const orbx_keypoint* kps, int n
 	return ORBX_OK;
 }
 
+orbx_status orbx_undistort_keypoints_device(const orbx_keypoint* d_kps, int n, const orbx_camera* camera, const float* dist, int ndist,
+                                            orbx_keypoint* d_kps_un, void* stream)
+{
+	if (!d_kps || !d_kps_un || !camera || n < 0 || ndist < 0 || ndist > 14 || (ndist > 0 && !dist)) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (n == 0) return ORBX_OK;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (ndist == 0 || dist[0] == 0.f)            // src/System.cc:155-159: dst = src
+	{
+		if (d_kps_un != d_kps) CU(cudaMemcpyAsync(d_kps_un, d_kps, sizeof(orbx_keypoint) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+		return ORBX_OK;
+	}
+	const float cam4[4] = { camera->fx, camera->fy, camera->cx, camera->cy };
+	orbx_launch_undistort(d_kps, d_kps_un, n, cam4, dist, ndist, st);
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
 orbx_status orbx_stereo_from_rgbd(int device, const orbx_keypoint* kps, const orbx_keypoint* kps_un, int n, const float* depth_map,
                                   int width, int height, size_t pitch, const orbx_camera* camera, float* uright, float* depth)
 {

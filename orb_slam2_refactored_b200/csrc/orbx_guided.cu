@@ -965,6 +965,12 @@ orbx_status assign_frame(orbx_frame_s* f, const orbx_frame_view* v)
 	return ORBX_OK;
 }
 
+__global__ void k_fill_float(float* p, int n, float v)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+
 orbx_status check_view(const orbx_frame_view* v)
 {
 	if (!v) return orbx_fail(ORBX_ERR_INVALID, "null argument");
@@ -1023,6 +1029,36 @@ orbx_status orbx_frame_assign(orbx_frame f, const orbx_frame_view* v)
 	if (!f) return orbx_fail(ORBX_ERR_INVALID, "null handle");
 	if (orbx_status s = check_view(v)) return s;
 	return assign_frame(f, v);
+}
+
+orbx_status orbx_frame_assign_device(orbx_frame f, const orbx_keypoint* d_kps_un, const uint8_t* d_desc, const float* d_uright, int n,
+                                     const orbx_bounds* bounds, int nlevels, const float* scale_factors)
+{
+	if (!f || !bounds || !scale_factors || n < 0 || (n > 0 && (!d_kps_un || !d_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (n >= (1 << E_IDX_BITS)) return orbx_fail(ORBX_ERR_INVALID, "more than 524287 keypoints in a frame");
+	if (nlevels < 1 || nlevels > 16) return orbx_fail(ORBX_ERR_INVALID, "nlevels must be in [1, 16]");
+	if (!(bounds->maxx > bounds->minx) || !(bounds->maxy > bounds->miny))
+		return orbx_fail(ORBX_ERR_INVALID, "empty image bounds (the reference divides by zero, src/Frame.cc:73-74)");
+	GCU(cudaSetDevice(f->device));
+	f->n = n; f->nlevels = nlevels; f->b = *bounds;
+	f->invW = GRID_COLS / (bounds->maxx - bounds->minx);
+	f->invH = GRID_ROWS / (bounds->maxy - bounds->miny);
+	for (int i = 0; i < 16; i++) f->sf[i] = i < nlevels ? scale_factors[i] : 0.f;
+	const size_t cap = (size_t)std::max(n, 1);
+	GCU(f->kps.ensure(cap)); GCU(f->desc.ensure(cap * 32)); GCU(f->uright.ensure(cap));
+	GCU(f->cell_start.ensure(GRID_CELLS + 1)); GCU(f->cell_of.ensure(cap)); GCU(f->rec.ensure(cap));
+	if (n > 0)
+	{
+		// the frame keeps its own copy: the extractor's output buffers are overwritten by the next Extract
+		GCU(cudaMemcpyAsync(f->kps.p, d_kps_un, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyDeviceToDevice, f->st));
+		GCU(cudaMemcpyAsync(f->desc.p, d_desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, f->st));
+		if (d_uright) GCU(cudaMemcpyAsync(f->uright.p, d_uright, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, f->st));
+		else k_fill_float<<<(n + 255) / 256, 256, 0, f->st>>>(f->uright.p, n, -1.f);
+	}
+	k_grid_build<<<1, G_THREADS, 0, f->st>>>(f->kps.p, f->n, f->b, f->invW, f->invH, f->cell_start.p, f->rec.p, f->cell_of.p);
+	GCU(cudaGetLastError());
+	GCU(cudaStreamSynchronize(f->st));
+	return ORBX_OK;
 }
 
 orbx_status orbx_frame_destroy(orbx_frame f)

@@ -109,3 +109,40 @@ def test_contract_errors(orbx):
     pts['flags'][0] = 1
     with pytest.raises(orbx.OrbxError):
         orbx.ORBmatcher(0.8).SearchByProjection(f, pts, desc, 3.0)
+
+
+def test_resident_chain_extract_undistort_frame_search(orbx, oracle_port):
+    """Extract -> UndistortKeyPoints -> Frame (grid) -> SearchByProjection with keypoints and descriptors staying on the GPU
+    (orbx_extract_batch_device, orbx_undistort_keypoints_device, orbx_frame_assign_device): same frame.mappoints as the oracle fed with
+    host copies of the same data."""
+    import ctypes as C
+    import torch
+    from test_oracle_golden import UNDISTORT_CASES
+    cam4, dist = UNDISTORT_CASES['tum1']
+    cam = cam4 + (40.0, 40.0 / cam4[0])
+    img = synth.image(77, 640, 480)
+    ex = orbx.ORBextractor(nfeatures=1000)
+    d_img = torch.from_numpy(img[None]).cuda()
+    d_kps, d_desc, d_n = ex.extract_batch_device(d_img)
+    ex.synchronize()
+    n = int(d_n[0].item())
+    d_un = torch.empty_like(d_kps[0])
+    dcoef = np.array(dist, np.float32)
+    orbx._check(orbx.lib().orbx_undistort_keypoints_device(C.c_void_p(d_kps[0].data_ptr()), n, C.byref(orbx._Camera(*cam)), dcoef.ctypes.data, len(dcoef),
+                                                           C.c_void_p(d_un.data_ptr()), None))
+    torch.cuda.synchronize()
+    sf = ex.GetScaleFactors()
+    bounds = (-12.5, 655.25, -9.0, 491.5)                       # an undistorted image's bounds (src/System.cc:178-195)
+    seedfr = synth.frame(0, n=4)
+    f = orbx.Frame(seedfr['kps_un'], seedfr['desc'], seedfr['scale_factors'], seedfr['bounds'])
+    f.assign_device(d_un, d_desc[0], n, sf, bounds)
+    # host copies of the same data for the oracle
+    kps_un = d_un[:n].cpu().numpy().view(orbx.KP_DTYPE).reshape(-1)
+    kps_h, desc_h = ex.Extract(img)
+    assert kps_un.tobytes() == oracle_port.undistort_keypoints(kps_h, cam, dist).tobytes()
+    fr = dict(kps_un=kps_un, desc=d_desc[0, :n].cpu().numpy(), uright=None, bounds=bounds, nlevels=len(sf), scale_factors=sf)
+    assert np.array_equal(fr['desc'], desc_h)
+    pts, pdesc = synth.local_map_points(5, fr, npts=900)
+    got = orbx.ORBmatcher(0.8).SearchByProjection(f, pts, pdesc, 3.0)
+    want, wmp = oracle_port.search_local_map(fr, np.full(n, -1, np.int32), pts, pdesc, 3.0, 0.8)
+    assert got == want and np.array_equal(f.mappoints, wmp) and want > 200
