@@ -285,6 +285,14 @@ typedef struct orbx_keyframe_point { float xw[3]; float min_distance, max_distan
 orbx_status orbx_search_by_projection_keyframe(orbx_frame f, const orbx_camera* camera, const orbx_pose* pose, float log_scale_factor,
                                               int32_t* frame_mp, const orbx_keyframe_point* pts, const uint8_t* pt_desc, int npts, float th,
                                               int orb_dist, int check_orientation, int* nmatches);
+/* ORBmatcher::SearchByProjection(const KeyFrame* keyframe, const Sim3& Scw, const std::vector<MapPoint*>& mappoints,
+ * std::vector<MapPoint*>& matched, int th) — src/ORBmatcher.cc:518-612 (loop closing). `f` holds the key frame; matched (f->n entries,
+ * in/out): -1 = null, -2 = a map point found before the call, >= 0 = index of the point stored by this call. flags bit 0 of a point =
+ * !isBad() && not already in `matched` (:536-537). Host geometry as above (incl. the 60-degree viewing test), device window search. */
+typedef struct orbx_sim3 { float R[9]; float t[3]; float s; } orbx_sim3;                    /* include/Sim3.h */
+typedef struct orbx_sim3_point { float xw[3]; float normal[3]; float min_distance, max_distance; int32_t flags; } orbx_sim3_point;
+orbx_status orbx_search_by_projection_sim3(orbx_frame f, const orbx_camera* camera, const orbx_sim3* Scw, float log_scale_factor, int32_t* matched,
+                                          const orbx_sim3_point* pts, const uint8_t* pt_desc, int npts, int th, int* nmatches);
 /* The window search underneath it, for callers that evaluate the geometry themselves (the C++ mirror does, with the reference's own
  * MapPoint::PredictScale and camera classes): window i is centred on (u, v) with half-size radius and admits the octaves
  * [min_level, max_level] with GetFeaturesInArea's level semantics; flags bit 0 = search this point; angle = the orientation compared

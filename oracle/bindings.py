@@ -22,6 +22,7 @@ assert KP_DTYPE.itemsize == 28 and CAND_DTYPE.itemsize == 12
 TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
                               ('flags', '<i4')])
 LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
+SIM3_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('normal', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('flags', '<i4')])
 KF_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('angle', '<f4'), ('flags', '<i4')])
 assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24 and KF_POINT_DTYPE.itemsize == 28
 
@@ -37,6 +38,10 @@ class FrameView(C.Structure):
 
 class FeatureVector(C.Structure):
     _fields_ = [('nnodes', C.c_int32), ('node_ids', C.c_void_p), ('start', C.c_void_p), ('indices', C.c_void_p)]
+
+
+class Sim3(C.Structure):
+    _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3), ('s', C.c_float)]
 
 
 class Pose(C.Structure):
@@ -111,6 +116,8 @@ class Oracle:
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int])
         f('search_keyframe_projection', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int])
+        f('search_sim3_projection', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int])
         f('search_by_bow', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
                                      C.c_void_p, C.c_float, C.c_int, C.c_void_p])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
@@ -330,6 +337,20 @@ class Oracle:
         n = self._search_keyframe_projection(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(P), float(np.float32(log_scale_factor)),
                                              _p(mp), _p(pts), _p(pt_desc), len(pts), th, int(orb_dist), int(check_orientation))
         return n, mp
+
+    def search_sim3_projection(self, keyframe, cam, sim3, log_scale_factor, matched, pts, pt_desc, th=10):
+        """SearchByProjection(keyframe, Scw, mappoints, matched, th) (loop closing). sim3 = (R 3x3, t 3, s). Returns (nmatches, matched)."""
+        v, keep = self._frame_view(keyframe)
+        m = np.array(matched, np.int32)
+        pts = np.ascontiguousarray(pts).view(SIM3_POINT_DTYPE)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        S = Sim3()
+        S.R[:] = [float(x) for x in np.asarray(sim3[0], np.float32).reshape(9)]
+        S.t[:] = [float(x) for x in np.asarray(sim3[1], np.float32).reshape(3)]
+        S.s = float(np.float32(sim3[2]))
+        n = self._search_sim3_projection(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(S), float(np.float32(log_scale_factor)), _p(m),
+                                         _p(pts), _p(pt_desc), len(pts), int(th))
+        return n, m
 
     def search_for_initialization(self, f1, f2, prev_matched, window=100, nnratio=0.9, check_orientation=True):
         v1, k1 = self._frame_view(f1)

@@ -118,6 +118,14 @@ template <class T, int M, int N> inline Matx<T, M, N> operator-(const Matx<T, M,
 	for (int i = 0; i < M * N; i++) r.val[i] = a.val[i] * -1;
 	return r;
 }
+// scalar products: Matx(a, alpha, Matx_ScaleOp): val[i] = saturate_cast<T>(a.val[i] * alpha)
+template <class T, int M, int N> inline Matx<T, M, N> operator*(const Matx<T, M, N>& a, float alpha)
+{
+	Matx<T, M, N> r;
+	for (int i = 0; i < M * N; i++) r.val[i] = (T)(a.val[i] * alpha);
+	return r;
+}
+template <class T, int M, int N> inline Matx<T, M, N> operator*(float alpha, const Matx<T, M, N>& a) { return a * alpha; }
 typedef Matx<float, 3, 1> Matx31f;
 typedef Matx<float, 3, 3> Matx33f;
 // cv::norm(Matx) = std::sqrt(normL2Sqr<_Tp, double>(val, m*n)): squares accumulated in double (matx.hpp, base.hpp)

@@ -426,6 +426,61 @@ int orc_search_keyframe_projection(const oracle_frame_view* f, const oracle_came
 	return kept;
 }
 
+// SearchByProjection(keyframe, Scw, mappoints, matched, th) (:518-612, loop closing): geometry through the similarity transform in the
+// reference's operation order, then the same window search with octaves [predictedScale - 1, predictedScale] (:589-591).
+int orc_search_sim3_projection(const oracle_frame_view* f, const oracle_camera* cam, const oracle_sim3* S, float log_scale_factor, int32_t* matched,
+                               const oracle_sim3_point* pts, const uint8_t* pt_desc, int npts, int th)
+{
+	const Grid g = make_grid(f);
+	const float invs = 1.f / S->s;                 // Sim3::Invs
+	float t[3], Ow[3];
+	for (int i = 0; i < 3; i++) t[i] = S->t[i] * invs;   // pose(Scw.R(), Scw.Invs() * Scw.t()) (:523)
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0;
+		for (int k = 0; k < 3; k++) s += (S->R[k * 3 + i] * -1) * t[k];
+		Ow[i] = s;                                 // pose.Invt() (:525)
+	}
+	std::vector<Probe> probes((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		Probe& p = probes[i];
+		p.active = false;
+		p.obs = true;
+		if (!(pts[i].flags & 1)) continue;         // :536-537
+		float xc[3];
+		for (int r = 0; r < 3; r++)
+		{
+			float s = 0;
+			for (int k = 0; k < 3; k++) s += S->R[r * 3 + k] * pts[i].xw[k];
+			xc[r] = s + t[r];
+		}
+		if (xc[2] < 0.f) continue;                 // :546-547
+		const float invZ = 1.f / xc[2];
+		p.u = invZ * cam->fx * xc[0] + cam->cx;
+		p.v = invZ * cam->fy * xc[1] + cam->cy;
+		p.ur = NAN;
+		if (!(p.u >= f->bounds.minx && p.u < f->bounds.maxx && p.v >= f->bounds.miny && p.v < f->bounds.maxy)) continue;   // :555-556
+		float PO[3];
+		double ss = 0;
+		for (int k = 0; k < 3; k++) { PO[k] = pts[i].xw[k] - Ow[k]; ss += (double)PO[k] * (double)PO[k]; }
+		const float dist = (float)std::sqrt(ss);
+		const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;
+		if (dist < minDistance || dist > maxDistance) continue;                                            // :563-564
+		float dot = 0;                             // Matx::dot accumulates in the element type
+		for (int k = 0; k < 3; k++) dot += PO[k] * pts[i].normal[k];
+		if (dot < 0.5 * dist) continue;            // :568-569, compared in double
+		const float ratio = pts[i].max_distance / dist;
+		const int scale = (int)std::ceil(std::log((double)ratio) / log_scale_factor);
+		const int ps = std::max(0, std::min(scale, f->nlevels - 1));
+		p.radius = th * f->scale_factors[ps];      // :574
+		p.minLevel = ps - 1; p.maxLevel = ps;      // :590-591
+		p.active = true;
+	}
+	std::vector<int> choice;
+	return run_rounds(g, f, probes, pt_desc, matched, choice, [&](const Pick& k) { return k.idx >= 0 && k.best <= TH_LOW; }, true);
+}
+
 // SearchByBoW (:452-516 KeyFrame vs Frame when valid2 == NULL, :696-766 KeyFrame vs KeyFrame otherwise). FeatureVectorIterator
 // (:406-450) walks the nodes both feature vectors share, in ascending node id: a merge join of the two sorted id arrays.
 int orc_search_by_bow(const oracle_frame_view* f1, const oracle_feature_vector* fv1, const uint8_t* valid1, const oracle_frame_view* f2,

@@ -139,6 +139,13 @@ typedef struct oracle_kf_point { float xw[3]; float min_distance, max_distance; 
 int ORACLE_FN(search_keyframe_projection)(const oracle_frame_view* frame, const oracle_camera* cam, const oracle_pose* pose, float log_scale_factor,
                                           int32_t* frame_mp, const oracle_kf_point* pts, const uint8_t* pt_desc, int npts, float th, int orb_dist,
                                           int check_orientation);
+// one candidate map point of SearchByProjection(keyframe, Scw, mappoints, matched, th) (src/ORBmatcher.cc:518-612, loop closing): world
+// position, viewing normal (GetNormal), minDistance_ / maxDistance_; flags bit0 = !isBad() && not already in `matched`
+typedef struct oracle_sim3_point { float xw[3]; float normal[3]; float min_distance, max_distance; int32_t flags; } oracle_sim3_point;
+typedef struct oracle_sim3 { float R[9]; float t[3]; float s; } oracle_sim3;
+// matched (kf->n entries, in/out): -1 = null, -2 = some map point found before the call, >= 0 = index of the point stored by this call
+int ORACLE_FN(search_sim3_projection)(const oracle_frame_view* kf, const oracle_camera* cam, const oracle_sim3* Scw, float log_scale_factor,
+                                      int32_t* matched, const oracle_sim3_point* pts, const uint8_t* pt_desc, int npts, int th);
 // DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h) as CSR: node ids ascending, the feature indices of node k are
 // indices[start[k] .. start[k+1])
 typedef struct oracle_feature_vector { int32_t nnodes; const uint32_t* node_ids; const int32_t* start; const uint32_t* indices; } oracle_feature_vector;

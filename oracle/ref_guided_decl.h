@@ -6,6 +6,7 @@
 //   src/ORBmatcher.cc:37-58, 249-309           (constants, CheckOrientation)
 //   src/ORBmatcher.cc:315-382                  SearchByProjection(Frame&, mappoints, th)       — local-map tracking
 //   src/ORBmatcher.cc:406-516, 696-766         FeatureVectorIterator, SearchByBoW x2            — reference keyframe / relocalisation / loop
+//   src/ORBmatcher.cc:518-612                  SearchByProjection(keyframe, Scw, points, matched) — loop closing
 //   src/ORBmatcher.cc:614-694                  SearchForInitialization                          — monocular initialisation
 //   src/ORBmatcher.cc:1279-1362                SearchByProjection(currFrame, lastFrame, th, m)  — motion-model tracking
 //   src/ORBmatcher.cc:1364-1447                SearchByProjection(frame, keyframe, found, th, d) — relocalisation
@@ -43,6 +44,9 @@ struct MapPoint
 	float GetMinDistanceInvariance() const;
 	float GetMaxDistanceInvariance() const;
 	int PredictScale(float dist, const Frame* frame) const;
+	int PredictScale(float dist, const KeyFrame* keyframe) const;   // src/MapPoint.cc:394-403
+	Vec3D normal;
+	Vec3D GetNormal() const { return normal; }                      // src/MapPoint.cc:97-101
 
 	Point3D GetWorldPos() const { return worldPos; }
 	int Observations() const { return nobs; }
@@ -50,7 +54,6 @@ struct MapPoint
 	cv::Mat GetDescriptor() const { return descriptor; }
 };
 
-class Sim3;
 
 struct Frame
 {
@@ -86,6 +89,13 @@ struct KeyFrame
 	DBoW2::FeatureVector featureVector;
 	std::vector<MapPoint*> mappoints;
 	std::vector<MapPoint*> GetMapPointMatches() const { return mappoints; }
+	// what the Sim3 projection search reads (include/KeyFrame.h:83-87, 134, 154-157; src/KeyFrame.cc:491-499)
+	CameraParams camera;
+	ScalePyramidInfo pyramid;
+	ImageBounds imageBounds;
+	FeaturesGrid grid;
+	std::vector<size_t> GetFeaturesInArea(float x, float y, float r) const { return grid.GetFeaturesInArea(x, y, r); }
+	bool IsInImage(float x, float y) const { return imageBounds.Contains(x, y); }
 };
 
 // include/ORBmatcher.h:47-104, the members compiled here
@@ -97,6 +107,7 @@ public:
 	int SearchByProjection(Frame& frame, const std::vector<MapPoint*>& mappoints, float th = 3);
 	int SearchByProjection(Frame& currFrame, const Frame& lastFrame, float th, bool monocular);
 	int SearchByProjection(Frame& frame, KeyFrame* keyframe, const std::set<MapPoint*>& alreadyFound, float th, int ORBdist);
+	int SearchByProjection(const KeyFrame* keyframe, const Sim3& Scw, const std::vector<MapPoint*>& mappoints, std::vector<MapPoint*>& matched, int th);
 	int SearchByBoW(KeyFrame* keyframe, Frame& frame, std::vector<MapPoint*>& matches);
 	int SearchByBoW(KeyFrame* keyframe1, KeyFrame* keyframe2, std::vector<MapPoint*>& matches12);
 	int SearchForInitialization(Frame& frame1, Frame& frame2, std::vector<cv::Point2f>& prevMatched, std::vector<int>& matches12,

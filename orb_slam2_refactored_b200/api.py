@@ -54,6 +54,10 @@ class _FeatureVector(C.Structure):
     _fields_ = [('nnodes', C.c_int32), ('node_ids', C.c_void_p), ('start', C.c_void_p), ('indices', C.c_void_p)]
 
 
+class _Sim3(C.Structure):
+    _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3), ('s', C.c_float)]
+
+
 class _Pose(C.Structure):
     _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3)]
 
@@ -61,6 +65,7 @@ class _Pose(C.Structure):
 TRACK_POINT_DTYPE = np.dtype([('proj_x', '<f4'), ('proj_y', '<f4'), ('proj_xr', '<f4'), ('view_cos', '<f4'), ('scale_level', '<i4'),
                               ('flags', '<i4')])
 LAST_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('octave', '<i4'), ('angle', '<f4'), ('flags', '<i4')])
+SIM3_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('normal', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('flags', '<i4')])
 KF_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('angle', '<f4'), ('flags', '<i4')])
 assert TRACK_POINT_DTYPE.itemsize == 24 and LAST_POINT_DTYPE.itemsize == 24 and KF_POINT_DTYPE.itemsize == 28
 GRID_COLS, GRID_ROWS = 64, 48   # include/Frame.h:72-73
@@ -131,6 +136,8 @@ _SIGNATURES = {
     'orbx_frame_last_stats': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p]),
     'orbx_search_by_projection_keyframe': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                                      C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    'orbx_search_by_projection_sim3': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'orbx_search_by_bow': (C.c_int, [C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_float,
                                      C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
@@ -529,6 +536,21 @@ class ORBmatcher:
         _check(lib().orbx_search_by_projection_keyframe(frame._h, C.byref(cam), C.byref(P), float(np.float32(logScaleFactor)), _p(frame.mappoints),
                                                         _p(pts), _p(desc), len(pts), th, int(ORBdist), int(bool(self.checkOrientation_)),
                                                         C.byref(n)))
+        return n.value
+
+    def SearchByProjectionSim3(self, keyframe, camera, Scw, logScaleFactor, mappoints, descriptors, th):
+        """SearchByProjection(keyframe, Scw, mappoints, matched, th) — src/ORBmatcher.cc:518-612 (loop closing). Scw = (R 3x3, t 3, s);
+        mappoints: SIM3_POINT_DTYPE records. keyframe.mappoints plays `matched` (in/out). Returns nmatches."""
+        pts = np.ascontiguousarray(mappoints).view(SIM3_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        S = _Sim3()
+        S.R[:] = [float(x) for x in np.asarray(Scw[0], np.float32).reshape(9)]
+        S.t[:] = [float(x) for x in np.asarray(Scw[1], np.float32).reshape(3)]
+        S.s = float(np.float32(Scw[2]))
+        n = C.c_int()
+        cam = _Camera(*[float(c) for c in camera])
+        _check(lib().orbx_search_by_projection_sim3(keyframe._h, C.byref(cam), C.byref(S), float(np.float32(logScaleFactor)), _p(keyframe.mappoints),
+                                                    _p(pts), _p(desc), len(pts), int(th), C.byref(n)))
         return n.value
 
     def SearchByBoW(self, keyframe, featureVector1, valid1, frame, featureVector2, valid2=None):

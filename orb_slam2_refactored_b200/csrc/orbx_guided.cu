@@ -1284,6 +1284,64 @@ orbx_status orbx_search_by_projection_keyframe(orbx_frame f, const orbx_camera* 
 	return finish_windows(f, A, S, frame_mp, pt_desc, npts, orb_dist, check_orientation, nmatches);
 }
 
+orbx_status orbx_search_by_projection_sim3(orbx_frame f, const orbx_camera* cam, const orbx_sim3* Scw, float log_scale_factor, int32_t* matched,
+                                          const orbx_sim3_point* pts, const uint8_t* pt_desc, int npts, int th, int* nmatches)
+{
+	if (!f || !cam || !Scw || !matched || npts < 0 || (npts > 0 && (!pts || !pt_desc))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (!(log_scale_factor > 0.f)) return orbx_fail(ORBX_ERR_INVALID, "logScaleFactor must be positive");
+	for (int c = 0; c < f->n; c++)
+		if (matched[c] < -3 || matched[c] >= npts) return orbx_fail(ORBX_ERR_INVALID, "matched entry is not -3..-1 or a point index");
+	GuidedArgs A;
+	Staging S;
+	if (orbx_status s = prepare(f, npts, (size_t)npts * sizeof(GuidedWindow), (size_t)npts * 32, (size_t)f->n * sizeof(int), (size_t)f->n, 0, A, S)) return s;
+	// The geometry of src/ORBmatcher.cc:521-574 per map point in the reference's operation order: pose(Scw.R(), Scw.Invs() * Scw.t()),
+	// cv::Matx products accumulating from 0, cv::norm in double, Matx::dot in float, PredictScale's log in double.
+	GuidedWindow* win = reinterpret_cast<GuidedWindow*>(f->h_in + S.in_pts);
+	const float invs = 1.f / Scw->s;
+	float t[3], Ow[3];
+	for (int i = 0; i < 3; i++) t[i] = Scw->t[i] * invs;
+	for (int i = 0; i < 3; i++)
+	{
+		float s = 0.f;
+		for (int k = 0; k < 3; k++) s += (Scw->R[k * 3 + i] * -1) * t[k];
+		Ow[i] = s;
+	}
+	for (int i = 0; i < npts; i++)
+	{
+		GuidedWindow& w = win[i];
+		w.u = w.v = w.radius = w.angle = 0.f; w.levels = 0; w.flags = 0;
+		if (!(pts[i].flags & 1)) continue;         // :536-537
+		float xc[3];
+		for (int r = 0; r < 3; r++)
+		{
+			float s = 0.f;
+			for (int k = 0; k < 3; k++) s += Scw->R[r * 3 + k] * pts[i].xw[k];
+			xc[r] = s + t[r];
+		}
+		if (xc[2] < 0.f) continue;                 // :546-547
+		const float invZ = 1.f / xc[2];
+		const float u = invZ * cam->fx * xc[0] + cam->cx, v = invZ * cam->fy * xc[1] + cam->cy;
+		if (!(u >= f->b.minx && u < f->b.maxx && v >= f->b.miny && v < f->b.maxy)) continue;   // IsInImage, :555-556
+		float PO[3];
+		double ss = 0;
+		for (int k = 0; k < 3; k++) { PO[k] = pts[i].xw[k] - Ow[k]; ss += (double)PO[k] * (double)PO[k]; }
+		const float dist = (float)std::sqrt(ss);
+		const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;
+		if (dist < minDistance || dist > maxDistance) continue;                                // :563-564
+		float dot = 0.f;
+		for (int k = 0; k < 3; k++) dot += PO[k] * pts[i].normal[k];
+		if (dot < 0.5 * dist) continue;            // viewing angle below 60 degrees, :568-569 (compared in double)
+		const float ratio = pts[i].max_distance / dist;                                        // PredictScale, src/MapPoint.cc:394-403
+		const int scale = (int)std::ceil(std::log((double)ratio) / log_scale_factor);
+		const int ps = std::max(0, std::min(scale, f->nlevels - 1));
+		w.u = u; w.v = v;
+		w.radius = th * f->sf[ps];                 // :574
+		w.levels = ((ps - 1) & 0xffff) | (ps << 16);   // octave in [predictedScale - 1, predictedScale], :590-591
+		w.flags = 1;
+	}
+	return finish_windows(f, A, S, matched, pt_desc, npts, TH_LOW, 0, nmatches);   // bestDist <= TH_LOW, :603
+}
+
 orbx_status orbx_search_windows(orbx_frame f, int32_t* frame_mp, const orbx_window* windows, const uint8_t* pt_desc, int npts, int max_dist,
                                 int check_orientation, int* nmatches)
 {

@@ -319,3 +319,27 @@ def keyframe_points(seed, fr, cam, npts=1200, dup=0.2, max_flips=70):
     pts['angle'] = lp['angle']
     pts['flags'] = (r.rand(npts) < 0.85).astype(np.int32)
     return (R, t), pts, desc
+
+
+SIM3_POINT_DTYPE = np.dtype([('xw', '<f4', (3,)), ('normal', '<f4', (3,)), ('min_distance', '<f4'), ('max_distance', '<f4'), ('flags', '<i4')])
+
+
+def sim3_points(seed, fr, cam, npts=1200, scale=1.07):
+    """Candidate map points for the loop-closing search SearchByProjection(keyframe, Scw, mappoints, matched, th): the points of
+    keyframe_points() expressed in a world that is `scale` times larger, so that Scw = (R, scale * t, scale) maps them onto the key
+    frame's keypoints; normals point roughly at the camera (some beyond 60 degrees). Returns (sim3, pts, desc)."""
+    r = np.random.RandomState(seed + 6)
+    (R, t), kp, desc = keyframe_points(seed, fr, cam, npts=npts)
+    s = np.float32(scale)
+    pts = np.zeros(npts, SIM3_POINT_DTYPE)
+    pts['xw'] = kp['xw']
+    pts['min_distance'], pts['max_distance'] = kp['min_distance'], kp['max_distance']
+    pts['flags'] = kp['flags']
+    Ow = -(R.astype(np.float64).T @ t.astype(np.float64))
+    to_cam = pts['xw'].astype(np.float64) - Ow
+    nrm = to_cam / np.linalg.norm(to_cam, axis=1, keepdims=True)
+    tilt = r.randn(npts, 3) * 0.5
+    tilt[r.rand(npts) < 0.15] *= 6.0
+    nrm = nrm + tilt
+    pts['normal'] = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    return (R, (t * s).astype(np.float32), s), pts, desc

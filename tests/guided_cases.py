@@ -42,6 +42,9 @@ def cases(small=False):
         kpose, kpts, kdesc = synth.keyframe_points(seed, fr, cam, npts=700 if small else 1200)
         out.append((f'reloc{seed}', 'reloc', dict(frame=fr, cam=cam, pose=kpose, mp=mp0, pts=kpts, desc=kdesc, th=10.0 if seed % 2 else 3.0,
                                                   orb_dist=100 if seed % 2 else 64, check=seed != 1)))
+        S, spts, sdesc = synth.sim3_points(seed, fr, cam, npts=700 if small else 1200)
+        m0 = np.where(mp0 == -1, -1, -2).astype(np.int32)
+        out.append((f'sim3_{seed}', 'sim3', dict(frame=fr, cam=cam, sim3=S, matched=m0, pts=spts, desc=sdesc, th=10 if seed % 2 else 4)))
         f1, fv1, va1, f2, fv2, va2 = synth.bow_pair(seed, n=800 if small else 1500)
         out.append((f'bow{seed}_kf_frame', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=None, nnratio=0.7, check=seed != 5)))
         out.append((f'bow{seed}_kf_kf', 'bow', dict(f1=f1, fv1=fv1, valid1=va1, f2=f2, fv2=fv2, valid2=va2, nnratio=0.8 if seed % 2 else 0.75,
@@ -100,6 +103,9 @@ def run_oracle(o, kind, c):
         n, mp = o.search_keyframe_projection(c['frame'], c['cam'], c['pose'], synth.log_scale_factor(), c['mp'], c['pts'], c['desc'], c['th'],
                                              c['orb_dist'], c['check'])
         return dict(n=np.int32(n), mp=mp)
+    if kind == 'sim3':
+        n, m = o.search_sim3_projection(c['frame'], c['cam'], c['sim3'], synth.log_scale_factor(), c['matched'], c['pts'], c['desc'], c['th'])
+        return dict(n=np.int32(n), matched=m)
     if kind == 'bow':
         n, m2 = o.search_by_bow(c['f1'], c['fv1'], c['valid1'], c['f2'], c['fv2'], c['valid2'], c['nnratio'], c['check'])
         return dict(n=np.int32(n), m2=m2)
@@ -134,6 +140,11 @@ def run_product(api, kind, c, device=0):
         n = api.ORBmatcher(0.9, c['check'], device).SearchByProjectionKeyFrame(f, c['cam'], c['pose'], synth.log_scale_factor(), c['pts'], c['desc'],
                                                                                c['th'], c['orb_dist'])
         return dict(n=np.int32(n), mp=f.mappoints.copy(), _rounds=f.last_rounds())
+    if kind == 'sim3':
+        f = make_frame(api, c['frame'], device)
+        f.mappoints[:] = c['matched']
+        n = api.ORBmatcher(0.75, True, device).SearchByProjectionSim3(f, c['cam'], c['sim3'], synth.log_scale_factor(), c['pts'], c['desc'], c['th'])
+        return dict(n=np.int32(n), matched=f.mappoints.copy(), _rounds=f.last_rounds())
     f1, f2 = make_frame(api, c['f1'], device), make_frame(api, c['f2'], device)
     if kind == 'bow':
         n, m2 = api.ORBmatcher(c['nnratio'], c['check'], device).SearchByBoW(f1, c['fv1'], c['valid1'], f2, c['fv2'], c['valid2'])

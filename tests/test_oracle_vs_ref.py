@@ -141,5 +141,5 @@ def test_guided_matchers_equal(oracle_port, oracle_ref):
             max_rounds = max(max_rounds, stat(0))
         if kind == 'init':
             revoked += stat(1)
-    assert kinds == {'grid', 'local', 'last', 'init', 'bow', 'reloc'}
+    assert kinds == {'grid', 'local', 'last', 'init', 'bow', 'reloc', 'sim3'}
     assert max_rounds >= 12 and revoked > 50, (max_rounds, revoked)
