@@ -5,6 +5,7 @@
 #include "orbx_internal.cuh"
 
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <stdio.h>
 
@@ -303,7 +304,7 @@ __device__ __forceinline__ int arc_score_bound(const uint8_t* __restrict__ c)
 //   C. strict 8-neighbour local maxima among them with S > iniTh. If the cell has none (the retry of :526-530), the second
 //      bitmap is evaluated too and the test repeats with minTh over both;
 //   D. ordered emit from the survivor bitmap: DetectFAST's cell-major / row-major push_back order without global atomics.
-__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps)
+__global__ void __launch_bounds__(FT_THREADS) k_fast_cells_v1(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps)
 {
 	__shared__ __align__(128) uint8_t tile[FT_TH * FT_TS];
 	__shared__ __align__(8) uint64_t tma_bar;
@@ -467,6 +468,251 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const OrbxPlanDev P, 
 			out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
 		}
 	if (tid == 0)
+		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
+}
+
+// ---- warp-per-cell FAST (the default). The CTA-per-cell kernel above spends 2/3 of its instructions outside the bound pass: four
+// warps each run the scans, list building, NMS and emit of one cell, separated by block barriers (ncu: barrier is the top stall).
+// Here ONE warp owns a cell end to end, so those phases cost a quarter and need only __syncwarp, and the bound pass works on
+// 4 horizontally adjacent pixels per lane: aligned 32-bit words of the tile are turned into packed u16x2 operands with PRMT
+// (a pixel sits in the HIGH byte of a 16-bit lane, the low byte is a neighbour pixel and never decides a min/max), so the 8 ring
+// loads + 8 packs + 7 min/max per pixel of the byte-wise version become 11 word loads + 13 PRMT + 24 VIMNMX per FOUR pixels.
+#define FW_WARPS 4
+#define FW_TSW (FT_TS / 4)
+
+struct OrbxFastLayout
+{
+	int score_stride;            // bytes per score row (region width + 2, rounded up to 16)
+	int off_score, off_list, off_bm;
+	int bm_rows;                 // rows per bitmap (max region height)
+	int warp_bytes;              // multiple of 128: every warp's tile is a TMA destination
+};
+
+// Bound pass for the 4 pixels of tile word q[0] (centre row). Returns one byte: bits (0,1,4,5) = U > minTh for pixels 0..3,
+// bits (2,3,6,7) = U > iniTh, where U >= S is the 4-pair upper bound of arc_score_bound(). kini/kmin = (0x8000 - 1 - t) in both
+// halves fold the "+255" of the lane arithmetic and the threshold into one constant: bit 15 of a lane <=> U > t.
+__device__ __forceinline__ uint32_t fast_bound_flags4(const uint32_t* __restrict__ q, const uint32_t kini, const uint32_t kdelta)
+{
+	const uint32_t c0 = q[-1], c1 = q[0], c2 = q[1];
+	const uint32_t p3 = q[3 * FW_TSW], m3 = q[-3 * FW_TSW];
+	const uint32_t pa = q[2 * FW_TSW - 1], pb = q[2 * FW_TSW], pc = q[2 * FW_TSW + 1];
+	const uint32_t ma = q[-2 * FW_TSW - 1], mb = q[-2 * FW_TSW], mc = q[-2 * FW_TSW + 1];
+	uint32_t f[2];
+#pragma unroll
+	for (int par = 0; par < 2; par++)
+	{
+		// par 0: pixels 1 and 3 (operand = bytes s..s+3 of the row, s = ring dx); par 1: pixels 0 and 2 (bytes s-1..s+2)
+		const uint32_t a1 = par == 0 ? p3 : p3 << 8;                                              // ( 0, +3)
+		const uint32_t a2 = par == 0 ? m3 : m3 << 8;                                              // ( 0, -3)
+		const uint32_t b1 = par == 0 ? __byte_perm(pb, pc, 0x5432) : __byte_perm(pb, pc, 0x4321); // (+2, +2)
+		const uint32_t b2 = par == 0 ? __byte_perm(ma, mb, 0x5432) : __byte_perm(ma, mb, 0x4321); // (-2, -2)
+		const uint32_t d1 = par == 0 ? __byte_perm(c1, c2, 0x6543) : __byte_perm(c1, c2, 0x5432); // (+3,  0)
+		const uint32_t d2 = par == 0 ? __byte_perm(c0, c1, 0x4321) : c0;                          // (-3,  0)
+		const uint32_t e1 = par == 0 ? __byte_perm(mb, mc, 0x5432) : __byte_perm(mb, mc, 0x4321); // (+2, -2)
+		const uint32_t e2 = par == 0 ? __byte_perm(pa, pb, 0x5432) : __byte_perm(pa, pb, 0x4321); // (-2, +2)
+		const uint32_t hi = __vminu2(__vimin3_u16x2(__vmaxu2(a1, a2), __vmaxu2(b1, b2), __vmaxu2(d1, d2)), __vmaxu2(e1, e2));   // min_k max(pair): bright side
+		const uint32_t lo = __vmaxu2(__vimax3_u16x2(__vminu2(a1, a2), __vminu2(b1, b2), __vminu2(d1, d2)), __vminu2(e1, e2));   // max_k min(pair): dark side
+		// high bytes -> clean 16-bit lanes (PRMT against a zero register)
+		const uint32_t H = __byte_perm(hi, 0, 0x4341), Lo = __byte_perm(lo, 0, 0x4341);
+		const uint32_t C = par == 0 ? __byte_perm(c1, 0, 0x4341) : __byte_perm(c1, 0, 0x4240);
+		// lanes: (H - c) + K and (c - Lo) + K with K = 0x7fff - t >= 255: no lane ever borrows or carries
+		const uint32_t sb = H + kini - C, sd = C + kini - Lo;
+		f[par] = __vmaxu2(sb, sd);
+	}
+	// bit 15 / 31 of f: U > iniTh; of f + kdelta (kdelta = iniTh - minTh per lane): U > minTh
+	const uint32_t g0 = f[0] + kdelta, g1 = f[1] + kdelta;
+	uint32_t z = f[0] & 0x80008000u;
+	z |= (f[1] >> 1) & 0x40004000u;
+	z |= (g0 >> 2) & 0x20002000u;
+	z |= (g1 >> 3) & 0x10001000u;
+	const uint32_t y = z >> 12;
+	return (y | (y >> 12)) & 0xffu;
+}
+
+// 4 flag bytes (16 pixels) -> 16 consecutive bits; shift 2 selects the iniTh flags, 0 the minTh flags
+__device__ __forceinline__ uint32_t fast_gather16(uint32_t w, int shift)
+{
+	uint32_t x = (w >> shift) & 0x33333333u;
+	x = (x | (x >> 2)) & 0x0f0f0f0fu;
+	x = (x | (x >> 4)) & 0x00ff00ffu;
+	return (x | (x >> 8)) & 0xffffu;
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxFastLayout Y)
+{
+	extern __shared__ __align__(128) uint8_t fw_smem[];
+	__shared__ __align__(8) uint64_t tma_bar[FW_WARPS];
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int cell = blockIdx.x * FW_WARPS + warp, f = blockIdx.y;
+	if (cell >= P.cells_per_frame) return;           // whole warps leave; there is no block barrier below
+	uint8_t* const base = fw_smem + (size_t)warp * Y.warp_bytes;
+	uint8_t* const tile = base;
+	uint8_t* const score = base + Y.off_score;
+	uint16_t* const list = reinterpret_cast<uint16_t*>(base + Y.off_list);
+	uint8_t* const nib = base + Y.off_list;          // flag bytes of the bound pass, dead before the list is built
+	uint32_t* const bm_a = reinterpret_cast<uint32_t*>(base + Y.off_bm);   // [row][2]: 64 bits per region row
+	uint32_t* const bm_b = bm_a + 2 * Y.bm_rows;
+	uint32_t* const bm_sel = bm_b + 2 * Y.bm_rows;
+	const int SS = Y.score_stride;
+
+	const int4 ct = __ldg(P.cell_tab + cell);
+	const int x0 = ct.x & 0xffff, y0 = ct.x >> 16, vw = ct.y & 0xffff, vh = ct.y >> 16, lvl = ct.z, c = ct.w;
+	const OrbxLevel& L = P.lv[lvl];
+	const int rw = vw - 6, rh = vh - 6;
+	const int sh = x0 & 15;                           // see k_fast_cells_v1: the TMA box starts 16-byte aligned
+	if (lane == 0)
+	{
+		mbar_init(&tma_bar[warp], 1);
+		mbar_expect_tx(&tma_bar[warp], (unsigned)(FT_TS * maps.box_h[lvl]));
+		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, &tma_bar[warp]);
+	}
+	for (int i = lane; i < (rh + 2) * (SS / 16); i += 32)
+		reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+	for (int i = lane; i < 2 * rh; i += 32) bm_sel[i] = 0;
+	__syncwarp();
+	mbar_wait(&tma_bar[warp], 0);
+
+	const int tmin = P.min_th, tini = P.ini_th;
+	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
+
+	// ---- A: bound pass, 4 pixels per lane. Groups are the aligned words of a tile row that overlap the region: the first one
+	//      starts `a` pixels left of it. Pixels outside the region produce flags that the row assembly below shifts/masks away.
+	const int a = (sh + 3) & 3, G = (a + rw + 3) >> 2, ngroups = G * rh;
+	{
+		const uint32_t kini = (uint32_t)(0x7fff - tini) * 0x00010001u, kdelta = (uint32_t)(tini - tmin) * 0x00010001u;
+		const uint32_t* __restrict__ q0 = reinterpret_cast<const uint32_t*>(tile) + 3 * FW_TSW + ((sh + 3) >> 2);
+		const uint32_t invG = c_inv20[G];
+		for (int g = lane; g < ngroups; g += 32)
+		{
+			const int ry = (int)(((uint32_t)g * invG) >> 20), cg = g - ry * G;
+			nib[ry * 16 + cg] = (uint8_t)fast_bound_flags4(q0 + ry * FW_TSW + cg, kini, kdelta);
+		}
+	}
+	__syncwarp();
+	// rows -> bitmaps: lane r assembles region rows r and r + 32 (bm_b = U > minTh, a superset of bm_a = U > iniTh)
+	uint32_t wa[4], wb[4];                           // this lane's rows: [row slot][lo, hi]
+	{
+		const uint64_t rowmask = rw >= 64 ? ~0ull : ((1ull << rw) - 1ull);
+#pragma unroll
+		for (int k = 0; k < 2; k++)
+		{
+			const int r = lane + 32 * k;
+			uint64_t va = 0, vb = 0;
+			if (r < rh)
+			{
+				const uint4 n = *reinterpret_cast<const uint4*>(nib + r * 16);
+				va = (uint64_t)(fast_gather16(n.x, 2) | (fast_gather16(n.y, 2) << 16)) | ((uint64_t)(fast_gather16(n.z, 2) | (fast_gather16(n.w, 2) << 16)) << 32);
+				vb = (uint64_t)(fast_gather16(n.x, 0) | (fast_gather16(n.y, 0) << 16)) | ((uint64_t)(fast_gather16(n.z, 0) | (fast_gather16(n.w, 0) << 16)) << 32);
+				va = (va >> a) & rowmask; vb = (vb >> a) & rowmask;
+			}
+			wa[2 * k] = (uint32_t)va; wa[2 * k + 1] = (uint32_t)(va >> 32);
+			wb[2 * k] = (uint32_t)vb & ~wa[2 * k]; wb[2 * k + 1] = (uint32_t)(vb >> 32) & ~wa[2 * k + 1];   // minTh < U <= iniTh
+		}
+	}
+	__syncwarp();                                    // nib is dead: the list may overwrite it
+
+	// exclusive warp scan of (c0, c1) in "all first rows, then all second rows" order = row-major; returns offsets, total in `total`
+	auto scan2 = [&](int c0, int c1, int& o0, int& o1, int& total) {
+		int i0 = c0, i1 = c1;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const int u0 = __shfl_up_sync(0xffffffffu, i0, d), u1 = __shfl_up_sync(0xffffffffu, i1, d);
+			if (lane >= d) { i0 += u0; i1 += u1; }
+		}
+		const int t0s = __shfl_sync(0xffffffffu, i0, 31), t1s = __shfl_sync(0xffffffffu, i1, 31);
+		o0 = i0 - c0; o1 = t0s + i1 - c1; total = t0s + t1s;
+	};
+	// append the pixels of this lane's row words to the list as ry << 6 | rx; returns how many the warp appended
+	auto expand = [&](const uint32_t* w, int at) {
+		int o0, o1, total;
+		scan2(__popc(w[0]) + __popc(w[1]), __popc(w[2]) + __popc(w[3]), o0, o1, total);
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			uint32_t x = w[k];
+			int pos = at + (k < 2 ? o0 : o1);
+			if (k == 1) pos += __popc(w[0]);
+			if (k == 3) pos += __popc(w[2]);
+			const int tag = ((lane + 32 * (k >> 1)) << 6) | (32 * (k & 1));
+			while (x)
+			{
+				list[pos++] = (uint16_t)(tag + __ffs(x) - 1);
+				x &= x - 1;
+			}
+		}
+		return total;
+	};
+	auto evaluate = [&](int from, int to) {
+		for (int j = from + lane; j < to; j += 32)
+		{
+			const int e = list[j], ry = e >> 6, rx = e & 63;
+			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
+			score[(ry + 1) * SS + rx + 1] = (uint8_t)max(s, 0);
+		}
+	};
+	auto select = [&](int to, int t) {
+		bool found = false;
+		for (int j = lane; j < to; j += 32)
+		{
+			const int e = list[j], ry = e >> 6, rx = e & 63;
+			const uint8_t* sp = score + (ry + 1) * SS + rx + 1;
+			const int s = sp[0];
+			if (s > t)
+			{
+				const int m = max(max(max((int)sp[-SS - 1], (int)sp[-SS]), max((int)sp[-SS + 1], (int)sp[-1])),
+				                  max(max((int)sp[1], (int)sp[SS - 1]), max((int)sp[SS], (int)sp[SS + 1])));
+				if (s > m) { atomicOr(&bm_sel[2 * ry + (rx >> 5)], 1u << (rx & 31)); found = true; }
+			}
+		}
+		return found;
+	};
+
+	// ---- B + C at iniTh; retry at minTh if the cell has no corner (:526-530)
+	const int n1 = expand(wa, 0);
+	__syncwarp();
+	evaluate(0, n1);
+	__syncwarp();
+	if (!__any_sync(0xffffffffu, select(n1, tini)))
+	{
+		const int n2 = expand(wb, n1);
+		__syncwarp();
+		evaluate(n1, n1 + n2);
+		__syncwarp();
+		select(n1 + n2, tmin);
+	}
+	__syncwarp();
+
+	// ---- D: ordered emit (rows ascending, x ascending = cv::FAST's order inside the view)
+	uint32_t ws[4];
+#pragma unroll
+	for (int k = 0; k < 2; k++)
+	{
+		const int r = lane + 32 * k;
+		ws[2 * k] = r < rh ? bm_sel[2 * r] : 0u;
+		ws[2 * k + 1] = r < rh ? bm_sel[2 * r + 1] : 0u;
+	}
+	int o0, o1, total;
+	scan2(__popc(ws[0]) + __popc(ws[1]), __popc(ws[2]) + __popc(ws[3]), o0, o1, total);
+	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		uint32_t x = ws[k];
+		int pos = (k < 2 ? o0 : o1);
+		if (k == 1) pos += __popc(ws[0]);
+		if (k == 3) pos += __popc(ws[2]);
+		const int ry = lane + 32 * (k >> 1);
+		while (x)
+		{
+			const int rx = 32 * (k & 1) + __ffs(x) - 1;
+			x &= x - 1;
+			const int s = score[(ry + 1) * SS + rx + 1];
+			out[pos++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
+		}
+	}
+	if (lane == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
 }
 
@@ -1339,8 +1585,39 @@ int orbx_fast_tile_rows() { return FT_TH; }
 
 void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st)
 {
-	dim3 grid(P.cells_per_frame, P.frames);
-	k_fast_cells<<<grid, FT_THREADS, 0, st>>>(P, maps);
+	static const bool v1 = getenv("ORBX_FAST_V1") != nullptr;   // A/B knob: the CTA-per-cell kernel
+	if (v1)
+	{
+		dim3 grid(P.cells_per_frame, P.frames);
+		k_fast_cells_v1<<<grid, FT_THREADS, 0, st>>>(P, maps);
+		return;
+	}
+	// per-warp shared memory, sized by the largest cell of the plan: tile | score (1 px zero border) | list (aliases the flag bytes) | 3 bitmaps
+	int rows = 0, maxrw = 0, maxrh = 0;
+	for (int s = 0; s < P.nlevels; s++)
+	{
+		rows = std::max(rows, maps.box_h[s]);
+		maxrw = std::max(maxrw, P.lv[s].cellw);
+		maxrh = std::max(maxrh, P.lv[s].cellh);
+	}
+	OrbxFastLayout Y;
+	Y.score_stride = (maxrw + 2 + 15) & ~15;
+	Y.off_score = (rows * FT_TS + 15) & ~15;
+	Y.off_list = Y.off_score + (maxrh + 2) * Y.score_stride;
+	Y.off_bm = (Y.off_list + std::max(maxrw * maxrh * 2, maxrh * 16) + 15) & ~15;
+	Y.bm_rows = maxrh;
+	Y.warp_bytes = (Y.off_bm + 3 * 8 * maxrh + 127) & ~127;
+	const int smem = FW_WARPS * Y.warp_bytes;
+	static int attr_smem[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 64 && attr_smem[dev] < smem)
+	{
+		cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		attr_smem[dev] = smem;
+	}
+	dim3 grid((P.cells_per_frame + FW_WARPS - 1) / FW_WARPS, P.frames);
+	k_fast_cells<<<grid, FW_WARPS * 32, smem, st>>>(P, maps, Y);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }
