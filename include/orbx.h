@@ -308,13 +308,54 @@ typedef struct orbx_feature_vector { int32_t nnodes; const uint32_t* node_ids; c
  * FeatureVectorIterator (:406-450) and CheckOrientation. f1 is the (first) key frame, f2 the frame / second key frame, both resident.
  * valid1 / valid2: per keypoint, map point present && !isBad(). match2 (f2->n entries, out) = the keypoint of f1 matched to keypoint
  * idx2 of f2, or -1: `matches[idx2] = mappoints1[match2[idx2]]` for the first variant, `matches12[match2[idx2]] = mappoints2[idx2]`
- * for the second. The vocabulary transform that produces the feature vectors is not part of this library. */
+ * for the second. The feature vectors come from orbx_bow_transform below (or from DBoW2 on the host). */
 orbx_status orbx_search_by_bow(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* valid1, orbx_frame f2, const orbx_feature_vector* fv2,
                                const uint8_t* valid2, float nnratio, int check_orientation, int32_t* match2, int* nmatches);
 /* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1), the kernel's duration (CUDA events) and
  * the microseconds its phases took (enumeration, -, -, distances, rounds, finalisation, and the part of `rounds` spent staging state into
  * shared memory; %globaltimer). Any pointer may be NULL; phase_us needs room for 7 floats. */
 orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms, float* phase_us);
+
+/* ---- Bag-of-words transform: Frame::ComputeBoW / KeyFrame::ComputeBoW — src/Frame.cc:208-214, src/KeyFrame.cc:66-74,
+ * i.e. ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h). ---------------- */
+typedef struct orbx_vocabulary_s* orbx_vocabulary;
+/* The tree as loadFromTextFile reads it: entry i describes node id i + 1 (node 0 is the root), in file order — a parent precedes its
+ * children, Node::children is filled in that order and word ids are handed out in that order to the entries with is_leaf != 0.
+ * scoring / weighting = DBoW2::ScoringType / WeightingType (BowVector.h:36-55); the reference's vocabulary is k 10, L 6, L1_NORM, TF_IDF. */
+typedef struct orbx_vocabulary_desc
+{
+	int32_t k, L, scoring, weighting;
+	int64_t nnodes;                  /* without the root */
+	const int32_t* parent;           /* [nnodes] node id of the parent (0 = root) */
+	const uint8_t* is_leaf;          /* [nnodes] */
+	const uint8_t* descriptors;      /* [nnodes][32] */
+	const double* weights;           /* [nnodes] Node::weight */
+} orbx_vocabulary_desc;
+orbx_status orbx_vocabulary_create(const orbx_vocabulary_desc* desc, int device, orbx_vocabulary* out);
+/* TemplatedVocabulary<FORB::TDescriptor, FORB>::loadFromTextFile — Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.cpp:21-90, with this fork's
+ * tokenizer (strtok + atoi, weight read as int, :67). A file the reference rejects (:37) returns ORBX_ERR_INVALID. */
+orbx_status orbx_vocabulary_load_text(const char* path, int device, orbx_vocabulary* out);
+orbx_status orbx_vocabulary_info(orbx_vocabulary v, int* k, int* L, int* scoring, int* weighting, int64_t* nodes, int64_t* words);
+orbx_status orbx_vocabulary_destroy(orbx_vocabulary v);
+/* TemplatedVocabulary::transform(features, BowVector& v, FeatureVector& fv, levelsup) — TemplatedVocabulary.h:1129-1197 (per feature
+ * :1220-1262, FORB::distance FORB.cpp:79-98, BowVector.cpp:32-87, FeatureVector.cpp:30-44). desc = n x 32 descriptor rows (what
+ * Converter::toDescriptorVector splits). Outputs, each with room for n entries (fv_start: n + 1): the BowVector as (word_ids ascending,
+ * word_vals) and the FeatureVector in the orbx_feature_vector layout. feat_word / feat_node (optional, n entries): the word and the
+ * levelsup-ancestor of every feature, stopped or not. A leaf above level L - levelsup leaves the node id unset in the reference
+ * (uninitialised NodeId, :1156); it is reported as node 0 here. n <= 16384. */
+orbx_status orbx_bow_transform(orbx_vocabulary v, const uint8_t* desc, int n, int levelsup, int32_t* word_ids, double* word_vals, int32_t* n_words,
+                               uint32_t* fv_nodes, int32_t* fv_start, uint32_t* fv_items, int32_t* n_fv_nodes, int32_t* feat_word, int32_t* feat_node);
+/* The same for a batch of frames resident on the vocabulary's device, e.g. the outputs of orbx_extract_batch_device: d_desc
+ * [frames][cap][32], d_n [frames]. Outputs [frames][cap] (d_fv_start [frames][cap + 1], d_counts [frames][2] = n_words, n_fv_nodes;
+ * d_feat_word / d_feat_node optional). Enqueued on `stream` (a cudaStream_t; NULL = the vocabulary's own stream), no copies, no sync. */
+orbx_status orbx_bow_transform_batch_device(orbx_vocabulary v, const uint8_t* d_desc, const int32_t* d_n, int frames, int cap, int levelsup,
+                                            int32_t* d_word_ids, double* d_word_vals, uint32_t* d_fv_nodes, int32_t* d_fv_start, uint32_t* d_fv_items,
+                                            int32_t* d_counts, int32_t* d_feat_word, int32_t* d_feat_node, void* stream);
+/* L1Scoring::score(v1, v2) — Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:24-58, what ORBVocabulary::score evaluates for the reference's
+ * vocabulary (src/KeyFrameDatabase.cc:117, 216; src/LoopClosing.cc:176) — for npairs pairs of BowVectors stored back to back: vector i is
+ * (ids, vals)[offsets[i] .. offsets[i+1]), ids ascending. */
+orbx_status orbx_bow_score_l1(orbx_vocabulary v, const int32_t* ids, const double* vals, const int32_t* offsets, const int32_t* pair_a,
+                              const int32_t* pair_b, int npairs, double* scores);
 
 /* Integer-pipe microbenchmark used as the roofline denominator of the matcher: sustained POPC.32 per second on
  * `device` (all SMs, register operands). */

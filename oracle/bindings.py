@@ -121,6 +121,14 @@ class Oracle:
         f('search_by_bow', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
                                      C.c_void_p, C.c_float, C.c_int, C.c_void_p])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
+        f('voc_load_text', C.c_void_p, [C.c_char_p])
+        f('voc_destroy', None, [C.c_void_p])
+        f('bow_transform', C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6)
+        f('bow_score', C.c_double, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int])
+        f('time_bow_transform', C.c_double, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int])
+        if self.pre == 'orc_':
+            f('voc_create', C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+            f('bow_descend', None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p])
         f('cv_resize', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t])
         f('cv_fast', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int])
         f('cv_gaussian7', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t])
@@ -360,6 +368,10 @@ class Oracle:
         n = self._search_for_initialization(C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(window), nnratio, int(check_orientation))
         return n, m12, prev
 
+    def vocabulary(self, path=None, arrays=None):
+        """path: a vocabulary text file (loadFromTextFile); arrays (port only): dict k, L, scoring, weighting, parent, is_leaf, desc, weights."""
+        return OracleVocabulary(self, path, arrays)
+
     def extractor(self, nfeatures=2000, scale=1.2, nlevels=8, ini=20, mn=7):
         return _Extractor(self, nfeatures, scale, nlevels, ini, mn)
 
@@ -423,3 +435,50 @@ class _Extractor:
         t = [np.empty(self.nlevels, np.float32) for _ in range(4)]
         self.o._extractor_tables(self.h, *[_p(a) for a in t])
         return t
+
+
+class OracleVocabulary:
+    """ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) of one oracle library."""
+
+    def __init__(self, o, path=None, arrays=None):
+        self.o = o
+        if path is not None:
+            self.h = o._voc_load_text(os.fsencode(path))
+        else:
+            a = arrays
+            parent = np.ascontiguousarray(a['parent'], np.int32); leaf = np.ascontiguousarray(a['is_leaf'], np.uint8)
+            desc = np.ascontiguousarray(a['desc'], np.uint8); w = np.ascontiguousarray(a['weights'], np.float64)
+            self.h = o._voc_create(a['k'], a['L'], a['scoring'], a['weighting'], len(parent), _p(parent), _p(leaf), _p(desc), _p(w))
+        if not self.h:
+            raise ValueError('vocabulary rejected')
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.o._voc_destroy(self.h)
+            self.h = None
+
+    def transform(self, desc, levelsup=4):
+        """Returns (word_ids, word_vals, (fv_nodes, fv_start, fv_items))."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wi = np.empty(n + 1, np.int32); wv = np.empty(n + 1, np.float64)
+        fn = np.empty(n + 1, np.uint32); fs = np.empty(n + 2, np.int32); fi = np.empty(n + 1, np.uint32)
+        nfv = C.c_int32(0)
+        nw = self.o._bow_transform(self.h, _p(desc), n, levelsup, _p(wi), _p(wv), _p(fn), _p(fs), _p(fi), C.byref(nfv))
+        m = nfv.value
+        return wi[:nw].copy(), wv[:nw].copy(), (fn[:m].copy(), fs[:m + 1].copy(), fi[:fs[m]].copy())
+
+    def descend(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        w = np.empty(len(desc), np.int32); nd = np.empty(len(desc), np.int32)
+        self.o._bow_descend(self.h, _p(desc), len(desc), levelsup, _p(w), _p(nd))
+        return w, nd
+
+    def score(self, a, b):
+        ia = np.ascontiguousarray(a[0], np.int32); va = np.ascontiguousarray(a[1], np.float64)
+        ib = np.ascontiguousarray(b[0], np.int32); vb = np.ascontiguousarray(b[1], np.float64)
+        return self.o._bow_score(self.h, _p(ia), _p(va), len(ia), _p(ib), _p(vb), len(ib))
+
+    def time_transform(self, desc, levelsup=4, reps=5):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        return self.o._time_bow_transform(self.h, _p(desc), len(desc), levelsup, reps)

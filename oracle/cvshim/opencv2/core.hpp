@@ -181,6 +181,7 @@ public:
 		owner_ = std::make_shared<std::vector<uchar>>((size_t)r * c * esz(type));
 		rows = r; cols = c; type_ = type; step = (size_t)c * esz(type); data = owner_->data();
 	}
+	void create(Size s, int type) { create(s.height, s.width, type); }
 	void release() { owner_.reset(); rows = cols = 0; step = 0; data = nullptr; }
 	void setTo(int v)
 	{

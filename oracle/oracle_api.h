@@ -166,6 +166,19 @@ double ORACLE_FN(time_search_last_frame)(const oracle_frame_view* cur, const ora
 int ORACLE_FN(search_for_initialization)(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev_matched, int32_t* matches12,
                                          int window, float nnratio, int check_orientation);
 
+// ---- bag-of-words transform: ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> ----
+// loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.cpp:21-90); NULL when the file is rejected
+void* ORACLE_FN(voc_load_text)(const char* path);
+void ORACLE_FN(voc_destroy)(void* voc);
+// transform(features, BowVector, FeatureVector, levelsup) (TemplatedVocabulary.h:1129-1197). Outputs have room for n entries
+// (fv_start: n + 1): the BowVector as ascending (word id, value), the FeatureVector as CSR (see oracle_feature_vector). Returns the number of words.
+int ORACLE_FN(bow_transform)(void* voc, const uint8_t* desc, int n, int levelsup, int32_t* word_ids, double* word_vals, uint32_t* fv_nodes,
+                             int32_t* fv_start, uint32_t* fv_items, int32_t* n_fv_nodes);
+// TemplatedVocabulary::score = the scoring object's score (L1Scoring::score, ScoringObject.cpp:24-58, for the reference's vocabulary)
+double ORACLE_FN(bow_score)(void* voc, const int32_t* ida, const double* va, int na, const int32_t* idb, const double* vb, int nb);
+// mean seconds per transform call over reps repetitions (CPU baseline)
+double ORACLE_FN(time_bow_transform)(void* voc, const uint8_t* desc, int n, int levelsup, int reps);
+
 // ---- pinned third-party primitives (same code in both libraries; checked against cv2 4.13.0) ----
 void ORACLE_FN(cv_resize)(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep);
 int ORACLE_FN(cv_fast)(const uint8_t* img, int w, int h, size_t step, int th, int nms, oracle_cand* out, int cap);

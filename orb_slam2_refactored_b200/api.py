@@ -54,6 +54,11 @@ class _FeatureVector(C.Structure):
     _fields_ = [('nnodes', C.c_int32), ('node_ids', C.c_void_p), ('start', C.c_void_p), ('indices', C.c_void_p)]
 
 
+class _VocabularyDesc(C.Structure):
+    _fields_ = [('k', C.c_int32), ('L', C.c_int32), ('scoring', C.c_int32), ('weighting', C.c_int32), ('nnodes', C.c_int64),
+                ('parent', C.c_void_p), ('is_leaf', C.c_void_p), ('descriptors', C.c_void_p), ('weights', C.c_void_p)]
+
+
 class _Sim3(C.Structure):
     _fields_ = [('R', C.c_float * 9), ('t', C.c_float * 3), ('s', C.c_float)]
 
@@ -144,6 +149,14 @@ _SIGNATURES = {
     'orbx_frame_assign_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Bounds), C.c_int, C.c_void_p]),
     'orbx_undistort_keypoints_device': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_Camera), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
+    'orbx_vocabulary_create': (C.c_int, [C.POINTER(_VocabularyDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    'orbx_vocabulary_load_text': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    'orbx_vocabulary_info': (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_int64)] * 2),
+    'orbx_vocabulary_destroy': (C.c_int, [C.c_void_p]),
+    'orbx_bow_transform': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    'orbx_bow_transform_batch_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9),
+    'orbx_bow_score_l1': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 
@@ -690,6 +703,93 @@ def ComputeDistinctiveDescriptors(descriptor_sets, device=0):
     best = np.empty(len(sets), np.int32)
     _check(lib().orbx_distinctive_descriptors(device, _p(allrows), _p(off), len(sets), _p(best)))
     return best
+
+
+class ORBVocabulary:
+    """ORB_SLAM2::ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h,
+    Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): the part Frame::ComputeBoW / KeyFrame::ComputeBoW and the key-frame database use —
+    loadFromTextFile, transform(features, BowVector, FeatureVector, levelsup) and score. The tree lives on the GPU."""
+    L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT = range(6)   # DBoW2::ScoringType
+    TF_IDF, TF, IDF, BINARY = range(4)                                        # DBoW2::WeightingType
+
+    def __init__(self, device=0):
+        self.device = device
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value and _lib is not None:
+            _lib.orbx_vocabulary_destroy(h)
+            self._h = C.c_void_p()
+
+    def loadFromTextFile(self, filename):
+        """TemplatedVocabulary.cpp:21-90; False where the reference returns false."""
+        self.__del__()
+        st = lib().orbx_vocabulary_load_text(os.fsencode(filename), self.device, C.byref(self._h))
+        if st == ORBX_ERR_INVALID:
+            return False
+        _check(st)
+        return True
+
+    def create(self, k, L, parent, is_leaf, descriptors, weights, scoring=0, weighting=0):
+        """The same tree from arrays: entry i is node id i + 1 in file order."""
+        self.__del__()
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        descriptors = np.ascontiguousarray(descriptors, np.uint8); weights = np.ascontiguousarray(weights, np.float64)
+        d = _VocabularyDesc(k, L, scoring, weighting, len(parent), parent.ctypes.data, is_leaf.ctypes.data, descriptors.ctypes.data, weights.ctypes.data)
+        _check(lib().orbx_vocabulary_create(C.byref(d), self.device, C.byref(self._h)))
+        return self
+
+    def info(self):
+        v = [C.c_int() for _ in range(4)] + [C.c_int64(), C.c_int64()]
+        _check(lib().orbx_vocabulary_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(('k', 'L', 'scoring', 'weighting', 'nodes', 'words'), [x.value for x in v]))
+
+    def empty(self):
+        return self.info()['words'] == 0
+
+    def transform(self, features, levelsup=4, per_feature=False):
+        """transform(features, v, fv, levelsup), TemplatedVocabulary.h:1129-1197. features: N x 32 descriptor rows. Returns
+        (word_ids, word_values) = the BowVector in ascending word id and (node_ids, start, indices) = the FeatureVector as CSR
+        (what ORBmatcher.SearchByBoW takes); with per_feature also every feature's (word, node)."""
+        features = np.ascontiguousarray(features, np.uint8).reshape(-1, 32)
+        n = len(features)
+        wi = np.empty(n + 1, np.int32); wv = np.empty(n + 1, np.float64)
+        fn = np.empty(n + 1, np.uint32); fs = np.empty(n + 2, np.int32); fi = np.empty(n + 1, np.uint32)
+        fw = np.empty(n + 1, np.int32); fnode = np.empty(n + 1, np.int32)
+        nw, nf = C.c_int32(0), C.c_int32(0)
+        _check(lib().orbx_bow_transform(self._h, _p(features), n, levelsup, _p(wi), _p(wv), C.byref(nw), _p(fn), _p(fs), _p(fi), C.byref(nf),
+                                        _p(fw) if per_feature else None, _p(fnode) if per_feature else None))
+        m = nf.value
+        out = (wi[:nw.value].copy(), wv[:nw.value].copy()), (fn[:m].copy(), fs[:m + 1].copy(), fi[:fs[m]].copy())
+        return out + ((fw[:n].copy(), fnode[:n].copy()),) if per_feature else out
+
+    def transform_batch_device(self, d_desc, d_n, frames, cap, levelsup=4, stream=None):
+        """Batch of frames resident on the device (torch tensors: d_desc [frames, cap, 32] u8, d_n [frames] i32), e.g. what
+        ORBextractor.extract_batch_device leaves there. Returns torch tensors (word_ids, word_vals, fv_nodes, fv_start, fv_items, counts)."""
+        import torch
+        dev = d_desc.device
+        word_ids = torch.empty((frames, cap), dtype=torch.int32, device=dev); word_vals = torch.empty((frames, cap), dtype=torch.float64, device=dev)
+        fv_nodes = torch.empty((frames, cap), dtype=torch.int32, device=dev); fv_start = torch.empty((frames, cap + 1), dtype=torch.int32, device=dev)
+        fv_items = torch.empty((frames, cap), dtype=torch.int32, device=dev); counts = torch.empty((frames, 2), dtype=torch.int32, device=dev)
+        _check(lib().orbx_bow_transform_batch_device(self._h, d_desc.data_ptr(), d_n.data_ptr(), frames, cap, levelsup, word_ids.data_ptr(),
+                                                     word_vals.data_ptr(), fv_nodes.data_ptr(), fv_start.data_ptr(), fv_items.data_ptr(),
+                                                     counts.data_ptr(), None, None, stream))
+        return word_ids, word_vals, fv_nodes, fv_start, fv_items, counts
+
+    def score(self, a, b):
+        """TemplatedVocabulary::score for the reference's L1 vocabulary (ScoringObject.cpp:24-58); a, b = (word_ids, word_values)."""
+        return float(self.score_pairs([a, b], [(0, 1)])[0])
+
+    def score_pairs(self, vectors, pairs):
+        ids = np.concatenate([np.asarray(v[0], np.int32) for v in vectors]) if vectors else np.empty(0, np.int32)
+        vals = np.concatenate([np.asarray(v[1], np.float64) for v in vectors]) if vectors else np.empty(0, np.float64)
+        off = np.zeros(len(vectors) + 1, np.int32); off[1:] = np.cumsum([len(v[0]) for v in vectors])
+        pa = np.ascontiguousarray([p[0] for p in pairs], np.int32); pb = np.ascontiguousarray([p[1] for p in pairs], np.int32)
+        out = np.empty(len(pairs), np.float64)
+        ids = np.ascontiguousarray(ids); vals = np.ascontiguousarray(vals)
+        _check(lib().orbx_bow_score_l1(self._h, _p(ids), _p(vals), _p(off), _p(pa), _p(pb), len(pairs), _p(out)))
+        return out
 
 
 def measure_popc_peak(device=0):

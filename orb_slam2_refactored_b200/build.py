@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'liborbx_b200.so')
-SOURCES = ['orbx_extract.cu', 'orbx_match.cu', 'orbx_guided.cu', 'orbx_api.cu']
+SOURCES = ['orbx_extract.cu', 'orbx_match.cu', 'orbx_guided.cu', 'orbx_bow.cu', 'orbx_api.cu']
 DEPS = SOURCES + ['orbx_internal.cuh', 'orbx_sort.cuh', 'orb_pattern.inc', os.path.join('..', '..', 'include', 'orbx.h')]
 
 NVCC_FLAGS = [

@@ -343,3 +343,71 @@ def sim3_points(seed, fr, cam, npts=1200, scale=1.07):
     nrm = nrm + tilt
     pts['normal'] = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
     return (R, (t * s).astype(np.float32), s), pts, desc
+
+
+def vocabulary(seed, k=10, L=6, prune=0.0, stop=0.1, min_leaf_level=2, hier_flips=40):
+    """A synthetic ORB vocabulary tree in the node order DBoW2's HKmeansStep produces (the children of a node get consecutive ids, then each
+    child is expanded depth-first), which is also the line order of the text file loadFromTextFile reads. prune > 0 drops children and
+    ends branches early (never above min_leaf_level, where the reference's node id would be unset). A child's descriptor is its
+    parent's with hier_flips random bit flips, so that the walk down the tree is decided by close calls and ties. Weights are small
+    non-negative integers (this fork reads the weight with atoi), a share `stop` of the words has weight 0 (stopped).
+    Returns dict(k, L, scoring, weighting, parent, is_leaf, desc, weights, text_weights)."""
+    r = np.random.RandomState(seed)
+    parent, leaf, level = [], [], []
+    stack = [(0, 0)]
+    nxt = 1
+    while stack:
+        node, lvl = stack.pop()
+        nchild = k if (prune == 0.0 or r.rand() > prune) else max(1, int(r.randint(1, k + 1)))
+        ids = list(range(nxt, nxt + nchild))
+        nxt += nchild
+        expand = []
+        for c in ids:
+            parent.append(node); level.append(lvl + 1)
+            is_leaf = lvl + 1 >= L or (prune > 0.0 and lvl + 1 >= min_leaf_level and r.rand() < prune)
+            leaf.append(is_leaf)
+            if not is_leaf:
+                expand.append((c, lvl + 1))
+        stack.extend(reversed(expand))
+    n = len(parent)
+    parent = np.asarray(parent, np.int32); leaf = np.asarray(leaf, np.uint8)
+    bits = np.zeros((n + 1, 256), np.uint8)
+    bits[0] = r.randint(0, 2, 256)
+    flips = r.randint(0, 256, (n, hier_flips))
+    level = np.asarray(level)
+    for lvl in range(1, L + 1):                               # parents before children, one level at a time
+        idx = np.flatnonzero(level == lvl)
+        if len(idx) == 0:
+            break
+        mask = np.zeros((len(idx), 256), np.uint8)
+        mask[np.arange(len(idx))[:, None], flips[idx]] = 1    # a position drawn twice flips once
+        bits[idx + 1] = bits[parent[idx]] ^ mask
+    desc = np.packbits(bits[1:], axis=1, bitorder='little')
+    w = r.randint(1, 10, n).astype(np.float64)
+    w[r.rand(n) < stop] = 0.0
+    frac = r.randint(0, 100, n)
+    text = [f'{int(w[i])}.{frac[i]:02d}' if frac[i] % 2 else f'{int(w[i])}' for i in range(n)]
+    return dict(k=k, L=L, scoring=0, weighting=0, parent=parent, is_leaf=leaf, desc=desc, weights=w, text_weights=text)
+
+
+def write_vocabulary_text(voc, path):
+    """ORBvoc.txt layout: header `k L scoring weighting`, then one line per node: parent id, leaf flag, 32 descriptor bytes, weight."""
+    with open(path, 'w') as f:
+        f.write(f"{voc['k']} {voc['L']} {voc['scoring']} {voc['weighting']}\n")
+        d = voc['desc']
+        for i in range(len(voc['parent'])):
+            f.write(f"{voc['parent'][i]} {int(voc['is_leaf'][i])} " + ' '.join(map(str, d[i])) + f" {voc['text_weights'][i]} \n")
+
+
+def vocabulary_features(seed, voc, n=1500, exact=0.1, near=0.5, flips=30):
+    """Descriptors to push through a vocabulary: random ones, copies of word descriptors (distance 0) and noisy copies."""
+    r = np.random.RandomState(seed)
+    d = r.randint(0, 256, (n, 32)).astype(np.uint8)
+    words = np.flatnonzero(voc['is_leaf'])
+    for i in range(n):
+        u = r.rand()
+        if u < exact + near:
+            d[i] = voc['desc'][words[r.randint(len(words))]]
+            if u >= exact:
+                d[i] = _flip_bits(r, d[i], r.randint(1, flips + 1))
+    return d

@@ -7,6 +7,7 @@ primitives.npz   outputs of cv2 4.13.0 (IPP off) for the four un-vendored primit
 pipeline.npz     outputs of the REFERENCE's own translation units (oracle/_ref, built from
                  /root/reference/src/ORBextractor.cc and ORBmatcher.cc line ranges) for Extract, the stages,
                  ComputeStereoMatches and the best/second scan on small synthetic inputs.
+bow.npz          outputs of the reference's own DBoW2 text (transform: BowVector + FeatureVector) on the small cases of tests/bow_cases.py.
 guided.npz       outputs of the reference's guided matchers (src/Frame.cc, src/ORBmatcher.cc line ranges) on seeded scenes.
 Inputs are regenerated from orb_slam2_refactored_b200/synth.py (numpy RandomState); a CRC of every input is stored so
 that a silent change of the generator is caught.
@@ -162,9 +163,35 @@ def guided():
     print('guided.npz:', len(out), 'arrays')
 
 
+def bow():
+    """bow.npz: outputs of the reference's DBoW2 text (oracle/_ref, rule bow_gen.cc) on the small cases of tests/bow_cases.py; the
+    vocabulary goes through a text file and the reference's own loadFromTextFile."""
+    import tempfile
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bow_cases as bc
+    from orb_slam2_refactored_b200 import synth
+    ref = bindings.Oracle('ref')
+    out = {}
+    for name in bc.SMALL:
+        voc, feats, levelsup = bc.make(name)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, 'voc.txt')
+            synth.write_vocabulary_text(voc, path)
+            wi, wv, fv = ref.vocabulary(path=path).transform(feats, levelsup)
+        for k, v in bc.flatten(((wi, wv), fv)).items():
+            out[f'{name}_{k}'] = v
+        out[f'{name}_features'] = feats
+    np.savez_compressed(os.path.join(HERE, 'bow.npz'), **out)
+    print('bow.npz:', len(out), 'arrays')
+
+
 if __name__ == '__main__':
+    if 'bow' in sys.argv[1:]:
+        bow()
+        sys.exit(0)
     primitives()
     pipeline()
     guided()
-    for f in ('primitives.npz', 'pipeline.npz', 'guided.npz'):
+    bow()
+    for f in ('primitives.npz', 'pipeline.npz', 'guided.npz', 'bow.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
