@@ -311,6 +311,44 @@ typedef struct orbx_feature_vector { int32_t nnodes; const uint32_t* node_ids; c
  * for the second. The feature vectors come from orbx_bow_transform below (or from DBoW2 on the host). */
 orbx_status orbx_search_by_bow(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* valid1, orbx_frame f2, const orbx_feature_vector* fv2,
                                const uint8_t* valid2, float nnratio, int check_orientation, int32_t* match2, int* nmatches);
+/* ---- Matchers of local mapping and loop closing whose per-point search is independent of the other points. --------------------------
+ * The window search underneath them: for every window the keypoint of `f` with the smallest descriptor distance among
+ * GetFeaturesInArea(u, v, radius) with octave in [min_level, max_level] — the first one in GetFeaturesInArea's order on ties
+ * (`dist < bestDist`) — and that distance; (-1, 256) when there is none. flags bit 0 = search this window; bit 1 = also apply the
+ * chi-square gate of Fuse (src/ORBmatcher.cc:934-945: stereo keypoints against (u, v, ur) at 7.8, monocular ones against (u, v) at 5.99,
+ * scaled by inv_sigma_sq[octave]). */
+typedef struct orbx_best_window { float u, v, radius, ur; int32_t min_level, max_level; int32_t flags; } orbx_best_window;
+orbx_status orbx_search_best_in_windows(orbx_frame f, const orbx_best_window* windows, const uint8_t* pt_desc, int npts, const float* inv_sigma_sq,
+                                        int32_t* best_idx, int32_t* best_dist);
+/* ORBmatcher::Fuse(KeyFrame* keyframe, const std::vector<MapPoint*>& mappoints, float th) — src/ORBmatcher.cc:868-980, the search half:
+ * projection, image / distance / 60-degree gates, PredictScale, window, octave and chi-square gates, best distance (:879-954), host
+ * geometry in the reference's operation order as for orbx_search_by_projection_sim3. flags bit 0 of a point = non-null && !isBad().
+ * The map mutation (:956-976: Replace / AddObservation / AddMapPoint when best_dist <= TH_LOW) and the IsInKeyFrame test of :876 depend
+ * on the points before and stay with the caller, who replays them in order over (best_idx, best_dist): the search itself reads nothing
+ * they change. inv_sigma_sq = keyframe->pyramid.invSigmaSq. */
+orbx_status orbx_fuse(orbx_frame f, const orbx_camera* camera, const orbx_pose* pose, float log_scale_factor, const float* inv_sigma_sq,
+                      const orbx_sim3_point* pts, const uint8_t* pt_desc, int npts, float th, int32_t* best_idx, int32_t* best_dist);
+/* ORBmatcher::Fuse(KeyFrame*, const Sim3& Scw, mappoints, th, replacePoints) — src/ORBmatcher.cc:982-1088, the search half (:987-1067).
+ * flags bit 0 = !isBad() && not in keyframe->GetMapPoints() (:1002-1003). The caller applies :1069-1084 over (best_idx, best_dist <= TH_LOW). */
+orbx_status orbx_fuse_sim3(orbx_frame f, const orbx_camera* camera, const orbx_sim3* Scw, float log_scale_factor, const orbx_sim3_point* pts,
+                           const uint8_t* pt_desc, int npts, float th, int32_t* best_idx, int32_t* best_dist);
+/* ORBmatcher::SearchBySim3(kf1, kf2, matches12, S12, th) — src/ORBmatcher.cc:1090-1277. pts1 / pts2: one entry per keypoint of f1 / f2
+ * (GetMapPointMatches), flags bit 0 = map point present && !alreadyMatched && !isBad() (:1130, :1197; `angle` unused); desc1 / desc2 the
+ * map points' descriptors. Outputs: match1 / match2 (optional) = the two directed searches (:1127-1258), matches12[i1] = the keypoint of
+ * f2 on which both agree or -1 (:1260-1274; the caller stores mappoints2[idx2]), *nfound. */
+orbx_status orbx_search_by_sim3(orbx_frame f1, const orbx_camera* camera1, const orbx_pose* pose1, float log_scale_factor1, orbx_frame f2,
+                                const orbx_camera* camera2, const orbx_pose* pose2, float log_scale_factor2, const orbx_sim3* S12, float th,
+                                const orbx_keyframe_point* pts1, const uint8_t* desc1, const orbx_keyframe_point* pts2, const uint8_t* desc2,
+                                int32_t* match1, int32_t* match2, int32_t* matches12, int* nfound);
+/* ORBmatcher::SearchForTriangulation(kf1, kf2, F12, matchIds, onlyStereo) — src/ORBmatcher.cc:768-866 with CheckDistEpipolarLine
+ * (:384-404), FeatureVectorIterator and CheckOrientation. has_mp1 / has_mp2: per keypoint, GetMapPoint(idx) != NULL. F12 row-major 3x3,
+ * epipole2 = proj2.WorldToImage(keyframe1->GetCameraCenter()) (:772-773), sigma_sq2 = keyframe2->pyramid.sigmaSq. matches12 (f1->n
+ * entries, out) = the keypoint of f2 matched to keypoint idx1 or -1; matchIds of the reference = the pairs (idx1, matches12[idx1] >= 0)
+ * in ascending idx1. This fork never sets matched2 (:780, :814), so two keypoints of f1 may share a keypoint of f2 — reproduced. */
+orbx_status orbx_search_for_triangulation(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* has_mp1, orbx_frame f2,
+                                          const orbx_feature_vector* fv2, const uint8_t* has_mp2, const float* F12, const float* epipole2,
+                                          const float* sigma_sq2, int only_stereo, int check_orientation, int32_t* matches12, int* nmatches);
+
 /* Diagnostics of the last search on `f`: rounds needed to reach the sequential result (>= 1), the kernel's duration (CUDA events) and
  * the microseconds its phases took (enumeration, -, -, distances, rounds, finalisation, and the part of `rounds` spent staging state into
  * shared memory; %globaltimer). Any pointer may be NULL; phase_us needs room for 7 floats. */

@@ -121,6 +121,14 @@ class Oracle:
         f('search_by_bow', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
                                      C.c_void_p, C.c_float, C.c_int, C.c_void_p])
         f('search_for_initialization', C.c_int, [C.POINTER(FrameView), C.POINTER(FrameView), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int])
+        f('fuse', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)])
+        f('fuse_sim3', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)])
+        f('search_by_sim3', C.c_int, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.POINTER(FrameView), C.POINTER(Camera),
+                                      C.POINTER(Pose), C.c_float, C.POINTER(Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+        f('search_for_triangulation', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p])
         f('voc_load_text', C.c_void_p, [C.c_char_p])
         f('voc_destroy', None, [C.c_void_p])
         f('bow_transform', C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6)
@@ -367,6 +375,67 @@ class Oracle:
         m12 = np.empty(v1.n, np.int32)
         n = self._search_for_initialization(C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(window), nnratio, int(check_orientation))
         return n, m12, prev
+
+    @staticmethod
+    def _sim3(S):
+        out = Sim3()
+        out.R[:] = [float(x) for x in np.asarray(S[0], np.float32).reshape(9)]
+        out.t[:] = [float(x) for x in np.asarray(S[1], np.float32).reshape(3)]
+        out.s = float(np.float32(S[2]))
+        return out
+
+    @staticmethod
+    def _pose1(p):
+        out = Pose()
+        out.R[:] = [float(x) for x in np.asarray(p[0], np.float32).reshape(9)]
+        out.t[:] = [float(x) for x in np.asarray(p[1], np.float32).reshape(3)]
+        return out
+
+    def fuse(self, kf, cam, pose, log_scale_factor, inv_sigma_sq, pts, pt_desc, th, state):
+        """Fuse(keyframe, mappoints, th) on the one-key-frame map model; state = dict(kf_mp, nobs, bad, in_kf) (copied).
+        Returns (nfused, kf_mp, nobs, bad, in_kf, log)."""
+        v, keep = self._frame_view(kf)
+        pts = np.ascontiguousarray(pts); pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        sig = np.ascontiguousarray(inv_sigma_sq, np.float32)
+        kf_mp = state['kf_mp'].astype(np.int32).copy(); nobs = state['nobs'].astype(np.int32).copy()
+        bad = state['bad'].astype(np.uint8).copy(); in_kf = state['in_kf'].astype(np.uint8).copy()
+        log = np.zeros(3 * len(pts) + 3, np.int32); nlog = C.c_int(0)
+        n = self._fuse(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(self._pose1(pose)), float(log_scale_factor), _p(sig), _p(pts),
+                       _p(pt_desc), len(pts), float(th), _p(kf_mp), _p(nobs), _p(bad), _p(in_kf), _p(log), len(log), C.byref(nlog))
+        return n, kf_mp, nobs, bad, in_kf, log[:nlog.value].copy()
+
+    def fuse_sim3(self, kf, cam, sim3, log_scale_factor, pts, pt_desc, th, state):
+        """Fuse(keyframe, Scw, mappoints, th, replacePoints). Returns (nfused, kf_mp, nobs, bad, replace, log)."""
+        v, keep = self._frame_view(kf)
+        pts = np.ascontiguousarray(pts); pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+        kf_mp = state['kf_mp'].astype(np.int32).copy(); nobs = state['nobs'].astype(np.int32).copy(); bad = state['bad'].astype(np.uint8).copy()
+        rep = np.full(max(len(pts), 1), -1, np.int32)
+        log = np.zeros(3 * len(pts) + 3, np.int32); nlog = C.c_int(0)
+        n = self._fuse_sim3(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(self._sim3(sim3)), float(log_scale_factor), _p(pts),
+                            _p(pt_desc), len(pts), float(th), _p(kf_mp), _p(nobs), _p(bad), _p(rep), _p(log), len(log), C.byref(nlog))
+        return n, kf_mp, nobs, bad, rep[:len(pts)], log[:nlog.value].copy()
+
+    def search_by_sim3(self, c, th):
+        """SearchBySim3 on a synth.sim3_pair() scene. Returns (nfound, matches12)."""
+        v1, k1 = self._frame_view(c['f1']); v2, k2 = self._frame_view(c['f2'])
+        cam = Camera(*[float(x) for x in c['cam']])
+        p1 = np.ascontiguousarray(c['pts1']); p2 = np.ascontiguousarray(c['pts2'])
+        d1 = np.ascontiguousarray(c['desc1'], np.uint8); d2 = np.ascontiguousarray(c['desc2'], np.uint8)
+        m12 = np.empty(max(v1.n, 1), np.int32)
+        lsf = float(c['lsf'])
+        n = self._search_by_sim3(C.byref(v1), C.byref(cam), C.byref(self._pose1(c['pose1'])), lsf, C.byref(v2), C.byref(cam),
+                                 C.byref(self._pose1(c['pose2'])), lsf, C.byref(self._sim3(c['S12'])), float(th), _p(p1), _p(d1), _p(p2), _p(d2), _p(m12))
+        return n, m12[:v1.n]
+
+    def search_for_triangulation(self, c, only_stereo, check_orientation):
+        v1, k1 = self._frame_view(c['f1']); v2, k2 = self._frame_view(c['f2'])
+        c1, keep1 = self._fv(c['fv1']); c2, keep2 = self._fv(c['fv2'])
+        h1 = np.ascontiguousarray(c['has1'], np.uint8); h2 = np.ascontiguousarray(c['has2'], np.uint8)
+        F = np.ascontiguousarray(c['F12'], np.float32).reshape(9); ep = np.ascontiguousarray(c['ep2'], np.float32); sg = np.ascontiguousarray(c['sigma_sq2'], np.float32)
+        m12 = np.empty(max(v1.n, 1), np.int32)
+        n = self._search_for_triangulation(C.byref(v1), C.byref(c1), _p(h1), C.byref(v2), C.byref(c2), _p(h2), _p(F), _p(ep), _p(sg), int(only_stereo),
+                                           int(check_orientation), _p(m12))
+        return n, m12[:v1.n]
 
     def vocabulary(self, path=None, arrays=None):
         """path: a vocabulary text file (loadFromTextFile); arrays (port only): dict k, L, scoring, weighting, parent, is_leaf, desc, weights."""

@@ -54,6 +54,8 @@ template <class T> struct Point_
 	Point_(T x_, T y_) : x(x_), y(y_) {}
 	Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }
 };
+// OpenCV's types.hpp: a - b = Point_<T>(saturate_cast<T>(a.x - b.x), saturate_cast<T>(a.y - b.y))
+template <class T> static inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>((T)(a.x - b.x), (T)(a.y - b.y)); }
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
 

@@ -589,4 +589,295 @@ int orc_search_for_initialization(const oracle_frame_view* f1, const oracle_fram
 	return nmatches;
 }
 
+
+// ---- Fuse x2, SearchBySim3, SearchForTriangulation (src/ORBmatcher.cc:868-980, 982-1088, 1090-1277, 768-866) ----------------------------
+// Restated in two halves, the split the CUDA library uses: (1) a per-point search that reads only the key frame's keypoints and the point
+// (projection, gates, window, best distance, first keypoint on ties), (2) the sequential replay of the map mutation over the search results.
+// The map model is the one of oracle/ref_guided_decl.h (one key frame; AddObservation / Replace as in src/MapPoint.cc:103-121, 193-240).
+namespace {
+
+struct Best { int idx, dist; };
+
+// best keypoint of a window: octave in [lo, hi], optional chi-square gate of Fuse (:934-945); `dist < bestDist` keeps the first minimum
+Best best_in_window(const Grid& g, const oracle_frame_view* f, float u, float v, float radius, int lo, int hi, const uint8_t* desc, bool gate,
+                    float ur, const float* inv_sigma_sq)
+{
+	Best b = { -1, 256 };
+	g.query(u, v, radius, -1, -1, [&](int idx) {
+		const oracle_keypoint& kp = f->kps_un[idx];
+		const int scale = kp.octave;
+		if (scale < lo || scale > hi) return;
+		if (gate)
+		{
+			const float dx = u - kp.x, dy = v - kp.y;
+			const float ur2 = f->uright ? f->uright[idx] : -1.f;
+			if (ur2 >= 0)
+			{
+				const float dz = ur - ur2;
+				if ((dx * dx + dy * dy + dz * dz) * inv_sigma_sq[scale] > 7.8) return;
+			}
+			else if ((dx * dx + dy * dy) * inv_sigma_sq[scale] > 5.99) return;
+		}
+		const int d = hamming256(desc, f->desc + (size_t)idx * 32);
+		if (d < b.dist) { b.dist = d; b.idx = idx; }
+	});
+	return b;
+}
+
+void mul3(const float* R, const float* x, float* y) { for (int r = 0; r < 3; r++) { float s = 0; for (int k = 0; k < 3; k++) s += R[r * 3 + k] * x[k]; y[r] = s; } }
+void invt(const float* R, const float* t, float* o) { for (int i = 0; i < 3; i++) { float s = 0; for (int k = 0; k < 3; k++) s += (R[k * 3 + i] * -1) * t[k]; o[i] = s; } }
+float norm3(const float* v) { double ss = 0; for (int k = 0; k < 3; k++) ss += (double)v[k] * (double)v[k]; return (float)std::sqrt(ss); }
+int predict_scale(float max_distance, float dist, float lsf, int nlevels)
+{
+	const float ratio = max_distance / dist;
+	const int scale = (int)std::ceil(std::log((double)ratio) / lsf);
+	return std::max(0, std::min(scale, nlevels - 1));
+}
+bool in_image(const oracle_frame_view* f, float u, float v) { return u >= f->bounds.minx && u < f->bounds.maxx && v >= f->bounds.miny && v < f->bounds.maxy; }
+
+// :879-954 / :1002-1066 for one point given its camera coordinates
+Best fuse_search(const Grid& g, const oracle_frame_view* f, const oracle_camera* cam, const float* xc, const float* Ow, const oracle_sim3_point& p,
+                 const uint8_t* desc, float lsf, float th, bool gate, const float* inv_sigma_sq)
+{
+	const Best none = { -1, 256 };
+	if (xc[2] < 0.f) return none;
+	const float invZ = 1.f / xc[2];
+	const float u = invZ * cam->fx * xc[0] + cam->cx, v = invZ * cam->fy * xc[1] + cam->cy;
+	if (!in_image(f, u, v)) return none;
+	const float ur = u - cam->bf / xc[2];
+	const float maxDistance = 1.2f * p.max_distance, minDistance = 0.8f * p.min_distance;
+	float PO[3];
+	for (int k = 0; k < 3; k++) PO[k] = p.xw[k] - Ow[k];
+	const float dist3D = norm3(PO);
+	if (dist3D < minDistance || dist3D > maxDistance) return none;
+	float dot = 0;
+	for (int k = 0; k < 3; k++) dot += PO[k] * p.normal[k];
+	if (dot < 0.5 * dist3D) return none;
+	const int ps = predict_scale(p.max_distance, dist3D, lsf, f->nlevels);
+	return best_in_window(g, f, u, v, th * f->scale_factors[ps], ps - 1, ps, desc, gate, ur, inv_sigma_sq);
+}
+
+struct MapModel
+{
+	int32_t* kf_mp; int32_t* nobs; uint8_t* bad; std::vector<int> where;   // where[p] = keypoint holding p in the key frame, -1 = not in it
+	std::vector<int> log;
+	const oracle_frame_view* f;
+	void add_observation(int p, int idx)
+	{
+		log.push_back(2); log.push_back(p); log.push_back(idx);
+		where[p] = idx;
+		nobs[p] += (f->uright && f->uright[idx] >= 0) ? 2 : 1;
+		kf_mp[idx] = p;                                    // keyframe->AddMapPoint
+	}
+	void replace(int p, int other)                         // p->Replace(other)
+	{
+		log.push_back(1); log.push_back(p); log.push_back(other);
+		if (p == other) return;
+		bad[p] = 1;
+		if (where[p] >= 0)
+		{
+			if (where[other] < 0) { kf_mp[where[p]] = other; where[other] = where[p]; nobs[other] += nobs[p]; }
+			else kf_mp[where[p]] = -1;
+		}
+	}
+};
+
+}  // namespace
+
+int orc_fuse(const oracle_frame_view* f, const oracle_camera* cam, const oracle_pose* pose, float lsf, const float* inv_sigma_sq,
+             const oracle_sim3_point* pts, const uint8_t* pt_desc, int npts, float th, int32_t* kf_mp, int32_t* nobs, uint8_t* bad, uint8_t* in_kf,
+             int32_t* log, int cap, int* nlog)
+{
+	const Grid g = make_grid(f);
+	float Ow[3];
+	invt(pose->R, pose->t, Ow);
+	// (1) search, independent per point
+	std::vector<Best> best((size_t)npts, Best{ -1, 256 });
+	for (int i = 0; i < npts; i++)
+	{
+		if (!(pts[i].flags & 1)) continue;
+		float xc[3];
+		mul3(pose->R, pts[i].xw, xc);
+		for (int k = 0; k < 3; k++) xc[k] += pose->t[k];
+		best[i] = fuse_search(g, f, cam, xc, Ow, pts[i], pt_desc + (size_t)i * 32, lsf, th, true, inv_sigma_sq);
+	}
+	// (2) replay of :876 and :956-976 in order
+	MapModel M{ kf_mp, nobs, bad, std::vector<int>((size_t)npts, -1), {}, f };
+	for (int c = 0; c < f->n; c++)
+		if (kf_mp[c] >= 0 && in_kf[kf_mp[c]]) M.where[kf_mp[c]] = c;
+	int nfused = 0;
+	for (int i = 0; i < npts; i++)
+	{
+		if (!(pts[i].flags & 1) || bad[i] || M.where[i] >= 0) continue;
+		if (best[i].dist > TH_LOW) continue;
+		const int held = kf_mp[best[i].idx];
+		if (held >= 0)
+		{
+			if (!bad[held])
+			{
+				if (nobs[held] > nobs[i]) M.replace(i, held);
+				else M.replace(held, i);
+			}
+		}
+		else M.add_observation(i, best[i].idx);
+		nfused++;
+	}
+	for (int i = 0; i < npts; i++) in_kf[i] = M.where[i] >= 0;
+	*nlog = (int)std::min<size_t>(M.log.size(), (size_t)cap);
+	for (int i = 0; i < *nlog; i++) log[i] = M.log[i];
+	return nfused;
+}
+
+int orc_fuse_sim3(const oracle_frame_view* f, const oracle_camera* cam, const oracle_sim3* S, float lsf, const oracle_sim3_point* pts,
+                  const uint8_t* pt_desc, int npts, float th, int32_t* kf_mp, int32_t* nobs, uint8_t* bad, int32_t* replace, int32_t* log, int cap,
+                  int* nlog)
+{
+	const Grid g = make_grid(f);
+	const float invs = 1.f / S->s;
+	float t[3], Ow[3];
+	for (int i = 0; i < 3; i++) t[i] = S->t[i] * invs;
+	invt(S->R, t, Ow);
+	// alreadyFound = keyframe->GetMapPoints() taken once, before the loop (:992)
+	std::vector<uint8_t> found((size_t)npts, 0);
+	for (int c = 0; c < f->n; c++)
+		if (kf_mp[c] >= 0 && !bad[kf_mp[c]]) found[kf_mp[c]] = 1;
+	std::vector<Best> best((size_t)npts, Best{ -1, 256 });
+	for (int i = 0; i < npts; i++)
+	{
+		float xc[3];
+		mul3(S->R, pts[i].xw, xc);
+		for (int k = 0; k < 3; k++) xc[k] += t[k];
+		best[i] = fuse_search(g, f, cam, xc, Ow, pts[i], pt_desc + (size_t)i * 32, lsf, th, false, nullptr);
+	}
+	MapModel M{ kf_mp, nobs, bad, std::vector<int>((size_t)npts, -1), {}, f };
+	for (int c = 0; c < f->n; c++)
+		if (kf_mp[c] >= 0) M.where[kf_mp[c]] = c;
+	int nfused = 0;
+	for (int i = 0; i < npts; i++)
+	{
+		replace[i] = -1;
+		if (bad[i] || found[i]) continue;                  // :1002-1003: isBad() is read at this point of the loop, alreadyFound is the snapshot
+		if (best[i].dist > TH_LOW) continue;
+		const int held = kf_mp[best[i].idx];
+		if (held >= 0) { if (!bad[held]) replace[i] = held; }
+		else M.add_observation(i, best[i].idx);
+		nfused++;
+	}
+	*nlog = (int)std::min<size_t>(M.log.size(), (size_t)cap);
+	for (int i = 0; i < *nlog; i++) log[i] = M.log[i];
+	return nfused;
+}
+
+int orc_search_by_sim3(const oracle_frame_view* f1, const oracle_camera* cam1, const oracle_pose* pose1, float lsf1, const oracle_frame_view* f2,
+                       const oracle_camera* cam2, const oracle_pose* pose2, float lsf2, const oracle_sim3* S12, float th, const oracle_kf_point* pts1,
+                       const uint8_t* desc1, const oracle_kf_point* pts2, const uint8_t* desc2, int32_t* matches12)
+{
+	const Grid g1 = make_grid(f1), g2 = make_grid(f2);
+	const int N1 = f1->n, N2 = f2->n;
+	// S21 = S12.Inverse() (include/Sim3.h:42-47)
+	float R21[9], t21[3], sR12[9], sR21[9];
+	const float is12 = 1.f / S12->s, nis = -is12;
+	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R21[r * 3 + c] = S12->R[c * 3 + r];
+	for (int i = 0; i < 3; i++) { float s = 0; for (int k = 0; k < 3; k++) s += (R21[i * 3 + k] * nis) * S12->t[k]; t21[i] = s; }
+	for (int k = 0; k < 9; k++) { sR12[k] = S12->R[k] * S12->s; sR21[k] = R21[k] * is12; }
+	// alreadyMatched (:1109-1121): flags bit1 of a kf1 point = matches12 holds kf2's point (i1 * 7) % N2 on entry
+	std::vector<uint8_t> am1((size_t)N1, 0), am2((size_t)N2, 0);
+	for (int i = 0; i < N1; i++)
+		if (pts1[i].flags & 2) { am1[i] = 1; am2[(size_t)((i * 7) % N2)] = 1; }
+	auto direction = [&](const oracle_frame_view* from, const oracle_pose* pf, const oracle_kf_point* pts, const uint8_t* desc, const std::vector<uint8_t>& am,
+	                     const float* sR, const float* t, const Grid& gt, const oracle_frame_view* to, const oracle_camera* cam, float lsf) {
+		std::vector<int> match((size_t)from->n, -1);
+		for (int i = 0; i < from->n; i++)
+		{
+			if (!(pts[i].flags & (1 | 4)) || am[i] || (pts[i].flags & 4)) continue;     // null, already matched, bad
+			float xa[3], xb[3];
+			mul3(pf->R, pts[i].xw, xa);
+			for (int k = 0; k < 3; k++) xa[k] += pf->t[k];
+			mul3(sR, xa, xb);
+			for (int k = 0; k < 3; k++) xb[k] += t[k];
+			if (xb[2] < 0.f) continue;
+			const float invZ = 1.f / xb[2];
+			const float u = invZ * cam->fx * xb[0] + cam->cx, v = invZ * cam->fy * xb[1] + cam->cy;
+			if (!in_image(to, u, v)) continue;
+			const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;
+			const float dist3D = norm3(xb);
+			if (dist3D < minDistance || dist3D > maxDistance) continue;
+			const int ps = predict_scale(pts[i].max_distance, dist3D, lsf, to->nlevels);
+			const Best b = best_in_window(gt, to, u, v, th * to->scale_factors[ps], ps - 1, ps, desc + (size_t)i * 32, false, 0.f, nullptr);
+			if (b.dist <= TH_HIGH) match[i] = b.idx;
+		}
+		return match;
+	};
+	const std::vector<int> m1 = direction(f1, pose1, pts1, desc1, am1, sR21, t21, g2, f2, cam2, lsf2);
+	const std::vector<int> m2 = direction(f2, pose2, pts2, desc2, am2, sR12, S12->t, g1, f1, cam1, lsf1);
+	int nfound = 0;
+	for (int i = 0; i < N1; i++)
+	{
+		matches12[i] = am1[i] ? (i * 7) % N2 : -1;
+		const int idx2 = m1[i];
+		if (idx2 >= 0 && m2[idx2] == i) { matches12[i] = idx2; nfound++; }
+	}
+	return nfound;
+}
+
+int orc_search_for_triangulation(const oracle_frame_view* f1, const oracle_feature_vector* fv1, const uint8_t* has1, const oracle_frame_view* f2,
+                                 const oracle_feature_vector* fv2, const uint8_t* has2, const float* F, const float* ep2, const float* sigma_sq2,
+                                 int only_stereo, int check_ori, int32_t* matches12)
+{
+	for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+	int nmatches = 0;
+	std::vector<std::pair<int, int>> tmp;
+	for (int a = 0, b = 0; a < fv1->nnodes && b < fv2->nnodes;)
+	{
+		if (fv1->node_ids[a] < fv2->node_ids[b]) { a++; continue; }
+		if (fv1->node_ids[a] > fv2->node_ids[b]) { b++; continue; }
+		for (int j = fv1->start[a]; j < fv1->start[a + 1]; j++)
+		{
+			const int idx1 = (int)fv1->indices[j];
+			if (has1[idx1]) continue;
+			const bool stereo1 = f1->uright && f1->uright[idx1] >= 0;
+			if (only_stereo && !stereo1) continue;
+			const oracle_keypoint& k1 = f1->kps_un[idx1];
+			const float la = k1.x * F[0] + k1.y * F[3] + F[6];
+			const float lb = k1.x * F[1] + k1.y * F[4] + F[7];
+			const float lc = k1.x * F[2] + k1.y * F[5] + F[8];
+			int bestDist = TH_LOW, bestIdx2 = -1;
+			for (int q = fv2->start[b]; q < fv2->start[b + 1]; q++)
+			{
+				const int idx2 = (int)fv2->indices[q];
+				if (has2[idx2]) continue;                  // matched2 is never set in this fork
+				const bool stereo2 = f2->uright && f2->uright[idx2] >= 0;
+				if (only_stereo && !stereo2) continue;
+				const int dist = hamming256(f1->desc + (size_t)idx1 * 32, f2->desc + (size_t)idx2 * 32);
+				if (dist > TH_LOW || dist > bestDist) continue;
+				const oracle_keypoint& k2 = f2->kps_un[idx2];
+				if (!stereo1 && !stereo2)
+				{
+					const float dx = ep2[0] - k2.x, dy = ep2[1] - k2.y;
+					if (dx * dx + dy * dy < 100 * f2->scale_factors[k2.octave]) continue;
+				}
+				const float num = la * k2.x + lb * k2.y + lc;
+				const float den = la * la + lb * lb;
+				if (den == 0) continue;
+				const float dsqr = num * num / den;
+				if (dsqr < 3.84 * sigma_sq2[k2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+			}
+			if (bestIdx2 >= 0)
+			{
+				matches12[idx1] = bestIdx2;
+				nmatches++;
+				if (check_ori) tmp.emplace_back(bestIdx2, idx1);
+			}
+		}
+		a++; b++;
+	}
+	if (check_ori)
+	{
+		std::vector<int> erased;
+		nmatches = check_orientation(tmp, &f2->kps_un[0].angle, sizeof(oracle_keypoint), &f1->kps_un[0].angle, sizeof(oracle_keypoint), erased);
+		for (int i2 : erased) matches12[i2] = -1;
+	}
+	return nmatches;
+}
+
 }  // extern "C"

@@ -166,6 +166,29 @@ double ORACLE_FN(time_search_last_frame)(const oracle_frame_view* cur, const ora
 int ORACLE_FN(search_for_initialization)(const oracle_frame_view* f1, const oracle_frame_view* f2, float* prev_matched, int32_t* matches12,
                                          int window, float nnratio, int check_orientation);
 
+// ---- the matchers of local mapping / loop closing whose per-point search is independent (second half) ----
+// One-key-frame model of the map state Fuse mutates (see ref_guided_decl.h): kf_mp[N] = point index held by a keypoint or -1 (in/out),
+// nobs / bad / in_kf per point (in/out). log (cap ints, out): the mutations in order as triples (1, point, other point) = Replace,
+// (2, point, keypoint) = AddObservation + AddMapPoint; *nlog = ints written. Returns nfused.
+int ORACLE_FN(fuse)(const oracle_frame_view* kf, const oracle_camera* cam, const oracle_pose* pose, float log_scale_factor, const float* inv_sigma_sq,
+                    const oracle_sim3_point* pts, const uint8_t* pt_desc, int npts, float th, int32_t* kf_mp, int32_t* nobs, uint8_t* bad,
+                    uint8_t* in_kf, int32_t* log, int cap, int* nlog);
+// Fuse(keyframe, Scw, mappoints, th, replacePoints): replace[npts] out = point index held by the matched keypoint or -1
+int ORACLE_FN(fuse_sim3)(const oracle_frame_view* kf, const oracle_camera* cam, const oracle_sim3* Scw, float log_scale_factor,
+                         const oracle_sim3_point* pts, const uint8_t* pt_desc, int npts, float th, int32_t* kf_mp, int32_t* nobs, uint8_t* bad,
+                         int32_t* replace, int32_t* log, int cap, int* nlog);
+// SearchBySim3: pts1 / pts2 one per keypoint (flags bit0 = map point present && !bad; bit1 = already in matches12 on entry, with
+// GetIndexInKeyFrame(kf2) = its own index... see the wrapper). matches12[n1] out = keypoint of kf2 or -1. Returns nfound.
+int ORACLE_FN(search_by_sim3)(const oracle_frame_view* kf1, const oracle_camera* cam1, const oracle_pose* pose1, float lsf1,
+                              const oracle_frame_view* kf2, const oracle_camera* cam2, const oracle_pose* pose2, float lsf2, const oracle_sim3* S12,
+                              float th, const oracle_kf_point* pts1, const uint8_t* desc1, const oracle_kf_point* pts2, const uint8_t* desc2,
+                              int32_t* matches12);
+// SearchForTriangulation: has1 / has2 per keypoint = GetMapPoint(idx) != NULL; F12 row-major; the epipole is computed by the reference
+// text from pose2 / cam2 / Ow1 when ep2 == NULL (ref library only), else taken as given. matches12[n1] out. Returns nmatches.
+int ORACLE_FN(search_for_triangulation)(const oracle_frame_view* kf1, const oracle_feature_vector* fv1, const uint8_t* has1,
+                                        const oracle_frame_view* kf2, const oracle_feature_vector* fv2, const uint8_t* has2, const float* F12,
+                                        const float* ep2, const float* sigma_sq2, int only_stereo, int check_orientation, int32_t* matches12);
+
 // ---- bag-of-words transform: ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> ----
 // loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.cpp:21-90); NULL when the file is rejected
 void* ORACLE_FN(voc_load_text)(const char* path);

@@ -10,6 +10,9 @@
 //   src/ORBmatcher.cc:614-694                  SearchForInitialization                          — monocular initialisation
 //   src/ORBmatcher.cc:1279-1362                SearchByProjection(currFrame, lastFrame, th, m)  — motion-model tracking
 //   src/ORBmatcher.cc:1364-1447                SearchByProjection(frame, keyframe, found, th, d) — relocalisation
+//   src/ORBmatcher.cc:384-404, 768-866         CheckDistEpipolarLine, SearchForTriangulation      — local mapping
+//   src/ORBmatcher.cc:868-980, 982-1088        Fuse x2                                            — local mapping, loop closing
+//   src/ORBmatcher.cc:1090-1277                SearchBySim3                                       — loop closing
 //   src/MapPoint.cc:382-392, 405-414; src/Frame.cc:203-206   distance invariance, PredictScale, GetCameraCenter
 // compiles by line range (oracle/Makefile, rule guided_gen.cc) with the reference's own include/Point.h,
 // include/CameraParameters.h, include/CameraPose.h and include/CameraProjection.h. The real Frame/MapPoint/KeyFrame drag
@@ -47,6 +50,18 @@ struct MapPoint
 	int PredictScale(float dist, const KeyFrame* keyframe) const;   // src/MapPoint.cc:394-403
 	Vec3D normal;
 	Vec3D GetNormal() const { return normal; }                      // src/MapPoint.cc:97-101
+
+	// what Fuse and SearchBySim3 call besides (include/MapPoint.h:52-60, 70-72): a one-key-frame model of the observation graph, enough
+	// to drive every branch of src/ORBmatcher.cc:876, 956-976, 1069-1084, 1109-1121; each mutation is appended to `actions` as
+	// (kind, this point, other point or keypoint index): 1 = this->Replace(other), 2 = this->AddObservation(kf, idx)
+	int id = -1;
+	const KeyFrame* inKeyFrame = nullptr;
+	int indexInKeyFrame = -1;
+	std::vector<int>* actions = nullptr;
+	bool IsInKeyFrame(const KeyFrame* kf) const { return inKeyFrame == kf; }
+	int GetIndexInKeyFrame(const KeyFrame* kf) const { return inKeyFrame == kf ? indexInKeyFrame : -1; }
+	void AddObservation(KeyFrame* kf, size_t idx);
+	void Replace(MapPoint* other);
 
 	Point3D GetWorldPos() const { return worldPos; }
 	int Observations() const { return nobs; }
@@ -96,7 +111,49 @@ struct KeyFrame
 	FeaturesGrid grid;
 	std::vector<size_t> GetFeaturesInArea(float x, float y, float r) const { return grid.GetFeaturesInArea(x, y, r); }
 	bool IsInImage(float x, float y) const { return imageBounds.Contains(x, y); }
+	// what Fuse x2, SearchBySim3 and SearchForTriangulation read or change besides (include/KeyFrame.h:60-62, 93-100, 131; src/KeyFrame.cc:76-92, 188-196)
+	CameraPose pose;
+	std::vector<float> uright;
+	CameraPose GetPose() const { return pose; }
+	Point3D GetCameraCenter() const { return pose.Invt(); }
+	MapPoint* GetMapPoint(size_t idx) const { return mappoints[idx]; }
+	void AddMapPoint(MapPoint* mp, size_t idx) { mappoints[idx] = mp; }
+	std::set<MapPoint*> GetMapPoints() const
+	{
+		std::set<MapPoint*> s;
+		for (MapPoint* mp : mappoints)
+			if (mp && !mp->isBad()) s.insert(mp);
+		return s;
+	}
 };
+
+// src/MapPoint.cc:103-121 (AddObservation: +2 observations for a stereo keypoint, +1 otherwise) and :193-240 (Replace: this point goes bad,
+// its observation moves to `other` unless `other` is already in that key frame, in which case the key frame's slot is cleared), for the
+// one key frame of the model
+inline void MapPoint::AddObservation(KeyFrame* kf, size_t idx)
+{
+	if (actions) { actions->push_back(2); actions->push_back(id); actions->push_back((int)idx); }
+	inKeyFrame = kf; indexInKeyFrame = (int)idx;
+	nobs += kf->uright.size() > idx && kf->uright[idx] >= 0 ? 2 : 1;
+}
+inline void MapPoint::Replace(MapPoint* other)
+{
+	if (actions) { actions->push_back(1); actions->push_back(id); actions->push_back(other->id); }
+	if (other == this) return;
+	bad = true;
+	if (inKeyFrame)
+	{
+		KeyFrame* kf = const_cast<KeyFrame*>(inKeyFrame);
+		if (!other->IsInKeyFrame(kf))
+		{
+			kf->mappoints[(size_t)indexInKeyFrame] = other;
+			other->inKeyFrame = kf; other->indexInKeyFrame = indexInKeyFrame;
+			other->nobs += nobs;
+		}
+		else
+			kf->mappoints[(size_t)indexInKeyFrame] = nullptr;
+	}
+}
 
 // include/ORBmatcher.h:47-104, the members compiled here
 class ORBmatcher
@@ -112,6 +169,11 @@ public:
 	int SearchByBoW(KeyFrame* keyframe1, KeyFrame* keyframe2, std::vector<MapPoint*>& matches12);
 	int SearchForInitialization(Frame& frame1, Frame& frame2, std::vector<cv::Point2f>& prevMatched, std::vector<int>& matches12,
 		int windowSize = 10);
+	int SearchForTriangulation(const KeyFrame* keyframe1, const KeyFrame* keyframe2, const cv::Mat& F12,
+		std::vector<std::pair<size_t, size_t>>& matchIds, bool onlyStereo);
+	int Fuse(KeyFrame* keyframe, const std::vector<MapPoint*>& mappoints, float th = 3.f);
+	int Fuse(KeyFrame* keyframe, const Sim3& Scw, const std::vector<MapPoint*>& mappoints, float th, std::vector<MapPoint*>& replacePoints);
+	int SearchBySim3(KeyFrame* keyframe1, KeyFrame* keyframe2, std::vector<MapPoint*>& matches12, const Sim3& S12, float th);
 
 private:
 	float fNNRatio_;

@@ -149,6 +149,16 @@ _SIGNATURES = {
     'orbx_frame_assign_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_Bounds), C.c_int, C.c_void_p]),
     'orbx_undistort_keypoints_device': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_Camera), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'orbx_frame_assign': (C.c_int, [C.c_void_p, C.POINTER(_FrameView)]),
+    'orbx_search_best_in_windows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'orbx_fuse': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                            C.c_void_p, C.c_void_p]),
+    'orbx_fuse_sim3': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p]),
+    'orbx_search_by_sim3': (C.c_int, [C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose), C.c_float, C.c_void_p, C.POINTER(_Camera), C.POINTER(_Pose),
+                                      C.c_float, C.POINTER(_Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_int)]),
+    'orbx_search_for_triangulation': (C.c_int, [C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p, C.c_void_p, C.POINTER(_FeatureVector), C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     'orbx_vocabulary_create': (C.c_int, [C.POINTER(_VocabularyDesc), C.c_int, C.POINTER(C.c_void_p)]),
     'orbx_vocabulary_load_text': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     'orbx_vocabulary_info': (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_int64)] * 2),
@@ -582,6 +592,70 @@ class ORBmatcher:
         _check(lib().orbx_search_by_bow(keyframe._h, C.byref(c1), _p(v1), frame._h, C.byref(c2), None if v2 is None else _p(v2), self.fNNRatio_,
                                         int(bool(self.checkOrientation_)), _p(m2), C.byref(n)))
         return n.value, m2[:frame.N]
+
+    @staticmethod
+    def _sim3(S):
+        out = _Sim3()
+        out.R[:] = [float(x) for x in np.asarray(S[0], np.float32).reshape(9)]
+        out.t[:] = [float(x) for x in np.asarray(S[1], np.float32).reshape(3)]
+        out.s = float(np.float32(S[2]))
+        return out
+
+    def FuseSearch(self, keyframe, camera, pose, logScaleFactor, invSigmaSq, mappoints, descriptors, th=3.0):
+        """The search half of Fuse(keyframe, mappoints, th) — src/ORBmatcher.cc:868-954. mappoints: SIM3_POINT_DTYPE records (flags bit 0 =
+        non-null and not bad). Returns (bestIdx, bestDist) per point; the caller replays :876 and :956-976 in order (see FuseApply)."""
+        pts = np.ascontiguousarray(mappoints).view(SIM3_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        sig = np.ascontiguousarray(invSigmaSq, np.float32)
+        bi = np.empty(max(len(pts), 1), np.int32); bd = np.empty(max(len(pts), 1), np.int32)
+        cam = _Camera(*[float(c) for c in camera]); P = _pose(pose)
+        _check(lib().orbx_fuse(keyframe._h, C.byref(cam), C.byref(P), float(np.float32(logScaleFactor)), _p(sig), _p(pts), _p(desc), len(pts),
+                               float(th), _p(bi), _p(bd)))
+        return bi[:len(pts)], bd[:len(pts)]
+
+    def FuseSim3Search(self, keyframe, camera, Scw, logScaleFactor, mappoints, descriptors, th=4.0):
+        """The search half of Fuse(keyframe, Scw, mappoints, th, replacePoints) — src/ORBmatcher.cc:982-1067."""
+        pts = np.ascontiguousarray(mappoints).view(SIM3_POINT_DTYPE)
+        desc = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        bi = np.empty(max(len(pts), 1), np.int32); bd = np.empty(max(len(pts), 1), np.int32)
+        cam = _Camera(*[float(c) for c in camera]); S = self._sim3(Scw)
+        _check(lib().orbx_fuse_sim3(keyframe._h, C.byref(cam), C.byref(S), float(np.float32(logScaleFactor)), _p(pts), _p(desc), len(pts), float(th),
+                                    _p(bi), _p(bd)))
+        return bi[:len(pts)], bd[:len(pts)]
+
+    def SearchBySim3(self, keyframe1, camera1, pose1, logScaleFactor1, keyframe2, camera2, pose2, logScaleFactor2, S12, th, mappoints1,
+                     descriptors1, mappoints2, descriptors2):
+        """SearchBySim3(kf1, kf2, matches12, S12, th) — src/ORBmatcher.cc:1090-1277. mappoints1/2: KF_POINT_DTYPE records, one per keypoint
+        (flags bit 0 = present, not already matched, not bad). Returns (nfound, matches12, match1, match2): matches12[i1] = keypoint of kf2."""
+        p1 = np.ascontiguousarray(mappoints1).view(KF_POINT_DTYPE); p2 = np.ascontiguousarray(mappoints2).view(KF_POINT_DTYPE)
+        d1 = np.ascontiguousarray(descriptors1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(descriptors2, np.uint8).reshape(-1, 32)
+        assert len(p1) == keyframe1.N and len(p2) == keyframe2.N
+        m1 = np.empty(max(keyframe1.N, 1), np.int32); m2 = np.empty(max(keyframe2.N, 1), np.int32); m12 = np.empty(max(keyframe1.N, 1), np.int32)
+        n = C.c_int()
+        c1 = _Camera(*[float(c) for c in camera1]); c2 = _Camera(*[float(c) for c in camera2])
+        P1 = _pose(pose1); P2 = _pose(pose2); S = self._sim3(S12)
+        _check(lib().orbx_search_by_sim3(keyframe1._h, C.byref(c1), C.byref(P1), float(np.float32(logScaleFactor1)), keyframe2._h, C.byref(c2),
+                                         C.byref(P2), float(np.float32(logScaleFactor2)), C.byref(S), float(th), _p(p1), _p(d1), _p(p2), _p(d2),
+                                         _p(m1), _p(m2), _p(m12), C.byref(n)))
+        return n.value, m12[:keyframe1.N], m1[:keyframe1.N], m2[:keyframe2.N]
+
+    def SearchForTriangulation(self, keyframe1, featureVector1, hasMapPoint1, keyframe2, featureVector2, hasMapPoint2, F12, epipole2, sigmaSq2,
+                               onlyStereo=False):
+        """SearchForTriangulation(kf1, kf2, F12, matchIds, onlyStereo) — src/ORBmatcher.cc:768-866. Returns (nmatches, matches12); matchIds of
+        the reference = [(idx1, matches12[idx1]) for idx1 in ascending order if matches12[idx1] >= 0]."""
+        def fv(t):
+            ids = np.ascontiguousarray(t[0], np.uint32); start = np.ascontiguousarray(t[1], np.int32); idx = np.ascontiguousarray(t[2], np.uint32)
+            return _FeatureVector(len(ids), ids.ctypes.data, start.ctypes.data, idx.ctypes.data), (ids, start, idx)
+        c1, k1 = fv(featureVector1)
+        c2, k2 = fv(featureVector2)
+        h1 = np.ascontiguousarray(hasMapPoint1, np.uint8); h2 = np.ascontiguousarray(hasMapPoint2, np.uint8)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); ep = np.ascontiguousarray(epipole2, np.float32).reshape(2)
+        sg = np.ascontiguousarray(sigmaSq2, np.float32)
+        m12 = np.empty(max(keyframe1.N, 1), np.int32)
+        n = C.c_int()
+        _check(lib().orbx_search_for_triangulation(keyframe1._h, C.byref(c1), _p(h1), keyframe2._h, C.byref(c2), _p(h2), _p(F), _p(ep), _p(sg),
+                                                   int(bool(onlyStereo)), int(bool(self.checkOrientation_)), _p(m12), C.byref(n)))
+        return n.value, m12[:keyframe1.N]
 
     def SearchForInitialization(self, frame1, frame2, prevMatched, windowSize=10):
         """src/ORBmatcher.cc:614-694. prevMatched: (N1, 2) float32, updated in place; returns (nmatches, matches12)."""

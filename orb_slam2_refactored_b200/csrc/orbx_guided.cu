@@ -1426,4 +1426,432 @@ orbx_status orbx_frame_last_stats(orbx_frame f, int* rounds, float* kernel_ms, f
 	return ORBX_OK;
 }
 
+
+// =====================================================================================================================================
+// Matchers whose per-point search does not depend on the other points (local mapping / loop closing):
+//   ORBmatcher::Fuse(keyframe, mappoints, th)                       src/ORBmatcher.cc:868-980
+//   ORBmatcher::Fuse(keyframe, Scw, mappoints, th, replacePoints)   src/ORBmatcher.cc:982-1088
+//   ORBmatcher::SearchBySim3(kf1, kf2, matches12, S12, th)          src/ORBmatcher.cc:1090-1277
+//   ORBmatcher::SearchForTriangulation(kf1, kf2, F12, ids, stereo)  src/ORBmatcher.cc:768-866 (+ CheckDistEpipolarLine :384-404)
+// In Fuse the map is mutated between points (Replace / AddObservation / AddMapPoint, :956-976), but what a point searches — projection,
+// window, scale gate, chi-square gate, best distance, first keypoint on ties — reads only the key frame's keypoints and the point itself,
+// so the search of all points runs at once and the caller replays :874-877 and :956-976 in order over (best_idx, best_dist).
+// SearchForTriangulation never sets matched2 in this fork (:780, :814), so every keypoint of key frame 1 is independent as well.
+// =====================================================================================================================================
+extern "C++" {
+namespace {
+
+struct BestWindow { float u, v, radius, ur; int min_level, max_level; int flags; int pad; };   // flags bit0 = search, bit1 = Fuse's chi-square gate
+
+// 8 lanes per point. A candidate's rank in GetFeaturesInArea's output order is (cell column, position in the column's record run), so
+// "smallest distance, first in that order" is the minimum of distance << 22 | column << 16 | position.
+__global__ void __launch_bounds__(256) k_best_in_windows(const GridDev G, const orbx_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+                                                         const float* __restrict__ uright, const BestWindow* __restrict__ win,
+                                                         const uint8_t* __restrict__ pt_desc, const int npts, const float* __restrict__ inv_sigma_sq,
+                                                         int2* __restrict__ out)
+{
+	const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+	if (i >= npts) return;
+	const unsigned gmask = 0xffu << (threadIdx.x & 24);
+	const BestWindow w = win[i];
+	uint32_t best = 0xffffffffu;
+	int besti = -1;
+	if (w.flags & 1)
+	{
+		const float x = w.u, y = w.v, r = w.radius;
+		const int mincx = max(__float2int_rd(G.invW * (x - r - G.b.minx)), 0);
+		const int maxcx = min(__float2int_ru(G.invW * (x + r - G.b.minx)), GRID_COLS - 1);
+		const int mincy = max(__float2int_rd(G.invH * (y - r - G.b.miny)), 0);
+		const int maxcy = min(__float2int_ru(G.invH * (y + r - G.b.miny)), GRID_ROWS - 1);
+		if (!(mincx >= GRID_COLS || maxcx < 0 || mincy >= GRID_ROWS || maxcy < 0))
+		{
+			const uint8_t* d1 = pt_desc + (size_t)i * 32;
+			for (int cx = mincx; cx <= maxcx; cx++)
+			{
+				const int a = G.cell_start[cx * GRID_ROWS + mincy], b = G.cell_start[cx * GRID_ROWS + maxcy + 1];
+				for (int p = a + sub; p < b; p += 8)
+				{
+					const int4 rec = G.rec[p];
+					if (!(fabsf(__int_as_float(rec.x) - x) < r && fabsf(__int_as_float(rec.y) - y) < r)) continue;   // src/Frame.cc:136-139
+					if (rec.w < w.min_level || rec.w > w.max_level) continue;                                       // :930-931, :1057-1058, :1175
+					if (w.flags & 2)
+					{
+						// chi-square gate of Fuse (:934-945): float products and sums in source order, compared in double
+						const float dx = __fsub_rn(x, __int_as_float(rec.x)), dy = __fsub_rn(y, __int_as_float(rec.y));
+						const float ur2 = uright[rec.z];
+						const float e2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+						const float is = inv_sigma_sq[rec.w];
+						if (ur2 >= 0.f)
+						{
+							const float dz = __fsub_rn(w.ur, ur2);
+							if ((double)__fmul_rn(__fadd_rn(e2, __fmul_rn(dz, dz)), is) > 7.8) continue;
+						}
+						else if ((double)__fmul_rn(e2, is) > 5.99) continue;
+					}
+					const uint32_t key = ((uint32_t)hamming256(d1, desc + (size_t)rec.z * 32) << 22) | ((uint32_t)(cx - mincx) << 16) | (uint32_t)min(p - a, 65535);
+					if (key < best) { best = key; besti = rec.z; }
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int d = 1; d < 8; d <<= 1)
+	{
+		const uint32_t ob = __shfl_xor_sync(gmask, best, d);
+		const int oi = __shfl_xor_sync(gmask, besti, d);
+		if (ob < best) { best = ob; besti = oi; }
+	}
+	if (sub == 0) out[i] = make_int2(besti, besti >= 0 ? (int)(best >> 22) : 256);
+}
+
+// SearchForTriangulation: one thread per keypoint of key frame 1 that has a vocabulary node in common with key frame 2; its candidates
+// are that node's features of key frame 2, scanned in order with the reference's `dist > TH_LOW || dist > bestDist` (a later candidate
+// at the same distance replaces an earlier one).
+struct TriArgs
+{
+	const orbx_keypoint* kps1; const uint8_t* desc1; const float* uright1;
+	const orbx_keypoint* kps2; const uint8_t* desc2; const float* uright2;
+	const int* item;             // [nitems][3]: idx1, first position in idx2 list, count
+	const uint32_t* idx2;
+	const uint8_t* has_mp2;
+	int nitems, only_stereo;
+	float F[9], ex, ey;
+	float sf2[16], sigma_sq2[16];
+	int* match;                  // [nitems] best idx2 or -1
+};
+__global__ void __launch_bounds__(128) k_triangulation_search(const TriArgs A)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= A.nitems) return;
+	const int idx1 = A.item[3 * t], first = A.item[3 * t + 1], cnt = A.item[3 * t + 2];
+	const bool stereo1 = A.uright1[idx1] >= 0.f;
+	if (A.only_stereo && !stereo1) { A.match[t] = -1; return; }         // :800-802
+	const orbx_keypoint k1 = A.kps1[idx1];
+	// epipolar line in the second image (:391-393), products and sums in source order
+	const float a = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[0]), __fmul_rn(k1.y, A.F[3])), A.F[6]);
+	const float b = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[1]), __fmul_rn(k1.y, A.F[4])), A.F[7]);
+	const float c = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, A.F[2]), __fmul_rn(k1.y, A.F[5])), A.F[8]);
+	const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+	int bestDist = TH_LOW, bestIdx2 = -1;
+	for (int j = 0; j < cnt; j++)
+	{
+		const int idx2 = (int)A.idx2[first + j];
+		if (A.has_mp2[idx2]) continue;                                   // :814 (matched2 is never set)
+		const bool stereo2 = A.uright2[idx2] >= 0.f;
+		if (A.only_stereo && !stereo2) continue;
+		const int dist = hamming256(A.desc1 + (size_t)idx1 * 32, A.desc2 + (size_t)idx2 * 32);
+		if (dist > TH_LOW || dist > bestDist) continue;                  // :823
+		const orbx_keypoint k2 = A.kps2[idx2];
+		if (!stereo1 && !stereo2)
+		{
+			const float dx = __fsub_rn(A.ex, k2.x), dy = __fsub_rn(A.ey, k2.y);
+			if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, A.sf2[k2.octave])) continue;   // :828-833
+		}
+		// CheckDistEpipolarLine (:395-403)
+		const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, k2.x), __fmul_rn(b, k2.y)), c);
+		if (den == 0.f) continue;
+		const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+		if ((double)dsqr < __dmul_rn(3.84, (double)A.sigma_sq2[k2.octave])) { bestIdx2 = idx2; bestDist = dist; }
+	}
+	A.match[t] = bestIdx2;
+}
+
+// CheckOrientation (src/ORBmatcher.cc:249-309) on the host, for the matchers whose matches come back to the host anyway. std::sort is
+// libstdc++'s own here (the host side is compiled by the GCC the reference's behaviour is pinned to), applied to 30 items with the
+// reference's comparator: the same comparisons, hence the same order among equal sizes. pairs = (i1, i2): angle1[i1] - angle2[i2].
+int orbx_check_orientation_host(const float* angle1, const float* angle2, const std::vector<std::pair<int, int>>& pairs, int32_t* status, int n)
+{
+	const float factor = 1.f / HISTO_LENGTH;
+	std::vector<int> hist[HISTO_LENGTH];
+	for (const auto& m : pairs)
+	{
+		float diff = angle1[m.first] - angle2[m.second];
+		if (diff < 0) diff += 360;
+		int bin = (int)std::nearbyint(factor * diff);                   // cvRound(float): round half to even
+		if (bin == HISTO_LENGTH) bin = 0;
+		if (bin < 0 || bin >= HISTO_LENGTH) continue;                   // CV_Assert in the reference
+		hist[bin].push_back(m.second);
+	}
+	std::sort(std::begin(hist), std::end(hist), [](const std::vector<int>& lhs, const std::vector<int>& rhs) { return lhs.size() > rhs.size(); });
+	const size_t max1 = hist[0].size(), max2 = hist[1].size(), max3 = hist[2].size();
+	int eraseBin = 3;
+	if (max2 < 0.1 * max1) eraseBin = 1;
+	else if (max3 < 0.1 * max1) eraseBin = 2;
+	int reduction = 0;
+	for (int bin = eraseBin; bin < HISTO_LENGTH; bin++)
+		for (int i2 : hist[bin]) { status[i2] = -1; reduction++; }
+	return (int)pairs.size() - reduction;
+}
+
+// H2D (windows + descriptors [+ invSigmaSq]) -> kernel -> D2H on f's stream, through f's staging buffers
+orbx_status best_in_windows(orbx_frame_s* f, const std::vector<BestWindow>& win, const uint8_t* pt_desc, const float* inv_sigma_sq, int32_t* best_idx,
+                            int32_t* best_dist)
+{
+	const int npts = (int)win.size();
+	if (npts == 0) return ORBX_OK;
+	GCU(cudaSetDevice(f->device));
+	const size_t o_desc = up16((size_t)npts * sizeof(BestWindow)), o_sig = o_desc + up16((size_t)npts * 32), in_bytes = o_sig + 64;
+	const size_t out_bytes = (size_t)npts * sizeof(int2);
+	GCU(f->ensure_staging(in_bytes, out_bytes));
+	memcpy(f->h_in, win.data(), (size_t)npts * sizeof(BestWindow));
+	memcpy(f->h_in + o_desc, pt_desc, (size_t)npts * 32);
+	float sig[16] = {};
+	if (inv_sigma_sq) for (int l = 0; l < f->nlevels && l < 16; l++) sig[l] = inv_sigma_sq[l];
+	memcpy(f->h_in + o_sig, sig, sizeof(sig));
+	GCU(cudaMemcpyAsync(f->d_in.p, f->h_in, in_bytes, cudaMemcpyHostToDevice, f->st));
+	GCU(cudaEventRecord(f->ev0, f->st));
+	k_best_in_windows<<<(npts * 8 + 255) / 256, 256, 0, f->st>>>(f->grid(), f->kps.p, f->desc.p, f->uright.p, reinterpret_cast<const BestWindow*>(f->d_in.p),
+	                                                             f->d_in.p + o_desc, npts, reinterpret_cast<const float*>(f->d_in.p + o_sig),
+	                                                             reinterpret_cast<int2*>(f->d_out.p));
+	GCU(cudaGetLastError());
+	GCU(cudaEventRecord(f->ev1, f->st));
+	GCU(cudaMemcpyAsync(f->h_out, f->d_out.p, out_bytes, cudaMemcpyDeviceToHost, f->st));
+	GCU(cudaStreamSynchronize(f->st));
+	cudaEventElapsedTime(&f->last_kernel_ms, f->ev0, f->ev1);
+	const int2* r = reinterpret_cast<const int2*>(f->h_out);
+	for (int i = 0; i < npts; i++) { best_idx[i] = r[i].x; best_dist[i] = r[i].y; }
+	return ORBX_OK;
+}
+
+// cv::Matx arithmetic in the reference's operation order (products accumulate from 0 in k order; no contraction on the host)
+inline void matx_mul(const float* R, const float* x, float* y) { for (int r = 0; r < 3; r++) { float s = 0.f; for (int k = 0; k < 3; k++) s += R[r * 3 + k] * x[k]; y[r] = s; } }
+inline void pose_invt(const float* R, const float* t, float* o) { for (int i = 0; i < 3; i++) { float s = 0.f; for (int k = 0; k < 3; k++) s += (R[k * 3 + i] * -1) * t[k]; o[i] = s; } }   // -R.t() * t
+inline float norm3(const float* v) { double ss = 0; for (int k = 0; k < 3; k++) ss += (double)v[k] * (double)v[k]; return (float)std::sqrt(ss); }   // cv::norm
+inline int predict_scale(float max_distance, float dist, float log_scale_factor, int nlevels)     // src/MapPoint.cc:394-403
+{
+	const float ratio = max_distance / dist;
+	const int scale = (int)std::ceil(std::log((double)ratio) / log_scale_factor);
+	return std::max(0, std::min(scale, nlevels - 1));
+}
+inline bool in_image(const orbx_frame_s* f, float u, float v) { return u >= f->b.minx && u < f->b.maxx && v >= f->b.miny && v < f->b.maxy; }
+
+// the projection / distance / viewing-angle / scale part shared by the two Fuse variants (:879-919, :1005-1046); xc = camera coordinates
+inline void fuse_window(const orbx_frame_s* f, const orbx_camera* cam, const float* xc, const float* Ow, const orbx_sim3_point& p, float log_scale_factor,
+                        float th, bool gate, BestWindow& w)
+{
+	w = BestWindow{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0 };
+	if (xc[2] < 0.f) return;
+	const float invZ = 1.f / xc[2];
+	const float u = invZ * cam->fx * xc[0] + cam->cx, v = invZ * cam->fy * xc[1] + cam->cy;
+	if (!in_image(f, u, v)) return;
+	const float ur = u - cam->bf / xc[2];                               // DepthToDisparity
+	const float maxDistance = 1.2f * p.max_distance, minDistance = 0.8f * p.min_distance;   // src/MapPoint.cc:382-392
+	float PO[3];
+	for (int k = 0; k < 3; k++) PO[k] = p.xw[k] - Ow[k];
+	const float dist3D = norm3(PO);
+	if (dist3D < minDistance || dist3D > maxDistance) return;
+	float dot = 0.f;
+	for (int k = 0; k < 3; k++) dot += PO[k] * p.normal[k];
+	if (dot < 0.5 * dist3D) return;                                     // compared in double
+	const int ps = predict_scale(p.max_distance, dist3D, log_scale_factor, f->nlevels);
+	w.u = u; w.v = v; w.ur = ur;
+	w.radius = th * f->sf[ps];
+	w.min_level = ps - 1; w.max_level = ps;
+	w.flags = gate ? 3 : 1;
+}
+
+}  // namespace
+}  // extern "C++"
+
+orbx_status orbx_search_best_in_windows(orbx_frame f, const orbx_best_window* windows, const uint8_t* pt_desc, int npts, const float* inv_sigma_sq,
+                                        int32_t* best_idx, int32_t* best_dist)
+{
+	if (!f || npts < 0 || (npts > 0 && (!windows || !pt_desc || !best_idx || !best_dist))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	std::vector<BestWindow> win((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		const orbx_best_window& s = windows[i];
+		if ((s.flags & 2) && !inv_sigma_sq) return orbx_fail(ORBX_ERR_INVALID, "the chi-square gate needs invSigmaSq");
+		win[i] = BestWindow{ s.u, s.v, s.radius, s.ur, s.min_level, s.max_level, s.flags & 3, 0 };
+	}
+	return best_in_windows(f, win, pt_desc, inv_sigma_sq, best_idx, best_dist);
+}
+
+orbx_status orbx_fuse(orbx_frame f, const orbx_camera* cam, const orbx_pose* pose, float log_scale_factor, const float* inv_sigma_sq,
+                      const orbx_sim3_point* pts, const uint8_t* pt_desc, int npts, float th, int32_t* best_idx, int32_t* best_dist)
+{
+	if (!f || !cam || !pose || !inv_sigma_sq || npts < 0 || (npts > 0 && (!pts || !pt_desc || !best_idx || !best_dist))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (!(log_scale_factor > 0.f)) return orbx_fail(ORBX_ERR_INVALID, "logScaleFactor must be positive");
+	float Ow[3];
+	pose_invt(pose->R, pose->t, Ow);                                    // keyframe->GetCameraCenter()
+	std::vector<BestWindow> win((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		win[i] = BestWindow{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0 };
+		if (!(pts[i].flags & 1)) continue;                              // null or bad (:876-877); IsInKeyFrame is the caller's, at replay time
+		float xc[3];
+		matx_mul(pose->R, pts[i].xw, xc);
+		for (int k = 0; k < 3; k++) xc[k] += pose->t[k];
+		fuse_window(f, cam, xc, Ow, pts[i], log_scale_factor, th, true, win[i]);
+	}
+	return best_in_windows(f, win, pt_desc, inv_sigma_sq, best_idx, best_dist);
+}
+
+orbx_status orbx_fuse_sim3(orbx_frame f, const orbx_camera* cam, const orbx_sim3* Scw, float log_scale_factor, const orbx_sim3_point* pts,
+                           const uint8_t* pt_desc, int npts, float th, int32_t* best_idx, int32_t* best_dist)
+{
+	if (!f || !cam || !Scw || npts < 0 || (npts > 0 && (!pts || !pt_desc || !best_idx || !best_dist))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (!(log_scale_factor > 0.f)) return orbx_fail(ORBX_ERR_INVALID, "logScaleFactor must be positive");
+	const float invs = 1.f / Scw->s;                                    // pose(Scw.R(), Scw.Invs() * Scw.t()), :987
+	float t[3], Ow[3];
+	for (int i = 0; i < 3; i++) t[i] = Scw->t[i] * invs;
+	pose_invt(Scw->R, t, Ow);
+	std::vector<BestWindow> win((size_t)npts);
+	for (int i = 0; i < npts; i++)
+	{
+		win[i] = BestWindow{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0 };
+		if (!(pts[i].flags & 1)) continue;                              // bad or already in the key frame (:1002-1003)
+		float xc[3];
+		matx_mul(Scw->R, pts[i].xw, xc);
+		for (int k = 0; k < 3; k++) xc[k] += t[k];
+		fuse_window(f, cam, xc, Ow, pts[i], log_scale_factor, th, false, win[i]);
+	}
+	return best_in_windows(f, win, pt_desc, nullptr, best_idx, best_dist);
+}
+
+orbx_status orbx_search_by_sim3(orbx_frame f1, const orbx_camera* cam1, const orbx_pose* pose1, float log_scale_factor1, orbx_frame f2,
+                                const orbx_camera* cam2, const orbx_pose* pose2, float log_scale_factor2, const orbx_sim3* S12, float th,
+                                const orbx_keyframe_point* pts1, const uint8_t* desc1, const orbx_keyframe_point* pts2, const uint8_t* desc2,
+                                int32_t* match1, int32_t* match2, int32_t* matches12, int* nfound)
+{
+	if (!f1 || !f2 || !cam1 || !cam2 || !pose1 || !pose2 || !S12 || !matches12) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if ((f1->n > 0 && (!pts1 || !desc1)) || (f2->n > 0 && (!pts2 || !desc2))) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if (!(log_scale_factor1 > 0.f) || !(log_scale_factor2 > 0.f)) return orbx_fail(ORBX_ERR_INVALID, "logScaleFactor must be positive");
+	// S21 = S12.Inverse() = Sim3(R^T, -(1/s) * R^T * t, 1/s) (include/Sim3.h:42-47); Map(x) = (s * R) * x + t
+	float R21[9], t21[3];
+	const float is12 = 1.f / S12->s, nis = -is12;
+	for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R21[r * 3 + c] = S12->R[c * 3 + r];
+	for (int i = 0; i < 3; i++) { float s = 0.f; for (int k = 0; k < 3; k++) s += (R21[i * 3 + k] * nis) * S12->t[k]; t21[i] = s; }
+	float sR12[9], sR21[9];
+	for (int k = 0; k < 9; k++) { sR12[k] = S12->R[k] * S12->s; sR21[k] = R21[k] * is12; }
+	auto direction = [&](orbx_frame_s* from, const orbx_pose* pfrom, const orbx_keyframe_point* pts, const uint8_t* desc, const float* sR, const float* t,
+	                     orbx_frame_s* to, const orbx_camera* cam_to, float lsf_to, std::vector<int32_t>& match) -> orbx_status {
+		const int n = from->n;
+		std::vector<BestWindow> win((size_t)n);
+		for (int i = 0; i < n; i++)
+		{
+			BestWindow& w = win[i];
+			w = BestWindow{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0 };
+			if (!(pts[i].flags & 1)) continue;                          // null, already matched or bad (:1130, :1197)
+			float xa[3], xb[3];
+			matx_mul(pfrom->R, pts[i].xw, xa);
+			for (int k = 0; k < 3; k++) xa[k] += pfrom->t[k];           // proj.WorldToCamera
+			matx_mul(sR, xa, xb);
+			for (int k = 0; k < 3; k++) xb[k] += t[k];                  // S.Map
+			if (xb[2] < 0.f) continue;
+			const float invZ = 1.f / xb[2];
+			const float u = invZ * cam_to->fx * xb[0] + cam_to->cx, v = invZ * cam_to->fy * xb[1] + cam_to->cy;
+			if (!in_image(to, u, v)) continue;
+			const float maxDistance = 1.2f * pts[i].max_distance, minDistance = 0.8f * pts[i].min_distance;
+			const float dist3D = norm3(xb);
+			if (dist3D < minDistance || dist3D > maxDistance) continue;
+			const int ps = predict_scale(pts[i].max_distance, dist3D, lsf_to, to->nlevels);
+			w.u = u; w.v = v; w.radius = th * to->sf[ps];
+			w.min_level = ps - 1; w.max_level = ps; w.flags = 1;
+		}
+		std::vector<int32_t> dist((size_t)n);
+		match.assign((size_t)n, -1);
+		if (orbx_status s = best_in_windows(to, win, desc, nullptr, match.data(), dist.data())) return s;
+		for (int i = 0; i < n; i++)
+			if (!(dist[i] <= TH_HIGH)) match[i] = -1;                   // :1187, :1254
+		return ORBX_OK;
+	};
+	std::vector<int32_t> m1, m2;
+	if (orbx_status s = direction(f1, pose1, pts1, desc1, sR21, t21, f2, cam2, log_scale_factor2, m1)) return s;
+	if (orbx_status s = direction(f2, pose2, pts2, desc2, sR12, S12->t, f1, cam1, log_scale_factor1, m2)) return s;
+	int found = 0;
+	for (int i1 = 0; i1 < f1->n; i1++)                                  // agreement, :1260-1274
+	{
+		matches12[i1] = -1;
+		const int idx2 = m1[i1];
+		if (idx2 >= 0 && m2[idx2] == i1) { matches12[i1] = idx2; found++; }
+	}
+	if (match1) memcpy(match1, m1.data(), (size_t)f1->n * 4);
+	if (match2) memcpy(match2, m2.data(), (size_t)f2->n * 4);
+	if (nfound) *nfound = found;
+	return ORBX_OK;
+}
+
+orbx_status orbx_search_for_triangulation(orbx_frame f1, const orbx_feature_vector* fv1, const uint8_t* has_mp1, orbx_frame f2,
+                                          const orbx_feature_vector* fv2, const uint8_t* has_mp2, const float* F12, const float* epipole2,
+                                          const float* sigma_sq2, int only_stereo, int check_orientation, int32_t* matches12, int* nmatches)
+{
+	if (!f1 || !f2 || !fv1 || !fv2 || !F12 || !epipole2 || !sigma_sq2 || !matches12) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	if ((f1->n > 0 && !has_mp1) || (f2->n > 0 && !has_mp2)) return orbx_fail(ORBX_ERR_INVALID, "bad argument");
+	GCU(cudaSetDevice(f1->device));
+	// FeatureVectorIterator (:406-450): nodes present in both vectors, ascending; items in the order the reference visits idx1
+	std::vector<int> items;
+	for (int a = 0, b = 0; a < fv1->nnodes && b < fv2->nnodes;)
+	{
+		if (fv1->node_ids[a] == fv2->node_ids[b])
+		{
+			for (int j = fv1->start[a]; j < fv1->start[a + 1]; j++)
+			{
+				const uint32_t idx1 = fv1->indices[j];
+				if (idx1 >= (uint32_t)f1->n) return orbx_fail(ORBX_ERR_INVALID, "feature index outside key frame 1");
+				if (has_mp1[idx1]) continue;                            // :796-797
+				items.push_back((int)idx1); items.push_back(fv2->start[b]); items.push_back(fv2->start[b + 1] - fv2->start[b]);
+			}
+			a++; b++;
+		}
+		else if (fv1->node_ids[a] < fv2->node_ids[b]) a++;
+		else b++;
+	}
+	const int nitems = (int)items.size() / 3, n2items = fv2->nnodes ? fv2->start[fv2->nnodes] : 0;
+	for (int j = 0; j < n2items; j++)
+		if (fv2->indices[j] >= (uint32_t)f2->n) return orbx_fail(ORBX_ERR_INVALID, "feature index outside key frame 2");
+	for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+	if (nmatches) *nmatches = 0;
+	if (nitems == 0) return ORBX_OK;
+	const size_t o_idx2 = up16((size_t)nitems * 12), o_mp2 = o_idx2 + up16((size_t)n2items * 4), in_bytes = o_mp2 + up16((size_t)f2->n);
+	GCU(f1->ensure_staging(in_bytes, (size_t)nitems * 4));
+	memcpy(f1->h_in, items.data(), (size_t)nitems * 12);
+	memcpy(f1->h_in + o_idx2, fv2->indices, (size_t)n2items * 4);
+	memcpy(f1->h_in + o_mp2, has_mp2, (size_t)f2->n);
+	TriArgs A;
+	A.kps1 = f1->kps.p; A.desc1 = f1->desc.p; A.uright1 = f1->uright.p;
+	A.kps2 = f2->kps.p; A.desc2 = f2->desc.p; A.uright2 = f2->uright.p;
+	A.item = reinterpret_cast<const int*>(f1->d_in.p); A.idx2 = reinterpret_cast<const uint32_t*>(f1->d_in.p + o_idx2); A.has_mp2 = f1->d_in.p + o_mp2;
+	A.nitems = nitems; A.only_stereo = only_stereo != 0;
+	for (int k = 0; k < 9; k++) A.F[k] = F12[k];
+	A.ex = epipole2[0]; A.ey = epipole2[1];
+	for (int l = 0; l < 16; l++) { A.sf2[l] = l < f2->nlevels ? f2->sf[l] : 0.f; A.sigma_sq2[l] = l < f2->nlevels ? sigma_sq2[l] : 0.f; }
+	A.match = reinterpret_cast<int*>(f1->d_out.p);
+	GCU(cudaMemcpyAsync(f1->d_in.p, f1->h_in, in_bytes, cudaMemcpyHostToDevice, f1->st));
+	GCU(cudaEventRecord(f1->ev0, f1->st));
+	k_triangulation_search<<<(nitems + 127) / 128, 128, 0, f1->st>>>(A);
+	GCU(cudaGetLastError());
+	GCU(cudaEventRecord(f1->ev1, f1->st));
+	GCU(cudaMemcpyAsync(f1->h_out, f1->d_out.p, (size_t)nitems * 4, cudaMemcpyDeviceToHost, f1->st));
+	GCU(cudaStreamSynchronize(f1->st));
+	cudaEventElapsedTime(&f1->last_kernel_ms, f1->ev0, f1->ev1);
+	const int* res = reinterpret_cast<const int*>(f1->h_out);
+	int n = 0;
+	std::vector<std::pair<int, int>> tmp;                               // (bestIdx2, idx1) in visiting order, :847-849
+	for (int t = 0; t < nitems; t++)
+	{
+		const int idx1 = items[3 * t];
+		if (res[t] < 0) continue;
+		matches12[idx1] = res[t];                                       // a keypoint listed under one node only: FeatureVector keys are disjoint
+		tmp.emplace_back(res[t], idx1);
+		n++;
+	}
+	if (check_orientation)
+	{
+		// CheckOrientation(keyframe2->keypointsUn, keyframe1->keypointsUn, tmpMatchIds, matches12) (:853-854, :249-309) on the host copy of
+		// the angles: 30-bin histogram of angle2 - angle1, the three largest bins survive (ComputeThreeMaxima :255-294)
+		std::vector<float> ang1((size_t)f1->n), ang2((size_t)f2->n);
+		{
+			std::vector<orbx_keypoint> k1((size_t)f1->n), k2((size_t)f2->n);
+			GCU(cudaMemcpy(k1.data(), f1->kps.p, (size_t)f1->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
+			GCU(cudaMemcpy(k2.data(), f2->kps.p, (size_t)f2->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
+			for (int i = 0; i < f1->n; i++) ang1[i] = k1[i].angle;
+			for (int i = 0; i < f2->n; i++) ang2[i] = k2[i].angle;
+		}
+		n = orbx_check_orientation_host(ang2.data(), ang1.data(), tmp, matches12, n);
+	}
+	if (nmatches) *nmatches = n;
+	return ORBX_OK;
+}
+
 }  // extern "C"

@@ -411,3 +411,115 @@ def vocabulary_features(seed, voc, n=1500, exact=0.1, near=0.5, flips=30):
             if u >= exact:
                 d[i] = _flip_bits(r, d[i], r.randint(1, flips + 1))
     return d
+
+
+def sigma_tables(scale_factors):
+    """pyramid.sigmaSq / invSigmaSq as ORBextractor::Init computes them (src/ORBextractor.cc:733-736): float products."""
+    sf = np.asarray(scale_factors, np.float32)
+    sig = (sf * sf).astype(np.float32)
+    return sig, (np.float32(1.0) / sig).astype(np.float32)
+
+
+def fuse_map(seed, fr, npts, p_occupied=0.5):
+    """The mutable state Fuse (src/ORBmatcher.cc:868-974) reads between points: which keypoints of the key frame hold a map point (an index
+    into the point list, so that Replace has both parties), every point's observation count and bad flag. Points that sit in the key
+    frame are `in_kf`. Returns dict(kf_mp [N], nobs [npts], bad [npts], in_kf [npts])."""
+    r = np.random.RandomState(seed + 77)
+    n = len(fr['kps_un'])
+    kf_mp = np.full(n, -1, np.int32)
+    holders = r.permutation(npts)[: int(min(npts, n) * p_occupied)]
+    slots = r.permutation(n)[: len(holders)]
+    kf_mp[slots] = holders
+    in_kf = np.zeros(npts, np.uint8)
+    in_kf[holders] = 1                               # the holders are candidates too: IsInKeyFrame skips them (:875)
+    nobs = r.randint(0, 9, npts).astype(np.int32)
+    bad = (r.rand(npts) < 0.05).astype(np.uint8)
+    return dict(kf_mp=kf_mp, nobs=nobs, bad=bad, in_kf=in_kf)
+
+
+def sim3_pair(seed, n=1200, w=640, h=480, cam=(517.3, 516.5, 318.6, 255.3, 40.0, 0.0773), scale=1.1, max_flips=50):
+    """Two key frames for SearchBySim3 (src/ORBmatcher.cc:1084-1277). Key frame k has pose_k and one map point per keypoint (some null /
+    already matched / bad). For a set of pairs (i1, i2) the map point of kf1's keypoint i1, taken through pose1 and S21, lands near kf2's
+    keypoint i2 and looks like it, and the other way round, so that part of the two directed searches agree; the rest disagree, miss the
+    image, the depth range or the octave. Returns dict(f1, f2, pose1, pose2, S12, pts1, desc1, pts2, desc2)."""
+    r = np.random.RandomState(seed + 31)
+    f1 = frame(seed + 300, n, w, h, stereo=False)
+    f2 = frame(seed + 301, n, w, h, stereo=False)
+    fx, fy, cx, cy = [np.float64(c) for c in cam[:4]]
+
+    def rot(ax, ang):
+        ax = np.asarray(ax, np.float64) / np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    R1, t1 = rot(r.randn(3), 0.2), r.randn(3) * 0.5
+    R2, t2 = rot(r.randn(3), 0.3), r.randn(3) * 0.5
+    R12, t12, s12 = rot(r.randn(3), 0.05), r.randn(3) * 0.05, np.float64(scale)
+    sf = f1['scale_factors'].astype(np.float64)
+    nl = f1['nlevels']
+    pts = [np.zeros(n, KF_POINT_DTYPE), np.zeros(n, KF_POINT_DTYPE)]
+    desc = [r.randint(0, 256, (n, 32)).astype(np.uint8), r.randint(0, 256, (n, 32)).astype(np.uint8)]
+    m = int(0.7 * n)
+    a = r.permutation(n)[:m]
+    b = r.permutation(n)[:m]
+    frames = (f1, f2)
+    # direction 0: point of kf1[a] -> kf2 keypoint b; direction 1: point of kf2[b'] -> kf1 keypoint a' (b', a' = same pairs for 60 %, shuffled rest)
+    b2 = b.copy(); a2 = a.copy()
+    sh = r.rand(m) < 0.4
+    a2[sh] = a[sh][r.permutation(sh.sum())]
+    for d, (src, dst) in enumerate(((a, b), (b2, a2))):
+        fs, ft = frames[d], frames[1 - d]
+        kt = ft['kps_un'][dst]
+        z = 2.0 + 6.0 * r.rand(m)
+        u = kt['x'].astype(np.float64) + r.randn(m) * 1.5
+        v = kt['y'].astype(np.float64) + r.randn(m) * 1.5
+        Xt = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)              # camera coordinates of the target key frame
+        if d == 0:      # Xc2 = S21.Map(Xc1)  =>  Xc1 = S12.Map(Xc2) = s12 R12 Xc2 + t12
+            Xs = (s12 * (R12 @ Xt.T)).T + t12
+            Rs, ts = R1, t1
+        else:           # Xc1 = S12.Map(Xc2)  =>  Xc2 = S21.Map(Xc1) = (1/s12) R12^T (Xc1 - t12)
+            Xs = ((R12.T @ (Xt - t12).T) / s12).T
+            Rs, ts = R2, t2
+        Xw = (Rs.T @ (Xs - ts).T).T
+        lvl = np.clip(kt['octave'] + r.choice([0, 0, 0, 1, -1, 2], m), 0, nl - 1)
+        dist = np.linalg.norm(Xt, axis=1)
+        P = pts[d]
+        P['xw'][src] = Xw.astype(np.float32)
+        P['max_distance'][src] = (dist * sf[lvl] * (1.0 + 0.03 * r.randn(m))).astype(np.float32)
+        P['min_distance'][src] = (P['max_distance'][src] / sf[nl - 1]).astype(np.float32)
+        far = r.rand(m) < 0.05
+        P['max_distance'][src[far]] *= np.float32(0.3)
+        P['flags'][src] = (r.rand(m) < 0.9).astype(np.int32)
+        for s_, t_ in zip(src, dst):
+            desc[d][s_] = _flip_bits(r, ft['desc'][t_], r.randint(0, max_flips + 1))
+    f32 = lambda x: np.asarray(x, np.float32)
+    return dict(f1=f1, f2=f2, cam=cam, pose1=(f32(R1), f32(t1)), pose2=(f32(R2), f32(t2)), S12=(f32(R12), f32(t12), np.float32(s12)),
+                pts1=pts[0], desc1=desc[0], pts2=pts[1], desc2=desc[1])
+
+
+def triangulation_pair(seed, n=1500, w=640, h=480, fy=516.5):
+    """Two key frames for SearchForTriangulation (src/ORBmatcher.cc:768-866): the bow_pair() scene with the matched keypoints of frame 2
+    moved onto (or near, or off) the epipolar line of their partner under a sideways-translation fundamental matrix with a small
+    perturbation, some stereo keypoints, map points on part of both frames and an epipole inside the image.
+    Returns dict(f1, fv1, has1, f2, fv2, has2, F12, ep2, sigma_sq2)."""
+    r = np.random.RandomState(seed + 57)
+    f1, fv1, va1, f2, fv2, va2 = bow_pair(seed, n, w, h)
+    k1, k2 = f1['kps_un'], f2['kps_un']
+    # re-pair by descriptor: every keypoint of frame 2 whose descriptor was copied from frame 1 gets its row
+    d1 = np.unpackbits(f1['desc'], axis=1).astype(np.int16); d2 = np.unpackbits(f2['desc'], axis=1).astype(np.int16)
+    for j in range(0, n, 3):
+        dist = np.abs(d1 - d2[j]).sum(1)
+        i = int(np.argmin(dist))
+        if dist[i] <= 60:
+            k2['y'][j] = k1['y'][i] + np.float32(r.choice([0.0, 0.5, 1.5, 2.5, 6.0]) * r.choice([-1, 1]) * f2['scale_factors'][k2['octave'][j]])
+            k1['y'][np.flatnonzero(dist <= 60)] = k1['y'][i]      # its look-alikes in frame 1 share the line: several idx1 may end on this idx2
+    F = np.array([[0, 0, 0], [0, 0, -1.0 / fy], [0, 1.0 / fy, 0]], np.float64)
+    F = F + r.randn(3, 3) * np.array([[1e-7, 1e-7, 1e-5], [1e-7, 1e-7, 1e-5], [1e-5, 1e-5, 1e-4]])
+    ur1 = np.full(n, -1, np.float32); ur2 = np.full(n, -1, np.float32)
+    s1 = r.rand(n) < 0.3; s2 = r.rand(n) < 0.3
+    ur1[s1] = k1['x'][s1] - 5.0; ur2[s2] = k2['x'][s2] - 5.0
+    f1['uright'], f2['uright'] = ur1, ur2
+    sig, _ = sigma_tables(f2['scale_factors'])
+    j = r.randint(0, n)
+    ep = np.array([k2['x'][j] + 3.0, k2['y'][j] - 2.0], np.float32)
+    return dict(f1=f1, fv1=fv1, has1=(r.rand(n) < 0.3).astype(np.uint8), f2=f2, fv2=fv2, has2=(r.rand(n) < 0.3).astype(np.uint8),
+                F12=F.astype(np.float32), ep2=ep, sigma_sq2=sig)

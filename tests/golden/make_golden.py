@@ -157,7 +157,7 @@ def guided():
         res = gc.run_oracle(ref, kind, c)
         for k, v in res.items():
             out[f'{name}.{k}'] = v
-        fr = c.get('frame') or c.get('f2')
+        fr = c.get('frame') or c.get('f2') or c['scene']['f2']
         out[f'{name}.crc'] = np.array([crc(fr['kps_un']), crc(fr['desc'])])
     np.savez_compressed(os.path.join(HERE, 'guided.npz'), **out)
     print('guided.npz:', len(out), 'arrays')

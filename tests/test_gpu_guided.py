@@ -48,7 +48,7 @@ def test_all_cases_against_oracle(orbx, oracle_port):
         max_rounds = max(max_rounds, got.get('_rounds', 0))
         if name == 'local_ladder':
             assert got['_rounds'] >= 12 and list(got['mp'][:12]) == list(range(12))
-    assert set(kinds) == {'grid', 'local', 'last', 'init', 'bow', 'reloc', 'sim3'} and max_rounds >= 12
+    assert set(kinds) == {'grid', 'local', 'last', 'init', 'bow', 'reloc', 'sim3', 'fuse', 'fuse_sim3', 'sim3_search', 'triang'} and max_rounds >= 12
 
 
 def test_reference_golden(orbx):

@@ -132,6 +132,8 @@ def test_guided_matchers_equal(oracle_port, oracle_ref):
     stat = oracle_port.lib.orc_guided_stat
     stat.restype, stat.argtypes = ctypes.c_int, [ctypes.c_int]
     max_rounds, revoked, kinds = 0, 0, set()
+    import collections
+    cover = collections.Counter()
     for name, kind, c in gc.cases():
         a, b = gc.run_oracle(oracle_ref, kind, c), gc.run_oracle(oracle_port, kind, c)
         for k in a:
@@ -141,5 +143,18 @@ def test_guided_matchers_equal(oracle_port, oracle_ref):
             max_rounds = max(max_rounds, stat(0))
         if kind == 'init':
             revoked += stat(1)
-    assert kinds == {'grid', 'local', 'last', 'init', 'bow', 'reloc', 'sim3'}
+        # the cases of the independent matchers must reach every branch of the replayed mutation and find agreeing / erased matches
+        if kind == 'fuse':
+            lg = a['log'].reshape(-1, 3)
+            cover['replace'] += int((lg[:, 0] == 1).sum()); cover['add'] += int((lg[:, 0] == 2).sum())
+        if kind == 'fuse_sim3':
+            cover['replacePoints'] += int((a['replace'] >= 0).sum())
+        if kind == 'sim3_search':
+            cover['sim3_found'] += int(a['n'])
+        if kind == 'triang':
+            cover['triang'] += int(a['n'])
+            cover['triang_shared'] += int(len(a['m12'][a['m12'] >= 0]) - len(np.unique(a['m12'][a['m12'] >= 0])))
+    assert kinds == {'grid', 'local', 'last', 'init', 'bow', 'reloc', 'sim3', 'fuse', 'fuse_sim3', 'sim3_search', 'triang'}
     assert max_rounds >= 12 and revoked > 50, (max_rounds, revoked)
+    assert (cover['replace'] > 50 and cover['add'] > 100 and cover['replacePoints'] > 100 and cover['sim3_found'] > 500 and cover['triang'] > 150
+            and cover['triang_shared'] >= 1), cover
