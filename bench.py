@@ -503,6 +503,49 @@ def run_b200(args, rank, world, local_rank, emit):
                               'note': 'the 2.9 MB table is shared by all frames of a launch and stays in L2, so DRAM traffic is ~2 B/px'}}
         del d_rect, d_raw
 
+    # ---- bag-of-words transform (Frame::ComputeBoW): the reference's vocabulary shape (k 10, L 6, levelsup 4) with
+    #      synthetic nodes; per call through the C ABI with host buffers, and a device-resident batch behind Extract
+    bow = None
+    if rank == 0 and not args.skip_guided:
+        vt = synth.vocabulary(7, 10, 6)
+        gv = api.ORBVocabulary(device=local_rank).create(10, 6, vt['parent'], vt['is_leaf'], vt['desc'], vt['weights'])
+        bfe = synth.vocabulary_features(3, vt, 1000)
+        for _ in range(10):
+            gv.transform(bfe, 4)
+        t0b = time.perf_counter()
+        for _ in range(200):
+            gv.transform(bfe, 4)
+        us_call = (time.perf_counter() - t0b) / 200 * 1e6
+        BF, BCAP = 256, 1024
+        d_bdesc = torch.from_numpy(np.ascontiguousarray(np.stack([synth.vocabulary_features(10 + f_ % 8, vt, BCAP) for f_ in range(8)])[np.arange(BF) % 8])).to(dev)
+        d_bn = torch.full((BF,), 1000, dtype=torch.int32, device=dev)
+        bs = torch.cuda.ExternalStream(ex.stream(), device=dev)
+        for _ in range(3):
+            gv.transform_batch_device(d_bdesc, d_bn, BF, BCAP, 4, stream=ex.stream())
+        ex.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(bs)
+        for _ in range(10):
+            gv.transform_batch_device(d_bdesc, d_bn, BF, BCAP, 4, stream=ex.stream())
+        b1.record(bs)
+        b1.synchronize()
+        ms_b = b0.elapsed_time(b1) / 10
+        bow = {'workload': 'DBoW2 transform, vocabulary k 10 / L 6 (1.1 M nodes, synthetic), 1000 descriptors per frame, levelsup 4',
+               'us_per_call': us_call, 'api': 'orbx_bow_transform (host descriptors in, BowVector + FeatureVector out)',
+               'batch_frames_per_s': BF / (ms_b * 1e-3), 'batch_ms_per_step': ms_b,
+               'batch_api': f'orbx_bow_transform_batch_device, {BF} frames per call, device-resident (2 launches)',
+               'h2d_bytes_per_call': 32000, 'd2h_bytes_per_call': int(1000 * (4 + 8 + 4 + 4) + 16)}
+        if world == 1 and not args.skip_cpu:
+            try:
+                from oracle import bindings as ob
+                op = ob.Oracle('port', native=True)
+                ovv = op.vocabulary(arrays=vt)
+                bow['cpu_baseline'] = {'us_per_call': ovv.time_transform(bfe, 4, 50) * 1e6, 'cores': 1, 'kind': 'port',
+                                       'sample': '50 transforms of the same 1000 descriptors, oracle/bow_oracle.cc (-O3 -march=x86-64-v3)'}
+            except Exception as e:
+                bow['cpu_baseline'] = {'unavailable': str(e)}
+        del d_bdesc
+
     # ---- single-frame latency: what SystemImpl::Track* sees per image (one Extract call, host frame in, keypoints + descriptors out)
     latency = None
     if rank == 0 and not args.skip_guided:
@@ -555,6 +598,7 @@ def run_b200(args, rank, world, local_rank, emit):
             'guided': guided,
             'remap': remap,
             'latency': latency,
+            'bow': bow,
         }
         emit(json.dumps(line))
 

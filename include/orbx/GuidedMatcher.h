@@ -11,6 +11,11 @@
 //                                                                          include/ORBmatcher.h:72-73, src/ORBmatcher.cc:406-516, 696-766
 //   int ORBmatcher::SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int windowSize)
 //                                                                          include/ORBmatcher.h:80,  src/ORBmatcher.cc:614-694
+//   int ORBmatcher::Fuse(KeyFrame*, const std::vector<MapPoint*>&, float th) / Fuse(KeyFrame*, const Sim3&, ..., replacePoints)
+//                                                                          src/ORBmatcher.cc:868-980, 982-1088
+//   int ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, std::vector<MapPoint*>&, const Sim3&, float th)   src/ORBmatcher.cc:1090-1277
+//   int ORBmatcher::SearchForTriangulation(const KeyFrame*, const KeyFrame*, const cv::Mat& F12, matchIds, bool onlyStereo)
+//                                                                          src/ORBmatcher.cc:768-866
 //
 // The methods are templates over the reference's own Frame and MapPoint types: they read exactly the members the reference code
 // reads (frame.keypointsUn, .descriptors, .uright, .mappoints, .outlier, .keypoints, .imageBounds, .pyramid.scaleFactors, .camera,
@@ -22,6 +27,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include <opencv2/core.hpp>
@@ -259,6 +265,233 @@ public:
 		const int nmatches = Bow(keyframe1->featureVector, valid1, dev1, keyframe2->featureVector, &valid2, dev2, match2);
 		for (size_t c = 0; c < valid2.size(); c++)
 			if (match2[c] >= 0) matches12[(size_t)match2[c]] = mappoints2[c];                   // :752
+		return nmatches;
+	}
+
+	// ---- Matchers of local mapping and loop closing whose per-point search reads nothing the loop changes -----------------------------
+	// src/ORBmatcher.cc:868-980. The geometry of every point is evaluated here with the reference's own classes (:879-919), all window
+	// searches with their octave and chi-square gates run in one kernel, and the loop of the reference is then replayed from :876 and
+	// :956-976 over the results — the map calls (Replace, AddObservation, AddMapPoint) are the reference's own, in its order.
+	template <class KeyFrameT, class MapPointT>
+	int Fuse(KeyFrameT* keyframe, DeviceFrame& dev, const std::vector<MapPointT*>& mappoints, float th = 3.f) const
+	{
+		const int npts = static_cast<int>(mappoints.size());
+		std::vector<orbx_best_window> win((size_t)npts);
+		std::vector<uint8_t> desc((size_t)npts * 32);
+		const auto pose = keyframe->GetPose();
+		const cv::Matx33f Rcw = pose.R();
+		const cv::Matx31f tcw = pose.t();
+		const cv::Matx31f Ow = keyframe->GetCameraCenter();
+		for (int i = 0; i < npts; i++)
+		{
+			orbx_best_window& w = win[i];
+			w = orbx_best_window{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0 };
+			MapPointT* mappoint = mappoints[i];
+			if (!mappoint || mappoint->isBad()) continue;
+			const cv::Matx31f Xw = mappoint->GetWorldPos();
+			const cv::Matx31f Xc = Rcw * Xw + tcw;
+			if (Xc(2) < 0.f) continue;
+			const float invZ = 1.f / Xc(2);
+			const float u = invZ * keyframe->camera.fx * Xc(0) + keyframe->camera.cx, v = invZ * keyframe->camera.fy * Xc(1) + keyframe->camera.cy;
+			if (!keyframe->IsInImage(u, v)) continue;
+			const float ur = u - keyframe->camera.bf / Xc(2);
+			const cv::Matx31f PO = Xw - Ow;
+			const float dist3D = static_cast<float>(cv::norm(PO));
+			if (dist3D < mappoint->GetMinDistanceInvariance() || dist3D > mappoint->GetMaxDistanceInvariance()) continue;
+			const cv::Matx31f Pn = mappoint->GetNormal();
+			if (PO.dot(Pn) < 0.5 * dist3D) continue;
+			const int predictedScale = mappoint->PredictScale(dist3D, keyframe);
+			w.u = u; w.v = v; w.ur = ur;
+			w.radius = th * keyframe->pyramid.scaleFactors[predictedScale];
+			w.min_level = predictedScale - 1; w.max_level = predictedScale;              // :930
+			w.flags = 3;                                                                 // with the chi-square gate of :934-945
+			std::memcpy(&desc[(size_t)i * 32], mappoint->GetDescriptor().data, 32);
+		}
+		std::vector<int32_t> bestIdx((size_t)npts + 1), bestDist((size_t)npts + 1);
+		Check(orbx_search_best_in_windows(dev.Handle(), win.data(), desc.data(), npts, keyframe->pyramid.invSigmaSq.data(), bestIdx.data(),
+			bestDist.data()), "Fuse");
+		int nfused = 0;
+		for (int i = 0; i < npts; i++)
+		{
+			MapPointT* mappoint = mappoints[i];
+			if (!mappoint || mappoint->isBad() || mappoint->IsInKeyFrame(keyframe)) continue;    // :876, with the state the loop has produced so far
+			if (!(win[i].flags & 1) || bestDist[i] > 50) continue;                               // TH_LOW, :957
+			MapPointT* MPInKF = keyframe->GetMapPoint(bestIdx[i]);
+			if (MPInKF)
+			{
+				if (!MPInKF->isBad())
+				{
+					if (MPInKF->Observations() > mappoint->Observations()) mappoint->Replace(MPInKF);
+					else MPInKF->Replace(mappoint);
+				}
+			}
+			else
+			{
+				mappoint->AddObservation(keyframe, bestIdx[i]);
+				keyframe->AddMapPoint(mappoint, bestIdx[i]);
+			}
+			nfused++;
+		}
+		return nfused;
+	}
+
+	// src/ORBmatcher.cc:982-1088 (loop closing)
+	template <class KeyFrameT, class Sim3T, class MapPointT>
+	int Fuse(KeyFrameT* keyframe, DeviceFrame& dev, const Sim3T& Scw, const std::vector<MapPointT*>& mappoints, float th,
+		std::vector<MapPointT*>& replacePoints) const
+	{
+		const int npts = static_cast<int>(mappoints.size());
+		std::vector<orbx_best_window> win((size_t)npts);
+		std::vector<uint8_t> desc((size_t)npts * 32);
+		const cv::Matx33f Rcw = Scw.R();
+		const cv::Matx31f tcw = Scw.Invs() * Scw.t();                                    // pose(Scw.R(), Scw.Invs() * Scw.t()), :987
+		const cv::Matx31f Ow = -Rcw.t() * tcw;                                           // pose.Invt()
+		const auto alreadyFound = keyframe->GetMapPoints();                              // :992
+		for (int i = 0; i < npts; i++)
+		{
+			orbx_best_window& w = win[i];
+			w = orbx_best_window{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0 };
+			MapPointT* mappoint = mappoints[i];
+			if (mappoint->isBad() || alreadyFound.count(mappoint)) continue;
+			const cv::Matx31f Xw = mappoint->GetWorldPos();
+			const cv::Matx31f Xc = Rcw * Xw + tcw;
+			if (Xc(2) < 0.f) continue;
+			const float invZ = 1.f / Xc(2);
+			const float u = invZ * keyframe->camera.fx * Xc(0) + keyframe->camera.cx, v = invZ * keyframe->camera.fy * Xc(1) + keyframe->camera.cy;
+			if (!keyframe->IsInImage(u, v)) continue;
+			const cv::Matx31f PO = Xw - Ow;
+			const float dist3D = static_cast<float>(cv::norm(PO));
+			if (dist3D < mappoint->GetMinDistanceInvariance() || dist3D > mappoint->GetMaxDistanceInvariance()) continue;
+			const cv::Matx31f Pn = mappoint->GetNormal();
+			if (PO.dot(Pn) < 0.5 * dist3D) continue;
+			const int predictedScale = mappoint->PredictScale(dist3D, keyframe);
+			w.u = u; w.v = v;
+			w.radius = th * keyframe->pyramid.scaleFactors[predictedScale];
+			w.min_level = predictedScale - 1; w.max_level = predictedScale;              // :1057
+			w.flags = 1;
+			std::memcpy(&desc[(size_t)i * 32], mappoint->GetDescriptor().data, 32);
+		}
+		std::vector<int32_t> bestIdx((size_t)npts + 1), bestDist((size_t)npts + 1);
+		Check(orbx_search_best_in_windows(dev.Handle(), win.data(), desc.data(), npts, nullptr, bestIdx.data(), bestDist.data()), "Fuse");
+		int nfused = 0;
+		for (int i = 0; i < npts; i++)
+		{
+			MapPointT* mappoint = mappoints[i];
+			if (mappoint->isBad() || alreadyFound.count(mappoint)) continue;             // :1002 (nothing in this loop makes a point bad)
+			if (!(win[i].flags & 1) || bestDist[i] > 50) continue;                       // TH_LOW, :1070
+			MapPointT* MPInKF = keyframe->GetMapPoint(bestIdx[i]);
+			if (MPInKF)
+			{
+				if (!MPInKF->isBad()) replacePoints[i] = MPInKF;
+			}
+			else
+			{
+				mappoint->AddObservation(keyframe, bestIdx[i]);
+				keyframe->AddMapPoint(mappoint, bestIdx[i]);
+			}
+			nfused++;
+		}
+		return nfused;
+	}
+
+	// src/ORBmatcher.cc:1090-1277 (loop closing): both directed searches on the GPU, the agreement test here
+	template <class KeyFrameT, class Sim3T, class MapPointT>
+	int SearchBySim3(KeyFrameT* keyframe1, DeviceFrame& dev1, KeyFrameT* keyframe2, DeviceFrame& dev2, std::vector<MapPointT*>& matches12,
+		const Sim3T& S12, float th) const
+	{
+		const Sim3T S21 = S12.Inverse();
+		const auto mappoints1 = keyframe1->GetMapPointMatches();
+		const auto mappoints2 = keyframe2->GetMapPointMatches();
+		const int N1 = static_cast<int>(mappoints1.size()), N2 = static_cast<int>(mappoints2.size());
+		std::vector<bool> alreadyMatched1((size_t)N1, false), alreadyMatched2((size_t)N2, false);
+		for (int i = 0; i < N1; i++)                                                     // :1109-1121
+		{
+			MapPointT* mappoint = matches12[i];
+			if (mappoint)
+			{
+				alreadyMatched1[i] = true;
+				const int idx2 = mappoint->GetIndexInKeyFrame(keyframe2);
+				if (idx2 >= 0 && idx2 < N2) alreadyMatched2[idx2] = true;
+			}
+		}
+		auto direction = [&](KeyFrameT* from, const std::vector<MapPointT*>& mappoints, const std::vector<bool>& already, const Sim3T& S,
+			KeyFrameT* to, DeviceFrame& devTo, std::vector<int32_t>& match)
+		{
+			const int n = static_cast<int>(mappoints.size());
+			std::vector<orbx_best_window> win((size_t)n);
+			std::vector<uint8_t> desc((size_t)n * 32);
+			const auto pose = from->GetPose();
+			const cv::Matx33f R = pose.R();
+			const cv::Matx31f t = pose.t();
+			for (int i = 0; i < n; i++)
+			{
+				orbx_best_window& w = win[i];
+				w = orbx_best_window{ 0.f, 0.f, 0.f, 0.f, 0, 0, 0 };
+				MapPointT* mappoint = mappoints[i];
+				if (!mappoint || already[i] || mappoint->isBad()) continue;              // :1130, :1197
+				const cv::Matx31f Xw = mappoint->GetWorldPos();
+				const cv::Matx31f Xa = R * Xw + t;
+				const cv::Matx31f Xb = S.Map(Xa);
+				if (Xb(2) < 0.f) continue;
+				const float invZ = 1.f / Xb(2);
+				const float u = invZ * to->camera.fx * Xb(0) + to->camera.cx, v = invZ * to->camera.fy * Xb(1) + to->camera.cy;
+				if (!to->IsInImage(u, v)) continue;
+				const float dist3D = static_cast<float>(cv::norm(Xb));
+				if (dist3D < mappoint->GetMinDistanceInvariance() || dist3D > mappoint->GetMaxDistanceInvariance()) continue;
+				const int predictedScale = mappoint->PredictScale(dist3D, to);
+				w.u = u; w.v = v;
+				w.radius = th * to->pyramid.scaleFactors[predictedScale];
+				w.min_level = predictedScale - 1; w.max_level = predictedScale;          // :1175, :1242
+				w.flags = 1;
+				std::memcpy(&desc[(size_t)i * 32], mappoint->GetDescriptor().data, 32);
+			}
+			std::vector<int32_t> bestDist((size_t)n + 1);
+			match.assign((size_t)n + 1, -1);
+			Check(orbx_search_best_in_windows(devTo.Handle(), win.data(), desc.data(), n, nullptr, match.data(), bestDist.data()), "SearchBySim3");
+			for (int i = 0; i < n; i++)
+				if (bestDist[i] > 100) match[i] = -1;                                    // TH_HIGH, :1187, :1254
+		};
+		std::vector<int32_t> match1, match2;
+		direction(keyframe1, mappoints1, alreadyMatched1, S21, keyframe2, dev2, match1);
+		direction(keyframe2, mappoints2, alreadyMatched2, S12, keyframe1, dev1, match2);
+		int nfound = 0;
+		for (int i1 = 0; i1 < N1; i1++)                                                  // :1260-1274
+		{
+			const int idx2 = match1[i1];
+			if (idx2 >= 0 && match2[idx2] == i1)
+			{
+				matches12[i1] = mappoints2[idx2];
+				nfound++;
+			}
+		}
+		return nfound;
+	}
+
+	// src/ORBmatcher.cc:768-866 (local mapping). F12 is the 3x3 CV_32F matrix the reference passes; the epipole is computed as it does.
+	template <class KeyFrameT>
+	int SearchForTriangulation(const KeyFrameT* keyframe1, DeviceFrame& dev1, const KeyFrameT* keyframe2, DeviceFrame& dev2, const cv::Mat& F12,
+		std::vector<std::pair<size_t, size_t>>& matchIds, bool onlyStereo) const
+	{
+		const auto pose2 = keyframe2->GetPose();
+		const cv::Matx31f Xc = pose2.R() * keyframe1->GetCameraCenter() + pose2.t();     // proj2.WorldToImage(keyframe1->GetCameraCenter()), :772-773
+		const float invZ = 1.f / Xc(2);
+		const float ep[2] = { invZ * keyframe2->camera.fx * Xc(0) + keyframe2->camera.cx, invZ * keyframe2->camera.fy * Xc(1) + keyframe2->camera.cy };
+		float F[9];
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++) F[r * 3 + c] = F12.at<float>(r, c);
+		std::vector<uint8_t> has1((size_t)keyframe1->N), has2((size_t)keyframe2->N);
+		for (int i = 0; i < keyframe1->N; i++) has1[i] = keyframe1->GetMapPoint(i) != nullptr;
+		for (int i = 0; i < keyframe2->N; i++) has2[i] = keyframe2->GetMapPoint(i) != nullptr;
+		const FlatFeatureVector a = Flatten(keyframe1->featureVector), b = Flatten(keyframe2->featureVector);
+		const orbx_feature_vector va = a.view(), vb = b.view();
+		std::vector<int32_t> matches12((size_t)keyframe1->N + 1);
+		int nmatches = 0;
+		Check(orbx_search_for_triangulation(dev1.Handle(), &va, has1.data(), dev2.Handle(), &vb, has2.data(), F, ep, keyframe2->pyramid.sigmaSq.data(),
+			onlyStereo ? 1 : 0, checkOrientation_ ? 1 : 0, matches12.data(), &nmatches), "SearchForTriangulation");
+		matchIds.clear();
+		matchIds.reserve((size_t)nmatches);
+		for (int idx1 = 0; idx1 < keyframe1->N; idx1++)                                  // :859-863
+			if (matches12[idx1] >= 0) matchIds.push_back(std::make_pair((size_t)idx1, (size_t)matches12[idx1]));
 		return nmatches;
 	}
 
