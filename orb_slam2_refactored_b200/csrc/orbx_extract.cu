@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells_v1(const OrbxPlanDev 
 // 4 horizontally adjacent pixels per lane: aligned 32-bit words of the tile are turned into packed u16x2 operands with PRMT
 // (a pixel sits in the HIGH byte of a 16-bit lane, the low byte is a neighbour pixel and never decides a min/max), so the 8 ring
 // loads + 8 packs + 7 min/max per pixel of the byte-wise version become 11 word loads + 13 PRMT + 24 VIMNMX per FOUR pixels.
-#define FW_WARPS 4
+#define FW_WARPS 1           // warps (= cells) per CTA; 1: a finished warp frees its shared memory at once (measured best, see orbx_launch_fast)
 #define FW_TSW (FT_TS / 4)
 
 struct OrbxFastLayout
@@ -538,13 +538,14 @@ __device__ __forceinline__ uint32_t fast_gather16(uint32_t w, int shift)
 	return (x | (x >> 8)) & 0xffffu;
 }
 
-__global__ void __launch_bounds__(FW_WARPS * 32) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxFastLayout Y)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxFastLayout Y)
 {
 	extern __shared__ __align__(128) uint8_t fw_smem[];
-	__shared__ __align__(8) uint64_t tma_bar[FW_WARPS];
+	__shared__ __align__(8) uint64_t tma_bar[NW];
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int cell = blockIdx.x * FW_WARPS + warp, f = blockIdx.y;
+	const int cell = blockIdx.x * NW + warp, f = blockIdx.y;
 	if (cell >= P.cells_per_frame) return;           // whole warps leave; there is no block barrier below
 	uint8_t* const base = fw_smem + (size_t)warp * Y.warp_bytes;
 	uint8_t* const tile = base;
@@ -1607,17 +1608,26 @@ void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_
 	Y.off_bm = (Y.off_list + std::max(maxrw * maxrh * 2, maxrh * 16) + 15) & ~15;
 	Y.bm_rows = maxrh;
 	Y.warp_bytes = (Y.off_bm + 3 * 8 * maxrh + 127) & ~127;
-	const int smem = FW_WARPS * Y.warp_bytes;
-	static int attr_smem[64] = {};
+	// Warps per CTA: a CTA's shared memory is released when its LAST warp retires, and cells differ in cost (retry, corner count), so
+	// with 4 warps per CTA a fifth of the resident warp slots sat idle behind a straggler (ncu: 19 of 24 possible warps active).
+	static const int nw_env = getenv("ORBX_FAST_WARPS") ? atoi(getenv("ORBX_FAST_WARPS")) : FW_WARPS;   // tuning knob: 1, 2 or 4
+	const int nw = (nw_env == 2 || nw_env == 4) ? nw_env : 1;
+	const int smem = nw * Y.warp_bytes;
+	static int attr_smem[64][3] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 64 && attr_smem[dev] < smem)
+	const int slot = nw == 1 ? 0 : nw == 2 ? 1 : 2;
+	if (dev >= 0 && dev < 64 && attr_smem[dev][slot] < smem)
 	{
-		cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		attr_smem[dev] = smem;
+		if (nw == 1) cudaFuncSetAttribute(k_fast_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		else if (nw == 2) cudaFuncSetAttribute(k_fast_cells<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		else cudaFuncSetAttribute(k_fast_cells<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		attr_smem[dev][slot] = smem;
 	}
-	dim3 grid((P.cells_per_frame + FW_WARPS - 1) / FW_WARPS, P.frames);
-	k_fast_cells<<<grid, FW_WARPS * 32, smem, st>>>(P, maps, Y);
+	dim3 grid((P.cells_per_frame + nw - 1) / nw, P.frames);
+	if (nw == 1) k_fast_cells<1><<<grid, 32, smem, st>>>(P, maps, Y);
+	else if (nw == 2) k_fast_cells<2><<<grid, 64, smem, st>>>(P, maps, Y);
+	else k_fast_cells<4><<<grid, 128, smem, st>>>(P, maps, Y);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }

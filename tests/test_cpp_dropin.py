@@ -9,6 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, 'tests', 'cpp', '_build', 'dropin_test')
 EXE_GUIDED = os.path.join(ROOT, 'tests', 'cpp', '_build', 'guided_dropin_test')
+EXE_MAPPING = os.path.join(ROOT, 'tests', 'cpp', '_build', 'mapping_dropin_test')
 
 
 def build_exe():
@@ -18,7 +19,7 @@ def build_exe():
     bindings.build()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     hdrs = [os.path.join(ROOT, 'include', 'orbx', h) for h in ('ORBextractor.h', 'ORBmatcher.h', 'GuidedMatcher.h')]
-    for name, exe in (('dropin_test.cc', EXE), ('guided_dropin_test.cc', EXE_GUIDED)):
+    for name, exe in (('dropin_test.cc', EXE), ('guided_dropin_test.cc', EXE_GUIDED), ('mapping_dropin_test.cc', EXE_MAPPING)):
         src = os.path.join(ROOT, 'tests', 'cpp', name)
         if os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(src), os.path.getmtime(lib)] + [os.path.getmtime(h) for h in hdrs]):
             continue
@@ -31,7 +32,7 @@ def build_exe():
 
 def test_dropin_headers_compile_and_link():
     build_exe()
-    assert os.path.exists(EXE) and os.path.exists(EXE_GUIDED)
+    assert os.path.exists(EXE) and os.path.exists(EXE_GUIDED) and os.path.exists(EXE_MAPPING)
 
 
 @pytest.mark.gpu
@@ -49,5 +50,15 @@ def test_guided_dropin_matches_oracle():
     """include/orbx/GuidedMatcher.h driven with Frame / MapPoint types that carry the reference's member names."""
     build_exe()
     r = subprocess.run([EXE_GUIDED], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert r.stdout.decode().startswith('OK')
+
+
+@pytest.mark.gpu
+def test_mapping_dropin_matches_oracle():
+    """Fuse x2, SearchBySim3 and SearchForTriangulation of include/orbx/GuidedMatcher.h: KeyFrame / MapPoint / Sim3 types with the
+    reference's member names; results and the order of the map mutations equal the oracle's."""
+    build_exe()
+    r = subprocess.run([EXE_MAPPING], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     assert r.stdout.decode().startswith('OK')
