@@ -291,8 +291,8 @@ def run_b200(args, rank, world, local_rank, emit):
     kname = {'fast': 'k_fast_cells', 'describe': 'k_orient_describe', 'quadtree': 'k_quadtree'}.get(dominant)   # single-launch stages
     if os.path.exists(tj) and kname:
         t = json.load(open(tj)).get(kname)
-        if t:   # dram__bytes_read + write of one launch at 256 frames (ncu --set full, profiles/), scaled to this batch
-            traffic = t['dram_bytes_per_launch'] * B / 256.0
+        if t:   # dram__bytes_read + write of one captured launch (ncu --set full, profiles/), scaled to this batch
+            traffic = t['dram_bytes_per_launch'] * B / float(t.get('frames_per_launch') or 256)
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': dom_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'launches_per_step': launches_per_stage[dominant],
@@ -455,6 +455,41 @@ def run_b200(args, rank, world, local_rank, emit):
                   'last_frame': per_call(g_last), 'last_frame_kernel': gf.last_stats()[1] * 1e3, 'rounds': gf.last_rounds(),
                   'frame_assign': per_call(lambda: gf.assign(fr['kps_un'], fr['desc'], fr['scale_factors'], fr['bounds'], fr['uright'])),
                   'h2d_bytes_per_call': int(gpts.nbytes + gdesc.nbytes + 4 * len(fr['kps_un'])), 'd2h_bytes_per_call': int(4 * len(fr['kps_un']) + 16)}
+        # the matchers of local mapping / loop closing (Fuse, SearchBySim3, SearchForTriangulation): search on the device, per call
+        _, inv_sig = synth.sigma_tables(fr['scale_factors'])
+        Sf, fpts, fdesc = synth.sim3_points(21, fr, synth.KITTI_CAMERA, npts=1000, scale=1.0)
+        fstate = synth.fuse_map(1, fr, len(fpts))
+        lsf = synth.log_scale_factor()
+        sp = synth.sim3_pair(1, n=1000)
+        sp['lsf'] = lsf
+        sf1 = api.Frame(sp['f1']['kps_un'], sp['f1']['desc'], sp['f1']['scale_factors'], sp['f1']['bounds'], sp['f1']['uright'], device=local_rank)
+        sf2 = api.Frame(sp['f2']['kps_un'], sp['f2']['desc'], sp['f2']['scale_factors'], sp['f2']['bounds'], sp['f2']['uright'], device=local_rank)
+        tp = synth.triangulation_pair(1, n=1000)
+        tf1 = api.Frame(tp['f1']['kps_un'], tp['f1']['desc'], tp['f1']['scale_factors'], tp['f1']['bounds'], tp['f1']['uright'], device=local_rank)
+        tf2 = api.Frame(tp['f2']['kps_un'], tp['f2']['desc'], tp['f2']['scale_factors'], tp['f2']['bounds'], tp['f2']['uright'], device=local_rank)
+        gm2 = api.ORBmatcher(0.6, True, device=local_rank)
+        guided['mapping'] = {
+            'workload': '1000 keypoints per key frame, 1000 map points; the search half of Fuse, SearchBySim3 (both directions + agreement) and '
+                        'SearchForTriangulation, host buffers in and out',
+            'unit': 'us per call',
+            'fuse': per_call(lambda: gm2.FuseSearch(gf, synth.KITTI_CAMERA, (Sf[0], Sf[1]), lsf, inv_sig, fpts, fdesc, 3.0)),
+            'search_by_sim3': per_call(lambda: gm2.SearchBySim3(sf1, sp['cam'], sp['pose1'], lsf, sf2, sp['cam'], sp['pose2'], lsf, sp['S12'], 7.5,
+                                                                sp['pts1'], sp['desc1'], sp['pts2'], sp['desc2'])),
+            'search_for_triangulation': per_call(lambda: gm2.SearchForTriangulation(tf1, tp['fv1'], tp['has1'], tf2, tp['fv2'], tp['has2'], tp['F12'],
+                                                                                    tp['ep2'], tp['sigma_sq2'], False))}
+        if world == 1 and not args.skip_cpu:
+            try:
+                o, kind, native = load_cpu_reference()
+                if kind == 'reference':
+                    guided['mapping']['cpu_baseline'] = {
+                        'fuse': o.time_fuse(fr, synth.KITTI_CAMERA, (Sf[0], Sf[1]), lsf, inv_sig, fpts, fdesc, 3.0, fstate, 50) * 1e6,
+                        'search_by_sim3': o.time_search_by_sim3(sp, 7.5, 50) * 1e6,
+                        'search_for_triangulation': o.time_search_for_triangulation(tp, False, True, 50) * 1e6,
+                        'unit': 'us per call', 'cores': 1, 'kind': kind,
+                        'sample': '50 calls each of the whole reference function (search + map mutation); key frames, grids and map points built outside '
+                                  'the timed region'}
+            except Exception as e:
+                guided['mapping']['cpu_baseline'] = {'unavailable': str(e)}
         if world == 1 and not args.skip_cpu:
             try:
                 o, kind, native = load_cpu_reference()

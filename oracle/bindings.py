@@ -129,6 +129,13 @@ class Oracle:
                                       C.POINTER(Pose), C.c_float, C.POINTER(Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
         f('search_for_triangulation', C.c_int, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView), C.POINTER(FeatureVector),
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p])
+        if self.pre == 'ref_':
+            f('time_fuse', C.c_double, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int])
+            f('time_search_by_sim3', C.c_double, [C.POINTER(FrameView), C.POINTER(Camera), C.POINTER(Pose), C.c_float, C.POINTER(FrameView), C.POINTER(Camera),
+                                                  C.POINTER(Pose), C.c_float, C.POINTER(Sim3), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int])
+            f('time_search_for_triangulation', C.c_double, [C.POINTER(FrameView), C.POINTER(FeatureVector), C.c_void_p, C.POINTER(FrameView),
+                                                            C.POINTER(FeatureVector), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int])
         f('voc_load_text', C.c_void_p, [C.c_char_p])
         f('voc_destroy', None, [C.c_void_p])
         f('bow_transform', C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6)
@@ -436,6 +443,30 @@ class Oracle:
         n = self._search_for_triangulation(C.byref(v1), C.byref(c1), _p(h1), C.byref(v2), C.byref(c2), _p(h2), _p(F), _p(ep), _p(sg), int(only_stereo),
                                            int(check_orientation), _p(m12))
         return n, m12[:v1.n]
+
+    def time_fuse(self, kf, cam, pose, log_scale_factor, inv_sigma_sq, pts, pt_desc, th, state, reps=20):
+        v, keep = self._frame_view(kf)
+        pts = np.ascontiguousarray(pts); pt_desc = np.ascontiguousarray(pt_desc, np.uint8); sig = np.ascontiguousarray(inv_sigma_sq, np.float32)
+        a = [np.ascontiguousarray(state[k], t) for k, t in (('kf_mp', np.int32), ('nobs', np.int32), ('bad', np.uint8), ('in_kf', np.uint8))]
+        return self._time_fuse(C.byref(v), C.byref(Camera(*[float(c) for c in cam])), C.byref(self._pose1(pose)), float(log_scale_factor), _p(sig), _p(pts),
+                               _p(pt_desc), len(pts), float(th), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), reps)
+
+    def time_search_by_sim3(self, c, th, reps=20):
+        v1, k1 = self._frame_view(c['f1']); v2, k2 = self._frame_view(c['f2'])
+        cam = Camera(*[float(x) for x in c['cam']])
+        p1 = np.ascontiguousarray(c['pts1']); p2 = np.ascontiguousarray(c['pts2'])
+        d1 = np.ascontiguousarray(c['desc1'], np.uint8); d2 = np.ascontiguousarray(c['desc2'], np.uint8)
+        lsf = float(c['lsf'])
+        return self._time_search_by_sim3(C.byref(v1), C.byref(cam), C.byref(self._pose1(c['pose1'])), lsf, C.byref(v2), C.byref(cam),
+                                         C.byref(self._pose1(c['pose2'])), lsf, C.byref(self._sim3(c['S12'])), float(th), _p(p1), _p(d1), _p(p2), _p(d2), reps)
+
+    def time_search_for_triangulation(self, c, only_stereo, check_orientation, reps=20):
+        v1, k1 = self._frame_view(c['f1']); v2, k2 = self._frame_view(c['f2'])
+        c1, keep1 = self._fv(c['fv1']); c2, keep2 = self._fv(c['fv2'])
+        h1 = np.ascontiguousarray(c['has1'], np.uint8); h2 = np.ascontiguousarray(c['has2'], np.uint8)
+        F = np.ascontiguousarray(c['F12'], np.float32).reshape(9); ep = np.ascontiguousarray(c['ep2'], np.float32); sg = np.ascontiguousarray(c['sigma_sq2'], np.float32)
+        return self._time_search_for_triangulation(C.byref(v1), C.byref(c1), _p(h1), C.byref(v2), C.byref(c2), _p(h2), _p(F), _p(ep), _p(sg),
+                                                   int(only_stereo), int(check_orientation), reps)
 
     def vocabulary(self, path=None, arrays=None):
         """path: a vocabulary text file (loadFromTextFile); arrays (port only): dict k, L, scoring, weighting, parent, is_leaf, desc, weights."""

@@ -37,6 +37,8 @@ struct VocabDev
 	int64_t nnodes;              // including the root (node 0)
 	int64_t nwords;
 	const int32_t* child_start;  // [nnodes + 1]
+	const int4* node_info;       // [nnodes]: first slot in child_ids, number of children, id of the first child when the children's ids are
+	                             // consecutive (the order HKmeansStep creates them in) else -1, word id: one 16-byte load per level instead of a chain
 	const int32_t* child_ids;    // [nnodes - 1], push_back order of Node::children
 	const uint32_t* desc;        // [nnodes][8]
 	const int32_t* word_id;      // [nnodes]: Node::word_id (0 for nodes that are not words, as in the reference)
@@ -59,29 +61,34 @@ __global__ void __launch_bounds__(256) k_bow_descend(const VocabDev V, const uin
 	int nid = 0;                 // :1232: root when nid_level <= 0. A leaf shallower than nid_level leaves *nid unset in the reference (the
 	                             // caller's variable is uninitialised there); this implementation reports node 0 for that case.
 	int node = 0, level = 0;
+	int word = 0;
 	for (;;)
 	{
-		const int cs = __ldg(V.child_start + node), ce = __ldg(V.child_start + node + 1);
-		if (cs == ce) break;     // Node::isLeaf()
+		const int4 info = __ldg(V.node_info + node);
+		const int cs = info.x, nch = info.y, first = info.z;
+		word = info.w;
+		if (nch == 0) break;     // Node::isLeaf()
 		++level;
 		uint32_t best = 0xffffffffu;
-		for (int c = cs; c < ce; c += 2)
+		for (int c = 0; c < nch; c += 2)
 		{
-			const int id0 = __ldg(V.child_ids + c), id1 = c + 1 < ce ? __ldg(V.child_ids + c + 1) : id0;
+			const bool two = c + 1 < nch;
+			const int id0 = first >= 0 ? first + c : __ldg(V.child_ids + cs + c);
+			const int id1 = !two ? id0 : (first >= 0 ? first + c + 1 : __ldg(V.child_ids + cs + c + 1));
 			uint32_t d = (uint32_t)__popc(fw ^ __ldg(V.desc + (int64_t)id0 * 8 + sub)) | ((uint32_t)__popc(fw ^ __ldg(V.desc + (int64_t)id1 * 8 + sub)) << 16);
 			d += __shfl_xor_sync(gmask, d, 1);
 			d += __shfl_xor_sync(gmask, d, 2);
 			d += __shfl_xor_sync(gmask, d, 4);
 			const uint32_t d0 = d & 0xffffu, d1 = d >> 16;
 			if (d0 < best) { best = d0; node = id0; }                    // strict: the first minimum in children order wins (:1249)
-			if (c + 1 < ce && d1 < best) { best = d1; node = id1; }
+			if (two && d1 < best) { best = d1; node = id1; }
 		}
 		if (level == nid_level) nid = node;
 	}
 	if (sub == 0)
 	{
 		const int64_t o = (int64_t)frame * cap + i;
-		feat_word[o] = __ldg(V.word_id + node);
+		feat_word[o] = word;
 		feat_node[o] = nid;
 		feat_w[o] = __ldg(V.weight + node);
 	}
@@ -291,13 +298,15 @@ struct orbx_vocabulary_s
 	cudaStream_t stream = nullptr;
 	VocabDev V = {};
 	Buf<int32_t> child_start, child_ids, word_id;
+	Buf<int4> node_info;
 	Buf<uint32_t> desc;
 	Buf<double> weight;
 	// scratch of the transform calls
 	Buf<int32_t> feat_word, feat_node, n, word_ids, fv_start;
 	Buf<uint32_t> fv_nodes, fv_items;
 	Buf<double> feat_w, word_vals;
-	Buf<uint8_t> in_desc;
+	Buf<uint8_t> in_desc, out_block;
+	uint8_t* h_in = nullptr; uint8_t* h_out = nullptr; size_t h_cap = 0;   // pinned staging of orbx_bow_transform
 	Buf<int2> counts;
 	Buf<BowPair> pairs; Buf<double> scores; Buf<int32_t> sc_ids; Buf<double> sc_vals;
 };
@@ -350,6 +359,19 @@ orbx_status build_vocabulary(int k, int L, int scoring, int weighting, int64_t n
 	BCU(cudaMemcpy(v->word_id.p, wid.data(), total * 4, cudaMemcpyHostToDevice));
 	BCU(cudaMemcpy(v->desc.p, d.data(), total * 32, cudaMemcpyHostToDevice));
 	BCU(cudaMemcpy(v->weight.p, w.data(), total * 8, cudaMemcpyHostToDevice));
+	{
+		std::vector<int4> info((size_t)total);
+		for (int64_t i = 0; i < total; i++)
+		{
+			const int cs = cstart[i], nch = cstart[i + 1] - cstart[i];
+			bool consecutive = nch > 0;
+			for (int c = 1; c < nch; c++) consecutive = consecutive && cids[cs + c] == cids[cs] + c;
+			info[i] = make_int4(cs, nch, consecutive ? cids[cs] : -1, wid[i]);
+		}
+		BCU(v->node_info.ensure(total));
+		BCU(cudaMemcpy(v->node_info.p, info.data(), total * sizeof(int4), cudaMemcpyHostToDevice));
+		v->V.node_info = v->node_info.p;
+	}
 	v->V.k = k; v->V.L = L; v->V.scoring = scoring; v->V.weighting = weighting; v->V.nnodes = total; v->V.nwords = nwords;
 	v->V.child_start = v->child_start.p; v->V.child_ids = v->child_ids.p; v->V.desc = v->desc.p; v->V.word_id = v->word_id.p; v->V.weight = v->weight.p;
 	*out = v;
@@ -432,6 +454,8 @@ orbx_status orbx_vocabulary_destroy(orbx_vocabulary v)
 	if (!v) return ORBX_OK;
 	cudaSetDevice(v->device);
 	if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+	if (v->h_in) cudaFreeHost(v->h_in);
+	if (v->h_out) cudaFreeHost(v->h_out);
 	delete v;
 	return ORBX_OK;
 }
@@ -456,34 +480,43 @@ orbx_status orbx_bow_transform(orbx_vocabulary v, const uint8_t* desc, int n, in
 	if (n == 0) return ORBX_OK;
 	if (n > BW_MAX_FEATURES) return orbx_fail(ORBX_ERR_INVALID, "more than 16384 features per frame");
 	BCU(cudaSetDevice(v->device));
-	const int cap = n;
-	BCU(v->in_desc.ensure((size_t)cap * 32)); BCU(v->n.ensure(1)); BCU(v->word_ids.ensure(cap)); BCU(v->word_vals.ensure(cap));
-	BCU(v->fv_nodes.ensure(cap)); BCU(v->fv_start.ensure(cap + 1)); BCU(v->fv_items.ensure(cap)); BCU(v->counts.ensure(1));
-	BCU(v->feat_word.ensure(cap)); BCU(v->feat_node.ensure(cap));
+	// One pinned staging buffer each way, one copy each way, one synchronisation: [n | descriptors] in,
+	// [counts | word_vals | word_ids | fv_nodes | fv_start | fv_items | feat_word | feat_node] out.
+	const size_t cap = (size_t)n, c16 = (cap * 4 + 15) & ~(size_t)15;
+	const size_t in_bytes = 16 + cap * 32;
+	const size_t o_vals = 16, o_ids = o_vals + ((cap * 8 + 15) & ~(size_t)15), o_nodes = o_ids + c16, o_start = o_nodes + c16, o_items = o_start + c16 + 16,
+	             o_fw = o_items + c16, o_fn = o_fw + c16, out_bytes = o_fn + c16;
+	if (v->h_cap < std::max(in_bytes, out_bytes))
+	{
+		if (v->h_in) cudaFreeHost(v->h_in);
+		if (v->h_out) cudaFreeHost(v->h_out);
+		v->h_in = v->h_out = nullptr; v->h_cap = 0;
+		const size_t want = 2 * std::max(in_bytes, out_bytes);
+		BCU(cudaMallocHost(&v->h_in, want)); BCU(cudaMallocHost(&v->h_out, want));
+		v->h_cap = want;
+	}
+	BCU(v->in_desc.ensure(in_bytes)); BCU(v->out_block.ensure(out_bytes));
 	cudaStream_t st = v->stream;
-	BCU(cudaMemcpyAsync(v->in_desc.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
-	BCU(cudaMemcpyAsync(v->n.p, &n, 4, cudaMemcpyHostToDevice, st));
-	const orbx_status s = transform_device(v, v->in_desc.p, v->n.p, 1, cap, levelsup, v->word_ids.p, v->word_vals.p, v->fv_nodes.p, v->fv_start.p,
-	                                       v->fv_items.p, v->counts.p, v->feat_word.p, v->feat_node.p, st);
+	memcpy(v->h_in, &n, 4);
+	memcpy(v->h_in + 16, desc, cap * 32);
+	BCU(cudaMemcpyAsync(v->in_desc.p, v->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+	uint8_t* o = v->out_block.p;
+	const orbx_status s = transform_device(v, v->in_desc.p + 16, reinterpret_cast<const int32_t*>(v->in_desc.p), 1, (int)cap, levelsup,
+	                                       reinterpret_cast<int32_t*>(o + o_ids), reinterpret_cast<double*>(o + o_vals), reinterpret_cast<uint32_t*>(o + o_nodes),
+	                                       reinterpret_cast<int32_t*>(o + o_start), reinterpret_cast<uint32_t*>(o + o_items), reinterpret_cast<int2*>(o),
+	                                       reinterpret_cast<int32_t*>(o + o_fw), reinterpret_cast<int32_t*>(o + o_fn), st);
 	if (s != ORBX_OK) return s;
-	int2 c;
-	BCU(cudaMemcpyAsync(&c, v->counts.p, 8, cudaMemcpyDeviceToHost, st));
+	BCU(cudaMemcpyAsync(v->h_out, o, out_bytes, cudaMemcpyDeviceToHost, st));
 	BCU(cudaStreamSynchronize(st));
+	const int2 c = *reinterpret_cast<const int2*>(v->h_out);
 	*n_words = c.x; *n_fv_nodes = c.y;
-	if (c.x > 0)
-	{
-		BCU(cudaMemcpyAsync(word_ids, v->word_ids.p, (size_t)c.x * 4, cudaMemcpyDeviceToHost, st));
-		BCU(cudaMemcpyAsync(word_vals, v->word_vals.p, (size_t)c.x * 8, cudaMemcpyDeviceToHost, st));
-	}
-	BCU(cudaMemcpyAsync(fv_start, v->fv_start.p, (size_t)(c.y + 1) * 4, cudaMemcpyDeviceToHost, st));
-	if (c.y > 0)
-	{
-		BCU(cudaMemcpyAsync(fv_nodes, v->fv_nodes.p, (size_t)c.y * 4, cudaMemcpyDeviceToHost, st));
-		BCU(cudaMemcpyAsync(fv_items, v->fv_items.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));   // only the first fv_start[n_fv_nodes] are meaningful
-	}
-	if (feat_word) BCU(cudaMemcpyAsync(feat_word, v->feat_word.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-	if (feat_node) BCU(cudaMemcpyAsync(feat_node, v->feat_node.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-	BCU(cudaStreamSynchronize(st));
+	memcpy(word_ids, v->h_out + o_ids, (size_t)c.x * 4);
+	memcpy(word_vals, v->h_out + o_vals, (size_t)c.x * 8);
+	memcpy(fv_nodes, v->h_out + o_nodes, (size_t)c.y * 4);
+	memcpy(fv_start, v->h_out + o_start, (size_t)(c.y + 1) * 4);
+	memcpy(fv_items, v->h_out + o_items, (size_t)reinterpret_cast<const int32_t*>(v->h_out + o_start)[c.y] * 4);
+	if (feat_word) memcpy(feat_word, v->h_out + o_fw, cap * 4);
+	if (feat_node) memcpy(feat_node, v->h_out + o_fn, cap * 4);
 	return ORBX_OK;
 }
 

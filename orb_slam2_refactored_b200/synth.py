@@ -390,6 +390,26 @@ def vocabulary(seed, k=10, L=6, prune=0.0, stop=0.1, min_leaf_level=2, hier_flip
     return dict(k=k, L=L, scoring=0, weighting=0, parent=parent, is_leaf=leaf, desc=desc, weights=w, text_weights=text)
 
 
+def scatter_vocabulary(voc, seed):
+    """The same tree with the nodes of every level in random order (parents still precede their children, as loadFromTextFile needs):
+    siblings no longer have consecutive ids, children lists keep their relative order by new id."""
+    r = np.random.RandomState(seed)
+    n = len(voc['parent'])
+    level = np.zeros(n + 1, np.int64)
+    for i in range(n):
+        level[i + 1] = level[voc['parent'][i]] + 1
+    order = np.lexsort((r.rand(n), level[1:]))             # old index (0-based) of the node that becomes new node k + 1
+    new_id = np.zeros(n + 1, np.int64)
+    new_id[order + 1] = np.arange(1, n + 1)
+    out = dict(voc)
+    out['parent'] = new_id[voc['parent'][order]].astype(np.int32)
+    out['is_leaf'] = voc['is_leaf'][order]
+    out['desc'] = voc['desc'][order]
+    out['weights'] = voc['weights'][order]
+    out['text_weights'] = [voc['text_weights'][i] for i in order]
+    return out
+
+
 def write_vocabulary_text(voc, path):
     """ORBvoc.txt layout: header `k L scoring weighting`, then one line per node: parent id, leaf flag, 32 descriptor bytes, weight."""
     with open(path, 'w') as f:

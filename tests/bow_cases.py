@@ -12,6 +12,7 @@ CASES = [
     ('k8L3_idf_dot', dict(seed=4, k=8, L=3), 1200, 1, 5, 2),                       # IDF + DOT_PRODUCT: addIfNotExist, no normalisation
     ('k8L3_tf_dot', dict(seed=4, k=8, L=3), 1200, 1, 5, 1),                        # TF without normalisation: divided by the word count
     ('k20L2_binary_chi', dict(seed=5, k=20, L=2, stop=0.5), 3000, 0, 2, 3),        # BINARY + CHI_SQUARE (L1), half of the words stopped
+    ('k9L3_scattered', dict(seed=8, k=9, L=3, prune=0.2, min_leaf_level=2, scatter=True), 1500, 1, 0, 0),   # siblings without consecutive ids
     ('k2L10_all_stopped', dict(seed=6, k=2, L=10, stop=1.0), 300, 4, 0, 0),        # every word stopped: both outputs empty
 ]
 SMALL = ('k6L5_pruned', 'k8L3_idf_dot', 'k20L2_binary_chi')   # the cases whose reference outputs are committed as golden
@@ -21,7 +22,11 @@ def make(name):
     for c in CASES:
         if c[0] == name:
             _, kw, n, levelsup, scoring, weighting = c
+            kw = dict(kw)
+            scatter = kw.pop('scatter', False)
             voc = synth.vocabulary(**kw)
+            if scatter:
+                voc = synth.scatter_vocabulary(voc, kw['seed'])
             voc['scoring'], voc['weighting'] = scoring, weighting
             feats = synth.vocabulary_features(kw['seed'] + 100, voc, n)
             return voc, feats, levelsup

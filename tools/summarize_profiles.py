@@ -75,9 +75,11 @@ tj = os.path.join(P, f'{R}_traffic.json')
 traffic = json.load(open(tj)) if os.path.exists(tj) else {}      # captures arrive one gpurun call at a time: keep what is already there
 NOTES = {'k_guided_search': 'one search, 1000 keypoints x 1000 map points (tools/guided_probe.py), a cluster of 8 CTAs',
          'k_remap_to_l0': 'one launch of 256 frames 752x480 (bench.py remap block)',
-         'k_stereo_match': 'one launch of 64 C2 stereo pairs (bench.py stereo block)'}
+         'k_stereo_match': 'one launch of 64 C2 stereo pairs (bench.py stereo block)',
+         'k_bow_descend': 'one launch of 256 frames x 1000 descriptors through the k 10 / L 6 vocabulary (bench.py bow block)',
+         'k_bow_finalize': 'one launch of 256 frames (bench.py bow block), one CTA per frame'}
 for k in ('k_fast_cells', 'k_gauss7', 'k_pyramid_resize', 'k_orient_describe', 'k_quadtree', 'k_knn2_partial', 'k_guided_search', 'k_remap_to_l0',
-          'k_stereo_match'):
+          'k_stereo_match', 'k_bow_descend', 'k_bow_finalize', 'k_best_in_windows'):
     d = full(k)
     if d and 'dram__bytes_read.sum' in d:
         traffic[k] = {'dram_bytes_per_launch': to_bytes(*d['dram__bytes_read.sum']) + to_bytes(*d['dram__bytes_write.sum']),
