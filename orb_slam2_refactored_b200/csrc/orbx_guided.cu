@@ -795,6 +795,7 @@ struct orbx_frame_s
 	GBuf<uint32_t> list;
 	GBuf<float> qf;
 	GBuf<int> qi, qoff, qidx;
+	std::vector<float> h_angle;     // keypoint angles on the host (CheckOrientation of the host-side matchers); empty = not fetched yet
 
 	cudaError_t ensure_staging(size_t in_bytes, size_t out_bytes)
 	{
@@ -950,6 +951,8 @@ orbx_status assign_frame(orbx_frame_s* f, const orbx_frame_view* v)
 	if (v->n > 0)
 	{
 		memcpy(f->h_in, v->kps_un, (size_t)v->n * sizeof(orbx_keypoint));
+		f->h_angle.resize((size_t)v->n);
+		for (int i = 0; i < v->n; i++) f->h_angle[i] = v->kps_un[i].angle;
 		memcpy(f->h_in + o_desc, v->desc, (size_t)v->n * 32);
 		float* ur = reinterpret_cast<float*>(f->h_in + o_ur);
 		if (v->uright) memcpy(ur, v->uright, (size_t)v->n * sizeof(float));
@@ -1041,6 +1044,7 @@ orbx_status orbx_frame_assign_device(orbx_frame f, const orbx_keypoint* d_kps_un
 		return orbx_fail(ORBX_ERR_INVALID, "empty image bounds (the reference divides by zero, src/Frame.cc:73-74)");
 	GCU(cudaSetDevice(f->device));
 	f->n = n; f->nlevels = nlevels; f->b = *bounds;
+	f->h_angle.clear();
 	f->invW = GRID_COLS / (bounds->maxx - bounds->minx);
 	f->invH = GRID_ROWS / (bounds->maxy - bounds->miny);
 	for (int i = 0; i < 16; i++) f->sf[i] = i < nlevels ? scale_factors[i] : 0.f;
@@ -1839,15 +1843,16 @@ orbx_status orbx_search_for_triangulation(orbx_frame f1, const orbx_feature_vect
 	if (check_orientation)
 	{
 		// CheckOrientation(keyframe2->keypointsUn, keyframe1->keypointsUn, tmpMatchIds, matches12) (:853-854, :249-309) on the host copy of
-		// the angles: 30-bin histogram of angle2 - angle1, the three largest bins survive (ComputeThreeMaxima :255-294)
-		std::vector<float> ang1((size_t)f1->n), ang2((size_t)f2->n);
-		{
-			std::vector<orbx_keypoint> k1((size_t)f1->n), k2((size_t)f2->n);
-			GCU(cudaMemcpy(k1.data(), f1->kps.p, (size_t)f1->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
-			GCU(cudaMemcpy(k2.data(), f2->kps.p, (size_t)f2->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
-			for (int i = 0; i < f1->n; i++) ang1[i] = k1[i].angle;
-			for (int i = 0; i < f2->n; i++) ang2[i] = k2[i].angle;
-		}
+		// the angles: 30-bin histogram of angle2 - angle1, the bins past the three largest (after std::sort by size) are erased
+		for (orbx_frame_s* f : { f1, f2 })
+			if ((int)f->h_angle.size() != f->n)      // a frame assigned from device pointers: fetch the angles once
+			{
+				std::vector<orbx_keypoint> k((size_t)f->n);
+				GCU(cudaMemcpy(k.data(), f->kps.p, (size_t)f->n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
+				f->h_angle.resize((size_t)f->n);
+				for (int i = 0; i < f->n; i++) f->h_angle[i] = k[i].angle;
+			}
+		const std::vector<float>& ang1 = f1->h_angle; const std::vector<float>& ang2 = f2->h_angle;
 		n = orbx_check_orientation_host(ang2.data(), ang1.data(), tmp, matches12, n);
 	}
 	if (nmatches) *nmatches = n;
