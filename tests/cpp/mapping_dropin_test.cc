@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "orbx/GuidedMatcher.h"
+#include "orbx/ORBVocabulary.h"
 
 #define ORACLE_PREFIX orc_
 #include "oracle_api.h"
@@ -195,7 +196,7 @@ struct FlatFv
 
 }  // namespace
 
-int main()
+int main(int argc, char** argv)
 {
 	try
 	{
@@ -410,7 +411,48 @@ int main()
 			}
 		}
 
-		printf("OK fuse %d, fuse sim3 %d, sim3 %d, triangulation %d\n", summary[0], summary[1], summary[2], summary[3]);
+		// ---- ORBVocabulary::loadFromTextFile / transform / score through std::map types shaped like DBoW2::BowVector / FeatureVector
+		int bow_words = -1;
+		if (argc > 1)
+		{
+			ORB_SLAM2::b200::ORBVocabulary voc;
+			if (voc.loadFromTextFile("/nonexistent/voc.txt")) { printf("loadFromTextFile accepted a missing file\n"); return 1; }
+			if (!voc.loadFromTextFile(argv[1])) { printf("loadFromTextFile rejected %s\n", argv[1]); return 1; }
+			void* ov = orc_voc_load_text(argv[1]);
+			if (!ov) { printf("oracle rejected the vocabulary\n"); return 1; }
+			const int nf = 900;
+			std::vector<unsigned char> fd((size_t)nf * 32);
+			for (auto& b : fd) b = (unsigned char)rng();
+			std::vector<cv::Mat> features;
+			for (int i = 0; i < nf; i++) features.push_back(cv::Mat(1, 32, CV_8U, &fd[(size_t)i * 32], 32));
+			std::map<unsigned, double> bv, bv2;
+			std::map<unsigned, std::vector<unsigned>> fvec;
+			voc.transform(features, bv, fvec, 2);
+			std::vector<int32_t> wi(nf + 1), fs(nf + 2); std::vector<double> wv(nf + 1); std::vector<uint32_t> fnodes(nf + 1), fi(nf + 1);
+			int32_t nfv = 0;
+			const int nw = orc_bow_transform(ov, fd.data(), nf, 2, wi.data(), wv.data(), fnodes.data(), fs.data(), fi.data(), &nfv);
+			if ((int)bv.size() != nw || (int)fvec.size() != nfv) { printf("BoW sizes %zu/%zu vs %d/%d\n", bv.size(), fvec.size(), nw, nfv); return 1; }
+			int k = 0;
+			for (const auto& e : bv) { if ((int)e.first != wi[k] || memcmp(&e.second, &wv[k], 8) != 0) { printf("BowVector entry %d\n", k); return 1; } k++; }
+			k = 0;
+			for (const auto& e : fvec)
+			{
+				if (e.first != fnodes[k] || (int)e.second.size() != fs[k + 1] - fs[k] || memcmp(e.second.data(), &fi[fs[k]], 4 * e.second.size()) != 0) { printf("FeatureVector node %d\n", k); return 1; }
+				k++;
+			}
+			std::vector<cv::Mat> half(features.begin(), features.begin() + nf / 2);
+			std::map<unsigned, std::vector<unsigned>> fv2;
+			voc.transform(half, bv2, fv2, 2);
+			std::vector<int32_t> wi2(nf + 1); std::vector<double> wv2(nf + 1);
+			const int nw2 = orc_bow_transform(ov, fd.data(), nf / 2, 2, wi2.data(), wv2.data(), fnodes.data(), fs.data(), fi.data(), &nfv);
+			const double want_s = orc_bow_score(ov, wi.data(), wv.data(), nw, wi2.data(), wv2.data(), nw2), got_s = voc.score(bv, bv2);
+			if (memcmp(&want_s, &got_s, 8) != 0) { printf("score %.17g vs %.17g\n", got_s, want_s); return 1; }
+			orc_voc_destroy(ov);
+			bow_words = nw;
+			if (nw < 100) { printf("vocabulary too thin (%d words)\n", nw); return 1; }
+		}
+
+		printf("OK fuse %d, fuse sim3 %d, sim3 %d, triangulation %d, bow words %d\n", summary[0], summary[1], summary[2], summary[3], bow_words);
 		return 0;
 	}
 	catch (const cv::Exception& e)

@@ -18,7 +18,7 @@ def build_exe():
     lib = build.build()
     bindings.build()
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    hdrs = [os.path.join(ROOT, 'include', 'orbx', h) for h in ('ORBextractor.h', 'ORBmatcher.h', 'GuidedMatcher.h')]
+    hdrs = [os.path.join(ROOT, 'include', 'orbx', h) for h in ('ORBextractor.h', 'ORBmatcher.h', 'GuidedMatcher.h', 'ORBVocabulary.h')]
     for name, exe in (('dropin_test.cc', EXE), ('guided_dropin_test.cc', EXE_GUIDED), ('mapping_dropin_test.cc', EXE_MAPPING)):
         src = os.path.join(ROOT, 'tests', 'cpp', name)
         if os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(src), os.path.getmtime(lib)] + [os.path.getmtime(h) for h in hdrs]):
@@ -58,7 +58,10 @@ def test_guided_dropin_matches_oracle():
 def test_mapping_dropin_matches_oracle():
     """Fuse x2, SearchBySim3 and SearchForTriangulation of include/orbx/GuidedMatcher.h: KeyFrame / MapPoint / Sim3 types with the
     reference's member names; results and the order of the map mutations equal the oracle's."""
+    from orb_slam2_refactored_b200 import synth
     build_exe()
-    r = subprocess.run([EXE_MAPPING], capture_output=True, timeout=300)
+    voc_path = os.path.join(os.path.dirname(EXE_MAPPING), 'voc_k10L3.txt')
+    synth.write_vocabulary_text(synth.vocabulary(5, 10, 3), voc_path)       # ORBVocabulary::loadFromTextFile / transform / score as well
+    r = subprocess.run([EXE_MAPPING, voc_path], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     assert r.stdout.decode().startswith('OK')
