@@ -727,488 +727,15 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 //     because its order among equal sizes decides which nodes are split before the quota break (:666-667).
 // =====================================================================================================
 #define QT_THREADS 256
-#define QT_WARPS 8
-
-struct QNode
-{
-	uint16_t x0, y0, x1, y1;
-	uint32_t beg;
-	uint32_t cnt;     // bit 31: which ping-pong buffer holds the segment
-};
-#define QN_CNT(n) ((n).cnt & 0x7fffffffu)
-#define QN_BUF(n) ((n).cnt >> 31)
-
-template <class Pred, class Emit>
-__device__ __forceinline__ int block_ordered(int n, int* s_w, Pred pred, Emit emit)
-{
-	// calls emit(i, rank) for every i in [0,n) with pred(i), rank = number of earlier true elements. Uniform result.
-	const int tid = threadIdx.x, warp = tid >> 5;
-	int base = 0;
-	for (int c0 = 0; c0 < n; c0 += QT_THREADS)
-	{
-		const int i = c0 + tid;
-		const bool p = (i < n) && pred(i);
-		const unsigned bal = __ballot_sync(0xffffffffu, p);
-		if ((tid & 31) == 0) s_w[warp] = __popc(bal);
-		__syncthreads();
-		int wbase = 0, tot = 0;
-#pragma unroll
-		for (int w = 0; w < QT_WARPS; w++)
-		{
-			const int v = s_w[w];
-			if (w < warp) wbase += v;
-			tot += v;
-		}
-		if (p) emit(i, base + wbase + __popc(bal & lanemask_lt()));
-		base += tot;
-		__syncthreads();
-	}
-	return base;
-}
-
-template <class Get, class Put>
-__device__ __forceinline__ int block_exscan(int n, int* s_w, Get get, Put put)
-{
-	// put(i, exclusive prefix of get) for i in [0,n); returns the total. Uniform result.
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	int base = 0;
-	for (int c0 = 0; c0 < n; c0 += QT_THREADS)
-	{
-		const int i = c0 + tid;
-		const int v = (i < n) ? get(i) : 0;
-		int inc = v;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			const int t = __shfl_up_sync(0xffffffffu, inc, d);
-			if (lane >= d) inc += t;
-		}
-		if (lane == 31) s_w[warp] = inc;
-		__syncthreads();
-		int wbase = 0, tot = 0;
-#pragma unroll
-		for (int w = 0; w < QT_WARPS; w++)
-		{
-			const int t = s_w[w];
-			if (w < warp) wbase += t;
-			tot += t;
-		}
-		if (i < n) put(i, base + wbase + inc - v);
-		base += tot;
-		__syncthreads();
-	}
-	return base;
-}
-
-// std::sort replayed by the whole CTA with the SAME result as the serial algorithm. Two facts make that possible:
-//  * after a partition step the two sub-ranges are never touched together again, so __introsort_loop's "recurse right,
-//    iterate left" can run both sides at the same time: every round, each pending range (> 16 elements) is partitioned by
-//    one thread; a range keeps the depth budget it would have had (both sides inherit depth - 1; budget 0 = heapsort);
-//  * the partition leaves every element of a left range "not after" every element of the range to its right (sizes >= pivot
-//    on the left, <= pivot on the right), so __final_insertion_sort never moves an element across a range boundary: it is
-//    a stable insertion sort of every final range (<= 16 elements) on its own.
-// Time is ~2n serial steps (n + n/2 + n/4 ...) instead of ~1.4 n log2 n.
-struct QSeg { int first, last, depth; };
-
-__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, int2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */)
-{
-	const int tid = threadIdx.x;
-	if (tid == 0)
-	{
-		int lg = 0;
-		for (int m = n; m > 1; m >>= 1) ++lg;
-		s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
-		if (n > 16) { segq[0] = { 0, n, 2 * lg }; s_cnt[0] = 1; }
-		else if (n > 1) { leaf[0] = make_int2(0, n); s_cnt[2] = 1; }
-	}
-	__syncthreads();
-	int cur = 0;
-	for (;;)
-	{
-		const int ns = s_cnt[cur];
-		if (ns == 0) break;
-		__syncthreads();
-		if (tid == 0) s_cnt[cur ^ 1] = 0;
-		__syncthreads();
-		QSeg* in = segq + cur * segcap;
-		QSeg* out = segq + (cur ^ 1) * segcap;
-		for (int si = tid; si < ns; si += QT_THREADS)
-		{
-			const QSeg sg = in[si];
-			if (sg.depth == 0) { qs_heapsort(a, sg.first, sg.last); continue; }     // fully sorted, no insertion pass needed
-			const int cut = qs_partition(a, sg.first, sg.last);
-#pragma unroll
-			for (int side = 0; side < 2; side++)
-			{
-				const int f0 = side ? cut : sg.first, l0 = side ? sg.last : cut;
-				if (l0 - f0 > 16) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = { f0, l0, sg.depth - 1 };
-				else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_int2(f0, l0);
-			}
-		}
-		__syncthreads();
-		cur ^= 1;
-	}
-	const int nleaf = s_cnt[2];
-	for (int li = tid; li < nleaf; li += QT_THREADS) qs_insertion(a, leaf[li].x, leaf[li].y);
-	__syncthreads();
-}
-
-__device__ __forceinline__ int quadrant_of(uint32_t v, int xm, int ym)
-{
-	const int x = orbx_px(v), y = orbx_py(v);
-	return x < xm ? (y < ym ? 0 : 2) : (y < ym ? 1 : 3);
-}
-
-// Stable 4-way partition of one big node by the whole CTA (see the call site).
-__device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint32_t* buf1, uint32_t* cc, int (*s_bigc)[4], int (*s_bigw)[QT_WARPS][4])
-{
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int cnt = (int)QN_CNT(nd);
-	const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
-	uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
-	const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
-	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-	for (int i = tid; i < cnt; i += QT_THREADS)
-	{
-		const int q = quadrant_of(src[i], xm, ym);
-		c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
-	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1)
-	{
-		c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-		c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
-	}
-	if (lane == 0) { s_bigc[warp][0] = c0; s_bigc[warp][1] = c1; s_bigc[warp][2] = c2; s_bigc[warp][3] = c3; }
-	__syncthreads();
-	int tot[4], run[4];
-#pragma unroll
-	for (int q = 0; q < 4; q++)
-	{
-		tot[q] = 0;
-#pragma unroll
-		for (int w = 0; w < QT_WARPS; w++) tot[q] += s_bigc[w][q];
-	}
-	run[0] = 0; run[1] = tot[0]; run[2] = tot[0] + tot[1]; run[3] = tot[0] + tot[1] + tot[2];
-	int par = 0;
-	for (int i0 = 0; i0 < cnt; i0 += QT_THREADS, par ^= 1)
-	{
-		const int i = i0 + tid;
-		const bool ok = i < cnt;
-		const uint32_t v = ok ? src[i] : 0u;
-		const int q = ok ? quadrant_of(v, xm, ym) : -1;
-		unsigned bq[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++) bq[k] = __ballot_sync(0xffffffffu, q == k);
-		if (lane < 4) s_bigw[par][warp][lane] = __popc(lane == 0 ? bq[0] : lane == 1 ? bq[1] : lane == 2 ? bq[2] : bq[3]);
-		__syncthreads();                     // one barrier per chunk: the count buffers alternate
-		int before = 0, mine = 0, chunk_tot[4];
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-		{
-			chunk_tot[k] = 0;
-#pragma unroll
-			for (int w = 0; w < QT_WARPS; w++)
-			{
-				const int x = s_bigw[par][w][k];
-				chunk_tot[k] += x;
-				if (w < warp && k == q) before += x;
-			}
-			if (k == q) mine = run[k] + __popc(bq[k] & lanemask_lt());
-		}
-		if (ok) dst[mine + before] = v;
-#pragma unroll
-		for (int k = 0; k < 4; k++) run[k] += chunk_tot[k];
-	}
-	if (tid == 0) { cc[0] = tot[0]; cc[1] = tot[1]; cc[2] = tot[2]; cc[3] = tot[3]; }
-	__syncthreads();
-}
-
-// BIG selects the variant with the CTA-parallel sort and big-node partition (4K-class levels); the plain variant keeps the
-// register count at 40 for VGA-class levels, where occupancy matters more than the serial tails.
-template <bool BIG>
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off, const int big_node_min, const int par_sort_min, unsigned long long* dbg)
-{
-	int dbgk = 0;
-#define QT_STAMP() do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && dbgk < 63) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[1 + dbgk++] = t_; dbg[0] = dbgk; } } while (0)
-	QT_STAMP();
-	extern __shared__ __align__(16) uint8_t qsm[];
-	const int M = P.node_cap;
-	QNode* listA = reinterpret_cast<QNode*>(qsm);
-	QNode* listB = listA + M;
-	uint64_t* items = reinterpret_cast<uint64_t*>(listB + M);          // phase-2 sort items
-	uint32_t* childcnt = reinterpret_cast<uint32_t*>(items + M);       // [M][4]
-	uint32_t* proc = childcnt + 4 * M;                                 // positions (old list) to divide, processing order
-	uint32_t* pbase = proc + M;                                        // exclusive scan of non-empty child counts
-	int2* leaf = reinterpret_cast<int2*>(pbase + M);                   // ranges (<= 16 items) left for the insertion pass of the sort
-	const int segcap = M / 16 + 4;
-	QSeg* segq = reinterpret_cast<QSeg*>(leaf + M);                    // [2][segcap] ranges still to be partitioned
-	uint8_t* gone = reinterpret_cast<uint8_t*>(segq + 2 * segcap);     // old-list positions removed by this pass
-	__shared__ int s_w[QT_WARPS];
-	__shared__ int s_K;
-	__shared__ int s_sort[3];
-	__shared__ int s_rootcnt[ORBX_MAX_ROOTS];
-	__shared__ int s_bigc[QT_WARPS][4], s_bigw[2][QT_WARPS][4];
-
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int lvl = blockIdx.y, f = blockIdx.x;      // x = frame: all level-0 CTAs (the longest) are scheduled first
-	const OrbxLevel& L = P.lv[lvl];
-	const int ncell = L.ncx * L.ncy;
-	const int* __restrict__ ccount = P.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
-	int* __restrict__ coff = cell_off + (int64_t)f * P.cells_per_frame + L.cell_base;
-	const uint32_t* __restrict__ slots = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base;
-	uint32_t* buf0 = P.qbuf0 + (int64_t)f * P.cand_per_frame + L.cand_base;
-	uint32_t* buf1 = P.qbuf1 + (int64_t)f * P.cand_per_frame + L.cand_base;
-
-	// ---- K3: cell-major compaction of the candidate slots (DetectFAST's push_back order, :532-537)
-	const int n = block_exscan(ncell, s_w, [&](int i) { return ccount[i]; }, [&](int i, int off) { coff[i] = off; });
-	if (tid == 0) P.cand_count[(int64_t)f * P.nlevels + lvl] = n;
-	__syncthreads();
-	const int nroots = L.n_roots;
-	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
-	// 8 lanes per cell (a cell holds ~15 candidates): four cells per warp in flight, so the chain of dependent loads
-	// (count, offset, slots) is walked ncell / 32 times per warp instead of ncell / 8 times
-	for (int cidx = tid >> 3; cidx < ncell; cidx += QT_THREADS / 8)
-	{
-		const int cnt = ccount[cidx], off = coff[cidx];
-		const uint32_t* src = slots + (int64_t)cidx * L.cell_cap;
-		for (int k = tid & 7; k < cnt; k += 8) gathered[off + k] = src[k];
-	}
-	__syncthreads();
-	QT_STAMP();
-	if (n == 0)
-	{
-		if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = 0;    // early return of :544-545 (dst == src stays empty)
-		return;
-	}
-
-	// ---- roots (:547-581): vertical strips; candidate -> strip by the host-built table (double arithmetic there)
-	const int* __restrict__ rootx = P.root_x + L.root_base;
-	const uint8_t* __restrict__ rlut = P.root_lut + L.rootlut_base;
-	if (nroots == 1)
-	{
-		if (tid == 0) s_rootcnt[0] = n;
-	}
-	else
-	{
-		int at = 0;
-		for (int r = 0; r < nroots; r++)
-		{
-			const int c = block_ordered(n, s_w, [&](int i) { return rlut[orbx_px(buf1[i])] == r; },
-			                            [&](int i, int rank) { buf0[at + rank] = buf1[i]; });
-			if (tid == 0) s_rootcnt[r] = c;
-			at += c;
-		}
-	}
-	__syncthreads();
-	int listLen = 0;
-	{
-		int at = 0;
-		for (int r = 0; r < nroots; r++)
-		{
-			const int c = s_rootcnt[r];
-			if (c > 0)
-			{
-				if (tid == 0)
-				{
-					QNode nd;
-					nd.x0 = (uint16_t)rootx[r]; nd.y0 = (uint16_t)L.miny; nd.x1 = (uint16_t)rootx[r + 1]; nd.y1 = (uint16_t)L.maxy;
-					nd.beg = (uint32_t)at; nd.cnt = (uint32_t)c;     // buffer 0
-					listA[listLen] = nd;
-				}
-				listLen++;
-			}
-			at += c;
-		}
-	}
-	__syncthreads();
-
-	QT_STAMP();
-	QNode* cur = listA;
-	QNode* nxt = listB;
-	const int quota = L.quota;
-	int phase = 1, lastP = 0;
-	for (;;)
-	{
-		// ---- which nodes does this pass divide, and in which order
-		int np;
-		if (phase == 1)
-		{
-			// every divisible node, list order (:588-631)
-			np = block_ordered(listLen, s_w, [&](int i) { return QN_CNT(cur[i]) > 1; }, [&](int i, int rank) { proc[rank] = i; });
-		}
-		else
-		{
-			// children of the previous pass with > 1 point, in push order (= back to front of the first lastP list
-			// entries), sorted by size descending with libstdc++'s tie order (:635-643)
-			np = block_ordered(lastP, s_w, [&](int g) { return QN_CNT(cur[lastP - 1 - g]) > 1; },
-			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
-			__syncthreads();
-			if (BIG && np > par_sort_min)
-				qs_sort_block(items, np, segq, segcap, leaf, s_sort);      // large levels (4K): ~2n serial steps instead of ~1.4 n log2 n
-			else
-			{
-				if (tid == 0) qs_sort_serial(items, np);
-				__syncthreads();
-			}
-			for (int i = tid; i < np; i += QT_THREADS) proc[i] = (uint32_t)(items[i] & 0xffffffffu);
-		}
-		for (int i = tid; i < listLen; i += QT_THREADS) gone[i] = 0;
-		__syncthreads();
-		QT_STAMP();
-
-		// ---- big nodes (the first passes of a large level: one node can hold tens of thousands of candidates) are divided by
-		//      the whole CTA: chunks of QT_THREADS elements in order, position = quadrant base + earlier chunks + earlier warps of the
-		//      chunk + earlier lanes of the warp, i.e. the same stable 4-way partition as the warp version below.
-		if (BIG && np <= 64)
-			for (int t = 0; t < np; t++)
-			{
-				const QNode nd = cur[proc[t]];
-				if ((int)QN_CNT(nd) >= big_node_min)            // uniform: every thread sees the same node
-					qt_divide_big(nd, buf0, buf1, childcnt + 4 * t, s_bigc, s_bigw);
-			}
-
-		// ---- divide (speculatively all of them; Phase 2 may stop early, parents stay intact in their buffer)
-		for (int t = warp; t < np; t += QT_WARPS)
-		{
-			const QNode nd = cur[proc[t]];
-			const int cnt = (int)QN_CNT(nd);
-			if (BIG && np <= 64 && cnt >= big_node_min) continue;  // done by the whole CTA above
-			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
-			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
-			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
-			int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-			for (int i0 = 0; i0 < cnt; i0 += 32)
-			{
-				const int i = i0 + lane;
-				const bool ok = i < cnt;
-				const int q = ok ? quadrant_of(src[i], xm, ym) : -1;
-				c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
-				c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
-				c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
-				c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
-			}
-			int a0 = 0, a1 = c0, a2 = c0 + c1, a3 = c0 + c1 + c2;
-			for (int i0 = 0; i0 < cnt; i0 += 32)
-			{
-				const int i = i0 + lane;
-				const bool ok = i < cnt;
-				const uint32_t v = ok ? src[i] : 0u;
-				const int q = ok ? quadrant_of(v, xm, ym) : -1;
-				const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
-				const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
-				const unsigned lt = lanemask_lt();
-				if (q == 0) dst[a0 + __popc(b0 & lt)] = v;
-				else if (q == 1) dst[a1 + __popc(b1 & lt)] = v;
-				else if (q == 2) dst[a2 + __popc(b2 & lt)] = v;
-				else if (q == 3) dst[a3 + __popc(b3 & lt)] = v;
-				a0 += __popc(b0); a1 += __popc(b1); a2 += __popc(b2); a3 += __popc(b3);
-			}
-			if (lane == 0)
-			{
-				childcnt[4 * t + 0] = c0; childcnt[4 * t + 1] = c1; childcnt[4 * t + 2] = c2; childcnt[4 * t + 3] = c3;
-			}
-		}
-		__syncthreads();
-
-		QT_STAMP();
-		// ---- how many of them are really processed: Phase 2 breaks once the list reaches the quota (:666-667)
-		auto nkids = [&](int t) { return (int)(childcnt[4 * t] > 0) + (int)(childcnt[4 * t + 1] > 0) + (int)(childcnt[4 * t + 2] > 0) + (int)(childcnt[4 * t + 3] > 0); };
-		const int totalPush = block_exscan(np, s_w, nkids, [&](int t, int ex) { pbase[t] = ex; });
-		int K = np, Ppush = totalPush;
-		if (phase == 2)
-		{
-			if (tid == 0) s_K = np;
-			__syncthreads();
-			// list length after processing t+1 items = listLen + pbase[t] + nkids(t) - (t+1); non-decreasing in t
-			for (int t = tid; t < np; t += QT_THREADS)
-			{
-				const int after = listLen + (int)pbase[t] + nkids(t) - (t + 1);
-				const int before = listLen + (int)pbase[t] - t;
-				if (after >= quota && before < quota) s_K = t + 1;
-			}
-			__syncthreads();
-			K = s_K;
-			Ppush = (K < np) ? (int)pbase[K] : totalPush;
-			__syncthreads();
-		}
-
-		QT_STAMP();
-		// ---- rebuild the list: children in reverse push order, then the surviving old nodes in old order
-		for (int t = tid; t < K; t += QT_THREADS)
-		{
-			const int pos = proc[t];
-			gone[pos] = 1;
-			const QNode nd = cur[pos];
-			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
-			const uint32_t nb = (QN_BUF(nd) ^ 1u) << 31;
-			uint32_t at = nd.beg;
-			int g = (int)pbase[t];
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-			{
-				const uint32_t c = childcnt[4 * t + q];
-				if (c > 0)
-				{
-					QNode ch;
-					ch.x0 = (q & 1) ? (uint16_t)xm : nd.x0; ch.x1 = (q & 1) ? nd.x1 : (uint16_t)xm;
-					ch.y0 = (q & 2) ? (uint16_t)ym : nd.y0; ch.y1 = (q & 2) ? nd.y1 : (uint16_t)ym;
-					ch.beg = at; ch.cnt = c | nb;
-					nxt[Ppush - 1 - g] = ch;
-					g++;
-				}
-				at += c;
-			}
-		}
-		__syncthreads();
-		const int kept = block_ordered(listLen, s_w, [&](int i) { return gone[i] == 0; }, [&](int i, int rank) { nxt[Ppush + rank] = cur[i]; });
-		const int newLen = Ppush + kept;
-		{ QNode* t = cur; cur = nxt; nxt = t; }
-		const int prevLen = listLen;
-		listLen = newLen;
-		lastP = Ppush;
-		__syncthreads();
-		if (listLen >= quota || listLen == prevLen)
-			break;
-		if (phase == 1)
-		{
-			// toExpand = children of this pass with > 1 point (:617-622); switch to largest-first near the quota (:633-634)
-			const int ndiv = block_ordered(lastP, s_w, [&](int i) { return QN_CNT(cur[i]) > 1; }, [&](int, int) {});
-			if (listLen + 3 * ndiv > quota) phase = 2;
-		}
-	}
-
-	QT_STAMP();
-	// ---- keep the best response of every node, first wins ties, list order (:677-692)
-	uint32_t* __restrict__ sel = P.sel + (int64_t)f * P.sel_per_frame + L.sel_base;
-	// 8 lanes per node (final nodes hold ~10 candidates): four nodes per warp in flight. The loop bound is rounded up so that every
-	// lane of a warp takes part in the shuffles.
-	for (int i0 = 0; i0 < listLen; i0 += QT_THREADS / 8)
-	{
-		const int i = i0 + (tid >> 3);
-		const bool live = i < listLen;
-		const QNode nd = cur[live ? i : 0];
-		const int cnt = live ? (int)QN_CNT(nd) : 0;
-		const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
-		int bestr = 0, besti = 0x7fffffff;
-		for (int k = tid & 7; k < cnt; k += 8)
-		{
-			const int r = orbx_pr(src[k]);
-			if (r > bestr) { bestr = r; besti = k; }
-		}
-#pragma unroll
-		for (int d = 4; d > 0; d >>= 1)
-		{
-			const int orr = __shfl_xor_sync(0xffffffffu, bestr, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
-			if (orr > bestr || (orr == bestr && oi < besti)) { bestr = orr; besti = oi; }
-		}
-		if (live && (tid & 7) == 0) sel[i] = src[besti];
-	}
-	if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = listLen;
-	QT_STAMP();
-#undef QT_STAMP
-}
-
+#define QT_NS qt256
+#include "orbx_quadtree.cuh"
+#undef QT_THREADS
+#undef QT_NS
+#define QT_THREADS 128
+#define QT_NS qt128
+#include "orbx_quadtree.cuh"
+#undef QT_THREADS
+#undef QT_NS
 // =====================================================================================================
 // K6  gauss7x7_u8 — cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's 8.8 fixed point
 //     (src/ORBextractor.cc:799). Tile 128 x 32 with a 3 px halo in shared memory.
@@ -1656,13 +1183,14 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	if (want_dbg) cudaMemsetAsync(dbg, 0, 64 * 8, st);
 	if (force_big >= 0 ? force_big != 0 : (large_plan || small_batch))
 	{
-		cudaFuncSetAttribute(k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_quadtree<true><<<grid, QT_THREADS, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+		cudaFuncSetAttribute(qt256::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		qt256::k_quadtree<true><<<grid, 256, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
 	}
 	else
 	{
-		cudaFuncSetAttribute(k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_quadtree<false><<<grid, QT_THREADS, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+		// large batches: 128-thread CTAs, so that more of them share an SM while others are in their serial phases (orbx_quadtree.cuh)
+		cudaFuncSetAttribute(qt128::k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		qt128::k_quadtree<false><<<grid, 128, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 	}
 	if (want_dbg)
 	{
