@@ -111,6 +111,17 @@ def test_score_pairs(orbx, oracle_port):
     assert abs(got[0] - 1.0) < 1e-12 and got[len(vecs) - 1] == 0.0
 
 
+def test_empty_vocabulary(orbx, tmp_path):
+    """A header-only file loads (the reference accepts it) and leaves a vocabulary without words: transform returns empty vectors
+    (TemplatedVocabulary.h:1137-1140)."""
+    p = tmp_path / 'empty.txt'
+    p.write_text('10 6 0 0\n')
+    v = orbx.ORBVocabulary()
+    assert v.loadFromTextFile(str(p)) and v.empty() and v.info()['nodes'] == 1
+    (wi, wv), (fn, fs, fi) = v.transform(np.random.RandomState(0).randint(0, 256, (50, 32)).astype(np.uint8), 4)
+    assert len(wi) == 0 and len(fn) == 0 and list(fs) == [0]
+
+
 def test_loader_rejects_what_the_reference_rejects(orbx, tmp_path):
     for header in ('21 6 0 0', '10 11 0 0', '10 0 0 0', '10 6 6 0', '10 6 0 4'):
         p = tmp_path / 'bad.txt'
