@@ -36,12 +36,11 @@ struct VocabDev
 	int k, L, scoring, weighting;
 	int64_t nnodes;              // including the root (node 0)
 	int64_t nwords;
-	const int32_t* child_start;  // [nnodes + 1]
 	const int4* node_info;       // [nnodes]: first slot in child_ids, number of children, id of the first child when the children's ids are
-	                             // consecutive (the order HKmeansStep creates them in) else -1, word id: one 16-byte load per level instead of a chain
+	                             // consecutive (the order HKmeansStep creates them in) else -1, Node::word_id (0 for nodes that are not words, as
+	                             // in the reference): one 16-byte load per level instead of a chain of dependent loads
 	const int32_t* child_ids;    // [nnodes - 1], push_back order of Node::children
 	const uint32_t* desc;        // [nnodes][8]
-	const int32_t* word_id;      // [nnodes]: Node::word_id (0 for nodes that are not words, as in the reference)
 	const double* weight;        // [nnodes]: Node::weight
 };
 
@@ -297,17 +296,15 @@ struct orbx_vocabulary_s
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	VocabDev V = {};
-	Buf<int32_t> child_start, child_ids, word_id;
+	Buf<int32_t> child_ids;
 	Buf<int4> node_info;
 	Buf<uint32_t> desc;
 	Buf<double> weight;
 	// scratch of the transform calls
-	Buf<int32_t> feat_word, feat_node, n, word_ids, fv_start;
-	Buf<uint32_t> fv_nodes, fv_items;
-	Buf<double> feat_w, word_vals;
+	Buf<int32_t> feat_word, feat_node;
+	Buf<double> feat_w;
 	Buf<uint8_t> in_desc, out_block;
 	uint8_t* h_in = nullptr; uint8_t* h_out = nullptr; size_t h_cap = 0;   // pinned staging of orbx_bow_transform
-	Buf<int2> counts;
 	Buf<BowPair> pairs; Buf<double> scores; Buf<int32_t> sc_ids; Buf<double> sc_vals;
 };
 
@@ -352,11 +349,9 @@ orbx_status build_vocabulary(int k, int L, int scoring, int weighting, int64_t n
 	v->device = device;
 	BCU(cudaSetDevice(device));
 	BCU(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-	BCU(v->child_start.ensure(total + 1)); BCU(v->child_ids.ensure(cids.size())); BCU(v->word_id.ensure(total));
+	BCU(v->child_ids.ensure(cids.size()));
 	BCU(v->desc.ensure(total * 8)); BCU(v->weight.ensure(total));
-	BCU(cudaMemcpy(v->child_start.p, cstart.data(), (total + 1) * 4, cudaMemcpyHostToDevice));
 	BCU(cudaMemcpy(v->child_ids.p, cids.data(), cids.size() * 4, cudaMemcpyHostToDevice));
-	BCU(cudaMemcpy(v->word_id.p, wid.data(), total * 4, cudaMemcpyHostToDevice));
 	BCU(cudaMemcpy(v->desc.p, d.data(), total * 32, cudaMemcpyHostToDevice));
 	BCU(cudaMemcpy(v->weight.p, w.data(), total * 8, cudaMemcpyHostToDevice));
 	{
@@ -373,7 +368,7 @@ orbx_status build_vocabulary(int k, int L, int scoring, int weighting, int64_t n
 		v->V.node_info = v->node_info.p;
 	}
 	v->V.k = k; v->V.L = L; v->V.scoring = scoring; v->V.weighting = weighting; v->V.nnodes = total; v->V.nwords = nwords;
-	v->V.child_start = v->child_start.p; v->V.child_ids = v->child_ids.p; v->V.desc = v->desc.p; v->V.word_id = v->word_id.p; v->V.weight = v->weight.p;
+	v->V.child_ids = v->child_ids.p; v->V.desc = v->desc.p; v->V.weight = v->weight.p;
 	*out = v;
 	return ORBX_OK;
 }

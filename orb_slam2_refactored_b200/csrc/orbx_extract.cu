@@ -482,9 +482,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells_v1(const OrbxPlanDev 
 
 struct OrbxFastLayout
 {
-	int score_stride;            // bytes per score row (region width + 2, rounded up to 16)
-	int off_score, off_list, off_bm;
-	int bm_rows;                 // rows per bitmap (max region height)
+	int score_stride;            // bytes per score row (region width + 2, rounded up to 8)
+	int off_score, off_list, off_bm, off_bar;   // bm: the survivor bitmap, 64 bits per region row; bar: the warp's TMA mbarrier
 	int warp_bytes;              // multiple of 128: every warp's tile is a TMA destination
 };
 
@@ -541,8 +540,7 @@ __device__ __forceinline__ uint32_t fast_gather16(uint32_t w, int shift)
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxFastLayout Y)
 {
-	extern __shared__ __align__(128) uint8_t fw_smem[];
-	__shared__ __align__(8) uint64_t tma_bar[NW];
+	extern __shared__ __align__(128) uint8_t fw_smem[];    // no static shared memory: 25 single-warp CTAs of 8 KB + 1 KB reserved fit an SM
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int cell = blockIdx.x * NW + warp, f = blockIdx.y;
@@ -552,9 +550,8 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 	uint8_t* const score = base + Y.off_score;
 	uint16_t* const list = reinterpret_cast<uint16_t*>(base + Y.off_list);
 	uint8_t* const nib = base + Y.off_list;          // flag bytes of the bound pass, dead before the list is built
-	uint32_t* const bm_a = reinterpret_cast<uint32_t*>(base + Y.off_bm);   // [row][2]: 64 bits per region row
-	uint32_t* const bm_b = bm_a + 2 * Y.bm_rows;
-	uint32_t* const bm_sel = bm_b + 2 * Y.bm_rows;
+	uint32_t* const bm_sel = reinterpret_cast<uint32_t*>(base + Y.off_bm);   // [row][2]: 64 bits per region row
+	uint64_t* const tma_bar = reinterpret_cast<uint64_t*>(base + Y.off_bar);
 	const int SS = Y.score_stride;
 
 	const int4 ct = __ldg(P.cell_tab + cell);
@@ -564,15 +561,15 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 	const int sh = x0 & 15;                           // see k_fast_cells_v1: the TMA box starts 16-byte aligned
 	if (lane == 0)
 	{
-		mbar_init(&tma_bar[warp], 1);
-		mbar_expect_tx(&tma_bar[warp], (unsigned)(FT_TS * maps.box_h[lvl]));
-		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, &tma_bar[warp]);
+		mbar_init(tma_bar, 1);
+		mbar_expect_tx(tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
+		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, tma_bar);
 	}
-	for (int i = lane; i < (rh + 2) * (SS / 16); i += 32)
-		reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+	for (int i = lane; i < (rh + 2) * (SS / 8); i += 32)
+		reinterpret_cast<uint2*>(score)[i] = make_uint2(0, 0);
 	for (int i = lane; i < 2 * rh; i += 32) bm_sel[i] = 0;
 	__syncwarp();
-	mbar_wait(&tma_bar[warp], 0);
+	mbar_wait(tma_bar, 0);
 
 	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
@@ -591,7 +588,7 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 		}
 	}
 	__syncwarp();
-	// rows -> bitmaps: lane r assembles region rows r and r + 32 (bm_b = U > minTh, a superset of bm_a = U > iniTh)
+	// rows -> bitmaps, kept in registers: lane r assembles region rows r and r + 32 (wa = U > iniTh, wb = minTh < U <= iniTh)
 	uint32_t wa[4], wb[4];                           // this lane's rows: [row slot][lo, hi]
 	{
 		const uint64_t rowmask = rw >= 64 ? ~0ull : ((1ull << rw) - 1ull);
@@ -1120,7 +1117,7 @@ void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_
 		k_fast_cells_v1<<<grid, FT_THREADS, 0, st>>>(P, maps);
 		return;
 	}
-	// per-warp shared memory, sized by the largest cell of the plan: tile | score (1 px zero border) | list (aliases the flag bytes) | 3 bitmaps
+	// per-warp shared memory, sized by the largest cell of the plan: tile | score (1 px zero border) | list (aliases the flag bytes) | survivor bitmap | mbarrier
 	int rows = 0, maxrw = 0, maxrh = 0;
 	for (int s = 0; s < P.nlevels; s++)
 	{
@@ -1129,12 +1126,12 @@ void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_
 		maxrh = std::max(maxrh, P.lv[s].cellh);
 	}
 	OrbxFastLayout Y;
-	Y.score_stride = (maxrw + 2 + 15) & ~15;
+	Y.score_stride = (maxrw + 2 + 7) & ~7;
 	Y.off_score = (rows * FT_TS + 15) & ~15;
-	Y.off_list = Y.off_score + (maxrh + 2) * Y.score_stride;
+	Y.off_list = (Y.off_score + (maxrh + 2) * Y.score_stride + 15) & ~15;          // 16-byte aligned: the flag bytes are read as uint4
 	Y.off_bm = (Y.off_list + std::max(maxrw * maxrh * 2, maxrh * 16) + 15) & ~15;
-	Y.bm_rows = maxrh;
-	Y.warp_bytes = (Y.off_bm + 3 * 8 * maxrh + 127) & ~127;
+	Y.off_bar = Y.off_bm + 8 * maxrh;
+	Y.warp_bytes = (Y.off_bar + 8 + 127) & ~127;
 	// Warps per CTA: a CTA's shared memory is released when its LAST warp retires, and cells differ in cost (retry, corner count), so
 	// with 4 warps per CTA a fifth of the resident warp slots sat idle behind a straggler (ncu: 19 of 24 possible warps active).
 	static const int nw_env = getenv("ORBX_FAST_WARPS") ? atoi(getenv("ORBX_FAST_WARPS")) : FW_WARPS;   // tuning knob: 1, 2 or 4
