@@ -733,6 +733,11 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 #include "orbx_quadtree.cuh"
 #undef QT_THREADS
 #undef QT_NS
+#define QT_THREADS 512
+#define QT_NS qt512
+#include "orbx_quadtree.cuh"
+#undef QT_THREADS
+#undef QT_NS
 // =====================================================================================================
 // K6  gauss7x7_u8 — cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) in OpenCV's 8.8 fixed point
 //     (src/ORBextractor.cc:799). Tile 128 x 32 with a 3 px halo in shared memory.
@@ -1180,8 +1185,20 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	if (want_dbg) cudaMemsetAsync(dbg, 0, 64 * 8, st);
 	if (force_big >= 0 ? force_big != 0 : (large_plan || small_batch))
 	{
-		cudaFuncSetAttribute(qt256::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		qt256::k_quadtree<true><<<grid, 256, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+		// 4K-class plans keep > 1000 keypoints per level: the node lists need > 100 KB of shared memory, one CTA per SM, so a bigger CTA
+		// costs no occupancy and its block-wide partition and parallel sort rounds use every warp
+		// (measured at 3840x2160 / 8000 kp, 32 frames: 256 thr 63.8 us per frame, 512 thr 53.7, 1024 thr 66.2)
+		static const int big_threads = getenv("ORBX_QT_THREADS") ? atoi(getenv("ORBX_QT_THREADS")) : 512;   // tuning knob: 256 or 512
+		if (large_plan && !small_batch && big_threads == 512)
+		{
+			cudaFuncSetAttribute(qt512::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			qt512::k_quadtree<true><<<grid, 512, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+		}
+		else
+		{
+			cudaFuncSetAttribute(qt256::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			qt256::k_quadtree<true><<<grid, 256, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+		}
 	}
 	else
 	{

@@ -1,7 +1,8 @@
 // Quadtree selection kernel body, included by orbx_extract.cu once per CTA size (the includer defines QT_THREADS and QT_NS):
 // 256 threads for small batches and 4K-class plans, where one CTA's latency is what the launch waits for and the CTA-parallel sort /
 // block-wide partition use every thread; 128 threads for large batches, where more co-resident CTAs fill the SM while others sit in
-// their serial phases (measured per 512 C1 frames: 256 thr 0.355 ms, 128 thr 0.301 ms, 64 thr 0.390 ms).
+// their serial phases (measured per 512 C1 frames: 256 thr 0.355 ms, 128 thr 0.301 ms, 64 thr 0.390 ms); 512 threads for batches of
+// 4K-class plans, whose node lists take > 100 KB of shared memory (one CTA per SM either way).
 #define QT_WARPS (QT_THREADS / 32)
 namespace QT_NS {
 

@@ -3,7 +3,7 @@ import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from orb_slam2_refactored_b200 import api, synth
-for name, B in (('C1', 512), ('C2', 256), ('C3', 512), ('C4', 32)):
+for name, B in (('C1', 512), ('C2', 256), ('C3', 512), ('C4', 32), ('C4', 128)):
     c = synth.CONFIGS[name]
     base = np.stack([synth.image(s, c['w'], c['h']) for s in range(4)])
     d = torch.from_numpy(base).cuda().repeat((B + 3) // 4, 1, 1)[:B].contiguous()
