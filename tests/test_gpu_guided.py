@@ -146,3 +146,47 @@ def test_resident_chain_extract_undistort_frame_search(orbx, oracle_port):
     got = orbx.ORBmatcher(0.8).SearchByProjection(f, pts, pdesc, 3.0)
     want, wmp = oracle_port.search_local_map(fr, np.full(n, -1, np.int32), pts, pdesc, 3.0, 0.8)
     assert got == want and np.array_equal(f.mappoints, wmp) and want > 200
+
+
+def test_mapping_matchers_degenerate_inputs(orbx, oracle_port):
+    """Fuse / SearchBySim3 / SearchForTriangulation on empty and disjoint inputs: same answers as the oracle, no work lost or invented."""
+    fr = synth.frame(70, n=500)
+    f = gc.make_frame(orbx, fr)
+    m = orbx.ORBmatcher(0.6, True)
+    _, inv_sig = synth.sigma_tables(fr['scale_factors'])
+    S, pts, desc = synth.sim3_points(70, fr, gc.TUM_CAMERA, npts=300, scale=1.0)
+    # no points at all, then points that are all flagged off
+    bi, bd = m.FuseSearch(f, gc.TUM_CAMERA, (S[0], S[1]), synth.log_scale_factor(), inv_sig, pts[:0], desc[:0], 3.0)
+    assert len(bi) == 0 and len(bd) == 0
+    off = pts.copy(); off['flags'] = 0
+    bi, bd = m.FuseSearch(f, gc.TUM_CAMERA, (S[0], S[1]), synth.log_scale_factor(), inv_sig, off, desc, 3.0)
+    assert (bi == -1).all() and (bd == 256).all()
+    bi, bd = m.FuseSim3Search(f, gc.TUM_CAMERA, S, synth.log_scale_factor(), off, desc, 4.0)
+    assert (bi == -1).all() and (bd == 256).all()
+    # a radius so small that no window holds a keypoint
+    bi, bd = m.FuseSim3Search(f, gc.TUM_CAMERA, S, synth.log_scale_factor(), pts, desc, 1e-4)
+    assert (bi == -1).all()
+    # triangulation: disjoint vocabulary nodes, then only_stereo on monocular key frames
+    tp = synth.triangulation_pair(3, n=400)
+    f1, f2 = gc.make_frame(orbx, tp['f1']), gc.make_frame(orbx, tp['f2'])
+    ids2, st2, ix2 = tp['fv2']
+    n, m12 = m.SearchForTriangulation(f1, tp['fv1'], tp['has1'], f2, ((ids2 + 1000000).astype(np.uint32), st2, ix2), tp['has2'], tp['F12'], tp['ep2'],
+                                      tp['sigma_sq2'], False)
+    assert n == 0 and (m12 == -1).all()
+    mono = dict(tp); mono['f1'] = dict(tp['f1']); mono['f2'] = dict(tp['f2'])
+    mono['f1']['uright'] = np.full(400, -1, np.float32); mono['f2']['uright'] = np.full(400, -1, np.float32)
+    g1, g2 = gc.make_frame(orbx, mono['f1']), gc.make_frame(orbx, mono['f2'])
+    n, m12 = m.SearchForTriangulation(g1, mono['fv1'], mono['has1'], g2, mono['fv2'], mono['has2'], mono['F12'], mono['ep2'], mono['sigma_sq2'], True)
+    wn, wm = oracle_port.search_for_triangulation(mono, True, True)
+    assert n == wn == 0 and np.array_equal(m12, wm)
+    # every keypoint of both key frames already holds a map point: nothing to triangulate
+    full = np.ones(400, np.uint8)
+    n, m12 = m.SearchForTriangulation(f1, tp['fv1'], full, f2, tp['fv2'], full, tp['F12'], tp['ep2'], tp['sigma_sq2'], False)
+    assert n == 0 and (m12 == -1).all()
+    # SearchBySim3 with no eligible map point on either side
+    sp = synth.sim3_pair(4, n=300); sp['lsf'] = synth.log_scale_factor()
+    s1, s2 = gc.make_frame(orbx, sp['f1']), gc.make_frame(orbx, sp['f2'])
+    p1 = sp['pts1'].copy(); p2 = sp['pts2'].copy(); p1['flags'] = 0; p2['flags'] = 0
+    n, m12, m1, m2 = orbx.ORBmatcher(0.75, True).SearchBySim3(s1, sp['cam'], sp['pose1'], sp['lsf'], s2, sp['cam'], sp['pose2'], sp['lsf'], sp['S12'], 7.5,
+                                                             p1, sp['desc1'], p2, sp['desc2'])
+    assert n == 0 and (m12 == -1).all() and (m1 == -1).all() and (m2 == -1).all()
