@@ -140,15 +140,21 @@ __device__ __forceinline__ int quadrant_of(uint32_t v, int xm, int ym)
 }
 
 // Stable 4-way partition of one big node by the whole CTA (see the call site).
-__device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint32_t* buf1, uint32_t* cc, int (*s_bigc)[4], int (*s_bigw)[QT_WARPS][4])
+__device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint32_t* buf1, uint32_t* cc, int (*s_bigc)[4])
 {
+	// Stable 4-way partition of one big node by the whole CTA. Every warp owns a CONTIGUOUS run of the node's elements (a multiple of 32
+	// long), so after one exchange of the per-warp quadrant counts each warp knows where its elements of every quadrant start and scatters
+	// them with ballots alone: no barrier and no shared-memory traffic per chunk (the chunk-synchronous version spent 1.6 us per 512
+	// elements on them: 242 us per pass over the 78 k candidates of a 4K level 0).
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int cnt = (int)QN_CNT(nd);
 	const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 	uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
 	const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+	const int seg = ((cnt + QT_WARPS - 1) / QT_WARPS + 31) & ~31;
+	const int s0 = min(warp * seg, cnt), s1 = min(s0 + seg, cnt);
 	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-	for (int i = tid; i < cnt; i += QT_THREADS)
+	for (int i = s0 + lane; i < s1; i += 32)
 	{
 		const int q = quadrant_of(src[i], xm, ym);
 		c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
@@ -165,40 +171,33 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 #pragma unroll
 	for (int q = 0; q < 4; q++)
 	{
-		tot[q] = 0;
+		tot[q] = 0; run[q] = 0;
 #pragma unroll
-		for (int w = 0; w < QT_WARPS; w++) tot[q] += s_bigc[w][q];
+		for (int w = 0; w < QT_WARPS; w++)
+		{
+			const int x = s_bigc[w][q];
+			tot[q] += x;
+			if (w < warp) run[q] += x;                   // elements of quadrant q held by the warps before this one
+		}
 	}
-	run[0] = 0; run[1] = tot[0]; run[2] = tot[0] + tot[1]; run[3] = tot[0] + tot[1] + tot[2];
-	int par = 0;
-	for (int i0 = 0; i0 < cnt; i0 += QT_THREADS, par ^= 1)
+	run[1] += tot[0]; run[2] += tot[0] + tot[1]; run[3] += tot[0] + tot[1] + tot[2];
+	for (int i0 = s0; i0 < s1; i0 += 32)
 	{
-		const int i = i0 + tid;
-		const bool ok = i < cnt;
+		const int i = i0 + lane;
+		const bool ok = i < s1;
 		const uint32_t v = ok ? src[i] : 0u;
 		const int q = ok ? quadrant_of(v, xm, ym) : -1;
 		unsigned bq[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) bq[k] = __ballot_sync(0xffffffffu, q == k);
-		if (lane < 4) s_bigw[par][warp][lane] = __popc(lane == 0 ? bq[0] : lane == 1 ? bq[1] : lane == 2 ? bq[2] : bq[3]);
-		__syncthreads();                     // one barrier per chunk: the count buffers alternate
-		int before = 0, mine = 0, chunk_tot[4];
+		int mine = 0;
 #pragma unroll
 		for (int k = 0; k < 4; k++)
 		{
-			chunk_tot[k] = 0;
-#pragma unroll
-			for (int w = 0; w < QT_WARPS; w++)
-			{
-				const int x = s_bigw[par][w][k];
-				chunk_tot[k] += x;
-				if (w < warp && k == q) before += x;
-			}
 			if (k == q) mine = run[k] + __popc(bq[k] & lanemask_lt());
+			run[k] += __popc(bq[k]);
 		}
-		if (ok) dst[mine + before] = v;
-#pragma unroll
-		for (int k = 0; k < 4; k++) run[k] += chunk_tot[k];
+		if (ok) dst[mine] = v;
 	}
 	if (tid == 0) { cc[0] = tot[0]; cc[1] = tot[1]; cc[2] = tot[2]; cc[3] = tot[3]; }
 	__syncthreads();
@@ -228,7 +227,8 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	__shared__ int s_K;
 	__shared__ int s_sort[3];
 	__shared__ int s_rootcnt[ORBX_MAX_ROOTS];
-	__shared__ int s_bigc[QT_WARPS][4], s_bigw[2][QT_WARPS][4];
+	__shared__ int s_bigc[QT_WARPS][4];
+	__shared__ int s_rc[QT_WARPS][ORBX_MAX_ROOTS];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lvl = blockIdx.y, f = blockIdx.x;      // x = frame: all level-0 CTAs (the longest) are scheduled first
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
 	// 8 lanes per cell (a cell holds ~15 candidates): four cells per warp in flight, so the chain of dependent loads
 	// (count, offset, slots) is walked ncell / 32 times per warp instead of ncell / 8 times
+#pragma unroll 4
 	for (int cidx = tid >> 3; cidx < ncell; cidx += QT_THREADS / 8)
 	{
 		const int cnt = ccount[cidx], off = coff[cidx];
@@ -271,13 +272,52 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	}
 	else
 	{
-		int at = 0;
-		for (int r = 0; r < nroots; r++)
+		// stable partition of the n candidates into the root strips, same scheme as qt_divide_big: a contiguous run per warp, one exchange
+		// of per-warp counts, then ballots only. Lane r of a warp keeps the count / write cursor of strip r (nroots <= 16).
+		const int seg = ((n + QT_WARPS - 1) / QT_WARPS + 31) & ~31;
+		const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
+		int c = 0;
+		for (int i0 = s0; i0 < s1; i0 += 32)
 		{
-			const int c = block_ordered(n, s_w, [&](int i) { return rlut[orbx_px(buf1[i])] == r; },
-			                            [&](int i, int rank) { buf0[at + rank] = buf1[i]; });
-			if (tid == 0) s_rootcnt[r] = c;
-			at += c;
+			const int i = i0 + lane;
+			const int key = i < s1 ? (int)rlut[orbx_px(buf1[i])] : -1;
+			for (int r = 0; r < nroots; r++)
+			{
+				const unsigned b = __ballot_sync(0xffffffffu, key == r);
+				if (lane == r) c += __popc(b);
+			}
+		}
+		if (lane < ORBX_MAX_ROOTS) s_rc[warp][lane] = lane < nroots ? c : 0;
+		__syncthreads();
+		int run = 0;                                   // lane r: where this warp's elements of strip r start in buf0
+		if (lane < nroots)
+		{
+			for (int r = 0; r < lane; r++)
+				for (int w = 0; w < QT_WARPS; w++) run += s_rc[w][r];
+			int tot = 0;
+			for (int w = 0; w < QT_WARPS; w++)
+			{
+				const int x = s_rc[w][lane];
+				if (w < warp) run += x;
+				tot += x;
+			}
+			if (warp == 0) s_rootcnt[lane] = tot;
+		}
+		for (int i0 = s0; i0 < s1; i0 += 32)
+		{
+			const int i = i0 + lane;
+			const bool ok = i < s1;
+			const uint32_t v = ok ? buf1[i] : 0u;
+			const int key = ok ? (int)rlut[orbx_px(v)] : -1;
+			int pos = 0;
+			for (int r = 0; r < nroots; r++)
+			{
+				const unsigned b = __ballot_sync(0xffffffffu, key == r);
+				const int base = __shfl_sync(0xffffffffu, run, r);
+				if (key == r) pos = base + __popc(b & lanemask_lt());
+				if (lane == r) run += __popc(b);
+			}
+			if (ok) buf0[pos] = v;
 		}
 	}
 	__syncthreads();
@@ -338,14 +378,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 		QT_STAMP();
 
 		// ---- big nodes (the first passes of a large level: one node can hold tens of thousands of candidates) are divided by
-		//      the whole CTA: chunks of QT_THREADS elements in order, position = quadrant base + earlier chunks + earlier warps of the
-		//      chunk + earlier lanes of the warp, i.e. the same stable 4-way partition as the warp version below.
+		//      the whole CTA: every warp takes a contiguous run of the node, position = quadrant base + the quadrant's elements in earlier
+		//      warps + in earlier chunks of this warp + in earlier lanes, i.e. the same stable 4-way partition as the warp version below.
 		if (BIG && np <= 64)
 			for (int t = 0; t < np; t++)
 			{
 				const QNode nd = cur[proc[t]];
 				if ((int)QN_CNT(nd) >= big_node_min)            // uniform: every thread sees the same node
-					qt_divide_big(nd, buf0, buf1, childcnt + 4 * t, s_bigc, s_bigw);
+					qt_divide_big(nd, buf0, buf1, childcnt + 4 * t, s_bigc);
 			}
 
 		// ---- divide (speculatively all of them; Phase 2 may stop early, parents stay intact in their buffer)
