@@ -272,6 +272,17 @@ def run_b200(args, rank, world, local_rank, emit):
     ex.enable_stage_timing(False)
     frames_total = world * B * args.steps
     fps = frames_total / (ms * 1e-3)
+    # the same K steps once more WITHOUT the per-stage events (informational): with them the library runs a batch as one launch per stage,
+    # without them as two halves on two streams, which is what a caller gets
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    u1.record(stream)
+    u1.synchronize()
+    barrier()
+    fps_plain = frames_total / (max_over_ranks(u0.elapsed_time(u1)) * 1e-3)
 
     # keypoint counts of the last step, for the algorithmic byte count
     n_last = outs[2].cpu().numpy()
@@ -625,6 +636,8 @@ def run_b200(args, rank, world, local_rank, emit):
                     'handles': NH, 'api': f'orbx_extract_batch (pinned host frames in, keypoints + descriptors out), {NH} extractor instances on '
                                           f'{NH} host threads per GPU, one {B}-frame batch per call; wall clock around the synchronous calls'},
             'gpu_launches': launches,
+            'uninstrumented': {'value': fps_plain, 'unit': 'frames/s',
+                               'note': 'the same steps without the per-stage CUDA events of the timed region (two half-batches on two streams instead of one launch per stage)'},
             'clocks': clocks,
             'roofline': roofline,
             'cpu_baseline': cpu,
