@@ -105,6 +105,8 @@ struct orbx_extractor
 	cudaStream_t stream2 = nullptr;     // second lane of the chunk pipeline of the host-buffer API
 	cudaEvent_t done = nullptr;
 	cudaEvent_t fork = nullptr, join = nullptr;   // order the second lane inside the handle's stream for the device-resident API
+	cudaStream_t side[2] = { nullptr, nullptr };  // per lane: the blur runs here, beside the quadtree (latency-bound, leaves the SMs half empty)
+	cudaEvent_t side_fork[2] = { nullptr, nullptr }, side_join[2] = { nullptr, nullptr };
 	std::vector<float> scale, inv_scale, sigma_sq, inv_sigma_sq;
 	std::vector<int> quota;
 
@@ -134,7 +136,7 @@ struct orbx_extractor
 	DevBuf<int> st_sad, st_rows;
 	DevBuf<uint2> st_items;
 	bool stage_timing = false;
-	std::vector<cudaEvent_t> ev_pool;   // 6 events per timed extract call
+	std::vector<cudaEvent_t> ev_pool;   // 10 events per timed extract call
 	size_t ev_used = 0;
 	bool have_result = false;
 	int last_frames = 0, last_cap = 0;
@@ -389,31 +391,54 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	P.sel += (int64_t)fb * P.sel_per_frame;
 	d_kps += (int64_t)fb * cap; d_desc += (int64_t)fb * cap * 32; d_n += fb;
 
+	// 10 events per timed call: (start, end) of pyramid, FAST, quadtree, blur, describe on the stream each stage runs on
 	cudaEvent_t* ev = nullptr;
 	if (h->stage_timing)
 	{
-		while (h->ev_pool.size() < h->ev_used + 6)
+		while (h->ev_pool.size() < h->ev_used + 10)
 		{
 			cudaEvent_t e;
 			CU(cudaEventCreate(&e));
 			h->ev_pool.push_back(e);
 		}
 		ev = h->ev_pool.data() + h->ev_used;
-		h->ev_used += 6;
+		h->ev_used += 10;
 	}
+	// The blur on a side stream beside the quadtree was measured: +1.2 % device-resident (178.3 k vs 176.1 k frames/s), -3 % end to end
+	// (147.6 k vs 151.9 k: two more streams per handle in the chunk pipeline), no change without the stage events. Default: in line.
+	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr;
+	const int lane = st == h->stream2 ? 1 : 0;
+	cudaStream_t side = blur_inline ? st : h->side[lane];
 	if (ev) CU(cudaEventRecord(ev[0], st));
 	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, st);
-	// blur right after the pyramid (it only depends on it): its 1 MB/frame of dirty lines drain from L2 while FAST and the
-	// quadtree run, instead of competing with the descriptor stage's gathers
 	if (ev) CU(cudaEventRecord(ev[1], st));
-	orbx_launch_blur(P, st);
+	if (blur_inline)
+	{
+		if (ev) CU(cudaEventRecord(ev[6], st));
+		orbx_launch_blur(P, st);
+		if (ev) CU(cudaEventRecord(ev[7], st));
+	}
 	if (ev) CU(cudaEventRecord(ev[2], st));
 	orbx_launch_fast(P, h->maps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
-	orbx_launch_quadtree(P, cell_off, st);
+	if (!blur_inline)
+	{
+		// The blur only depends on the pyramid and only the descriptor stage reads it: it runs beside the quadtree, whose CTAs spend
+		// most of their time in serial phases and leave the SMs' issue slots half empty. (Beside FAST it would only share a busy SM.)
+		CU(cudaEventRecord(h->side_fork[lane], st));
+		CU(cudaStreamWaitEvent(side, h->side_fork[lane], 0));
+		if (ev) CU(cudaEventRecord(ev[6], side));
+		orbx_launch_blur(P, side);
+		if (ev) CU(cudaEventRecord(ev[7], side));
+		CU(cudaEventRecord(h->side_join[lane], side));
+	}
 	if (ev) CU(cudaEventRecord(ev[4], st));
-	orbx_launch_describe(P, d_kps, d_desc, d_n, st);
+	orbx_launch_quadtree(P, cell_off, st);
 	if (ev) CU(cudaEventRecord(ev[5], st));
+	if (!blur_inline) CU(cudaStreamWaitEvent(st, h->side_join[lane], 0));
+	if (ev) CU(cudaEventRecord(ev[8], st));
+	orbx_launch_describe(P, d_kps, d_desc, d_n, st);
+	if (ev) CU(cudaEventRecord(ev[9], st));
 	CU(cudaGetLastError());
 	return ORBX_OK;
 }
@@ -465,6 +490,12 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming);
+	for (int l = 0; l < 2; l++)
+	{
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side[l], cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side_fork[l], cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side_join[l], cudaEventDisableTiming);
+	}
 	if (e == cudaSuccess) e = orbx_upload_pattern();
 	if (e != cudaSuccess)
 	{
@@ -495,6 +526,12 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (h->join) cudaEventDestroy(h->join);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	if (h->stream2) cudaStreamDestroy(h->stream2);
+	for (int l = 0; l < 2; l++)
+	{
+		if (h->side[l]) { cudaStreamSynchronize(h->side[l]); cudaStreamDestroy(h->side[l]); }
+		if (h->side_fork[l]) cudaEventDestroy(h->side_fork[l]);
+		if (h->side_join[l]) cudaEventDestroy(h->side_join[l]);
+	}
 	delete h;
 	return ORBX_OK;
 }
@@ -558,13 +595,13 @@ orbx_status orbx_stage_times(orbx_handle h, float ms_sum[5], int* calls)
 	CU(cudaSetDevice(h->device));
 	CU(cudaStreamSynchronize(h->stream));
 	for (int i = 0; i < 5; i++) ms_sum[i] = 0.f;
-	const size_t n = h->ev_used / 6;
+	const size_t n = h->ev_used / 10;
 	for (size_t c = 0; c < n; c++)
 		for (int i = 0; i < 5; i++)
 		{
 			float ms = 0.f;
-			CU(cudaEventElapsedTime(&ms, h->ev_pool[6 * c + i], h->ev_pool[6 * c + i + 1]));
-			static const int slot[5] = { 0, 3, 1, 2, 4 };   // launch order is pyramid, blur, FAST, quadtree, describe
+			CU(cudaEventElapsedTime(&ms, h->ev_pool[10 * c + 2 * i], h->ev_pool[10 * c + 2 * i + 1]));
+			static const int slot[5] = { 0, 1, 2, 3, 4 };   // event pairs are pyramid, FAST, quadtree, blur, describe = the order of ms_sum
 			ms_sum[slot[i]] += ms;
 		}
 	if (calls) *calls = (int)n;
