@@ -154,6 +154,7 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 	const int seg = ((cnt + QT_WARPS - 1) / QT_WARPS + 31) & ~31;
 	const int s0 = min(warp * seg, cnt), s1 = min(s0 + seg, cnt);
 	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 4
 	for (int i = s0 + lane; i < s1; i += 32)
 	{
 		const int q = quadrant_of(src[i], xm, ym);
@@ -181,23 +182,35 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 		}
 	}
 	run[1] += tot[0]; run[2] += tot[0] + tot[1]; run[3] += tot[0] + tot[1] + tot[2];
-	for (int i0 = s0; i0 < s1; i0 += 32)
+	for (int i0 = s0; i0 < s1; i0 += 128)              // four chunks' loads in flight before the ballots
 	{
-		const int i = i0 + lane;
-		const bool ok = i < s1;
-		const uint32_t v = ok ? src[i] : 0u;
-		const int q = ok ? quadrant_of(v, xm, ym) : -1;
-		unsigned bq[4];
+		uint32_t vv[4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) bq[k] = __ballot_sync(0xffffffffu, q == k);
-		int mine = 0;
-#pragma unroll
-		for (int k = 0; k < 4; k++)
+		for (int u = 0; u < 4; u++)
 		{
-			if (k == q) mine = run[k] + __popc(bq[k] & lanemask_lt());
-			run[k] += __popc(bq[k]);
+			const int i = i0 + 32 * u + lane;
+			vv[u] = i < s1 ? src[i] : 0u;
 		}
-		if (ok) dst[mine] = v;
+#pragma unroll
+		for (int u = 0; u < 4; u++)
+		{
+			if (i0 + 32 * u >= s1) break;                // uniform
+			const int i = i0 + 32 * u + lane;
+			const bool ok = i < s1;
+			const uint32_t v = vv[u];
+			const int q = ok ? quadrant_of(v, xm, ym) : -1;
+			unsigned bq[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) bq[k] = __ballot_sync(0xffffffffu, q == k);
+			int mine = 0;
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+			{
+				if (k == q) mine = run[k] + __popc(bq[k] & lanemask_lt());
+				run[k] += __popc(bq[k]);
+			}
+			if (ok) dst[mine] = v;
+		}
 	}
 	if (tid == 0) { cc[0] = tot[0]; cc[1] = tot[1]; cc[2] = tot[2]; cc[3] = tot[3]; }
 	__syncthreads();
@@ -397,32 +410,48 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
 			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
+			// The candidates sit in global memory (L2): one chunk per trip costs a full L2 round trip. The count loop keeps per-lane
+			// counters (no ballot between its loads, so they overlap); the scatter loop loads four chunks before it touches them.
 			int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-			for (int i0 = 0; i0 < cnt; i0 += 32)
+#pragma unroll 4
+			for (int i = lane; i < cnt; i += 32)
 			{
-				const int i = i0 + lane;
-				const bool ok = i < cnt;
-				const int q = ok ? quadrant_of(src[i], xm, ym) : -1;
-				c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
-				c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
-				c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
-				c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+				const int q = quadrant_of(src[i], xm, ym);
+				c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
+			}
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1)
+			{
+				c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+				c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
 			}
 			int a0 = 0, a1 = c0, a2 = c0 + c1, a3 = c0 + c1 + c2;
-			for (int i0 = 0; i0 < cnt; i0 += 32)
+			for (int i0 = 0; i0 < cnt; i0 += 128)
 			{
-				const int i = i0 + lane;
-				const bool ok = i < cnt;
-				const uint32_t v = ok ? src[i] : 0u;
-				const int q = ok ? quadrant_of(v, xm, ym) : -1;
-				const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
-				const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
-				const unsigned lt = lanemask_lt();
-				if (q == 0) dst[a0 + __popc(b0 & lt)] = v;
-				else if (q == 1) dst[a1 + __popc(b1 & lt)] = v;
-				else if (q == 2) dst[a2 + __popc(b2 & lt)] = v;
-				else if (q == 3) dst[a3 + __popc(b3 & lt)] = v;
-				a0 += __popc(b0); a1 += __popc(b1); a2 += __popc(b2); a3 += __popc(b3);
+				uint32_t vv[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+				{
+					const int i = i0 + 32 * u + lane;
+					vv[u] = i < cnt ? src[i] : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+				{
+					if (i0 + 32 * u >= cnt) break;               // uniform
+					const int i = i0 + 32 * u + lane;
+					const bool ok = i < cnt;
+					const uint32_t v = vv[u];
+					const int q = ok ? quadrant_of(v, xm, ym) : -1;
+					const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+					const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+					const unsigned lt = lanemask_lt();
+					if (q == 0) dst[a0 + __popc(b0 & lt)] = v;
+					else if (q == 1) dst[a1 + __popc(b1 & lt)] = v;
+					else if (q == 2) dst[a2 + __popc(b2 & lt)] = v;
+					else if (q == 3) dst[a3 + __popc(b3 & lt)] = v;
+					a0 += __popc(b0); a1 += __popc(b1); a2 += __popc(b2); a3 += __popc(b3);
+				}
 			}
 			if (lane == 0)
 			{

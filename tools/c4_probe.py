@@ -15,4 +15,4 @@ ex.synchronize(); dt = (time.perf_counter() - t) / 8
 ex.enable_stage_timing(True); ex.stage_times()
 for i in range(4): ex.extract_batch_device(d, *outs)
 ms, calls = ex.stage_times()
-print(os.environ.get('ORBX_QT_THREADS', '256'), f'{B / dt:.0f} frames/s', {k: round(v / calls / B * 1e3, 2) for k, v in ms.items()})
+print(os.environ.get('ORBX_QT_THREADS', 'default (512)'), f'{B / dt:.0f} frames/s', {k: round(v / calls / B * 1e3, 2) for k, v in ms.items()})
