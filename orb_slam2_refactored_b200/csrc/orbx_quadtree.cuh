@@ -261,12 +261,41 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
 	// 8 lanes per cell (a cell holds ~15 candidates): four cells per warp in flight, so the chain of dependent loads
 	// (count, offset, slots) is walked ncell / 32 times per warp instead of ncell / 8 times
-#pragma unroll 4
-	for (int cidx = tid >> 3; cidx < ncell; cidx += QT_THREADS / 8)
+	// (two cells per group and trip, counts / offsets and then the first 16 candidates of both loaded before anything is stored: the
+	// dependent chain count -> slots is walked once for both)
+	for (int c0 = tid >> 3; c0 < ncell; c0 += QT_THREADS / 4)
 	{
-		const int cnt = ccount[cidx], off = coff[cidx];
-		const uint32_t* src = slots + (int64_t)cidx * L.cell_cap;
-		for (int k = tid & 7; k < cnt; k += 8) gathered[off + k] = src[k];
+		int cnt[2], off[2];
+		const uint32_t* srcp[2];
+#pragma unroll
+		for (int u = 0; u < 2; u++)
+		{
+			const int cidx = c0 + u * (QT_THREADS / 8);
+			const bool live = cidx < ncell;
+			cnt[u] = live ? ccount[cidx] : 0;
+			off[u] = live ? coff[cidx] : 0;
+			srcp[u] = slots + (int64_t)(live ? cidx : 0) * L.cell_cap;
+		}
+		uint32_t v[2][2];
+#pragma unroll
+		for (int u = 0; u < 2; u++)
+#pragma unroll
+			for (int j = 0; j < 2; j++)
+			{
+				const int k = (tid & 7) + 8 * j;
+				v[u][j] = k < cnt[u] ? srcp[u][k] : 0u;
+			}
+#pragma unroll
+		for (int u = 0; u < 2; u++)
+		{
+#pragma unroll
+			for (int j = 0; j < 2; j++)
+			{
+				const int k = (tid & 7) + 8 * j;
+				if (k < cnt[u]) gathered[off[u] + k] = v[u][j];
+			}
+			for (int k = (tid & 7) + 16; k < cnt[u]; k += 8) gathered[off[u] + k] = srcp[u][k];
+		}
 	}
 	__syncthreads();
 	QT_STAMP();
@@ -532,26 +561,41 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	uint32_t* __restrict__ sel = P.sel + (int64_t)f * P.sel_per_frame + L.sel_base;
 	// 8 lanes per node (final nodes hold ~10 candidates): four nodes per warp in flight. The loop bound is rounded up so that every
 	// lane of a warp takes part in the shuffles.
-	for (int i0 = 0; i0 < listLen; i0 += QT_THREADS / 8)
+	// Two nodes per 8-lane group and trip, their candidates loaded before either reduction starts, and the winner's packed value
+	// travels through the shuffles with its response: one L2 round trip per trip instead of four.
+	for (int i0 = 0; i0 < listLen; i0 += QT_THREADS / 4)
 	{
-		const int i = i0 + (tid >> 3);
-		const bool live = i < listLen;
-		const QNode nd = cur[live ? i : 0];
-		const int cnt = live ? (int)QN_CNT(nd) : 0;
-		const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
-		int bestr = 0, besti = 0x7fffffff;
-		for (int k = tid & 7; k < cnt; k += 8)
+		int bestr[2], besti[2], cntu[2];
+		uint32_t bestv[2];
+#pragma unroll
+		for (int u = 0; u < 2; u++)
 		{
-			const int r = orbx_pr(src[k]);
-			if (r > bestr) { bestr = r; besti = k; }
+			const int i = i0 + u * (QT_THREADS / 8) + (tid >> 3);
+			const bool live = i < listLen;
+			const QNode nd = cur[live ? i : 0];
+			cntu[u] = live ? (int)QN_CNT(nd) : 0;
+			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
+			bestr[u] = 0; besti[u] = 0x7fffffff; bestv[u] = 0u;
+			for (int k = tid & 7; k < cntu[u]; k += 8)
+			{
+				const uint32_t v = src[k];
+				const int r = orbx_pr(v);
+				if (r > bestr[u]) { bestr[u] = r; besti[u] = k; bestv[u] = v; }
+			}
 		}
 #pragma unroll
-		for (int d = 4; d > 0; d >>= 1)
+		for (int u = 0; u < 2; u++)
 		{
-			const int orr = __shfl_xor_sync(0xffffffffu, bestr, d), oi = __shfl_xor_sync(0xffffffffu, besti, d);
-			if (orr > bestr || (orr == bestr && oi < besti)) { bestr = orr; besti = oi; }
+#pragma unroll
+			for (int d = 4; d > 0; d >>= 1)
+			{
+				const int orr = __shfl_xor_sync(0xffffffffu, bestr[u], d), oi = __shfl_xor_sync(0xffffffffu, besti[u], d);
+				const uint32_t ov = __shfl_xor_sync(0xffffffffu, bestv[u], d);
+				if (orr > bestr[u] || (orr == bestr[u] && oi < besti[u])) { bestr[u] = orr; besti[u] = oi; bestv[u] = ov; }
+			}
+			const int i = i0 + u * (QT_THREADS / 8) + (tid >> 3);
+			if (i < listLen && (tid & 7) == 0) sel[i] = bestv[u];
 		}
-		if (live && (tid & 7) == 0) sel[i] = src[besti];
 	}
 	if (tid == 0) P.sel_count[(int64_t)f * P.nlevels + lvl] = listLen;
 	QT_STAMP();
