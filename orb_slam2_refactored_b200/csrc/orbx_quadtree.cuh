@@ -345,21 +345,37 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			}
 			if (warp == 0) s_rootcnt[lane] = tot;
 		}
-		for (int i0 = s0; i0 < s1; i0 += 32)
+		for (int i0 = s0; i0 < s1; i0 += 128)          // four chunks (candidate, then its strip) loaded before the ballots
 		{
-			const int i = i0 + lane;
-			const bool ok = i < s1;
-			const uint32_t v = ok ? buf1[i] : 0u;
-			const int key = ok ? (int)rlut[orbx_px(v)] : -1;
-			int pos = 0;
-			for (int r = 0; r < nroots; r++)
+			uint32_t vv[4];
+			int kk[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
 			{
-				const unsigned b = __ballot_sync(0xffffffffu, key == r);
-				const int base = __shfl_sync(0xffffffffu, run, r);
-				if (key == r) pos = base + __popc(b & lanemask_lt());
-				if (lane == r) run += __popc(b);
+				const int i = i0 + 32 * u + lane;
+				vv[u] = i < s1 ? buf1[i] : 0u;
 			}
-			if (ok) buf0[pos] = v;
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				const int i = i0 + 32 * u + lane;
+				kk[u] = i < s1 ? (int)rlut[orbx_px(vv[u])] : -1;
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				if (i0 + 32 * u >= s1) break;            // uniform
+				const int key = kk[u];
+				int pos = 0;
+				for (int r = 0; r < nroots; r++)
+				{
+					const unsigned b = __ballot_sync(0xffffffffu, key == r);
+					const int base = __shfl_sync(0xffffffffu, run, r);
+					if (key == r) pos = base + __popc(b & lanemask_lt());
+					if (lane == r) run += __popc(b);
+				}
+				if (key >= 0) buf0[pos] = vv[u];
+			}
 		}
 	}
 	__syncthreads();
