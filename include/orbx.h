@@ -99,8 +99,16 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int frames, int width, int height,
                                       size_t pitch, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
                                       int cap, int32_t* d_n);
-/* upper bound of keypoints per frame: sum over levels of (quota + 3) (the quadtree overshoots by at most 3) */
+/* upper bound of keypoints per frame: sum over levels of (quota + 3) (the quadtree overshoots by at most 3). Before the
+ * handle has seen an image size the bound assumes the widest aspect ratio; orbx_plan makes it exact. */
 int orbx_max_keypoints(orbx_handle h);
+/* Builds (or re-uses) the plan for `frames` images of width x height without extracting: level sizes, tables, device
+ * buffers. What every extract call does first; call it to size output buffers exactly (ORBextractor's constructor plus the
+ * first image's size, src/ORBextractor.cc:695-741, :455-470). */
+orbx_status orbx_plan(orbx_handle h, int width, int height, int frames);
+/* Shape of the device-resident result of the last extract call on this handle: number of frames and the row capacity
+ * (keypoints per frame) of its keypoint / descriptor / uright / depth arrays. ORBX_ERR_STATE before the first extract. */
+orbx_status orbx_last_result_shape(orbx_handle h, int* frames, int* cap);
 orbx_status orbx_synchronize(orbx_handle h);
 /* the handle's cudaStream_t, as void* */
 void* orbx_stream(orbx_handle h);
@@ -134,8 +142,8 @@ orbx_status orbx_descriptor_distance(int device, const uint8_t* a, const uint8_t
 
 /* ComputeStereoMatches — include/ORBmatcher.h:41-45, src/ORBmatcher.cc:72-247 — on the device-resident results
  * of the last extract of `left` and `right` (same batch size, same image size, same device). uright/depth: host,
- * frames*cap floats laid out like the keypoints of that extract (cap = its cap); entries past n[f] are not
- * written. No keypoint/descriptor/pyramid traffic leaves the GPU. */
+ * frames*cap floats laid out like the keypoints of that extract (frames, cap = orbx_last_result_shape(left)); entries
+ * past n[f] are not written. No keypoint/descriptor/pyramid traffic leaves the GPU. */
 orbx_status orbx_stereo_match(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* uright, float* depth);
 orbx_status orbx_stereo_match_device(orbx_handle left, orbx_handle right, const orbx_camera* camera, float* d_uright,
                                      float* d_depth);

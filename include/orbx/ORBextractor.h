@@ -61,7 +61,7 @@ public:
 	void Extract(const cv::Mat& image, KeyPoints& keypoints, cv::Mat& descriptors)
 	{
 		if (image.type() != CV_8U)
-			throw cv::Exception(cvExceptionArgs("image.type() == CV_8U"));
+			throw cv::Exception(cv::Error::StsAssert, "image.type() == CV_8U", "ORB_SLAM2::b200::ORBextractor::Extract", __FILE__, __LINE__);
 		static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint must be 7 x 4 bytes");
 		const int cap = orbx_max_keypoints(handle_);
 		kpScratch_.resize(static_cast<size_t>(cap));
@@ -80,6 +80,11 @@ public:
 		for (int i = 0; i < n; i++)
 			std::memcpy(descriptors.ptr(i), descScratch_.ptr(i), 32);
 	}
+
+	// cv::ORB-style call operator of upstream ORB_SLAM2 (ORBextractor::operator()(image, mask, keypoints, descriptors)); this fork
+	// renamed it to Extract and dropped the mask, which upstream ignores as well.
+	template <class MaskT>
+	void operator()(const cv::Mat& image, const MaskT& /*mask*/, KeyPoints& keypoints, cv::Mat& descriptors) { Extract(image, keypoints, descriptors); }
 
 	int GetLevels() const { return param_.nlevels; }
 	float GetScaleFactor() const { return param_.scaleFactor; }
@@ -111,11 +116,10 @@ public:
 
 private:
 
-	static std::string cvExceptionArgs(const char* what) { return std::string("ORBextractor (B200): ") + what; }
 	static void Check(orbx_status st, const char* where)
 	{
 		if (st != ORBX_OK)
-			throw cv::Exception(std::string(where) + ": " + orbx_last_error());
+			throw cv::Exception(cv::Error::StsError, orbx_last_error(), where, __FILE__, __LINE__);
 	}
 
 	std::vector<float> scaleFactors_, invScaleFactors_, sigmaSq_, invSigmaSq_;

@@ -28,7 +28,7 @@ using Pyramid = std::vector<cv::Mat>;   // include/ORBmatcher.h:39
 inline void Check(orbx_status st, const char* where)
 {
 	if (st != ORBX_OK)
-		throw cv::Exception(std::string(where) + ": " + orbx_last_error());
+		throw cv::Exception(cv::Error::StsError, orbx_last_error(), where, __FILE__, __LINE__);
 }
 
 // The reference's argument list, host data (one stereo pair). CameraT needs fx, fy, cx, cy, bf, baseline (include/CameraParameters.h:29-40).
@@ -72,8 +72,11 @@ inline void ComputeStereoMatches(const ORBextractor& extractorL, const ORBextrac
 	std::vector<float>& uright, std::vector<float>& depth)
 {
 	const orbx_camera cam = { camera.fx, camera.fy, camera.cx, camera.cy, camera.bf, camera.baseline };
-	std::vector<float> u(orbx_max_keypoints(extractorL.Handle())), d(u.size());
+	int frames = 0, cap = 0;     // the result arrays are laid out like the keypoints of the last extract: frames x cap
+	Check(orbx_last_result_shape(extractorL.Handle(), &frames, &cap), "ComputeStereoMatches");
+	std::vector<float> u(static_cast<size_t>(frames) * cap), d(u.size());
 	Check(orbx_stereo_match(extractorL.Handle(), extractorR.Handle(), &cam, u.data(), d.data()), "ComputeStereoMatches");
+	if (nkeypointsL > static_cast<size_t>(cap)) nkeypointsL = static_cast<size_t>(cap);
 	uright.assign(u.begin(), u.begin() + nkeypointsL);
 	depth.assign(d.begin(), d.begin() + nkeypointsL);
 }

@@ -31,15 +31,24 @@ typedef unsigned char uchar;
 
 namespace cv {
 
+namespace Error { enum Code { StsError = -2, StsAssert = -215 }; }
+
+// the constructors real OpenCV has (core.hpp: Exception() and Exception(code, err, func, file, line)) and no others
 class Exception : public std::runtime_error
 {
 public:
-	explicit Exception(const std::string& m) : std::runtime_error(m) {}
+	Exception() : std::runtime_error("") {}
+	Exception(int code_, const std::string& err_, const std::string& func_, const std::string& file_, int line_)
+		: std::runtime_error(file_ + ":" + std::to_string(line_) + ": error: (" + std::to_string(code_) + ") " + err_ + " in function '" + func_ + "'"),
+		  code(code_), err(err_), func(func_), file(file_), line(line_) {}
+	int code = 0;
+	std::string err, func, file;
+	int line = 0;
 };
 
 }  // namespace cv
 
-#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception(std::string("CV_Assert failed: ") + #expr); } while (0)
+#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception(cv::Error::StsAssert, #expr, __func__, __FILE__, __LINE__); } while (0)
 
 inline int cvRound(double v) { return (int)lrint(v); }
 inline int cvRound(float v) { return (int)lrintf(v); }

@@ -91,6 +91,8 @@ _SIGNATURES = {
     'orbx_extract_batch_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_void_p]),
     'orbx_max_keypoints': (C.c_int, [C.c_void_p]),
+    'orbx_plan': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    'orbx_last_result_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'orbx_synchronize': (C.c_int, [C.c_void_p]),
     'orbx_stream': (C.c_void_p, [C.c_void_p]),
     'orbx_enable_stage_timing': (C.c_int, [C.c_void_p, C.c_int]),
@@ -321,8 +323,13 @@ class ORBextractor:
         import torch
         F, H, W = d_images.shape
         assert d_images.dtype == torch.uint8 and d_images.is_cuda and d_images.stride(2) == 1
+        # the library's stream is not torch's: order it behind whatever produced d_images (and the output tensors' last use)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(d_images.device))
+        torch.cuda.ExternalStream(self.stream(), device=d_images.device).wait_event(ev)
         if d_kps is None:
             # plan first so that cap is the exact per-size bound
+            _check(lib().orbx_plan(self._h, W, H, F))
             cap = max(self.max_keypoints(), 1)
             d_kps = torch.empty((F, cap, 7), dtype=torch.float32, device=d_images.device)
             d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device=d_images.device)
@@ -410,8 +417,9 @@ def ComputeStereoMatchesResident(extractorL, extractorR, camera):
     """The same on the device-resident results of the last ExtractBatch of two extractors (what SystemImpl::TrackStereo
     does at src/System.cc:449-461, without moving keypoints, descriptors or pyramids off the GPU).
     Returns (uright, depth) as (F, cap) arrays; entries past a frame's keypoint count are undefined."""
-    F = extractorL._last_frames
-    cap = extractorL.max_keypoints()
+    f, c = C.c_int(), C.c_int()
+    _check(lib().orbx_last_result_shape(extractorL._h, C.byref(f), C.byref(c)))
+    F, cap = f.value, c.value         # the arrays are laid out like the keypoints of that extract
     ur = np.full((F, cap), -1, np.float32); dp = np.full((F, cap), -1, np.float32)
     cam = _Camera(*[float(v) for v in camera])
     _check(lib().orbx_stereo_match(extractorL._h, extractorR._h, C.byref(cam), _p(ur), _p(dp)))

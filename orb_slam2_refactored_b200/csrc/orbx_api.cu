@@ -114,6 +114,9 @@ struct orbx_extractor
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
 	OrbxTmaMaps maps;
+	OrbxStripMaps smaps;                // strip kernels (blur, dense FAST bound): every level with the strip box
+	OrbxPyrMaps pmaps;                  // strip resize kernel: level s - 1 with the source box of a tile of level s
+	DevBuf<uint8_t> fmap_ini, fmap_min; // FAST bound bitmaps (1 bit per level pixel each)
 	DevBuf<uint8_t> color;              // interleaved colour frames / unrectified frames of the current batch (orbx_extract_batch_color / _rectified)
 	DevBuf<int2> rect_tab;              // rectification table (orbx_set_rectification): per output pixel (ix | iy << 16, fx | fy << 5)
 	int rect_w = 0, rect_h = 0, rect_sw = 0, rect_sh = 0;
@@ -198,11 +201,14 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		h->P.frames = frames;
 		return ORBX_OK;
 	}
+	// from here on the old plan is gone: a failed rebuild must not leave a size cache that matches a zeroed plan
+	h->pw = h->ph = h->frames_cap = 0;
+	h->have_result = false;
+	OrbxPlanDev& P = h->P;
+	std::memset(&P, 0, sizeof(P));
 	if (w > 4096 || hgt > 4096)
 		return fail(ORBX_ERR_INVALID, "image larger than 4096 px per side (candidate packing limit)");
 
-	OrbxPlanDev& P = h->P;
-	std::memset(&P, 0, sizeof(P));
 	P.nlevels = nl; P.frames = frames;
 	P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
 
@@ -296,6 +302,30 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			if (max_rows > orbx_pyramid_max_src_rows() || max_bytes > orbx_pyramid_max_src_bytes())
 				return fail(ORBX_ERR_INVALID, "scaleFactor too large for the resize kernel (max about 2.2)");
 			L.py_smem = max_rows * max_bytes;
+			// strip resize kernel (one warp per 128 x TH tile, source rectangle by one TMA box): box rows/bytes over all tiles. A lane reads
+			// three aligned words from its first source column on and picks its four (s[x], s[x+1]) pairs out of 8 bytes.
+			{
+				const int sth = orbx_pyramid_strip_rows();
+				int brows = 0, bbytes = 0, emax = 0;
+				for (int y0 = 0; y0 < L.h; y0 += sth)
+				{
+					const int y1 = std::min(y0 + sth, L.h) - 1;
+					brows = std::max(brows, std::min(yofs[L.ytab_base + y1] + 1, P.lv[s - 1].h - 1) - yofs[L.ytab_base + y0] + 1);
+				}
+				for (int x0 = 0; x0 < L.w; x0 += tw)
+				{
+					const int xa = xofs[L.xtab_base + x0] & ~15;
+					for (int x = x0; x < std::min(x0 + tw, L.w); x += 4)
+					{
+						const int xl = std::min(x + 3, L.w - 1);
+						emax = std::max(emax, xofs[L.xtab_base + xl] - xofs[L.xtab_base + x]);
+						bbytes = std::max(bbytes, ((xofs[L.xtab_base + x] - xa) & ~3) + 12);
+					}
+				}
+				bbytes = (int)align_up(bbytes, 16);
+				if (emax <= 6 && bbytes <= 256 && brows <= 256 && bbytes * brows <= 96 * 1024) { L.py_bw = bbytes; L.py_bh = brows; }
+				else { L.py_bw = 0; L.py_bh = 0; }      // scale factor too large for one TMA box: the cp.async kernel produces this level
+			}
 		}
 	}
 	P.slab = slab;
@@ -314,6 +344,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(h->l0buf.ensure(F * h->l0_stride + 512));
 	h->l0base = h->l0buf.p + 256;
 	CU(h->cand.ensure(F * cands)); CU(h->qbuf0.ensure(F * cands)); CU(h->qbuf1.ensure(F * cands));
+	CU(h->fmap_ini.ensure(F * (slab >> 3) + 64)); CU(h->fmap_min.ensure(F * (slab >> 3) + 64));
 	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
 	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl));
 	CU(h->sel.ensure(F * sels));
@@ -335,6 +366,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(cudaStreamSynchronize(h->stream));    // the host vectors above die with this scope
 
 	P.pyr = h->pyr.p + 256; P.blur = h->blur.p;
+	P.fmap_ini = h->fmap_ini.p; P.fmap_min = h->fmap_min.p;
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
@@ -348,6 +380,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
 		if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
 		std::memset(&h->maps, 0, sizeof(h->maps));
+		std::memset(&h->smaps, 0, sizeof(h->smaps));
+		std::memset(&h->pmaps, 0, sizeof(h->pmaps));
 		for (int s = 0; s < nl; s++)
 		{
 			const OrbxLevel& L = P.lv[s];
@@ -364,6 +398,21 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 			                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			if (r != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+			// the same tensor with the strip box (blur, dense FAST bound) ...
+			const cuuint32_t sbox[3] = { (cuuint32_t)orbx_strip_box_w(), (cuuint32_t)orbx_strip_box_h(), 1 };
+			const CUresult r2 = ((EncodeFn)fn)(&h->smaps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, sbox, estr,
+			                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			if (r2 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (strip box) failed with CUresult " + std::to_string((int)r2));
+			// ... and, as the SOURCE of level s + 1, with that level's resize box
+			if (s + 1 < nl && P.lv[s + 1].py_bw > 0)
+			{
+				const cuuint32_t pbox[3] = { (cuuint32_t)P.lv[s + 1].py_bw, (cuuint32_t)P.lv[s + 1].py_bh, 1 };
+				const CUresult r3 = ((EncodeFn)fn)(&h->pmaps.src[s + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, pbox, estr,
+				                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+				                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+				if (r3 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (resize box) failed with CUresult " + std::to_string((int)r3));
+			}
 		}
 	}
 	h->pw = w; h->ph = hgt; h->frames_cap = frames;
@@ -406,20 +455,22 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	}
 	// The blur on a side stream beside the quadtree was measured: +1.2 % device-resident (178.3 k vs 176.1 k frames/s), -3 % end to end
 	// (147.6 k vs 151.9 k: two more streams per handle in the chunk pipeline), no change without the stage events. Default: in line.
-	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr;
+	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr || orbx_fused_blur_fast();
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
 	if (ev) CU(cudaEventRecord(ev[0], st));
-	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, s, st);
+	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, h->pmaps, s, st);
 	if (ev) CU(cudaEventRecord(ev[1], st));
+	const bool fused = orbx_fused_blur_fast();      // blur + dense FAST bound as one strip kernel: the stage events then book it all under FAST
 	if (blur_inline)
 	{
 		if (ev) CU(cudaEventRecord(ev[6], st));
-		orbx_launch_blur(P, st);
+		if (!fused) orbx_launch_blur(P, h->smaps, st);
 		if (ev) CU(cudaEventRecord(ev[7], st));
 	}
 	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_fast(P, h->maps, st);
+	if (fused) orbx_launch_blur_fast(P, h->maps, h->smaps, st);
+	else orbx_launch_fast(P, h->maps, h->smaps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
 	if (!blur_inline)
 	{
@@ -428,7 +479,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 		CU(cudaEventRecord(h->side_fork[lane], st));
 		CU(cudaStreamWaitEvent(side, h->side_fork[lane], 0));
 		if (ev) CU(cudaEventRecord(ev[6], side));
-		orbx_launch_blur(P, side);
+		orbx_launch_blur(P, h->smaps, side);
 		if (ev) CU(cudaEventRecord(ev[7], side));
 		CU(cudaEventRecord(h->side_join[lane], side));
 	}
@@ -497,6 +548,7 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side_join[l], cudaEventDisableTiming);
 	}
 	if (e == cudaSuccess) e = orbx_upload_pattern();
+	if (e == cudaSuccess) e = orbx_kernels_init();
 	if (e != cudaSuccess)
 	{
 		delete h;
@@ -515,7 +567,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->l0buf.release(); h->color.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
 	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
-	h->cell_tab.release();
+	h->cell_tab.release(); h->fmap_ini.release(); h->fmap_min.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release(); h->st_rows.release(); h->st_items.release();
@@ -570,6 +622,23 @@ int orbx_max_keypoints(orbx_handle h)
 	int s = 0;
 	for (int q : h->quota) s += std::max(q + 3, 4 * ORBX_MAX_ROOTS);
 	return s;
+}
+
+orbx_status orbx_plan(orbx_handle h, int width, int height, int frames)
+{
+	if (!h) return fail(ORBX_ERR_INVALID, "null handle");
+	if (frames < 1 || width < 1 || height < 1) return fail(ORBX_ERR_INVALID, "bad image geometry");
+	CU(cudaSetDevice(h->device));
+	return build_plan(h, width, height, frames);
+}
+
+orbx_status orbx_last_result_shape(orbx_handle h, int* frames, int* cap)
+{
+	if (!h) return fail(ORBX_ERR_INVALID, "null handle");
+	if (!h->have_result) return fail(ORBX_ERR_STATE, "no extract has run on this handle");
+	if (frames) *frames = h->last_frames;
+	if (cap) *cap = h->last_cap;
+	return ORBX_OK;
 }
 
 orbx_status orbx_synchronize(orbx_handle h)
@@ -703,6 +772,10 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 		h->h_counts_n = (size_t)frames;
 	}
 	int32_t* counts = h->h_counts;
+	// the per-frame buffers are shared with whatever an earlier asynchronous call (orbx_extract_batch_device, stereo) left pending on the
+	// handle's stream: the second lane starts behind it
+	CU(cudaEventRecord(h->fork, h->stream));
+	CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
 	int ci = 0;
 	for (int fb = 0; fb < frames; fb += chunk, ci++)
 	{

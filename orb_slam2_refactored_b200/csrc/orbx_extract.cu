@@ -233,9 +233,11 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 
 // =====================================================================================================
 // K2  fast9_cell — DetectFAST (src/ORBextractor.cc:489-540) with cv::FAST(..., nms = true) semantics
-//     (SURVEY App. A.4). One CTA per ~30 px cell: the cell view (cell + 6 px) is staged in shared memory,
+//     (SURVEY App. A.4). One warp per ~30 px cell: the cell view (cell + 6 px) is staged in shared memory,
 //     the threshold-independent arc score S is computed for the pixels that pass a cheap 4-pair rejection
-//     at minThFAST, local maxima are found once, and the iniTh -> minTh retry is just a second count.
+//     (every arc of 9 contains one pixel of each opposite pair (k, k+8), so min_arc(ring) <= max(ring_k, ring_k+8):
+//     S_bright <= min_k max(ring_k, ring_k+8) - centre, S_dark <= centre - max_k min(ring_k, ring_k+8), k = 0, 2, 4, 6),
+//     local maxima are found once, and the iniTh -> minTh retry is a second pass over the pixels in between.
 //     Candidates are emitted row-major into the cell's private slot range, so DetectFAST's cell-major /
 //     row-major push_back order is reproduced without atomics on global memory.
 // =====================================================================================================
@@ -243,9 +245,6 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 #define FT_TH 66
 #define FT_SS 64            // score row stride (region <= 60 px + 1 px zero border each side)
 #define FT_MAXR 60
-#define FT_THREADS 128
-#define FT_WORDS ((FT_MAXR * FT_MAXR + 31) / 32)                      // bitmap words for the largest region
-#define FT_WPT ((FT_WORDS + FT_THREADS - 1) / FT_THREADS)           // bitmap words owned by one thread
 
 __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 {
@@ -280,200 +279,8 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 	return max(dark, bright);
 }
 
-// Upper bound of the arc score from the 4 opposite pairs at even ring positions: every arc of 9 contains one pixel of each
-// pair (k, k+8), so min_arc(ring) <= max(ring_k, ring_k+8) for every k, hence
-//   S_bright <= min_k max(ring_k, ring_k+8) - centre,   S_dark <= centre - max_k min(ring_k, ring_k+8).
-// Same packing as the exact network: both polarities in one VIMNMX.U16x2 chain.
-__device__ __forceinline__ int arc_score_bound(const uint8_t* __restrict__ c)
-{
-	constexpr int R[8] = { 3 * FT_TS, 2 * FT_TS + 2, 3, -2 * FT_TS + 2, -3 * FT_TS, -2 * FT_TS - 2, -3, 2 * FT_TS - 2 };   // ring 0,2,..,14
-	uint32_t v[8];
-#pragma unroll
-	for (int k = 0; k < 8; k++)
-		v[k] = (uint32_t)c[R[k]] * 0xFFFF0001u + 0x00FF0000u;
-	const uint32_t m = __vminu2(__vminu2(__vmaxu2(v[0], v[4]), __vmaxu2(v[1], v[5])), __vminu2(__vmaxu2(v[2], v[6]), __vmaxu2(v[3], v[7])));
-	const int centre = c[0];
-	return max((int)(m & 0xffffu) - centre, centre - 255 + (int)(m >> 16));
-}
-
-// One CTA (4 warps) per cell:
-//   A. every region pixel gets the cheap upper bound U >= S; warp ballots of (U > iniTh) and (minTh < U <= iniTh) are the
-//      row-major bitmaps of the pixels that can matter at either threshold;
-//   B. the exact arc score S is computed only for the pixels of the first bitmap (a few percent), compacted into a list so
-//      that every lane works; pixels never evaluated keep score 0, which is what M_t = (S > t ? S - 1 : 0) gives them anyway;
-//   C. strict 8-neighbour local maxima among them with S > iniTh. If the cell has none (the retry of :526-530), the second
-//      bitmap is evaluated too and the test repeats with minTh over both;
-//   D. ordered emit from the survivor bitmap: DetectFAST's cell-major / row-major push_back order without global atomics.
-__global__ void __launch_bounds__(FT_THREADS) k_fast_cells_v1(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps)
-{
-	__shared__ __align__(128) uint8_t tile[FT_TH * FT_TS];
-	__shared__ __align__(8) uint64_t tma_bar;
-	__shared__ __align__(16) uint8_t score[(FT_MAXR + 2) * FT_SS];
-	__shared__ uint16_t list[FT_MAXR * FT_MAXR];
-	__shared__ uint32_t bm_a[FT_WPT * FT_THREADS], bm_b[FT_WPT * FT_THREADS], bm_sel[FT_WPT * FT_THREADS];   // one bit per region pixel, row-major (<= 3600 bits)
-	__shared__ int s_wsum[FT_THREADS / 32];
-
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int cell = blockIdx.x, f = blockIdx.y;
-	const int4 ct = __ldg(P.cell_tab + cell);        // host-built: x0 | y0 << 16, vw | vh << 16, level, cell index inside the level
-	const int x0 = ct.x & 0xffff, y0 = ct.x >> 16, vw = ct.y & 0xffff, vh = ct.y >> 16, lvl = ct.z, c = ct.w;
-	const OrbxLevel& L = P.lv[lvl];
-	const int rw = vw - 6, rh = vh - 6;              // detection region, >= 1 by the reference's loop conditions (:519,521)
-	const int npx = rw * rh;
-	const uint32_t inv_rw = c_inv20[rw];
-
-	// ---- stage the view with one TMA tile load: box FT_TS x box_h of level `lvl`, frame `frame0 + f`. The innermost start
-	//      coordinate of a u8 tile must be a multiple of 16 bytes (measured: tools/tma_probe.cu faults otherwise), so the box
-	//      starts at x0 - sh and pixel (x0 + i, y0 + j) lands at tile[j*FT_TS + sh + i]. Columns/rows past the view are other
-	//      pixels of the level (or zero fill past its edge) and are never read.
-	const int sh = x0 & 15;
-	if (tid == 0)
-	{
-		mbar_init(&tma_bar, 1);
-		mbar_expect_tx(&tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
-		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, &tma_bar);
-	}
-	for (int i = tid; i < (rh + 2) * (FT_SS / 4); i += FT_THREADS)
-		reinterpret_cast<uint32_t*>(score)[i] = 0;
-#pragma unroll
-	for (int k = 0; k < FT_WPT; k++) { bm_a[tid * FT_WPT + k] = 0; bm_b[tid * FT_WPT + k] = 0; bm_sel[tid * FT_WPT + k] = 0; }
-	__syncthreads();            // the barrier init by thread 0 is visible to every waiter
-	mbar_wait(&tma_bar, 0);
-
-	const int tmin = P.min_th, tini = P.ini_th;
-	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
-
-	// ---- A: upper bound for every pixel. A warp covers 32 consecutive row-major pixels per iteration, so its ballots
-	//      are the bitmap words of those pixels.
-	{
-		// (ry, rx) of pixel tid, then stepped by 128 pixels per iteration without multiplications
-		const int step_y = (int)(((uint32_t)FT_THREADS * inv_rw) >> 20), step_x = FT_THREADS - step_y * rw;
-		int ry = (int)(((uint32_t)tid * inv_rw) >> 20), rx = tid - ry * rw;
-		const uint8_t* p = t0 + ry * FT_TS + rx;
-		const int step_p = step_y * FT_TS + step_x, wrap_p = FT_TS - rw;
-		for (int i0 = 0; i0 < npx; i0 += FT_THREADS)
-		{
-			const int u = (i0 + tid < npx) ? arc_score_bound(p) : 0;
-			const unsigned ba = __ballot_sync(0xffffffffu, u > tini), bb = __ballot_sync(0xffffffffu, u > tmin && u <= tini);
-			if (lane == 0) { bm_a[(i0 >> 5) + warp] = ba; bm_b[(i0 >> 5) + warp] = bb; }
-			rx += step_x; p += step_p;
-			if (rx >= rw) { rx -= rw; p += wrap_p; }
-		}
-	}
-	__syncthreads();
-
-	// helpers -------------------------------------------------------------------------------------------------------
-	// exclusive block scan of one int per thread; returns this thread's offset, total in `total`
-	auto block_scan = [&](int v, int& total) {
-		int inc = v;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			const int t = __shfl_up_sync(0xffffffffu, inc, d);
-			if (lane >= d) inc += t;
-		}
-		__syncthreads();                   // s_wsum may still be read from the previous scan
-		if (lane == 31) s_wsum[warp] = inc;
-		__syncthreads();
-		int base = inc - v;
-		total = 0;
-#pragma unroll
-		for (int w = 0; w < FT_THREADS / 32; w++)
-		{
-			const int t = s_wsum[w];
-			if (w < warp) base += t;
-			total += t;
-		}
-		return base;
-	};
-	// append the pixels of a bitmap to the list (row-major inside the bitmap); returns how many
-	auto expand = [&](const uint32_t* bm, int at) {
-		uint32_t w[FT_WPT];
-		int cnt = 0;
-#pragma unroll
-		for (int k = 0; k < FT_WPT; k++) { w[k] = bm[tid * FT_WPT + k]; cnt += __popc(w[k]); }
-		int total;
-		int pos = at + block_scan(cnt, total);
-#pragma unroll
-		for (int k = 0; k < FT_WPT; k++)
-			while (w[k])
-			{
-				list[pos++] = (uint16_t)((tid * FT_WPT + k) * 32 + __ffs(w[k]) - 1);
-				w[k] &= w[k] - 1;
-			}
-		return total;
-	};
-	// exact score of list[from, to)
-	auto evaluate = [&](int from, int to) {
-		for (int j = from + tid; j < to; j += FT_THREADS)
-		{
-			const int i = list[j];
-			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
-			score[(ry + 1) * FT_SS + rx + 1] = (uint8_t)max(s, 0);
-		}
-	};
-	// strict local maxima with S > t among list[0, to): set their bit; returns whether this thread found one
-	auto select = [&](int to, int t) {
-		bool found = false;
-		for (int j = tid; j < to; j += FT_THREADS)
-		{
-			const int i = list[j];
-			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-			const uint8_t* sp = score + (ry + 1) * FT_SS + rx + 1;
-			const int s = sp[0];
-			if (s > t)
-			{
-				const int m = max(max(max((int)sp[-FT_SS - 1], (int)sp[-FT_SS]), max((int)sp[-FT_SS + 1], (int)sp[-1])),
-				                  max(max((int)sp[1], (int)sp[FT_SS - 1]), max((int)sp[FT_SS], (int)sp[FT_SS + 1])));
-				if (s > m) { atomicOr(&bm_sel[i >> 5], 1u << (i & 31)); found = true; }
-			}
-		}
-		return found;
-	};
-
-	// ---- B + C at iniTh
-	const int n1 = expand(bm_a, 0);
-	__syncthreads();
-	evaluate(0, n1);
-	__syncthreads();
-	const int any_hi = __syncthreads_or(select(n1, tini));
-	if (!any_hi)
-	{
-		// ---- retry at minTh (:529-530): the pixels with minTh < U <= iniTh become relevant too
-		const int n2 = expand(bm_b, n1);
-		__syncthreads();
-		evaluate(n1, n1 + n2);
-		__syncthreads();
-		select(n1 + n2, tmin);
-		__syncthreads();
-	}
-
-	// ---- D: ordered emit; thread t owns bitmap words [t*FT_WPT, (t+1)*FT_WPT)
-	uint32_t selw[FT_WPT];
-	int nsel = 0;
-#pragma unroll
-	for (int k = 0; k < FT_WPT; k++) { selw[k] = bm_sel[tid * FT_WPT + k]; nsel += __popc(selw[k]); }
-	int total;
-	int base = block_scan(nsel, total);
-	uint32_t* __restrict__ out = P.cand + (int64_t)f * P.cand_per_frame + L.cand_base + (int64_t)c * L.cell_cap;
-#pragma unroll
-	for (int k = 0; k < FT_WPT; k++)
-		while (selw[k])
-		{
-			const int i = (tid * FT_WPT + k) * 32 + __ffs(selw[k]) - 1;
-			selw[k] &= selw[k] - 1;
-			const int ry = (int)(((uint32_t)i * inv_rw) >> 20), rx = i - ry * rw;
-			const int s = score[(ry + 1) * FT_SS + rx + 1];
-			out[base++] = orbx_pack(x0 + 3 + rx, y0 + 3 + ry, s - 1);
-		}
-	if (tid == 0)
-		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
-}
-
-// ---- warp-per-cell FAST (the default). The CTA-per-cell kernel above spends 2/3 of its instructions outside the bound pass: four
-// warps each run the scans, list building, NMS and emit of one cell, separated by block barriers (ncu: barrier is the top stall).
-// Here ONE warp owns a cell end to end, so those phases cost a quarter and need only __syncwarp, and the bound pass works on
+// ---- warp-per-cell FAST with the bound pass inside the cell (ORBX_LEGACY=1; the default is the dense strip pass + k_fast_cells2
+// of orbx_strip.cuh). ONE warp owns a cell end to end, so the phases need only __syncwarp, and the bound pass works on
 // 4 horizontally adjacent pixels per lane: aligned 32-bit words of the tile are turned into packed u16x2 operands with PRMT
 // (a pixel sits in the HIGH byte of a 16-bit lane, the low byte is a neighbour pixel and never decides a min/max), so the 8 ring
 // loads + 8 packs + 7 min/max per pixel of the byte-wise version become 11 word loads + 13 PRMT + 24 VIMNMX per FOUR pixels.
@@ -488,7 +295,7 @@ struct OrbxFastLayout
 };
 
 // Bound pass for the 4 pixels of tile word q[0] (centre row). Returns one byte: bits (0,1,4,5) = U > minTh for pixels 0..3,
-// bits (2,3,6,7) = U > iniTh, where U >= S is the 4-pair upper bound of arc_score_bound(). kini/kmin = (0x8000 - 1 - t) in both
+// bits (2,3,6,7) = U > iniTh, where U >= S is the 4-pair upper bound described above. kini/kmin = (0x8000 - 1 - t) in both
 // halves fold the "+255" of the lane arithmetic and the threshold into one constant: bit 15 of a lane <=> U > t.
 __device__ __forceinline__ uint32_t fast_bound_flags4(const uint32_t* __restrict__ q, const uint32_t kini, const uint32_t kdelta)
 {
@@ -558,7 +365,7 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 	const int x0 = ct.x & 0xffff, y0 = ct.x >> 16, vw = ct.y & 0xffff, vh = ct.y >> 16, lvl = ct.z, c = ct.w;
 	const OrbxLevel& L = P.lv[lvl];
 	const int rw = vw - 6, rh = vh - 6;
-	const int sh = x0 & 15;                           // see k_fast_cells_v1: the TMA box starts 16-byte aligned
+	const int sh = x0 & 15;                           // the TMA box starts 16-byte aligned
 	if (lane == 0)
 	{
 		mbar_init(tma_bar, 1);
@@ -713,6 +520,8 @@ __global__ void __launch_bounds__(NW * 32) k_fast_cells(const OrbxPlanDev P, con
 	if (lane == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
 }
+
+#include "orbx_strip.cuh"
 
 // =====================================================================================================
 // K3+K4  quadtree_select — QuadTreeSuppression + QTreeNode::divide (src/ORBextractor.cc:402-453, :542-693)
@@ -1089,22 +898,59 @@ void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int 
 	k_remap_to_l0<<<grid, 256, 0, st>>>(src, spitch, sstride, sw, sh, tab, dst, dpitch, dstride, w, h);
 }
 
-void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
+// ---- tuning knobs, read once per process
+static int env_int(const char* name, int dflt)
+{
+	const char* e = getenv(name);
+	return e ? atoi(e) : dflt;
+}
+static bool legacy_kernels() { static const bool v = env_int("ORBX_LEGACY", 0) != 0; return v; }     // A/B: the round-1 kernels
+bool orbx_fused_blur_fast() { static const bool v = env_int("ORBX_FUSE", 0) != 0 && !legacy_kernels(); return v; }
+int orbx_strip_rows() { static const int v = env_int("ORBX_STRIP_TH", 32) == 64 ? 64 : env_int("ORBX_STRIP_TH", 32) == 16 ? 16 : 32; return v; }
+int orbx_strip_box_w() { return ST_BW; }
+int orbx_strip_box_h() { return orbx_strip_rows() + 2 * ST_HALO; }
+int orbx_pyramid_strip_rows() { static const int v = env_int("ORBX_PYR_TH", 32) == 16 ? 16 : 32; return v; }
+
+#define QT_SMEM_MAX (200 * 1024)
+// Function attributes are per device and cost a driver call each: set once per orbx_create, not per launch.
+cudaError_t orbx_kernels_init()
+{
+	cudaError_t e = cudaSuccess;
+	auto set = [&](auto fn, int bytes) {
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	};
+	set(k_pyramid_resize<PY_RW>, PY_SRC * PY_SW);
+	set(k_pyramid_resize<4>, PY_SRC * PY_SW);
+	set(k_pyramid_strip<32>, 100 * 1024);
+	set(k_pyramid_strip<16>, 100 * 1024);
+	set(k_fast_cells<1>, 64 * 1024);
+	set(k_fast_cells2, 64 * 1024);
+	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024); set(k_level_strip<16, true, true>, 64 * 1024);
+	set(k_level_strip<32, true, false>, 64 * 1024); set(k_level_strip<32, false, true>, 64 * 1024); set(k_level_strip<32, true, true>, 64 * 1024);
+	set(k_level_strip<64, true, false>, 64 * 1024); set(k_level_strip<64, false, true>, 64 * 1024); set(k_level_strip<64, true, true>, 64 * 1024);
+	set(qt128::k_quadtree<false>, QT_SMEM_MAX); set(qt256::k_quadtree<false>, QT_SMEM_MAX);
+	set(qt256::k_quadtree<true>, QT_SMEM_MAX); set(qt512::k_quadtree<true>, QT_SMEM_MAX);
+	set(k_orient_describe, OD_SMEM);
+	return e;
+}
+
+void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps& pmaps, int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
+	if (D.py_bw > 0 && !legacy_kernels())
+	{
+		// strip kernel: one warp per 128 x TH output tile, source rectangle by one TMA box
+		const int th = orbx_pyramid_strip_rows();
+		dim3 grid((D.w + ST_TW - 1) / ST_TW, (D.h + th - 1) / th, P.frames);
+		const int smem = ((D.py_bw * D.py_bh + 127) & ~127) + 16;
+		if (th == 16) k_pyramid_strip<16><<<grid, 32, smem, st>>>(P, pmaps, level);
+		else k_pyramid_strip<32><<<grid, 32, smem, st>>>(P, pmaps, level);
+		return;
+	}
 	const bool small_batch = P.frames <= 16;
 	const int th = small_batch ? 32 : PY_TH;
 	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + th - 1) / th, P.frames);
-	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem), up to PY_SRC * PY_SW = 86 KB
-	static bool attr_set[64] = {};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 64 && !attr_set[dev])
-	{
-		cudaFuncSetAttribute(k_pyramid_resize<PY_RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
-		cudaFuncSetAttribute(k_pyramid_resize<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PY_SRC * PY_SW);
-		attr_set[dev] = true;
-	}
+	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem), up to PY_SRC * PY_SW = 86 KB.
 	// py_smem is sized for the 128-row tile: an upper bound for the 32-row one
 	if (small_batch) k_pyramid_resize<4><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 	else k_pyramid_resize<PY_RW><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
@@ -1113,23 +959,76 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st)
 int orbx_fast_tile_stride() { return FT_TS; }
 int orbx_fast_tile_rows() { return FT_TH; }
 
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st)
+static OrbxStripTiles strip_tiles(const OrbxPlanDev& P, int th)
 {
-	static const bool v1 = getenv("ORBX_FAST_V1") != nullptr;   // A/B knob: the CTA-per-cell kernel
-	if (v1)
+	OrbxStripTiles T = {};
+	T.base[0] = 0;
+	for (int s = 0; s < P.nlevels; s++)
 	{
-		dim3 grid(P.cells_per_frame, P.frames);
-		k_fast_cells_v1<<<grid, FT_THREADS, 0, st>>>(P, maps);
-		return;
+		const OrbxLevel& L = P.lv[s];
+		T.tx[s] = (L.w + ST_TW - 1) / ST_TW;
+		T.base[s + 1] = T.base[s] + T.tx[s] * ((L.h + th - 1) / th);
 	}
-	// per-warp shared memory, sized by the largest cell of the plan: tile | score (1 px zero border) | list (aliases the flag bytes) | survivor bitmap | mbarrier
-	int rows = 0, maxrw = 0, maxrh = 0;
+	for (int s = P.nlevels; s < ORBX_MAX_LEVELS; s++) { T.tx[s] = 1; T.base[s + 1] = T.base[s]; }
+	return T;
+}
+
+// one launch over the tiles of all levels: blur (mode 1), dense FAST bound (mode 2) or both (mode 3)
+static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps& smaps, int mode, cudaStream_t st)
+{
+	const int th = orbx_strip_rows();
+	const OrbxStripTiles T = strip_tiles(P, th);
+	dim3 grid(T.base[P.nlevels], P.frames);
+	const int smem = st_tile_bytes(th) + 16;
+#define ORBX_STRIP_CASE(TH_)                                                                                      \
+	if (mode == 1) k_level_strip<TH_, true, false><<<grid, 32, smem, st>>>(P, smaps, T);                           \
+	else if (mode == 2) k_level_strip<TH_, false, true><<<grid, 32, smem, st>>>(P, smaps, T);                      \
+	else k_level_strip<TH_, true, true><<<grid, 32, smem, st>>>(P, smaps, T);
+	if (th == 16) { ORBX_STRIP_CASE(16) }
+	else if (th == 64) { ORBX_STRIP_CASE(64) }
+	else { ORBX_STRIP_CASE(32) }
+#undef ORBX_STRIP_CASE
+}
+
+// per-warp shared memory of the cell kernels, sized by the largest cell of the plan
+static void cell_extents(const OrbxPlanDev& P, const OrbxTmaMaps& maps, int& rows, int& maxrw, int& maxrh)
+{
+	rows = 0; maxrw = 0; maxrh = 0;
 	for (int s = 0; s < P.nlevels; s++)
 	{
 		rows = std::max(rows, maps.box_h[s]);
 		maxrw = std::max(maxrw, P.lv[s].cellw);
 		maxrh = std::max(maxrh, P.lv[s].cellh);
 	}
+}
+
+static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st)
+{
+	int rows, maxrw, maxrh;
+	cell_extents(P, maps, rows, maxrw, maxrh);
+	// tile | score (1 px zero border) | list of pixels to score | survivor bitmap | mbarrier
+	OrbxCellLayout Y;
+	Y.score_stride = (maxrw + 2 + 7) & ~7;
+	Y.off_score = (rows * FT_TS + 15) & ~15;
+	Y.off_list = (Y.off_score + (maxrh + 2) * Y.score_stride + 15) & ~15;
+	Y.off_bm = (Y.off_list + maxrw * maxrh * 2 + 15) & ~15;
+	Y.off_bar = Y.off_bm + 8 * maxrh;
+	Y.warp_bytes = (Y.off_bar + 8 + 127) & ~127;
+	dim3 grid(P.cells_per_frame, P.frames);
+	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
+}
+
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st)
+{
+	if (!legacy_kernels())
+	{
+		launch_strip(P, smaps, 2, st);
+		launch_cells2(P, maps, st);
+		return;
+	}
+	// per-warp shared memory, sized by the largest cell of the plan: tile | score (1 px zero border) | list (aliases the flag bytes) | survivor bitmap | mbarrier
+	int rows, maxrw, maxrh;
+	cell_extents(P, maps, rows, maxrw, maxrh);
 	OrbxFastLayout Y;
 	Y.score_stride = (maxrw + 2 + 7) & ~7;
 	Y.off_score = (rows * FT_TS + 15) & ~15;
@@ -1137,26 +1036,16 @@ void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_
 	Y.off_bm = (Y.off_list + std::max(maxrw * maxrh * 2, maxrh * 16) + 15) & ~15;
 	Y.off_bar = Y.off_bm + 8 * maxrh;
 	Y.warp_bytes = (Y.off_bar + 8 + 127) & ~127;
-	// Warps per CTA: a CTA's shared memory is released when its LAST warp retires, and cells differ in cost (retry, corner count), so
-	// with 4 warps per CTA a fifth of the resident warp slots sat idle behind a straggler (ncu: 19 of 24 possible warps active).
-	static const int nw_env = getenv("ORBX_FAST_WARPS") ? atoi(getenv("ORBX_FAST_WARPS")) : FW_WARPS;   // tuning knob: 1, 2 or 4
-	const int nw = (nw_env == 2 || nw_env == 4) ? nw_env : 1;
-	const int smem = nw * Y.warp_bytes;
-	static int attr_smem[64][3] = {};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	const int slot = nw == 1 ? 0 : nw == 2 ? 1 : 2;
-	if (dev >= 0 && dev < 64 && attr_smem[dev][slot] < smem)
-	{
-		if (nw == 1) cudaFuncSetAttribute(k_fast_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		else if (nw == 2) cudaFuncSetAttribute(k_fast_cells<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		else cudaFuncSetAttribute(k_fast_cells<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		attr_smem[dev][slot] = smem;
-	}
-	dim3 grid((P.cells_per_frame + nw - 1) / nw, P.frames);
-	if (nw == 1) k_fast_cells<1><<<grid, 32, smem, st>>>(P, maps, Y);
-	else if (nw == 2) k_fast_cells<2><<<grid, 64, smem, st>>>(P, maps, Y);
-	else k_fast_cells<4><<<grid, 128, smem, st>>>(P, maps, Y);
+	// One warp per CTA: a CTA's shared memory is released when its LAST warp retires, and cells differ in cost (retry, corner count); with
+	// 2 or 4 warps per CTA resident warp slots sat idle behind a straggler (measured 0.492 / 0.503 vs 0.471 ms per 256 frames).
+	dim3 grid(P.cells_per_frame, P.frames);
+	k_fast_cells<1><<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
+}
+
+void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st)
+{
+	launch_strip(P, smaps, 3, st);
+	launch_cells2(P, maps, st);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }
@@ -1191,12 +1080,10 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		static const int big_threads = getenv("ORBX_QT_THREADS") ? atoi(getenv("ORBX_QT_THREADS")) : 512;   // tuning knob: 256 or 512
 		if (large_plan && !small_batch && big_threads == 512)
 		{
-			cudaFuncSetAttribute(qt512::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			qt512::k_quadtree<true><<<grid, 512, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
 		}
 		else
 		{
-			cudaFuncSetAttribute(qt256::k_quadtree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			qt256::k_quadtree<true><<<grid, 256, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
 		}
 	}
@@ -1209,12 +1096,10 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		const int small_threads = small_env ? small_env : (P.frames >= 256 ? 128 : 256);
 		if (small_threads == 256)
 		{
-			cudaFuncSetAttribute(qt256::k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			qt256::k_quadtree<false><<<grid, 256, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 		}
 		else
 		{
-			cudaFuncSetAttribute(qt128::k_quadtree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			qt128::k_quadtree<false><<<grid, 128, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 		}
 	}
@@ -1229,8 +1114,13 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	}
 }
 
-void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStream_t st)
 {
+	if (!legacy_kernels())
+	{
+		launch_strip(P, smaps, 1, st);
+		return;
+	}
 	// Small batches (a frame at a time): one launch over the tiles of all levels, 8 launches fewer on the critical path (single-frame
 	// blur 36 -> 9 us). Large batches: one launch per level, which measures ~6 % faster there.
 	const bool one_launch = P.frames <= 16;
@@ -1260,6 +1150,5 @@ void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st)
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st)
 {
 	dim3 grid((P.out_cap + OD_WARPS - 1) / OD_WARPS, P.frames);
-	cudaFuncSetAttribute(k_orient_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, OD_SMEM);
 	k_orient_describe<<<grid, OD_WARPS * 32, OD_SMEM, st>>>(P, d_kps, d_desc, d_n);
 }

@@ -39,7 +39,8 @@ struct OrbxLevel
 	// resize tables of this level as destination (level >= 1)
 	int xtab_base, ytab_base;
 	float scale;                 // scaleFactors_[s]
-	int py_smem;                 // dynamic shared memory of the resize kernel producing this level
+	int py_smem;                 // dynamic shared memory of the cp.async resize kernel producing this level
+	int py_bw, py_bh;            // TMA box (bytes x rows of level s - 1) of the strip resize kernel producing this level; 0: not usable
 };
 
 struct OrbxPlanDev
@@ -54,6 +55,7 @@ struct OrbxPlanDev
 	// level 0 may alias the caller's device buffer
 	const uint8_t* l0; int64_t l0_pitch, l0_stride;
 	uint8_t* pyr; uint8_t* blur; int64_t slab;         // frame slabs (levels >= 1 of pyr; all levels of blur)
+	uint8_t* fmap_ini; uint8_t* fmap_min;   // FAST bound bitmaps, [frames][slab / 8]: bit x of row y of level s at (offset_s + y * pitch_s) / 8 + x / 8
 	uint32_t* cand;              // [frames][cand_per_frame] per-cell slots
 	int* cell_count;             // [frames][cells_per_frame]
 	const int4* cell_tab;        // [cells_per_frame] x0 | y0 << 16, view w | h << 16, level, cell index inside the level
@@ -84,16 +86,27 @@ struct OrbxTmaMaps
 };
 int orbx_fast_tile_stride();
 int orbx_fast_tile_rows();
+// TMA descriptors of the strip kernels: the levels as (pitch, h, frames) u8 tensors with the strip box (blur + dense FAST bound), and
+// level s - 1 with the source box of the resize tile that produces level s
+struct OrbxStripMaps { CUtensorMap level[ORBX_MAX_LEVELS]; };
+struct OrbxPyrMaps { CUtensorMap src[ORBX_MAX_LEVELS]; };
+int orbx_strip_rows();            // tile rows of the blur / FAST-bound strip kernel (fixed per process: ORBX_STRIP_TH, default 32)
+int orbx_strip_box_w();
+int orbx_strip_box_h();
+int orbx_pyramid_strip_rows();    // tile rows of the strip resize kernel
+cudaError_t orbx_kernels_init();  // per-device function attributes (dynamic shared memory limits); called once per orbx_create
 
 // kernel launchers (orbx_extract.cu)
 void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,
                       int w, int h, int frames, cudaStream_t st);
 void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
-void orbx_launch_pyramid(const OrbxPlanDev& P, int level, cudaStream_t st);
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st);
+void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps& pmaps, int level, cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
-void orbx_launch_blur(const OrbxPlanDev& P, cudaStream_t st);
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStream_t st);
+void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st);   // fused strip pass + cells
+bool orbx_fused_blur_fast();      // ORBX_FUSE=1: the blur and the dense FAST bound run as one strip kernel
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap);
 int orbx_pyramid_tile_rows();
