@@ -836,6 +836,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 	}
 }
 
+#include "orbx_describe.cuh"
+
 }  // namespace
 
 // =====================================================================================================
@@ -962,6 +964,7 @@ int orbx_fast_tile_rows() { return FT_TH; }
 static OrbxStripTiles strip_tiles(const OrbxPlanDev& P, int th)
 {
 	OrbxStripTiles T = {};
+	T.one = 1;
 	T.base[0] = 0;
 	for (int s = 0; s < P.nlevels; s++)
 	{
@@ -1149,6 +1152,12 @@ void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStre
 
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st)
 {
+	if (!legacy_kernels())
+	{
+		dim3 grid((P.out_cap + OD2_G - 1) / OD2_G, P.frames);
+		k_orient_describe2<<<grid, 32, OD2_SMEM, st>>>(P, d_kps, d_desc, d_n);
+		return;
+	}
 	dim3 grid((P.out_cap + OD_WARPS - 1) / OD_WARPS, P.frames);
 	k_orient_describe<<<grid, OD_WARPS * 32, OD_SMEM, st>>>(P, d_kps, d_desc, d_n);
 }

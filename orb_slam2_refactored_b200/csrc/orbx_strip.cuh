@@ -16,7 +16,7 @@
 #define ST_BWW (ST_BW / 4)
 #define ST_HALO 3
 
-struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; };
+struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int one; };   // one = 1, a value the compiler cannot fold (see FastRowOps)
 
 __host__ __device__ constexpr int st_tile_bytes(int th) { return ((ST_BW * (th + 2 * ST_HALO) + 127) / 128) * 128; }
 
@@ -51,38 +51,55 @@ __device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&p0)[4], const uin
 	return __byte_perm(__byte_perm(v[0], v[1], 0x6262), __byte_perm(v[2], v[3], 0x6262), 0x5410);
 }
 
-// ---- dense FAST bound for the lane's 4 pixels of one row (same arithmetic as the in-cell bound pass it replaces, see
-//      arc_score_bound): rows y-3 (m3), y-2 (ma mb mc), y (c0 c1 c2), y+2 (pa pb pc), y+3 (p3); a/b/c = word left / own / right.
-//      Returns 8 bits: bits 0..3 = U > iniTh for pixels 0..3, bits 4..7 = U > minTh.
-__device__ __forceinline__ uint32_t fast_bound_row4(uint32_t m3, uint32_t ma, uint32_t mb, uint32_t mc, uint32_t c0, uint32_t c1, uint32_t c2,
-                                                    uint32_t pa, uint32_t pb, uint32_t pc, uint32_t p3, const uint32_t kini, const uint32_t kdelta)
+// ---- dense FAST bound for the lane's 4 pixels of one row (same arithmetic as the in-cell bound pass it replaces): rows y-3 (m3),
+//      y-2, y, y+2, y+3 (p3). Returns 8 bits: bits 0..3 = U > iniTh for pixels 0..3, bits 4..7 = U > minTh.
+//      The kernel is bound by the ALU pipe (VIMNMX, PRMT, LOP3, SHF, IADD3 all issue there; ncu: 91 % ALU, 6 % FMA), so everything
+//      that has an integer multiply-add form is written as one: `one` / `mone` are 1 and -1 the compiler cannot see, which turns
+//      a + b and a - b into IMADs (FMA pipe). In particular min(a, b) = a + b - max(a, b): exact as a 32-bit word for packed 16-bit
+//      lanes (the final lanes are in range, modular arithmetic absorbs the borrows in between), one VIMNMX per pair instead of two.
+struct FastRowOps
+{
+	uint32_t one, mone, c256, kini, kdelta;
+	__device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) const { return a * one + b; }
+	__device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) const { return b * mone + a; }      // a - b
+};
+// operands of one row in its three roles. D[0..3]: the row's bytes moved two columns left / right, both parities, used when the row
+// is two above or two below the centre: (x+2: par 0, par 1), (x-2: par 0, par 1)
+__device__ __forceinline__ void fast_row_diag(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t (&D)[4])
+{
+	D[0] = __byte_perm(wb, wc, 0x5432); D[1] = __byte_perm(wb, wc, 0x4321);
+	D[2] = __byte_perm(wa, wb, 0x5432); D[3] = __byte_perm(wa, wb, 0x4321);
+}
+__device__ __forceinline__ uint32_t fast_bound_row4(const FastRowOps& K, uint32_t m3, const uint32_t (&Dm)[4], uint32_t c0, uint32_t c1, uint32_t c2,
+                                                    const uint32_t (&Dp)[4], uint32_t p3)
 {
 	uint32_t f[2];
 #pragma unroll
 	for (int par = 0; par < 2; par++)
 	{
 		// par 0: pixels 1 and 3 sit in the high bytes of the two 16-bit lanes; par 1: pixels 0 and 2 (operands one byte further left)
-		const uint32_t a1 = par == 0 ? p3 : p3 << 8;                                              // ( 0, +3)
-		const uint32_t a2 = par == 0 ? m3 : m3 << 8;                                              // ( 0, -3)
-		const uint32_t b1 = par == 0 ? __byte_perm(pb, pc, 0x5432) : __byte_perm(pb, pc, 0x4321); // (+2, +2)
-		const uint32_t b2 = par == 0 ? __byte_perm(ma, mb, 0x5432) : __byte_perm(ma, mb, 0x4321); // (-2, -2)
+		const uint32_t a1 = par == 0 ? p3 : p3 * K.c256;                                            // ( 0, +3)
+		const uint32_t a2 = par == 0 ? m3 : m3 * K.c256;                                            // ( 0, -3)
+		const uint32_t b1 = Dp[par], b2 = Dm[2 + par];                                            // (+2, +2), (-2, -2)
 		const uint32_t d1 = par == 0 ? __byte_perm(c1, c2, 0x6543) : __byte_perm(c1, c2, 0x5432); // (+3,  0)
 		const uint32_t d2 = par == 0 ? __byte_perm(c0, c1, 0x4321) : c0;                          // (-3,  0)
-		const uint32_t e1 = par == 0 ? __byte_perm(mb, mc, 0x5432) : __byte_perm(mb, mc, 0x4321); // (+2, -2)
-		const uint32_t e2 = par == 0 ? __byte_perm(pa, pb, 0x5432) : __byte_perm(pa, pb, 0x4321); // (-2, +2)
-		const uint32_t hi = __vminu2(__vimin3_u16x2(__vmaxu2(a1, a2), __vmaxu2(b1, b2), __vmaxu2(d1, d2)), __vmaxu2(e1, e2));   // min_k max(pair)
-		const uint32_t lo = __vmaxu2(__vimax3_u16x2(__vminu2(a1, a2), __vminu2(b1, b2), __vminu2(d1, d2)), __vminu2(e1, e2));   // max_k min(pair)
+		const uint32_t e1 = Dm[par], e2 = Dp[2 + par];                                            // (+2, -2), (-2, +2)
+		const uint32_t xa = __vmaxu2(a1, a2), xb = __vmaxu2(b1, b2), xd = __vmaxu2(d1, d2), xe = __vmaxu2(e1, e2);
+		const uint32_t na = K.sub(K.add(a1, a2), xa), nb = K.sub(K.add(b1, b2), xb), nd = K.sub(K.add(d1, d2), xd), ne = K.sub(K.add(e1, e2), xe);
+		const uint32_t hi = __vminu2(__vimin3_u16x2(xa, xb, xd), xe);      // min_k max(pair)
+		const uint32_t lo = __vmaxu2(__vimax3_u16x2(na, nb, nd), ne);      // max_k min(pair)
 		const uint32_t H = __byte_perm(hi, 0, 0x4341), Lo = __byte_perm(lo, 0, 0x4341);
 		const uint32_t C = par == 0 ? __byte_perm(c1, 0, 0x4341) : __byte_perm(c1, 0, 0x4240);
-		// lanes: (H - c) + K and (c - Lo) + K with K = 0x7fff - iniTh: bit 15 of a lane <=> U > iniTh; no lane borrows or carries
-		f[par] = __vmaxu2(H + kini - C, C + kini - Lo);
+		// lanes: (H - c) + K and (c - Lo) + K with K = 0x7fff - iniTh: bit 15 of a lane <=> U > iniTh; the final lanes neither borrow nor carry
+		f[par] = __vmaxu2(K.sub(K.add(H, K.kini), C), K.sub(K.add(C, K.kini), Lo));
 	}
-	const uint32_t g0 = f[0] + kdelta, g1 = f[1] + kdelta;     // kdelta = iniTh - minTh per lane: bit 15 <=> U > minTh
-	// pixel order 0,1,2,3 = f[1].lo, f[0].lo, f[1].hi, f[0].hi: the four sign bits land in bits 7,15,23,31 of one word, a multiply gathers them
-	const uint32_t fi = __byte_perm(f[1], f[0], 0x7351), gi = __byte_perm(g1, g0, 0x7351);
-	const uint32_t ni = (((fi >> 7) & 0x01010101u) * 0x01020408u) >> 24;
-	const uint32_t nm = (((gi >> 7) & 0x01010101u) * 0x01020408u) >> 24;
-	return ni | (nm << 4);
+	const uint32_t g0 = K.add(f[0], K.kdelta), g1 = K.add(f[1], K.kdelta);     // kdelta = iniTh - minTh per lane: bit 15 <=> U > minTh
+	// pixel order 0,1,2,3 = f[1].lo, f[0].lo, f[1].hi, f[0].hi: the sign bits land in bits 7,15,23,31 of one word (iniTh) and, moved
+	// down by 4, in bits 3,11,19,27 (minTh); ONE multiply gathers all eight: bit 7 + 8j -> 24 + j, bit 3 + 8j -> 20 + j ... the partial
+	// products fall on distinct bits, so nothing carries
+	const uint32_t fi = __byte_perm(f[1], f[0], 0x7351) & 0x80808080u, gi = (__byte_perm(g1, g0, 0x7351) >> 4) & 0x08080808u;
+	const uint32_t m = (fi | gi) * 0x00204081u;      // bit 7 + 8j -> 28 + j (iniTh), bit 3 + 8j -> 24 + j (minTh)
+	return m >> 24;                                  // low nibble = minTh flags, high nibble = iniTh flags
 }
 
 // Row walk of one tile. CHECK = false: every output row of the tile exists and (FAST) lies inside the cells' rows, so the loop has a
@@ -90,21 +107,22 @@ __device__ __forceinline__ uint32_t fast_bound_row4(uint32_t m3, uint32_t ma, ui
 // cell row.
 template <int TH, bool DO_BLUR, bool DO_FAST, bool CHECK>
 __device__ __forceinline__ void strip_rows(const uint32_t* __restrict__ tw, uint8_t* __restrict__ bdst, const int64_t pitch, const bool bstore,
-                                           uint8_t* __restrict__ fdst, const int64_t pitch8, const uint32_t kini, const uint32_t kdelta, const uint32_t selx,
+                                           uint8_t* __restrict__ fdst, const int64_t pitch8, const FastRowOps K, const uint32_t selx,
                                            const int lane, const int nrows, const int f0, const int f1)
 {
-	uint32_t R[8][3];            // FAST: raw words of the last 8 rows
+	uint32_t R[8][3];            // FAST: raw words of the last 8 rows (left / right words are dead once the row has been the centre)
+	uint32_t Dg[8][4];           // FAST: their two-column shifts (fast_row_diag), made when a row enters, dead once it is two above the centre
 	uint32_t Pp[4][4];           // blur: horizontal sums of the last 4 row pairs
 	auto load_pair = [&](const uint32_t* q, const int rs, const int slot) {      // box rows at q, q + ST_BWW into row slots rs, rs + 1 and pair slot `slot`
 		uint32_t he[4], ho[4];
 		{
 			const uint32_t W0 = q[0], W1 = q[1], W2 = q[2];
-			if (DO_FAST) { R[rs][0] = W0; R[rs][1] = W1; R[rs][2] = W2; }
+			if (DO_FAST) { R[rs][0] = W0; R[rs][1] = W1; R[rs][2] = W2; fast_row_diag(W0, W1, W2, Dg[rs]); }
 			if (DO_BLUR) blur_hrow(W0, W1, W2, he);
 		}
 		{
 			const uint32_t W0 = q[ST_BWW], W1 = q[ST_BWW + 1], W2 = q[ST_BWW + 2];
-			if (DO_FAST) { R[rs + 1][0] = W0; R[rs + 1][1] = W1; R[rs + 1][2] = W2; }
+			if (DO_FAST) { R[rs + 1][0] = W0; R[rs + 1][1] = W1; R[rs + 1][2] = W2; fast_row_diag(W0, W1, W2, Dg[rs + 1]); }
 			if (DO_BLUR) blur_hrow(W0, W1, W2, ho);
 		}
 		if (DO_BLUR)
@@ -115,12 +133,11 @@ __device__ __forceinline__ void strip_rows(const uint32_t* __restrict__ tw, uint
 	};
 	// FAST flags of the output row whose centre is window slot c
 	auto fast_row = [&](const int c, uint8_t* dst) {
-		const uint32_t v = fast_bound_row4(R[(c + 5) & 7][1], R[(c + 6) & 7][0], R[(c + 6) & 7][1], R[(c + 6) & 7][2], R[c][0], R[c][1], R[c][2],
-		                                   R[(c + 2) & 7][0], R[(c + 2) & 7][1], R[(c + 2) & 7][2], R[(c + 3) & 7][1], kini, kdelta);
+		const uint32_t v = fast_bound_row4(K, R[(c + 5) & 7][1], Dg[(c + 6) & 7], R[c][0], R[c][1], R[c][2], Dg[(c + 2) & 7], R[(c + 3) & 7][1]);
 		const uint32_t o = __shfl_xor_sync(0xffffffffu, v, 1);
-		// X = flags of the pair's lower 4 pixels | flags of its upper 4 pixels << 8; even lanes keep the iniTh nibbles, odd lanes the minTh ones
+		// X = flags of the pair's lower 4 pixels | flags of its upper 4 pixels << 8; even lanes keep the iniTh (high) nibbles, odd lanes the minTh ones
 		uint32_t X = __byte_perm(v, o, selx);
-		X >>= 4 * (lane & 1);
+		X >>= 4 * ((lane & 1) ^ 1);
 		*dst = (uint8_t)((X & 0xfu) | ((X >> 4) & 0xf0u));
 	};
 
@@ -190,12 +207,14 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 	if (DO_BLUR) bdst = P.blur + (int64_t)f * P.slab + L.offset + (int64_t)y0 * pitch + x;
 	// bound bitmaps: bit x of row y, one byte per lane pair; even lanes write the iniTh map, odd lanes the minTh map
 	uint8_t* __restrict__ fdst = nullptr;
-	uint32_t kini = 0, kdelta = 0, selx = 0;
+	FastRowOps K = {};
+	uint32_t selx = 0;
 	int f0 = 0, f1 = 0;
 	if (DO_FAST)
 	{
 		fdst = ((lane & 1) ? P.fmap_min : P.fmap_ini) + (int64_t)f * (P.slab >> 3) + (L.offset >> 3) + (int64_t)y0 * pitch8 + (x0 >> 3) + (lane >> 1);
-		kini = (uint32_t)(0x7fff - P.ini_th) * 0x00010001u; kdelta = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;
+		K.one = (uint32_t)T.one; K.mone = 0u - K.one; K.c256 = 256u * K.one;
+		K.kini = (uint32_t)(0x7fff - P.ini_th) * 0x00010001u; K.kdelta = (uint32_t)(P.ini_th - P.min_th) * 0x00010001u;
 		selx = (lane & 1) ? 0x1104u : 0x1140u;
 		// tile rows that belong to some cell's interior (cv::FAST skips a 3-pixel border of the cell view)
 		f0 = L.miny + 3 - y0; f1 = L.maxy - 3 - y0;
@@ -239,8 +258,8 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 
 	const uint32_t* __restrict__ tw = reinterpret_cast<const uint32_t*>(st_smem) + 3 + lane;   // word of columns x-4..x-1 of box row 0
 	const bool full = nrows == TH && (!DO_FAST || (f0 <= 0 && f1 >= TH));
-	if (full) strip_rows<TH, DO_BLUR, DO_FAST, false>(tw, bdst, pitch, x < w, fdst, pitch8, kini, kdelta, selx, lane, nrows, f0, f1);
-	else strip_rows<TH, DO_BLUR, DO_FAST, true>(tw, bdst, pitch, x < w, fdst, pitch8, kini, kdelta, selx, lane, nrows, f0, f1);
+	if (full) strip_rows<TH, DO_BLUR, DO_FAST, false>(tw, bdst, pitch, x < w, fdst, pitch8, K, selx, lane, nrows, f0, f1);
+	else strip_rows<TH, DO_BLUR, DO_FAST, true>(tw, bdst, pitch, x < w, fdst, pitch8, K, selx, lane, nrows, f0, f1);
 }
 
 // =====================================================================================================
@@ -260,7 +279,7 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 	const int bw = D.py_bw, bh = D.py_bh;
 	uint64_t* const bar = reinterpret_cast<uint64_t*>(py_smem + ((bw * bh + 127) & ~127));
 	const int lane = threadIdx.x, f = blockIdx.z;
-	const int sw = P.lv[level - 1].w, sh = P.lv[level - 1].h;
+	const int sh = P.lv[level - 1].h;
 	const int dx0 = blockIdx.x * ST_TW, dy0 = blockIdx.y * TH;
 	const int* __restrict__ yofs = P.yofs + D.ytab_base;
 	const int* __restrict__ xofs = P.xofs + D.xtab_base;
@@ -303,6 +322,7 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 	const bool store = dx0 + 4 * lane < D.w;
 	const int nrows = min(TH, D.h - dy0);
 	const int bww = bw >> 2;
+	const int64_t dpitch = D.pitch;
 	__syncwarp();
 	mbar_wait(bar, 0);
 
@@ -335,7 +355,8 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 #pragma unroll
 		for (int j = 0; j < 4; j++) s[j] = ((b0 * h0[j] + (2 << 16)) >> 16) + ((b1 * h1[j]) >> 16);   // = (b0 h0 >> 16) + (b1 h1 >> 16) + 2, in [0, 1023]
 		const uint32_t q01 = __byte_perm((uint32_t)s[0], (uint32_t)s[1], 0x5410) >> 2, q23 = __byte_perm((uint32_t)s[2], (uint32_t)s[3], 0x5410) >> 2;
-		if (store) *reinterpret_cast<uint32_t*>(dst + (int64_t)k * D.pitch) = __byte_perm(q01, q23, 0x6420);   // pitch is a multiple of 128: in-row padding absorbs the tail
+		if (store) *reinterpret_cast<uint32_t*>(dst) = __byte_perm(q01, q23, 0x6420);   // pitch is a multiple of 128: in-row padding absorbs the tail
+		dst += dpitch;
 	}
 }
 
@@ -402,9 +423,13 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 			wb[2 * k] = b0 & ~a0; wb[2 * k + 1] = b1 & ~a1;        // minTh < U <= iniTh
 		}
 	}
-	for (int i = lane; i < (rh + 2) * (SS / 8); i += 32)
-		reinterpret_cast<uint2*>(score)[i] = make_uint2(0, 0);
-	for (int i = lane; i < 2 * rh; i += 32) bm_sel[i] = 0;
+	{
+		const int n8 = (rh + 2) * (SS >> 3);              // score rows -1 .. rh, 8 bytes at a time (off_score is 16-byte aligned, SS a multiple of 8)
+#pragma unroll 1
+		for (int i = lane; i < n8; i += 32) reinterpret_cast<uint2*>(score)[i] = make_uint2(0, 0);
+		if (lane < rh) reinterpret_cast<uint2*>(bm_sel)[lane] = make_uint2(0, 0);
+		if (lane + 32 < rh) reinterpret_cast<uint2*>(bm_sel)[lane + 32] = make_uint2(0, 0);
+	}
 	__syncwarp();
 	mbar_wait(tma_bar, 0);
 
