@@ -129,6 +129,59 @@ def cpu_extract_rate(o, frames, threads, per_thread):
     return sum(done) / dt, dt
 
 
+def cpu_config_rate(o, name, threads, seconds=4.0):
+    """frames/s of the CPU Extract on frames of BASELINE.json config `name`, one frame per thread at a time, a bounded sample of about `seconds`."""
+    c = synth.CONFIGS[name]
+    frames = [synth.image(700 + s, c['w'], c['h']) for s in range(min(threads, 8))]
+    exs = [o.extractor(c['nfeatures']) for _ in range(threads)]
+    t0 = time.perf_counter()
+    exs[0].extract(frames[0])
+    one = time.perf_counter() - t0                      # single-thread time of one frame (also the warm-up of extractor 0)
+    per_thread = max(1, int(seconds / max(one, 1e-3)))
+    done = [0] * threads
+
+    def work(t):
+        for i in range(per_thread):
+            exs[t].extract(frames[(t + i) % len(frames)])
+            done[t] += 1
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th: x.start()
+    for x in th: x.join()
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, f'{sum(done)} frames {c["w"]}x{c["h"]} / {c["nfeatures"]} kp, one frame per thread at a time, {dt:.1f} s'
+
+
+def cpu_stereo_rate(o, threads, seconds=4.0):
+    """stereo pairs/s of Extract(left) + Extract(right) + ComputeStereoMatches on the CPU at the C2 shape, one pair per thread at a time."""
+    c = synth.CONFIGS['C2']
+    pairs = [synth.stereo_pair(800 + s, c['w'], c['h']) for s in range(min(threads, 4))]
+    exs = [(o.extractor(c['nfeatures']), o.extractor(c['nfeatures'])) for _ in range(threads)]
+
+    def one_pair(t, i):
+        L, R = pairs[(t + i) % len(pairs)]
+        eL, eR = exs[t]
+        kl, dl = eL.extract(L); kr, dr = eR.extract(R)
+        tb = eL.tables()
+        o.stereo(kl, dl, eL.pyramid(), kr, dr, eR.pyramid(), tb[0], tb[1], c['camera'])
+    t0 = time.perf_counter()
+    one_pair(0, 0)
+    one = time.perf_counter() - t0
+    per_thread = max(1, int(seconds / max(one, 1e-3)))
+    done = [0] * threads
+
+    def work(t):
+        for i in range(per_thread):
+            one_pair(t, i)
+            done[t] += 1
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th: x.start()
+    for x in th: x.join()
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, f'{sum(done)} stereo pairs 1241x376 / 2000 kp (Extract x2 + ComputeStereoMatches), one pair per thread at a time, {dt:.1f} s'
+
+
 def cpu_knn_rate(o, threads, nq=8192, nt=1000000):
     q = synth.descriptors(1, nq); t = synth.descriptors(2, nt)
     o.knn2(q[:64], t[:1000], 50, 0.6, threads=1)
@@ -172,6 +225,13 @@ def run_reference(args, rank, world, emit):
 # ---------------------------------------------------------------------------------------------------------------------
 # this repository's arm
 # ---------------------------------------------------------------------------------------------------------------------
+def _gpu_cpu_mask(pynvml, index, words):
+    try:
+        return pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), words)
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(local_rank):
     """One process per GPU: keep the process (and therefore its pinned staging buffers, first-touch) on the CPU cores NVML reports as
     local to that GPU, so that host<->device copies of different ranks do not cross the socket interconnect. Returns a note for `config`."""
@@ -182,10 +242,18 @@ def bind_to_gpu_numa_node(local_rank):
         words = (os.cpu_count() + 63) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
         cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
-        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        cpus = sorted(c for c in cpus if c in os.sched_getaffinity(0))
+        world = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', 1)))
         if cpus:
+            # ranks whose GPUs share a socket get DISJOINT slices of its cores: copy threads and the CUDA driver threads of different ranks
+            # must not migrate over each other (pinned staging is first-touched after this call, so it lands on the same cores' memory)
+            same = [r for r in range(world) if _gpu_cpu_mask(pynvml, r, words) == mask] if world > 1 else [local_rank]
+            if len(same) > 1 and local_rank in same and len(cpus) >= 2 * len(same):
+                per = len(cpus) // len(same)
+                k = same.index(local_rank)
+                cpus = cpus[k * per:(k + 1) * per]
             os.sched_setaffinity(0, cpus)
-            return f'{len(cpus)} cores local to GPU {local_rank}'
+            return f'{len(cpus)} cores local to GPU {local_rank} ({cpus[0]}-{cpus[-1]}), disjoint from the other ranks on the socket'
     except Exception as e:     # affinity is an optimisation, never load-bearing
         return f'unavailable ({type(e).__name__})'
     return 'unavailable'
@@ -293,18 +361,20 @@ def run_b200(args, rank, world, local_rank, emit):
     b_alg = 5 * S - P0 - P7 + 1321 * n_mean
     per_step = {k: v / max(calls, 1) for k, v in stage_ms.items()}
     dominant = max(per_step, key=per_step.get)
-    launches_per_stage = {'pyramid': len(sizes) - 1, 'fast': 1, 'quadtree': 1, 'blur': 1, 'describe': 1}
+    # FAST is two kernels (dense bound pass over the level tiles, then one warp per cell); the blur of all levels is one launch
+    launches_per_stage = {'pyramid': len(sizes) - 1, 'fast': 2, 'quadtree': 1, 'blur': 1, 'describe': 1}
     # roofline of the dominant stage, per launch: its algorithmic bytes for the whole batch / its device time
     dom_bytes_per_step = alg[dominant] * B
     dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0
     traffic = None
-    tj = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    kname = {'fast': 'k_fast_cells', 'describe': 'k_orient_describe', 'quadtree': 'k_quadtree'}.get(dominant)   # single-launch stages
-    if os.path.exists(tj) and kname:
-        t = json.load(open(tj)).get(kname)
-        if t:   # dram__bytes_read + write of one captured launch (ncu --set full, profiles/), scaled to this batch
-            traffic = t['dram_bytes_per_launch'] * B / float(t.get('frames_per_launch') or 256)
-    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+    tj = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.exists(tj):
+        t = json.load(open(tj)).get(dominant)
+        if t:   # dram__bytes_read + write of the stage's kernels in one captured step (ncu --set full, profiles/), scaled to this batch
+            traffic = t['dram_bytes_per_step'] * B / float(t.get('frames_per_step') or 256)
+    stage_kernels = {'pyramid': 'k_pyramid_strip x7', 'fast': 'k_level_strip<FAST> + k_fast_cells2', 'quadtree': 'k_quadtree', 'blur': 'k_level_strip<BLUR>',
+                     'describe': 'k_orient_describe2'}
+    roofline = {'bound': 'hbm', 'kernel': dominant, 'kernels': stage_kernels[dominant], 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': dom_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'launches_per_step': launches_per_stage[dominant],
                 'algorithmic_bytes_per_launch': dom_bytes_per_step / launches_per_stage[dominant],
@@ -347,7 +417,34 @@ def run_b200(args, rank, world, local_rank, emit):
     e2e_fps = world * NH * B * e2e_steps / (ms_e2e * 1e-3)
     n_h = bufs[0][2]
     h2d = B * W * H
-    d2h = int(n_h.sum()) * 60 + 4 * B
+    d2h = B * kcap * 60 + 4 * B                       # the call downloads whole capacity rows (a strided copy per chunk), not n[f] rows
+    # what the platform allows for exactly these transfers: the same bytes per step as plain pinned cudaMemcpyAsync on two streams (one per
+    # direction), no kernels, all ranks at once — the ceiling of ANY end-to-end number on this host
+    cs_in, cs_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_in = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    d_out = torch.empty((B, kcap, 60), dtype=torch.uint8, device=dev)
+    h_out = torch.empty((B, kcap, 60), dtype=torch.uint8).pin_memory()
+
+    def copy_step(i):
+        with torch.cuda.stream(cs_in):
+            d_in.copy_(pinned[i % 2], non_blocking=True)
+        with torch.cuda.stream(cs_out):
+            h_out.copy_(d_out, non_blocking=True)
+    for i in range(2):
+        copy_step(i)
+    torch.cuda.synchronize(dev)
+    barrier()
+    t_c = time.perf_counter()
+    csteps = 2 * e2e_steps
+    for i in range(csteps):
+        copy_step(i)
+    torch.cuda.synchronize(dev)
+    ms_copy = max_over_ranks((time.perf_counter() - t_c) * 1e3)
+    barrier()
+    copy_fps = world * B * csteps / (ms_copy * 1e-3)
+    copy_ceiling = {'value': copy_fps, 'unit': 'frames/s', 'gb_per_s_per_direction': {'h2d': world * h2d * csteps / ms_copy / 1e6, 'd2h': world * d2h * csteps / ms_copy / 1e6},
+                    'note': 'pinned cudaMemcpyAsync of the same H2D and D2H bytes per step, one stream per direction, no kernels, all ranks concurrently'}
+    del d_in, d_out, h_out
 
     # ---- kNN: per-GPU share of configs[4]
     knn = None
@@ -356,8 +453,24 @@ def run_b200(args, rank, world, local_rank, emit):
         nq, nt = args.knn_queries, args.knn_train_per_gpu
         g = torch.Generator(device=dev); g.manual_seed(1234)
         dq = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)     # queries replicated on every rank
-        g.manual_seed(99 + rank)
-        dt = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)     # this rank's train shard
+        nplant = max(1, nq // (8 * world))
+
+        def make_shard(r):
+            """Rank r's train shard: uniform random rows, plus nplant rows that are a query with ~16 of its 256 bits flipped (so that the
+            TH_LOW / ratio test accepts matches) and, for every 5th of them, an exact copy at a second row (lowest index must win)."""
+            gg = torch.Generator(device=dev); gg.manual_seed(99 + r)
+            t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=gg)
+            k = torch.arange(nplant, device=dev)
+            qi = (k * 131 + r * 7919) % nq
+            tj = (k * 977 + 13) % nt
+            flips = torch.randint(0, 256, (nplant, 32), dtype=torch.uint8, device=dev, generator=gg)
+            for _ in range(3):
+                flips &= torch.randint(0, 256, (nplant, 32), dtype=torch.uint8, device=dev, generator=gg)
+            t[tj] = dq[qi] ^ flips
+            dup = k[::5]
+            t[(tj[dup] + nt // 2) % nt] = t[tj[dup]]
+            return t
+        dt = make_shard(rank)                                                                # this rank's train shard
         m = api.ORBmatcher(0.6, device=local_rank)
         gathered = torch.empty((world, nq), dtype=torch.int64, device=dev) if world > 1 else None
         part = torch.empty(nq, dtype=torch.int64, device=dev)
@@ -380,8 +493,31 @@ def run_b200(args, rank, world, local_rank, emit):
         ms_knn = max_over_ranks(k0.elapsed_time(k1)) / args.knn_steps
         gpairs = nq * (nt * world) / (ms_knn * 1e-3) / 1e9
         popc_peak = api.measure_popc_peak(local_rank)
+        # check (every N): the first `nchk` queries of the timed result against ONE GPU scanning every shard in rank order — rank 0 rebuilds
+        # the other ranks' shards from their seeds, scans each with the right index base and merges; all four outputs must be identical
+        import hashlib
+        nchk = min(nq, 32768)
+        check = None
+        if rank == 0:
+            parts = torch.empty((world, nchk), dtype=torch.int64, device=dev)
+            for r in range(world):
+                sh = dt if r == 0 else make_shard(r)
+                api.knn2_partial_device(dq[:nchk], sh, r * nt, parts[r])
+                torch.cuda.synchronize(dev)
+                del sh
+            ref = api.knn2_merge_device(parts, world, nchk, 50, 0.6)
+            torch.cuda.synchronize(dev)
+            same = all(bool(torch.equal(a[:nchk], b)) for a, b in zip(res, ref))
+            dig = hashlib.sha256(b''.join(a[:nchk].cpu().numpy().tobytes() for a in res)).hexdigest()[:16]
+            check = {'result': 'ok' if same else 'MISMATCH', 'queries_checked': nchk, 'sha256_16': dig,
+                     'against': f'single-GPU scan of all {world} shard(s) in rank order (orbx_knn2_partial_device per shard + orbx_knn2_merge_device)'}
+            if not same:
+                raise RuntimeError('kNN: the sharded result differs from the single-GPU scan of the same data')
+        barrier()
         knn = {'value': gpairs, 'unit': 'Gpairs/s', 'ms_per_step': ms_knn, 'steps': args.knn_steps,
-               'workload': f'C5 share: {nq} queries x {nt} train rows per GPU ({nt * world} total), uniform random 256-bit descriptors',
+               'check': check['result'] if check else None, 'check_detail': check,
+               'workload': f'C5 share: {nq} queries x {nt} train rows per GPU ({nt * world} total), uniform random 256-bit descriptors with '
+                           f'{nplant} planted near-duplicates per shard',
                'roofline': {'bound': 'popc', 'achieved': 8 * gpairs / world * 1e9, 'peak': popc_peak, 'unit': 'POPC.32/s',
                             'frac': 8 * gpairs / world * 1e9 / popc_peak,
                             'peak_source': 'orbx_measure_popc_peak (register-operand POPC loop on all SMs, same run)'},
@@ -432,9 +568,73 @@ def run_b200(args, rank, world, local_rank, emit):
         barrier()
         ms_st = max_over_ranks(s0.elapsed_time(s1)) / ssteps
         matched = int((d_dp[:, :] > 0).sum().item())
-        stereo = {'value': world * SB / (ms_st * 1e-3), 'unit': 'stereo pairs/s', 'ms_per_step': ms_st, 'pairs_per_step_per_gpu': SB,
+        szS = eL.level_sizes()
+        S2 = sum(w_ * h_ for w_, h_ in szS)
+        nS = float(oL[2].float().mean().item())
+        b_alg2 = 2 * (5 * S2 - szS[0][0] * szS[0][1] - szS[-1][0] * szS[-1][1] + 1321 * nS)       # two extractions per pair; the match itself adds < 1 %
+        pairs_s = world * SB / (ms_st * 1e-3)
+        stereo = {'value': pairs_s, 'unit': 'stereo pairs/s', 'ms_per_step': ms_st, 'pairs_per_step_per_gpu': SB,
                   'workload': 'C2: 1241x376 stereo, 2000 kp per image, Extract left + right and ComputeStereoMatches, device-resident',
-                  'matched_per_pair': matched / SB}
+                  'matched_per_pair': matched / SB, 'keypoints_per_image': nS,
+                  'roofline': {'bound': 'hbm', 'frame': {'algorithmic_bytes_per_pair': b_alg2, 'achieved': b_alg2 * pairs_s / world / 1e9, 'unit': 'GB/s',
+                                                         'peak': hbm_peak, 'frac': b_alg2 * pairs_s / world / 1e9 / hbm_peak}}}
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            try:
+                o, kind, native = load_cpu_reference()
+                r_, smp = cpu_stereo_rate(o, os.cpu_count() or 1)
+                stereo['cpu_baseline'] = {'value': r_, 'unit': 'stereo pairs/s', 'cores': os.cpu_count() or 1, 'kind': kind, 'sample': smp}
+            except Exception as e:
+                stereo['cpu_baseline'] = {'unavailable': str(e)}
+        del dL, dR, eL, eR, oL, oR
+
+    # ---- BASELINE.json configs[2] and configs[3]: EuRoC-shape 752x480 / 1200 kp and 4K 3840x2160 / 8000 kp, device-resident extraction on
+    #      every rank's own frames (frames sharded, no collective), frame-level roofline, CPU reference beside it at N = 1
+    configs = None
+    if not args.skip_configs:
+        configs = {}
+        for name, cb, csteps_ in (('C3', 256, 6), ('C4', 16, 4)):
+            c = synth.CONFIGS[name]
+            base = np.stack([synth.image(2000 + 17 * rank + s_, c['w'], c['h']) for s_ in range(4)])
+            d1 = torch.from_numpy(base).to(dev).repeat((cb + 3) // 4, 1, 1)[:cb].contiguous()
+            d2 = torch.flip(d1, dims=[1]).contiguous()
+            ec = api.ORBextractor(nfeatures=c['nfeatures'], device=local_rank)
+            oc = ec.extract_batch_device(d1)
+            for i in range(3):
+                ec.extract_batch_device(d2 if i & 1 else d1, *oc)
+            ec.synchronize()
+            barrier()
+            sc = torch.cuda.ExternalStream(ec.stream(), device=dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(sc)
+            for i in range(csteps_):
+                ec.extract_batch_device(d2 if i & 1 else d1, *oc)
+            a1.record(sc)
+            a1.synchronize()
+            barrier()
+            ms_c = max_over_ranks(a0.elapsed_time(a1)) / csteps_
+            szc = ec.level_sizes()
+            Sc = sum(w_ * h_ for w_, h_ in szc)
+            nc = float(oc[2].float().mean().item())
+            b_c = 5 * Sc - szc[0][0] * szc[0][1] - szc[-1][0] * szc[-1][1] + 1321 * nc
+            fps_c = world * cb / (ms_c * 1e-3)
+            blk = {'workload': f'{name}: {c["w"]}x{c["h"]}, {c["nfeatures"]} kp, 8 levels, device-resident, {cb} frames per step per GPU '
+                               f'(two alternating batches of {cb * c["w"] * c["h"] / 1e6:.0f} MB + slabs: larger than L2)',
+                   'value': fps_c, 'unit': 'frames/s', 'ms_per_step': ms_c, 'steps': csteps_, 'keypoints_per_frame': nc,
+                   'roofline': {'bound': 'hbm', 'frame': {'algorithmic_bytes_per_frame': b_c, 'achieved': b_c * fps_c / world / 1e9, 'unit': 'GB/s',
+                                                          'peak': hbm_peak, 'frac': b_c * fps_c / world / 1e9 / hbm_peak}}}
+            if name == 'C3':
+                blk['sequence_10k_frames_s'] = 10000.0 / fps_c       # configs[2]: a 10k-frame sequence sharded over the GPUs of this run
+            if rank == 0 and world == 1 and not args.skip_cpu:
+                try:
+                    o, kind, native = load_cpu_reference()
+                    r_, smp = cpu_config_rate(o, name, os.cpu_count() or 1, 3.0)
+                    blk['cpu_baseline'] = {'value': r_, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': kind, 'sample': smp}
+                except Exception as e:
+                    blk['cpu_baseline'] = {'unavailable': str(e)}
+            configs[name] = blk
+            del d1, d2, ec, oc
+        if stereo is not None:
+            configs['C2'] = {k_: stereo[k_] for k_ in ('workload', 'value', 'unit', 'ms_per_step', 'roofline', 'cpu_baseline') if k_ in stereo}
 
     # ---- guided matchers: one tracking search per call through the C ABI, host buffers in and out. Latency-bound
     #      (one CTA per search), so it is reported as microseconds per call next to the reference text on one host core.
@@ -513,8 +713,8 @@ def run_b200(args, rank, world, local_rank, emit):
             except Exception as e:
                 guided['cpu_baseline'] = {'unavailable': str(e)}
 
-    # ---- rectification remap (Examples/Stereo/stereo_euroc.cc:100-101) at the EuRoC frame size, device-resident: the one HBM-bound
-    #      kernel of the set (8 B of table + 1 B gathered + 1 B written per pixel)
+    # ---- rectification remap (Examples/Stereo/stereo_euroc.cc:100-101) at the EuRoC frame size, device-resident: an L2-bound
+    #      kernel (8 B of table per pixel out of L2, 1 B gathered + 1 B written per pixel of DRAM traffic)
     remap = None
     if rank == 0 and not args.skip_guided:
         RB, RW, RH = 256, 752, 480
@@ -541,12 +741,14 @@ def run_b200(args, rank, world, local_rank, emit):
         r1.record(rs)
         r1.synchronize()
         ms_r = r0.elapsed_time(r1) / rsteps
-        alg = RB * RW * RH * 10
+        alg = RB * RW * RH * 2 + RW * RH * 8          # one byte gathered + one written per pixel, the 8-byte table entries once per launch
         remap = {'workload': f'cv::remap INTER_LINEAR of {RB} frames {RW}x{RH} with one rectification table, device-resident',
                  'value': RB / (ms_r * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms_r,
                  'roofline': {'bound': 'hbm', 'kernel': 'k_remap_to_l0', 'achieved': alg / (ms_r * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                              'frac': alg / (ms_r * 1e-3) / 1e9 / hbm_peak, 'algorithmic_bytes_per_pixel': 10,
-                              'note': 'the 2.9 MB table is shared by all frames of a launch and stays in L2, so DRAM traffic is ~2 B/px'}}
+                              'frac': alg / (ms_r * 1e-3) / 1e9 / hbm_peak, 'algorithmic_bytes_per_pixel': 2,
+                              'l2_bytes_per_pixel': 10,
+                              'note': 'L2-bound, not HBM-bound: every pixel reads its 8-byte table entry, but the 2.9 MB table is shared by all frames of '
+                                      'a launch and stays in L2 (ncu r01: 1.59 B/px of DRAM traffic); the HBM fraction counts 2 B/px + the table once'}}
         del d_rect, d_raw
 
     # ---- bag-of-words transform (Frame::ComputeBoW): the reference's vocabulary shape (k 10, L 6, levelsup 4) with
@@ -633,6 +835,7 @@ def run_b200(args, rank, world, local_rank, emit):
                        'frames_per_step_per_gpu': B, 'keypoints_per_frame': n_mean, 'cpu_affinity': affinity, 'parallelism': f'frames sharded over {world} GPU(s), no data-path collective',
                        'l2': f'inputs larger than L2: {NB} rotating device batches of {B} frames ({NB * B * W * H / 1e6:.0f} MB) + {B * 2.1:.0f} MB of pyramid/blur slabs per step'},
             'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                    'copy_ceiling': copy_ceiling, 'frac_of_copy_ceiling': e2e_fps / copy_fps if copy_fps > 0 else None,
                     'handles': NH, 'api': f'orbx_extract_batch (pinned host frames in, keypoints + descriptors out), {NH} extractor instances on '
                                           f'{NH} host threads per GPU, one {B}-frame batch per call; wall clock around the synchronous calls'},
             'gpu_launches': launches,
@@ -642,6 +845,7 @@ def run_b200(args, rank, world, local_rank, emit):
             'roofline': roofline,
             'cpu_baseline': cpu,
             'knn': knn,
+            'configs': configs,
             'stereo': stereo,
             'guided': guided,
             'remap': remap,
@@ -664,6 +868,7 @@ def main():
     ap.add_argument('--knn-train-per-gpu', type=int, default=1250000)
     ap.add_argument('--skip-knn', action='store_true')
     ap.add_argument('--skip-stereo', action='store_true')
+    ap.add_argument('--skip-configs', action='store_true', help='skip the C3 / C4 blocks')
     ap.add_argument('--stereo-pairs', type=int, default=64)
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-guided', action='store_true')

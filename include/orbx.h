@@ -133,6 +133,10 @@ orbx_status orbx_pyramid_level_device(orbx_handle h, int frame, int level, const
 orbx_status orbx_debug_candidates(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n);
 orbx_status orbx_debug_selected(orbx_handle h, int frame, int level, int32_t* xyr, int cap, int* n);
 orbx_status orbx_debug_blurred_level(orbx_handle h, int frame, int level, uint8_t* dst, size_t dst_pitch);
+/* The rotation terms of ComputeOrbDescriptor — src/ORBextractor.cc:105-107: (float)cos / (float)sin of angle * factorPI — as the
+ * descriptor kernel forms them, for the n float angles (degrees) whose bit patterns are first_bits, first_bits + 1, ...; host buffers.
+ * Exists so that a test can compare EVERY float angle in [0, 360) with the host's libm. */
+orbx_status orbx_debug_cos_sin(int device, uint32_t first_bits, int64_t n, float* cos_out, float* sin_out);
 
 /* ---- Matching (include/ORBmatcher.h, src/ORBmatcher.cc) ---- */
 
@@ -175,6 +179,16 @@ orbx_status orbx_knn2_partial_device(const uint8_t* d_query, int64_t nq, const u
                                      int64_t index_base, uint64_t* d_partial, void* stream);
 orbx_status orbx_knn2_merge_device(const uint64_t* d_gathered, int ranks, int64_t nq, int th_low, float nnratio,
                                    int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match, void* stream);
+/* The three steps in one call for a C/C++ host that owns an NCCL communicator: scan this rank's shard, ncclAllGather the
+ * 8-byte-per-query partials of all `nranks` ranks over `comm` (an ncclComm_t, passed as void*), merge. Everything is enqueued on `stream`
+ * (a cudaStream_t as void*); results are identical on every rank and equal one ascending scan over the whole train set. The library does
+ * not link NCCL: ncclAllGather is resolved at the first call from the NCCL already loaded in the process (the one `comm` was created with),
+ * else from libnccl.so.2; ORBX_ERR_STATE when neither exists. d_work: device scratch of (nranks + orbx_knn2_work_parts(nq, nt_shard)) * nq
+ * uint64, or NULL to let the call allocate and free it stream-ordered. */
+orbx_status orbx_knn2_sharded(void* comm, int rank, int nranks, const uint8_t* d_query, int64_t nq, const uint8_t* d_train_shard,
+                              int64_t nt_shard, int64_t index_base, int th_low, float nnratio, int32_t* d_idx, uint16_t* d_best,
+                              uint16_t* d_second, int32_t* d_match, uint64_t* d_work, void* stream);
+int orbx_knn2_work_parts(int64_t nq, int64_t nt_shard);
 
 /* ---- rows "next" of the hot path: the steps either side of Extract and the N x N Hamming site ---- */
 

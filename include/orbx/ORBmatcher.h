@@ -11,6 +11,7 @@
 
 #include <cstdint>
 #include <string>
+#include <cstring>
 #include <vector>
 
 #include <opencv2/core.hpp>
@@ -81,7 +82,32 @@ inline void ComputeStereoMatches(const ORBextractor& extractorL, const ORBextrac
 	depth.assign(d.begin(), d.begin() + nkeypointsL);
 }
 
-// ORBmatcher::DescriptorDistance: 1 x 32 CV_8U row headers
+// The N x N Hamming site of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:286-314) for MANY map points in one call: sets[p] are
+// the observation descriptors of map point p (1 x 32 CV_8U rows); the result is, per map point, the index of the descriptor with the least
+// median distance to the others (first on ties, as the reference's strict `<`), -1 for an empty set. This — not a DescriptorDistance call
+// per pair, which would be a GPU round trip per pair — is what replaces the loop at :289-299.
+inline std::vector<int32_t> ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat>>& sets, int device = 0)
+{
+	std::vector<int64_t> offsets(sets.size() + 1, 0);
+	for (size_t p = 0; p < sets.size(); p++) offsets[p + 1] = offsets[p] + static_cast<int64_t>(sets[p].size());
+	std::vector<uint8_t> rows(static_cast<size_t>(offsets.back()) * 32 + 32);
+	for (size_t p = 0; p < sets.size(); p++)
+		for (size_t i = 0; i < sets[p].size(); i++)
+			std::memcpy(rows.data() + (static_cast<size_t>(offsets[p]) + i) * 32, sets[p][i].data, 32);
+	std::vector<int32_t> best(sets.size(), -1);
+	if (!sets.empty())
+		Check(orbx_distinctive_descriptors(device, rows.data(), offsets.data(), static_cast<int>(sets.size()), best.data()), "ComputeDistinctiveDescriptors");
+	return best;
+}
+// one map point: the reference's own shape (descriptors of its observations in, index of the representative out)
+inline size_t ComputeDistinctiveDescriptors(const std::vector<cv::Mat>& descriptors, int device = 0)
+{
+	const std::vector<int32_t> best = ComputeDistinctiveDescriptors(std::vector<std::vector<cv::Mat>>(1, descriptors), device);
+	return best[0] < 0 ? 0 : static_cast<size_t>(best[0]);
+}
+
+// ORBmatcher::DescriptorDistance: 1 x 32 CV_8U row headers. One pair per call costs a host-device round trip; loops over pairs
+// (MapPoint::ComputeDistinctiveDescriptors, :289-299) use the batched forms above / orbx_descriptor_distance with n pairs.
 inline int DescriptorDistance(const cv::Mat& a, const cv::Mat& b, int device = 0)
 {
 	int32_t dist = 0;

@@ -101,6 +101,7 @@ class Oracle:
                                       C.c_void_p, C.c_void_p])
         f('knn2', None, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_void_p, C.c_int])
+        f('cos_sin_range', None, [C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int])
         f('convert_to_gray', None, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t])
         f('stereo_from_rgbd', None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(Camera), C.c_void_p, C.c_void_p])
         f('distinctive_index', C.c_int, [C.c_void_p, C.c_int])
@@ -492,6 +493,12 @@ class Oracle:
         rc = self._stereo_matches(_p(kpL), len(kpL), _p(descL), pl, _p(kpR), len(kpR), _p(descR), pr, _p(lw), _p(lh), _p(lp), n,
                                   _p(scale), _p(inv_scale), C.byref(c), _p(ur), _p(dp))
         return rc, ur, dp
+
+    def cos_sin_range(self, first_bits, n, threads=1):
+        """(cos, sin) float32 arrays for the n float angles (degrees) whose bit patterns start at first_bits (src/ORBextractor.cc:105-107)."""
+        c = np.empty(n, np.float32); s = np.empty(n, np.float32)
+        self._cos_sin_range(first_bits, n, _p(c), _p(s), threads)
+        return c, s
 
     def knn2(self, query, train, th_low=50, nnratio=0.6, threads=1):
         query = np.ascontiguousarray(query, np.uint8); train = np.ascontiguousarray(train, np.uint8)

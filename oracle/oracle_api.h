@@ -84,6 +84,10 @@ int ORACLE_FN(stereo_matches)(const oracle_keypoint* kpL, int nL, const uint8_t*
 void ORACLE_FN(knn2)(const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int th_low, float nnratio,
                      int32_t* idx, uint16_t* best, uint16_t* second, int32_t* match, int threads);
 
+// (float)cos / (float)sin of angle * factorPI exactly as ComputeOrbDescriptor forms them (src/ORBextractor.cc:105-107), for the n float angles with
+// bit patterns first_bits, first_bits + 1, ... — the host side of the exhaustive device-vs-glibc sweep
+void ORACLE_FN(cos_sin_range)(uint32_t first_bits, int64_t n, float* c, float* s, int threads);
+
 // ---- rows "next" of SURVEY §8(f) ----
 // ConvertToGray (src/System.cc:122-137): channels 3 or 4, rgb != 0 when the first channel is R
 void ORACLE_FN(convert_to_gray)(const uint8_t* src, int w, int h, size_t pitch, int channels, int rgb, uint8_t* dst, size_t dst_pitch);

@@ -612,6 +612,28 @@ void orc_knn2(const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt
 	for (auto& t : pool) t.join();
 }
 
+// the rotation terms of ComputeOrbDescriptor (src/ORBextractor.cc:105-107) for the n float angles whose bit patterns are first_bits,
+// first_bits + 1, ...: factorPI = (float)(CV_PI / 180.f); float angle = kpt.angle * factorPI; a = (float)cos(angle), b = (float)sin(angle)
+// (the double overloads, glibc). Lets a test sweep EVERY float angle in [0, 360) against the device.
+void orc_cos_sin_range(uint32_t first_bits, int64_t n, float* c, float* s, int threads)
+{
+	auto work = [&](int64_t i0, int64_t i1) {
+		const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+		for (int64_t i = i0; i < i1; i++)
+		{
+			const uint32_t bits = first_bits + (uint32_t)i;
+			float kp_angle;
+			std::memcpy(&kp_angle, &bits, 4);
+			float angle = (float)kp_angle * factorPI;
+			c[i] = (float)cos(angle); s[i] = (float)sin(angle);
+		}
+	};
+	if (threads <= 1) { work(0, n); return; }
+	std::vector<std::thread> pool;
+	for (int t = 0; t < threads; t++) pool.emplace_back(work, n * t / threads, n * (t + 1) / threads);
+	for (auto& t : pool) t.join();
+}
+
 // ---- rows "next" of SURVEY §8(f) ----
 // ConvertToGray (src/System.cc:122-137) = cv::cvtColor with the code picked from (channels, RGB flag)
 void orc_convert_to_gray(const uint8_t* src, int w, int h, size_t pitch, int channels, int rgb, uint8_t* dst, size_t dst_pitch)

@@ -90,6 +90,7 @@ _SIGNATURES = {
                                      C.c_int, C.c_void_p]),
     'orbx_extract_batch_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_void_p]),
+    'orbx_debug_cos_sin': (C.c_int, [C.c_int, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     'orbx_max_keypoints': (C.c_int, [C.c_void_p]),
     'orbx_plan': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'orbx_last_result_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -116,6 +117,9 @@ _SIGNATURES = {
     'orbx_knn2_partial_device': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     'orbx_knn2_merge_device': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    'orbx_knn2_sharded': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'orbx_knn2_work_parts': (C.c_int, [C.c_int64, C.c_int64]),
     'orbx_convert_to_gray': (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     'orbx_extract_batch_color': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -3,6 +3,8 @@
 // No CPU compute path exists: without a usable sm_100 device every entry point fails with ORBX_ERR_CUDA.
 #include "orbx_internal.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -990,6 +992,62 @@ orbx_status orbx_knn2_merge_device(const uint64_t* d_gathered, int ranks, int64_
 	return ORBX_OK;
 }
 
+int orbx_knn2_work_parts(int64_t nq, int64_t nt_shard) { return orbx_knn2_splits(nq, nt_shard) > 1 ? orbx_knn2_splits(nq, nt_shard) + 1 : 1; }
+
+// ncclAllGather(sendbuff, recvbuff, sendcount, datatype, comm, stream); ncclUint64 = 5 in every NCCL 2.x (nccl.h: ncclInt8 0, ncclUint8 1,
+// ncclInt32 2, ncclUint32 3, ncclInt64 4, ncclUint64 5). The library itself does not link NCCL.
+typedef int (*orbx_nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+static orbx_nccl_allgather_fn resolve_nccl_allgather()
+{
+	static orbx_nccl_allgather_fn fn = []() -> orbx_nccl_allgather_fn {
+		void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");        // the NCCL the caller's communicator came from
+		if (!sym)
+			for (const char* name : { "libnccl.so.2", "libnccl.so" })
+				if (void* lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) { sym = dlsym(lib, "ncclAllGather"); if (sym) break; }
+		return reinterpret_cast<orbx_nccl_allgather_fn>(sym);
+	}();
+	return fn;
+}
+
+orbx_status orbx_knn2_sharded(void* comm, int rank, int nranks, const uint8_t* d_query, int64_t nq, const uint8_t* d_train_shard,
+                              int64_t nt_shard, int64_t index_base, int th_low, float nnratio, int32_t* d_idx, uint16_t* d_best,
+                              uint16_t* d_second, int32_t* d_match, uint64_t* d_work, void* stream)
+{
+	if (!d_query || !d_train_shard || nq < 1 || nt_shard < 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ORBX_ERR_INVALID, "bad argument");
+	if (nranks > 1 && !comm) return fail(ORBX_ERR_INVALID, "an NCCL communicator is required for more than one rank");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int parts = orbx_knn2_work_parts(nq, nt_shard);
+	uint64_t* work = d_work;
+	if (!work) CU(cudaMallocAsync(&work, sizeof(uint64_t) * (size_t)(nranks + parts) * nq, st));
+	uint64_t* gathered = work;                                   // [nranks][nq]
+	uint64_t* mine = work + (size_t)nranks * nq;                 // this rank's partial (and its split scratch behind it)
+	orbx_status rc = ORBX_OK;
+	if (parts == 1)
+		orbx_launch_knn2_partial(d_query, nq, d_train_shard, nt_shard, index_base, mine, st);
+	else
+	{
+		orbx_launch_knn2_partial(d_query, nq, d_train_shard, nt_shard, index_base, mine + nq, st);
+		orbx_launch_knn2_fold(mine + nq, parts - 1, nq, mine, st);
+	}
+	if (nranks == 1)
+		orbx_launch_knn2_merge(mine, 1, nq, th_low, nnratio, d_idx, d_best, d_second, d_match, st);
+	else
+	{
+		orbx_nccl_allgather_fn allgather = resolve_nccl_allgather();
+		if (!allgather) rc = fail(ORBX_ERR_STATE, "ncclAllGather not found: no NCCL is loaded in this process and libnccl.so.2 cannot be opened");
+		else
+		{
+			const int r = allgather(mine, gathered, (size_t)nq, 5 /* ncclUint64 */, comm, st);
+			if (r != 0) rc = fail(ORBX_ERR_CUDA, "ncclAllGather failed with ncclResult_t " + std::to_string(r));
+			else orbx_launch_knn2_merge(gathered, nranks, nq, th_low, nnratio, d_idx, d_best, d_second, d_match, st);
+		}
+	}
+	if (!d_work) cudaFreeAsync(work, st);
+	if (rc != ORBX_OK) return rc;
+	CU(cudaGetLastError());
+	return ORBX_OK;
+}
+
 orbx_status orbx_knn2_device(const uint8_t* d_query, int64_t nq, const uint8_t* d_train, int64_t nt, int th_low,
                              float nnratio, int32_t* d_idx, uint16_t* d_best, uint16_t* d_second, int32_t* d_match,
                              void* stream)
@@ -1302,6 +1360,22 @@ orbx_status orbx_distinctive_descriptors(int device, const uint8_t* desc, const 
 	orbx_launch_distinctive(dd.p, dof.p, nsets, db.p, 0);
 	CU(cudaGetLastError());
 	CU(cudaMemcpy(best, db.p, sizeof(int32_t) * nsets, cudaMemcpyDeviceToHost));
+	return ORBX_OK;
+}
+
+orbx_status orbx_debug_cos_sin(int device, uint32_t first_bits, int64_t n, float* cos_out, float* sin_out)
+{
+	if (!cos_out || !sin_out || n < 0) return fail(ORBX_ERR_INVALID, "bad argument");
+	std::string why;
+	if (!device_ok(device, why)) return fail(ORBX_ERR_CUDA, why);
+	if (n == 0) return ORBX_OK;
+	CU(cudaSetDevice(device));
+	DevBuf<float> dc, ds;
+	CU(dc.ensure((size_t)n)); CU(ds.ensure((size_t)n));
+	orbx_launch_debug_cos_sin(first_bits, n, dc.p, ds.p, 0);
+	CU(cudaGetLastError());
+	CU(cudaMemcpy(cos_out, dc.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(sin_out, ds.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
 	return ORBX_OK;
 }
 

@@ -162,9 +162,7 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 	if (lane < nk)
 	{
 		angle = fast_atan2_deg((float)my01, (float)my10);
-		const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
-		const float arad = __fmul_rn(angle, factorPI);
-		ca = __double2float_rn(cos((double)arad)); sb = __double2float_rn(sin((double)arad));
+		orb_cos_sin(angle, ca, sb);
 	}
 
 	// ---- phase 3: steered BRIEF (:103-140): lane = descriptor byte, 8 pairs each, samples from the staged patch

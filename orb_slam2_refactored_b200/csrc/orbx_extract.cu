@@ -700,6 +700,24 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 	return a;
 }
 
+// The rotation terms of ComputeOrbDescriptor (src/ORBextractor.cc:105-107): angle * factorPI in float, then the DOUBLE cos / sin rounded to
+// float. tests/test_gpu_cos_sin_sweep.py evaluates this for every float angle in [0, 360) against glibc on the host.
+__device__ __forceinline__ void orb_cos_sin(float angle_deg, float& a, float& b)
+{
+	const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
+	const float arad = __fmul_rn(angle_deg, factorPI);
+	a = __double2float_rn(cos((double)arad));
+	b = __double2float_rn(sin((double)arad));
+}
+__global__ void __launch_bounds__(256) k_debug_cos_sin(uint32_t first_bits, int64_t n, float* __restrict__ c, float* __restrict__ s)
+{
+	const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	float a, b;
+	orb_cos_sin(__uint_as_float(first_bits + (uint32_t)i), a, b);
+	c[i] = a; s[i] = b;
+}
+
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c)
 {
 	int d;
@@ -804,9 +822,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_describe(const OrbxPla
 	const float angle = fast_atan2_deg((float)m01, (float)m10);
 
 	// ---- steered BRIEF (ComputeOrbDescriptor, :103-140): lane = descriptor byte, 8 pairs each, samples from the staged patch
-	const float factorPI = (float)(3.1415926535897932384626433832795 / (double)180.f);
-	const float arad = __fmul_rn(angle, factorPI);
-	const float ca = __double2float_rn(cos((double)arad)), sb = __double2float_rn(sin((double)arad));
+	float ca, sb;
+	orb_cos_sin(angle, ca, sb);
 	const uint8_t* bl = pblr + 18 * OD_PS + (x - xb);
 	uint32_t byte = 0;
 #pragma unroll
@@ -884,6 +901,11 @@ cudaError_t orbx_upload_pattern()
 	if ((e = cudaMemcpyToSymbol(g_patf, patf, sizeof(patf))) != cudaSuccess) return e;
 	if ((e = cudaMemcpyToSymbol(g_mom, mom, sizeof(mom))) != cudaSuccess) return e;
 	return cudaSuccess;
+}
+
+void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st)
+{
+	k_debug_cos_sin<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first_bits, n, d_cos, d_sin);
 }
 
 void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int channels, int rgb, uint8_t* dst, int64_t dpitch, int64_t dstride,

@@ -108,6 +108,7 @@ void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStre
 void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st);   // fused strip pass + cells
 bool orbx_fused_blur_fast();      // ORBX_FUSE=1: the blur and the dense FAST bound run as one strip kernel
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
+void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap);
 int orbx_pyramid_tile_rows();
 int orbx_pyramid_max_src_rows();

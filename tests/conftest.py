@@ -35,6 +35,18 @@ def oracle_ref():
 
 
 @pytest.fixture(scope='session')
+def oracle_final():
+    """The strongest checker present for whole-pipeline outputs: the reference's own TUs (oracle/_ref) where the library exists
+    (it travels to the GPU box with the snapshot), else the restatement. port == ref is held by tests/test_oracle_vs_ref.py."""
+    from oracle import bindings
+    bindings.build()
+    try:
+        return bindings.Oracle('ref')
+    except (FileNotFoundError, OSError):
+        return bindings.Oracle('port')
+
+
+@pytest.fixture(scope='session')
 def orbx():
     """The product: liborbx_b200.so through its Python mirror. Fails loudly if the library is missing."""
     from orb_slam2_refactored_b200 import api

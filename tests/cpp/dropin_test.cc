@@ -59,10 +59,36 @@ int main(int argc, char** argv)
 		orc_knn2(dl.data, n, dr.data, dr.rows, 50, 0.8f, idx.data(), best.data(), second.data(), match.data(), 4);
 		if (idx != r.idx || best != r.best || second != r.second || match != r.match) { printf("knn2 differs\n"); return 1; }
 
-		// error behaviour: too small an image is refused with an exception, not a crash
+		// MapPoint::ComputeDistinctiveDescriptors: observation sets of 1..9 descriptors cut from the extracted rows, one call for all sets
+		{
+			std::vector<std::vector<cv::Mat>> sets;
+			for (int p = 0, at = 0; at + 9 < n && p < 40; p++) { std::vector<cv::Mat> s; for (int i = 0; i < 1 + p % 9; i++) s.push_back(dl.row(at++)); sets.push_back(s); }
+			const std::vector<int32_t> best = ORB_SLAM2::b200::ComputeDistinctiveDescriptors(sets);
+			for (size_t p = 0; p < sets.size(); p++)
+			{
+				std::vector<uint8_t> rows(sets[p].size() * 32);
+				for (size_t i = 0; i < sets[p].size(); i++) memcpy(rows.data() + 32 * i, sets[p][i].data, 32);
+				if (best[p] != orc_distinctive_index(rows.data(), (int)sets[p].size())) { printf("distinctive descriptor of set %d differs\n", (int)p); return 1; }
+			}
+			if (ORB_SLAM2::b200::ComputeDistinctiveDescriptors(sets[8]) != (size_t)best[8]) { printf("single-set form differs\n"); return 1; }
+		}
+
+		// the cv::ORB-style call operator of upstream ORB_SLAM2 (mask ignored)
+		{
+			ORB_SLAM2::KeyPoints k2; cv::Mat d2m;
+			exL(left, cv::Mat(), k2, d2m);
+			if ((int)k2.size() != n || memcmp(d2m.data, od.data(), 32 * (size_t)n) != 0) { printf("operator() differs from Extract\n"); return 1; }
+		}
+
+		// error behaviour: too small an image is refused with an exception, not a crash; the handle survives it (plan cache)
 		bool threw = false;
-		try { cv::Mat tiny(90, 120, CV_8U); tiny.setTo(0); exL.Extract(tiny, kl, dl); } catch (const cv::Exception&) { threw = true; }
+		try { cv::Mat tiny(90, 120, CV_8U); tiny.setTo(0); ORB_SLAM2::KeyPoints kt; cv::Mat dt; exL.Extract(tiny, kt, dt); } catch (const cv::Exception&) { threw = true; }
 		if (!threw) { printf("no exception for undersized image\n"); return 1; }
+		{
+			ORB_SLAM2::KeyPoints k3; cv::Mat d3;
+			exL.Extract(left, k3, d3);
+			if ((int)k3.size() != n || memcmp(d3.data, od.data(), 32 * (size_t)n) != 0) { printf("extract after a refused size differs\n"); return 1; }
+		}
 		printf("OK %d keypoints, %d stereo matches\n", n, matched);
 		return 0;
 	}

@@ -10,6 +10,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, 'tests', 'cpp', '_build', 'dropin_test')
 EXE_GUIDED = os.path.join(ROOT, 'tests', 'cpp', '_build', 'guided_dropin_test')
 EXE_MAPPING = os.path.join(ROOT, 'tests', 'cpp', '_build', 'mapping_dropin_test')
+EXE_KNN = os.path.join(ROOT, 'tests', 'cpp', '_build', 'knn_sharded_test')
+
+
+def build_knn_exe():
+    """tests/cpp/knn_sharded_test.cc: a C++ host with its own NCCL communicator (system libnccl) calling orbx_knn2_sharded."""
+    from orb_slam2_refactored_b200 import build
+    lib = build.build()
+    src = os.path.join(ROOT, 'tests', 'cpp', 'knn_sharded_test.cc')
+    os.makedirs(os.path.dirname(EXE_KNN), exist_ok=True)
+    if os.path.exists(EXE_KNN) and os.path.getmtime(EXE_KNN) > max(os.path.getmtime(src), os.path.getmtime(lib)):
+        return True
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    if not os.path.exists('/usr/include/nccl.h'):
+        return False
+    cmd = ['g++', '-std=c++14', '-O1', '-Wall', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(cuda, 'include'), src, '-o', EXE_KNN,
+           '-L', os.path.dirname(lib), '-lorbx_b200', '-L', os.path.join(cuda, 'lib64'), '-lcudart', '-lnccl', '-lpthread',
+           '-Wl,-rpath,' + os.path.dirname(lib), '-Wl,-rpath,' + os.path.join(cuda, 'lib64')]
+    subprocess.run(cmd, check=True)
+    return True
 
 
 def build_exe():
@@ -65,3 +84,20 @@ def test_mapping_dropin_matches_oracle():
     r = subprocess.run([EXE_MAPPING, voc_path], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     assert r.stdout.decode().startswith('OK')
+
+
+def test_knn_sharded_host_compiles_and_links():
+    if not build_knn_exe():
+        pytest.skip('no NCCL header on this machine')
+    assert os.path.exists(EXE_KNN)
+
+
+@pytest.mark.gpu
+def test_knn_sharded_c_abi_matches_single_scan():
+    """orbx_knn2_sharded from a C++ host: with two or more GPUs two ranks all-gather over NCCL, with one GPU the single-rank path runs;
+    either way every rank's result equals the single-GPU scan of the whole train set (planted matches, cross-shard duplicates)."""
+    if not build_knn_exe():
+        pytest.skip('no NCCL header on this machine')
+    r = subprocess.run([EXE_KNN], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert r.stdout.decode().startswith('OK'), r.stdout.decode()

@@ -72,7 +72,7 @@ def test_batch_equals_single_and_ref(orbx, oracle_port, oracle_ref):
     assert k1.tobytes() == kb[4].tobytes() and np.array_equal(d1, db[4])
 
 
-def test_device_resident_batch(orbx, oracle_port):
+def test_device_resident_batch(orbx, oracle_final):
     import torch
     c = synth.CONFIGS['C1']
     imgs = np.stack([synth.image(s + 10, c['w'], c['h']) for s in range(4)])
@@ -83,7 +83,7 @@ def test_device_resident_batch(orbx, oracle_port):
     n = n.cpu().numpy()
     kps = kps.cpu().numpy().view(np.uint8).reshape(len(imgs), -1, 28)
     desc = desc.cpu().numpy()
-    e = oracle_port.extractor(c['nfeatures'])
+    e = oracle_final.extractor(c['nfeatures'])
     for f in range(len(imgs)):
         okps, odesc = e.extract(imgs[f])
         assert n[f] == len(okps)
@@ -91,7 +91,7 @@ def test_device_resident_batch(orbx, oracle_port):
         assert np.array_equal(desc[f, :n[f]], odesc)
 
 
-def test_strided_and_misaligned_input(orbx, oracle_port):
+def test_strided_and_misaligned_input(orbx, oracle_final):
     # a sub-matrix view (row stride != width, base not 16-byte aligned), as cv::Mat ROIs are
     c = synth.CONFIGS['C1']
     big = synth.image(5, c['w'] + 13, c['h'] + 4)
@@ -102,7 +102,7 @@ def test_strided_and_misaligned_input(orbx, oracle_port):
     cap = ex.max_keypoints()
     kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int()
     _check(lib().orbx_extract(ex._h, C.c_void_p(view.ctypes.data), c['w'], c['h'], view.strides[0], _p(kps), _p(desc), cap, C.byref(n)))
-    okps, odesc = oracle_port.extractor(500).extract(np.ascontiguousarray(view))
+    okps, odesc = oracle_final.extractor(500).extract(np.ascontiguousarray(view))
     assert n.value == len(okps) and kps[:n.value].tobytes() == okps.tobytes() and np.array_equal(desc[:n.value], odesc)
 
 
@@ -113,14 +113,64 @@ def test_flat_image_yields_nothing(orbx):
     assert len(k) == 0 and len(d) == 0
 
 
-def test_tie_blocks_image(orbx, oracle_port):
+def test_tie_blocks_image(orbx, oracle_final):
     # flat 8x8 blocks: adjacent equal scores suppress each other under strict NMS, so cells retry at minTh (App. A.4)
     r = np.random.RandomState(3)
     img = np.kron(r.randint(0, 256, (60, 80)), np.ones((8, 8))).astype(np.uint8)
     ex = orbx.ORBextractor(nfeatures=1000)
     k, d = ex.Extract(img)
-    ok, od = oracle_port.extractor(1000).extract(img)
+    ok, od = oracle_final.extractor(1000).extract(img)
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+
+
+def test_handle_survives_a_refused_size(orbx, oracle_final):
+    # good extract, then a size the plan builder refuses, then the first size again on the SAME handle: the size cache must not
+    # match a plan that the failed rebuild zeroed (illegal address and a sticky context error before the fix)
+    c = synth.CONFIGS['C1']
+    img = synth.image(21, c['w'], c['h'])
+    ex = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    k0, d0 = ex.Extract(img)
+    with pytest.raises(orbx.OrbxError) as e:
+        ex.Extract(np.zeros((100, 100), np.uint8))
+    assert e.value.status == orbx.ORBX_ERR_INVALID
+    k1, d1 = ex.Extract(img)
+    ok, od = oracle_final.extractor(c['nfeatures']).extract(img)
+    assert k0.tobytes() == ok.tobytes() and k1.tobytes() == ok.tobytes() and np.array_equal(d0, od) and np.array_equal(d1, od)
+    # and a different valid size right after the failure
+    img2 = synth.image(22, 752, 480)
+    with pytest.raises(orbx.OrbxError):
+        ex.Extract(np.zeros((640, 300), np.uint8))
+    k2, d2 = ex.Extract(img2)
+    ok2, od2 = oracle_final.extractor(c['nfeatures']).extract(img2)
+    assert k2.tobytes() == ok2.tobytes() and np.array_equal(d2, od2)
+
+
+def test_stereo_result_buffers_follow_the_last_extract(orbx):
+    # orbx_stereo_match writes last_frames x last_cap floats: the mirror sizes its arrays from orbx_last_result_shape, whatever cap the
+    # device-resident extract was given (a cap above max_keypoints() overran the host arrays)
+    import torch
+    c = synth.CONFIGS['C3']
+    L, R = synth.stereo_pair(31, c['w'], c['h'])
+    eL = orbx.ORBextractor(nfeatures=c['nfeatures']); eR = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    dL = torch.from_numpy(np.stack([L, L[::-1].copy()])).cuda(); dR = torch.from_numpy(np.stack([R, R[::-1].copy()])).cuda()
+    lib = orbx.lib()
+    import ctypes as C
+    orbx._check(lib.orbx_plan(eL._h, c['w'], c['h'], 2))
+    cap = eL.max_keypoints() + 37                     # a roomier layout than the plan's own
+    outs = []
+    for e, d in ((eL, dL), (eR, dR)):
+        k = torch.empty((2, cap, 7), dtype=torch.float32, device='cuda'); ds = torch.empty((2, cap, 32), dtype=torch.uint8, device='cuda')
+        n = torch.empty((2,), dtype=torch.int32, device='cuda')
+        e.extract_batch_device(d, k, ds, n)
+        outs.append((k, ds, n))
+    ur, dp = orbx.ComputeStereoMatchesResident(eL, eR, c['camera'])
+    assert ur.shape == (2, cap) and dp.shape == (2, cap)
+    # the same pair through the plan's own layout gives the same matches
+    kl, dl = eL.ExtractBatch(np.stack([L, L[::-1].copy()])); kr, dr = eR.ExtractBatch(np.stack([R, R[::-1].copy()]))
+    ur2, dp2 = orbx.ComputeStereoMatchesResident(eL, eR, c['camera'])
+    for f in range(2):
+        n = len(kl[f])
+        assert ur[f, :n].tobytes() == ur2[f, :n].tobytes() and dp[f, :n].tobytes() == dp2[f, :n].tobytes()
 
 
 def test_input_contract(orbx):
@@ -144,10 +194,10 @@ def test_getters_match_reference_tables(orbx, oracle_port):
     assert list(orbx.ORBextractor(nfeatures=8000).GetFeatureQuotas()) == [1737, 1448, 1207, 1005, 838, 698, 582, 485]
 
 
-def test_plan_rebuild_and_odd_batches(orbx, oracle_port):
+def test_plan_rebuild_and_odd_batches(orbx, oracle_final):
     # one handle, changing image sizes and batch sizes (plan rebuild, chunk pipeline with a ragged last chunk)
     ex = orbx.ORBextractor(nfeatures=700)
-    e = oracle_port.extractor(700)
+    e = oracle_final.extractor(700)
     for (w, h, frames) in ((640, 480, 3), (752, 480, 1), (640, 480, 70), (400, 300, 5), (640, 480, 2)):
         imgs = np.stack([synth.image(1000 + w + s, w, h) for s in range(min(frames, 6))])
         if frames > len(imgs):
@@ -162,7 +212,7 @@ def test_plan_rebuild_and_odd_batches(orbx, oracle_port):
             assert k[f].tobytes() == ref[key][0].tobytes() and np.array_equal(d[f], ref[key][1]), (w, h, frames, f)
 
 
-def test_two_extractors_on_two_threads(orbx, oracle_port):
+def test_two_extractors_on_two_threads(orbx, oracle_final):
     # src/System.cc:449-452 runs the left and right extractor on two std::threads
     import threading
     c = synth.CONFIGS['C3']
@@ -177,7 +227,7 @@ def test_two_extractors_on_two_threads(orbx, oracle_port):
     for t in th: t.start()
     for t in th: t.join()
     for i, img in enumerate((L, R)):
-        ok, od = oracle_port.extractor(c['nfeatures']).extract(img)
+        ok, od = oracle_final.extractor(c['nfeatures']).extract(img)
         assert out[i][0].tobytes() == ok.tobytes() and np.array_equal(out[i][1], od)
 
 
