@@ -116,8 +116,8 @@ struct orbx_extractor
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
 	OrbxTmaMaps maps;
-	OrbxStripMaps smaps;                // strip kernels (blur, dense FAST bound): every level with the strip box
-	OrbxPyrMaps pmaps;                  // strip resize kernel: level s - 1 with the source box of a tile of level s
+	OrbxStripMaps smaps[2];             // strip kernels (blur, dense FAST bound): every level with the strip box; [1]: the 8-row tiles of small batches
+	OrbxPyrMaps pmaps[2];               // strip resize kernel: level s - 1 with the source box of a tile of level s
 	DevBuf<uint8_t> fmap_ini, fmap_min; // FAST bound bitmaps (1 bit per level pixel each)
 	DevBuf<uint8_t> color;              // interleaved colour frames / unrectified frames of the current batch (orbx_extract_batch_color / _rectified)
 	DevBuf<int2> rect_tab;              // rectification table (orbx_set_rectification): per output pixel (ix | iy << 16, fx | fy << 5)
@@ -306,8 +306,9 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			L.py_smem = max_rows * max_bytes;
 			// strip resize kernel (one warp per 128 x TH tile, source rectangle by one TMA box): box rows/bytes over all tiles. A lane reads
 			// three aligned words from its first source column on and picks its four (s[x], s[x+1]) pairs out of 8 bytes.
+			for (int which = 0; which < 2; which++)
 			{
-				const int sth = orbx_pyramid_strip_rows();
+				const int sth = orbx_pyramid_strip_rows(which);
 				int brows = 0, bbytes = 0, emax = 0;
 				for (int y0 = 0; y0 < L.h; y0 += sth)
 				{
@@ -325,8 +326,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 					}
 				}
 				bbytes = (int)align_up(bbytes, 16);
-				if (emax <= 6 && bbytes <= 256 && brows <= 256 && bbytes * brows <= 96 * 1024) { L.py_bw = bbytes; L.py_bh = brows; }
-				else { L.py_bw = 0; L.py_bh = 0; }      // scale factor too large for one TMA box: the cp.async kernel produces this level
+				if (emax <= 6 && bbytes <= 256 && brows <= 256 && bbytes * brows <= 96 * 1024) { L.py_bw[which] = bbytes; L.py_bh[which] = brows; }
+				else { L.py_bw[which] = 0; L.py_bh[which] = 0; }      // scale factor too large for one TMA box: the cp.async kernel produces this level
 			}
 		}
 	}
@@ -382,8 +383,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
 		if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
 		std::memset(&h->maps, 0, sizeof(h->maps));
-		std::memset(&h->smaps, 0, sizeof(h->smaps));
-		std::memset(&h->pmaps, 0, sizeof(h->pmaps));
+		std::memset(h->smaps, 0, sizeof(h->smaps));
+		std::memset(h->pmaps, 0, sizeof(h->pmaps));
 		for (int s = 0; s < nl; s++)
 		{
 			const OrbxLevel& L = P.lv[s];
@@ -400,20 +401,23 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 			                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			if (r != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-			// the same tensor with the strip box (blur, dense FAST bound) ...
-			const cuuint32_t sbox[3] = { (cuuint32_t)orbx_strip_box_w(), (cuuint32_t)orbx_strip_box_h(), 1 };
-			const CUresult r2 = ((EncodeFn)fn)(&h->smaps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, sbox, estr,
-			                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-			                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-			if (r2 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (strip box) failed with CUresult " + std::to_string((int)r2));
-			// ... and, as the SOURCE of level s + 1, with that level's resize box
-			if (s + 1 < nl && P.lv[s + 1].py_bw > 0)
+			for (int which = 0; which < 2; which++)
 			{
-				const cuuint32_t pbox[3] = { (cuuint32_t)P.lv[s + 1].py_bw, (cuuint32_t)P.lv[s + 1].py_bh, 1 };
-				const CUresult r3 = ((EncodeFn)fn)(&h->pmaps.src[s + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, pbox, estr,
+				// the same tensor with the strip box (blur, dense FAST bound) ...
+				const cuuint32_t sbox[3] = { (cuuint32_t)orbx_strip_box_w(), (cuuint32_t)(orbx_strip_rows(which) + 6), 1 };
+				const CUresult r2 = ((EncodeFn)fn)(&h->smaps[which].level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, sbox, estr,
 				                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 				                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-				if (r3 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (resize box) failed with CUresult " + std::to_string((int)r3));
+				if (r2 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (strip box) failed with CUresult " + std::to_string((int)r2));
+				// ... and, as the SOURCE of level s + 1, with that level's resize box
+				if (s + 1 < nl && P.lv[s + 1].py_bw[which] > 0)
+				{
+					const cuuint32_t pbox[3] = { (cuuint32_t)P.lv[s + 1].py_bw[which], (cuuint32_t)P.lv[s + 1].py_bh[which], 1 };
+					const CUresult r3 = ((EncodeFn)fn)(&h->pmaps[which].src[s + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, pbox, estr,
+					                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+					                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+					if (r3 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (resize box) failed with CUresult " + std::to_string((int)r3));
+				}
 			}
 		}
 	}

@@ -9,7 +9,6 @@
 //     lrint), so the quarter-rate conversion pipe is not used and the bias folds into the patch base address.
 // Float semantics as before: every reference float op is an explicit round-to-nearest intrinsic.
 // =====================================================================================================
-#define OD2_G 8                      // keypoints per warp
 #define OD2_IPS 48                   // un-blurred patch: 31 rows x 48 bytes from (x - 16) & ~15 (three 16-byte chunks: a copy instruction then spans ~11 rows,
                                      // 4-byte copies with one row per lane were measured 1.5x slower overall: 31 cache lines per instruction)
 #define OD2_IBUF (31 * OD2_IPS)      // 1488 bytes; a ring of four, so four keypoints' patches are in flight
@@ -33,12 +32,15 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// G = keypoints per warp: 8 for throughput; 2 when a frame at a time is extracted (the launch then has four times the warps and a
+// quarter of the serial chain per warp)
+template <int G>
 __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps, uint8_t* __restrict__ d_desc,
                                                         int32_t* __restrict__ d_n)
 {
 	extern __shared__ __align__(16) uint8_t od2_smem[];
 	const int lane = threadIdx.x, f = blockIdx.y;
-	const int slot0 = blockIdx.x * OD2_G;
+	const int slot0 = blockIdx.x * G;
 
 	// levels are concatenated in order (:792-819): lane l holds level l's count and the inclusive prefix
 	const int cnt = (lane < P.nlevels) ? P.sel_count[(int64_t)f * P.nlevels + lane] : 0;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 	}
 	const int total = __shfl_sync(0xffffffffu, incl, ORBX_MAX_LEVELS - 1);
 	if (slot0 == 0 && lane == 0) d_n[f] = total;
-	const int nk = min(min(total, P.out_cap) - slot0, OD2_G);
+	const int nk = min(min(total, P.out_cap) - slot0, G);
 	if (nk <= 0) return;
 
 	// lane k < nk owns keypoint slot0 + k: its level, position, and the origins of its two patches

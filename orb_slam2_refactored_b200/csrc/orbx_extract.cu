@@ -930,10 +930,17 @@ static int env_int(const char* name, int dflt)
 }
 static bool legacy_kernels() { static const bool v = env_int("ORBX_LEGACY", 0) != 0; return v; }     // A/B: the round-1 kernels
 bool orbx_fused_blur_fast() { static const bool v = env_int("ORBX_FUSE", 0) != 0 && !legacy_kernels(); return v; }
-int orbx_strip_rows() { static const int v = env_int("ORBX_STRIP_TH", 32) == 64 ? 64 : env_int("ORBX_STRIP_TH", 32) == 16 ? 16 : 32; return v; }
+int orbx_strip_rows(int which)
+{
+	static const int v = env_int("ORBX_STRIP_TH", 32) == 64 ? 64 : env_int("ORBX_STRIP_TH", 32) == 16 ? 16 : 32;
+	return which ? 8 : v;
+}
 int orbx_strip_box_w() { return ST_BW; }
-int orbx_strip_box_h() { return orbx_strip_rows() + 2 * ST_HALO; }
-int orbx_pyramid_strip_rows() { static const int v = env_int("ORBX_PYR_TH", 32) == 16 ? 16 : 32; return v; }
+int orbx_pyramid_strip_rows(int which)
+{
+	static const int v = env_int("ORBX_PYR_TH", 32) == 16 ? 16 : 32;
+	return which ? 8 : v;
+}
 
 #define QT_SMEM_MAX (200 * 1024)
 // Function attributes are per device and cost a driver call each: set once per orbx_create, not per launch.
@@ -947,31 +954,36 @@ cudaError_t orbx_kernels_init()
 	set(k_pyramid_resize<4>, PY_SRC * PY_SW);
 	set(k_pyramid_strip<32>, 100 * 1024);
 	set(k_pyramid_strip<16>, 100 * 1024);
+	set(k_pyramid_strip<8>, 100 * 1024);
 	set(k_fast_cells<1>, 64 * 1024);
 	set(k_fast_cells2, 64 * 1024);
+	set(k_level_strip<8, true, false>, 64 * 1024); set(k_level_strip<8, false, true>, 64 * 1024); set(k_level_strip<8, true, true>, 64 * 1024);
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024); set(k_level_strip<16, true, true>, 64 * 1024);
 	set(k_level_strip<32, true, false>, 64 * 1024); set(k_level_strip<32, false, true>, 64 * 1024); set(k_level_strip<32, true, true>, 64 * 1024);
 	set(k_level_strip<64, true, false>, 64 * 1024); set(k_level_strip<64, false, true>, 64 * 1024); set(k_level_strip<64, true, true>, 64 * 1024);
 	set(qt128::k_quadtree<false>, QT_SMEM_MAX); set(qt256::k_quadtree<false>, QT_SMEM_MAX);
 	set(qt256::k_quadtree<true>, QT_SMEM_MAX); set(qt512::k_quadtree<true>, QT_SMEM_MAX);
 	set(k_orient_describe, OD_SMEM);
+	set(k_orient_describe2<8>, OD2_SMEM); set(k_orient_describe2<2>, OD2_SMEM);
 	return e;
 }
 
-void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps& pmaps, int level, cudaStream_t st)
+void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st)
 {
 	const OrbxLevel& D = P.lv[level];
-	if (D.py_bw > 0 && !legacy_kernels())
+	const bool small_batch = P.frames <= ORBX_SMALL_BATCH;
+	const int which = small_batch ? 1 : 0;
+	if (D.py_bw[which] > 0 && !legacy_kernels())
 	{
 		// strip kernel: one warp per 128 x TH output tile, source rectangle by one TMA box
-		const int th = orbx_pyramid_strip_rows();
+		const int th = orbx_pyramid_strip_rows(which), bw = D.py_bw[which], bh = D.py_bh[which];
 		dim3 grid((D.w + ST_TW - 1) / ST_TW, (D.h + th - 1) / th, P.frames);
-		const int smem = ((D.py_bw * D.py_bh + 127) & ~127) + 16;
-		if (th == 16) k_pyramid_strip<16><<<grid, 32, smem, st>>>(P, pmaps, level);
-		else k_pyramid_strip<32><<<grid, 32, smem, st>>>(P, pmaps, level);
+		const int smem = ((bw * bh + 127) & ~127) + 16;
+		if (th == 8) k_pyramid_strip<8><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
+		else if (th == 16) k_pyramid_strip<16><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
+		else k_pyramid_strip<32><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
 		return;
 	}
-	const bool small_batch = P.frames <= 16;
 	const int th = small_batch ? 32 : PY_TH;
 	dim3 grid((D.w + PY_TW - 1) / PY_TW, (D.h + th - 1) / th, P.frames);
 	// dynamic shared memory: staged source rows; sized per level by the host (P.lv[level].py_smem), up to PY_SRC * PY_SW = 86 KB.
@@ -999,9 +1011,11 @@ static OrbxStripTiles strip_tiles(const OrbxPlanDev& P, int th)
 }
 
 // one launch over the tiles of all levels: blur (mode 1), dense FAST bound (mode 2) or both (mode 3)
-static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps& smaps, int mode, cudaStream_t st)
+static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps smaps_both[2], int mode, cudaStream_t st)
 {
-	const int th = orbx_strip_rows();
+	const int which = P.frames <= ORBX_SMALL_BATCH ? 1 : 0;
+	const OrbxStripMaps& smaps = smaps_both[which];
+	const int th = orbx_strip_rows(which);
 	const OrbxStripTiles T = strip_tiles(P, th);
 	dim3 grid(T.base[P.nlevels], P.frames);
 	const int smem = st_tile_bytes(th) + 16;
@@ -1009,7 +1023,8 @@ static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps& smaps, int m
 	if (mode == 1) k_level_strip<TH_, true, false><<<grid, 32, smem, st>>>(P, smaps, T);                           \
 	else if (mode == 2) k_level_strip<TH_, false, true><<<grid, 32, smem, st>>>(P, smaps, T);                      \
 	else k_level_strip<TH_, true, true><<<grid, 32, smem, st>>>(P, smaps, T);
-	if (th == 16) { ORBX_STRIP_CASE(16) }
+	if (th == 8) { ORBX_STRIP_CASE(8) }
+	else if (th == 16) { ORBX_STRIP_CASE(16) }
 	else if (th == 64) { ORBX_STRIP_CASE(64) }
 	else { ORBX_STRIP_CASE(32) }
 #undef ORBX_STRIP_CASE
@@ -1043,7 +1058,7 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st)
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st)
 {
 	if (!legacy_kernels())
 	{
@@ -1067,7 +1082,7 @@ void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxS
 	k_fast_cells<1><<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 
-void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st)
+void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st)
 {
 	launch_strip(P, smaps, 3, st);
 	launch_cells2(P, maps, st);
@@ -1139,7 +1154,7 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	}
 }
 
-void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStream_t st)
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st)
 {
 	if (!legacy_kernels())
 	{
@@ -1176,8 +1191,16 @@ void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d
 {
 	if (!legacy_kernels())
 	{
-		dim3 grid((P.out_cap + OD2_G - 1) / OD2_G, P.frames);
-		k_orient_describe2<<<grid, 32, OD2_SMEM, st>>>(P, d_kps, d_desc, d_n);
+		if (P.frames <= ORBX_SMALL_BATCH)
+		{
+			dim3 grid((P.out_cap + 1) / 2, P.frames);
+			k_orient_describe2<2><<<grid, 32, OD2_SMEM, st>>>(P, d_kps, d_desc, d_n);
+		}
+		else
+		{
+			dim3 grid((P.out_cap + 7) / 8, P.frames);
+			k_orient_describe2<8><<<grid, 32, OD2_SMEM, st>>>(P, d_kps, d_desc, d_n);
+		}
 		return;
 	}
 	dim3 grid((P.out_cap + OD_WARPS - 1) / OD_WARPS, P.frames);

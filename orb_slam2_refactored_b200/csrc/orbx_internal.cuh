@@ -40,7 +40,8 @@ struct OrbxLevel
 	int xtab_base, ytab_base;
 	float scale;                 // scaleFactors_[s]
 	int py_smem;                 // dynamic shared memory of the cp.async resize kernel producing this level
-	int py_bw, py_bh;            // TMA box (bytes x rows of level s - 1) of the strip resize kernel producing this level; 0: not usable
+	int py_bw[2], py_bh[2];      // TMA box (bytes x rows of level s - 1) of the strip resize kernel producing this level, [0] throughput tiles, [1] the
+	                             // 8-row tiles of small batches; 0: not usable (scale factor too large for one box)
 };
 
 struct OrbxPlanDev
@@ -90,10 +91,12 @@ int orbx_fast_tile_rows();
 // level s - 1 with the source box of the resize tile that produces level s
 struct OrbxStripMaps { CUtensorMap level[ORBX_MAX_LEVELS]; };
 struct OrbxPyrMaps { CUtensorMap src[ORBX_MAX_LEVELS]; };
-int orbx_strip_rows();            // tile rows of the blur / FAST-bound strip kernel (fixed per process: ORBX_STRIP_TH, default 32)
+// Tile rows of the strip kernels. which = 0: throughput tiles (ORBX_STRIP_TH / ORBX_PYR_TH, default 32); which = 1: the 8-row tiles used when
+// a launch covers at most ORBX_SMALL_BATCH frames (Tracking extracts one frame at a time: more, shorter warps cut the launch's latency)
+#define ORBX_SMALL_BATCH 16
+int orbx_strip_rows(int which);
 int orbx_strip_box_w();
-int orbx_strip_box_h();
-int orbx_pyramid_strip_rows();    // tile rows of the strip resize kernel
+int orbx_pyramid_strip_rows(int which);
 cudaError_t orbx_kernels_init();  // per-device function attributes (dynamic shared memory limits); called once per orbx_create
 
 // kernel launchers (orbx_extract.cu)
@@ -101,11 +104,11 @@ void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int c
                       int w, int h, int frames, cudaStream_t st);
 void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
-void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps& pmaps, int level, cudaStream_t st);
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st);
+void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
-void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps& smaps, cudaStream_t st);
-void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps& smaps, cudaStream_t st);   // fused strip pass + cells
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);
+void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);   // fused strip pass + cells
 bool orbx_fused_blur_fast();      // ORBX_FUSE=1: the blur and the dense FAST bound run as one strip kernel
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);

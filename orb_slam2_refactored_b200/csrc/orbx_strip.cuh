@@ -271,12 +271,11 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 // cp.async kernel (k_pyramid_resize) runs.
 // =====================================================================================================
 template <int TH>
-__global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const int level)
+__global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const int level, const int bw, const int bh)
 {
 	static_assert(TH <= 32, "lane k holds the table entry of tile row k");
 	extern __shared__ __align__(128) uint8_t py_smem[];
 	const OrbxLevel& D = P.lv[level];
-	const int bw = D.py_bw, bh = D.py_bh;
 	uint64_t* const bar = reinterpret_cast<uint64_t*>(py_smem + ((bw * bh + 127) & ~127));
 	const int lane = threadIdx.x, f = blockIdx.z;
 	const int sh = P.lv[level - 1].h;
