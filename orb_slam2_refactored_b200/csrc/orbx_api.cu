@@ -383,6 +383,12 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
 		if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
 		std::memset(&h->maps, 0, sizeof(h->maps));
+		int max_view_w = 0;
+		for (int s = 0; s < nl; s++)
+			for (int cx = 0, x0 = P.lv[s].minx; cx < P.lv[s].ncx; cx++, x0 += P.lv[s].cellw)
+				max_view_w = std::max(max_view_w, std::min(x0 + P.lv[s].cellw + 6, P.lv[s].maxx) - x0);
+		h->maps.tile_stride = orbx_fast_tile_stride(max_view_w);
+		if (max_view_w + 15 > h->maps.tile_stride) return fail(ORBX_ERR_INVALID, "cell wider than the FAST tile");
 		std::memset(h->smaps, 0, sizeof(h->smaps));
 		std::memset(h->pmaps, 0, sizeof(h->pmaps));
 		for (int s = 0; s < nl; s++)
@@ -395,7 +401,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			void* base = s == 0 ? (void*)h->l0base : (void*)(P.pyr + L.offset);
 			const cuuint64_t dims[3] = { (cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)frames };
 			const cuuint64_t strides[2] = { (cuuint64_t)L.pitch, (cuuint64_t)(s == 0 ? h->l0_stride : P.slab) };
-			const cuuint32_t box[3] = { (cuuint32_t)orbx_fast_tile_stride(), (cuuint32_t)box_h, 1 };
+			const cuuint32_t box[3] = { (cuuint32_t)h->maps.tile_stride, (cuuint32_t)box_h, 1 };
 			const cuuint32_t estr[3] = { 1, 1, 1 };
 			const CUresult r = ((EncodeFn)fn)(&h->maps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
 			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -461,22 +467,20 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	}
 	// The blur on a side stream beside the quadtree was measured: +1.2 % device-resident (178.3 k vs 176.1 k frames/s), -3 % end to end
 	// (147.6 k vs 151.9 k: two more streams per handle in the chunk pipeline), no change without the stage events. Default: in line.
-	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr || orbx_fused_blur_fast();
+	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr;
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
 	if (ev) CU(cudaEventRecord(ev[0], st));
 	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, h->pmaps, s, st);
 	if (ev) CU(cudaEventRecord(ev[1], st));
-	const bool fused = orbx_fused_blur_fast();      // blur + dense FAST bound as one strip kernel: the stage events then book it all under FAST
 	if (blur_inline)
 	{
 		if (ev) CU(cudaEventRecord(ev[6], st));
-		if (!fused) orbx_launch_blur(P, h->smaps, st);
+		orbx_launch_blur(P, h->smaps, st);
 		if (ev) CU(cudaEventRecord(ev[7], st));
 	}
 	if (ev) CU(cudaEventRecord(ev[2], st));
-	if (fused) orbx_launch_blur_fast(P, h->maps, h->smaps, st);
-	else orbx_launch_fast(P, h->maps, h->smaps, st);
+	orbx_launch_fast(P, h->maps, h->smaps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
 	if (!blur_inline)
 	{

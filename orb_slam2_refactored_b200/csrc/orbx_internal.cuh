@@ -84,8 +84,9 @@ struct OrbxTmaMaps
 {
 	CUtensorMap level[ORBX_MAX_LEVELS];
 	int box_h[ORBX_MAX_LEVELS];
+	int tile_stride;             // box width in bytes = row stride of the staged cell view (64 or 96)
 };
-int orbx_fast_tile_stride();
+int orbx_fast_tile_stride(int max_view_w);
 int orbx_fast_tile_rows();
 // TMA descriptors of the strip kernels: the levels as (pitch, h, frames) u8 tensors with the strip box (blur + dense FAST bound), and
 // level s - 1 with the source box of the resize tile that produces level s
@@ -108,8 +109,6 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int l
 void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);
-void orbx_launch_blur_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);   // fused strip pass + cells
-bool orbx_fused_blur_fast();      // ORBX_FUSE=1: the blur and the dense FAST bound run as one strip kernel
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap);

@@ -1,5 +1,5 @@
 """Device-resident extraction throughput and per-stage times for one BASELINE.json config (default C1, 512 frames).
-usage: stage_probe.py [C1|C2|C3|C4] [batch] — tuning knobs come from the environment (ORBX_LEGACY, ORBX_STRIP_TH, ORBX_FUSE, ORBX_PYR_TH)."""
+usage: stage_probe.py [C1|C2|C3|C4] [batch] — tuning knobs come from the environment (ORBX_STRIP_TH, ORBX_FUSE, ORBX_PYR_TH, ORBX_BLUR_SIDE, ORBX_LANES)."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
