@@ -467,7 +467,9 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	}
 	// The blur on a side stream beside the quadtree was measured: +1.2 % device-resident (178.3 k vs 176.1 k frames/s), -3 % end to end
 	// (147.6 k vs 151.9 k: two more streams per handle in the chunk pipeline), no change without the stage events. Default: in line.
-	static const bool blur_inline = getenv("ORBX_BLUR_SIDE") == nullptr;
+	// Small batches (a frame per call) are latency-bound: the blur then runs as a parallel branch beside FAST + quadtree.
+	static const bool blur_side_env = getenv("ORBX_BLUR_SIDE") != nullptr;
+	const bool blur_inline = !(blur_side_env || (fc <= ORBX_SMALL_BATCH && !h->stage_timing));
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
 	if (ev) CU(cudaEventRecord(ev[0], st));
@@ -479,13 +481,10 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 		orbx_launch_blur(P, h->smaps, st);
 		if (ev) CU(cudaEventRecord(ev[7], st));
 	}
-	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_fast(P, h->maps, h->smaps, st);
-	if (ev) CU(cudaEventRecord(ev[3], st));
-	if (!blur_inline)
+	else
 	{
-		// The blur only depends on the pyramid and only the descriptor stage reads it: it runs beside the quadtree, whose CTAs spend
-		// most of their time in serial phases and leave the SMs' issue slots half empty. (Beside FAST it would only share a busy SM.)
+		// The blur only depends on the pyramid and only the descriptor stage reads it: a parallel branch beside FAST + quadtree (the quadtree
+		// leaves most of the GPU idle on a small batch; in a captured graph this fork / join becomes two independent paths)
 		CU(cudaEventRecord(h->side_fork[lane], st));
 		CU(cudaStreamWaitEvent(side, h->side_fork[lane], 0));
 		if (ev) CU(cudaEventRecord(ev[6], side));
@@ -493,6 +492,9 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 		if (ev) CU(cudaEventRecord(ev[7], side));
 		CU(cudaEventRecord(h->side_join[lane], side));
 	}
+	if (ev) CU(cudaEventRecord(ev[2], st));
+	orbx_launch_fast(P, h->maps, h->smaps, st);
+	if (ev) CU(cudaEventRecord(ev[3], st));
 	if (ev) CU(cudaEventRecord(ev[4], st));
 	orbx_launch_quadtree(P, cell_off, st);
 	if (ev) CU(cudaEventRecord(ev[5], st));
@@ -824,6 +826,8 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 			                 h->l0_pitch, h->l0_stride, width, height, fc, st);
 		}
 		st = (ci & 1) ? h->stream2 : h->stream;
+		// (Replaying the ~12 launches of a one-frame call as a CUDA graph was measured: 0.212 vs 0.203 ms per call — the call is bound by the
+		// GPU's dependent chain (quadtree 54 us, 7 pyramid levels 33 us), not by launch overhead, which the host hides behind it.)
 		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
 		if (e != ORBX_OK) return e;
 		CU(cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st));
