@@ -387,8 +387,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 		for (int s = 0; s < nl; s++)
 			for (int cx = 0, x0 = P.lv[s].minx; cx < P.lv[s].ncx; cx++, x0 += P.lv[s].cellw)
 				max_view_w = std::max(max_view_w, std::min(x0 + P.lv[s].cellw + 6, P.lv[s].maxx) - x0);
-		h->maps.tile_stride = orbx_fast_tile_stride(max_view_w);
-		if (max_view_w + 15 > h->maps.tile_stride) return fail(ORBX_ERR_INVALID, "cell wider than the FAST tile");
+		if (max_view_w + 15 > orbx_fast_tile_stride()) return fail(ORBX_ERR_INVALID, "cell wider than the FAST tile");
 		std::memset(h->smaps, 0, sizeof(h->smaps));
 		std::memset(h->pmaps, 0, sizeof(h->pmaps));
 		for (int s = 0; s < nl; s++)
@@ -401,7 +400,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			void* base = s == 0 ? (void*)h->l0base : (void*)(P.pyr + L.offset);
 			const cuuint64_t dims[3] = { (cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)frames };
 			const cuuint64_t strides[2] = { (cuuint64_t)L.pitch, (cuuint64_t)(s == 0 ? h->l0_stride : P.slab) };
-			const cuuint32_t box[3] = { (cuuint32_t)h->maps.tile_stride, (cuuint32_t)box_h, 1 };
+			const cuuint32_t box[3] = { (cuuint32_t)orbx_fast_tile_stride(), (cuuint32_t)box_h, 1 };
 			const cuuint32_t estr[3] = { 1, 1, 1 };
 			const CUresult r = ((EncodeFn)fn)(&h->maps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
 			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

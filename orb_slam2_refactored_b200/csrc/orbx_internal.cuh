@@ -84,9 +84,8 @@ struct OrbxTmaMaps
 {
 	CUtensorMap level[ORBX_MAX_LEVELS];
 	int box_h[ORBX_MAX_LEVELS];
-	int tile_stride;             // box width in bytes = row stride of the staged cell view (64 or 96)
 };
-int orbx_fast_tile_stride(int max_view_w);
+int orbx_fast_tile_stride();
 int orbx_fast_tile_rows();
 // TMA descriptors of the strip kernels: the levels as (pitch, h, frames) u8 tensors with the strip box (blur + dense FAST bound), and
 // level s - 1 with the source box of the resize tile that produces level s

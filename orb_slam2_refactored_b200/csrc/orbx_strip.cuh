@@ -372,8 +372,6 @@ struct OrbxCellLayout
 	int warp_bytes;
 };
 
-// TS = tile row stride in bytes = TMA box width: 64 when every cell view (+ 15 bytes of alignment slack) fits, else 96
-template <int TS>
 __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
 {
 	extern __shared__ __align__(128) uint8_t fw_smem[];
@@ -394,7 +392,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	if (lane == 0)
 	{
 		mbar_init(tma_bar, 1);
-		mbar_expect_tx(tma_bar, (unsigned)(TS * maps.box_h[lvl]));
+		mbar_expect_tx(tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
 		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, tma_bar);
 	}
 	// the region's rows of the bound bitmaps: lane r holds rows r and r + 32 as 64-bit masks (bit i = region column i)
@@ -435,7 +433,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	mbar_wait(tma_bar, 0);
 
 	const int tmin = P.min_th, tini = P.ini_th;
-	const uint8_t* __restrict__ t0 = tile + 3 * TS + sh + 3;
+	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
 
 	// exclusive warp scan of (c0, c1) in "all first rows, then all second rows" order = row-major; returns offsets, total in `total`
 	auto scan2 = [&](int c0, int c1, int& o0, int& o1, int& total) {
@@ -487,7 +485,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		for (int j = from + lane; j < to; j += 32)
 		{
 			const int e = list[j], ry = e >> 6, rx = e & 63;
-			const int s = arc_score_packed<TS>(t0 + ry * TS + rx);
+			const int s = arc_score_packed(t0 + ry * FT_TS + rx);
 			score[(ry + 1) * SS + rx + 1] = (uint8_t)max(s, 0);
 		}
 	};
