@@ -227,7 +227,7 @@ def run_reference(args, rank, world, emit):
 # ---------------------------------------------------------------------------------------------------------------------
 def _gpu_cpu_mask(pynvml, index, words):
     try:
-        return pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), words)
+        return tuple(int(w) for w in pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), words))
     except Exception:
         return None
 
@@ -240,7 +240,7 @@ def bind_to_gpu_numa_node(local_rank):
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
         words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        mask = tuple(int(w) for w in pynvml.nvmlDeviceGetCpuAffinity(h, words))
         cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
         cpus = sorted(c for c in cpus if c in os.sched_getaffinity(0))
         world = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', 1)))
@@ -367,11 +367,13 @@ def run_b200(args, rank, world, local_rank, emit):
     dom_bytes_per_step = alg[dominant] * B
     dom_gbs = dom_bytes_per_step / (per_step[dominant] * 1e-3) / 1e9 if per_step[dominant] > 0 else 0.0
     traffic = None
+    pipes = None
     tj = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.exists(tj):
         t = json.load(open(tj)).get(dominant)
         if t:   # dram__bytes_read + write of the stage's kernels in one captured step (ncu --set full, profiles/), scaled to this batch
             traffic = t['dram_bytes_per_step'] * B / float(t.get('frames_per_step') or 256)
+            pipes = t.get('pipes')
     stage_kernels = {'pyramid': 'k_pyramid_strip x7', 'fast': 'k_level_strip<FAST> + k_fast_cells2', 'quadtree': 'k_quadtree', 'blur': 'k_level_strip<BLUR>',
                      'describe': 'k_orient_describe2'}
     roofline = {'bound': 'hbm', 'kernel': dominant, 'kernels': stage_kernels[dominant], 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
@@ -379,6 +381,7 @@ def run_b200(args, rank, world, local_rank, emit):
                 'launches_per_step': launches_per_stage[dominant],
                 'algorithmic_bytes_per_launch': dom_bytes_per_step / launches_per_stage[dominant],
                 'avg_launch_ms': per_step[dominant] / launches_per_stage[dominant],
+                'ncu_pipes': pipes,      # committed ncu capture (profiles/r02_*.txt), not this run: issue-slot / ALU / FMA / LSU utilisation of the stage's kernels
                 'stages_ms_per_step': per_step,
                 'stages_gbs': {k: (alg[k] * B / (per_step[k] * 1e-3) / 1e9 if per_step[k] > 0 else None) for k in per_step},
                 'frame': {'algorithmic_bytes_per_frame': b_alg, 'achieved': b_alg * fps / world / 1e9, 'frac': b_alg * fps / world / 1e9 / hbm_peak}}
@@ -420,30 +423,32 @@ def run_b200(args, rank, world, local_rank, emit):
     d2h = B * kcap * 60 + 4 * B                       # the call downloads whole capacity rows (a strided copy per chunk), not n[f] rows
     # what the platform allows for exactly these transfers: the same bytes per step as plain pinned cudaMemcpyAsync on two streams (one per
     # direction), no kernels, all ranks at once — the ceiling of ANY end-to-end number on this host
-    cs_in, cs_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    d_in = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    cs_in = [torch.cuda.Stream(dev) for _ in range(NH)]; cs_out = [torch.cuda.Stream(dev) for _ in range(NH)]
+    d_in = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(NH)]
     d_out = torch.empty((B, kcap, 60), dtype=torch.uint8, device=dev)
-    h_out = torch.empty((B, kcap, 60), dtype=torch.uint8).pin_memory()
+    h_out = [torch.empty((B, kcap, 60), dtype=torch.uint8).pin_memory() for _ in range(NH)]
 
     def copy_step(i):
-        with torch.cuda.stream(cs_in):
-            d_in.copy_(pinned[i % 2], non_blocking=True)
-        with torch.cuda.stream(cs_out):
-            h_out.copy_(d_out, non_blocking=True)
+        for hi in range(NH):          # as many transfers per direction in flight as the end-to-end leg has extractor instances
+            with torch.cuda.stream(cs_in[hi]):
+                d_in[hi].copy_(pinned[(i + hi) % 2], non_blocking=True)
+            with torch.cuda.stream(cs_out[hi]):
+                h_out[hi].copy_(d_out, non_blocking=True)
     for i in range(2):
         copy_step(i)
     torch.cuda.synchronize(dev)
     barrier()
     t_c = time.perf_counter()
-    csteps = 2 * e2e_steps
+    csteps = e2e_steps
     for i in range(csteps):
         copy_step(i)
     torch.cuda.synchronize(dev)
     ms_copy = max_over_ranks((time.perf_counter() - t_c) * 1e3)
     barrier()
-    copy_fps = world * B * csteps / (ms_copy * 1e-3)
-    copy_ceiling = {'value': copy_fps, 'unit': 'frames/s', 'gb_per_s_per_direction': {'h2d': world * h2d * csteps / ms_copy / 1e6, 'd2h': world * d2h * csteps / ms_copy / 1e6},
-                    'note': 'pinned cudaMemcpyAsync of the same H2D and D2H bytes per step, one stream per direction, no kernels, all ranks concurrently'}
+    copy_fps = world * NH * B * csteps / (ms_copy * 1e-3)
+    copy_ceiling = {'value': copy_fps, 'unit': 'frames/s',
+                    'gb_per_s_per_direction': {'h2d': world * NH * h2d * csteps / ms_copy / 1e6, 'd2h': world * NH * d2h * csteps / ms_copy / 1e6},
+                    'note': f'pinned cudaMemcpyAsync of the same H2D and D2H bytes per step, {NH} streams per direction, no kernels, all ranks concurrently'}
     del d_in, d_out, h_out
 
     # ---- kNN: per-GPU share of configs[4]
@@ -592,7 +597,7 @@ def run_b200(args, rank, world, local_rank, emit):
     configs = None
     if not args.skip_configs:
         configs = {}
-        for name, cb, csteps_ in (('C3', 256, 6), ('C4', 16, 4)):
+        for name, cb, csteps_ in (('C3', 256, 6), ('C4', args.c4_batch, 4)):
             c = synth.CONFIGS[name]
             base = np.stack([synth.image(2000 + 17 * rank + s_, c['w'], c['h']) for s_ in range(4)])
             d1 = torch.from_numpy(base).to(dev).repeat((cb + 3) // 4, 1, 1)[:cb].contiguous()
@@ -869,6 +874,7 @@ def main():
     ap.add_argument('--skip-knn', action='store_true')
     ap.add_argument('--skip-stereo', action='store_true')
     ap.add_argument('--skip-configs', action='store_true', help='skip the C3 / C4 blocks')
+    ap.add_argument('--c4-batch', type=int, default=96, help='4K frames per step per GPU (the quadtree is one CTA per frame and level: small batches leave SMs idle)')
     ap.add_argument('--stereo-pairs', type=int, default=64)
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-guided', action='store_true')

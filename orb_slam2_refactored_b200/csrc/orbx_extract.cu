@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(256) k_pyramid_resize(const OrbxPlanDev P, con
 #define FT_TS 80
 #define FT_TH 66
 
+//@phase exact arc score (16 ring loads, packed min/max network)
 __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 {
 	constexpr int TS = FT_TS;
@@ -282,6 +283,7 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c)
 	return max(dark, bright);
 }
 
+//@end
 #include "orbx_strip.cuh"
 
 // =====================================================================================================

@@ -20,6 +20,7 @@ struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; 
 
 __host__ __device__ constexpr int st_tile_bytes(int th) { return ((ST_BW * (th + 2 * ST_HALO) + 127) / 128) * 128; }
 
+//@phase blur arithmetic (horizontal IDP.4A, vertical IDP.2A, pack)
 // ---- 7-tap Gaussian, OpenCV 8.8 fixed point: K = {18, 34, 48, 56, 48, 34, 18} / 256, h = sum K s (16 bits, exact),
 //      v = sum K h (< 2^24), out = (v + 2^15) >> 16. Nothing is rounded in between, so any evaluation order is exact.
 // horizontal pass of one row for the lane's 4 pixels; W0 W1 W2 = columns x-4..x-1, x..x+3, x+4..x+7
@@ -51,6 +52,7 @@ __device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&p0)[4], const uin
 	return __byte_perm(__byte_perm(v[0], v[1], 0x6262), __byte_perm(v[2], v[3], 0x6262), 0x5410);
 }
 
+//@phase FAST bound arithmetic (operands, pair max/min, thresholds, flag gather)
 // ---- dense FAST bound for the lane's 4 pixels of one row (same arithmetic as the in-cell bound pass it replaces): rows y-3 (m3),
 //      y-2, y, y+2, y+3 (p3). Returns 8 bits: bits 0..3 = U > iniTh for pixels 0..3, bits 4..7 = U > minTh.
 //      The kernel is bound by the ALU pipe (VIMNMX, PRMT, LOP3, SHF, IADD3 all issue there; ncu: 91 % ALU, 6 % FMA), so everything
@@ -102,6 +104,7 @@ __device__ __forceinline__ uint32_t fast_bound_row4(const FastRowOps& K, uint32_
 	return m >> 24;                                  // low nibble = minTh flags, high nibble = iniTh flags
 }
 
+//@phase row walk: loads, window rotation, stores
 // Row walk of one tile. CHECK = false: every output row of the tile exists and (FAST) lies inside the cells' rows, so the loop has a
 // static trip count and no per-row predicate; CHECK = true: the last tile row of a level / the tiles that straddle the first or last
 // cell row.
@@ -110,6 +113,7 @@ __device__ __forceinline__ void strip_rows(const uint32_t* __restrict__ tw, uint
                                            uint8_t* __restrict__ fdst, const int64_t pitch8, const FastRowOps K, const uint32_t selx,
                                            const int lane, const int nrows, const int f0, const int f1)
 {
+	//@phase row walk: loads, window rotation, stores
 	uint32_t R[8][3];            // FAST: raw words of the last 8 rows (left / right words are dead once the row has been the centre)
 	uint32_t Dg[8][4];           // FAST: their two-column shifts (fast_row_diag), made when a row enters, dead once it is two above the centre
 	uint32_t Pp[4][4];           // blur: horizontal sums of the last 4 row pairs
@@ -180,6 +184,7 @@ __device__ __forceinline__ void strip_rows(const uint32_t* __restrict__ tw, uint
 template <int TH, bool DO_BLUR, bool DO_FAST>
 __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const __grid_constant__ OrbxStripMaps maps, const OrbxStripTiles T)
 {
+	//@phase tile header: level lookup, TMA issue, pointers, border patch
 	static_assert(TH % 8 == 0, "the row window rotates with period 8");
 	extern __shared__ __align__(128) uint8_t st_smem[];
 	uint64_t* const bar = reinterpret_cast<uint64_t*>(st_smem + st_tile_bytes(TH));
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 	else strip_rows<TH, DO_BLUR, DO_FAST, true>(tw, bdst, pitch, x < w, fdst, pitch8, K, selx, lane, nrows, f0, f1);
 }
 
+//@end
 // =====================================================================================================
 // k_pyramid_strip — cv::resize INTER_LINEAR 8UC1 in OpenCV's 11-bit fixed point for one 128 x TH output tile.
 // The source rectangle of the tile is one TMA box. A lane produces 4 adjacent output pixels per row and walks down the tile:
@@ -374,6 +380,7 @@ struct OrbxCellLayout
 
 __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
 {
+	//@phase cell table, TMA issue
 	extern __shared__ __align__(128) uint8_t fw_smem[];
 	const int lane = threadIdx.x;
 	const int cell = blockIdx.x, f = blockIdx.y;
@@ -395,6 +402,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		mbar_expect_tx(tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
 		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, tma_bar);
 	}
+	//@phase bound bitmaps of the region (loads, funnel shifts)
 	// the region's rows of the bound bitmaps: lane r holds rows r and r + 32 as 64-bit masks (bit i = region column i)
 	uint32_t wa[4], wb[4];
 	{
@@ -422,6 +430,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 			wb[2 * k] = b0 & ~a0; wb[2 * k + 1] = b1 & ~a1;        // minTh < U <= iniTh
 		}
 	}
+	//@phase zero scores and survivor bitmap, wait for the tile
 	{
 		const int n8 = (rh + 2) * (SS >> 3);              // score rows -1 .. rh, 8 bytes at a time (off_score is 16-byte aligned, SS a multiple of 8)
 #pragma unroll 1
@@ -435,6 +444,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
 
+	//@phase warp scans
 	// exclusive warp scan of (c0, c1) in "all first rows, then all second rows" order = row-major; returns offsets, total in `total`
 	auto scan2 = [&](int c0, int c1, int& o0, int& o1, int& total) {
 		int i0 = c0, i1 = c1;
@@ -458,6 +468,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		total = __shfl_sync(0xffffffffu, i0, 31);
 		o0 = i0 - c0;
 	};
+	//@phase candidate list build (expand)
 	const bool tall = rh > 32;                        // warp-uniform: most plans have no cell taller than 32 rows
 	// append the pixels of this lane's row words to the list as ry << 6 | rx; returns how many the warp appended
 	auto expand = [&](const uint32_t* w, int at) {
@@ -481,6 +492,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		}
 		return total;
 	};
+	//@phase exact-score loop around the network (evaluate)
 	auto evaluate = [&](int from, int to) {
 		for (int j = from + lane; j < to; j += 32)
 		{
@@ -489,6 +501,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 			score[(ry + 1) * SS + rx + 1] = (uint8_t)max(s, 0);
 		}
 	};
+	//@phase strict 8-neighbour maxima (select)
 	auto select = [&](int to, int t) {
 		bool found = false;
 		for (int j = lane; j < to; j += 32)
@@ -506,6 +519,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		return found;
 	};
 
+	//@phase iniTh pass, retry decision, minTh pass (control flow)
 	// exact scores + maxima at iniTh; retry at minTh if the cell has no corner (:526-530)
 	const int n1 = expand(wa, 0);
 	__syncwarp();
@@ -521,6 +535,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	}
 	__syncwarp();
 
+	//@phase ordered emit
 	// ordered emit (rows ascending, x ascending = cv::FAST's order inside the view)
 	uint32_t ws[4];
 #pragma unroll
@@ -554,3 +569,4 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	if (lane == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
 }
+//@end

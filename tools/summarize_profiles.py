@@ -1,5 +1,6 @@
-"""Turns gpurun_out/<round>_*.{csv,ncu-rep} (written by tools/make_profiles.sh on the GPU box) into the committed text
-summaries under profiles/. Run here (needs the ncu CLI, no GPU)."""
+"""Turns gpurun_out/<round>_{launches.csv,step.ncu-rep,k_knn2_partial.ncu-rep} (written by tools/make_profiles.sh on the GPU box) into the
+committed text summaries under profiles/: one file per kernel, the launch list, and <round>_traffic.json (DRAM bytes per stage and step,
+read by bench.py for roofline.traffic). Run here (needs the ncu CLI, no GPU). usage: summarize_profiles.py r02 [frames_per_step]"""
 import collections
 import csv
 import json
@@ -8,7 +9,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+R = sys.argv[1] if len(sys.argv) > 1 else 'r02'
+FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 G = os.path.join(ROOT, 'gpurun_out')
 P = os.path.join(ROOT, 'profiles')
 os.makedirs(P, exist_ok=True)
@@ -16,6 +18,7 @@ os.makedirs(P, exist_ok=True)
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'launch__waves_per_multiprocessor', 'lts__t_sector_hit_rate.pct',
@@ -23,69 +26,112 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
+UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+TIME = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}
+CMD = 'python bench.py --steps 3 --warmup 3 --batch 256 --skip-cpu --skip-stereo --skip-configs --skip-guided --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144'
+
+
+def short(name):
+    return name.split('(')[0].replace('<unnamed>::', '').replace('void ', '').strip()
 
 
 def launches():
     f = os.path.join(G, f'{R}_launches.csv')
     if not os.path.exists(f):
         return
-    rows = [r for r in csv.reader(open(f)) if len(r) > 5]
+    rows = [r for r in csv.reader(open(f, errors='replace')) if len(r) > 5]
     h = rows[0]
-    ki, vi = h.index('Kernel Name'), h.index('Metric Value')
+    ki, vi, ui = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
     agg = collections.OrderedDict()
     for r in rows[1:]:
-        agg.setdefault(r[ki].split('(')[0].replace('<unnamed>::', ''), []).append(float(r[vi].replace(',', '')))
+        agg.setdefault(short(r[ki]), []).append(float(r[vi].replace(',', '')) * TIME.get(r[ui], 1e-3))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(P, f'{R}_launches.txt'), 'w') as o:
         o.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES), window of {len(rows) - 1} launches\n')
-        o.write('# command: python bench.py --steps 3 --warmup 3 --batch 256 --skip-cpu --knn-steps 1 --knn-queries 131072 --knn-train-per-gpu 262144 (tools/profile_one.sh)\n')
-        o.write(f'{"kernel":28s} {"n":>4s} {"sum_us":>10s} {"avg_us":>9s} {"share":>7s}\n')
+        o.write(f'# command: {CMD} (tools/make_profiles.sh)\n')
+        o.write(f'{"kernel":44s} {"n":>4s} {"sum_us":>10s} {"avg_us":>9s} {"share":>7s}\n')
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            o.write(f'{k[:28]:28s} {len(v):4d} {sum(v) / 1e3:10.1f} {sum(v) / len(v) / 1e3:9.1f} {sum(v) / tot:7.3f}\n')
+            o.write(f'{k[:44]:44s} {len(v):4d} {sum(v):10.1f} {sum(v) / len(v):9.1f} {sum(v) / tot:7.3f}\n')
     os.replace(f, os.path.join(P, f'{R}_launches.csv'))
     print(open(os.path.join(P, f'{R}_launches.txt')).read())
 
 
-def full(kernel, frames_per_launch=None):
-    rep = os.path.join(G, f'{R}_{kernel}.ncu-rep')
-    if not os.path.exists(rep):
-        return None
+def raw(rep):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    h, u, v = rows[0], rows[1], rows[-1]
-    d = {}
-    with open(os.path.join(P, f'{R}_{kernel}.txt'), 'w') as o:
-        o.write(f'# ncu --set full --clock-control none --import-source on -k regex:{kernel} -c 1 (one launch)\n')
+    return rows[0], rows[1], rows[2:]
+
+
+STAGE = {'k_pyramid_strip': 'pyramid', 'k_level_strip<32, 1, 0>': 'blur', 'k_level_strip<32, 0, 1>': 'fast', 'k_fast_cells2': 'fast',
+         'k_quadtree': 'quadtree', 'k_orient_describe2': 'describe'}
+
+
+def stage_of(name):
+    for k, v in STAGE.items():
+        if k in name:
+            return v
+    return None
+
+
+def step():
+    rep = os.path.join(G, f'{R}_step.ncu-rep')
+    if not os.path.exists(rep):
+        return
+    h, u, rows = raw(rep)
+    ki = h.index('Kernel Name')
+    groups = collections.OrderedDict()
+    for r in rows:
+        groups.setdefault(short(r[ki]), []).append(r)
+    traffic = {}
+    for name, rs in groups.items():
+        fn = name.replace('<', '_').replace('>', '').replace(', ', '_').replace('::', '_').replace(' ', '')
+        with open(os.path.join(P, f'{R}_{fn}.txt'), 'w') as o:
+            o.write(f'# ncu --set full --clock-control none --import-source on, {len(rs)} launch(es) of {name} inside one device-resident step of {FRAMES} C1 frames\n')
+            o.write(f'# command: {CMD} (tools/make_profiles.sh); times are cold-cache and serialised\n')
+            for n, r in enumerate(rs):
+                if len(rs) > 1:
+                    o.write(f'## launch {n + 1} of {len(rs)}\n')
+                for k in KEYS:
+                    if k in h:
+                        i = h.index(k)
+                        o.write(f'{k:90s} {r[i]:>18s} {u[i]}\n')
+        st = stage_of(name)
+        if st:
+            t = traffic.setdefault(st, {'dram_bytes_per_step': 0.0, 'kernel_us_per_step': 0.0, 'frames_per_step': FRAMES, 'kernels': []})
+            for r in rs:
+                rd, wr = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
+                t['dram_bytes_per_step'] += float(r[rd].replace(',', '')) * UNIT[u[rd]] + float(r[wr].replace(',', '')) * UNIT[u[wr]]
+                ti = h.index('gpu__time_duration.sum')
+                t['kernel_us_per_step'] += float(r[ti].replace(',', '')) * TIME[u[ti]]
+            t['kernels'].append(f'{name} x{len(rs)}')
+            # issue-slot and pipe utilisation of the stage's longest launch: what actually bounds these integer kernels
+            big = max(rs, key=lambda r: float(r[h.index('gpu__time_duration.sum')].replace(',', '')))
+            pipes = t.setdefault('pipes', {})
+            pipes[name] = {k2: float(big[h.index(k1)].replace(',', '')) for k2, k1 in (
+                ('issue_active_pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                ('alu_pct', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
+                ('fma_pct', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'),
+                ('fmaheavy_pct_elapsed', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+                ('lsu_pct', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'),
+                ('dram_pct', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')) if k1 in h}
+        print(name, len(rs), 'launches')
+    json.dump(traffic, open(os.path.join(P, f'{R}_traffic.json'), 'w'), indent=1)
+    print(json.dumps(traffic, indent=1))
+
+
+def knn():
+    rep = os.path.join(G, f'{R}_k_knn2_partial.ncu-rep')
+    if not os.path.exists(rep):
+        return
+    h, u, rows = raw(rep)
+    with open(os.path.join(P, f'{R}_k_knn2_partial.txt'), 'w') as o:
+        o.write('# ncu --set full --clock-control none --import-source on -k regex:k_knn2_partial -c 1 (131072 queries x 262144 train rows)\n')
         for k in KEYS:
             if k in h:
                 i = h.index(k)
-                o.write(f'{k:90s} {v[i]:>18s} {u[i]}\n')
-                d[k] = (v[i], u[i])
-    print(open(os.path.join(P, f'{R}_{kernel}.txt')).read())
-    return d
-
-
-def to_bytes(val, unit):
-    x = float(val.replace(',', ''))
-    return x * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+                o.write(f'{k:90s} {rows[-1][i]:>18s} {u[i]}\n')
 
 
 launches()
-tj = os.path.join(P, f'{R}_traffic.json')
-traffic = json.load(open(tj)) if os.path.exists(tj) else {}      # captures arrive one gpurun call at a time: keep what is already there
-NOTES = {'k_guided_search': 'one search, 1000 keypoints x 1000 map points (tools/guided_probe.py), a cluster of 8 CTAs',
-         'k_remap_to_l0': 'one launch of 256 frames 752x480 (bench.py remap block)',
-         'k_stereo_match': 'one launch of 64 C2 stereo pairs (bench.py stereo block)',
-         'k_bow_descend': 'one launch of 256 frames x 1000 descriptors through the k 10 / L 6 vocabulary (bench.py bow block)',
-         'k_bow_finalize': 'one launch of 256 frames (bench.py bow block), one CTA per frame'}
-for k in ('k_fast_cells', 'k_gauss7', 'k_pyramid_resize', 'k_orient_describe', 'k_quadtree', 'k_knn2_partial', 'k_guided_search', 'k_remap_to_l0',
-          'k_stereo_match', 'k_bow_descend', 'k_bow_finalize', 'k_best_in_windows'):
-    d = full(k)
-    if d and 'dram__bytes_read.sum' in d:
-        traffic[k] = {'dram_bytes_per_launch': to_bytes(*d['dram__bytes_read.sum']) + to_bytes(*d['dram__bytes_write.sum']),
-                      'launch_us': float(d['gpu__time_duration.sum'][0].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}[d['gpu__time_duration.sum'][1]],
-                      'grid': d['launch__grid_size'][0],
-                      'note': NOTES.get(k, 'one launch of the bench default batch (256 frames); k_gauss7 / k_pyramid_resize: one level of it')}
-if traffic:
-    json.dump(traffic, open(os.path.join(P, f'{R}_traffic.json'), 'w'), indent=1)
-    print(traffic)
+step()
+knn()
