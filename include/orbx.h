@@ -95,7 +95,10 @@ orbx_status orbx_extract_batch(orbx_handle h, const uint8_t* images, int frames,
 
 /* Device-resident variant: inputs already in HBM, outputs stay in HBM (d_kps: frames*cap keypoints, d_desc:
  * frames*cap*32 bytes, d_n: frames int32). Asynchronous on the handle's stream; call orbx_synchronize (or use
- * orbx_stream) before reading. cap must be >= orbx_max_keypoints(h). */
+ * orbx_stream) before reading. cap must be >= orbx_max_keypoints(h). When d_images, pitch and frame_stride are multiples of
+ * 16 bytes the frames are read in place and ARE level 0 of the pyramid until the next extract on this handle
+ * (orbx_pyramid_level(_device) of level 0 and orbx_stereo_match read them): keep them unchanged that long. Other layouts
+ * are copied into an internal buffer first (ComputePyramid's own copyTo, src/ORBextractor.cc:462). */
 orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, int frames, int width, int height,
                                       size_t pitch, size_t frame_stride, orbx_keypoint* d_kps, uint8_t* d_desc,
                                       int cap, int32_t* d_n);

@@ -119,6 +119,9 @@ struct orbx_extractor
 	OrbxStripMaps smaps[2];             // strip kernels (blur, dense FAST bound): every level with the strip box; [1]: the 8-row tiles of small batches
 	OrbxPyrMaps pmaps[2];               // strip resize kernel: level s - 1 with the source box of a tile of level s
 	DevBuf<uint8_t> fmap_ini, fmap_min; // FAST bound bitmaps (1 bit per level pixel each)
+	const uint8_t* l0_map_base = nullptr;   // what the level-0 descriptors currently point at
+	int64_t l0_map_pitch = 0, l0_map_stride = 0;
+	int l0_map_frames = 0;
 	DevBuf<uint8_t> color;              // interleaved colour frames / unrectified frames of the current batch (orbx_extract_batch_color / _rectified)
 	DevBuf<int2> rect_tab;              // rectification table (orbx_set_rectification): per output pixel (ix | iy << 16, fx | fy << 5)
 	int rect_w = 0, rect_h = 0, rect_sw = 0, rect_sh = 0;
@@ -193,6 +196,53 @@ void resize_tables(int dn, int sn, int* ofs, short2* coef)
 		coef[d].x = sat_s16(cv_round((1.f - f) * 2048.f));
 		coef[d].y = sat_s16(cv_round(f * 2048.f));
 	}
+}
+
+// TMA descriptors of level s seen as a (dimx, h, frames) u8 tensor with row pitch `pitch` and frame stride `stride` at `base`: the cell
+// view box (FAST cell kernel), the strip boxes (blur, dense FAST bound; throughput and small-batch tile heights) and, as the SOURCE of level
+// s + 1, that level's resize boxes. base must be 16-byte aligned, pitch and stride multiples of 16 (cuTensorMapEncodeTiled checks).
+orbx_status encode_level_maps(orbx_extractor* h, int s, const void* base, int64_t dimx, int64_t pitch, int64_t stride, int frames)
+{
+	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+	                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static const EncodeFn fn = []() -> EncodeFn {          // resolved once (thread-safe static initialisation)
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+		return (EncodeFn)p;
+	}();
+	if (!fn) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+	const OrbxPlanDev& P = h->P;
+	const OrbxLevel& L = P.lv[s];
+	const cuuint64_t dims[3] = { (cuuint64_t)dimx, (cuuint64_t)L.h, (cuuint64_t)frames };
+	const cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)stride };
+	const cuuint32_t estr[3] = { 1, 1, 1 };
+	auto enc = [&](CUtensorMap* m, int bw, int bh, const char* what) -> orbx_status {
+		const cuuint32_t box[3] = { (cuuint32_t)bw, (cuuint32_t)bh, 1 };
+		const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, std::string("cuTensorMapEncodeTiled (") + what + ") failed with CUresult " + std::to_string((int)r));
+		return ORBX_OK;
+	};
+	orbx_status st = enc(&h->maps.level[s], orbx_fast_tile_stride(), h->maps.box_h[s], "cell view");
+	for (int which = 0; which < 2 && st == ORBX_OK; which++)
+	{
+		st = enc(&h->smaps[which].level[s], orbx_strip_box_w(), orbx_strip_rows(which) + 6, "strip box");
+		if (st == ORBX_OK && s + 1 < P.nlevels && P.lv[s + 1].py_bw[which] > 0)
+			st = enc(&h->pmaps[which].src[s + 1], P.lv[s + 1].py_bw[which], P.lv[s + 1].py_bh[which], "resize box");
+	}
+	return st;
+}
+
+// level 0 lives either in the handle's padded buffer or, for the device-resident API, in the caller's own buffer (no repack): its
+// descriptors follow whichever the current call uses
+orbx_status ensure_level0_maps(orbx_extractor* h, const uint8_t* base, int64_t dimx, int64_t pitch, int64_t stride, int frames)
+{
+	if (h->l0_map_base == base && h->l0_map_pitch == pitch && h->l0_map_stride == stride && h->l0_map_frames >= frames) return ORBX_OK;
+	const orbx_status st = encode_level_maps(h, 0, base, dimx, pitch, stride, frames);
+	if (st != ORBX_OK) { h->l0_map_base = nullptr; return st; }
+	h->l0_map_base = base; h->l0_map_pitch = pitch; h->l0_map_stride = stride; h->l0_map_frames = frames;
+	return ORBX_OK;
 }
 
 orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
@@ -374,14 +424,8 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
-	// TMA descriptors for the FAST kernel's tile loads: level s of every frame as a (pitch, h, frames) u8 tensor
+	// TMA descriptors of every level as a (pitch, h, frames) u8 tensor, one per box shape (encode_level_maps)
 	{
-		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-		                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-		void* fn = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-		if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
 		std::memset(&h->maps, 0, sizeof(h->maps));
 		int max_view_w = 0;
 		for (int s = 0; s < nl; s++)
@@ -397,34 +441,11 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 			for (int cy = 0, y0 = L.miny; cy < L.ncy; cy++, y0 += L.cellh) box_h = std::max(box_h, std::min(y0 + L.cellh + 6, L.maxy) - y0);
 			if (box_h > orbx_fast_tile_rows()) return fail(ORBX_ERR_INVALID, "cell taller than the FAST tile");
 			h->maps.box_h[s] = box_h;
-			void* base = s == 0 ? (void*)h->l0base : (void*)(P.pyr + L.offset);
-			const cuuint64_t dims[3] = { (cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)frames };
-			const cuuint64_t strides[2] = { (cuuint64_t)L.pitch, (cuuint64_t)(s == 0 ? h->l0_stride : P.slab) };
-			const cuuint32_t box[3] = { (cuuint32_t)orbx_fast_tile_stride(), (cuuint32_t)box_h, 1 };
-			const cuuint32_t estr[3] = { 1, 1, 1 };
-			const CUresult r = ((EncodeFn)fn)(&h->maps.level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
-			                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-			                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-			if (r != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-			for (int which = 0; which < 2; which++)
-			{
-				// the same tensor with the strip box (blur, dense FAST bound) ...
-				const cuuint32_t sbox[3] = { (cuuint32_t)orbx_strip_box_w(), (cuuint32_t)(orbx_strip_rows(which) + 6), 1 };
-				const CUresult r2 = ((EncodeFn)fn)(&h->smaps[which].level[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, sbox, estr,
-				                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-				                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-				if (r2 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (strip box) failed with CUresult " + std::to_string((int)r2));
-				// ... and, as the SOURCE of level s + 1, with that level's resize box
-				if (s + 1 < nl && P.lv[s + 1].py_bw[which] > 0)
-				{
-					const cuuint32_t pbox[3] = { (cuuint32_t)P.lv[s + 1].py_bw[which], (cuuint32_t)P.lv[s + 1].py_bh[which], 1 };
-					const CUresult r3 = ((EncodeFn)fn)(&h->pmaps[which].src[s + 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, pbox, estr,
-					                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-					                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-					if (r3 != CUDA_SUCCESS) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (resize box) failed with CUresult " + std::to_string((int)r3));
-				}
-			}
+			const orbx_status st = s == 0 ? encode_level_maps(h, 0, h->l0base, L.pitch, L.pitch, h->l0_stride, frames)
+			                              : encode_level_maps(h, s, P.pyr + L.offset, L.pitch, L.pitch, P.slab, frames);
+			if (st != ORBX_OK) return st;
 		}
+		h->l0_map_base = h->l0base; h->l0_map_pitch = h->l0_pitch; h->l0_map_stride = h->l0_stride; h->l0_map_frames = frames;
 	}
 	h->pw = w; h->ph = hgt; h->frames_cap = frames;
 	h->have_result = false;
@@ -700,16 +721,28 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 	if (st != ORBX_OK) return st;
 	if (cap < h->P.sel_per_frame || cap >= 65536)
 		return fail(ORBX_ERR_CAPACITY, "cap must be >= orbx_max_keypoints() (and < 65536)");
-	// Level 0 is always copied into the padded level-0 buffer (the kernels stage tiles with aligned 16-byte copies that may
-	// reach a few bytes outside a row); this is ComputePyramid's own copyTo (:462) and costs 2 x 300 KiB of HBM traffic per frame.
-	if (frame_stride == pitch * (size_t)height)
-		CU(cudaMemcpy2DAsync(h->l0base, h->l0_pitch, d_images, pitch, width, (size_t)height * frames, cudaMemcpyDeviceToDevice, h->stream));
-	else
-		for (int f = 0; f < frames; f++)
-			CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, d_images + (size_t)f * frame_stride, pitch,
-			                     width, height, cudaMemcpyDeviceToDevice, h->stream));
-	const uint8_t* l0 = h->l0base;
-	const int64_t l0_pitch = h->l0_pitch, l0_stride = h->l0_stride;
+	// Level 0: every kernel that reads a level stages it by TMA (rows and columns outside the tensor arrive as zeros) or by 16-byte copies
+	// from a 16-byte aligned row start, so a caller's buffer whose base, pitch and frame stride are multiples of 16 is read IN PLACE: no
+	// repack, 2 x 300 KiB of HBM traffic per VGA frame less. The buffer then IS level 0 of the pyramid until the next extract on this handle
+	// (GetImagePyramid()[0], the stereo matcher's SAD window read it). Anything else (odd pitch such as 1241, or a plan whose level 1 comes
+	// from the cp.async resize kernel, which reads a few bytes outside a row) is copied into the padded level-0 buffer, which is
+	// ComputePyramid's own copyTo (:462).
+	static const bool allow_direct = getenv("ORBX_NO_DIRECT") == nullptr;
+	const bool direct = allow_direct && ((uintptr_t)d_images % 16 == 0) && pitch % 16 == 0 && frame_stride % 16 == 0 &&
+	                    (h->prm.nlevels == 1 || (h->P.lv[1].py_bw[0] > 0 && h->P.lv[1].py_bw[1] > 0));
+	const uint8_t* l0 = direct ? d_images : h->l0base;
+	const int64_t l0_pitch = direct ? (int64_t)pitch : h->l0_pitch, l0_stride = direct ? (int64_t)frame_stride : h->l0_stride;
+	if (!direct)
+	{
+		if (frame_stride == pitch * (size_t)height)
+			CU(cudaMemcpy2DAsync(h->l0base, h->l0_pitch, d_images, pitch, width, (size_t)height * frames, cudaMemcpyDeviceToDevice, h->stream));
+		else
+			for (int f = 0; f < frames; f++)
+				CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, d_images + (size_t)f * frame_stride, pitch,
+				                     width, height, cudaMemcpyDeviceToDevice, h->stream));
+	}
+	st = ensure_level0_maps(h, l0, direct ? width : h->l0_pitch, l0_pitch, l0_stride, direct ? frames : h->frames_cap);
+	if (st != ORBX_OK) return st;
 	// The stages are bound by different things (FAST by instruction issue, pyramid/descriptor by memory latency), so the two
 	// halves of a large batch run on two streams and fill each other's stalls. The second lane is forked from and joined back
 	// into the handle's stream, so the call stays stream-ordered for the caller.
@@ -765,6 +798,8 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 	CU(cudaSetDevice(h->device));
 	if (rectify) { width = h->rect_w; height = h->rect_h; }
 	orbx_status st = build_plan(h, width, height, frames);
+	if (st != ORBX_OK) return st;
+	st = ensure_level0_maps(h, h->l0base, h->l0_pitch, h->l0_pitch, h->l0_stride, h->frames_cap);
 	if (st != ORBX_OK) return st;
 	const OrbxPlanDev& P = h->P;
 	const int ocap = P.sel_per_frame;
