@@ -91,6 +91,33 @@ def test_device_resident_batch(orbx, oracle_final):
         assert np.array_equal(desc[f, :n[f]], odesc)
 
 
+@pytest.mark.parametrize('pad,shift', [(16, 0), (10, 0), (32, 4), (0, 0)])
+def test_device_resident_layouts(orbx, oracle_final, pad, shift):
+    """orbx_extract_batch_device reads 16-byte aligned frames IN PLACE as level 0 (pitch / frame stride / base multiples of 16) and copies
+    every other layout into its padded buffer first: (16, 0) in place with pitch != width, (10, 0) odd pitch -> copy, (32, 4) base off by 4 bytes
+    -> copy, (0, 0) contiguous -> in place. Same keypoints and descriptors either way, and the level-0 view of GetImagePyramid is the frame."""
+    import torch
+    c = synth.CONFIGS['C1']
+    w, h = c['w'], c['h']
+    imgs = np.stack([synth.image(40 + s, w, h) for s in range(3)])
+    big = torch.zeros((3, h, w + pad), dtype=torch.uint8, device='cuda')
+    view = big[:, :, shift:shift + w]
+    view.copy_(torch.from_numpy(imgs).cuda())
+    ex = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    kps, desc, n = ex.extract_batch_device(view)
+    ex.synchronize()
+    n = n.cpu().numpy(); kps = kps.cpu().numpy().view(np.uint8).reshape(3, -1, 28); desc = desc.cpu().numpy()
+    e = oracle_final.extractor(c['nfeatures'])
+    for f in range(3):
+        okps, odesc = e.extract(imgs[f])
+        assert n[f] == len(okps) and kps[f, :n[f]].tobytes() == okps.tobytes() and np.array_equal(desc[f, :n[f]], odesc), f'frame {f}'
+    assert np.array_equal(ex.GetImagePyramid(1)[0], imgs[1])
+    # a host-buffer call on the same handle afterwards (its level 0 lives in the handle's own buffer again)
+    k1, d1 = ex.Extract(imgs[2])
+    okps, odesc = e.extract(imgs[2])
+    assert k1.tobytes() == okps.tobytes() and np.array_equal(d1, odesc)
+
+
 def test_strided_and_misaligned_input(orbx, oracle_final):
     # a sub-matrix view (row stride != width, base not 16-byte aligned), as cv::Mat ROIs are
     c = synth.CONFIGS['C1']
