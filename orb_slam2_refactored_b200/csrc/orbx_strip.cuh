@@ -72,8 +72,9 @@ __device__ __forceinline__ void fast_row_diag(uint32_t wa, uint32_t wb, uint32_t
 	D[0] = __byte_perm(wb, wc, 0x5432); D[1] = __byte_perm(wb, wc, 0x4321);
 	D[2] = __byte_perm(wa, wb, 0x5432); D[3] = __byte_perm(wa, wb, 0x4321);
 }
-__device__ __forceinline__ uint32_t fast_bound_row4(const FastRowOps& K, uint32_t m3, const uint32_t (&Dm)[4], uint32_t c0, uint32_t c1, uint32_t c2,
-                                                    const uint32_t (&Dp)[4], uint32_t p3)
+// raw form: the iniTh flags in bits 28..31, the minTh flags in bits 24..27, partial products below
+__device__ __forceinline__ uint32_t fast_bound_row4_raw(const FastRowOps& K, uint32_t m3, const uint32_t (&Dm)[4], uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        const uint32_t (&Dp)[4], uint32_t p3)
 {
 	uint32_t f[2];
 #pragma unroll
@@ -100,8 +101,12 @@ __device__ __forceinline__ uint32_t fast_bound_row4(const FastRowOps& K, uint32_
 	// down by 4, in bits 3,11,19,27 (minTh); ONE multiply gathers all eight: bit 7 + 8j -> 24 + j, bit 3 + 8j -> 20 + j ... the partial
 	// products fall on distinct bits, so nothing carries
 	const uint32_t fi = __byte_perm(f[1], f[0], 0x7351) & 0x80808080u, gi = (__byte_perm(g1, g0, 0x7351) >> 4) & 0x08080808u;
-	const uint32_t m = (fi | gi) * 0x00204081u;      // bit 7 + 8j -> 28 + j (iniTh), bit 3 + 8j -> 24 + j (minTh)
-	return m >> 24;                                  // low nibble = minTh flags, high nibble = iniTh flags
+	return (fi | gi) * 0x00204081u;                  // bit 7 + 8j -> 28 + j (iniTh), bit 3 + 8j -> 24 + j (minTh)
+}
+__device__ __forceinline__ uint32_t fast_bound_row4(const FastRowOps& K, uint32_t m3, const uint32_t (&Dm)[4], uint32_t c0, uint32_t c1, uint32_t c2,
+                                                    const uint32_t (&Dp)[4], uint32_t p3)
+{
+	return fast_bound_row4_raw(K, m3, Dm, c0, c1, c2, Dp, p3) >> 24;      // low nibble = minTh flags, high nibble = iniTh flags
 }
 
 //@phase row walk: loads, window rotation, stores
