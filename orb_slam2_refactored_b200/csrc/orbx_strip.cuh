@@ -16,7 +16,9 @@
 #define ST_BWW (ST_BW / 4)
 #define ST_HALO 3
 
-struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int one; };   // one = 1, a value the compiler cannot fold (see FastRowOps)
+// one = 1, a value the compiler cannot fold (see FastRowOps); (xorg, yorg) = origin of the tile grid: (0, 0) for the blur, the 16-byte
+// aligned column / the first row of the cells' interiors for the FAST bound, whose tiles then cover only what DetectFAST looks at
+struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int one, xorg, yorg; };
 
 __host__ __device__ constexpr int st_tile_bytes(int th) { return ((ST_BW * (th + 2 * ST_HALO) + 127) / 128) * 128; }
 
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 	const int tile_y = tile / tx, tile_x = tile - tile_y * tx;
 	const OrbxLevel& L = P.lv[level];
 	const int w = L.w, h = L.h;
-	const int x0 = tile_x * ST_TW, y0 = tile_y * TH;
+	const int x0 = tile_x * ST_TW + T.xorg, y0 = tile_y * TH + T.yorg;
 	if (lane == 0)
 	{
 		mbar_init(bar, 1);
