@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'liborbx_b200.so')
 SOURCES = ['orbx_extract.cu', 'orbx_match.cu', 'orbx_guided.cu', 'orbx_bow.cu', 'orbx_api.cu']
-DEPS = SOURCES + ['orbx_internal.cuh', 'orbx_sort.cuh', 'orbx_quadtree.cuh', 'orbx_strip.cuh', 'orbx_fastgroup.cuh', 'orbx_describe.cuh', 'orb_pattern.inc', os.path.join('..', '..', 'include', 'orbx.h')]
+DEPS = SOURCES + ['orbx_internal.cuh', 'orbx_sort.cuh', 'orbx_quadtree.cuh', 'orbx_strip.cuh', 'orbx_describe.cuh', 'orb_pattern.inc', os.path.join('..', '..', 'include', 'orbx.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -118,8 +118,6 @@ struct orbx_extractor
 	OrbxTmaMaps maps;
 	OrbxStripMaps smaps[2];             // strip kernels (blur, dense FAST bound): every level with the strip box; [1]: the 8-row tiles of small batches
 	OrbxPyrMaps pmaps[2];               // strip resize kernel: level s - 1 with the source box of a tile of level s
-	OrbxGroupMaps gmaps;                // cell-group FAST kernel: every level with the group box
-	DevBuf<int4> group_tab;
 	DevBuf<uint8_t> fmap_ini, fmap_min; // FAST bound bitmaps (1 bit per level pixel each)
 	const uint8_t* l0_map_base = nullptr;   // what the level-0 descriptors currently point at
 	int64_t l0_map_pitch = 0, l0_map_stride = 0;
@@ -227,7 +225,6 @@ orbx_status encode_level_maps(orbx_extractor* h, int s, const void* base, int64_
 		return ORBX_OK;
 	};
 	orbx_status st = enc(&h->maps.level[s], orbx_fast_tile_stride(), h->maps.box_h[s], "cell view");
-	if (st == ORBX_OK && h->gmaps.box_h > 0) st = enc(&h->gmaps.level[s], orbx_strip_box_w(), h->gmaps.box_h, "cell group box");
 	for (int which = 0; which < 2 && st == ORBX_OK; which++)
 	{
 		st = enc(&h->smaps[which].level[s], orbx_strip_box_w(), orbx_strip_rows(which) + 6, "strip box");
@@ -270,9 +267,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	std::vector<int> root_x, xofs, yofs;
 	std::vector<uint8_t> root_lut;
 	std::vector<short2> xcoef, ycoef;
-	std::vector<int4> cell_tab, group_tab;
-	bool groups_ok = true;
-	int max_cellh = 0;
+	std::vector<int4> cell_tab;
 	int64_t slab = 0;
 	int cells = 0, cands = 0, sels = 0, node_cap = 0;
 	for (int s = 0; s < nl; s++)
@@ -309,30 +304,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 				const int x1 = std::min(x0 + L.cellw + 6, L.maxx), y1 = std::min(y0 + L.cellh + 6, L.maxy);
 				cell_tab.push_back(make_int4(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16), s, cy * L.ncx + cx));
 			}
-		// cell groups (k_fast_groups): the interiors [x0 + 3, x1 - 3) of the cells of a cell row tile [minx + 3, maxx - 3); a group is a run
-		// of at most four of them that fits the 128 columns of a warp
-		max_cellh = std::max(max_cellh, L.cellh);
-		if (L.cellh > orbx_group_max_rows() || L.cellw > 63) groups_ok = false;
-		for (int cy = 0; cy < L.ncy && groups_ok; cy++)
-		{
-			const int iy0 = L.miny + 3 + cy * L.cellh, iy1 = std::min(iy0 + L.cellh, L.maxy - 3);
-			for (int cx = 0; cx < L.ncx;)
-			{
-				const int ix0 = L.minx + 3 + cx * L.cellw;
-				int n = 0, ix1 = ix0;
-				while (n < 4 && cx + n < L.ncx)
-				{
-					const int e = std::min(ix0 + (n + 1) * L.cellw, L.maxx - 3);
-					if (e - ix0 > orbx_group_max_cols()) break;
-					ix1 = e; n++;
-				}
-				if (n == 0) { groups_ok = false; break; }
-				group_tab.push_back(make_int4(ix0 | (iy0 << 16), (ix1 - ix0) | ((iy1 - iy0) << 16), s | (n << 8) | (L.cellw << 16), cy * L.ncx + cx));
-				cx += n;
-			}
-		}
 		L.cell_cap = ((L.cellw + 1) / 2) * ((L.cellh + 1) / 2);
-		if (L.cell_cap > 65535) groups_ok = false;
 		L.cand_base = cands;
 		L.cand_cap = L.ncx * L.ncy * L.cell_cap;
 		cands += L.cand_cap;
@@ -434,11 +406,6 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(h->yofs.ensure(std::max<size_t>(yofs.size(), 1))); CU(h->ycoef.ensure(std::max<size_t>(ycoef.size(), 1)));
 	CU(h->cell_tab.ensure(cell_tab.size()));
 	CU(cudaMemcpyAsync(h->cell_tab.p, cell_tab.data(), cell_tab.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-	if (groups_ok)
-	{
-		CU(h->group_tab.ensure(group_tab.size()));
-		CU(cudaMemcpyAsync(h->group_tab.p, group_tab.data(), group_tab.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-	}
 	CU(h->out_kps.ensure(F * sels)); CU(h->out_desc.ensure(F * sels * 32)); CU(h->out_n.ensure(F));
 	CU(cudaMemcpyAsync(h->root_x.p, root_x.data(), root_x.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
 	CU(cudaMemcpyAsync(h->root_lut.p, root_lut.data(), root_lut.size(), cudaMemcpyHostToDevice, h->stream));
@@ -456,13 +423,10 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
-	P.group_tab = groups_ok ? h->group_tab.p : nullptr; P.groups_per_frame = groups_ok ? (int)group_tab.size() : 0;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
 	// TMA descriptors of every level as a (pitch, h, frames) u8 tensor, one per box shape (encode_level_maps)
 	{
 		std::memset(&h->maps, 0, sizeof(h->maps));
-		std::memset(&h->gmaps, 0, sizeof(h->gmaps));
-		h->gmaps.box_h = groups_ok ? max_cellh + 6 : 0;
 		int max_view_w = 0;
 		for (int s = 0; s < nl; s++)
 			for (int cx = 0, x0 = P.lv[s].minx; cx < P.lv[s].ncx; cx++, x0 += P.lv[s].cellw)
@@ -549,7 +513,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 		CU(cudaEventRecord(h->side_join[lane], side));
 	}
 	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_fast(P, h->maps, h->smaps, h->gmaps, st);
+	orbx_launch_fast(P, h->maps, h->smaps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
 	if (ev) CU(cudaEventRecord(ev[4], st));
 	orbx_launch_quadtree(P, cell_off, st);
@@ -635,7 +599,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->l0buf.release(); h->color.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
 	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
-	h->cell_tab.release(); h->group_tab.release(); h->fmap_ini.release(); h->fmap_min.release();
+	h->cell_tab.release(); h->fmap_ini.release(); h->fmap_min.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release(); h->st_rows.release(); h->st_items.release();

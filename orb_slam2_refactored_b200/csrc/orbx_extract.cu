@@ -286,7 +286,6 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c) {
 
 //@end
 #include "orbx_strip.cuh"
-#include "orbx_fastgroup.cuh"
 
 // =====================================================================================================
 // K3+K4  quadtree_select — QuadTreeSuppression + QTreeNode::divide (src/ORBextractor.cc:402-453, :542-693)
@@ -472,7 +471,6 @@ cudaError_t orbx_kernels_init()
 	set(k_pyramid_strip<16>, 100 * 1024);
 	set(k_pyramid_strip<8>, 100 * 1024);
 	set(k_fast_cells2, 64 * 1024);
-	set(k_fast_groups, 64 * 1024);
 	set(k_level_strip<8, true, false>, 64 * 1024); set(k_level_strip<8, false, true>, 64 * 1024);
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024);
 	set(k_level_strip<32, true, false>, 64 * 1024); set(k_level_strip<32, false, true>, 64 * 1024);
@@ -579,33 +577,8 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 
-int orbx_group_max_rows() { return FG_TH; }
-int orbx_group_max_cols() { return ST_TW; }
-
-// one warp per run of up to four cells, dense bound to ordered emit (orbx_fastgroup.cuh)
-static void launch_groups(const OrbxPlanDev& P, const OrbxGroupMaps& gmaps, cudaStream_t st)
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st)
 {
-	int maxrh = 0;
-	for (int s = 0; s < P.nlevels; s++) maxrh = std::max(maxrh, P.lv[s].cellh);
-	// staged tile | bound flags | survivor bitmap (+ 2 spare rows) | score map (tile stride, 1 px zero border) | list | mbarrier. The row walk reads up
-	// to 8 * ceil(rows / 8) + 6 box rows (the surplus feeds predicated-off rows): whatever lies behind the tile is at least that long.
-	OrbxGroupLayout Y;
-	Y.off_bits = (ST_BW * gmaps.box_h + 15) & ~15;
-	Y.off_sel = Y.off_bits + 8 * 32 * (FG_TH / 8);
-	Y.off_score = Y.off_sel + 16 * (FG_TH + 2);
-	Y.off_list = (Y.off_score + (maxrh + 2) * FG_SS + 15) & ~15;
-	Y.off_bar = Y.off_list + 2 * FG_LIST_CAP;
-	Y.bytes = (Y.off_bar + 8 + 127) & ~127;
-	dim3 grid(P.groups_per_frame, P.frames);
-	k_fast_groups<<<grid, 32, Y.bytes, st>>>(P, gmaps, Y, 1);
-}
-
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], const OrbxGroupMaps& gmaps, cudaStream_t st)
-{
-	// Throughput batches: the cell-group kernel. A frame at a time (what Tracking does) has too few groups to fill the GPU and a group's
-	// warp runs ~5000 instructions back to back, so small batches keep the two-launch form with its 8-row tiles and warp per cell.
-	static const int mode = env_int("ORBX_FAST_GROUPS", 0);      // tuning knob: 0 = always the two-launch form, 2 = always the group kernel
-	if (mode && P.group_tab && (P.frames > ORBX_SMALL_BATCH || mode == 2)) { launch_groups(P, gmaps, st); return; }
 	// (Two cells per warp with one merged candidate list — 15 % fewer instructions per cell — was measured: 1.13 vs 0.96 ms per 512
 	// frames. The doubled shared memory per warp halves the resident warps, and this kernel lives on latency hiding.)
 	launch_strip(P, smaps, 2, st);

@@ -60,9 +60,6 @@ struct OrbxPlanDev
 	uint32_t* cand;              // [frames][cand_per_frame] per-cell slots
 	int* cell_count;             // [frames][cells_per_frame]
 	const int4* cell_tab;        // [cells_per_frame] x0 | y0 << 16, view w | h << 16, level, cell index inside the level
-	const int4* group_tab;       // [groups_per_frame] runs of up to four cells of one cell row (k_fast_groups): first interior column | row << 16, interior
-	                             // width | rows << 16, level | cells << 8 | nominal cell width << 16, first cell index inside the level; null: plan not eligible
-	int groups_per_frame;
 	uint32_t* qbuf0; uint32_t* qbuf1;   // [frames][cand_per_frame] quadtree ping-pong segments
 	int* cand_count;             // [frames][nlevels] DetectFAST totals (debug/probes)
 	uint32_t* sel;               // [frames][sel_per_frame] selected keypoints, list order
@@ -93,10 +90,6 @@ int orbx_fast_tile_rows();
 // TMA descriptors of the strip kernels: the levels as (pitch, h, frames) u8 tensors with the strip box (blur + dense FAST bound), and
 // level s - 1 with the source box of the resize tile that produces level s
 struct OrbxStripMaps { CUtensorMap level[ORBX_MAX_LEVELS]; };
-// the levels with the box of the cell-group FAST kernel: strip box width x (tallest cell interior + 6) rows
-struct OrbxGroupMaps { CUtensorMap level[ORBX_MAX_LEVELS]; int box_h; };
-int orbx_group_max_rows();        // tallest cell interior the group kernel takes
-int orbx_group_max_cols();        // widest run of cell interiors (incl. the up to 3 columns in front of it that word alignment adds)
 struct OrbxPyrMaps { CUtensorMap src[ORBX_MAX_LEVELS]; };
 // Tile rows of the strip kernels. which = 0: throughput tiles (ORBX_STRIP_TH / ORBX_PYR_TH, default 32); which = 1: the 8-row tiles used when
 // a launch covers at most ORBX_SMALL_BATCH frames (Tracking extracts one frame at a time: more, shorter warps cut the launch's latency)
@@ -112,7 +105,7 @@ void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int c
 void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
 void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st);
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], const OrbxGroupMaps& gmaps, cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);

@@ -61,7 +61,7 @@ def counts(rep, kernel, launch):
 def marker_phases():
     """//@phase <name> ... (next marker or //@end) in the kernel sources -> [name, file suffix, first line, last line]"""
     out = []
-    for fn in ('orbx_extract.cu', 'orbx_strip.cuh', 'orbx_fastgroup.cuh', 'orbx_describe.cuh'):
+    for fn in ('orbx_extract.cu', 'orbx_strip.cuh', 'orbx_describe.cuh'):
         cur = None
         for n, ln in enumerate(open(os.path.join(ROOT, 'orb_slam2_refactored_b200', 'csrc', fn)), 1):
             t = ln.strip()
