@@ -8,6 +8,10 @@
 //   * cvRound is one FADD with 1.5 * 2^23 (the rounded integer appears in the low mantissa bits, ties to even like cvRound's
 //     lrint), so the quarter-rate conversion pipe is not used and the bias folds into the patch base address.
 // Float semantics as before: every reference float op is an explicit round-to-nearest intrinsic.
+// (Blackwell's packed FP32 pairs — mul/fma.rn.f32x2, SASS FMUL2 / FFMA2 — would halve the rotation's float instructions, but ptxas 12.9
+// contracts mul.rn.f32x2 into a following add / fma(p, 1.0, q) even with -fmad=false, dropping a rounding the reference performs: one
+// descriptor bit in 300 000 differed on a noise image (tests/test_gpu_extract.py::test_noise_images_overflow_the_cell_list). Scalar
+// __fmul_rn / __fadd_rn are never contracted.)
 // =====================================================================================================
 #define OD2_IPS 48                   // un-blurred patch: 31 rows x 48 bytes from (x - 16) & ~15 (three 16-byte chunks: a copy instruction then spans ~11 rows,
                                      // 4-byte copies with one row per lane were measured 1.5x slower overall: 31 cache lines per instruction)
@@ -29,12 +33,6 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 	asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(saddr));
 	return v;
 }
-// Packed FP32 pairs (Blackwell FMUL2 / FFMA2 / FADD2): two independent IEEE round-to-nearest operations per instruction, bit-identical
-// to the scalar ones. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false (observed, CUDA 12.9), which would
-// drop a rounding the reference performs; so the sum of two rounded products is written fma(p1, 1.0, p2): exact product, one rounding.
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) { return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32); }
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ uint64_t f2_sum(uint64_t p1, uint64_t one, uint64_t p2) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(p1), "l"(one), "l"(p2)); return d; }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -90,13 +88,9 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 #pragma unroll
 		for (int k = 0; k < 8; k++) { const uint2 cf = __ldg(g_mom + k * 16 + av); mones[k] = cf.x; mus[k] = cf.y; }
 	}
-	uint64_t patx[8], paty[8];                     // (x0, x1), (y0, y1) of the pair's two points
+	float4 pat[8];
 #pragma unroll
-	for (int bit = 0; bit < 8; bit++)
-	{
-		const float4 pt = __ldg(g_patf + bit * 32 + lane);
-		patx[bit] = f2_pack(pt.x, pt.z); paty[bit] = f2_pack(pt.y, pt.w);
-	}
+	for (int bit = 0; bit < 8; bit++) pat[bit] = __ldg(g_patf + bit * 32 + lane);
 
 	auto bcast_ptr = [&](const uint8_t* p, int k) {
 		const unsigned long long v = (unsigned long long)p;
@@ -187,16 +181,15 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 		// shared address of sample (r, q) = base + r * BPS + q with r, q taken as the raw bits of the magic-rounded floats: the bias
 		// 0x4B400000 * (BPS + 1) is folded into the base, all in 32-bit modular arithmetic (shared addresses are 32 bits)
 		const uint32_t bl = (uint32_t)__cvta_generic_to_shared(od2_smem + (k & 1) * OD2_BUF + 18 * OD2_BPS + xo) - (uint32_t)OD2_MAGIC_BITS * (uint32_t)(OD2_BPS + 1);
-		// x b + y a and x a - y b for both points of a pair at once: every product and every sum rounded separately, as the reference's
-		// scalar code does (x a - y b = x a + y (-b) exactly); then the magic add
-		const uint64_t aa = f2_pack(a, a), bb = f2_pack(b, b), nb = f2_pack(-b, -b), one2 = f2_pack(1.f, 1.f), magic2 = f2_pack(OD2_MAGIC, OD2_MAGIC);
 		uint32_t byte = 0;
 #pragma unroll
 		for (int bit = 0; bit < 8; bit++)
 		{
-			const uint64_t r = f2_sum(f2_sum(f2_mul(patx[bit], bb), one2, f2_mul(paty[bit], aa)), one2, magic2);
-			const uint64_t q = f2_sum(f2_sum(f2_mul(patx[bit], aa), one2, f2_mul(paty[bit], nb)), one2, magic2);
-			const uint32_t r0 = (uint32_t)r, r1 = (uint32_t)(r >> 32), q0 = (uint32_t)q, q1 = (uint32_t)(q >> 32);
+			const float4 pt = pat[bit];
+			const uint32_t r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), OD2_MAGIC));
+			const uint32_t q0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), OD2_MAGIC));
+			const uint32_t r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)), OD2_MAGIC));
+			const uint32_t q1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)), OD2_MAGIC));
 			const uint32_t t0 = lds_u8(bl + r0 * OD2_BPS + q0), t1 = lds_u8(bl + r1 * OD2_BPS + q1);
 			byte |= (uint32_t)(t0 < t1) << bit;
 		}

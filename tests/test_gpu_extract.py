@@ -150,6 +150,23 @@ def test_tie_blocks_image(orbx, oracle_final):
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
 
 
+@pytest.mark.parametrize('lo,hi', [(0, 256), (100, 119), (96, 136), (90, 150)])
+def test_noise_images_overflow_the_cell_list(orbx, oracle_port, lo, hi):
+    # white noise flags most pixels of a cell: more than the cell kernel's list holds (FT_LIST_CAP), at iniTh ((0, 256)), only at
+    # minTh ((100, 119): no pixel can pass iniTh), or only once the minTh pixels join ((96, 136), (90, 150)) — the chunked passes
+    r = np.random.RandomState(hi)
+    img = r.randint(lo, hi, (240, 320)).astype(np.uint8)
+    ex = orbx.ORBextractor(nfeatures=1500)
+    k, d = ex.Extract(img)
+    o = oracle_port.extractor(1500)
+    ok, od = o.extract(img)
+    for s, pl in enumerate(o.pyramid()):
+        want = _as_xyr(oracle_port.detect_fast(pl))
+        got = ex.debug_candidates(0, s)
+        assert np.array_equal(got, want), f'FAST candidates differ at level {s}: {len(got)} vs {len(want)}'
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+
+
 def test_handle_survives_a_refused_size(orbx, oracle_final):
     # good extract, then a size the plan builder refuses, then the first size again on the SAME handle: the size cache must not
     # match a plan that the failed rebuild zeroed (illegal address and a sticky context error before the fix)
