@@ -100,3 +100,13 @@ def test_cos_sin_device_matches_host_sweep(orbx, oracle_port):
     d0 = desc[kps['octave'] == 0]
     for k, d in zip(lvl0[:200], d0[:200]):
         assert np.array_equal(oracle_port.descriptor(blur, int(k['x']), int(k['y']), k['angle']), d)
+
+
+def test_fuzz_extract_20_seconds():
+    # tools/fuzz_extract.py: random image kinds (noise, blocks, binary, ramps, checkerboards, saturated bands, rectangles), sizes and
+    # extractor parameters through the C ABI against the oracle, bit for bit
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_extract.py'), '20', '7'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert 'mismatches' in r.stdout and ' 0 mismatches' in r.stdout, r.stdout[-2000:]
