@@ -387,7 +387,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.out_cap = sels;
 	if (sels >= 65536)
 		return fail(ORBX_ERR_INVALID, "more than 65535 keypoints per frame");
-	if (orbx_quadtree_smem(P.node_cap) > 200 * 1024)
+	if (orbx_quadtree_smem(P.node_cap, true) > 200 * 1024)
 		return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree kernel's shared memory");
 
 	CU(cudaSetDevice(h->device));

@@ -590,15 +590,17 @@ int orbx_pyramid_max_src_rows() { return PY_SRC; }
 int orbx_pyramid_tile_cols() { return PY_TW; }
 int orbx_pyramid_max_src_bytes() { return PY_SW; }
 
-size_t orbx_quadtree_smem(int node_cap)
+size_t orbx_quadtree_smem(int node_cap, bool big)
 {
-	// listA, listB (16 B), items (8 B), childcnt (16 B), proc, pbase (4 B each), leaf (8 B), gone (1 B), 2 segment queues (12 B x cap/16)
-	return (size_t)node_cap * (16 + 16 + 8 + 16 + 4 + 4 + 8 + 1) + 2 * 12 * ((size_t)node_cap / 16 + 4) + 64;
+	// listA, listB (16 B), childcnt (16 B, its first half doubles as the sort items), proc, pbase (4 B each), gone (1 B); the CTA-parallel
+	// sort of the BIG variant adds leaf (8 B) and 2 segment queues (12 B x cap/16)
+	const size_t base = (size_t)node_cap * (16 + 16 + 16 + 4 + 4 + 1) + 64;
+	return big ? base + (size_t)node_cap * 8 + 2 * 12 * ((size_t)node_cap / 16 + 4) : base;
 }
 
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 {
-	const size_t smem = orbx_quadtree_smem(P.node_cap);
+	const size_t smem = orbx_quadtree_smem(P.node_cap, true), smem_plain = orbx_quadtree_smem(P.node_cap, false);
 	dim3 grid(P.frames, P.nlevels);
 	// Two variants: BIG replays std::sort with the whole CTA and partitions large nodes block-wide. It costs registers (61 vs 40),
 	// so it pays where one CTA's latency is what the launch waits for: levels that keep more than ~1000 keypoints (4K plans), and
@@ -633,11 +635,11 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		const int small_threads = small_env ? small_env : (P.frames >= 256 ? 128 : 256);
 		if (small_threads == 256)
 		{
-			qt256::k_quadtree<false><<<grid, 256, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 		}
 		else
 		{
-			qt128::k_quadtree<false><<<grid, 128, smem, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+			qt128::k_quadtree<false><<<grid, 128, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 		}
 	}
 	if (want_dbg)

@@ -110,7 +110,7 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);
 void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);
-size_t orbx_quadtree_smem(int node_cap);
+size_t orbx_quadtree_smem(int node_cap, bool big);
 int orbx_pyramid_tile_rows();
 int orbx_pyramid_max_src_rows();
 int orbx_pyramid_tile_cols();

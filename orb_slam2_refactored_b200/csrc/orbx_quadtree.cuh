@@ -228,13 +228,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	const int M = P.node_cap;
 	QNode* listA = reinterpret_cast<QNode*>(qsm);
 	QNode* listB = listA + M;
-	uint64_t* items = reinterpret_cast<uint64_t*>(listB + M);          // phase-2 sort items
-	uint32_t* childcnt = reinterpret_cast<uint32_t*>(items + M);       // [M][4]
+	uint32_t* childcnt = reinterpret_cast<uint32_t*>(listB + M);       // [M][4]
+	uint64_t* items = reinterpret_cast<uint64_t*>(childcnt);           // phase-2 sort items: dead (copied to proc) before the divide step writes childcnt
 	uint32_t* proc = childcnt + 4 * M;                                 // positions (old list) to divide, processing order
 	uint32_t* pbase = proc + M;                                        // exclusive scan of non-empty child counts
+	// the CTA-parallel sort's work lists exist only in the BIG variant: the plain one runs more CTAs per SM on the shared memory they would take
 	int2* leaf = reinterpret_cast<int2*>(pbase + M);                   // ranges (<= 16 items) left for the insertion pass of the sort
-	const int segcap = M / 16 + 4;
-	QSeg* segq = reinterpret_cast<QSeg*>(leaf + M);                    // [2][segcap] ranges still to be partitioned
+	const int segcap = BIG ? M / 16 + 4 : 0;
+	QSeg* segq = reinterpret_cast<QSeg*>(leaf + (BIG ? M : 0));        // [2][segcap] ranges still to be partitioned
 	uint8_t* gone = reinterpret_cast<uint8_t*>(segq + 2 * segcap);     // old-list positions removed by this pass
 	__shared__ int s_w[QT_WARPS];
 	__shared__ int s_K;
