@@ -129,7 +129,7 @@ struct orbx_extractor
 	int64_t l0_pitch = 0, l0_stride = 0;
 	uint8_t* l0base = nullptr;          // l0buf.p + 256: kernels may read up to 16 bytes in front of a row (aligned 16-byte tile copies)
 	DevBuf<uint32_t> cand, qbuf0, qbuf1, sel;
-	DevBuf<int> cell_count, cand_count, sel_count;
+	DevBuf<int> cell_count, cand_count, sel_count, pyr_done;
 	DevBuf<int> root_x, xofs, yofs;
 	DevBuf<uint8_t> root_lut;
 	DevBuf<short2> xcoef, ycoef;
@@ -399,7 +399,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(h->cand.ensure(F * cands)); CU(h->qbuf0.ensure(F * cands)); CU(h->qbuf1.ensure(F * cands));
 	CU(h->fmap_ini.ensure(F * (slab >> 3) + 64)); CU(h->fmap_min.ensure(F * (slab >> 3) + 64));
 	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
-	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl));
+	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl)); CU(h->pyr_done.ensure(F * ORBX_MAX_LEVELS));
 	CU(h->sel.ensure(F * sels));
 	CU(h->root_x.ensure(root_x.size())); CU(h->root_lut.ensure(root_lut.size()));
 	CU(h->xofs.ensure(std::max<size_t>(xofs.size(), 1))); CU(h->xcoef.ensure(std::max<size_t>(xcoef.size(), 1)));
@@ -421,7 +421,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.pyr = h->pyr.p + 256; P.blur = h->blur.p;
 	P.fmap_ini = h->fmap_ini.p; P.fmap_min = h->fmap_min.p;
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
-	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p;
+	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p; P.pyr_done = h->pyr_done.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
 	// TMA descriptors of every level as a (pitch, h, frames) u8 tensor, one per box shape (encode_level_maps)
@@ -493,7 +493,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
 	if (ev) CU(cudaEventRecord(ev[0], st));
-	for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, h->pmaps, s, st);
+	CU(orbx_launch_pyramid_all(P, h->pmaps, st));
 	if (ev) CU(cudaEventRecord(ev[1], st));
 	if (blur_inline)
 	{
@@ -598,7 +598,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (h->stream2) cudaStreamSynchronize(h->stream2);
 	h->l0buf.release(); h->color.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
-	h->cell_count.release(); h->cand_count.release(); h->sel_count.release();
+	h->cell_count.release(); h->cand_count.release(); h->sel_count.release(); h->pyr_done.release();
 	h->cell_tab.release(); h->fmap_ini.release(); h->fmap_min.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();

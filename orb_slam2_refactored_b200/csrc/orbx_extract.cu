@@ -470,6 +470,7 @@ cudaError_t orbx_kernels_init()
 	set(k_pyramid_strip<32>, 100 * 1024);
 	set(k_pyramid_strip<16>, 100 * 1024);
 	set(k_pyramid_strip<8>, 100 * 1024);
+	set(k_pyramid_all<32>, 100 * 1024); set(k_pyramid_all<16>, 100 * 1024); set(k_pyramid_all<8>, 100 * 1024);
 	set(k_fast_cells2, 64 * 1024);
 	set(k_level_strip<8, true, false>, 64 * 1024); set(k_level_strip<8, false, true>, 64 * 1024);
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024);
@@ -503,6 +504,41 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int l
 	// py_smem is sized for the 128-row tile: an upper bound for the 32-row one
 	if (small_batch) k_pyramid_resize<4><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 	else k_pyramid_resize<PY_RW><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
+}
+
+cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st)
+{
+	// One launch for a frame at a time (C1: 0.201 -> 0.193 ms per Extract call). For batches it was measured both ways: the pyramid stage
+	// alone gains 3 % (0.309 -> 0.300 ms per 512 frames), but the step as callers run it — two half-batches on two streams — loses 2 %
+	// (256.0 k -> 251.3 k frames/s): seven short launches per lane interleave better with the other lane's kernels than one long one.
+	static const int merged = env_int("ORBX_PYR_ONE", -1);     // tuning knob: 0 = one launch per level, 1 = always one launch
+	const int which = P.frames <= ORBX_SMALL_BATCH ? 1 : 0;
+	bool ok = (merged < 0 ? which == 1 : merged != 0) && P.nlevels > 2 && P.pyr_done;
+	for (int s = 1; s < P.nlevels && ok; s++) ok = P.lv[s].py_bw[which] > 0;
+	if (!ok)
+	{
+		for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, pmaps, s, st);
+		return cudaSuccess;
+	}
+	const int th = orbx_pyramid_strip_rows(which);
+	OrbxPyrTiles T = {};
+	T.which = which;
+	int smem = 0;
+	for (int s = 1; s < P.nlevels; s++)
+	{
+		const OrbxLevel& D = P.lv[s];
+		T.tx[s] = (D.w + ST_TW - 1) / ST_TW;
+		T.base[s + 1] = T.base[s] + T.tx[s] * ((D.h + th - 1) / th);
+		smem = std::max(smem, ((D.py_bw[which] * D.py_bh[which] + 127) & ~127) + 16);
+	}
+	for (int s = P.nlevels; s < ORBX_MAX_LEVELS; s++) T.base[s + 1] = T.base[s];
+	const cudaError_t e = cudaMemsetAsync(P.pyr_done + (int64_t)P.frame0 * ORBX_MAX_LEVELS, 0, sizeof(int) * ORBX_MAX_LEVELS * (size_t)P.frames, st);
+	if (e != cudaSuccess) return e;
+	const unsigned grid = (unsigned)T.base[P.nlevels] * (unsigned)P.frames;
+	if (th == 8) k_pyramid_all<8><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
+	else if (th == 16) k_pyramid_all<16><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
+	else k_pyramid_all<32><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
+	return cudaSuccess;
 }
 
 int orbx_fast_tile_stride() { return FT_TS; }

@@ -66,6 +66,7 @@ struct OrbxPlanDev
 	int* sel_count;              // [frames][nlevels]
 	const int* root_x; const uint8_t* root_lut;
 	const int* xofs; const short2* xcoef; const int* yofs; const short2* ycoef;   // resize tables
+	int* pyr_done;               // [frames of the plan][ORBX_MAX_LEVELS] tiles of a level finished in the current one-launch ComputePyramid
 };
 
 __device__ __forceinline__ const uint8_t* orbx_level_ptr(const OrbxPlanDev& P, int frame, int level)
@@ -105,6 +106,7 @@ void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int c
 void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
 void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st);
+cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st);   // every level; one launch where the plan allows
 void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);

@@ -283,16 +283,17 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 // 1-2 output rows that use it are produced. Box width <= 256 bytes limits this kernel to scale factors <= ~1.8; beyond that the
 // cp.async kernel (k_pyramid_resize) runs.
 // =====================================================================================================
+// one 128 x TH output tile of `level` of frame f; wait_src: spin (lane 0) until the source level is complete, see k_pyramid_all
 template <int TH>
-__global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const int level, const int bw, const int bh)
+__device__ __forceinline__ void pyramid_tile(const OrbxPlanDev& P, const OrbxPyrMaps& maps, uint8_t* py_smem, const int level, const int bw, const int bh,
+                                             const int tile_x, const int tile_y, const int f, const int* wait_src, const int wait_for)
 {
 	static_assert(TH <= 32, "lane k holds the table entry of tile row k");
-	extern __shared__ __align__(128) uint8_t py_smem[];
 	const OrbxLevel& D = P.lv[level];
 	uint64_t* const bar = reinterpret_cast<uint64_t*>(py_smem + ((bw * bh + 127) & ~127));
-	const int lane = threadIdx.x, f = blockIdx.z;
+	const int lane = threadIdx.x;
 	const int sh = P.lv[level - 1].h;
-	const int dx0 = blockIdx.x * ST_TW, dy0 = blockIdx.y * TH;
+	const int dx0 = tile_x * ST_TW, dy0 = tile_y * TH;
 	const int* __restrict__ yofs = P.yofs + D.ytab_base;
 	const int* __restrict__ xofs = P.xofs + D.xtab_base;
 	const int s_lo = __ldg(yofs + dy0);
@@ -301,6 +302,18 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 	{
 		mbar_init(bar, 1);
 		mbar_expect_tx(bar, (unsigned)(bw * bh));
+		if (wait_src)
+		{
+			// the source level is written by other CTAs of this launch: acquire its completion count, then order the copy engine's reads
+			// (async proxy) behind it. A lost count must not hang the device.
+			int seen, spins = 0;
+			do
+			{
+				asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(wait_src) : "memory");
+				if (seen < wait_for && ++spins > (1 << 22)) __trap();
+			} while (seen < wait_for);
+			asm volatile("fence.proxy.async.global;\n" ::: "memory");
+		}
 		tma_load_3d(py_smem, &maps.src[level], xa, s_lo, P.frame0 + f, bar);
 	}
 	// the lane's 4 columns: byte offset of the first source column, PRMT selectors of the (s[x], s[x+1]) pairs, packed coefficients
@@ -369,6 +382,44 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 		const uint32_t q01 = __byte_perm((uint32_t)s[0], (uint32_t)s[1], 0x5410) >> 2, q23 = __byte_perm((uint32_t)s[2], (uint32_t)s[3], 0x5410) >> 2;
 		if (store) *reinterpret_cast<uint32_t*>(dst) = __byte_perm(q01, q23, 0x6420);   // pitch is a multiple of 128: in-row padding absorbs the tail
 		dst += dpitch;
+	}
+}
+
+template <int TH>
+__global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const int level, const int bw, const int bh)
+{
+	extern __shared__ __align__(128) uint8_t py_smem[];
+	pyramid_tile<TH>(P, maps, py_smem, level, bw, bh, blockIdx.x, blockIdx.y, blockIdx.z, nullptr, 0);
+}
+
+// ComputePyramid as ONE launch: the tiles of levels 1 .. n-1 of every frame, level-major (every frame's level 1, then every frame's
+// level 2 ...). A tile of level s >= 2 needs level s - 1 of its own frame: the CTAs that produced it count themselves into
+// done[frame][s - 1] (release), the consumer's lane 0 spins on that count (acquire) before it issues its TMA load. CTAs are dispatched in
+// blockIdx order, so the producers of a tile are resident or finished before the tile starts: with 512 frames the count is there long
+// before it is needed, and for one frame the whole grid is resident at once. Seven dependent launches (and their tails: the three
+// smallest levels took 11 us each for 4 us of work) become one; a one-frame call saves six launch latencies.
+struct OrbxPyrTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int which; };   // base[s]: tiles per frame of the levels before s (base[1] = 0)
+template <int TH>
+__global__ void __launch_bounds__(32) k_pyramid_all(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const OrbxPyrTiles T, int* __restrict__ done)
+{
+	extern __shared__ __align__(128) uint8_t py_smem[];
+	const unsigned id = blockIdx.x, F = (unsigned)P.frames;
+	int level = 1;
+#pragma unroll
+	for (int s = 2; s < ORBX_MAX_LEVELS; s++)
+		if (s < P.nlevels && id >= (unsigned)T.base[s] * F) level = s;
+	const unsigned nt = (unsigned)(T.base[level + 1] - T.base[level]);
+	const unsigned rem = id - (unsigned)T.base[level] * F;
+	const unsigned f = rem / nt, tile = rem - f * nt;
+	const int tile_y = (int)(tile / (unsigned)T.tx[level]), tile_x = (int)tile - tile_y * T.tx[level];
+	int* const cnt = done + (int64_t)(P.frame0 + (int)f) * ORBX_MAX_LEVELS;
+	const OrbxLevel& D = P.lv[level];
+	pyramid_tile<TH>(P, maps, py_smem, level, D.py_bw[T.which], D.py_bh[T.which], tile_x, tile_y, (int)f, level > 1 ? cnt + level - 1 : nullptr,
+	                 T.base[level] - T.base[level - 1]);
+	if (level + 1 < P.nlevels)
+	{
+		__syncwarp();                                   // the warp's stores happen before lane 0's release
+		if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(cnt + level) : "memory");
 	}
 }
 
