@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = sys.argv[1] if len(sys.argv) > 1 else 'r02'
-FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 128      # frames in one captured launch (half of the bench command's --batch)
 G = os.path.join(ROOT, 'gpurun_out')
 P = os.path.join(ROOT, 'profiles')
 os.makedirs(P, exist_ok=True)
@@ -86,7 +86,7 @@ def step():
     for name, rs in groups.items():
         fn = name.replace('<', '_').replace('>', '').replace(', ', '_').replace('::', '_').replace(' ', '')
         with open(os.path.join(P, f'{R}_{fn}.txt'), 'w') as o:
-            o.write(f'# ncu --set full --clock-control none --import-source on, {len(rs)} launch(es) of {name} inside one device-resident step of {FRAMES} C1 frames\n')
+            o.write(f'# ncu --set full --clock-control none --import-source on, {len(rs)} launch(es) of {name} inside one device-resident half-batch ({FRAMES} C1 frames: an un-instrumented 256-frame step runs as two halves on two streams)\n')
             o.write(f'# command: {CMD} (tools/make_profiles.sh); times are cold-cache and serialised\n')
             for n, r in enumerate(rs):
                 if len(rs) > 1:
