@@ -653,7 +653,11 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		// costs no occupancy and its block-wide partition and parallel sort rounds use every warp
 		// (measured at 3840x2160 / 8000 kp, 32 frames: 256 thr 63.8 us per frame, 512 thr 53.7, 1024 thr 66.2)
 		static const int big_threads = getenv("ORBX_QT_THREADS") ? atoi(getenv("ORBX_QT_THREADS")) : 512;   // tuning knob: 256 or 512
-		if (large_plan && !small_batch && big_threads == 512)
+		// a frame at a time with more than ~300 keypoints per level (KITTI: 2000 per frame): the divide passes have more nodes than a
+		// 256-thread CTA has warps (one Extract call 0.329 -> 0.317 ms; at 1000 keypoints per frame no difference)
+		static const int small_threads_env = getenv("ORBX_QT_SMALL_THREADS") ? atoi(getenv("ORBX_QT_SMALL_THREADS")) : 0;   // tuning knob: 256 or 512
+		const int small_threads = small_threads_env ? small_threads_env : (P.node_cap > 320 ? 512 : 256);
+		if ((large_plan && !small_batch && big_threads == 512) || (small_batch && small_threads == 512))
 		{
 			qt512::k_quadtree<true><<<grid, 512, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
 		}
