@@ -140,6 +140,8 @@ struct orbx_extractor
 	DevBuf<int32_t> out_n;
 	int32_t* h_counts = nullptr;        // pinned staging for the per-frame counts (a pageable target would serialise the pipeline)
 	size_t h_counts_n = 0;
+	uint8_t* h_small = nullptr;         // pinned staging for the keypoints + descriptors of a small batch (a frame at a time): three queued copies and
+	size_t h_small_bytes = 0;           // one synchronisation instead of two blocking copies into the caller's pageable arrays
 	DevBuf<float> st_uright, st_depth;
 	DevBuf<int> st_sad, st_rows;
 	DevBuf<uint2> st_items;
@@ -604,6 +606,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release(); h->st_rows.release(); h->st_items.release();
 	if (h->h_counts) cudaFreeHost(h->h_counts);
+	if (h->h_small) cudaFreeHost(h->h_small);
 	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
 	if (h->fork) cudaEventDestroy(h->fork);
@@ -818,6 +821,19 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 		h->h_counts_n = (size_t)frames;
 	}
 	int32_t* counts = h->h_counts;
+	// a frame at a time: results go through pinned staging (the caller's arrays are usually pageable, and a device-to-pageable copy blocks)
+	const bool staged = frames <= ORBX_SMALL_BATCH && frames <= chunk && kps && desc && ccap > 0;
+	if (staged)
+	{
+		const size_t need_bytes = (size_t)frames * ocap * (sizeof(orbx_keypoint) + 32);
+		if (h->h_small_bytes < need_bytes)
+		{
+			if (h->h_small) cudaFreeHost(h->h_small);
+			h->h_small = nullptr; h->h_small_bytes = 0;
+			CU(cudaMallocHost(&h->h_small, need_bytes));
+			h->h_small_bytes = need_bytes;
+		}
+	}
 	// the per-frame buffers are shared with whatever an earlier asynchronous call (orbx_extract_batch_device, stereo) left pending on the
 	// handle's stream: the second lane starts behind it
 	CU(cudaEventRecord(h->fork, h->stream));
@@ -865,7 +881,13 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
 		if (e != ORBX_OK) return e;
 		CU(cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st));
-		if (kps && desc && ccap > 0)
+		if (staged)
+		{
+			// whole capacity rows of this (only) chunk, contiguous: keypoints, then descriptors
+			CU(cudaMemcpyAsync(h->h_small, h->out_kps.p, sizeof(orbx_keypoint) * (size_t)ocap * frames, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(h->h_small + sizeof(orbx_keypoint) * (size_t)ocap * frames, h->out_desc.p, (size_t)32 * ocap * frames, cudaMemcpyDeviceToHost, st));
+		}
+		else if (kps && desc && ccap > 0)
 		{
 			CU(cudaMemcpy2DAsync(kps + (size_t)fb * cap, sizeof(orbx_keypoint) * (size_t)cap, h->out_kps.p + (size_t)fb * ocap,
 			                     sizeof(orbx_keypoint) * (size_t)ocap, sizeof(orbx_keypoint) * (size_t)ccap, fc, cudaMemcpyDeviceToHost, st));
@@ -878,6 +900,16 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 	note_result(h, frames, ocap, h->out_kps.p, h->out_desc.p, h->out_n.p);
 	int need = 0;
 	for (int f = 0; f < frames; f++) { n[f] = counts[f]; need = std::max(need, counts[f]); }
+	if (staged)
+	{
+		const uint8_t* sk = h->h_small; const uint8_t* sd = h->h_small + sizeof(orbx_keypoint) * (size_t)ocap * frames;
+		for (int f = 0; f < frames; f++)
+		{
+			const size_t rows = (size_t)std::min(counts[f], ccap);
+			std::memcpy(kps + (size_t)f * cap, sk + sizeof(orbx_keypoint) * (size_t)ocap * f, sizeof(orbx_keypoint) * rows);
+			std::memcpy(desc + (size_t)f * cap * 32, sd + (size_t)32 * ocap * f, 32 * rows);
+		}
+	}
 	if (need > cap || (need > 0 && (!kps || !desc)))
 		return fail(ORBX_ERR_CAPACITY, "output buffers hold fewer keypoints than were found");
 	return ORBX_OK;
