@@ -836,8 +836,12 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 	}
 	// the per-frame buffers are shared with whatever an earlier asynchronous call (orbx_extract_batch_device, stereo) left pending on the
 	// handle's stream: the second lane starts behind it
-	CU(cudaEventRecord(h->fork, h->stream));
-	CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
+	const bool two_streams = frames > chunk;          // a single chunk (a frame at a time) never touches the second stream
+	if (two_streams)
+	{
+		CU(cudaEventRecord(h->fork, h->stream));
+		CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
+	}
 	int ci = 0;
 	for (int fb = 0; fb < frames; fb += chunk, ci++)
 	{
@@ -896,7 +900,7 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 		}
 	}
 	CU(cudaStreamSynchronize(h->stream));
-	CU(cudaStreamSynchronize(h->stream2));
+	if (two_streams) CU(cudaStreamSynchronize(h->stream2));
 	note_result(h, frames, ocap, h->out_kps.p, h->out_desc.p, h->out_n.p);
 	int need = 0;
 	for (int f = 0; f < frames; f++) { n[f] = counts[f]; need = std::max(need, counts[f]); }
