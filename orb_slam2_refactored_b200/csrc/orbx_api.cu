@@ -105,6 +105,8 @@ struct orbx_extractor
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr;     // second lane of the chunk pipeline of the host-buffer API
+	cudaStream_t copy_in = nullptr;     // uploads of the chunk pipeline: every chunk has its own region of the level-0 buffer, so the uploads of a call
+	std::vector<cudaEvent_t> ev_in;     // queue back to back here and the host-to-device engine never waits for a lane's kernels; one event per chunk
 	cudaEvent_t done = nullptr;
 	cudaEvent_t fork = nullptr, join = nullptr;   // order the second lane inside the handle's stream for the device-resident API
 	cudaStream_t side[2] = { nullptr, nullptr };  // per lane: the blur runs here, beside the quadtree (latency-bound, leaves the SMs half empty)
@@ -572,6 +574,7 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 	build_tables(h);
 	cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming);
@@ -613,6 +616,8 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (h->join) cudaEventDestroy(h->join);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	if (h->stream2) cudaStreamDestroy(h->stream2);
+	if (h->copy_in) { cudaStreamSynchronize(h->copy_in); cudaStreamDestroy(h->copy_in); }
+	for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
 	for (int l = 0; l < 2; l++)
 	{
 		if (h->side[l]) { cudaStreamSynchronize(h->side[l]); cudaStreamDestroy(h->side[l]); }
@@ -837,16 +842,30 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 	// the per-frame buffers are shared with whatever an earlier asynchronous call (orbx_extract_batch_device, stereo) left pending on the
 	// handle's stream: the second lane starts behind it
 	const bool two_streams = frames > chunk;          // a single chunk (a frame at a time) never touches the second stream
+	static const bool split_upload = getenv("ORBX_NO_COPY_STREAM") == nullptr;      // tuning knob
+	const bool own_upload = two_streams && split_upload;
 	if (two_streams)
 	{
 		CU(cudaEventRecord(h->fork, h->stream));
 		CU(cudaStreamWaitEvent(h->stream2, h->fork, 0));
+		if (own_upload)
+		{
+			CU(cudaStreamWaitEvent(h->copy_in, h->fork, 0));
+			const size_t nchunks = (size_t)((frames + chunk - 1) / chunk);
+			while (h->ev_in.size() < nchunks)
+			{
+				cudaEvent_t e;
+				CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+				h->ev_in.push_back(e);
+			}
+		}
 	}
 	int ci = 0;
 	for (int fb = 0; fb < frames; fb += chunk, ci++)
 	{
 		const int fc = std::min(chunk, frames - fb);
-		cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
+		const cudaStream_t lane_st = (ci & 1) ? h->stream2 : h->stream;
+		cudaStream_t st = own_upload ? h->copy_in : lane_st;        // the uploads; the conversion kernels behind them stay on the lane
 		if (rectify)
 		{
 			// the rectification remap (Examples/Stereo/stereo_euroc.cc:100-101) fused into the upload: raw frames land in a staging
@@ -855,8 +874,9 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 			for (int f = fb; f < fb + fc; f++)
 				CU(cudaMemcpy2DAsync(h->color.p + (size_t)f * rstride, raw_w, images + (size_t)f * frame_stride, pitch, raw_w, raw_h,
 				                     cudaMemcpyHostToDevice, st));
+			if (own_upload) { CU(cudaEventRecord(h->ev_in[ci], st)); CU(cudaStreamWaitEvent(lane_st, h->ev_in[ci], 0)); }
 			orbx_launch_remap(h->color.p + (size_t)fb * rstride, raw_w, (int64_t)rstride, raw_w, raw_h, h->rect_tab.p,
-			                  h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, h->l0_stride, width, height, fc, st);
+			                  h->l0base + (int64_t)fb * h->l0_stride, h->l0_pitch, h->l0_stride, width, height, fc, lane_st);
 		}
 		else if (channels == 1)
 		{
@@ -867,6 +887,7 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 				for (int f = fb; f < fb + fc; f++)
 					CU(cudaMemcpy2DAsync(h->l0base + (int64_t)f * h->l0_stride, h->l0_pitch, images + (size_t)f * frame_stride, pitch, width,
 					                     height, cudaMemcpyHostToDevice, st));
+			if (own_upload) { CU(cudaEventRecord(h->ev_in[ci], st)); CU(cudaStreamWaitEvent(lane_st, h->ev_in[ci], 0)); }
 		}
 		else
 		{
@@ -876,10 +897,11 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 			for (int f = fb; f < fb + fc; f++)
 				CU(cudaMemcpy2DAsync(h->color.p + (size_t)f * cstride, cpitch, images + (size_t)f * frame_stride, pitch, cpitch, height,
 				                     cudaMemcpyHostToDevice, st));
+			if (own_upload) { CU(cudaEventRecord(h->ev_in[ci], st)); CU(cudaStreamWaitEvent(lane_st, h->ev_in[ci], 0)); }
 			orbx_launch_gray(h->color.p + (size_t)fb * cstride, (int64_t)cpitch, (int64_t)cstride, channels, rgb, h->l0base + (int64_t)fb * h->l0_stride,
-			                 h->l0_pitch, h->l0_stride, width, height, fc, st);
+			                 h->l0_pitch, h->l0_stride, width, height, fc, lane_st);
 		}
-		st = (ci & 1) ? h->stream2 : h->stream;
+		st = lane_st;
 		// (Replaying the ~12 launches of a one-frame call as a CUDA graph was measured: 0.212 vs 0.203 ms per call — the call is bound by the
 		// GPU's dependent chain (quadtree 54 us, 7 pyramid levels 33 us), not by launch overhead, which the host hides behind it.)
 		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
