@@ -110,3 +110,13 @@ def test_fuzz_extract_20_seconds():
     r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_extract.py'), '20', '7'], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert 'mismatches' in r.stdout and ' 0 mismatches' in r.stdout, r.stdout[-2000:]
+
+
+def test_fuzz_stereo_15_seconds():
+    # tools/fuzz_stereo.py: random stereo pairs (size, disparity, noise, keypoint budget, camera, low-texture variants) through Extract
+    # left + right and the resident ComputeStereoMatches against the oracle, uright / depth byte for byte
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_stereo.py'), '15', '5'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert ' 0 mismatches' in r.stdout, r.stdout[-2000:]
