@@ -629,9 +629,10 @@ int orbx_pyramid_max_src_bytes() { return PY_SW; }
 size_t orbx_quadtree_smem(int node_cap, bool big)
 {
 	// listA, listB (16 B), childcnt (16 B, its first half doubles as the sort items), proc, pbase (4 B each), gone (1 B); the CTA-parallel
-	// sort of the BIG variant adds leaf (8 B) and 2 segment queues (12 B x cap/16)
+	// sort of the BIG variant adds its leaf ranges (4 B x cap/2) and 2 segment queues (12 B x cap/16). 59 B per node: the 1748 nodes of a 4K
+	// level 0 take 104 KB, so TWO 512-thread CTAs share an SM (at 65 B they did not)
 	const size_t base = (size_t)node_cap * (16 + 16 + 16 + 4 + 4 + 1) + 64;
-	return big ? base + (size_t)node_cap * 8 + 2 * 12 * ((size_t)node_cap / 16 + 4) : base;
+	return big ? base + 4 * (((size_t)node_cap / 2 + 2) & ~(size_t)1) + 2 * 12 * ((size_t)node_cap / 16 + 4) + 16 : base;
 }
 
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)

@@ -90,7 +90,7 @@ __device__ __forceinline__ int block_exscan(int n, int* s_w, Get get, Put put)
 // Time is ~2n serial steps (n + n/2 + n/4 ...) instead of ~1.4 n log2 n.
 struct QSeg { int first, last, depth; };
 
-__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, int2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */)
+__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, ushort2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */)
 {
 	const int tid = threadIdx.x;
 	if (tid == 0)
@@ -99,7 +99,7 @@ __device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int s
 		for (int m = n; m > 1; m >>= 1) ++lg;
 		s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
 		if (n > 16) { segq[0] = { 0, n, 2 * lg }; s_cnt[0] = 1; }
-		else if (n > 1) { leaf[0] = make_int2(0, n); s_cnt[2] = 1; }
+		else if (n > 1) { leaf[0] = make_ushort2(0, (unsigned short)n); s_cnt[2] = 1; }
 	}
 	__syncthreads();
 	int cur = 0;
@@ -122,7 +122,7 @@ __device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int s
 			{
 				const int f0 = side ? cut : sg.first, l0 = side ? sg.last : cut;
 				if (l0 - f0 > 16) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = { f0, l0, sg.depth - 1 };
-				else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_int2(f0, l0);
+				else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_ushort2((unsigned short)f0, (unsigned short)l0);
 			}
 		}
 		__syncthreads();
@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	uint32_t* proc = childcnt + 4 * M;                                 // positions (old list) to divide, processing order
 	uint32_t* pbase = proc + M;                                        // exclusive scan of non-empty child counts
 	// the CTA-parallel sort's work lists exist only in the BIG variant: the plain one runs more CTAs per SM on the shared memory they would take
-	int2* leaf = reinterpret_cast<int2*>(pbase + M);                   // ranges (<= 16 items) left for the insertion pass of the sort
+	ushort2* leaf = reinterpret_cast<ushort2*>(pbase + M);             // ranges (2 .. 16 items, so at most M / 2 of them; M < 65536) left for the insertion pass of the sort
 	const int segcap = BIG ? M / 16 + 4 : 0;
-	QSeg* segq = reinterpret_cast<QSeg*>(leaf + (BIG ? M : 0));        // [2][segcap] ranges still to be partitioned
+	QSeg* segq = reinterpret_cast<QSeg*>(leaf + (BIG ? (M / 2 + 2) & ~1 : 0));   // [2][segcap] ranges still to be partitioned
 	uint8_t* gone = reinterpret_cast<uint8_t*>(segq + 2 * segcap);     // old-list positions removed by this pass
 	__shared__ int s_w[QT_WARPS];
 	__shared__ int s_K;
