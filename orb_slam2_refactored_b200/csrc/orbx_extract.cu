@@ -311,6 +311,11 @@ __device__ __forceinline__ int arc_score_packed(const uint8_t* __restrict__ c) {
 #include "orbx_quadtree.cuh"
 #undef QT_THREADS
 #undef QT_NS
+#define QT_THREADS 96
+#define QT_NS qt96
+#include "orbx_quadtree.cuh"
+#undef QT_THREADS
+#undef QT_NS
 // =====================================================================================================
 // K5+K7  orient_describe — IC_Angle (src/ORBextractor.cc:74-101) on the un-blurred level, then
 //     ComputeOrbDescriptor (:103-140) on the blurred level, then the keypoint record of Extract (:768-773,
@@ -476,7 +481,7 @@ cudaError_t orbx_kernels_init()
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024);
 	set(k_level_strip<32, true, false>, 64 * 1024); set(k_level_strip<32, false, true>, 64 * 1024);
 	set(k_level_strip<64, true, false>, 64 * 1024); set(k_level_strip<64, false, true>, 64 * 1024);
-	set(qt128::k_quadtree<false>, QT_SMEM_MAX); set(qt256::k_quadtree<false>, QT_SMEM_MAX);
+	set(qt128::k_quadtree<false>, QT_SMEM_MAX); set(qt256::k_quadtree<false>, QT_SMEM_MAX); set(qt96::k_quadtree<false>, QT_SMEM_MAX);
 	set(qt256::k_quadtree<true>, QT_SMEM_MAX); set(qt512::k_quadtree<true>, QT_SMEM_MAX);
 	set(k_orient_describe2<8>, OD2_SMEM); set(k_orient_describe2<2>, OD2_SMEM);
 	return e;
@@ -669,14 +674,21 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	}
 	else
 	{
-		// launches of >= 256 frames (>= 2048 CTAs): 128-thread CTAs, so that more of them share an SM while others are in their serial
-		// phases; below that the SMs are not full and the CTA's own speed counts. Measured frames/s with 128 / 256 threads, one launch per
+		// launches of >= 256 frames (>= 2048 CTAs): small CTAs, so that more of them share an SM while others are in their serial phases;
+		// below that the SMs are not full and the CTA's own speed counts. Measured frames/s with 128 / 256 threads, one launch per
 		// stage: 32 frames 83.2 k / 89.0 k, 128 frames 136.8 k / 142.3 k, 256 frames 165.8 k / 162.9 k, 512 frames 177.4 k / 174.6 k.
-		static const int small_env = getenv("ORBX_QT_SMALL") ? atoi(getenv("ORBX_QT_SMALL")) : 0;   // tuning knob: 128 or 256
-		const int small_threads = small_env ? small_env : (P.frames >= 256 ? 128 : 256);
+		// 96 threads from 512 frames (>= 4096 CTAs, 1.7 waves): 40 registers x 96 threads and 57 B of shared memory per node allow 16 CTAs
+		// per SM where 128 threads get 12 (quadtree stage 0.268 -> 0.255 ms per 512 frames; at 256 frames per launch 128 threads are as
+		// fast or faster: 0.203 vs 0.221 ms at the EuRoC shape).
+		static const int small_env = getenv("ORBX_QT_SMALL") ? atoi(getenv("ORBX_QT_SMALL")) : 0;   // tuning knob: 96, 128 or 256
+		const int small_threads = small_env ? small_env : (P.frames >= 512 ? 96 : P.frames >= 256 ? 128 : 256);
 		if (small_threads == 256)
 		{
 			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+		}
+		else if (small_threads == 96)
+		{
+			qt96::k_quadtree<false><<<grid, 96, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
 		}
 		else
 		{
