@@ -39,7 +39,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // G = keypoints per warp: 8 for throughput; 2 when a frame at a time is extracted (the launch then has four times the warps and a
 // quarter of the serial chain per warp)
 template <int G>
-__global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps, uint8_t* __restrict__ d_desc,
+__global__ void __launch_bounds__(32, 32) k_orient_describe2(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps, uint8_t* __restrict__ d_desc,
                                                         int32_t* __restrict__ d_n)
 {
 	extern __shared__ __align__(16) uint8_t od2_smem[];
@@ -88,10 +88,6 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 #pragma unroll
 		for (int k = 0; k < 8; k++) { const uint2 cf = __ldg(g_mom + k * 16 + av); mones[k] = cf.x; mus[k] = cf.y; }
 	}
-	float4 pat[8];
-#pragma unroll
-	for (int bit = 0; bit < 8; bit++) pat[bit] = __ldg(g_patf + bit * 32 + lane);
-
 	auto bcast_ptr = [&](const uint8_t* p, int k) {
 		const unsigned long long v = (unsigned long long)p;
 		const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, k), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), k);
@@ -164,6 +160,11 @@ __global__ void __launch_bounds__(32, 24) k_orient_describe2(const OrbxPlanDev P
 	};
 	stage_blr(0);
 	if (nk > 1) stage_blr(1);
+	// the lane's 8 BRIEF pairs, loaded only now: phase 1's coefficient words are dead, so the two sets of constants never hold registers
+	// at the same time (80 -> 64 registers, 32 instead of 24 resident warps); the loads fly during the angle / cos / sin below
+	float4 pat[8];
+#pragma unroll
+	for (int bit = 0; bit < 8; bit++) pat[bit] = __ldg(g_patf + bit * 32 + lane);
 	float angle = 0.f, ca = 0.f, sb = 0.f;
 	if (lane < nk)
 	{
