@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// G = keypoints per warp: 8 for throughput; 2 when a frame at a time is extracted (the launch then has four times the warps and a
+// G = keypoints per warp: 16 (or 8) for throughput; 2 when a frame at a time is extracted (the launch then has four times the warps and a
 // quarter of the serial chain per warp)
 template <int G>
 __global__ void __launch_bounds__(32, 32) k_orient_describe2(const OrbxPlanDev P, orbx_keypoint* __restrict__ d_kps, uint8_t* __restrict__ d_desc,
