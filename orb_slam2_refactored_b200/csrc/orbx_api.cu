@@ -131,7 +131,8 @@ struct orbx_extractor
 	int64_t l0_pitch = 0, l0_stride = 0;
 	uint8_t* l0base = nullptr;          // l0buf.p + 256: kernels may read up to 16 bytes in front of a row (aligned 16-byte tile copies)
 	DevBuf<uint32_t> cand, qbuf0, qbuf1, sel;
-	DevBuf<int> cell_count, cand_count, sel_count, pyr_done;
+	DevBuf<int> cell_count, cand_count, sel_count, pyr_done, ovf_count;
+	DevBuf<uint32_t> ovf_list;          // cells left to the overflow launch of the FAST cell kernel, one region per frame range
 	DevBuf<int> root_x, xofs, yofs;
 	DevBuf<uint8_t> root_lut;
 	DevBuf<short2> xcoef, ycoef;
@@ -404,6 +405,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	CU(h->fmap_ini.ensure(F * (slab >> 3) + 64)); CU(h->fmap_min.ensure(F * (slab >> 3) + 64));
 	CU(h->cell_count.ensure(2 * F * cells));      // counts, then offsets
 	CU(h->cand_count.ensure(F * nl)); CU(h->sel_count.ensure(F * nl)); CU(h->pyr_done.ensure(F * ORBX_MAX_LEVELS));
+	CU(h->ovf_list.ensure(F * cells)); CU(h->ovf_count.ensure(2));
 	CU(h->sel.ensure(F * sels));
 	CU(h->root_x.ensure(root_x.size())); CU(h->root_lut.ensure(root_lut.size()));
 	CU(h->xofs.ensure(std::max<size_t>(xofs.size(), 1))); CU(h->xcoef.ensure(std::max<size_t>(xcoef.size(), 1)));
@@ -426,6 +428,7 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 	P.fmap_ini = h->fmap_ini.p; P.fmap_min = h->fmap_min.p;
 	P.cand = h->cand.p; P.cell_count = h->cell_count.p; P.qbuf0 = h->qbuf0.p; P.qbuf1 = h->qbuf1.p;
 	P.cand_count = h->cand_count.p; P.sel = h->sel.p; P.sel_count = h->sel_count.p; P.pyr_done = h->pyr_done.p;
+	P.ovf_list = h->ovf_list.p; P.ovf_count = h->ovf_count.p;
 	P.root_x = h->root_x.p; P.root_lut = h->root_lut.p; P.cell_tab = h->cell_tab.p;
 	P.xofs = h->xofs.p; P.xcoef = h->xcoef.p; P.yofs = h->yofs.p; P.ycoef = h->ycoef.p;
 	// TMA descriptors of every level as a (pitch, h, frames) u8 tensor, one per box shape (encode_level_maps)
@@ -472,6 +475,7 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	P.pyr += (int64_t)fb * P.slab; P.blur += (int64_t)fb * P.slab;
 	P.cand += (int64_t)fb * P.cand_per_frame; P.qbuf0 += (int64_t)fb * P.cand_per_frame; P.qbuf1 += (int64_t)fb * P.cand_per_frame;
 	P.cell_count += (int64_t)fb * P.cells_per_frame;
+	P.ovf_list += (int64_t)fb * P.cells_per_frame; P.ovf_count += st == h->stream2 ? 1 : 0;      // the two lanes run at the same time
 	P.cand_count += (int64_t)fb * P.nlevels; P.sel_count += (int64_t)fb * P.nlevels;
 	P.sel += (int64_t)fb * P.sel_per_frame;
 	d_kps += (int64_t)fb * cap; d_desc += (int64_t)fb * cap * 32; d_n += fb;
@@ -603,7 +607,7 @@ orbx_status orbx_destroy(orbx_handle h)
 	if (h->stream2) cudaStreamSynchronize(h->stream2);
 	h->l0buf.release(); h->color.release();
 	h->pyr.release(); h->blur.release(); h->cand.release(); h->qbuf0.release(); h->qbuf1.release(); h->sel.release();
-	h->cell_count.release(); h->cand_count.release(); h->sel_count.release(); h->pyr_done.release();
+	h->cell_count.release(); h->cand_count.release(); h->sel_count.release(); h->pyr_done.release(); h->ovf_list.release(); h->ovf_count.release();
 	h->cell_tab.release(); h->fmap_ini.release(); h->fmap_min.release();
 	h->root_x.release(); h->xofs.release(); h->yofs.release(); h->root_lut.release(); h->xcoef.release(); h->ycoef.release();
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();

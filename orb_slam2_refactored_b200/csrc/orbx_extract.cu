@@ -476,7 +476,7 @@ cudaError_t orbx_kernels_init()
 	set(k_pyramid_strip<16>, 100 * 1024);
 	set(k_pyramid_strip<8>, 100 * 1024);
 	set(k_pyramid_all<32>, 100 * 1024); set(k_pyramid_all<16>, 100 * 1024); set(k_pyramid_all<8>, 100 * 1024);
-	set(k_fast_cells2, 64 * 1024);
+	set(k_fast_cells2, 64 * 1024); set(k_fast_cells2_overflow, 64 * 1024);
 	set(k_level_strip<8, true, false>, 64 * 1024); set(k_level_strip<8, false, true>, 64 * 1024);
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024);
 	set(k_level_strip<32, true, false>, 64 * 1024); set(k_level_strip<32, false, true>, 64 * 1024);
@@ -607,14 +607,32 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	cell_extents(P, maps, rows, maxrw, maxrh);
 	// tile | score (1 px zero border) | list of pixels to score | survivor bitmap | mbarrier
 	const int ts = FT_TS;
-	OrbxCellLayout Y;
-	Y.score_stride = (maxrw + 2 + 7) & ~7;
-	Y.off_score = (rows * ts + 15) & ~15;
-	Y.off_list = (Y.off_score + (maxrh + 2) * Y.score_stride + 15) & ~15;
-	Y.off_bm = (Y.off_list + maxrw * maxrh * 2 + 15) & ~15;
-	Y.off_bar = Y.off_bm + 8 * maxrh;
-	Y.warp_bytes = (Y.off_bar + 8 + 127) & ~127;
+	auto layout = [&](int list_cap) {
+		OrbxCellLayout Y;
+		Y.score_stride = (maxrw + 2 + 7) & ~7;
+		Y.off_score = (rows * ts + 15) & ~15;
+		Y.off_list = (Y.off_score + (maxrh + 2) * Y.score_stride + 15) & ~15;
+		Y.list_cap = list_cap;
+		Y.off_bm = (Y.off_list + list_cap * 2 + 15) & ~15;
+		Y.off_bar = Y.off_bm + 8 * maxrh;
+		Y.warp_bytes = (Y.off_bar + 8 + 127) & ~127;
+		return Y;
+	};
+	const int full = maxrw * maxrh;
 	dim3 grid(P.cells_per_frame, P.frames);
+	// Throughput launches run with the short list (32 instead of 26 resident warps) and leave the rare cell that flags more pixels to a
+	// second, tiny launch; a frame at a time keeps the full list and the single launch (the GPU is far from full there).
+	static const int short_list = env_int("ORBX_SHORT_LIST", 1);      // tuning knob
+	if (short_list && P.frames > ORBX_SMALL_BATCH && full > FT_LIST_CAP && P.ovf_list)
+	{
+		cudaMemsetAsync(P.ovf_count, 0, sizeof(int), st);
+		const OrbxCellLayout Y = layout(FT_LIST_CAP);
+		k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
+		const OrbxCellLayout Yf = layout(full);
+		k_fast_cells2_overflow<<<592, 32, Yf.warp_bytes, st>>>(P, maps, Yf);
+		return;
+	}
+	const OrbxCellLayout Y = layout(full);
 	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 

@@ -67,6 +67,7 @@ struct OrbxPlanDev
 	const int* root_x; const uint8_t* root_lut;
 	const int* xofs; const short2* xcoef; const int* yofs; const short2* ycoef;   // resize tables
 	int* pyr_done;               // [frames of the plan][ORBX_MAX_LEVELS] tiles of a level finished in the current one-launch ComputePyramid
+	uint32_t* ovf_list; int* ovf_count;   // cells of this launch whose flagged pixels did not fit the cell kernel's list (frame * cells_per_frame + cell)
 };
 
 __device__ __forceinline__ const uint8_t* orbx_level_ptr(const OrbxPlanDev& P, int frame, int level)

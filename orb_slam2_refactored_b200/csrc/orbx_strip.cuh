@@ -429,19 +429,25 @@ __global__ void __launch_bounds__(32) k_pyramid_all(const OrbxPlanDev P, const _
 // for those pixels, finds strict 8-neighbour maxima above iniTh, retries at minTh when the cell has none (:526-530), and emits
 // in cv::FAST's row-major order. The cell view comes in by one TMA tile load, as before.
 // =====================================================================================================
+#define FT_LIST_CAP 512          // entries of the pixel list in throughput launches. A cell of the synthetic frames flags 80 (U > iniTh) to 400 (U > minTh,
+                                 // weak texture) pixels; the worst case, every pixel of a 37 x 34 cell, would take 2.5 KB per warp: 26 instead of 32
+                                 // resident warps. A cell with more (noise images) records itself and is redone by k_fast_cells2_overflow.
 struct OrbxCellLayout
 {
 	int score_stride;            // bytes per score row (region width + 2, rounded up to 8)
 	int off_score, off_list, off_bm, off_bar;
+	int list_cap;                // entries the list holds
 	int warp_bytes;
 };
 
-__global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
+// One cell. REDO = false: the usual launch; a cell whose flagged pixels do not fit the list appends itself to P.ovf_list and returns
+// before it has written anything. REDO = true: the overflow launch, whose list holds a whole cell.
+template <bool REDO>
+__device__ __forceinline__ void fast_cell(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxCellLayout& Y, uint8_t* fw_smem, const int cell, const int f,
+                                          const unsigned parity)
 {
 	//@phase cell table, TMA issue
-	extern __shared__ __align__(128) uint8_t fw_smem[];
 	const int lane = threadIdx.x;
-	const int cell = blockIdx.x, f = blockIdx.y;
 	uint8_t* const tile = fw_smem;
 	uint8_t* const score = fw_smem + Y.off_score;
 	uint16_t* const list = reinterpret_cast<uint16_t*>(fw_smem + Y.off_list);
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	const int sh = x0 & 15;                           // the TMA box starts 16-byte aligned
 	if (lane == 0)
 	{
-		mbar_init(tma_bar, 1);
+		if (!REDO) mbar_init(tma_bar, 1);             // the overflow kernel walks a list of cells: it initialises the barrier once
 		mbar_expect_tx(tma_bar, (unsigned)(FT_TS * maps.box_h[lvl]));
 		tma_load_3d(tile, &maps.level[lvl], x0 - sh, y0, P.frame0 + f, tma_bar);
 	}
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		if (lane + 32 < rh) reinterpret_cast<uint2*>(bm_sel)[lane + 32] = make_uint2(0, 0);
 	}
 	__syncwarp();
-	mbar_wait(tma_bar, 0);
+	mbar_wait(tma_bar, parity);
 
 	const int tmin = P.min_th, tini = P.ini_th;
 	const uint8_t* __restrict__ t0 = tile + 3 * FT_TS + sh + 3;
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 		int o0, o1 = 0, total;
 		if (tall) scan2(__popc(w[0]) + __popc(w[1]), __popc(w[2]) + __popc(w[3]), o0, o1, total);
 		else scan1(__popc(w[0]) + __popc(w[1]), o0, total);
+		if (!REDO && at + total > Y.list_cap) return -1;           // does not fit: nothing written
 #pragma unroll
 		for (int k = 0; k < 4; k++)
 		{
@@ -579,13 +586,18 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 
 	//@phase iniTh pass, retry decision, minTh pass (control flow)
 	// exact scores + maxima at iniTh; retry at minTh if the cell has no corner (:526-530)
+	auto overflow = [&]() {                            // leave the cell to the overflow launch (nothing of it has been written yet)
+		if (lane == 0) P.ovf_list[atomicAdd(P.ovf_count, 1)] = (uint32_t)f * (uint32_t)P.cells_per_frame + (uint32_t)cell;
+	};
 	const int n1 = expand(wa, 0);
+	if (!REDO && n1 < 0) { overflow(); return; }
 	__syncwarp();
 	evaluate(0, n1);
 	__syncwarp();
 	if (!__any_sync(0xffffffffu, select(n1, tini)))
 	{
 		const int n2 = expand(wb, n1);
+		if (!REDO && n2 < 0) { overflow(); return; }
 		__syncwarp();
 		evaluate(n1, n1 + n2);
 		__syncwarp();
@@ -626,5 +638,29 @@ __global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const _
 	}
 	if (lane == 0)
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
+}
+
+__global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
+{
+	extern __shared__ __align__(128) uint8_t fw_smem[];
+	fast_cell<false>(P, maps, Y, fw_smem, blockIdx.x, blockIdx.y, 0u);
+}
+
+// the cells the launch above left over: a fixed small grid walks the list (empty on ordinary images)
+__global__ void __launch_bounds__(32) k_fast_cells2_overflow(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
+{
+	extern __shared__ __align__(128) uint8_t fw_smem[];
+	const int n = *P.ovf_count;
+	if ((int)blockIdx.x >= n) return;
+	if (threadIdx.x == 0) mbar_init(reinterpret_cast<uint64_t*>(fw_smem + Y.off_bar), 1);
+	__syncwarp();
+	unsigned parity = 0;
+	for (int i = blockIdx.x; i < n; i += gridDim.x, parity ^= 1u)
+	{
+		const uint32_t e = P.ovf_list[i];
+		const int f = (int)(e / (uint32_t)P.cells_per_frame);
+		fast_cell<true>(P, maps, Y, fw_smem, (int)(e - (uint32_t)f * (uint32_t)P.cells_per_frame), f, parity);
+		__syncwarp();             // every lane is done with the tile before the next cell's load is issued
+	}
 }
 //@end

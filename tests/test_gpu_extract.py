@@ -165,6 +165,12 @@ def test_noise_images_overflow_the_cell_list(orbx, oracle_port, lo, hi):
         got = ex.debug_candidates(0, s)
         assert np.array_equal(got, want), f'FAST candidates differ at level {s}: {len(got)} vs {len(want)}'
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    # a throughput launch (more than 16 frames) runs the cell kernel with its short list and hands these cells to the overflow launch
+    kb, db = ex.ExtractBatch(np.stack([img, img[::-1].copy()] * 10))
+    ok2, od2 = oracle_port.extractor(1500).extract(img[::-1].copy())
+    for f in range(20):
+        wk, wd = (ok, od) if f % 2 == 0 else (ok2, od2)
+        assert kb[f].tobytes() == wk.tobytes() and np.array_equal(db[f], wd), f'frame {f} of the batch'
 
 
 def test_handle_survives_a_refused_size(orbx, oracle_final):
