@@ -629,7 +629,7 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 		const OrbxCellLayout Y = layout(FT_LIST_CAP);
 		k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 		const OrbxCellLayout Yf = layout(full);
-		k_fast_cells2_overflow<<<592, 32, Yf.warp_bytes, st>>>(P, maps, Yf);
+		k_fast_cells2_overflow<<<148, 32, Yf.warp_bytes, st>>>(P, maps, Yf);
 		return;
 	}
 	const OrbxCellLayout Y = layout(full);
