@@ -118,7 +118,7 @@ struct orbx_extractor
 	int pw = 0, ph = 0, frames_cap = 0;
 	OrbxPlanDev P;
 	OrbxTmaMaps maps;
-	OrbxStripMaps smaps[2];             // strip kernels (blur, dense FAST bound): every level with the strip box; [1]: the 8-row tiles of small batches
+	OrbxStripMaps smaps[3];             // strip kernels (blur, dense FAST bound): every level with the strip box; [1]: the 8-row tiles of small batches, [2]: the blur's 64-row tiles
 	OrbxPyrMaps pmaps[2];               // strip resize kernel: level s - 1 with the source box of a tile of level s
 	DevBuf<uint8_t> fmap_ini, fmap_min; // FAST bound bitmaps (1 bit per level pixel each)
 	const uint8_t* l0_map_base = nullptr;   // what the level-0 descriptors currently point at
@@ -230,6 +230,7 @@ orbx_status encode_level_maps(orbx_extractor* h, int s, const void* base, int64_
 		return ORBX_OK;
 	};
 	orbx_status st = enc(&h->maps.level[s], orbx_fast_tile_stride(), h->maps.box_h[s], "cell view");
+	if (st == ORBX_OK) st = enc(&h->smaps[2].level[s], orbx_strip_box_w(), orbx_strip_rows(2) + 6, "blur strip box");
 	for (int which = 0; which < 2 && st == ORBX_OK; which++)
 	{
 		st = enc(&h->smaps[which].level[s], orbx_strip_box_w(), orbx_strip_rows(which) + 6, "strip box");

@@ -453,7 +453,10 @@ static int env_int(const char* name, int dflt)
 int orbx_strip_rows(int which)
 {
 	static const int v = env_int("ORBX_STRIP_TH", 32) == 64 ? 64 : env_int("ORBX_STRIP_TH", 32) == 16 ? 16 : 32;
-	return which ? 8 : v;
+	// which = 2: the blur's throughput tiles. 64 rows: one tile header and one 6-row warm-up per 64 instead of per 32 rows (blur 0.254 ->
+	// 0.244 ms per 512 frames); the FAST bound is no faster with them (0.909 vs 0.903 ms: its tiles take 64 registers and 11 KB each)
+	static const int vb = env_int("ORBX_BLUR_TH", 64) == 32 ? 32 : 64;
+	return which == 1 ? 8 : which == 2 ? std::max(v, vb) : v;
 }
 int orbx_strip_box_w() { return ST_BW; }
 int orbx_pyramid_strip_rows(int which)
@@ -571,9 +574,9 @@ static OrbxStripTiles strip_tiles(const OrbxPlanDev& P, int th, bool fast)
 // one launch over the tiles of all levels: blur (mode 1) or dense FAST bound (mode 2). A fused form was measured: 110 registers, and both
 // halves are issue-bound by themselves (ncu: 85 % / 80 % issue), so one kernel doing both was slower than the two launches (1.25-1.29 vs
 // 0.98 + 0.25 ms per 512 frames).
-static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps smaps_both[2], int mode, cudaStream_t st)
+static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps smaps_both[3], int mode, cudaStream_t st)
 {
-	const int which = P.frames <= ORBX_SMALL_BATCH ? 1 : 0;
+	const int which = P.frames <= ORBX_SMALL_BATCH ? 1 : mode == 1 ? 2 : 0;
 	const OrbxStripMaps& smaps = smaps_both[which];
 	const int th = orbx_strip_rows(which);
 	const OrbxStripTiles T = strip_tiles(P, th, mode == 2);
@@ -636,7 +639,7 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st)
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st)
 {
 	// (Two cells per warp with one merged candidate list — 15 % fewer instructions per cell — was measured: 1.13 vs 0.96 ms per 512
 	// frames. The doubled shared memory per warp halves the resident warps, and this kernel lives on latency hiding.)
@@ -724,7 +727,7 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 	}
 }
 
-void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st)
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[3], cudaStream_t st)
 {
 	launch_strip(P, smaps, 1, st);
 }
@@ -738,8 +741,11 @@ void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d
 	}
 	else
 	{
-		// 16 keypoints per warp (8: 0.355 -> 0.351 ms per 512 frames; the per-group constants and the angle / cos / sin step amortise further)
-		static const int g = env_int("ORBX_DESC_G", 16);       // tuning knob: 8 or 16
+		// 16 keypoints per warp (8: 0.355 -> 0.351 ms per 512 frames; the per-group constants and the angle / cos / sin step amortise
+		// further) — except on 4K-class frames, whose patches come out of DRAM rather than L2: there the longer serial chain per warp
+		// costs more than it saves (0.645 -> 0.789 ms per 96 frames), so they keep 8
+		static const int g_env = env_int("ORBX_DESC_G", 0);    // tuning knob: 8 or 16
+		const int g = g_env ? g_env : ((int64_t)P.lv[0].w * P.lv[0].h > (1 << 21) ? 8 : 16);
 		if (g == 8)
 		{
 			dim3 grid((P.out_cap + 7) / 8, P.frames);

@@ -93,7 +93,8 @@ int orbx_fast_tile_rows();
 // level s - 1 with the source box of the resize tile that produces level s
 struct OrbxStripMaps { CUtensorMap level[ORBX_MAX_LEVELS]; };
 struct OrbxPyrMaps { CUtensorMap src[ORBX_MAX_LEVELS]; };
-// Tile rows of the strip kernels. which = 0: throughput tiles (ORBX_STRIP_TH / ORBX_PYR_TH, default 32); which = 1: the 8-row tiles used when
+// Tile rows of the strip kernels. which = 0: throughput tiles (ORBX_STRIP_TH / ORBX_PYR_TH, default 32); which = 2: the blur's throughput tiles
+// (default 64); which = 1: the 8-row tiles used when
 // a launch covers at most ORBX_SMALL_BATCH frames (Tracking extracts one frame at a time: more, shorter warps cut the launch's latency)
 #define ORBX_SMALL_BATCH 16
 int orbx_strip_rows(int which);
@@ -108,9 +109,9 @@ void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int 
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
 void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st);
 cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st);   // every level; one launch where the plan allows
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[2], cudaStream_t st);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st);
 void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
-void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[2], cudaStream_t st);
+void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[3], cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap, bool big);
