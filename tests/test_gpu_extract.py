@@ -248,7 +248,8 @@ def test_plan_rebuild_and_odd_batches(orbx, oracle_final):
     # one handle, changing image sizes and batch sizes (plan rebuild, chunk pipeline with a ragged last chunk)
     ex = orbx.ORBextractor(nfeatures=700)
     e = oracle_final.extractor(700)
-    for (w, h, frames) in ((640, 480, 3), (752, 480, 1), (640, 480, 70), (400, 300, 5), (640, 480, 2)):
+    # (320 x 240 and 1241 x 376 as throughput launches: levels lower than one 64-row blur tile, cells taller than 32 rows)
+    for (w, h, frames) in ((640, 480, 3), (752, 480, 1), (640, 480, 70), (400, 300, 5), (320, 240, 20), (1241, 376, 18), (640, 480, 2)):
         imgs = np.stack([synth.image(1000 + w + s, w, h) for s in range(min(frames, 6))])
         if frames > len(imgs):
             imgs = np.concatenate([imgs] * (frames // len(imgs) + 1))[:frames]
