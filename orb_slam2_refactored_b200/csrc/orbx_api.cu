@@ -462,8 +462,9 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 
 // enqueue the extraction of frames [fb, fb + fc) of the planned batch on stream st; level 0 of frame f is at
 // l0 + f*l0_stride. All per-frame buffers are indexed by frame, so a chunk is the same launch with offset bases.
+// paired: the call is one of the two lanes of a device-resident batch (see orbx_extract_batch_device) and takes that lane's stage order.
 orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, const uint8_t* l0, int64_t l0_pitch, int64_t l0_stride,
-                            orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap)
+                            orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap, bool paired = false)
 {
 	OrbxPlanDev& P0 = h->P;
 	P0.l0 = l0; P0.l0_pitch = l0_pitch; P0.l0_stride = l0_stride;
@@ -501,14 +502,32 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	const bool blur_inline = !(blur_side_env || (fc <= ORBX_SMALL_BATCH && !h->stage_timing));
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
+	// The two lanes of a batch are released by the same event, and which lane's first kernel the GPU takes first is then arbitrary (it
+	// differed from one B200 box to the next, and decided whether a stage order helped or hurt). Two memsets of a counter the lane owns
+	// put lane 1 a few microseconds behind lane 0, always. Tuning knob ORBX_LEAD: 0 = leave it to the hardware, 1 = lane 0 leads, 2 = lane 1.
+	static const int lead = getenv("ORBX_LEAD") ? atoi(getenv("ORBX_LEAD")) : 1;
+	if (paired && !ev && ((lead == 1 && lane == 1) || (lead == 2 && lane == 0)))
+		for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(P.ovf_count, 0, sizeof(int), st));
 	if (ev) CU(cudaEventRecord(ev[0], st));
 	CU(orbx_launch_pyramid_all(P, h->pmaps, st));
 	if (ev) CU(cudaEventRecord(ev[1], st));
+	// Where the in-line blur sits, one digit per lane (tuning knob ORBX_BLUR_POS): 0 = behind the pyramid, 1 = behind the dense FAST bound,
+	// 2 = behind the FAST cell kernel, 3 = behind the quadtree. Nothing but the descriptor stage reads the blurred levels. With "20" the
+	// leading lane runs pyramid, FAST, blur, quadtree and the other lane pyramid, blur, FAST, quadtree, so the lanes are never in the same
+	// stage at the same time: the blur (dot-product pipe) runs beside the dense FAST bound (ALU pipe), the quadtree (latency) beside either.
+	// 512 frames at C1, three B200 boxes: 2.058 -> 1.925 ms per step (248.8 k -> 266.0 k frames/s); tools/skew_probe.py has the grid.
+	static const char* blur_pos_env = getenv("ORBX_BLUR_POS");
+	const char* blur_pos_str = blur_pos_env && strlen(blur_pos_env) >= 2 ? blur_pos_env : "20";
+	int blur_pos = 0;
+	if (paired && blur_inline && !ev) blur_pos = std::max(0, std::min(3, blur_pos_str[lane] - '0'));
 	if (blur_inline)
 	{
-		if (ev) CU(cudaEventRecord(ev[6], st));
-		orbx_launch_blur(P, h->smaps, st);
-		if (ev) CU(cudaEventRecord(ev[7], st));
+		if (blur_pos == 0)
+		{
+			if (ev) CU(cudaEventRecord(ev[6], st));
+			orbx_launch_blur(P, h->smaps, st);
+			if (ev) CU(cudaEventRecord(ev[7], st));
+		}
 	}
 	else
 	{
@@ -522,11 +541,19 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 		CU(cudaEventRecord(h->side_join[lane], side));
 	}
 	if (ev) CU(cudaEventRecord(ev[2], st));
-	orbx_launch_fast(P, h->maps, h->smaps, st);
+	if (blur_pos == 1)
+	{
+		orbx_launch_fast(P, h->maps, h->smaps, st, 1);
+		orbx_launch_blur(P, h->smaps, st);
+		orbx_launch_fast(P, h->maps, h->smaps, st, 2);
+	}
+	else orbx_launch_fast(P, h->maps, h->smaps, st);
+	if (blur_pos == 2) orbx_launch_blur(P, h->smaps, st);
 	if (ev) CU(cudaEventRecord(ev[3], st));
 	if (ev) CU(cudaEventRecord(ev[4], st));
 	orbx_launch_quadtree(P, cell_off, st);
 	if (ev) CU(cudaEventRecord(ev[5], st));
+	if (blur_pos == 3) orbx_launch_blur(P, h->smaps, st);
 	if (!blur_inline) CU(cudaStreamWaitEvent(st, h->side_join[lane], 0));
 	if (ev) CU(cudaEventRecord(ev[8], st));
 	orbx_launch_describe(P, d_kps, d_desc, d_n, st);
@@ -779,8 +806,8 @@ orbx_status orbx_extract_batch_device(orbx_handle h, const uint8_t* d_images, in
 		else
 		{
 			const int half = (fc + 1) / 2;
-			st2 = enqueue_extract(h, fb, half, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
-			if (st2 == ORBX_OK && fc > half) st2 = enqueue_extract(h, fb + half, fc - half, h->stream2, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap);
+			st2 = enqueue_extract(h, fb, half, h->stream, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap, true);
+			if (st2 == ORBX_OK && fc > half) st2 = enqueue_extract(h, fb + half, fc - half, h->stream2, l0, l0_pitch, l0_stride, d_kps, d_desc, d_n, cap, true);
 		}
 	}
 	if (lanes == 2)

@@ -639,12 +639,12 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
 }
 
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st)
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st, int part)
 {
 	// (Two cells per warp with one merged candidate list — 15 % fewer instructions per cell — was measured: 1.13 vs 0.96 ms per 512
 	// frames. The doubled shared memory per warp halves the resident warps, and this kernel lives on latency hiding.)
-	launch_strip(P, smaps, 2, st);
-	launch_cells2(P, maps, st);
+	if (part != 2) launch_strip(P, smaps, 2, st);
+	if (part != 1) launch_cells2(P, maps, st);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }
