@@ -888,7 +888,7 @@ def main():
     ap.add_argument('--skip-stereo', action='store_true')
     ap.add_argument('--skip-configs', action='store_true', help='skip the C3 / C4 blocks')
     ap.add_argument('--c4-batch', type=int, default=96, help='4K frames per step per GPU (the quadtree is one CTA per frame and level: small batches leave SMs idle)')
-    ap.add_argument('--stereo-pairs', type=int, default=64)
+    ap.add_argument('--stereo-pairs', type=int, default=256, help='stereo pairs per step per GPU (C2 block)')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-guided', action='store_true')
     args = ap.parse_args()

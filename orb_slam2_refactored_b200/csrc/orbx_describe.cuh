@@ -136,12 +136,8 @@ __global__ void __launch_bounds__(32, 32) k_orient_describe2(const OrbxPlanDev P
 			}
 			m01 = (lane - ORBX_HALF_PATCH) * rowsum;
 		}
-#pragma unroll
-		for (int d = 16; d > 0; d >>= 1)
-		{
-			m10 += __shfl_xor_sync(0xffffffffu, m10, d);
-			m01 += __shfl_xor_sync(0xffffffffu, m01, d);
-		}
+		m10 = __reduce_add_sync(0xffffffffu, m10);          // REDUX: one instruction per sum instead of five shuffle + add steps
+		m01 = __reduce_add_sync(0xffffffffu, m01);
 		if (lane == k) { my01 = m01; my10 = m10; }
 		__syncwarp();                       // every lane is done with this buffer before the copies of keypoint k + 4 land in it
 		if (k + 4 < nk) stage_img(k + 4);

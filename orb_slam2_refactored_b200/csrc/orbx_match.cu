@@ -355,8 +355,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(const OrbxStereoArgs A)
 		}
 	}
 	any = __any_sync(0xffffffffu, any);
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) bestKey = min(bestKey, __shfl_xor_sync(0xffffffffu, bestKey, d));
+	bestKey = __reduce_min_sync(0xffffffffu, bestKey);          // one REDUX instead of five shuffle + min steps
 	const int bestDist = (int)(bestKey >> 16), bestR = (int)(bestKey & 0xffffu);
 
 	if (any && maxu >= 0.f && bestDist < TH_ORB)
@@ -389,8 +388,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(const OrbxStereoArgs A)
 #pragma unroll
 				for (int j = 0; j < 4; j++)
 					if (lane + 32 * j < 121) sum += abs(lv[j] - (int)__ldg(IR + ly[j] * pR + lx[j] + s) - sub);
-#pragma unroll
-				for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+				sum = __reduce_add_sync(0xffffffffu, sum);
 				dist[s] = sum;
 				if (sum < bestSad) { bestSad = sum; bestDx = s - SR; }
 			}

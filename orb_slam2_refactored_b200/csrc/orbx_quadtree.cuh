@@ -160,12 +160,9 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 		const int q = quadrant_of(src[i], xm, ym);
 		c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
 	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1)
-	{
-		c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-		c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
-	}
+	// one REDUX per counter instead of five shuffle + add steps (the divide of a node is a dependent chain: latency counts here)
+	c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+	c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
 	if (lane == 0) { s_bigc[warp][0] = c0; s_bigc[warp][1] = c1; s_bigc[warp][2] = c2; s_bigc[warp][3] = c3; }
 	__syncthreads();
 	int tot[4], run[4];
@@ -465,12 +462,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 				const int q = quadrant_of(src[i], xm, ym);
 				c0 += q == 0; c1 += q == 1; c2 += q == 2; c3 += q == 3;
 			}
-#pragma unroll
-			for (int d = 16; d > 0; d >>= 1)
-			{
-				c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-				c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
-			}
+			// one REDUX per counter instead of five shuffle + add steps (the divide of a node is a dependent chain: latency counts here)
+			c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+			c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
 			int a0 = 0, a1 = c0, a2 = c0 + c1, a3 = c0 + c1 + c2;
 			for (int i0 = 0; i0 < cnt; i0 += 128)
 			{
