@@ -820,6 +820,19 @@ def run_b200(args, rank, world, local_rank, emit):
             lex.ExtractBatch(one)
         latency = {'workload': 'C1, one frame per call through ORBextractor.ExtractBatch (pinned host frame in, host keypoints + descriptors out)',
                    'ms_per_call': (time.perf_counter() - t0l) / 100 * 1e3}
+        # the same call at the C ABI with the caller's arrays allocated once, as a C++ host makes it (no numpy allocation / slicing per call)
+        lcap = lex.max_keypoints()
+        lk = np.empty((1, lcap, 28), np.uint8); ld = np.empty((1, lcap, 32), np.uint8); ln = np.zeros(1, np.int32)
+        largs = (lex._h, C.c_void_p(one.ctypes.data), 1, W, H, W, W * H, C.c_void_p(lk.ctypes.data), C.c_void_p(ld.ctypes.data), lcap, C.c_void_p(ln.ctypes.data))
+        fn = api.lib().orbx_extract_batch
+        for _ in range(10):
+            api._check(fn(*largs))
+        t0l = time.perf_counter()
+        for _ in range(200):
+            fn(*largs)
+        latency['ms_per_call_c_abi'] = (time.perf_counter() - t0l) / 200 * 1e3
+        latency['note'] = ('ms_per_call: through the Python mirror (allocates and slices the result arrays per call); ms_per_call_c_abi: orbx_extract_batch with '
+                           'preallocated caller arrays. The call runs the levels as three groups (level 0 / 1-2 / 3-7) on parallel streams, replayed as one CUDA graph')
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores
     cpu = None

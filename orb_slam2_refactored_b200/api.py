@@ -210,6 +210,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _addr(a):
+    """Same as _p for a numpy array the caller keeps alive, without building the .ctypes helper object (the one-frame call path)."""
+    return C.c_void_p(a.__array_interface__['data'][0])
+
+
 def device_count():
     return lib().orbx_device_count()
 
@@ -283,12 +288,13 @@ class ORBextractor:
             raise OrbxError(ORBX_ERR_INVALID, 'CV_Assert(image.type() == CV_8U): expected (F, H, W) uint8')   # :457
         F, H, W = images.shape
         cap = lib().orbx_max_keypoints(self._h)
-        kps = np.zeros((F, cap), KP_DTYPE)
-        desc = np.zeros((F, cap, 32), np.uint8)
+        # rows past n[f] are never returned, so the arrays need no zero fill; a call owns its arrays, so the results are views of them
+        kps = np.empty((F, cap), KP_DTYPE)
+        desc = np.empty((F, cap, 32), np.uint8)
         n = np.zeros(F, np.int32)
-        _check(lib().orbx_extract_batch(self._h, _p(images), F, W, H, images.strides[1], images.strides[0], _p(kps), _p(desc), cap, _p(n)))
+        _check(lib().orbx_extract_batch(self._h, _addr(images), F, W, H, images.strides[1], images.strides[0], _addr(kps), _addr(desc), cap, _addr(n)))
         self._last_frames = F
-        return [kps[f, :n[f]].copy() for f in range(F)], [desc[f, :n[f]].copy() for f in range(F)]
+        return [kps[f, :n[f]] for f in range(F)], [desc[f, :n[f]] for f in range(F)]
 
     def ExtractBatchColor(self, images, RGB=True):
         """images: (F, H, W, 3|4) uint8. ConvertToGray (src/System.cc:122-137) fused into the upload, then Extract."""

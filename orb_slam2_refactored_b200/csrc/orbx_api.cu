@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -111,6 +112,9 @@ struct orbx_extractor
 	cudaEvent_t fork = nullptr, join = nullptr;   // order the second lane inside the handle's stream for the device-resident API
 	cudaStream_t side[2] = { nullptr, nullptr };  // per lane: the blur runs here, beside the quadtree (latency-bound, leaves the SMs half empty)
 	cudaEvent_t side_fork[2] = { nullptr, nullptr }, side_join[2] = { nullptr, nullptr };
+	// a frame at a time (latency path): the levels run as three groups on their own streams, see enqueue_extract
+	cudaStream_t grp[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+	cudaEvent_t grp_ev[2][4] = { { nullptr, nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr, nullptr } };   // pyramid of group B done, pyramid done, group B done, group C done
 	std::vector<float> scale, inv_scale, sigma_sq, inv_sigma_sq;
 	std::vector<int> quota;
 
@@ -143,6 +147,13 @@ struct orbx_extractor
 	DevBuf<int32_t> out_n;
 	int32_t* h_counts = nullptr;        // pinned staging for the per-frame counts (a pageable target would serialise the pipeline)
 	size_t h_counts_n = 0;
+	// a frame at a time through the host-buffer API: the grouped launches + the three result copies of enqueue_extract as ONE graph launch.
+	// Every pointer in it is the handle's own (level-0 buffer, result buffers, pinned staging); the key holds what it was captured with.
+	struct SmallKey { uint64_t gen; const void* l0; const void* kps; const void* desc; const void* n; const void* hs; const void* counts; int frames, ocap; };
+	SmallKey small_key = {};
+	cudaGraphExec_t small_exec = nullptr;
+	unsigned long long* trace = nullptr;   // ORBX_TRACE=1: 16 device slots of %globaltimer stamps along a one-frame call (debug)
+	uint64_t gen = 0;                   // bumped whenever a tensor map is (re-)encoded or the plan is rebuilt
 	uint8_t* h_small = nullptr;         // pinned staging for the keypoints + descriptors of a small batch (a frame at a time): three queued copies and
 	size_t h_small_bytes = 0;           // one synchronisation instead of two blocking copies into the caller's pageable arrays
 	DevBuf<float> st_uright, st_depth;
@@ -217,6 +228,7 @@ orbx_status encode_level_maps(orbx_extractor* h, int s, const void* base, int64_
 		return (EncodeFn)p;
 	}();
 	if (!fn) return fail(ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+	h->gen++;
 	const OrbxPlanDev& P = h->P;
 	const OrbxLevel& L = P.lv[s];
 	const cuuint64_t dims[3] = { (cuuint64_t)dimx, (cuuint64_t)L.h, (cuuint64_t)frames };
@@ -502,6 +514,59 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	const bool blur_inline = !(blur_side_env || (fc <= ORBX_SMALL_BATCH && !h->stage_timing));
 	const int lane = st == h->stream2 ? 1 : 0;
 	cudaStream_t side = blur_inline ? st : h->side[lane];
+	// ---- a frame at a time: what the caller waits for is the longest dependent chain, and that chain is level 0's (most candidates, the
+	// longest quadtree CTA). Level 0 needs nothing but the input, so FAST and the quadtree of level 0 start at once on the caller's stream
+	// while the pyramid is still being built; levels 1-2 and levels 3.. follow as two more groups on their own streams as soon as their part
+	// of the pyramid exists, the blur runs beside them, and the descriptor stage joins everything. Three chains of about equal length
+	// instead of pyramid -> FAST -> quadtree of all levels in a row. Tuning knob ORBX_GROUPS=0: the single chain.
+	static const bool groups_on = !(getenv("ORBX_GROUPS") && atoi(getenv("ORBX_GROUPS")) == 0);
+	if (groups_on && !blur_inline && !ev && P.nlevels >= 4)
+	{
+		const int n = P.nlevels, sB = 1, sC = 3;
+		cudaStream_t gB = h->grp[lane][0], gC = h->grp[lane][1];
+		cudaEvent_t* ge = h->grp_ev[lane];
+		static const bool trace_on = getenv("ORBX_TRACE") != nullptr;
+		auto stamp = [&](int slot, cudaStream_t s_) { if (trace_on && h->trace) orbx_launch_stamp(h->trace + slot, s_); };
+		stamp(0, st);
+		CU(cudaEventRecord(h->side_fork[lane], st));                     // the input (and whatever the caller queued before) is in place
+		// group B: levels 1-2
+		CU(cudaStreamWaitEvent(gB, h->side_fork[lane], 0));
+		CU(orbx_launch_pyramid_all(P, h->pmaps, gB, sB, sC));
+		stamp(1, gB);
+		CU(cudaEventRecord(ge[0], gB));
+		// group A: level 0
+		orbx_launch_fast(P, h->maps, h->smaps, st, 0, 0, 1);
+		stamp(2, st);
+		orbx_launch_quadtree(P, cell_off, st, 0, 1);
+		stamp(3, st);
+		// group C: levels 3 ..
+		CU(cudaStreamWaitEvent(gC, ge[0], 0));
+		CU(orbx_launch_pyramid_all(P, h->pmaps, gC, sC, n));
+		stamp(4, gC);
+		CU(cudaEventRecord(ge[1], gC));
+		orbx_launch_fast(P, h->maps, h->smaps, gB, 0, sB, sC);
+		stamp(5, gB);
+		orbx_launch_quadtree(P, cell_off, gB, sB, sC);
+		stamp(6, gB);
+		CU(cudaEventRecord(ge[2], gB));
+		orbx_launch_fast(P, h->maps, h->smaps, gC, 0, sC, n);
+		stamp(7, gC);
+		orbx_launch_quadtree(P, cell_off, gC, sC, n);
+		stamp(8, gC);
+		CU(cudaEventRecord(ge[3], gC));
+		// blur of all levels beside the groups
+		CU(cudaStreamWaitEvent(side, ge[1], 0));
+		orbx_launch_blur(P, h->smaps, side);
+		stamp(9, side);
+		CU(cudaEventRecord(h->side_join[lane], side));
+		CU(cudaStreamWaitEvent(st, ge[2], 0));
+		CU(cudaStreamWaitEvent(st, ge[3], 0));
+		CU(cudaStreamWaitEvent(st, h->side_join[lane], 0));
+		orbx_launch_describe(P, d_kps, d_desc, d_n, st);
+		stamp(10, st);
+		CU(cudaGetLastError());
+		return ORBX_OK;
+	}
 	// The two lanes of a batch are released by the same event, and which lane's first kernel the GPU takes first is then arbitrary (it
 	// differed from one B200 box to the next, and decided whether a stage order helped or hurt). Two memsets of a counter the lane owns
 	// put lane 1 a few microseconds behind lane 0, always. Tuning knob ORBX_LEAD: 0 = leave it to the hardware, 1 = lane 0 leads, 2 = lane 1.
@@ -615,7 +680,13 @@ orbx_status orbx_create(const orbx_params* params, int device, orbx_handle* out)
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side[l], cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side_fork[l], cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side_join[l], cudaEventDisableTiming);
+		for (int g = 0; g < 2; g++)
+			if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->grp[l][g], cudaStreamNonBlocking);
+		for (int g = 0; g < 4; g++)
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->grp_ev[l][g], cudaEventDisableTiming);
 	}
+	if (e == cudaSuccess && getenv("ORBX_TRACE")) e = cudaMalloc(&h->trace, 16 * sizeof(unsigned long long));
+	if (e == cudaSuccess && h->trace) e = cudaMemset(h->trace, 0, 16 * sizeof(unsigned long long));
 	if (e == cudaSuccess) e = orbx_upload_pattern();
 	if (e == cudaSuccess) e = orbx_kernels_init();
 	if (e != cudaSuccess)
@@ -641,6 +712,8 @@ orbx_status orbx_destroy(orbx_handle h)
 	h->out_kps.release(); h->out_desc.release(); h->out_n.release();
 	h->st_uright.release(); h->st_depth.release(); h->st_sad.release(); h->st_rows.release(); h->st_items.release();
 	if (h->h_counts) cudaFreeHost(h->h_counts);
+	if (h->small_exec) cudaGraphExecDestroy(h->small_exec);
+	if (h->trace) cudaFree(h->trace);
 	if (h->h_small) cudaFreeHost(h->h_small);
 	for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
 	if (h->done) cudaEventDestroy(h->done);
@@ -655,6 +728,10 @@ orbx_status orbx_destroy(orbx_handle h)
 		if (h->side[l]) { cudaStreamSynchronize(h->side[l]); cudaStreamDestroy(h->side[l]); }
 		if (h->side_fork[l]) cudaEventDestroy(h->side_fork[l]);
 		if (h->side_join[l]) cudaEventDestroy(h->side_join[l]);
+		for (int g = 0; g < 2; g++)
+			if (h->grp[l][g]) { cudaStreamSynchronize(h->grp[l][g]); cudaStreamDestroy(h->grp[l][g]); }
+		for (int g = 0; g < 4; g++)
+			if (h->grp_ev[l][g]) cudaEventDestroy(h->grp_ev[l][g]);
 	}
 	delete h;
 	return ORBX_OK;
@@ -824,6 +901,7 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
                                       bool rectify = false)
 {
 	if (!h || !images || !n) return fail(ORBX_ERR_INVALID, "null argument");
+	timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
 	// rectify: width x height is the RAW frame; Extract runs on the rectified image, whose size is the table's
 	const int raw_w = width, raw_h = height;
 	if (rectify)
@@ -936,6 +1014,36 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 		st = lane_st;
 		// (Replaying the ~12 launches of a one-frame call as a CUDA graph was measured: 0.212 vs 0.203 ms per call — the call is bound by the
 		// GPU's dependent chain (quadtree 54 us, 7 pyramid levels 33 us), not by launch overhead, which the host hides behind it.)
+		// A frame at a time: the grouped launches of enqueue_extract (three level groups + blur on four streams, ~26 API calls) and the three
+		// result copies are captured once per plan and replayed as one graph launch; every pointer in them is the handle's own. (For the
+		// single chain of round 1 a graph bought nothing: the GPU's dependent chain was longer than the host's launch sequence. With the
+		// chain cut into parallel groups the host became the limit.) Tuning knob ORBX_GRAPH=0: plain launches.
+		static const bool graph_on = !(getenv("ORBX_GRAPH") && atoi(getenv("ORBX_GRAPH")) == 0) && !(getenv("ORBX_GROUPS") && atoi(getenv("ORBX_GROUPS")) == 0);
+		if (staged && graph_on && !h->stage_timing && h->P.nlevels >= 4)
+		{
+			const orbx_extractor::SmallKey key = { h->gen, h->l0base, h->out_kps.p, h->out_desc.p, h->out_n.p, h->h_small, counts, frames, ocap };
+			if (!h->small_exec || std::memcmp(&key, &h->small_key, sizeof(key)) != 0)
+			{
+				if (h->small_exec) { cudaGraphExecDestroy(h->small_exec); h->small_exec = nullptr; }
+				cudaGraph_t g = nullptr;
+				CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+				orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
+				cudaError_t ce = cudaSuccess;
+				if (e == ORBX_OK) ce = cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st);
+				if (e == ORBX_OK && ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_small, h->out_kps.p, sizeof(orbx_keypoint) * (size_t)ocap * frames, cudaMemcpyDeviceToHost, st);
+				if (e == ORBX_OK && ce == cudaSuccess)
+					ce = cudaMemcpyAsync(h->h_small + sizeof(orbx_keypoint) * (size_t)ocap * frames, h->out_desc.p, (size_t)32 * ocap * frames, cudaMemcpyDeviceToHost, st);
+				const cudaError_t ee = cudaStreamEndCapture(st, &g);          // always: the stream must leave capture mode
+				if (e != ORBX_OK) { if (g) cudaGraphDestroy(g); return e; }
+				if (ce != cudaSuccess || ee != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return fail(ORBX_ERR_CUDA, "capturing the one-frame graph failed"); }
+				ce = cudaGraphInstantiate(&h->small_exec, g, 0);
+				cudaGraphDestroy(g);
+				if (ce != cudaSuccess) { h->small_exec = nullptr; return fail(ORBX_ERR_CUDA, cudaGetErrorString(ce)); }
+				h->small_key = key;
+			}
+			CU(cudaGraphLaunch(h->small_exec, st));
+			continue;
+		}
 		orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
 		if (e != ORBX_OK) return e;
 		CU(cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st));
@@ -953,8 +1061,25 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 			                     (size_t)32 * ccap, fc, cudaMemcpyDeviceToHost, st));
 		}
 	}
+	static const bool trace_on = getenv("ORBX_TRACE") != nullptr;
+	timespec ts1; if (trace_on) clock_gettime(CLOCK_MONOTONIC, &ts1);
 	CU(cudaStreamSynchronize(h->stream));
 	if (two_streams) CU(cudaStreamSynchronize(h->stream2));
+	if (trace_on && h->trace)
+	{
+		timespec ts2; clock_gettime(CLOCK_MONOTONIC, &ts2);
+		static int calls = 0;
+		if (++calls % 64 == 0)
+		{
+			unsigned long long t[16];
+			cudaMemcpy(t, h->trace, sizeof(t), cudaMemcpyDeviceToHost);
+			const char* names[11] = { "start", "pyrB", "fastA", "qtA", "pyrC", "fastB", "qtB", "fastC", "qtC", "blur", "describe" };
+			fprintf(stderr, "[trace us] enqueue %.1f sync-wait %.1f |", (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3,
+			        (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3);
+			for (int i = 1; i < 11; i++) fprintf(stderr, " %s %.1f", names[i], ((double)t[i] - (double)t[0]) * 1e-3);
+			fprintf(stderr, "\n");
+		}
+	}
 	note_result(h, frames, ocap, h->out_kps.p, h->out_desc.p, h->out_n.p);
 	int need = 0;
 	for (int f = 0; f < frames; f++) { n[f] = counts[f]; need = std::max(need, counts[f]); }

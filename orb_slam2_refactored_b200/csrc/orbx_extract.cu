@@ -425,6 +425,15 @@ cudaError_t orbx_upload_pattern()
 	return cudaSuccess;
 }
 
+// debug: one thread writes %globaltimer into a slot (ORBX_TRACE=1, tools/latency_trace.py): a timeline of the streams of a one-frame call
+__global__ void k_stamp(unsigned long long* slot)
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	*slot = t;
+}
+void orbx_launch_stamp(unsigned long long* slot, cudaStream_t st) { k_stamp<<<1, 1, 0, st>>>(slot); }
+
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st)
 {
 	k_debug_cos_sin<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first_bits, n, d_cos, d_sin);
@@ -514,8 +523,12 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int l
 	else k_pyramid_resize<PY_RW><<<grid, 256, P.lv[level].py_smem, st>>>(P, level);
 }
 
-cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st)
+// levels [s0, s1) (s0 >= 1; s1 <= 0: up to the last level)
+cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st, int s0, int s1)
 {
+	if (s1 <= 0 || s1 > P.nlevels) s1 = P.nlevels;
+	s0 = std::max(s0, 1);
+	if (s0 >= s1) return cudaSuccess;
 	// One launch for a frame at a time (C1: 0.201 -> 0.193 ms per Extract call). For batches it was measured both ways: the pyramid stage
 	// alone gains 3 % (0.309 -> 0.300 ms per 512 frames), but the step as callers run it — two half-batches on two streams — loses 2 %
 	// (256.0 k -> 251.3 k frames/s): seven short launches per lane interleave better with the other lane's kernels than one long one.
@@ -525,7 +538,7 @@ cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmap
 	for (int s = 1; s < P.nlevels && ok; s++) ok = P.lv[s].py_bw[which] > 0;
 	if (!ok)
 	{
-		for (int s = 1; s < P.nlevels; s++) orbx_launch_pyramid(P, pmaps, s, st);
+		for (int s = s0; s < s1; s++) orbx_launch_pyramid(P, pmaps, s, st);
 		return cudaSuccess;
 	}
 	const int th = orbx_pyramid_strip_rows(which);
@@ -540,9 +553,15 @@ cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmap
 		smem = std::max(smem, ((D.py_bw[which] * D.py_bh[which] + 127) & ~127) + 16);
 	}
 	for (int s = P.nlevels; s < ORBX_MAX_LEVELS; s++) T.base[s + 1] = T.base[s];
-	const cudaError_t e = cudaMemsetAsync(P.pyr_done + (int64_t)P.frame0 * ORBX_MAX_LEVELS, 0, sizeof(int) * ORBX_MAX_LEVELS * (size_t)P.frames, st);
-	if (e != cudaSuccess) return e;
-	const unsigned grid = (unsigned)T.base[P.nlevels] * (unsigned)P.frames;
+	// the completion counts are reset by the launch that starts the pyramid; a later launch over the next levels finds its source level's
+	// count complete (stream order)
+	if (s0 == 1)
+	{
+		const cudaError_t e = cudaMemsetAsync(P.pyr_done + (int64_t)P.frame0 * ORBX_MAX_LEVELS, 0, sizeof(int) * ORBX_MAX_LEVELS * (size_t)P.frames, st);
+		if (e != cudaSuccess) return e;
+	}
+	T.first = T.base[s0];
+	const unsigned grid = (unsigned)(T.base[s1] - T.base[s0]) * (unsigned)P.frames;
 	if (th == 8) k_pyramid_all<8><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
 	else if (th == 16) k_pyramid_all<16><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
 	else k_pyramid_all<32><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
@@ -574,13 +593,17 @@ static OrbxStripTiles strip_tiles(const OrbxPlanDev& P, int th, bool fast)
 // one launch over the tiles of all levels: blur (mode 1) or dense FAST bound (mode 2). A fused form was measured: 110 registers, and both
 // halves are issue-bound by themselves (ncu: 85 % / 80 % issue), so one kernel doing both was slower than the two launches (1.25-1.29 vs
 // 0.98 + 0.25 ms per 512 frames).
-static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps smaps_both[3], int mode, cudaStream_t st)
+static void launch_strip(const OrbxPlanDev& P, const OrbxStripMaps smaps_both[3], int mode, cudaStream_t st, int s0 = 0, int s1 = 0)
 {
+	if (s1 <= 0 || s1 > P.nlevels) s1 = P.nlevels;
+	if (s0 >= s1) return;
 	const int which = P.frames <= ORBX_SMALL_BATCH ? 1 : mode == 1 ? 2 : 0;
 	const OrbxStripMaps& smaps = smaps_both[which];
 	const int th = orbx_strip_rows(which);
-	const OrbxStripTiles T = strip_tiles(P, th, mode == 2);
-	dim3 grid(T.base[P.nlevels], P.frames);
+	OrbxStripTiles T = strip_tiles(P, th, mode == 2);
+	T.first = T.base[s0];
+	dim3 grid(T.base[s1] - T.base[s0], P.frames);
+	if (grid.x == 0) return;
 	const int smem = st_tile_bytes(th) + 16;
 #define ORBX_STRIP_CASE(TH_)                                                                                      \
 	if (mode == 1) k_level_strip<TH_, true, false><<<grid, 32, smem, st>>>(P, smaps, T);                           \
@@ -604,8 +627,12 @@ static void cell_extents(const OrbxPlanDev& P, const OrbxTmaMaps& maps, int& row
 	}
 }
 
-static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st)
+static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStream_t st, int s0 = 0, int s1 = 0)
 {
+	if (s1 <= 0 || s1 > P.nlevels) s1 = P.nlevels;
+	if (s0 >= s1) return;
+	const int cell0 = P.lv[s0].cell_base, cell1 = s1 < P.nlevels ? P.lv[s1].cell_base : P.cells_per_frame;
+	if (cell1 <= cell0) return;
 	int rows, maxrw, maxrh;
 	cell_extents(P, maps, rows, maxrw, maxrh);
 	// tile | score (1 px zero border) | list of pixels to score | survivor bitmap | mbarrier
@@ -622,7 +649,7 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 		return Y;
 	};
 	const int full = maxrw * maxrh;
-	dim3 grid(P.cells_per_frame, P.frames);
+	dim3 grid(cell1 - cell0, P.frames);
 	// Throughput launches run with the short list (32 instead of 26 resident warps) and leave the rare cell that flags more pixels to a
 	// second, tiny launch; a frame at a time keeps the full list and the single launch (the GPU is far from full there).
 	static const int short_list = env_int("ORBX_SHORT_LIST", 1);      // tuning knob
@@ -630,21 +657,21 @@ static void launch_cells2(const OrbxPlanDev& P, const OrbxTmaMaps& maps, cudaStr
 	{
 		cudaMemsetAsync(P.ovf_count, 0, sizeof(int), st);
 		const OrbxCellLayout Y = layout(FT_LIST_CAP);
-		k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
+		k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y, cell0);
 		const OrbxCellLayout Yf = layout(full);
 		k_fast_cells2_overflow<<<148, 32, Yf.warp_bytes, st>>>(P, maps, Yf);
 		return;
 	}
 	const OrbxCellLayout Y = layout(full);
-	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y);
+	k_fast_cells2<<<grid, 32, Y.warp_bytes, st>>>(P, maps, Y, cell0);
 }
 
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st, int part)
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st, int part, int s0, int s1)
 {
 	// (Two cells per warp with one merged candidate list — 15 % fewer instructions per cell — was measured: 1.13 vs 0.96 ms per 512
 	// frames. The doubled shared memory per warp halves the resident warps, and this kernel lives on latency hiding.)
-	if (part != 2) launch_strip(P, smaps, 2, st);
-	if (part != 1) launch_cells2(P, maps, st);
+	if (part != 2) launch_strip(P, smaps, 2, st, s0, s1);
+	if (part != 1) launch_cells2(P, maps, st, s0, s1);
 }
 
 int orbx_pyramid_tile_rows() { return PY_TH; }
@@ -661,10 +688,12 @@ size_t orbx_quadtree_smem(int node_cap, bool big)
 	return big ? base + 4 * (((size_t)node_cap / 2 + 2) & ~(size_t)1) + 2 * 12 * ((size_t)node_cap / 16 + 4) + 16 : base;
 }
 
-void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
+void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st, int s0, int s1)
 {
+	if (s1 <= 0 || s1 > P.nlevels) s1 = P.nlevels;
+	if (s0 >= s1) return;
 	const size_t smem = orbx_quadtree_smem(P.node_cap, true), smem_plain = orbx_quadtree_smem(P.node_cap, false);
-	dim3 grid(P.frames, P.nlevels);
+	dim3 grid(P.frames, s1 - s0);
 	// Two variants: BIG replays std::sort with the whole CTA and partitions large nodes block-wide. It costs registers (61 vs 40),
 	// so it pays where one CTA's latency is what the launch waits for: levels that keep more than ~1000 keypoints (4K plans), and
 	// small batches (a frame at a time, as Tracking calls Extract), where the GPU is far from full anyway.
@@ -684,13 +713,20 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		// 256-thread CTA has warps (one Extract call 0.329 -> 0.317 ms; at 1000 keypoints per frame no difference)
 		static const int small_threads_env = getenv("ORBX_QT_SMALL_THREADS") ? atoi(getenv("ORBX_QT_SMALL_THREADS")) : 0;   // tuning knob: 256 or 512
 		const int small_threads = small_threads_env ? small_threads_env : (P.node_cap > 320 ? 512 : 256);
+		// a frame at a time: room for the level's candidates (both ping-pong segments) in shared memory, see the kernel. 6144 per segment
+		// hold level 0 of a VGA or KITTI frame of ordinary texture; a level with more stays in global memory. Tuning knob ORBX_QT_SMEM_CAND.
+		static const int smem_cand_env = getenv("ORBX_QT_SMEM_CAND") ? atoi(getenv("ORBX_QT_SMEM_CAND")) : 6144;
+		int smem_cand = small_batch ? std::max(0, smem_cand_env) & ~3 : 0;
+		while (smem_cand > 0 && smem + 16 + 8 * (size_t)smem_cand > QT_SMEM_MAX) smem_cand /= 2;
+		smem_cand &= ~3;
+		const size_t smem_all = smem + (smem_cand ? 16 + 8 * (size_t)smem_cand : 0);
 		if ((large_plan && !small_batch && big_threads == 512) || (small_batch && small_threads == 512))
 		{
-			qt512::k_quadtree<true><<<grid, 512, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+			qt512::k_quadtree<true><<<grid, 512, smem_all, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr, s0, smem_cand);
 		}
 		else
 		{
-			qt256::k_quadtree<true><<<grid, 256, smem, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr);
+			qt256::k_quadtree<true><<<grid, 256, smem_all, st>>>(P, cell_off, small_batch ? 1024 : 2048, small_batch ? 48 : 512, want_dbg ? dbg : nullptr, s0, smem_cand);
 		}
 	}
 	else
@@ -707,15 +743,15 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st)
 		const int small_threads = small_env ? small_env : (P.frames >= 512 ? 96 : P.frames >= 128 ? 128 : 256);
 		if (small_threads == 256)
 		{
-			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
 		}
 		else if (small_threads == 96)
 		{
-			qt96::k_quadtree<false><<<grid, 96, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+			qt96::k_quadtree<false><<<grid, 96, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
 		}
 		else
 		{
-			qt128::k_quadtree<false><<<grid, 128, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr);
+			qt128::k_quadtree<false><<<grid, 128, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
 		}
 	}
 	if (want_dbg)

@@ -108,11 +108,13 @@ void orbx_launch_gray(const uint8_t* src, int64_t spitch, int64_t sstride, int c
 void orbx_launch_remap(const uint8_t* src, int64_t spitch, int64_t sstride, int sw, int sh, const int2* tab, uint8_t* dst, int64_t dpitch,
                        int64_t dstride, int w, int h, int frames, cudaStream_t st);   // tab[y*w + x] = (ix & 0xffff | iy << 16, fx | fy << 5)
 void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int level, cudaStream_t st);
-cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st);   // every level; one launch where the plan allows
-void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st, int part = 0);   // part: 0 both kernels, 1 dense bound, 2 cells
-void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st);   // cell_off: scratch, [frames][cells_per_frame]
+// levels [s0, s1) of every frame, one launch where the plan allows; the launchers below take level ranges too (s1 <= 0: up to the last level)
+cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], cudaStream_t st, int s0 = 1, int s1 = 0);
+void orbx_launch_fast(const OrbxPlanDev& P, const OrbxTmaMaps& maps, const OrbxStripMaps smaps[3], cudaStream_t st, int part = 0, int s0 = 0, int s1 = 0);   // part: 0 both kernels, 1 dense bound, 2 cells
+void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st, int s0 = 0, int s1 = 0);   // cell_off: scratch, [frames][cells_per_frame]
 void orbx_launch_blur(const OrbxPlanDev& P, const OrbxStripMaps smaps[3], cudaStream_t st);
 void orbx_launch_describe(const OrbxPlanDev& P, orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, cudaStream_t st);
+void orbx_launch_stamp(unsigned long long* slot, cudaStream_t st);
 void orbx_launch_debug_cos_sin(uint32_t first_bits, int64_t n, float* d_cos, float* d_sin, cudaStream_t st);
 size_t orbx_quadtree_smem(int node_cap, bool big);
 int orbx_pyramid_tile_rows();

@@ -216,7 +216,7 @@ __device__ __noinline__ void qt_divide_big(const QNode nd, uint32_t* buf0, uint3
 // BIG selects the variant with the CTA-parallel sort and big-node partition (4K-class levels); the plain variant keeps the
 // register count at 40 for VGA-class levels, where occupancy matters more than the serial tails.
 template <bool BIG>
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off, const int big_node_min, const int par_sort_min, unsigned long long* dbg)
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, int* __restrict__ cell_off, const int big_node_min, const int par_sort_min, unsigned long long* dbg, const int lvl0, const int smem_cand)
 {
 	int dbgk = 0;
 #define QT_STAMP() do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && dbgk < 63) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[1 + dbgk++] = t_; dbg[0] = dbgk; } } while (0)
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	__shared__ int s_rc[QT_WARPS][ORBX_MAX_ROOTS];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int lvl = blockIdx.y, f = blockIdx.x;      // x = frame: all level-0 CTAs (the longest) are scheduled first
+	const int lvl = (int)blockIdx.y + lvl0, f = blockIdx.x;      // lvl0: first level of the launch's level range      // x = frame: all level-0 CTAs (the longest) are scheduled first
 	const OrbxLevel& L = P.lv[lvl];
 	const int ncell = L.ncx * L.ncy;
 	const int* __restrict__ ccount = P.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
@@ -255,6 +255,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 	const int n = block_exscan(ncell, s_w, [&](int i) { return ccount[i]; }, [&](int i, int off) { coff[i] = off; });
 	if (tid == 0) P.cand_count[(int64_t)f * P.nlevels + lvl] = n;
 	__syncthreads();
+	// A frame at a time, the launch waits for its slowest CTA, and every pass of a CTA is a chain of dependent reads and writes of the
+	// candidate segments. When the level's candidates fit the space the launcher reserved behind the node lists, both ping-pong buffers
+	// live in shared memory instead of global memory (L2): n is uniform, so is the choice.
+	if (n <= smem_cand)
+	{
+		buf0 = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(gone + M) + 15) & ~(uintptr_t)15);
+		buf1 = buf0 + smem_cand;
+	}
 	const int nroots = L.n_roots;
 	uint32_t* gathered = (nroots == 1) ? buf0 : buf1;
 	// 8 lanes per cell (a cell holds ~15 candidates): four cells per warp in flight, so the chain of dependent loads

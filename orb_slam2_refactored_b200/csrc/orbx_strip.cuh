@@ -18,7 +18,7 @@
 
 // one = 1, a value the compiler cannot fold (see FastRowOps); (xorg, yorg) = origin of the tile grid: (0, 0) for the blur, the 16-byte
 // aligned column / the first row of the cells' interiors for the FAST bound, whose tiles then cover only what DetectFAST looks at
-struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int one, xorg, yorg; };
+struct OrbxStripTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int one, xorg, yorg; int first; };   // first: tile index of blockIdx.x = 0 (launches over a level range)
 
 __host__ __device__ constexpr int st_tile_bytes(int th) { return ((ST_BW * (th + 2 * ST_HALO) + 127) / 128) * 128; }
 
@@ -198,11 +198,12 @@ __global__ void __launch_bounds__(32) k_level_strip(const OrbxPlanDev P, const _
 	const int lane = threadIdx.x, f = blockIdx.y;
 
 	// which level does this tile belong to (unrolled: every index into T is a compile-time constant)
+	const int gtile = (int)blockIdx.x + T.first;
 	int level = 0, base = 0, tx = T.tx[0];
 #pragma unroll
 	for (int s = 1; s < ORBX_MAX_LEVELS; s++)
-		if ((int)blockIdx.x >= T.base[s] && T.base[s + 1] > T.base[s]) { level = s; base = T.base[s]; tx = T.tx[s]; }
-	const int tile = (int)blockIdx.x - base;
+		if (gtile >= T.base[s] && T.base[s + 1] > T.base[s]) { level = s; base = T.base[s]; tx = T.tx[s]; }
+	const int tile = gtile - base;
 	const int tile_y = tile / tx, tile_x = tile - tile_y * tx;
 	const OrbxLevel& L = P.lv[level];
 	const int w = L.w, h = L.h;
@@ -398,12 +399,12 @@ __global__ void __launch_bounds__(32) k_pyramid_strip(const OrbxPlanDev P, const
 // blockIdx order, so the producers of a tile are resident or finished before the tile starts: with 512 frames the count is there long
 // before it is needed, and for one frame the whole grid is resident at once. Seven dependent launches (and their tails: the three
 // smallest levels took 11 us each for 4 us of work) become one; a one-frame call saves six launch latencies.
-struct OrbxPyrTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int which; };   // base[s]: tiles per frame of the levels before s (base[1] = 0)
+struct OrbxPyrTiles { int base[ORBX_MAX_LEVELS + 1]; int tx[ORBX_MAX_LEVELS]; int which; int first; };   // first: tiles per frame of the levels before this launch's first level   // base[s]: tiles per frame of the levels before s (base[1] = 0)
 template <int TH>
 __global__ void __launch_bounds__(32) k_pyramid_all(const OrbxPlanDev P, const __grid_constant__ OrbxPyrMaps maps, const OrbxPyrTiles T, int* __restrict__ done)
 {
 	extern __shared__ __align__(128) uint8_t py_smem[];
-	const unsigned id = blockIdx.x, F = (unsigned)P.frames;
+	const unsigned F = (unsigned)P.frames, id = blockIdx.x + (unsigned)T.first * F;
 	int level = 1;
 #pragma unroll
 	for (int s = 2; s < ORBX_MAX_LEVELS; s++)
@@ -640,10 +641,10 @@ __device__ __forceinline__ void fast_cell(const OrbxPlanDev& P, const OrbxTmaMap
 		P.cell_count[(int64_t)f * P.cells_per_frame + cell] = total;
 }
 
-__global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y)
+__global__ void __launch_bounds__(32) k_fast_cells2(const OrbxPlanDev P, const __grid_constant__ OrbxTmaMaps maps, const OrbxCellLayout Y, const int cell0)
 {
 	extern __shared__ __align__(128) uint8_t fw_smem[];
-	fast_cell<false>(P, maps, Y, fw_smem, blockIdx.x, blockIdx.y, 0u);
+	fast_cell<false>(P, maps, Y, fw_smem, (int)blockIdx.x + cell0, blockIdx.y, 0u);      // cell0: first cell of the launch's level range
 }
 
 // the cells the launch above left over: a fixed small grid walks the list (empty on ordinary images)

@@ -306,3 +306,38 @@ def test_parameter_sweep(orbx, oracle_port, w, h, nf, scale, nlevels, ini, mn):
     for a, b in zip(ex.GetImagePyramid(), e.pyramid()):
         assert np.array_equal(a, b)
     assert np.array_equal(ex.GetFeatureQuotas(), oracle_port.quotas(nf, scale, nlevels))
+
+
+def test_one_frame_graph_replay_between_other_calls(orbx, oracle_final):
+    # A frame at a time through the host-buffer API replays a captured graph of the grouped launches (levels 0 / 1-2 / 3.. on parallel
+    # streams). The replay must follow whatever else the handle did in between: other images, a small batch (another graph), a
+    # device-resident batch that reads the caller's buffer in place (level-0 tensor maps re-encoded), a throughput batch, a re-plan.
+    import torch
+    c = synth.CONFIGS['C1']
+    imgs = [synth.image(40 + s, c['w'], c['h']) for s in range(5)]
+    small = synth.image(77, 400, 300)
+    ex = orbx.ORBextractor(nfeatures=c['nfeatures'])
+    e = oracle_final.extractor(c['nfeatures'])
+    ref = [e.extract(im) for im in imgs]
+    ref_small = e.extract(small)
+
+    def check(got, want, what):
+        assert got[0].tobytes() == want[0].tobytes() and np.array_equal(got[1], want[1]), what
+    for rnd in range(2):
+        for i in (0, 1, 0, 2):
+            check(ex.Extract(imgs[i]), ref[i], ('one frame', rnd, i))
+        k, d = ex.ExtractBatch(np.stack([imgs[3], imgs[4], imgs[1]]))
+        for j, i in enumerate((3, 4, 1)):
+            check((k[j], d[j]), ref[i], ('batch of three', rnd, i))
+        check(ex.Extract(imgs[2]), ref[2], ('after the small batch', rnd))
+        dv = torch.from_numpy(np.stack([imgs[(s + rnd) % 5] for s in range(20)])).cuda()
+        kk, dd, nn = ex.extract_batch_device(dv)
+        ex.synchronize()
+        n0 = int(nn[3].item())
+        assert kk[3, :n0].cpu().numpy().tobytes() == ref[(3 + rnd) % 5][0].tobytes(), ('device batch', rnd)
+        check(ex.Extract(imgs[4]), ref[4], ('after the device-resident batch', rnd))
+        k, d = ex.ExtractBatch(np.stack([imgs[s % 5] for s in range(70)]))
+        check((k[66], d[66]), ref[1], ('throughput batch', rnd))
+        check(ex.Extract(imgs[0]), ref[0], ('after the throughput batch', rnd))
+        check(ex.Extract(small), ref_small, ('re-plan', rnd))
+        check(ex.Extract(imgs[1]), ref[1], ('after the re-plan', rnd))
