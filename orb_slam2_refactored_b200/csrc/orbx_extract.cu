@@ -471,7 +471,8 @@ int orbx_strip_box_w() { return ST_BW; }
 int orbx_pyramid_strip_rows(int which)
 {
 	static const int v = env_int("ORBX_PYR_TH", 32) == 16 ? 16 : 32;
-	return which ? 8 : v;
+	static const int vs = env_int("ORBX_PYR_TH_SMALL", 8) == 4 ? 4 : 8;     // tile rows of one-frame launches
+	return which ? vs : v;
 }
 
 #define QT_SMEM_MAX (200 * 1024)
@@ -487,7 +488,8 @@ cudaError_t orbx_kernels_init()
 	set(k_pyramid_strip<32>, 100 * 1024);
 	set(k_pyramid_strip<16>, 100 * 1024);
 	set(k_pyramid_strip<8>, 100 * 1024);
-	set(k_pyramid_all<32>, 100 * 1024); set(k_pyramid_all<16>, 100 * 1024); set(k_pyramid_all<8>, 100 * 1024);
+	set(k_pyramid_all<32>, 100 * 1024); set(k_pyramid_all<16>, 100 * 1024); set(k_pyramid_all<8>, 100 * 1024); set(k_pyramid_all<4>, 100 * 1024);
+	set(k_pyramid_strip<4>, 100 * 1024);
 	set(k_fast_cells2, 64 * 1024); set(k_fast_cells2_overflow, 64 * 1024);
 	set(k_level_strip<8, true, false>, 64 * 1024); set(k_level_strip<8, false, true>, 64 * 1024);
 	set(k_level_strip<16, true, false>, 64 * 1024); set(k_level_strip<16, false, true>, 64 * 1024);
@@ -510,7 +512,8 @@ void orbx_launch_pyramid(const OrbxPlanDev& P, const OrbxPyrMaps pmaps[2], int l
 		const int th = orbx_pyramid_strip_rows(which), bw = D.py_bw[which], bh = D.py_bh[which];
 		dim3 grid((D.w + ST_TW - 1) / ST_TW, (D.h + th - 1) / th, P.frames);
 		const int smem = ((bw * bh + 127) & ~127) + 16;
-		if (th == 8) k_pyramid_strip<8><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
+		if (th == 4) k_pyramid_strip<4><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
+		else if (th == 8) k_pyramid_strip<8><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
 		else if (th == 16) k_pyramid_strip<16><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
 		else k_pyramid_strip<32><<<grid, 32, smem, st>>>(P, pmaps[which], level, bw, bh);
 		return;
@@ -562,7 +565,8 @@ cudaError_t orbx_launch_pyramid_all(const OrbxPlanDev& P, const OrbxPyrMaps pmap
 	}
 	T.first = T.base[s0];
 	const unsigned grid = (unsigned)(T.base[s1] - T.base[s0]) * (unsigned)P.frames;
-	if (th == 8) k_pyramid_all<8><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
+	if (th == 4) k_pyramid_all<4><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
+	else if (th == 8) k_pyramid_all<8><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
 	else if (th == 16) k_pyramid_all<16><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
 	else k_pyramid_all<32><<<grid, 32, smem, st>>>(P, pmaps[which], T, P.pyr_done);
 	return cudaSuccess;
