@@ -90,9 +90,9 @@ __device__ __forceinline__ int block_exscan(int n, int* s_w, Get get, Put put)
 // Time is ~2n serial steps (n + n/2 + n/4 ...) instead of ~1.4 n log2 n.
 struct QSeg { int first, last, depth; };
 
-__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, ushort2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */)
+__device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int segcap, ushort2* leaf, int* s_cnt /* [3]: nseg[2], nleaf */, uint16_t* rs /* [n] scratch */)
 {
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	if (tid == 0)
 	{
 		int lg = 0;
@@ -112,17 +112,22 @@ __device__ __noinline__ void qs_sort_block(uint64_t* a, int n, QSeg* segq, int s
 		__syncthreads();
 		QSeg* in = segq + cur * segcap;
 		QSeg* out = segq + (cur ^ 1) * segcap;
-		for (int si = tid; si < ns; si += QT_THREADS)
+		// one WARP per pending range: the partition step itself is parallel (qs_partition_warp), so the first rounds, where one or two long
+		// ranges are all there is, no longer run at the pace of a single thread
+		for (int si = warp; si < ns; si += QT_WARPS)
 		{
 			const QSeg sg = in[si];
-			if (sg.depth == 0) { qs_heapsort(a, sg.first, sg.last); continue; }     // fully sorted, no insertion pass needed
-			const int cut = qs_partition(a, sg.first, sg.last);
-#pragma unroll
-			for (int side = 0; side < 2; side++)
+			if (sg.depth == 0) { if (lane == 0) qs_heapsort(a, sg.first, sg.last); __syncwarp(); continue; }     // fully sorted, no insertion pass needed
+			const int cut = qs_partition_warp(a, sg.first, sg.last, rs);
+			if (lane == 0)
 			{
-				const int f0 = side ? cut : sg.first, l0 = side ? sg.last : cut;
-				if (l0 - f0 > 16) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = { f0, l0, sg.depth - 1 };
-				else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_ushort2((unsigned short)f0, (unsigned short)l0);
+#pragma unroll
+				for (int side = 0; side < 2; side++)
+				{
+					const int f0 = side ? cut : sg.first, l0 = side ? sg.last : cut;
+					if (l0 - f0 > 16) out[atomicAdd(&s_cnt[cur ^ 1], 1)] = { f0, l0, sg.depth - 1 };
+					else if (l0 - f0 > 1) leaf[atomicAdd(&s_cnt[2], 1)] = make_ushort2((unsigned short)f0, (unsigned short)l0);
+				}
 			}
 		}
 		__syncthreads();
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
 			__syncthreads();
 			if (BIG && np > par_sort_min)
-				qs_sort_block(items, np, segq, segcap, leaf, s_sort);      // large levels (4K): ~2n serial steps instead of ~1.4 n log2 n
+				qs_sort_block(items, np, segq, segcap, leaf, s_sort, reinterpret_cast<uint16_t*>(proc));      // proc / pbase are written only after the sort
 			else
 			{
 				if (tid == 0) qs_sort_serial(items, np);

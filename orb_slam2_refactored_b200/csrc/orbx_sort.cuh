@@ -106,6 +106,74 @@ __device__ inline int qs_partition(uint64_t* a, int first, int last)
 	return lo;
 }
 
+// The same partition step by a whole warp, with the same result (array contents and cut). The serial loop swaps the k-th element from the
+// left that is not before the pivot (a "left stopper") with the k-th element from the right that the pivot is not before (a "right
+// stopper") for as long as the former lies left of the latter. Both scans only ever read positions no swap has touched yet (a swap writes
+// at or below lo and at or above hi), so the stoppers can be taken from the array as it is BEFORE the first swap: with Ls ascending and Rs
+// descending over the original array, the swaps are (Ls[k], Rs[k]) for k < m, m = #{k : Ls[k] < Rs[k]}, and the cut is min(Ls[m], Rs[m - 1])
+// (the scan for the (m+1)-th left stopper also stops at the element the last swap moved to Rs[m - 1]). rs: scratch for Rs, one 16-bit entry
+// per element of the range (positions < 65536), indexed from `first` (ranges of concurrent calls are disjoint). All 32 lanes call it.
+__device__ __forceinline__ int qs_partition_warp(uint64_t* a, int first, int last, uint16_t* rs)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	if (lane == 0)
+	{
+		const int mid = first + (last - first) / 2;
+		const int r = first, x = first + 1, y = mid, z = last - 1;
+		if (qs_before(a[x], a[y]))
+		{
+			if (qs_before(a[y], a[z])) qs_swap(a, r, y);
+			else if (qs_before(a[x], a[z])) qs_swap(a, r, z);
+			else qs_swap(a, r, x);
+		}
+		else if (qs_before(a[x], a[z])) qs_swap(a, r, x);
+		else if (qs_before(a[y], a[z])) qs_swap(a, r, z);
+		else qs_swap(a, r, y);
+	}
+	__syncwarp();
+	const uint32_t p = (uint32_t)(a[first] >> 32);
+	// right stoppers, descending: positions j in [first, last) with !before(pivot, a[j]) <=> size(a[j]) >= p; j = first (the pivot) is the last one
+	int cntR = 0;
+	for (int base = last - 1; base >= first; base -= 32)
+	{
+		const int j = base - lane;
+		const bool f = j >= first && (uint32_t)(a[j] >> 32) >= p;
+		const unsigned b = __ballot_sync(0xffffffffu, f);
+		if (f) rs[first + cntR + __popc(b & lt)] = (uint16_t)j;
+		cntR += __popc(b);
+	}
+	__syncwarp();
+	// left stoppers, ascending: positions i in (first, last) with !before(a[i], pivot) <=> size(a[i]) <= p
+	int cntL = 0, cut = -1, lastR = 0x7fffffff;
+	for (int base = first + 1; base < last; base += 32)
+	{
+		const int i = base + lane;
+		const uint64_t v = i < last ? a[i] : 0ull;
+		const bool f = i < last && (uint32_t)(v >> 32) <= p;
+		const unsigned b = __ballot_sync(0xffffffffu, f);
+		const int k = cntL + __popc(b & lt);
+		const int r = (f && k < cntR) ? (int)rs[first + k] : -1;
+		const bool sw = f && i < r;
+		uint64_t vr = 0ull;
+		if (sw) vr = a[r];
+		const unsigned bs = __ballot_sync(0xffffffffu, sw);      // also orders every read above before the writes below
+		if (sw) { a[i] = vr; a[r] = v; }
+		// the swaps form a prefix of the left stoppers: the first stopper that does not swap ends the loop
+		const unsigned fail = b & ~bs;
+		if (bs) lastR = (int)rs[first + cntL + __popc(bs) - 1];
+		if (fail)
+		{
+			const int src = __ffs(fail) - 1;
+			cut = min(__shfl_sync(0xffffffffu, i, src), lastR);
+			break;
+		}
+		cntL += __popc(b);
+	}
+	__syncwarp();
+	return cut >= 0 ? cut : lastR;
+}
+
 // std::sort by one thread: __introsort_loop with an explicit stack, then __final_insertion_sort. Used for small inputs,
 // where the rounds of the block-parallel version below cost more barriers than they save.
 __device__ __noinline__ inline void qs_sort_serial(uint64_t* a, int n)
