@@ -742,20 +742,22 @@ void orbx_launch_quadtree(const OrbxPlanDev& P, int* cell_off, cudaStream_t st, 
 		// per SM where 128 threads get 12 (quadtree stage 0.268 -> 0.255 ms per 512 frames; at 256 frames per launch 128 threads are as
 		// fast or faster: 0.203 vs 0.221 ms at the EuRoC shape).
 		static const int small_env = getenv("ORBX_QT_SMALL") ? atoi(getenv("ORBX_QT_SMALL")) : 0;   // tuning knob: 96, 128 or 256
+		// sort replays of more items than this run CTA-parallel (warp-parallel partition steps) in the plain variant too. Tuning knob.
+		static const int plain_sort_min = getenv("ORBX_QT_PLAIN_SORT") ? atoi(getenv("ORBX_QT_PLAIN_SORT")) : 40;
 		// As one lane of a two-lane batch (what callers get), 128 threads already pay from 128 frames per launch: C1 256-frame batches
 		// 1.078 -> 1.034 ms, C3 1.276 -> 1.242 ms; lanes of 64 frames stay faster with 256 threads (tools/skew_probe.py).
 		const int small_threads = small_env ? small_env : (P.frames >= 512 ? 96 : P.frames >= 128 ? 128 : 256);
 		if (small_threads == 256)
 		{
-			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
+			qt256::k_quadtree<false><<<grid, 256, smem_plain, st>>>(P, cell_off, 1 << 30, plain_sort_min, want_dbg ? dbg : nullptr, s0, 0);
 		}
 		else if (small_threads == 96)
 		{
-			qt96::k_quadtree<false><<<grid, 96, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
+			qt96::k_quadtree<false><<<grid, 96, smem_plain, st>>>(P, cell_off, 1 << 30, plain_sort_min, want_dbg ? dbg : nullptr, s0, 0);
 		}
 		else
 		{
-			qt128::k_quadtree<false><<<grid, 128, smem_plain, st>>>(P, cell_off, 1 << 30, 1 << 30, want_dbg ? dbg : nullptr, s0, 0);
+			qt128::k_quadtree<false><<<grid, 128, smem_plain, st>>>(P, cell_off, 1 << 30, plain_sort_min, want_dbg ? dbg : nullptr, s0, 0);
 		}
 	}
 	if (want_dbg)

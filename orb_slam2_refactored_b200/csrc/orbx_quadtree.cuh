@@ -433,8 +433,19 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			np = block_ordered(lastP, s_w, [&](int g) { return QN_CNT(cur[lastP - 1 - g]) > 1; },
 			                   [&](int g, int rank) { const int pos = lastP - 1 - g; items[rank] = ((uint64_t)QN_CNT(cur[pos]) << 32) | (uint32_t)pos; });
 			__syncthreads();
+			// proc and pbase (8 M bytes, contiguous) are written only after the sort: the plain variant, which reserves no work lists for the
+			// CTA-parallel sort, borrows them: stopper scratch (2 M bytes), leaf ranges (2 M + 8), the two range queues (1.5 M + 96)
+			const int segcap_p = M / 16 + 4;
+			const size_t off_leaf = ((size_t)2 * M + 3) & ~(size_t)3, off_seg = (off_leaf + 4 * ((size_t)M / 2 + 2) + 15) & ~(size_t)15;
+			const bool fits = (size_t)8 * M >= off_seg + (size_t)2 * segcap_p * sizeof(QSeg);
 			if (BIG && np > par_sort_min)
-				qs_sort_block(items, np, segq, segcap, leaf, s_sort, reinterpret_cast<uint16_t*>(proc));      // proc / pbase are written only after the sort
+				qs_sort_block(items, np, segq, segcap, leaf, s_sort, reinterpret_cast<uint16_t*>(proc));
+			else if (!BIG && fits && np > par_sort_min)
+			{
+				uint8_t* sc = reinterpret_cast<uint8_t*>(proc);
+				qs_sort_block(items, np, reinterpret_cast<QSeg*>(sc + off_seg), segcap_p, reinterpret_cast<ushort2*>(sc + off_leaf), s_sort,
+				              reinterpret_cast<uint16_t*>(sc));
+			}
 			else
 			{
 				if (tid == 0) qs_sort_serial(items, np);
