@@ -522,7 +522,9 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	static const bool groups_on = !(getenv("ORBX_GROUPS") && atoi(getenv("ORBX_GROUPS")) == 0);
 	if (groups_on && !blur_inline && !ev && P.nlevels >= 4)
 	{
-		const int n = P.nlevels, sB = 1, sC = 3;
+		// first level of the third group (tuning knob ORBX_GROUP_C, 2 .. nlevels - 1)
+		static const int group_c = getenv("ORBX_GROUP_C") ? atoi(getenv("ORBX_GROUP_C")) : 3;
+		const int n = P.nlevels, sB = 1, sC = std::max(2, std::min(n - 1, group_c));
 		cudaStream_t gB = h->grp[lane][0], gC = h->grp[lane][1];
 		cudaEvent_t* ge = h->grp_ev[lane];
 		static const bool trace_on = getenv("ORBX_TRACE") != nullptr;
