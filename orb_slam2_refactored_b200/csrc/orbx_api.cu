@@ -475,8 +475,9 @@ orbx_status build_plan(orbx_extractor* h, int w, int hgt, int frames)
 // enqueue the extraction of frames [fb, fb + fc) of the planned batch on stream st; level 0 of frame f is at
 // l0 + f*l0_stride. All per-frame buffers are indexed by frame, so a chunk is the same launch with offset bases.
 // paired: the call is one of the two lanes of a device-resident batch (see orbx_extract_batch_device) and takes that lane's stage order.
+// grouped: a small batch whose launches are being captured into a graph: the levels run as three groups on parallel streams (below).
 orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, const uint8_t* l0, int64_t l0_pitch, int64_t l0_stride,
-                            orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap, bool paired = false)
+                            orbx_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, int cap, bool paired = false, bool grouped = false)
 {
 	OrbxPlanDev& P0 = h->P;
 	P0.l0 = l0; P0.l0_pitch = l0_pitch; P0.l0_stride = l0_stride;
@@ -518,9 +519,11 @@ orbx_status enqueue_extract(orbx_extractor* h, int fb, int fc, cudaStream_t st, 
 	// longest quadtree CTA). Level 0 needs nothing but the input, so FAST and the quadtree of level 0 start at once on the caller's stream
 	// while the pyramid is still being built; levels 1-2 and levels 3.. follow as two more groups on their own streams as soon as their part
 	// of the pyramid exists, the blur runs beside them, and the descriptor stage joins everything. Three chains of about equal length
-	// instead of pyramid -> FAST -> quadtree of all levels in a row. Tuning knob ORBX_GROUPS=0: the single chain.
+	// instead of pyramid -> FAST -> quadtree of all levels in a row. Tuning knob ORBX_GROUPS=0: the single chain. Only where the launches are
+	// replayed as a graph (the host-buffer API): issued call by call the 14 launches and 10 event operations are host-bound and slower than
+	// the single chain (0.188 vs 0.173 ms per call), so orbx_extract_batch_device keeps the chain for small batches.
 	static const bool groups_on = !(getenv("ORBX_GROUPS") && atoi(getenv("ORBX_GROUPS")) == 0);
-	if (groups_on && !blur_inline && !ev && P.nlevels >= 4)
+	if (groups_on && grouped && !blur_inline && !ev && P.nlevels >= 4)
 	{
 		// first level of the third group (tuning knob ORBX_GROUP_C, 2 .. nlevels - 1)
 		static const int group_c = getenv("ORBX_GROUP_C") ? atoi(getenv("ORBX_GROUP_C")) : 3;
@@ -1029,7 +1032,7 @@ static orbx_status extract_batch_impl(orbx_handle h, const uint8_t* images, int 
 				if (h->small_exec) { cudaGraphExecDestroy(h->small_exec); h->small_exec = nullptr; }
 				cudaGraph_t g = nullptr;
 				CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-				orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap);
+				orbx_status e = enqueue_extract(h, fb, fc, st, h->l0base, h->l0_pitch, h->l0_stride, h->out_kps.p, h->out_desc.p, h->out_n.p, ocap, false, true);
 				cudaError_t ce = cudaSuccess;
 				if (e == ORBX_OK) ce = cudaMemcpyAsync(counts + fb, h->out_n.p + fb, sizeof(int32_t) * fc, cudaMemcpyDeviceToHost, st);
 				if (e == ORBX_OK && ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_small, h->out_kps.p, sizeof(orbx_keypoint) * (size_t)ocap * frames, cudaMemcpyDeviceToHost, st);
