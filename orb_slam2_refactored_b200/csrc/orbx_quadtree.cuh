@@ -477,6 +477,27 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const OrbxPlanDev P, in
 			const uint32_t* src = (QN_BUF(nd) ? buf1 : buf0) + nd.beg;
 			uint32_t* dst = (QN_BUF(nd) ? buf0 : buf1) + nd.beg;
 			const int xm = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), ym = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);   // ceil(0.5*d), :408-409
+			if (cnt <= 32)
+			{
+				// most nodes of the later passes: one chunk. One load serves the counts (ballots) and the scatter, instead of a counting
+				// trip and a scattering trip through the candidates (two dependent L2 round trips where they live in global memory)
+				const bool ok = lane < cnt;
+				const uint32_t v = ok ? src[lane] : 0u;
+				const int q = ok ? quadrant_of(v, xm, ym) : -1;
+				const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+				const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+				const unsigned lt = lanemask_lt();
+				const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2);
+				if (q == 0) dst[__popc(b0 & lt)] = v;
+				else if (q == 1) dst[n0 + __popc(b1 & lt)] = v;
+				else if (q == 2) dst[n0 + n1 + __popc(b2 & lt)] = v;
+				else if (q == 3) dst[n0 + n1 + n2 + __popc(b3 & lt)] = v;
+				if (lane == 0)
+				{
+					childcnt[4 * t + 0] = n0; childcnt[4 * t + 1] = n1; childcnt[4 * t + 2] = n2; childcnt[4 * t + 3] = __popc(b3);
+				}
+				continue;
+			}
 			// The candidates sit in global memory (L2): one chunk per trip costs a full L2 round trip. The count loop keeps per-lane
 			// counters (no ballot between its loads, so they overlap); the scatter loop loads four chunks before it touches them.
 			int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
